@@ -1,0 +1,220 @@
+/*
+ * collision_b200.h — C ABI of the B200-native batched collision pipeline.
+ *
+ * This is the drop-in boundary for ONE hot path of rustgd/collision-rs 0.20.1:
+ * the 3-D narrow phase GJK3 (+EPA3) and the SweepAndPrune3 broad phase.  The
+ * reference has no FFI of its own (it is safe, generic Rust); each entry point
+ * below replaces one generic method specialised to
+ *     S = f32, P = Point3<f32>, T = Decomposed<Vector3<f32>, Quaternion<f32>>,
+ *     shapes in {Sphere, Cuboid, ConvexPolyhedron(VertexOnly)} (a subset of Primitive3<f32>)
+ * and batched (one record per pair instead of one call per pair).
+ * Citations are relative to the reference tree (src/...).
+ *
+ * Everything is plain C: POD structs, raw pointers, sizes.  No torch types.
+ * All functions return 0 on success and a negative cb2_error on failure;
+ * cb2_last_error(ctx) gives a human readable message.  There is NO CPU
+ * fallback: without a CUDA device cb2_create fails with CB2_ERR_NO_DEVICE.
+ */
+#ifndef COLLISION_B200_H
+#define COLLISION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB2_ABI_VERSION 1u
+
+/* ---- error codes (function return values) -------------------------------- */
+typedef enum cb2_error {
+    CB2_OK = 0,
+    CB2_ERR_NO_DEVICE = -1,    /* no CUDA device / cudaSetDevice failed          */
+    CB2_ERR_CUDA = -2,         /* a CUDA runtime call failed (see last_error)    */
+    CB2_ERR_ARG = -3,          /* null pointer, bad enum, index out of range     */
+    CB2_ERR_NOSPC = -4,        /* pairs_out too small; *n_pairs = required count */
+    CB2_ERR_UNSUPPORTED = -5,  /* e.g. max_iterations above CB2_MAX_ITERATIONS   */
+    CB2_ERR_NAN = -6           /* SAP input contains NaN (reference order is
+                                  unspecified for NaN keys, sweep_prune.rs:87-97) */
+} cb2_error;
+
+/* ---- per-pair status byte -------------------------------------------------
+ * The reference returns Option<..> or panics.  A batch cannot panic per pair,
+ * so every narrow-phase output record carries one status byte:              */
+typedef enum cb2_status {
+    CB2_NONE = 0,               /* Option::None                                  */
+    CB2_SOME = 1,               /* Option::Some(record)                          */
+    CB2_PANIC_UNWRAP_PLANE = 2, /* Plane::from_points(..).unwrap() on a degenerate
+                                   face, gjk/simplex/simplex3d.rs:146            */
+    CB2_PANIC_ASSERT_RANGE = 3, /* assert!(in_range(u) && ..), simplex3d.rs:150  */
+    CB2_PANIC_INV_SCALE = 4,    /* inverse_transform_vector(..).unwrap() with
+                                   scale ~ 0, primitive/util.rs:18, sphere.rs:36,
+                                   polyhedron.rs:394                             */
+    CB2_NONCONVERGED = 5,       /* time-of-impact loop hit iter_cap; the reference
+                                   loop (gjk/mod.rs:204) has no cap and would hang */
+    CB2_PANIC_EPA_EMPTY = 6     /* Polytope::closest_face_to_origin indexes
+                                   faces[0] of an empty Vec, epa/epa3d.rs:138    */
+} cb2_status;
+
+/* ---- CollisionStrategy (contact.rs:16-22); discriminants in declaration order */
+typedef enum cb2_strategy {
+    CB2_FULL_RESOLUTION = 0,
+    CB2_COLLISION_ONLY = 1
+} cb2_strategy;
+
+/* ---- shape kinds: the Primitive3 variants on the path (primitive3.rs:20-40) */
+typedef enum cb2_shape_kind {
+    CB2_SPHERE = 0,     /* p[0] = radius                        (sphere.rs:14-24)   */
+    CB2_CUBOID = 1,     /* p[0..3] = dim (full extents)         (cuboid.rs:18-42)   */
+    CB2_POLYHEDRON = 2  /* vertices [vtx_off, vtx_off+vtx_cnt), VertexOnly mode
+                           (polyhedron.rs:100-122)                                   */
+} cb2_shape_kind;
+
+/* One entry of the shape table (24 B). */
+typedef struct cb2_shape {
+    uint32_t kind;      /* cb2_shape_kind */
+    float p[3];
+    uint32_t vtx_off;   /* first vertex in the vertex table (polyhedra only) */
+    uint32_t vtx_cnt;
+} cb2_shape;
+
+/* cgmath Decomposed<Vector3<f32>, Quaternion<f32>> flattened (32 B):
+ * transform_point(p) = rot * (p * scale) + disp. Quaternion is (s; x,y,z).   */
+typedef struct cb2_xform {
+    float scale;
+    float qs, qx, qy, qz;
+    float dx, dy, dz;
+} cb2_xform;
+
+/* Contact<Point3<f32>> (contact.rs:30-46), 36 B. */
+typedef struct cb2_contact {
+    uint32_t strategy;  /* cb2_strategy */
+    float normal[3];
+    float penetration_depth;
+    float contact_point[3];
+    float time_of_impact;
+} cb2_contact;
+
+/* GJK::new_with_settings arguments (gjk/mod.rs:71-84). Defaults: gjk/mod.rs:22-24,
+ * epa/mod.rs:15-16 => {1e-6, 1e-6, 1e-5, 100}.                                */
+typedef struct cb2_settings {
+    float distance_tolerance;
+    float continuous_tolerance;
+    float epa_tolerance;
+    uint32_t max_iterations;
+} cb2_settings;
+
+/* Largest max_iterations the device kernels accept (EPA polytope scratch is
+ * sized for it: <= 3+max_iterations vertices, <= 2*(3+max_iterations)-4 faces). */
+#define CB2_MAX_ITERATIONS 100u
+
+/* Aabb3<f32> (volume/aabb/aabb3.rs:20-25): min.xyz, max.xyz (24 B). */
+typedef struct cb2_aabb3 {
+    float min[3];
+    float max[3];
+} cb2_aabb3;
+
+typedef struct cb2_ctx cb2_ctx;
+
+/* ---- context ---------------------------------------------------------------- */
+uint32_t cb2_abi_version(void);
+void cb2_default_settings(cb2_settings* out);         /* GJK::new(), gjk/mod.rs:60-68 */
+int cb2_create(int device, cb2_ctx** out);            /* one ctx per GPU / host thread */
+void cb2_destroy(cb2_ctx* ctx);
+const char* cb2_last_error(const cb2_ctx* ctx);       /* ctx may be NULL: create errors */
+int cb2_device_sm_count(const cb2_ctx* ctx);
+/* Number of this library's kernels launched through ctx since creation. */
+uint64_t cb2_kernel_launches(const cb2_ctx* ctx);
+
+/* ---- shape table -------------------------------------------------------------
+ * Replaces constructing Sphere::new / Cuboid::new / ConvexPolyhedron::new values
+ * (sphere.rs:20-24, cuboid.rs:29-42, polyhedron.rs:100-122).  verts_xyz is
+ * n_verts x 3 floats.  Host pointers; copied to the device.                      */
+int cb2_shapes_upload(cb2_ctx* ctx, const cb2_shape* shapes, uint32_t n_shapes,
+                      const float* verts_xyz, uint64_t n_verts);
+
+/* ---- narrow phase, HOST buffers (H2D, kernels, D2H inside the call) -----------
+ * out / status hold n records; out[i] is valid only where status[i] == CB2_SOME.
+ *
+ * cb2_gjk3_intersection  replaces GJK3::intersection      (gjk/mod.rs:362-391)
+ * cb2_gjk3_distance      replaces GJK3::distance          (gjk/mod.rs:271-321)
+ * cb2_gjk3_time_of_impact replaces GJK3::intersection_time_of_impact (gjk/mod.rs:163-256);
+ *   l_t0..l_t1 is the Range<&TL> start..end, likewise r_t0..r_t1; iter_cap bounds
+ *   the reference's uncapped while loop (0 => default 1024).                     */
+int cb2_gjk3_intersection(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                          const uint32_t* l_shape, const uint32_t* r_shape,
+                          const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                          cb2_contact* out, uint8_t* status);
+int cb2_gjk3_distance(cb2_ctx* ctx, const cb2_settings* settings,
+                      const uint32_t* l_shape, const uint32_t* r_shape,
+                      const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                      float* out, uint8_t* status);
+int cb2_gjk3_time_of_impact(cb2_ctx* ctx, const cb2_settings* settings,
+                            const uint32_t* l_shape, const uint32_t* r_shape,
+                            const cb2_xform* l_t0, const cb2_xform* l_t1,
+                            const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
+                            uint32_t iter_cap, cb2_contact* out, uint8_t* status);
+
+/* ---- narrow phase, DEVICE buffers (all pointers are device pointers; the work
+ * is enqueued on `stream` (a cudaStream_t, may be NULL) and NOT synchronised).
+ * With pair_body != NULL the transforms are per BODY and pair i uses bodies
+ * pair_body[2i], pair_body[2i+1] (shape = body_shape[..], xform = body_t[..]):
+ * this is how SweepAndPrune3 output feeds the narrow phase without a host trip. */
+int cb2_gjk3_intersection_dev(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                              const uint32_t* l_shape, const uint32_t* r_shape,
+                              const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                              cb2_contact* out, uint8_t* status, void* stream);
+int cb2_gjk3_distance_dev(cb2_ctx* ctx, const cb2_settings* settings,
+                          const uint32_t* l_shape, const uint32_t* r_shape,
+                          const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                          float* out, uint8_t* status, void* stream);
+int cb2_gjk3_time_of_impact_dev(cb2_ctx* ctx, const cb2_settings* settings,
+                                const uint32_t* l_shape, const uint32_t* r_shape,
+                                const cb2_xform* l_t0, const cb2_xform* l_t1,
+                                const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
+                                uint32_t iter_cap, cb2_contact* out, uint8_t* status,
+                                void* stream);
+int cb2_gjk3_intersection_bodies_dev(cb2_ctx* ctx, uint32_t strategy,
+                                     const cb2_settings* settings,
+                                     const uint32_t* body_shape, const cb2_xform* body_t,
+                                     const uint32_t* pair_body /* 2 x n, interleaved */,
+                                     uint64_t n, cb2_contact* out, uint8_t* status,
+                                     void* stream);
+
+/* ---- broad phase ---------------------------------------------------------------
+ * cb2_sap3_find_collider_pairs replaces SweepAndPrune3::find_collider_pairs
+ * (algorithm/broad_phase/sweep_prune.rs:76-136) for finite extents:
+ *   perm_out[k]  = original index of the box that the reference's stable sort
+ *                  (sweep_prune.rs:87-97) leaves at position k (the caller applies
+ *                  it to its &mut [A]); identity when n <= 1.
+ *   pairs_out    = (a, b) index pairs INTO THE SORTED ORDER, a < b, in the exact
+ *                  order of the reference's Vec (b ascending, then a ascending).
+ *   *axis_inout  = sweep axis used (in) / axis for the next call (out; always 0
+ *                  when n >= 2 — Variance3 accumulates nothing, sweep_prune.rs:254-277).
+ * If cap < number of pairs: returns CB2_ERR_NOSPC with *n_pairs = required.      */
+int cb2_sap3_find_collider_pairs(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint64_t n,
+                                 uint32_t* axis_inout, uint32_t* perm_out,
+                                 uint32_t* pairs_out /* 2 x cap */, uint64_t cap,
+                                 uint64_t* n_pairs);
+/* Device-resident variant: aabbs/perm_out/pairs_out are device pointers, the
+ * pair count is returned through the host pointer n_pairs (this call synchronises
+ * `stream` once, to learn the count).                                            */
+int cb2_sap3_find_collider_pairs_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint64_t n,
+                                     uint32_t axis, uint32_t* perm_out,
+                                     uint32_t* pairs_out, uint64_t cap,
+                                     uint64_t* n_pairs, void* stream);
+
+/* ---- world bounds (the step before the broad phase) -----------------------------
+ * out[i] = shape.compute_bound().transform_volume(&t[i])
+ * (ComputeBound: sphere.rs:41-51, cuboid.rs:82-92, polyhedron.rs:113-115,403-410;
+ *  Aabb3::transform: volume/aabb/aabb3.rs:90-100).                               */
+int cb2_world_aabbs(cb2_ctx* ctx, const uint32_t* shape, const cb2_xform* t, uint64_t n,
+                    cb2_aabb3* out);
+int cb2_world_aabbs_dev(cb2_ctx* ctx, const uint32_t* shape, const cb2_xform* t, uint64_t n,
+                        cb2_aabb3* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLLISION_B200_H */

@@ -1,0 +1,219 @@
+"""ctypes binding of the CPU oracle (oracle/collision_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs — never by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+SHAPE_DT = np.dtype([("kind", "<u4"), ("p", "<f4", (3,)), ("vtx_off", "<u4"), ("vtx_cnt", "<u4")])
+XFORM_DT = np.dtype([("scale", "<f4"), ("q", "<f4", (4,)), ("d", "<f4", (3,))])
+CONTACT_DT = np.dtype([("strategy", "<u4"), ("normal", "<f4", (3,)), ("depth", "<f4"),
+                       ("point", "<f4", (3,)), ("toi", "<f4")])
+AABB_DT = np.dtype([("min", "<f4", (3,)), ("max", "<f4", (3,))])
+
+
+class Settings(C.Structure):
+    _fields_ = [("distance_tolerance", C.c_float), ("continuous_tolerance", C.c_float),
+                ("epa_tolerance", C.c_float), ("max_iterations", C.c_uint32)]
+
+    @staticmethod
+    def default():
+        return Settings(np.float32(1e-6), np.float32(1e-6), np.float32(1e-5), 100)
+
+
+def build(force=False):
+    """make -C oracle (gcc only). Building the checker is not using it."""
+    out = os.path.join(_BUILD, "liboracle.so")
+    src = os.path.join(_HERE, "collision_oracle.cpp")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return out
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    def __init__(self, count_ops=False):
+        build()
+        name = "liboracle_count.so" if count_ops else "liboracle.so"
+        self.lib = C.CDLL(os.path.join(_BUILD, name))
+        self.lib.orc_sap3_find_collider_pairs.restype = C.c_uint64
+        self.lib.orc_brute_force_count.restype = C.c_uint64
+        self.lib.orc_ops_reset.restype = C.c_uint64
+        self.lib.orc_closest_point_to_origin.restype = C.c_uint8
+        self.lib.orc_epa3_process.restype = C.c_uint8
+        self.lib.orc_gjk3_intersect.restype = C.c_uint8
+        self.count_ops = count_ops
+
+    def hw_threads(self):
+        return int(self.lib.orc_hw_threads())
+
+    # ---- unit hooks ---------------------------------------------------------------
+    def support_point(self, shape, verts, xform, direction):
+        out = np.zeros(3, np.float32)
+        st = C.c_uint8(0)
+        d = np.asarray(direction, np.float32)
+        self.lib.orc_support_point(_p(shape), _p(verts), _p(xform), _p(d), _p(out), C.byref(st))
+        return out, st.value
+
+    def reduce_to_closest_feature(self, pts, v=(0, 0, 0)):
+        buf = np.zeros((8, 3), np.float32)
+        pts = np.asarray(pts, np.float32).reshape(-1, 3)
+        buf[:len(pts)] = pts
+        n = C.c_uint32(len(pts))
+        vv = np.asarray(v, np.float32).copy()
+        hit = self.lib.orc_reduce_to_closest_feature(_p(buf), C.byref(n), _p(vv))
+        return bool(hit), buf[:n.value].copy(), vv
+
+    def check_side(self, pts, above, ignore_ab):
+        buf = np.zeros((8, 3), np.float32)
+        pts = np.asarray(pts, np.float32).reshape(-1, 3)
+        buf[:len(pts)] = pts
+        n = C.c_uint32(len(pts))
+        vv = np.zeros(3, np.float32)
+        self.lib.orc_check_side(_p(buf), C.byref(n), int(above), int(ignore_ab), _p(vv))
+        return buf[:n.value].copy(), vv
+
+    def closest_point_to_origin(self, pts):
+        buf = np.zeros((8, 3), np.float32)
+        pts = np.asarray(pts, np.float32).reshape(-1, 3)
+        buf[:len(pts)] = pts
+        n = C.c_uint32(len(pts))
+        out = np.zeros(3, np.float32)
+        st = self.lib.orc_closest_point_to_origin(_p(buf), C.byref(n), _p(out))
+        return st, out, buf[:n.value].copy()
+
+    def closest_point_on_edge(self, start, end, point):
+        out = np.zeros(3, np.float32)
+        a, b, c = (np.asarray(x, np.float32) for x in (start, end, point))
+        self.lib.orc_closest_point_on_edge(_p(a), _p(b), _p(c), _p(out))
+        return out
+
+    def barycentric(self, p, a, b, c):
+        out = np.zeros(3, np.float32)
+        p, a, b, c = (np.asarray(x, np.float32) for x in (p, a, b, c))
+        self.lib.orc_barycentric(_p(p), _p(a), _p(b), _p(c), _p(out))
+        return out
+
+    def plane_from_points(self, a, b, c):
+        out = np.zeros(4, np.float32)
+        a, b, c = (np.asarray(x, np.float32) for x in (a, b, c))
+        ok = self.lib.orc_plane_from_points(_p(a), _p(b), _p(c), _p(out))
+        return (out[:3].copy(), out[3]) if ok else None
+
+    def polytope(self, verts, add=()):
+        verts = np.asarray(verts, np.float32).reshape(-1, 3)
+        add = np.asarray(add, np.float32).reshape(-1, 3)
+        idx = np.zeros((512, 3), np.uint32)
+        nd = np.zeros((512, 4), np.float32)
+        nf, closest, nv = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        self.lib.orc_polytope(_p(verts), C.c_uint32(len(verts)), _p(add), C.c_uint32(len(add)),
+                              _p(idx), _p(nd), C.byref(nf), C.byref(closest), C.byref(nv))
+        return idx[:nf.value].copy(), nd[:nf.value].copy(), closest.value, nv.value
+
+    def remove_or_add_edge(self, edges, e):
+        buf = np.zeros((64, 2), np.uint32)
+        edges = np.asarray(edges, np.uint32).reshape(-1, 2)
+        buf[:len(edges)] = edges
+        n = C.c_uint32(len(edges))
+        self.lib.orc_remove_or_add_edge(_p(buf), C.byref(n), C.c_uint32(e[0]), C.c_uint32(e[1]))
+        return [tuple(int(x) for x in r) for r in buf[:n.value]]
+
+    def epa3_process(self, simplex, l, lt, r, rt, verts=None, settings=None):
+        settings = settings or Settings.default()
+        s = np.asarray(simplex, np.float32).reshape(-1, 3)
+        out = np.zeros(1, CONTACT_DT)
+        st = self.lib.orc_epa3_process(_p(s), C.c_uint32(len(s)), _p(l), _p(lt), _p(r), _p(rt),
+                                       _p(verts), C.byref(settings), _p(out))
+        return st, out[0]
+
+    def gjk3_intersect(self, l, lt, r, rt, verts=None, settings=None):
+        settings = settings or Settings.default()
+        s = np.zeros((8, 3), np.float32)
+        n = C.c_uint32(0)
+        st = self.lib.orc_gjk3_intersect(_p(l), _p(lt), _p(r), _p(rt), _p(verts),
+                                         C.byref(settings), _p(s), C.byref(n))
+        return st, s[:n.value].copy()
+
+    def aabb3_intersects(self, a, b):
+        a = np.asarray(a, np.float32).reshape(6)
+        b = np.asarray(b, np.float32).reshape(6)
+        return bool(self.lib.orc_aabb3_intersects(_p(a), _p(b)))
+
+    # ---- batch ---------------------------------------------------------------------
+    def intersection(self, strategy, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None,
+                     nthreads=1, want_stats=False):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT_DT)
+        status = np.zeros(n, np.uint8)
+        stats = np.zeros((n, 4), np.uint32) if want_stats else None
+        self.lib.orc_gjk3_intersection_batch(
+            C.c_uint32(strategy), C.byref(settings), _p(shapes), _p(verts), _p(l_shape),
+            _p(r_shape), _p(l_t), _p(r_t), C.c_uint64(n), _p(out), _p(status), _p(stats),
+            int(nthreads))
+        return (out, status, stats) if want_stats else (out, status)
+
+    def distance(self, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None, nthreads=1,
+                 want_iters=False):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        iters = np.zeros(n, np.uint32) if want_iters else None
+        self.lib.orc_gjk3_distance_batch(
+            C.byref(settings), _p(shapes), _p(verts), _p(l_shape), _p(r_shape), _p(l_t), _p(r_t),
+            C.c_uint64(n), _p(out), _p(status), _p(iters), int(nthreads))
+        return (out, status, iters) if want_iters else (out, status)
+
+    def time_of_impact(self, shapes, verts, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1,
+                       settings=None, iter_cap=1024, nthreads=1, want_iters=False):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT_DT)
+        status = np.zeros(n, np.uint8)
+        iters = np.zeros(n, np.uint32) if want_iters else None
+        self.lib.orc_gjk3_toi_batch(
+            C.byref(settings), _p(shapes), _p(verts), _p(l_shape), _p(r_shape), _p(l_t0),
+            _p(l_t1), _p(r_t0), _p(r_t1), C.c_uint64(n), C.c_uint32(iter_cap), _p(out),
+            _p(status), _p(iters), int(nthreads))
+        return (out, status, iters) if want_iters else (out, status)
+
+    def world_aabbs(self, shapes, verts, shape, t, nthreads=1):
+        n = len(shape)
+        out = np.zeros(n, AABB_DT)
+        self.lib.orc_world_aabbs(_p(shapes), _p(verts), _p(shape), _p(t), C.c_uint64(n), _p(out),
+                                 int(nthreads))
+        return out
+
+    def sap3(self, aabbs, axis=0, cap=None):
+        n = len(aabbs)
+        perm = np.zeros(max(n, 1), np.uint32)
+        ax = C.c_uint32(axis)
+        if cap is None:
+            cnt = self.lib.orc_sap3_find_collider_pairs(_p(aabbs), C.c_uint64(n), C.byref(ax),
+                                                        _p(perm), None, C.c_uint64(0))
+            cap = int(cnt)
+            ax = C.c_uint32(axis)
+        pairs = np.zeros((max(cap, 1), 2), np.uint32)
+        cnt = self.lib.orc_sap3_find_collider_pairs(_p(aabbs), C.c_uint64(n), C.byref(ax),
+                                                    _p(perm), _p(pairs), C.c_uint64(cap))
+        return perm[:n].copy(), pairs[:min(int(cnt), cap)].copy(), int(cnt), ax.value
+
+    def brute_force_count(self, aabbs):
+        return int(self.lib.orc_brute_force_count(_p(aabbs), C.c_uint64(len(aabbs))))
+
+    def ops_reset(self):
+        return int(self.lib.orc_ops_reset())

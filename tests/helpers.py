@@ -1,0 +1,53 @@
+"""Fixture builders mirroring the reference's test helpers
+(transform_3d: gjk/mod.rs:609-620, epa3d.rs:366-377, sphere.rs:226-232)."""
+import ctypes
+import ctypes.util
+
+import numpy as np
+
+from oracle.binding import SHAPE_DT, XFORM_DT, AABB_DT
+
+_libm = ctypes.CDLL(ctypes.util.find_library("m"))
+_libm.sinf.restype = ctypes.c_float
+_libm.sinf.argtypes = [ctypes.c_float]
+_libm.cosf.restype = ctypes.c_float
+_libm.cosf.argtypes = [ctypes.c_float]
+
+
+def shape(kind, p=(0, 0, 0), off=0, cnt=0):
+    s = np.zeros(1, SHAPE_DT)
+    s["kind"] = kind
+    s["p"] = np.asarray(p, np.float32)
+    s["vtx_off"] = off
+    s["vtx_cnt"] = cnt
+    return s
+
+
+def sphere(r):
+    return shape(0, (r, 0, 0))
+
+
+def cuboid(x, y, z):
+    return shape(1, (x, y, z))
+
+
+def polyhedron(off, cnt):
+    return shape(2, (0, 0, 0), off, cnt)
+
+
+def transform_3d(x, y, z, angle_z=0.0, scale=1.0):
+    """Decomposed{disp:(x,y,z), rot: Quaternion::from_angle_z(Rad(angle_z)), scale}.
+    cgmath: from_angle_z(t) = (cos(t*0.5), 0, 0, sin(t*0.5)) in f32 (libm sinf/cosf like Rust)."""
+    h = np.float32(np.float32(angle_z) * np.float32(0.5))
+    t = np.zeros(1, XFORM_DT)
+    t["scale"] = scale
+    t["q"] = (_libm.cosf(h), 0.0, 0.0, _libm.sinf(h))
+    t["d"] = (x, y, z)
+    return t
+
+
+def aabb(mn, mx):
+    a = np.zeros(1, AABB_DT)
+    a["min"] = mn
+    a["max"] = mx
+    return a
