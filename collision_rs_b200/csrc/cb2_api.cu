@@ -1,0 +1,484 @@
+// cb2_api.cu — the extern "C" boundary declared in include/collision_b200.h.
+//
+// One ctx per GPU.  Host-buffer entry points stream the batch through the device in chunks on
+// two CUDA streams (H2D of chunk k+1 overlaps the kernel of chunk k and the D2H of chunk k-1;
+// truly asynchronous when the caller's buffers are pinned).  Device-buffer entry points only
+// enqueue kernels on the caller's stream.  No CPU fallback anywhere.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cb2_gjk.cuh"
+#include "cb2_kernels.h"
+
+using namespace cb2;
+
+struct cb2_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    uint64_t launches = 0;
+    // shape table
+    dshape* d_shapes = nullptr;
+    float4* d_verts = nullptr;
+    uint32_t n_shapes = 0;
+    uint64_t n_verts = 0;
+    // host-API staging
+    static constexpr int NS = 2;
+    cudaStream_t stream[NS] = {nullptr, nullptr};
+    cudaEvent_t done[NS] = {nullptr, nullptr};
+    char* d_stage[NS] = {nullptr, nullptr};
+    size_t stage_cap = 0;
+    sap_workspace* sap = nullptr;
+    void* d_misc = nullptr;  // host-API SAP / AABB buffers
+    size_t misc_cap = 0;
+};
+
+static std::string g_create_err;
+
+#define CK(ctx, x)                                                                     \
+    do {                                                                               \
+        cudaError_t e_ = (x);                                                          \
+        if (e_ != cudaSuccess) {                                                       \
+            (ctx)->err = std::string(#x) + ": " + cudaGetErrorString(e_);              \
+            return CB2_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+static int fail(cb2_ctx* c, int code, const char* msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+extern "C" {
+
+uint32_t cb2_abi_version(void) { return CB2_ABI_VERSION; }
+
+void cb2_default_settings(cb2_settings* out) {
+    out->distance_tolerance = 0.000001f;    // GJK_DISTANCE_TOLERANCE, gjk/mod.rs:23
+    out->continuous_tolerance = 0.000001f;  // GJK_CONTINUOUS_TOLERANCE, gjk/mod.rs:24
+    out->epa_tolerance = 0.00001f;          // EPA_TOLERANCE, epa/mod.rs:15
+    out->max_iterations = 100;              // MAX_ITERATIONS, gjk/mod.rs:22, epa/mod.rs:16
+}
+
+int cb2_create(int device, cb2_ctx** out) {
+    if (!out) return CB2_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_err = std::string("no usable CUDA device (") +
+                       (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range") +
+                       "); this library has no CPU fallback";
+        return CB2_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        g_create_err = "cudaSetDevice failed";
+        return CB2_ERR_NO_DEVICE;
+    }
+    cb2_ctx* c = new cb2_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        g_create_err = "cudaGetDeviceProperties failed";
+        delete c;
+        return CB2_ERR_CUDA;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < cb2_ctx::NS; ++i) {
+        if (cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) != cudaSuccess) {
+            g_create_err = "stream/event creation failed";
+            delete c;
+            return CB2_ERR_CUDA;
+        }
+    }
+    c->sap = sap_workspace_create();
+    if (!c->sap) {
+        g_create_err = "pinned allocation failed";
+        delete c;
+        return CB2_ERR_CUDA;
+    }
+    *out = c;
+    return CB2_OK;
+}
+
+void cb2_destroy(cb2_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < cb2_ctx::NS; ++i) {
+        if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+        if (c->done[i]) cudaEventDestroy(c->done[i]);
+        if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
+    }
+    if (c->d_shapes) cudaFree(c->d_shapes);
+    if (c->d_verts) cudaFree(c->d_verts);
+    if (c->d_misc) cudaFree(c->d_misc);
+    sap_workspace_destroy(c->sap);
+    delete c;
+}
+
+const char* cb2_last_error(const cb2_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+int cb2_device_sm_count(const cb2_ctx* c) { return c ? c->sm_count : 0; }
+uint64_t cb2_kernel_launches(const cb2_ctx* c) { return c ? c->launches : 0; }
+
+int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
+                      const float* verts_xyz, uint64_t n_verts) {
+    if (!c || (!shapes && n_shapes) || (!verts_xyz && n_verts)) return fail(c, CB2_ERR_ARG, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    std::vector<dshape> hs(n_shapes);
+    for (uint32_t i = 0; i < n_shapes; ++i) {
+        const cb2_shape& s = shapes[i];
+        dshape d;
+        std::memset(&d, 0, sizeof(d));
+        d.kind = s.kind;
+        if (s.kind == CB2_SPHERE) {
+            d.hx = s.p[0];
+        } else if (s.kind == CB2_CUBOID) {
+            // half_dim = dim / (1 + 1), cuboid.rs:36 (division by two is exact)
+            d.hx = s.p[0] / 2.0f;
+            d.hy = s.p[1] / 2.0f;
+            d.hz = s.p[2] / 2.0f;
+        } else if (s.kind == CB2_POLYHEDRON) {
+            if ((uint64_t)s.vtx_off + s.vtx_cnt > n_verts)
+                return fail(c, CB2_ERR_ARG, "polyhedron vertex range outside the vertex table");
+            d.voff = s.vtx_off;
+            d.vcnt = s.vtx_cnt;
+        } else {
+            return fail(c, CB2_ERR_ARG, "unknown shape kind");
+        }
+        hs[i] = d;
+    }
+    std::vector<float4> hv(n_verts);
+    for (uint64_t i = 0; i < n_verts; ++i)
+        hv[i] = make_float4(verts_xyz[3 * i], verts_xyz[3 * i + 1], verts_xyz[3 * i + 2], 0.0f);
+    CK(c, cudaDeviceSynchronize());
+    if (c->d_shapes) cudaFree(c->d_shapes);
+    if (c->d_verts) cudaFree(c->d_verts);
+    c->d_shapes = nullptr;
+    c->d_verts = nullptr;
+    CK(c, cudaMalloc(&c->d_shapes, sizeof(dshape) * (n_shapes ? n_shapes : 1)));
+    CK(c, cudaMalloc(&c->d_verts, sizeof(float4) * (n_verts ? n_verts : 1)));
+    if (n_shapes)
+        CK(c, cudaMemcpy(c->d_shapes, hs.data(), sizeof(dshape) * n_shapes, cudaMemcpyHostToDevice));
+    if (n_verts)
+        CK(c, cudaMemcpy(c->d_verts, hv.data(), sizeof(float4) * n_verts, cudaMemcpyHostToDevice));
+    c->n_shapes = n_shapes;
+    c->n_verts = n_verts;
+    return CB2_OK;
+}
+
+}  // extern "C"
+
+// ---- narrow phase ---------------------------------------------------------------------------------
+enum op_kind { OP_INTERSECTION, OP_DISTANCE, OP_TOI };
+
+static int check_settings(cb2_ctx* c, const cb2_settings* s) {
+    if (!s) return fail(c, CB2_ERR_ARG, "settings is null");
+    if (s->max_iterations > CB2_MAX_ITERATIONS)
+        return fail(c, CB2_ERR_UNSUPPORTED, "max_iterations above CB2_MAX_ITERATIONS (100)");
+    return CB2_OK;
+}
+
+static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, cudaStream_t st) {
+    A.shapes = c->d_shapes;
+    A.verts = c->d_verts;
+    cudaError_t e;
+    if (op == OP_INTERSECTION) e = launch_intersection(A, strategy == CB2_FULL_RESOLUTION, st);
+    else if (op == OP_DISTANCE) e = launch_distance(A, st);
+    else e = launch_time_of_impact(A, st);
+    ++c->launches;
+    if (e != cudaSuccess) {
+        c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
+        return CB2_ERR_CUDA;
+    }
+    return CB2_OK;
+}
+
+static int narrow_dev(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_settings* settings,
+                      const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t0,
+                      const cb2_xform* l_t1, const cb2_xform* r_t0, const cb2_xform* r_t1,
+                      const uint32_t* pair_body, uint64_t n, uint32_t iter_cap, cb2_contact* out_c,
+                      float* out_d, uint8_t* status, void* stream) {
+    if (!c) return CB2_ERR_ARG;
+    int rc = check_settings(c, settings);
+    if (rc) return rc;
+    if (op == OP_INTERSECTION && strategy > CB2_COLLISION_ONLY) return fail(c, CB2_ERR_ARG, "bad strategy");
+    if (n == 0) return CB2_OK;
+    if (!c->d_shapes) return fail(c, CB2_ERR_ARG, "cb2_shapes_upload has not been called");
+    if (!l_shape || !l_t0 || !status || (!pair_body && (!r_shape || !r_t0)))
+        return fail(c, CB2_ERR_ARG, "null argument");
+    if (op == OP_DISTANCE ? !out_d : !out_c) return fail(c, CB2_ERR_ARG, "null output");
+    if (op == OP_TOI && (!l_t1 || !r_t1)) return fail(c, CB2_ERR_ARG, "null end transform");
+    CK(c, cudaSetDevice(c->device));
+    narrow_args A;
+    std::memset(&A, 0, sizeof(A));
+    A.l_shape = l_shape;
+    A.r_shape = r_shape;
+    A.l_t = reinterpret_cast<const float4*>(l_t0);
+    A.r_t = reinterpret_cast<const float4*>(pair_body ? l_t0 : r_t0);
+    A.l_t1 = reinterpret_cast<const float4*>(l_t1);
+    A.r_t1 = reinterpret_cast<const float4*>(r_t1);
+    A.pair_body = pair_body;
+    A.n = n;
+    A.settings = *settings;
+    A.iter_cap = iter_cap ? iter_cap : 1024u;
+    A.out_contact = out_c;
+    A.out_distance = out_d;
+    A.out_status = status;
+    return launch_op(c, op, strategy, A, static_cast<cudaStream_t>(stream));
+}
+
+// Host-buffer path: chunked, double-buffered over two streams.
+static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_settings* settings,
+                       const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t0,
+                       const cb2_xform* l_t1, const cb2_xform* r_t0, const cb2_xform* r_t1,
+                       uint64_t n, uint32_t iter_cap, cb2_contact* out_c, float* out_d,
+                       uint8_t* status) {
+    if (!c) return CB2_ERR_ARG;
+    int rc = check_settings(c, settings);
+    if (rc) return rc;
+    if (op == OP_INTERSECTION && strategy > CB2_COLLISION_ONLY) return fail(c, CB2_ERR_ARG, "bad strategy");
+    if (n == 0) return CB2_OK;
+    if (!c->d_shapes) return fail(c, CB2_ERR_ARG, "cb2_shapes_upload has not been called");
+    if (!l_shape || !r_shape || !l_t0 || !r_t0 || !status) return fail(c, CB2_ERR_ARG, "null argument");
+    if (op == OP_DISTANCE ? !out_d : !out_c) return fail(c, CB2_ERR_ARG, "null output");
+    if (op == OP_TOI && (!l_t1 || !r_t1)) return fail(c, CB2_ERR_ARG, "null end transform");
+    // reject out-of-range shape indices up front (a Rust slice index would panic)
+    for (uint64_t i = 0; i < n; ++i)
+        if (l_shape[i] >= c->n_shapes || r_shape[i] >= c->n_shapes)
+            return fail(c, CB2_ERR_ARG, "shape index out of range");
+    CK(c, cudaSetDevice(c->device));
+    const uint64_t chunk = n < (1u << 19) ? n : (1u << 19);
+    const int n_xf = op == OP_TOI ? 4 : 2;
+    const size_t out_rec = op == OP_DISTANCE ? sizeof(float) : sizeof(cb2_contact);
+    // staging layout per stream: xforms | l_shape | r_shape | out | status   (256-byte aligned)
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_xf = 0;
+    const size_t xf_bytes = al(chunk * sizeof(cb2_xform));
+    const size_t o_ls = o_xf + n_xf * xf_bytes;
+    const size_t o_rs = o_ls + al(chunk * 4);
+    const size_t o_out = o_rs + al(chunk * 4);
+    const size_t o_st = o_out + al(chunk * out_rec);
+    const size_t need = o_st + al(chunk);
+    if (c->stage_cap < need) {
+        for (int i = 0; i < cb2_ctx::NS; ++i) {
+            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+            c->d_stage[i] = nullptr;
+        }
+        c->stage_cap = 0;
+        for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaMalloc(&c->d_stage[i], need));
+        c->stage_cap = need;
+    }
+    const cb2_xform* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
+    int k = 0;
+    for (uint64_t b = 0; b < n; b += chunk, ++k) {
+        const uint64_t m = (n - b < chunk) ? n - b : chunk;
+        const int s = k % cb2_ctx::NS;
+        cudaStream_t st = c->stream[s];
+        char* base = c->d_stage[s];
+        // the previous use of this staging buffer (chunk k-2) has been fully enqueued on the
+        // same stream, so stream order protects it.
+        for (int x = 0; x < n_xf; ++x)
+            CK(c, cudaMemcpyAsync(base + o_xf + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform),
+                                  cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemcpyAsync(base + o_ls, l_shape + b, m * 4, cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
+        narrow_args A;
+        std::memset(&A, 0, sizeof(A));
+        A.l_shape = reinterpret_cast<const uint32_t*>(base + o_ls);
+        A.r_shape = reinterpret_cast<const uint32_t*>(base + o_rs);
+        A.l_t = reinterpret_cast<const float4*>(base + o_xf);
+        A.r_t = reinterpret_cast<const float4*>(base + o_xf + xf_bytes);
+        if (op == OP_TOI) {
+            A.l_t1 = reinterpret_cast<const float4*>(base + o_xf + 2 * xf_bytes);
+            A.r_t1 = reinterpret_cast<const float4*>(base + o_xf + 3 * xf_bytes);
+        }
+        A.n = m;
+        A.settings = *settings;
+        A.iter_cap = iter_cap ? iter_cap : 1024u;
+        A.out_contact = reinterpret_cast<cb2_contact*>(base + o_out);
+        A.out_distance = reinterpret_cast<float*>(base + o_out);
+        A.out_status = reinterpret_cast<uint8_t*>(base + o_st);
+        rc = launch_op(c, op, strategy, A, st);
+        if (rc) return rc;
+        if (op == OP_DISTANCE)
+            CK(c, cudaMemcpyAsync(out_d + b, base + o_out, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+        else
+            CK(c, cudaMemcpyAsync(out_c + b, base + o_out, m * sizeof(cb2_contact),
+                                  cudaMemcpyDeviceToHost, st));
+        CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaStreamSynchronize(c->stream[i]));
+    return CB2_OK;
+}
+
+static int ensure_misc(cb2_ctx* c, size_t bytes) {
+    if (c->misc_cap >= bytes) return CB2_OK;
+    if (c->d_misc) cudaFree(c->d_misc);
+    c->d_misc = nullptr;
+    c->misc_cap = 0;
+    CK(c, cudaMalloc(&c->d_misc, bytes));
+    c->misc_cap = bytes;
+    return CB2_OK;
+}
+
+extern "C" {
+
+int cb2_gjk3_intersection(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                          const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t,
+                          const cb2_xform* r_t, uint64_t n, cb2_contact* out, uint8_t* status) {
+    return narrow_host(c, OP_INTERSECTION, strategy, settings, l_shape, r_shape, l_t, nullptr, r_t,
+                       nullptr, n, 0, out, nullptr, status);
+}
+int cb2_gjk3_distance(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                      const uint32_t* r_shape, const cb2_xform* l_t, const cb2_xform* r_t,
+                      uint64_t n, float* out, uint8_t* status) {
+    return narrow_host(c, OP_DISTANCE, 0, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, n,
+                       0, nullptr, out, status);
+}
+int cb2_gjk3_time_of_impact(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                            const uint32_t* r_shape, const cb2_xform* l_t0, const cb2_xform* l_t1,
+                            const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
+                            uint32_t iter_cap, cb2_contact* out, uint8_t* status) {
+    return narrow_host(c, OP_TOI, 0, settings, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, iter_cap,
+                       out, nullptr, status);
+}
+
+int cb2_gjk3_intersection_dev(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                              const uint32_t* l_shape, const uint32_t* r_shape,
+                              const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                              cb2_contact* out, uint8_t* status, void* stream) {
+    return narrow_dev(c, OP_INTERSECTION, strategy, settings, l_shape, r_shape, l_t, nullptr, r_t,
+                      nullptr, nullptr, n, 0, out, nullptr, status, stream);
+}
+int cb2_gjk3_distance_dev(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                          const uint32_t* r_shape, const cb2_xform* l_t, const cb2_xform* r_t,
+                          uint64_t n, float* out, uint8_t* status, void* stream) {
+    return narrow_dev(c, OP_DISTANCE, 0, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr,
+                      nullptr, n, 0, nullptr, out, status, stream);
+}
+int cb2_gjk3_time_of_impact_dev(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                                const uint32_t* r_shape, const cb2_xform* l_t0,
+                                const cb2_xform* l_t1, const cb2_xform* r_t0,
+                                const cb2_xform* r_t1, uint64_t n, uint32_t iter_cap,
+                                cb2_contact* out, uint8_t* status, void* stream) {
+    return narrow_dev(c, OP_TOI, 0, settings, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, nullptr, n,
+                      iter_cap, out, nullptr, status, stream);
+}
+int cb2_gjk3_intersection_bodies_dev(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                                     const uint32_t* body_shape, const cb2_xform* body_t,
+                                     const uint32_t* pair_body, uint64_t n, cb2_contact* out,
+                                     uint8_t* status, void* stream) {
+    if (!pair_body && n) return fail(c, CB2_ERR_ARG, "pair_body is null");
+    return narrow_dev(c, OP_INTERSECTION, strategy, settings, body_shape, nullptr, body_t, nullptr,
+                      nullptr, nullptr, pair_body, n, 0, out, nullptr, status, stream);
+}
+
+// ---- broad phase -------------------------------------------------------------------------------------
+int cb2_sap3_find_collider_pairs_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
+                                     uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap,
+                                     uint64_t* n_pairs, void* stream) {
+    if (!c || !n_pairs) return fail(c, CB2_ERR_ARG, "null argument");
+    *n_pairs = 0;
+    if (axis > 2) return fail(c, CB2_ERR_ARG, "sweep axis must be 0, 1 or 2");
+    if (n == 0) return CB2_OK;
+    if (!aabbs || !perm_out || (!pairs_out && cap)) return fail(c, CB2_ERR_ARG, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    const char* err = "";
+    int rc = sap_find_pairs(c->sap, aabbs, n, axis, perm_out, pairs_out, cap, n_pairs,
+                            static_cast<cudaStream_t>(stream), &c->launches, &err);
+    if (rc == CB2_ERR_NOSPC) c->err = "pairs_out too small; *n_pairs holds the required capacity";
+    else if (rc) c->err = err;
+    return rc;
+}
+
+int cb2_sap3_find_collider_pairs(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n,
+                                 uint32_t* axis_inout, uint32_t* perm_out, uint32_t* pairs_out,
+                                 uint64_t cap, uint64_t* n_pairs) {
+    if (!c || !axis_inout || !n_pairs) return fail(c, CB2_ERR_ARG, "null argument");
+    *n_pairs = 0;
+    if (*axis_inout > 2) return fail(c, CB2_ERR_ARG, "sweep axis must be 0, 1 or 2");
+    if (n == 0) return CB2_OK;
+    if (!aabbs || !perm_out || (!pairs_out && cap)) return fail(c, CB2_ERR_ARG, "null argument");
+    if (n == 1) {  // sweep_prune.rs:83-85: early return, axis untouched
+        perm_out[0] = 0;
+        return CB2_OK;
+    }
+    CK(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_box = 0, o_perm = al(n * sizeof(cb2_aabb3)), o_pairs = o_perm + al(n * 4);
+    int rc = ensure_misc(c, o_pairs + al(cap * 8));
+    if (rc) return rc;
+    char* base = static_cast<char*>(c->d_misc);
+    cudaStream_t st = c->stream[0];
+    CK(c, cudaMemcpyAsync(base + o_box, aabbs, n * sizeof(cb2_aabb3), cudaMemcpyHostToDevice, st));
+    rc = cb2_sap3_find_collider_pairs_dev(c, reinterpret_cast<cb2_aabb3*>(base + o_box), n,
+                                          *axis_inout, reinterpret_cast<uint32_t*>(base + o_perm),
+                                          reinterpret_cast<uint32_t*>(base + o_pairs), cap, n_pairs,
+                                          st);
+    if (rc && rc != CB2_ERR_NOSPC) return rc;
+    CK(c, cudaMemcpyAsync(perm_out, base + o_perm, n * 4, cudaMemcpyDeviceToHost, st));
+    if (rc == CB2_OK && *n_pairs)
+        CK(c, cudaMemcpyAsync(pairs_out, base + o_pairs, *n_pairs * 8, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    // compute_axis sees zero sums => axis 0 (sweep_prune.rs:130-133, 254-277); on NOSPC the
+    // axis is left alone so the caller can retry the same call with a larger buffer
+    if (rc == CB2_OK) *axis_inout = 0;
+    return rc;
+}
+
+// ---- world AABBs ---------------------------------------------------------------------------------------
+int cb2_world_aabbs_dev(cb2_ctx* c, const uint32_t* shape, const cb2_xform* t, uint64_t n,
+                        cb2_aabb3* out, void* stream) {
+    if (!c) return CB2_ERR_ARG;
+    if (n == 0) return CB2_OK;
+    if (!shape || !t || !out) return fail(c, CB2_ERR_ARG, "null argument");
+    if (!c->d_shapes) return fail(c, CB2_ERR_ARG, "cb2_shapes_upload has not been called");
+    CK(c, cudaSetDevice(c->device));
+    aabb_args A;
+    A.shapes = c->d_shapes;
+    A.verts = c->d_verts;
+    A.shape = shape;
+    A.t = reinterpret_cast<const float4*>(t);
+    A.n = n;
+    A.out = out;
+    cudaError_t e = launch_world_aabbs(A, static_cast<cudaStream_t>(stream));
+    ++c->launches;
+    if (e != cudaSuccess) {
+        c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
+        return CB2_ERR_CUDA;
+    }
+    return CB2_OK;
+}
+
+int cb2_world_aabbs(cb2_ctx* c, const uint32_t* shape, const cb2_xform* t, uint64_t n,
+                    cb2_aabb3* out) {
+    if (!c) return CB2_ERR_ARG;
+    if (n == 0) return CB2_OK;
+    if (!shape || !t || !out) return fail(c, CB2_ERR_ARG, "null argument");
+    for (uint64_t i = 0; i < n; ++i)
+        if (shape[i] >= c->n_shapes) return fail(c, CB2_ERR_ARG, "shape index out of range");
+    CK(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_sh = 0, o_t = al(n * 4), o_out = o_t + al(n * sizeof(cb2_xform));
+    int rc = ensure_misc(c, o_out + al(n * sizeof(cb2_aabb3)));
+    if (rc) return rc;
+    char* base = static_cast<char*>(c->d_misc);
+    cudaStream_t st = c->stream[0];
+    CK(c, cudaMemcpyAsync(base + o_sh, shape, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + o_t, t, n * sizeof(cb2_xform), cudaMemcpyHostToDevice, st));
+    rc = cb2_world_aabbs_dev(c, reinterpret_cast<uint32_t*>(base + o_sh),
+                             reinterpret_cast<cb2_xform*>(base + o_t), n,
+                             reinterpret_cast<cb2_aabb3*>(base + o_out), st);
+    if (rc) return rc;
+    CK(c, cudaMemcpyAsync(out, base + o_out, n * sizeof(cb2_aabb3), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return CB2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+// cb2_gjk.cuh — per-thread GJK3 / SimplexProcessor3 / EPA3 building blocks.
+//
+// Not a translation of the reference's container code: the simplex lives in
+// registers with compile-time indices (SmallVec::remove/swap become fixed register
+// moves), SimplexProcessor3's four call sites of check_side are flattened into ONE
+// predicated check (less divergence), support functions hoist per-pair invariants,
+// and the Cuboid corner scan uses 9 flops instead of 40 by exploiting the sign
+// symmetry of IEEE rounding — all while producing the same bits as the reference.
+#pragma once
+#include "cb2_math.cuh"
+
+namespace cb2 {
+
+enum : uint32_t { K_SPHERE = 0, K_CUBOID = 1, K_POLY = 2 };
+enum : uint8_t {
+    ST_NONE = 0,
+    ST_SOME = 1,
+    ST_PANIC_UNWRAP_PLANE = 2,
+    ST_PANIC_ASSERT_RANGE = 3,
+    ST_PANIC_INV_SCALE = 4,
+    ST_NONCONVERGED = 5,
+    ST_PANIC_EPA_EMPTY = 6,
+    ST_SCRATCH_OVERFLOW = 7
+};
+
+// Device shape-table entry (32 B, two 128-bit loads).  h = half_dim for a Cuboid
+// (dim / 2, cuboid.rs:36 — exact), h.x = radius for a Sphere.
+struct __align__(16) dshape {
+    uint32_t kind;
+    float hx, hy, hz;
+    uint32_t voff, vcnt, pad0, pad1;
+};
+
+struct shape {
+    uint32_t kind;
+    f3 h;
+    const float4* verts;  // polyhedron vertices (x,y,z,0), 16-byte records
+    uint32_t vcnt;
+};
+
+CB2_DI shape load_shape(const dshape* __restrict__ tab, const float4* __restrict__ verts,
+                        uint32_t idx) {
+    const float4* p = reinterpret_cast<const float4*>(tab + idx);
+    float4 a = __ldg(p);
+    float4 b = __ldg(p + 1);
+    shape s;
+    s.kind = __float_as_uint(a.x);
+    s.h = mk3(a.y, a.z, a.w);
+    s.verts = verts + __float_as_uint(b.x);
+    s.vcnt = __float_as_uint(b.y);
+    return s;
+}
+
+// ---- Primitive::support_point, local part (direction already in model space) ----------
+// Cuboid: util.rs:11-30 get_max_point over corners in cuboid.rs:54-65 order
+//   (+++)(-++)(--+)(+-+)(++-)(-+-)(---)(+--), first strictly greatest dot, start (origin,-inf).
+// With px=hx*dx, py=hy*dy, pz=hz*dz the eight dots (cx*dx + cy*dy) + cz*dz are
+//   d0=(px+py)+pz  d1=(py-px)+pz  d2=pz-(px+py)  d3=pz-(py-px)  d4=-d2 d5=-d3 d6=-d0 d7=-d1
+// bit-for-bit, because negation commutes with round-to-nearest.
+CB2_DI f3 cuboid_local_support(f3 h, f3 d) {
+    const float px = fmul(h.x, d.x), py = fmul(h.y, d.y), pz = fmul(h.z, d.z);
+    const float a = fadd(px, py);
+    const float b = fsub(py, px);
+    const float d0 = fadd(a, pz), d1 = fadd(b, pz), d2 = fsub(pz, a), d3 = fsub(pz, b);
+    float best = -INFINITY;
+    int idx = -1;
+    if (d0 > best) { best = d0; idx = 0; }
+    if (d1 > best) { best = d1; idx = 1; }
+    if (d2 > best) { best = d2; idx = 2; }
+    if (d3 > best) { best = d3; idx = 3; }
+    if (-d2 > best) { best = -d2; idx = 4; }
+    if (-d3 > best) { best = -d3; idx = 5; }
+    if (-d0 > best) { best = -d0; idx = 6; }
+    if (-d1 > best) { best = -d1; idx = 7; }
+    if (idx < 0) return zero3();  // every dot NaN / -inf: P::origin()
+    // sign masks of the corner table: x negative for {1,2,5,6}, y for {2,3,6,7}, z for {4..7}
+    const bool nx = (0x66 >> idx) & 1, ny = (0xCC >> idx) & 1, nz = idx >= 4;
+    return mk3(nx ? -h.x : h.x, ny ? -h.y : h.y, nz ? -h.z : h.z);
+}
+// Sphere: sphere.rs:32-38
+CB2_DI f3 sphere_local_support(float r, f3 d) { return normalize_to(d, r); }
+// ConvexPolyhedron VertexOnly: polyhedron.rs:160-176 (one thread scans; the cooperative
+// kernel in cb2_poly.cu replaces this with a sub-warp scan + shuffle argmax)
+CB2_DI f3 poly_local_support_serial(const float4* __restrict__ verts, uint32_t n, f3 d) {
+    f3 best = zero3();
+    float best_dot = -INFINITY;
+    for (uint32_t i = 0; i < n; ++i) {
+        float4 v = __ldg(verts + i);
+        f3 p = mk3(v.x, v.y, v.z);
+        float dt = dot(p, d);
+        if (dt > best_dot) {
+            best_dot = dt;
+            best = p;
+        }
+    }
+    return best;
+}
+
+CB2_DI f3 support_point(const shape& s, const xform& t, f3 dir) {
+    f3 d = inverse_transform_vector(t, dir);
+    f3 p;
+    if (s.kind == K_CUBOID) p = cuboid_local_support(s.h, d);
+    else if (s.kind == K_SPHERE) p = sphere_local_support(s.h.x, d);
+    else p = poly_local_support_serial(s.verts, s.vcnt, d);
+    return transform_point(t, p);
+}
+
+// ---- simplex in registers -----------------------------------------------------------------
+// v[i] = SupportPoint.v, a[i] = SupportPoint.sup_a (only kept when the EPA contact needs it;
+// sup_b is never read on the 3-D path).  Newest point is LAST, as in the reference.
+template <bool WITH_A>
+struct simplex {
+    f3 v[4];
+    f3 a[WITH_A ? 4 : 1];
+    int n;
+    CB2_DI void set(int i, f3 pv, f3 pa) {
+        v[i] = pv;
+        if (WITH_A) a[i] = pa;
+    }
+    CB2_DI void mov(int dst, int src) {
+        v[dst] = v[src];
+        if (WITH_A) a[dst] = a[src];
+    }
+    CB2_DI void swap01() {
+        f3 t = v[0];
+        v[0] = v[1];
+        v[1] = t;
+        if (WITH_A) {
+            f3 u = a[0];
+            a[0] = a[1];
+            a[1] = u;
+        }
+    }
+    CB2_DI void push(f3 pv, f3 pa) {  // n <= 3 on entry
+        if (n == 0) set(0, pv, pa);
+        else if (n == 1) set(1, pv, pa);
+        else if (n == 2) set(2, pv, pa);
+        else set(3, pv, pa);
+        ++n;
+    }
+};
+
+// SimplexProcessor3::reduce_to_closest_feature (simplex3d.rs:24-98) + check_side (:180-220).
+// Returns true iff the origin is inside the tetrahedron.  The reference calls check_side from
+// three places (ABC / ACD / triangle); here each place only selects operands and the single
+// check below runs once for the whole warp.
+template <bool WITH_A>
+CB2_DI bool reduce_to_closest_feature(simplex<WITH_A>& s, f3& v) {
+    bool check = false, above = false, ignore_ab = false;
+    f3 N, E1, E2, ao;
+    if (s.n == 4) {
+        const f3 a = s.v[3], b = s.v[2], c = s.v[1], d = s.v[0];
+        ao = -a;
+        const f3 ab = b - a, ac = c - a;
+        const f3 abc = cross(ab, ac);
+        if (dot(abc, ao) > 0.0f) {
+            // remove(0) -> [c, b, a]
+            s.mov(0, 1);
+            s.mov(1, 2);
+            s.mov(2, 3);
+            s.n = 3;
+            check = true; above = true;
+            N = abc; E1 = ab; E2 = ac;
+        } else {
+            const f3 ad = d - a;
+            const f3 acd = cross(ac, ad);
+            if (dot(acd, ao) > 0.0f) {
+                // remove(2) -> [d, c, a]
+                s.mov(2, 3);
+                s.n = 3;
+                check = true; above = true; ignore_ab = true;
+                N = acd; E1 = ac; E2 = ad;
+            } else {
+                const f3 adb = cross(ad, ab);
+                if (dot(adb, ao) > 0.0f) {
+                    // remove(1) -> [d, b, a]; swap(0,1) -> [b, d, a]
+                    s.mov(1, 0);
+                    s.mov(0, 2);
+                    s.mov(2, 3);
+                    s.n = 3;
+                    v = adb;
+                } else {
+                    return true;
+                }
+            }
+        }
+    } else if (s.n == 3) {
+        const f3 a = s.v[2], b = s.v[1], c = s.v[0];
+        ao = -a;
+        E1 = b - a;
+        E2 = c - a;
+        N = cross(E1, E2);
+        check = true;
+    } else if (s.n == 2) {
+        const f3 a = s.v[1], b = s.v[0];
+        const f3 ao2 = -a, ab = b - a;
+        v = cross_aba(ab, ao2);
+        if (ulps_eq_zero(v)) v.x = 0.1f;
+    }
+    if (check) {  // check_side(N=abc, E1=ab, E2=ac, ao, above, ignore_ab) on [C, B, A]
+        const f3 ab_perp = cross(E1, N);
+        if (!ignore_ab && dot(ab_perp, ao) > 0.0f) {
+            s.mov(0, 1);  // remove(0) -> [B, A]
+            s.mov(1, 2);
+            s.n = 2;
+            v = cross_aba(E1, ao);
+        } else {
+            const f3 ac_perp = cross(N, E2);
+            if (dot(ac_perp, ao) > 0.0f) {
+                s.mov(1, 2);  // remove(1) -> [C, A]
+                s.n = 2;
+                v = cross_aba(E2, ao);
+            } else if (above || dot(N, ao) > 0.0f) {
+                v = N;
+            } else {
+                s.swap01();
+                v = -N;
+            }
+        }
+    }
+    return false;
+}
+
+// util.rs:53-72
+CB2_DI void barycentric_vector(f3 p, f3 a, f3 b, f3 c, float& u, float& v, float& w) {
+    const f3 v0 = b - a, v1 = c - a, v2 = p - a;
+    const float d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0),
+                d21 = dot(v2, v1);
+    const float inv_denom = fdiv(1.0f, fsub(fmul(d00, d11), fmul(d01, d01)));
+    v = fmul(fsub(fmul(d11, d20), fmul(d01, d21)), inv_denom);
+    w = fmul(fsub(fmul(d00, d21), fmul(d01, d20)), inv_denom);
+    u = fsub(fsub(1.0f, v), w);
+}
+
+// util.rs:98-114 with point = origin
+CB2_DI f3 closest_point_on_edge_to_origin(f3 start, f3 end) {
+    const f3 line = end - start;
+    const f3 line_dir = normalize(line);
+    const f3 vv = zero3() - start;
+    const float d = dot(vv, line_dir);
+    if (d < 0.0f) return start;
+    if (fmul(d, d) > magnitude2(line)) return end;
+    return start + line_dir * d;
+}
+
+CB2_DI bool in_range(float x) { return x >= 0.0f && x <= 1.0f; }
+
+// simplex3d.rs:131-161 with Plane::from_points (plane.rs:78-95) and Plane ∩ Ray3
+// (plane.rs:176-188) inlined; ray = (origin, -normal).  status != 0 => reference panics.
+CB2_DI f3 closest_point_on_face(f3 a, f3 b, f3 c, f3 normal, uint8_t& status) {
+    const f3 origin = zero3();
+    const f3 dir = -normal;
+    const f3 v0 = b - a, v1 = c - a;
+    f3 n = cross(v0, v1);
+    if (ulps_eq_zero(n)) {
+        status = ST_PANIC_UNWRAP_PLANE;
+        return zero3();
+    }
+    n = normalize(n);
+    const float pd = -dot(a, n);
+    const float t = fdiv(-fadd(pd, dot(origin, n)), dot(dir, n));
+    if (t < 0.0f) return zero3();
+    const f3 point = origin + dir * t;
+    float u, v, w;
+    barycentric_vector(point, a, b, c, u, v, w);
+    if (!(in_range(u) && in_range(v) && in_range(w))) {
+        status = ST_PANIC_ASSERT_RANGE;
+        return zero3();
+    }
+    return point;
+}
+
+// SimplexProcessor3::get_closest_point_to_origin, simplex3d.rs:103-121
+CB2_DI f3 closest_point_to_origin(simplex<false>& s, uint8_t& status) {
+    f3 d = zero3();
+    if (reduce_to_closest_feature(s, d)) return d;
+    if (s.n == 1) return s.v[0];
+    if (s.n == 2) return closest_point_on_edge_to_origin(s.v[1], s.v[0]);
+    return closest_point_on_face(s.v[2], s.v[1], s.v[0], d, status);
+}
+
+}  // namespace cb2

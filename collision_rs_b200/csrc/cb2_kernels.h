@@ -1,0 +1,55 @@
+// cb2_kernels.h — internal launch interface between the C ABI (cb2_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/collision_b200.h"
+
+namespace cb2 {
+
+struct dshape;
+
+// All pointers are device pointers.
+struct narrow_args {
+    const dshape* shapes;     // device shape table (32-byte entries)
+    const float4* verts;      // polyhedron vertices, (x,y,z,0)
+    const uint32_t* l_shape;  // per pair; per BODY when pair_body != nullptr
+    const uint32_t* r_shape;
+    const float4* l_t;        // cb2_xform records as 2 x float4 (start pose for time of impact)
+    const float4* r_t;
+    const float4* l_t1;       // end poses (time of impact only)
+    const float4* r_t1;
+    const uint32_t* pair_body;  // optional 2 x n body indices (then l_t == r_t == body_t)
+    uint64_t n;
+    cb2_settings settings;
+    uint32_t iter_cap;
+    cb2_contact* out_contact;
+    float* out_distance;
+    uint8_t* out_status;
+};
+
+struct aabb_args {
+    const dshape* shapes;
+    const float4* verts;
+    const uint32_t* shape;
+    const float4* t;
+    uint64_t n;
+    cb2_aabb3* out;
+};
+
+cudaError_t launch_intersection(const narrow_args& A, bool full, cudaStream_t st);
+cudaError_t launch_distance(const narrow_args& A, cudaStream_t st);
+cudaError_t launch_time_of_impact(const narrow_args& A, cudaStream_t st);
+cudaError_t launch_world_aabbs(const aabb_args& A, cudaStream_t st);
+
+// ---- broad phase (cb2_sap.cu) ---------------------------------------------------------------
+struct sap_workspace;  // opaque, owned by the ctx
+sap_workspace* sap_workspace_create();
+void sap_workspace_destroy(sap_workspace* w);
+// Device-resident SweepAndPrune3::find_collider_pairs.  Returns 0 / cb2_error; *n_pairs is the
+// true pair count (pairs beyond cap are not written).  launches += kernels launched.
+int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
+                   uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
+                   cudaStream_t st, uint64_t* launches, const char** err);
+
+}  // namespace cb2

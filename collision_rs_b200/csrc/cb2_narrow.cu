@@ -1,0 +1,452 @@
+// cb2_narrow.cu — thread-per-pair GJK3 / EPA3 kernels (Sphere / Cuboid pairs; polyhedra are
+// accepted here with a serial vertex scan, the fast path for them is cb2_poly.cu).
+//
+// Replaces, batched: GJK3::intersection (gjk/mod.rs:362-391 -> intersect :101-146 +
+// EPA3::process epa3d.rs:27-65), GJK3::distance (:271-321) and
+// GJK3::intersection_time_of_impact (:163-256).
+//
+// Layout: transforms are 32-byte records read as two 128-bit loads per thread (a warp reads
+// 1 KiB contiguous); shape-table entries are 32 bytes, two 128-bit __ldg loads.  The simplex
+// is held in registers.  The EPA polytope (<= 104 vertices, <= 256 faces) is per-thread local
+// memory: the hardware interleaves local memory per lane, so a warp walking the face list in
+// lockstep reads 128-byte coalesced lines out of L1.
+#include "cb2_gjk.cuh"
+#include "cb2_kernels.h"
+
+namespace cb2 {
+
+struct pair_in {
+    shape ls, rs;
+    xform lt, rt;
+};
+
+template <bool WITH_A>
+CB2_DI void minkowski(const pair_in& p, f3 dir, f3& v, f3& a) {
+    const f3 l = support_point(p.ls, p.lt, dir);
+    const f3 r = support_point(p.rs, p.rt, -dir);
+    v = l - r;
+    if (WITH_A) a = l;
+}
+
+CB2_DI xform load_xform(const float4* __restrict__ t, uint64_t i) {
+    const float4 a = __ldg(t + 2 * i);
+    const float4 b = __ldg(t + 2 * i + 1);
+    return make_xform(a, b);
+}
+
+// seed direction shared by intersect and distance (gjk/mod.rs:117-122, :288-294)
+CB2_DI f3 seed_direction(const xform& lt, const xform& rt) {
+    const f3 left_pos = transform_point(lt, zero3());
+    const f3 right_pos = transform_point(rt, zero3());
+    f3 d = right_pos - left_pos;
+    if (ulps_eq_zero(d)) d = mk3(1.0f, 1.0f, 1.0f);
+    return d;
+}
+
+// GJK::intersect, gjk/mod.rs:101-146
+template <bool WITH_A>
+CB2_DI bool gjk_intersect(const pair_in& p, uint32_t max_iterations, simplex<WITH_A>& s) {
+    f3 d = seed_direction(p.lt, p.rt);
+    f3 v, a;
+    minkowski<WITH_A>(p, d, v, a);
+    if (dot(v, d) <= 0.0f) return false;
+    s.n = 0;
+    s.push(v, a);
+    d = -d;
+    for (uint32_t i = 0; i < max_iterations; ++i) {
+        minkowski<WITH_A>(p, d, v, a);
+        if (dot(v, d) <= 0.0f) return false;
+        s.push(v, a);
+        if (reduce_to_closest_feature(s, d)) return true;
+    }
+    return false;
+}
+
+// ---- EPA3 (epa3d.rs) with the polytope in per-thread local memory ---------------------------
+constexpr int EPA_MAX_VERTS = 104;   // 4 + (CB2_MAX_ITERATIONS - 1) adds = 103
+constexpr int EPA_MAX_FACES = 256;   // manifold bound 2V-4 = 202; slack for odd horizons
+constexpr int EPA_MAX_EDGES = 192;
+
+struct polytope {
+    float4 fnd[EPA_MAX_FACES];    // normal.xyz, distance
+    uint32_t fidx[EPA_MAX_FACES]; // v0 | v1<<8 | v2<<16
+    f3 pv[EPA_MAX_VERTS];         // SupportPoint.v
+    f3 pa[EPA_MAX_VERTS];         // SupportPoint.sup_a
+    uint16_t edges[EPA_MAX_EDGES];// a | b<<8, horizon list in reference order
+    int nf, nv;
+};
+
+// Face::new_impl, epa3d.rs:189-199
+CB2_DI void face_new(polytope& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
+    const f3 va = P.pv[a];
+    const f3 ab = P.pv[b] - va;
+    const f3 ac = P.pv[c] - va;
+    const f3 n = normalize(cross(ab, ac));
+    const float dist = dot(n, va);
+    P.fnd[slot] = make_float4(n.x, n.y, n.z, dist);
+    P.fidx[slot] = a | (b << 8) | (c << 16);
+}
+
+struct contact_out {
+    f3 normal;
+    float depth;
+    f3 point;
+    float toi;
+};
+
+// EPA3::process, epa3d.rs:27-65 (+ Polytope::add :147-175, contact :84-114)
+__device__ __noinline__ uint8_t epa_process(const pair_in& p, const simplex<true>& s, float tol,
+                                            uint32_t max_iterations, contact_out& out) {
+    polytope P;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        P.pv[i] = s.v[i];
+        P.pa[i] = s.a[i];
+    }
+    P.nv = 4;
+    face_new(P, 0, 3, 2, 1);  // Face::new, epa3d.rs:201-208
+    face_new(P, 1, 3, 1, 0);
+    face_new(P, 2, 3, 0, 2);
+    face_new(P, 3, 2, 0, 1);
+    P.nf = 4;
+    uint32_t it = 1;
+    for (;;) {
+        if (P.nf == 0) return ST_PANIC_EPA_EMPTY;
+        // closest_face_to_origin: first strictly smallest distance (:137-145)
+        int best = 0;
+        float best_d = P.fnd[0].w;
+        for (int f = 1; f < P.nf; ++f) {
+            const float d = P.fnd[f].w;
+            if (d < best_d) {
+                best_d = d;
+                best = f;
+            }
+        }
+        const float4 fb = P.fnd[best];
+        const f3 n = mk3(fb.x, fb.y, fb.z);
+        f3 sv, sa;
+        minkowski<true>(p, n, sv, sa);
+        const float d = dot(sv, n);
+        if (fsub(d, fb.w) < tol || it >= max_iterations) {
+            // contact(): barycentric of normal*distance on the face, blend sup_a (:84-114)
+            const uint32_t idx = P.fidx[best];
+            const uint32_t i0 = idx & 255u, i1 = (idx >> 8) & 255u, i2 = (idx >> 16) & 255u;
+            float u, v, w;
+            barycentric_vector(n * fb.w, P.pv[i0], P.pv[i1], P.pv[i2], u, v, w);
+            out.normal = n;
+            out.depth = fb.w;
+            out.point = (P.pa[i0] * u + P.pa[i1] * v) + P.pa[i2] * w;
+            out.toi = 0.0f;
+            return ST_SOME;
+        }
+        // Polytope::add: remove visible faces (swap_remove, no i++ on removal), toggle edges
+        int ne = 0;
+        int f = 0;
+        while (f < P.nf) {
+            const float4 fn = P.fnd[f];
+            const uint32_t idx = P.fidx[f];
+            const float vis = dot(mk3(fn.x, fn.y, fn.z), sv - P.pv[idx & 255u]);
+            if (vis > 0.0f) {
+                --P.nf;
+                P.fnd[f] = P.fnd[P.nf];
+                P.fidx[f] = P.fidx[P.nf];
+                const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    // remove_or_add_edge (:212-219): drop the first stored reverse edge, else push
+                    const uint32_t ea = e == 0 ? v0 : (e == 1 ? v1 : v2);
+                    const uint32_t eb = e == 0 ? v1 : (e == 1 ? v2 : v0);
+                    const uint16_t rev = (uint16_t)(eb | (ea << 8));
+                    int k = 0;
+                    while (k < ne && P.edges[k] != rev) ++k;
+                    if (k < ne) {
+                        for (int m = k; m + 1 < ne; ++m) P.edges[m] = P.edges[m + 1];
+                        --ne;
+                    } else {
+                        if (ne >= EPA_MAX_EDGES) return ST_SCRATCH_OVERFLOW;
+                        P.edges[ne++] = (uint16_t)(ea | (eb << 8));
+                    }
+                }
+            } else {
+                ++f;
+            }
+        }
+        if (P.nv >= EPA_MAX_VERTS || P.nf + ne > EPA_MAX_FACES) return ST_SCRATCH_OVERFLOW;
+        const uint32_t nn = (uint32_t)P.nv;
+        P.pv[nn] = sv;
+        P.pa[nn] = sa;
+        ++P.nv;
+        for (int k = 0; k < ne; ++k) {
+            const uint32_t e = P.edges[k];
+            face_new(P, P.nf + k, nn, e & 255u, e >> 8);
+        }
+        P.nf += ne;
+        ++it;
+    }
+}
+
+CB2_DI void store_contact(cb2_contact* __restrict__ out, uint64_t i, uint32_t strategy,
+                          const contact_out& c) {
+    float* o = reinterpret_cast<float*>(out + i);
+    o[0] = __uint_as_float(strategy);
+    o[1] = c.normal.x;
+    o[2] = c.normal.y;
+    o[3] = c.normal.z;
+    o[4] = c.depth;
+    o[5] = c.point.x;
+    o[6] = c.point.y;
+    o[7] = c.point.z;
+    o[8] = c.toi;
+}
+CB2_DI contact_out zero_contact() {
+    contact_out c;
+    c.normal = zero3();
+    c.depth = 0.0f;
+    c.point = zero3();
+    c.toi = 0.0f;
+    return c;
+}
+
+CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const float4* rt,
+                      pair_in& p) {
+    uint32_t li, ri;
+    uint64_t lx, rx;
+    if (A.pair_body) {  // body-indexed pairs (SweepAndPrune3 output feeding the narrow phase)
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(A.pair_body) + i);
+        lx = b.x;
+        rx = b.y;
+        li = __ldg(A.l_shape + lx);
+        ri = __ldg(A.l_shape + rx);
+    } else {
+        lx = rx = i;
+        li = __ldg(A.l_shape + i);
+        ri = __ldg(A.r_shape + i);
+    }
+    p.ls = load_shape(A.shapes, A.verts, li);
+    p.rs = load_shape(A.shapes, A.verts, ri);
+    p.lt = load_xform(lt, lx);
+    p.rt = load_xform(rt, rx);
+    // inverse_transform_vector(..).unwrap() panics when ulps_eq(scale, 0); every entry point
+    // reaches a support call before anything else can return (util.rs:18, sphere.rs:36)
+    return !(ulps_eq_zero(p.lt.scale) || ulps_eq_zero(p.rt.scale));
+}
+
+// ---- kernels -----------------------------------------------------------------------------------
+template <bool FULL>
+__global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    pair_in p;
+    contact_out c = zero_contact();
+    uint8_t st = ST_NONE;
+    if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+        st = ST_PANIC_INV_SCALE;
+    } else {
+        simplex<FULL> s;
+        if (gjk_intersect<FULL>(p, A.settings.max_iterations, s)) {
+            if constexpr (FULL) {
+                st = epa_process(p, reinterpret_cast<const simplex<true>&>(s),
+                                 A.settings.epa_tolerance, A.settings.max_iterations, c);
+                if (st != ST_SOME) c = zero_contact();
+            } else {
+                st = ST_SOME;
+            }
+        }
+    }
+    store_contact(A.out_contact, i, FULL ? CB2_FULL_RESOLUTION : CB2_COLLISION_ONLY, c);
+    A.out_status[i] = st;
+}
+
+// GJK::distance, gjk/mod.rs:271-321
+__global__ void __launch_bounds__(128) k_distance(narrow_args A) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    pair_in p;
+    uint8_t st = ST_NONE;
+    float result = 0.0f;
+    if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+        st = ST_PANIC_INV_SCALE;
+    } else {
+        const f3 d0 = seed_direction(p.lt, p.rt);
+        simplex<false> s;
+        s.n = 0;
+        f3 v, a;
+        minkowski<false>(p, d0, v, a);
+        s.push(v, a);
+        minkowski<false>(p, -d0, v, a);
+        s.push(v, a);
+        for (uint32_t it = 0; it < A.settings.max_iterations; ++it) {
+            uint8_t panic = 0;
+            f3 d = closest_point_to_origin(s, panic);
+            if (panic) {
+                st = panic;
+                break;
+            }
+            if (ulps_eq_zero(d)) break;  // None
+            d = -d;
+            minkowski<false>(p, d, v, a);
+            const float dp = dot(v, d);
+            const float dz = dot(s.v[0], d);
+            if (fsub(dp, dz) < A.settings.distance_tolerance) {
+                result = magnitude(d);
+                st = ST_SOME;
+                break;
+            }
+            s.push(v, a);
+        }
+    }
+    A.out_distance[i] = result;
+    A.out_status[i] = st;
+}
+
+// GJK::intersection_time_of_impact, gjk/mod.rs:163-256 (+ iter_cap -> ST_NONCONVERGED)
+__global__ void __launch_bounds__(128) k_time_of_impact(narrow_args A) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    pair_in p;
+    contact_out c = zero_contact();
+    uint8_t st = ST_NONE;
+    if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+        st = ST_PANIC_INV_SCALE;
+    } else {
+        uint64_t lx = i, rx = i;
+        const xform lt1 = load_xform(A.l_t1, lx);
+        const xform rt1 = load_xform(A.r_t1, rx);
+        const f3 left_lin_vel = transform_point(lt1, zero3()) - transform_point(p.lt, zero3());
+        const f3 right_lin_vel = transform_point(rt1, zero3()) - transform_point(p.rt, zero3());
+        const f3 ray = right_lin_vel - left_lin_vel;
+        float lambda = 0.0f;
+        f3 normal = zero3();
+        f3 ray_origin = zero3();
+        simplex<false> s;
+        s.n = 0;
+        f3 v, pv, a;
+        minkowski<false>(p, -ray, v, a);
+        uint32_t it = 0;
+        bool done = false;
+        while (magnitude2(v) > A.settings.continuous_tolerance) {
+            if (it >= A.iter_cap) {
+                st = ST_NONCONVERGED;
+                done = true;
+                break;
+            }
+            ++it;
+            minkowski<false>(p, -v, pv, a);
+            const float vp = dot(v, pv);
+            const float vr = dot(v, ray);
+            if (vp > fmul(lambda, vr)) {
+                if (vr > 0.0f) {
+                    lambda = fdiv(vp, vr);
+                    if (lambda > 1.0f) {
+                        done = true;
+                        break;
+                    }
+                    ray_origin = ray * lambda;
+                    s.n = 0;
+                    normal = -v;
+                } else {
+                    done = true;
+                    break;
+                }
+            }
+            s.push(pv - ray_origin, a);
+            uint8_t panic = 0;
+            v = closest_point_to_origin(s, panic);
+            if (panic) {
+                st = panic;
+                done = true;
+                break;
+            }
+        }
+        if (!done && magnitude2(v) <= A.settings.continuous_tolerance) {
+            // translation_interpolate (traits.rs:233-246): disp lerp, rot/scale from END
+            xform t = rt1;
+            t.disp = lerp(p.rt.disp, rt1.disp, lambda);
+            c.normal = -normalize(normal);
+            c.depth = magnitude(v);
+            c.point = transform_point(t, ray_origin);
+            c.toi = lambda;
+            st = ST_SOME;
+        }
+    }
+    store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, c);
+    A.out_status[i] = st;
+}
+
+// ---- world AABBs: shape.compute_bound().transform_volume(&t) ------------------------------------
+// ComputeBound: sphere.rs:41-51, cuboid.rs:82-92, polyhedron.rs:113-115 (fold from Aabb3::zero(),
+// so the bound always contains the origin); Aabb3::transform: aabb3.rs:39-50,90-100.
+CB2_DI float rmin(float l, float r) { return (l > r) ? r : l; }  // aabb/mod.rs:21-26
+CB2_DI float rmax(float l, float r) { return (l < r) ? r : l; }  // aabb/mod.rs:28-33
+
+__global__ void __launch_bounds__(256) k_world_aabbs(aabb_args A) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const shape s = load_shape(A.shapes, A.verts, __ldg(A.shape + i));
+    const xform t = load_xform(A.t, i);
+    f3 mn, mx;
+    if (s.kind == K_SPHERE) {
+        const float r = s.h.x;
+        mn = mk3(rmin(-r, r), rmin(-r, r), rmin(-r, r));
+        mx = mk3(rmax(-r, r), rmax(-r, r), rmax(-r, r));
+    } else if (s.kind == K_CUBOID) {
+        mn = mk3(rmin(-s.h.x, s.h.x), rmin(-s.h.y, s.h.y), rmin(-s.h.z, s.h.z));
+        mx = mk3(rmax(-s.h.x, s.h.x), rmax(-s.h.y, s.h.y), rmax(-s.h.z, s.h.z));
+    } else {
+        mn = zero3();
+        mx = zero3();
+        for (uint32_t k = 0; k < s.vcnt; ++k) {
+            const float4 v = __ldg(s.verts + k);
+            // grow(): Aabb::new(min(self.min,p), max(self.max,p)) then Aabb3::new re-sorts
+            const f3 a = mk3(rmin(mn.x, v.x), rmin(mn.y, v.y), rmin(mn.z, v.z));
+            const f3 b = mk3(rmax(mx.x, v.x), rmax(mx.y, v.y), rmax(mx.z, v.z));
+            mn = mk3(rmin(a.x, b.x), rmin(a.y, b.y), rmin(a.z, b.z));
+            mx = mk3(rmax(a.x, b.x), rmax(a.y, b.y), rmax(a.z, b.z));
+        }
+    }
+    f3 omn, omx;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {  // to_corners order, aabb3.rs:39-50
+        const f3 corner = mk3((c & 1) ? mx.x : mn.x, (c & 2) ? mx.y : mn.y, (c & 4) ? mx.z : mn.z);
+        const f3 q = transform_point(t, corner);
+        if (c == 0) {
+            omn = q;
+            omx = q;
+        } else {
+            const f3 a = mk3(rmin(omn.x, q.x), rmin(omn.y, q.y), rmin(omn.z, q.z));
+            const f3 b = mk3(rmax(omx.x, q.x), rmax(omx.y, q.y), rmax(omx.z, q.z));
+            omn = mk3(rmin(a.x, b.x), rmin(a.y, b.y), rmin(a.z, b.z));
+            omx = mk3(rmax(a.x, b.x), rmax(a.y, b.y), rmax(a.z, b.z));
+        }
+    }
+    float* o = reinterpret_cast<float*>(A.out + i);
+    o[0] = omn.x; o[1] = omn.y; o[2] = omn.z;
+    o[3] = omx.x; o[4] = omx.y; o[5] = omx.z;
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+cudaError_t launch_intersection(const narrow_args& A, bool full, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    if (full) k_intersection<true><<<grid_for(A.n, 128), 128, 0, st>>>(A);
+    else k_intersection<false><<<grid_for(A.n, 128), 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+cudaError_t launch_distance(const narrow_args& A, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    k_distance<<<grid_for(A.n, 128), 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+cudaError_t launch_time_of_impact(const narrow_args& A, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    k_time_of_impact<<<grid_for(A.n, 128), 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+cudaError_t launch_world_aabbs(const aabb_args& A, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    k_world_aabbs<<<grid_for(A.n, 256), 256, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+}  // namespace cb2

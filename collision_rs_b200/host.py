@@ -1,0 +1,353 @@
+"""Host-side mirror of the reference interface for the hot path, above the C ABI.
+
+Names follow the crate (GJK3, SweepAndPrune3, CollisionStrategy, Contact, Sphere, Cuboid,
+ConvexPolyhedron, Decomposed) so the parity tests read like the reference's own tests
+(gjk/mod.rs:622-826, sweep_prune.rs:279-371).  Everything computes on the GPU through
+libcollision_b200.so; there is no CPU implementation in this package.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi
+from .abi import (AABB_DT, COLLISION_ONLY, CONTACT_DT, CUBOID, FULL_RESOLUTION, POLYHEDRON,
+                  SHAPE_DT, SPHERE, XFORM_DT, Settings, ptr)
+
+
+class Cb2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cb2 error {code}: {msg}")
+        self.code = code
+
+
+class ReferencePanic(RuntimeError):
+    """The reference would have panicked (or hung) on this input; .status says where."""
+
+    def __init__(self, status):
+        names = {2: "Plane::from_points(..).unwrap() (simplex3d.rs:146)",
+                 3: "assert!(in_range(..)) (simplex3d.rs:150)",
+                 4: "inverse_transform_vector(..).unwrap() (util.rs:18)",
+                 5: "time-of-impact loop did not converge (gjk/mod.rs:204 has no cap)",
+                 6: "faces[0] on an empty polytope (epa3d.rs:138)",
+                 7: "device EPA scratch overflow"}
+        super().__init__(names.get(status, f"status {status}"))
+        self.status = status
+
+
+class Context:
+    """One cb2_ctx (one GPU).  Batch methods take numpy arrays (host path) or raw device
+    pointers (`*_dev`, for torch tensors: pass tensor.data_ptr())."""
+
+    def __init__(self, device=0):
+        self.lib = abi.load()
+        h = C.c_void_p()
+        rc = self.lib.cb2_create(int(device), C.byref(h))
+        if rc != 0:
+            raise Cb2Error(rc, self.lib.cb2_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self.n_shapes = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise Cb2Error(rc, self.lib.cb2_last_error(self.h).decode())
+
+    @property
+    def sm_count(self):
+        return int(self.lib.cb2_device_sm_count(self.h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.cb2_kernel_launches(self.h))
+
+    # ---- shape table --------------------------------------------------------------------
+    def upload_shapes(self, shapes, verts=None):
+        shapes = np.ascontiguousarray(shapes, SHAPE_DT)
+        nv = 0
+        if verts is not None:
+            verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+            nv = len(verts)
+        self._ck(self.lib.cb2_shapes_upload(self.h, ptr(shapes), len(shapes), ptr(verts), nv))
+        self.n_shapes = len(shapes)
+
+    # ---- narrow phase, host buffers --------------------------------------------------------
+    def intersection(self, strategy, l_shape, r_shape, l_t, r_t, settings=None, out=None,
+                     status=None):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT_DT) if out is None else out
+        status = np.zeros(n, np.uint8) if status is None else status
+        self._ck(self.lib.cb2_gjk3_intersection(
+            self.h, int(strategy), C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t),
+            ptr(r_t), n, ptr(out), ptr(status)))
+        return out, status
+
+    def distance(self, l_shape, r_shape, l_t, r_t, settings=None):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk3_distance(
+            self.h, C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t), ptr(r_t), n,
+            ptr(out), ptr(status)))
+        return out, status
+
+    def time_of_impact(self, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, settings=None,
+                       iter_cap=1024):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT_DT)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk3_time_of_impact(
+            self.h, C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t0), ptr(l_t1),
+            ptr(r_t0), ptr(r_t1), n, int(iter_cap), ptr(out), ptr(status)))
+        return out, status
+
+    def world_aabbs(self, shape, t):
+        n = len(shape)
+        out = np.zeros(n, AABB_DT)
+        self._ck(self.lib.cb2_world_aabbs(self.h, ptr(shape), ptr(t), n, ptr(out)))
+        return out
+
+    # ---- narrow phase, device pointers (ints) ------------------------------------------------
+    def intersection_dev(self, strategy, l_shape, r_shape, l_t, r_t, n, out, status, stream=0,
+                         settings=None):
+        settings = settings or Settings.default()
+        self._ck(self.lib.cb2_gjk3_intersection_dev(
+            self.h, int(strategy), C.byref(settings), l_shape, r_shape, l_t, r_t, int(n), out,
+            status, stream))
+
+    def distance_dev(self, l_shape, r_shape, l_t, r_t, n, out, status, stream=0, settings=None):
+        settings = settings or Settings.default()
+        self._ck(self.lib.cb2_gjk3_distance_dev(
+            self.h, C.byref(settings), l_shape, r_shape, l_t, r_t, int(n), out, status, stream))
+
+    def time_of_impact_dev(self, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, out, status,
+                           stream=0, settings=None, iter_cap=1024):
+        settings = settings or Settings.default()
+        self._ck(self.lib.cb2_gjk3_time_of_impact_dev(
+            self.h, C.byref(settings), l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, int(n),
+            int(iter_cap), out, status, stream))
+
+    def intersection_bodies_dev(self, strategy, body_shape, body_t, pair_body, n, out, status,
+                                stream=0, settings=None):
+        settings = settings or Settings.default()
+        self._ck(self.lib.cb2_gjk3_intersection_bodies_dev(
+            self.h, int(strategy), C.byref(settings), body_shape, body_t, pair_body, int(n), out,
+            status, stream))
+
+    def world_aabbs_dev(self, shape, t, n, out, stream=0):
+        self._ck(self.lib.cb2_world_aabbs_dev(self.h, shape, t, int(n), out, stream))
+
+    # ---- broad phase ------------------------------------------------------------------------------
+    def sap3(self, aabbs, axis=0, cap=None):
+        """Host-buffer SweepAndPrune3::find_collider_pairs. Returns (perm, pairs, axis_next)."""
+        aabbs = np.ascontiguousarray(aabbs, AABB_DT)
+        n = len(aabbs)
+        perm = np.zeros(max(n, 1), np.uint32)
+        cap = int(cap) if cap is not None else max(16, 8 * n)
+        while True:
+            pairs = np.zeros((max(cap, 1), 2), np.uint32)
+            ax = C.c_uint32(axis)
+            npairs = C.c_uint64(0)
+            rc = self.lib.cb2_sap3_find_collider_pairs(self.h, ptr(aabbs), n, C.byref(ax),
+                                                       ptr(perm), ptr(pairs), cap,
+                                                       C.byref(npairs))
+            if rc == abi.ERR_NOSPC:
+                cap = int(npairs.value)
+                continue
+            self._ck(rc)
+            return perm[:n], pairs[:npairs.value], ax.value
+
+    def sap3_dev(self, aabbs, n, axis, perm_out, pairs_out, cap, stream=0):
+        npairs = C.c_uint64(0)
+        rc = self.lib.cb2_sap3_find_collider_pairs_dev(self.h, aabbs, int(n), int(axis), perm_out,
+                                                       pairs_out, int(cap), C.byref(npairs), stream)
+        if rc == abi.ERR_NOSPC:
+            return rc, int(npairs.value)
+        self._ck(rc)
+        return 0, int(npairs.value)
+
+
+# ---- reference-shaped single-pair API (batch of 1; still the GPU) -----------------------------
+class CollisionStrategy:
+    """contact.rs:16-22"""
+    FullResolution = FULL_RESOLUTION
+    CollisionOnly = COLLISION_ONLY
+
+
+@dataclass
+class Contact:
+    """contact.rs:30-46"""
+    strategy: int
+    normal: tuple
+    penetration_depth: float
+    contact_point: tuple
+    time_of_impact: float
+
+    @staticmethod
+    def from_record(r):
+        return Contact(int(r["strategy"]), tuple(np.float32(x) for x in r["normal"]),
+                       np.float32(r["depth"]), tuple(np.float32(x) for x in r["point"]),
+                       np.float32(r["toi"]))
+
+
+@dataclass
+class Sphere:
+    """primitive/sphere.rs:14-24"""
+    radius: float
+
+
+@dataclass
+class Cuboid:
+    """primitive/cuboid.rs:18-42 (dim = full extents)"""
+    x: float
+    y: float
+    z: float
+
+
+class ConvexPolyhedron:
+    """primitive/polyhedron.rs:100-122, VertexOnly mode (ConvexPolyhedron::new)."""
+
+    def __init__(self, vertices):
+        self.vertices = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+
+
+@dataclass
+class Decomposed:
+    """cgmath Decomposed<Vector3<f32>, Quaternion<f32>>; rot = (s, x, y, z)."""
+    disp: tuple = (0.0, 0.0, 0.0)
+    rot: tuple = (1.0, 0.0, 0.0, 0.0)
+    scale: float = 1.0
+
+    def record(self):
+        t = np.zeros(1, XFORM_DT)
+        t["scale"] = self.scale
+        t["q"] = self.rot
+        t["d"] = self.disp
+        return t
+
+
+def _shape_table(prims):
+    shapes = np.zeros(len(prims), SHAPE_DT)
+    verts = []
+    off = 0
+    for i, p in enumerate(prims):
+        if isinstance(p, Sphere):
+            shapes[i]["kind"] = SPHERE
+            shapes[i]["p"] = (p.radius, 0, 0)
+        elif isinstance(p, Cuboid):
+            shapes[i]["kind"] = CUBOID
+            shapes[i]["p"] = (p.x, p.y, p.z)
+        elif isinstance(p, ConvexPolyhedron):
+            shapes[i]["kind"] = POLYHEDRON
+            shapes[i]["vtx_off"] = off
+            shapes[i]["vtx_cnt"] = len(p.vertices)
+            verts.append(p.vertices)
+            off += len(p.vertices)
+        else:
+            raise TypeError(f"unsupported primitive {type(p).__name__}")
+    v = np.concatenate(verts) if verts else None
+    return shapes, v
+
+
+_I0 = np.array([0], np.uint32)
+_I1 = np.array([1], np.uint32)
+
+
+class GJK3:
+    """GJK<SimplexProcessor3<f32>, EPA3<f32>, f32> (gjk/mod.rs:30,44-84), batch-of-1 wrappers."""
+
+    def __init__(self, ctx, distance_tolerance=1e-6, continuous_tolerance=1e-6,
+                 epa_tolerance=1e-5, max_iterations=100):
+        self.ctx = ctx
+        self.settings = Settings(np.float32(distance_tolerance), np.float32(continuous_tolerance),
+                                 np.float32(epa_tolerance), int(max_iterations))
+
+    @staticmethod
+    def new(ctx):
+        return GJK3(ctx)
+
+    @staticmethod
+    def new_with_settings(ctx, distance_tolerance, continuous_tolerance, epa_tolerance,
+                          max_iterations):
+        return GJK3(ctx, distance_tolerance, continuous_tolerance, epa_tolerance, max_iterations)
+
+    def _upload(self, left, right):
+        shapes, verts = _shape_table([left, right])
+        self.ctx.upload_shapes(shapes, verts)
+
+    def intersection(self, strategy, left, left_transform, right, right_transform):
+        """gjk/mod.rs:362-391 -> Option<Contact>"""
+        self._upload(left, right)
+        out, st = self.ctx.intersection(strategy, _I0, _I1, left_transform.record(),
+                                        right_transform.record(), self.settings)
+        if st[0] > 1:
+            raise ReferencePanic(int(st[0]))
+        return Contact.from_record(out[0]) if st[0] == 1 else None
+
+    def distance(self, left, left_transform, right, right_transform):
+        """gjk/mod.rs:271-321 -> Option<f32>"""
+        self._upload(left, right)
+        out, st = self.ctx.distance(_I0, _I1, left_transform.record(), right_transform.record(),
+                                    self.settings)
+        if st[0] > 1:
+            raise ReferencePanic(int(st[0]))
+        return np.float32(out[0]) if st[0] == 1 else None
+
+    def intersection_time_of_impact(self, left, left_range, right, right_range, iter_cap=1024):
+        """gjk/mod.rs:163-256; ranges are (start, end) pairs -> Option<Contact>"""
+        self._upload(left, right)
+        out, st = self.ctx.time_of_impact(_I0, _I1, left_range[0].record(), left_range[1].record(),
+                                          right_range[0].record(), right_range[1].record(),
+                                          self.settings, iter_cap)
+        if st[0] > 1:
+            raise ReferencePanic(int(st[0]))
+        return Contact.from_record(out[0]) if st[0] == 1 else None
+
+
+class SweepAndPrune3:
+    """SweepAndPrune<Variance3<f32, Aabb3<f32>>> (sweep_prune.rs:16, 34-136)."""
+
+    def __init__(self, ctx, sweep_axis=0):
+        self.ctx = ctx
+        self.sweep_axis = sweep_axis
+
+    @staticmethod
+    def new(ctx):
+        return SweepAndPrune3(ctx, 0)
+
+    @staticmethod
+    def with_sweep_axis(ctx, sweep_axis):
+        return SweepAndPrune3(ctx, sweep_axis)
+
+    def get_sweep_axis(self):
+        return self.sweep_axis
+
+    def find_collider_pairs(self, shapes, bound=lambda s: s):
+        """Sorts `shapes` (a list) in place like the reference and returns [(a, b), ...] over
+        the sorted list.  bound(shape) -> (min_xyz, max_xyz) plays HasBound::bound()."""
+        n = len(shapes)
+        if n <= 1:
+            return []
+        a = np.zeros(n, AABB_DT)
+        for i, s in enumerate(shapes):
+            mn, mx = bound(s)
+            a[i]["min"] = mn
+            a[i]["max"] = mx
+        perm, pairs, axis = self.ctx.sap3(a, self.sweep_axis)
+        shapes[:] = [shapes[int(i)] for i in perm]
+        self.sweep_axis = axis
+        return [(int(x), int(y)) for x, y in pairs]

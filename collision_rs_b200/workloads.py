@@ -1,0 +1,125 @@
+"""Synthetic inputs for the five BASELINE.json configs.
+
+Pure numpy, deterministic per seed; consumed identically by the oracle and by the
+CUDA path.  Rotation = normalised 4-vector of N(0,1); scale = 1; everything f32.
+"""
+import numpy as np
+
+from .abi import AABB_DT, CUBOID, POLYHEDRON, SHAPE_DT, SPHERE, XFORM_DT
+
+
+def random_xforms(rng, n, spread, scale=1.0):
+    t = np.zeros(n, XFORM_DT)
+    q = rng.standard_normal((n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    t["scale"] = scale
+    t["q"] = q.astype(np.float32)
+    t["d"] = rng.uniform(-spread, spread, (n, 3)).astype(np.float32)
+    return t
+
+
+def cuboid_shapes(rng, n, lo=0.5, hi=2.0):
+    s = np.zeros(n, SHAPE_DT)
+    s["kind"] = CUBOID
+    s["p"] = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    return s
+
+
+def mixed_shapes(rng, n):
+    """Sphere(r U[0.25,1]) w.p. 1/2 else Cuboid(U[0.5,2]^3)."""
+    s = cuboid_shapes(rng, n)
+    is_sphere = rng.random(n) < 0.5
+    r = rng.uniform(0.25, 1.0, n).astype(np.float32)
+    s["kind"][is_sphere] = SPHERE
+    s["p"][is_sphere, 0] = r[is_sphere]
+    s["p"][is_sphere, 1:] = 0
+    return s
+
+
+def cfg1_cuboid_pairs(n=10_000, seed=12345, spread=0.75):
+    """cfg 1: GJK3+EPA3 FullResolution on random Cuboid-Cuboid pairs (~91 % hits)."""
+    rng = np.random.default_rng(seed)
+    shapes = cuboid_shapes(rng, 2 * n)
+    l_shape = np.arange(0, n, dtype=np.uint32)
+    r_shape = np.arange(n, 2 * n, dtype=np.uint32)
+    return dict(shapes=shapes, verts=None, l_shape=l_shape, r_shape=r_shape,
+                l_t=random_xforms(rng, n, spread), r_t=random_xforms(rng, n, spread))
+
+
+def cfg2_mixed_pairs(n=1_000_000, seed=4242, spread=1.5):
+    """cfg 2: CollisionOnly + distance on mixed Sphere/Cuboid pairs (~25 % hits)."""
+    rng = np.random.default_rng(seed)
+    shapes = mixed_shapes(rng, 2 * n)
+    l_shape = np.arange(0, n, dtype=np.uint32)
+    r_shape = np.arange(n, 2 * n, dtype=np.uint32)
+    return dict(shapes=shapes, verts=None, l_shape=l_shape, r_shape=r_shape,
+                l_t=random_xforms(rng, n, spread), r_t=random_xforms(rng, n, spread))
+
+
+def polyhedron_table(n_shapes=4096, seed=777, sizes=(32, 64, 128, 256)):
+    """Shape table of convex polyhedra: V in sizes, vertices = unit-sphere directions x
+    per-axis radii U[0.5,1] (all points extreme => convex), VertexOnly mode."""
+    rng = np.random.default_rng(seed)
+    cnt = rng.choice(np.asarray(sizes, np.uint32), n_shapes).astype(np.uint32)
+    off = np.zeros(n_shapes, np.uint32)
+    off[1:] = np.cumsum(cnt)[:-1]
+    total = int(cnt.sum())
+    v = rng.standard_normal((total, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    radii = rng.uniform(0.5, 1.0, (n_shapes, 3))
+    v *= np.repeat(radii, cnt, axis=0)
+    shapes = np.zeros(n_shapes, SHAPE_DT)
+    shapes["kind"] = POLYHEDRON
+    shapes["vtx_off"] = off
+    shapes["vtx_cnt"] = cnt
+    return shapes, np.ascontiguousarray(v.astype(np.float32))
+
+
+def cfg3_polyhedron_pairs(n=4_000_000, seed=777, spread=0.75, n_shapes=4096,
+                          sizes=(32, 64, 128, 256), shard=0):
+    """cfg 3: GJK3+EPA3 on ConvexPolyhedron pairs (32-256 verts), ~80-90 % hits.
+    `shard` perturbs the pair stream (one shard per GPU) but not the shape table."""
+    shapes, verts = polyhedron_table(n_shapes, seed, sizes)
+    rng = np.random.default_rng([seed, 1, shard])
+    l_shape = rng.integers(0, n_shapes, n).astype(np.uint32)
+    r_shape = rng.integers(0, n_shapes, n).astype(np.uint32)
+    return dict(shapes=shapes, verts=verts, l_shape=l_shape, r_shape=r_shape,
+                l_t=random_xforms(rng, n, spread), r_t=random_xforms(rng, n, spread))
+
+
+def cfg4_aabbs(n=1_000_000, seed=2024, extent=200.0):
+    """cfg 4: centres U[0,extent)^3, half-extents U[0.5,1.5]^3; bodies are Cuboids with those
+    half-extents at identity rotation (so AABB == shape bound). extent scales as cbrt(n) to
+    keep density (and so ~4 pairs per box) when n is reduced for tests."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(0.0, extent, (n, 3)).astype(np.float32)
+    h = rng.uniform(0.5, 1.5, (n, 3)).astype(np.float32)
+    a = np.zeros(n, AABB_DT)
+    a["min"] = c - h
+    a["max"] = c + h
+    shapes = np.zeros(n, SHAPE_DT)
+    shapes["kind"] = CUBOID
+    shapes["p"] = (a["max"] - a["min"])
+    t = np.zeros(n, XFORM_DT)
+    t["scale"] = 1.0
+    t["q"][:, 0] = 1.0
+    t["d"] = c
+    return dict(aabbs=a, shapes=shapes, body_t=t)
+
+
+def cfg5_toi_pairs(n=1_000_000, seed=99, shard=0):
+    """cfg 5: continuous sweep on Cuboid pairs; start disp U[-3,3]^3, aimed end poses
+    (~75 % hits); rotation unchanged over the step."""
+    rng = np.random.default_rng([seed, shard])
+    shapes = cuboid_shapes(rng, 2 * n)
+    l_shape = np.arange(0, n, dtype=np.uint32)
+    r_shape = np.arange(n, 2 * n, dtype=np.uint32)
+    l0 = random_xforms(rng, n, 3.0)
+    r0 = random_xforms(rng, n, 3.0)
+    l1 = l0.copy()
+    r1 = r0.copy()
+    aim = (r0["d"] - l0["d"]) * rng.uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    l1["d"] = l0["d"] + aim + rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    r1["d"] = r0["d"] + rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    return dict(shapes=shapes, verts=None, l_shape=l_shape, r_shape=r_shape,
+                l_t0=l0, l_t1=l1, r_t0=r0, r_t1=r1)

@@ -53,8 +53,11 @@ typedef enum cb2_status {
                                    polyhedron.rs:394                             */
     CB2_NONCONVERGED = 5,       /* time-of-impact loop hit iter_cap; the reference
                                    loop (gjk/mod.rs:204) has no cap and would hang */
-    CB2_PANIC_EPA_EMPTY = 6     /* Polytope::closest_face_to_origin indexes
+    CB2_PANIC_EPA_EMPTY = 6,    /* Polytope::closest_face_to_origin indexes
                                    faces[0] of an empty Vec, epa/epa3d.rs:138    */
+    CB2_SCRATCH_OVERFLOW = 7    /* device EPA scratch exhausted (non-manifold horizon
+                                   grew the polytope past 2V-4 faces): result NOT
+                                   computed — loud, never a silent wrong answer  */
 } cb2_status;
 
 /* ---- CollisionStrategy (contact.rs:16-22); discriminants in declaration order */

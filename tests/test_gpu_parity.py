@@ -1,0 +1,342 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (north_star): Option/boolean outcomes and pair sets bit-exact; contact normal / depth /
+point / toi within 1e-4 relative.  The kernels follow the reference's unfused f32 operation
+order, so these tests assert the STRONGER property: every f32 bit-identical (NaN == NaN).
+"""
+import numpy as np
+import pytest
+
+from collision_rs_b200 import workloads as W
+from collision_rs_b200.host import (Cb2Error, CollisionStrategy, ConvexPolyhedron, Cuboid,
+                                    Decomposed, GJK3, ReferencePanic, Sphere, SweepAndPrune3)
+from helpers import transform_3d
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.float32(1.1920929e-7)
+
+
+def bits_equal(a, b):
+    """bitwise equality of f32 arrays, treating any NaN == any NaN"""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    same = a.view(np.uint32) == b.view(np.uint32)
+    same |= np.isnan(a) & np.isnan(b)
+    return same
+
+
+def assert_contacts_equal(got, gst, exp, est, what=""):
+    assert np.array_equal(gst, est), (
+        f"{what}: status mismatch at {np.nonzero(gst != est)[0][:10]}: "
+        f"gpu {gst[gst != est][:10]} oracle {est[gst != est][:10]}")
+    m = est == 1
+    for f in ("normal", "depth", "point", "toi"):
+        ok = bits_equal(got[f][m], exp[f][m])
+        assert ok.all(), f"{what}: {f} differs on {int((~ok).sum())} values"
+    assert np.array_equal(got["strategy"], exp["strategy"])
+
+
+def D(x, y, z, angle_z=0.0):
+    t = transform_3d(x, y, z, angle_z)
+    return Decomposed(tuple(t["d"][0]), tuple(t["q"][0]), float(t["scale"][0]))
+
+
+# ---- the reference's own 3-D tests, through the reference-shaped API on the GPU ----------------
+def test_gjk_exact_3d(ctx):  # gjk/mod.rs:634-642
+    gjk = GJK3.new(ctx)
+    shape, t = Cuboid(1, 1, 1), D(0, 0, 0)
+    assert gjk.intersection(CollisionStrategy.FullResolution, shape, t, shape, t) is not None
+    assert gjk.distance(shape, t, shape, t) is None
+
+
+def test_gjk_sphere(ctx):  # gjk/mod.rs:645-653
+    gjk = GJK3.new(ctx)
+    shape, t = Sphere(1.0), D(0, 0, 0)
+    assert gjk.intersection(CollisionStrategy.FullResolution, shape, t, shape, t) is not None
+    assert gjk.distance(shape, t, shape, t) is None
+
+
+def test_gjk_3d_hit(ctx):  # gjk/mod.rs:700-720
+    gjk = GJK3.new(ctx)
+    left, right = Cuboid(10, 10, 10), Cuboid(10, 10, 10)
+    c = gjk.intersection(CollisionStrategy.FullResolution, left, D(15, 0, 0), right, D(7, 2, 0))
+    assert c is not None
+    assert c.normal == (-1, 0, 0)
+    assert np.float32(2) - c.penetration_depth <= EPS
+    assert np.allclose(c.contact_point, (10, 1, 5), rtol=0, atol=5e-6)
+    c = gjk.intersection(CollisionStrategy.CollisionOnly, left, D(15, 0, 0), right, D(7, 2, 0))
+    assert c is not None and c.strategy == CollisionStrategy.CollisionOnly
+    assert c.normal == (0, 0, 0) and c.penetration_depth == 0
+    assert gjk.intersection(CollisionStrategy.FullResolution, left, D(15, 0, 0), right,
+                            D(-15, 0, 0)) is None
+
+
+def test_gjk_distance_3d(ctx):  # gjk/mod.rs:743-759
+    gjk = GJK3.new(ctx)
+    left, right = Cuboid(10, 10, 10), Cuboid(10, 10, 10)
+    assert gjk.distance(left, D(15, 0, 0), right, D(7, 2, 0)) is None
+    assert gjk.distance(left, D(15, 0, 0), right, D(1, 0, 0)) == np.float32(4.0)
+
+
+def test_gjk_time_of_impact_3d(ctx):  # gjk/mod.rs:795-825
+    gjk = GJK3.new(ctx)
+    left, right = Cuboid(10, 11, 10), Cuboid(10, 15, 10)
+    c = gjk.intersection_time_of_impact(left, (D(0, 0, 0), D(30, 0, 0)), right,
+                                        (D(15, 0, 0), D(15, 0, 0)))
+    assert c is not None
+    assert abs(c.time_of_impact - np.float32(0.1666667)) <= 2 * EPS
+    assert c.normal == (-1, 0, 0)
+    assert np.float32(0) - c.penetration_depth <= EPS
+    assert c.contact_point == (10, 0, 0)
+    assert gjk.intersection_time_of_impact(left, (D(0, 0, 0), D(0, 0, 0)), right,
+                                           (D(15, 0, 0), D(15, 0, 0))) is None
+
+
+def test_polyhedron_pair_single(ctx, oracle):
+    # a tetrahedron against a cuboid through the single-pair API
+    gjk = GJK3.new(ctx)
+    tet = ConvexPolyhedron([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, 0]])
+    c = gjk.intersection(CollisionStrategy.FullResolution, tet, D(0.2, 0.1, 0.0, 0.3),
+                         Cuboid(1, 1, 1), D(0.5, 0.2, 0.1))
+    assert c is not None and c.penetration_depth > 0
+
+
+def test_sweep_prune_reference_tests(ctx):  # sweep_prune.rs:317-361 (z padded to (0,1))
+    def run(boxes):
+        sap = SweepAndPrune3.new(ctx)
+        items = [((x0, y0, 0), (x1, y1, 1)) for (x0, y0, x1, y1) in boxes]
+        return sap.find_collider_pairs(items), items, sap.get_sweep_axis()
+
+    assert run([(8, 8, 10, 11), (12, 13, 18, 18)])[0] == []
+    assert run([(12, 13, 18, 18), (8, 8, 10, 11)])[0] == []
+    assert run([(8, 8, 10, 11), (9, 10, 18, 18)])[0] == [(0, 1)]
+    pairs, items, axis = run([(9, 10, 18, 18), (8, 8, 10, 11)])
+    assert pairs == [(0, 1)] and axis == 0
+    assert items[0][0][0] == 8  # slice was re-sorted in place
+
+
+# ---- batch parity against the oracle -------------------------------------------------------------------
+def _upload(ctx, w):
+    ctx.upload_shapes(w["shapes"], w.get("verts"))
+
+
+@pytest.mark.parametrize("spread", [0.75, 1.5])
+def test_cfg1_cuboid_full_resolution(ctx, oracle, spread):
+    w = W.cfg1_cuboid_pairs(10_000, spread=spread)
+    _upload(ctx, w)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    exp, est = oracle.intersection(0, w["shapes"], None, *args, nthreads=8)
+    got, gst = ctx.intersection(0, *args)
+    assert_contacts_equal(got, gst, exp, est, "cfg1 FullResolution")
+    assert 0.2 < (est == 1).mean() < 0.99
+    exp, est = oracle.intersection(1, w["shapes"], None, *args, nthreads=8)
+    got, gst = ctx.intersection(1, *args)
+    assert_contacts_equal(got, gst, exp, est, "cfg1 CollisionOnly")
+
+
+def test_cfg2_mixed_collision_only_distance_full(ctx, oracle):
+    w = W.cfg2_mixed_pairs(60_000)
+    _upload(ctx, w)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    exp, est = oracle.intersection(1, w["shapes"], None, *args, nthreads=8)
+    got, gst = ctx.intersection(1, *args)
+    assert_contacts_equal(got, gst, exp, est, "cfg2 CollisionOnly")
+    ed, est = oracle.distance(w["shapes"], None, *args, nthreads=8)
+    gd, gst = ctx.distance(*args)
+    assert np.array_equal(gst, est), f"distance status differs on {(gst != est).sum()}"
+    assert bits_equal(gd[est == 1], ed[est == 1]).all()
+    assert set(np.unique(est)) >= {0, 1, 2, 3}  # the panic paths are exercised
+    # FullResolution on curved shapes: EPA runs to the 100-iteration cap (103 verts / 202 faces)
+    exp, est = oracle.intersection(0, w["shapes"], None, *args, nthreads=8)
+    got, gst = ctx.intersection(0, *args)
+    assert_contacts_equal(got, gst, exp, est, "cfg2 FullResolution")
+
+
+def test_cfg3_polyhedra_full_resolution(ctx, oracle):
+    w = W.cfg3_polyhedron_pairs(8_000, n_shapes=512)
+    _upload(ctx, w)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    exp, est = oracle.intersection(0, w["shapes"], w["verts"], *args, nthreads=8)
+    got, gst = ctx.intersection(0, *args)
+    assert_contacts_equal(got, gst, exp, est, "cfg3 FullResolution")
+    ed, est = oracle.distance(w["shapes"], w["verts"], *args, nthreads=8)
+    gd, gst = ctx.distance(*args)
+    assert np.array_equal(gst, est)
+    assert bits_equal(gd[est == 1], ed[est == 1]).all()
+
+
+def test_cfg3_odd_vertex_counts(ctx, oracle):
+    # ragged polyhedra: 1..70 vertices incl. counts that are not multiples of the sub-warp width
+    w = W.cfg3_polyhedron_pairs(4_000, n_shapes=256, seed=5,
+                                sizes=(1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 33, 63, 70))
+    _upload(ctx, w)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    exp, est = oracle.intersection(0, w["shapes"], w["verts"], *args, nthreads=8)
+    got, gst = ctx.intersection(0, *args)
+    assert_contacts_equal(got, gst, exp, est, "ragged polyhedra")
+
+
+def test_cfg5_time_of_impact(ctx, oracle):
+    w = W.cfg5_toi_pairs(40_000)
+    _upload(ctx, w)
+    args = (w["l_shape"], w["r_shape"], w["l_t0"], w["l_t1"], w["r_t0"], w["r_t1"])
+    exp, est = oracle.time_of_impact(w["shapes"], None, *args, iter_cap=256, nthreads=8)
+    got, gst = ctx.time_of_impact(*args, iter_cap=256)
+    assert_contacts_equal(got, gst, exp, est, "cfg5 TOI")
+    assert (est == 5).sum() > 0  # NONCONVERGED limit cycles exist in this sample
+
+
+def test_mixed_toi_with_spheres(ctx, oracle):
+    w = W.cfg2_mixed_pairs(20_000, seed=7, spread=2.5)
+    _upload(ctx, w)
+    rng = np.random.default_rng(8)
+    l1, r1 = w["l_t"].copy(), w["r_t"].copy()
+    l1["d"] += (w["r_t"]["d"] - w["l_t"]["d"]) * rng.uniform(0.5, 1.5, (len(l1), 1)).astype(np.float32)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], l1, w["r_t"], r1)
+    exp, est = oracle.time_of_impact(w["shapes"], None, *args, iter_cap=300, nthreads=8)
+    got, gst = ctx.time_of_impact(*args, iter_cap=300)
+    assert_contacts_equal(got, gst, exp, est, "mixed TOI")
+
+
+def test_non_unit_scale_and_zero_scale(ctx, oracle):
+    w = W.cfg2_mixed_pairs(20_000, seed=11, spread=1.0)
+    rng = np.random.default_rng(12)
+    w["l_t"]["scale"] = rng.uniform(0.3, 2.0, len(w["l_t"])).astype(np.float32)
+    w["r_t"]["scale"] = rng.uniform(0.3, 2.0, len(w["r_t"])).astype(np.float32)
+    w["r_t"]["scale"][::97] = 0.0          # inverse_transform_vector(..).unwrap() panics
+    w["l_t"]["scale"][5::193] = 1e-8       # |scale| <= f32::EPSILON also counts as zero
+    w["l_t"]["scale"][7::211] = -1.5       # negative scale is legal
+    _upload(ctx, w)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    exp, est = oracle.intersection(0, w["shapes"], None, *args, nthreads=8)
+    got, gst = ctx.intersection(0, *args)
+    assert_contacts_equal(got, gst, exp, est, "scaled FullResolution")
+    assert (est == 4).sum() > 100
+    ed, est = oracle.distance(w["shapes"], None, *args, nthreads=8)
+    gd, gst = ctx.distance(*args)
+    assert np.array_equal(gst, est)
+    assert bits_equal(gd[est == 1], ed[est == 1]).all()
+
+
+def test_settings_are_honoured(ctx, oracle):
+    from collision_rs_b200.abi import Settings as S
+    from oracle.binding import Settings as OS
+    w = W.cfg2_mixed_pairs(10_000, seed=21)
+    _upload(ctx, w)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    for (dt, ct, et, mi) in [(1e-3, 1e-3, 1e-2, 7), (1e-6, 1e-6, 1e-5, 1), (1e-6, 1e-6, 1e-5, 0)]:
+        exp, est = oracle.intersection(0, w["shapes"], None, *args, settings=OS(dt, ct, et, mi),
+                                       nthreads=8)
+        got, gst = ctx.intersection(0, *args, settings=S(dt, ct, et, mi))
+        assert_contacts_equal(got, gst, exp, est, f"settings {mi}")
+        ed, est = oracle.distance(w["shapes"], None, *args, settings=OS(dt, ct, et, mi), nthreads=8)
+        gd, gst = ctx.distance(*args, settings=S(dt, ct, et, mi))
+        assert np.array_equal(gst, est) and bits_equal(gd[est == 1], ed[est == 1]).all()
+    with pytest.raises(Cb2Error) as e:
+        ctx.intersection(0, *args, settings=S(1e-6, 1e-6, 1e-5, 101))
+    assert e.value.code == -5
+
+
+def test_hazard_vectors(ctx, oracle):
+    # Appendix B vectors: the GPU must classify them exactly like the oracle
+    import test_oracle_hazards as H
+    for c in H.B1:
+        shapes = np.concatenate([H.cuboid(*H.dims(c["ld"])), H.cuboid(*H.dims(c["rd"]))])
+        ctx.upload_shapes(shapes)
+        out, st = ctx.time_of_impact(H.I0, H.I1, H.xf(c["l0"], c["lq"]), H.xf(c["l1"], c["lq"]),
+                                     H.xf(c["r0"], c["rq"]), H.xf(c["r1"], c["rq"]), iter_cap=500)
+        assert st[0] == 5
+    gjk = GJK3.new(ctx)
+    with pytest.raises(ReferencePanic) as e:
+        gjk.distance(Sphere(float.fromhex("0x1.b38cfap-1")),
+                     Decomposed(tuple(float.fromhex(x) for x in
+                                      ["0x1.eeb542p-1", "-0x1.39f1bep-1", "0x1.5da646p-1"]),
+                                tuple(float.fromhex(x) for x in
+                                      ["-0x1.1937eap-1", "0x1.6e74c0p-2", "0x1.620826p-4",
+                                       "-0x1.80186cp-1"])),
+                     Sphere(float.fromhex("0x1.a94cf4p-1")),
+                     Decomposed(tuple(float.fromhex(x) for x in
+                                      ["0x1.19c170p-3", "-0x1.45ed10p-2", "0x1.25f46cp+0"]),
+                                tuple(float.fromhex(x) for x in
+                                      ["0x1.0b81a6p-2", "-0x1.2b66e8p-1", "0x1.6d93c8p-1",
+                                       "0x1.21975ep-2"])))
+    assert e.value.status == 3
+
+
+def test_empty_and_tiny_batches(ctx):
+    w = W.cfg1_cuboid_pairs(3)
+    _upload(ctx, w)
+    z32 = np.zeros(0, np.uint32)
+    out, st = ctx.intersection(0, z32, z32, w["l_t"][:0], w["r_t"][:0])
+    assert len(out) == 0 and len(st) == 0
+    out, st = ctx.intersection(0, w["l_shape"][:1], w["r_shape"][:1], w["l_t"][:1], w["r_t"][:1])
+    assert len(st) == 1
+    with pytest.raises(Cb2Error):
+        ctx.intersection(0, np.array([99], np.uint32), w["r_shape"][:1], w["l_t"][:1], w["r_t"][:1])
+
+
+def test_world_aabbs(ctx, oracle):
+    w = W.cfg3_polyhedron_pairs(5_000, n_shapes=128)
+    m = W.cfg2_mixed_pairs(5_000, seed=3)
+    # one table with all three kinds
+    shapes = np.concatenate([w["shapes"], m["shapes"][:5000]])
+    ctx.upload_shapes(shapes, w["verts"])
+    rng = np.random.default_rng(1)
+    idx = rng.integers(0, len(shapes), 20_000).astype(np.uint32)
+    t = W.random_xforms(rng, len(idx), 5.0)
+    t["scale"] = rng.uniform(0.5, 2.0, len(idx)).astype(np.float32)
+    exp = oracle.world_aabbs(shapes, w["verts"], idx, t, nthreads=8)
+    got = ctx.world_aabbs(idx, t)
+    assert bits_equal(got["min"], exp["min"]).all() and bits_equal(got["max"], exp["max"]).all()
+
+
+# ---- broad phase ----------------------------------------------------------------------------------------
+def _check_sap(ctx, oracle, boxes, axis):
+    perm_e, pairs_e, cnt, axis_e = oracle.sap3(boxes, axis=axis)
+    perm_g, pairs_g, axis_g = ctx.sap3(boxes, axis=axis)
+    assert np.array_equal(perm_g, perm_e)
+    assert len(pairs_g) == cnt
+    assert np.array_equal(pairs_g, pairs_e)  # same pairs in the same Vec order
+    assert axis_g == axis_e
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_sap_random_boxes(ctx, oracle, axis):
+    n = 30_000
+    w = W.cfg4_aabbs(n, extent=200.0 * (n / 1e6) ** (1 / 3))
+    _check_sap(ctx, oracle, w["aabbs"], axis)
+
+
+def test_sap_ties_signed_zero_and_wide_boxes(ctx, oracle):
+    rng = np.random.default_rng(3)
+    n = 5_000
+    w = W.cfg4_aabbs(n, seed=9, extent=40.0)
+    a = w["aabbs"]
+    # quantise so that many min (and min+max) keys tie -> exercises stability
+    a["min"] = np.round(a["min"])
+    a["max"] = np.round(a["max"]) + 1
+    a["min"][::7, 0] = -0.0
+    a["min"][3::7, 0] = 0.0
+    a["min"][::501] = -100.0   # a few boxes spanning the whole scene
+    a["max"][::501] = 100.0
+    a["max"][10::97] = a["min"][10::97]  # zero-width boxes (strict test rejects touching)
+    for axis in (0, 2):
+        _check_sap(ctx, oracle, a, axis)
+
+
+def test_sap_small_n(ctx, oracle):
+    w = W.cfg4_aabbs(64, extent=8.0)
+    for n in (0, 1, 2, 3, 33):
+        perm_g, pairs_g, axis_g = ctx.sap3(w["aabbs"][:n], axis=1)
+        perm_e, pairs_e, cnt, axis_e = oracle.sap3(w["aabbs"][:n], axis=1)
+        assert np.array_equal(perm_g, perm_e[:n]) and np.array_equal(pairs_g, pairs_e)
+        assert axis_g == axis_e == (1 if n <= 1 else 0)
+
+
+def test_sap_nan_is_rejected_loudly(ctx):
+    w = W.cfg4_aabbs(100, extent=10.0)
+    w["aabbs"]["min"][5, 0] = np.nan
+    with pytest.raises(Cb2Error) as e:
+        ctx.sap3(w["aabbs"], axis=0)
+    assert e.value.code == -6
