@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 collision pipeline.
+
+Metric (BASELINE.json): "GJK3+EPA3 contact pairs/s at 1/2/4/8 B200 vs host CPU; SAP AABBs/s".
+Workload at every N: BASELINE.json configs[2], "GJK3+EPA3 on 4M ConvexPolyhedron pairs
+(32-256 verts each)" — the config the pairs/s metric is quoted on at 1/2/4/8 GPUs.  A step is
+one GJK3::intersection(FullResolution) pass over one batch of 4M pairs per GPU (weak scaling:
+every rank owns its own 4M-pair shard; the shape table is broadcast once over NCCL; no
+data-path collective).  Other configs (cfg1 cuboids, cfg2 mixed, cfg4 SAP, cfg5 TOI) are
+reported in the `extra` object of the same JSON line (N=1 only).
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+  python bench.py --impl reference ...                      (CPU oracle port, all host threads)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GJK3+EPA3 FullResolution contact pairs/s"
+UNIT = "pairs/s"
+WORKLOAD = "cfg3: GJK3+EPA3 FullResolution on ConvexPolyhedron pairs (32-256 verts), 4096-shape table"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=4_000_000, help="pairs per GPU per step")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs")
+    ap.add_argument("--cpu-sample", type=int, default=150_000)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops_per_pair(w, sample=20_000):
+    """Algorithmic flops = f32 + - * / sqrt the REFERENCE algorithm executes (oracle op counter),
+    measured on a prefix sample of this very workload."""
+    from oracle.binding import Oracle
+    oc = Oracle(count_ops=True)
+    m = min(sample, len(w["l_shape"]))
+    oc.ops_reset()
+    oc.intersection(0, w["shapes"], w["verts"], w["l_shape"][:m], w["r_shape"][:m],
+                    w["l_t"][:m], w["r_t"][:m], nthreads=1)
+    return oc.ops_reset() / m
+
+
+def cpu_baseline(w, sample, threads=None):
+    from oracle.binding import Oracle
+    o = Oracle()
+    threads = threads or o.hw_threads()
+    m = min(sample, len(w["l_shape"]))
+    args = (0, w["shapes"], w["verts"], w["l_shape"][:m], w["r_shape"][:m], w["l_t"][:m],
+            w["r_t"][:m])
+    o.intersection(0, w["shapes"], w["verts"], w["l_shape"][:2048], w["r_shape"][:2048],
+                   w["l_t"][:2048], w["r_t"][:2048], nthreads=threads)  # warm-up
+    t = time.perf_counter()
+    o.intersection(*args, nthreads=threads)
+    dt = time.perf_counter() - t
+    return {"value": m / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {m} pairs of the same workload, oracle port "
+                      f"(g++ -O2 -ffp-contract=off), {threads} threads, {dt:.2f} s"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(a):
+    """--impl reference: the reference algorithm's CPU path (the oracle port: the Rust crate
+    cannot be built here or on the box — no rustc, cgmath not vendored) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from collision_rs_b200 import workloads as W
+    from oracle.binding import Oracle
+    o = Oracle()
+    threads = o.hw_threads()
+    m = min(a.cpu_sample, a.pairs)
+    w = W.cfg3_polyhedron_pairs(m)
+    args = (0, w["shapes"], w["verts"], w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    for _ in range(a.warmup):
+        o.intersection(0, w["shapes"], w["verts"], w["l_shape"][:4096], w["r_shape"][:4096],
+                       w["l_t"][:4096], w["r_t"][:4096], nthreads=threads)
+    t = time.perf_counter()
+    for _ in range(a.steps):
+        o.intersection(*args, nthreads=threads)
+    dt = time.perf_counter() - t
+    v = m * a.steps / dt
+    sample = (f"{m} pairs/step of the same workload (bounded sample of the 4M-pair batch), "
+              f"oracle port on {threads} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "pairs_per_step": m},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    from collision_rs_b200 import workloads as W
+    from collision_rs_b200.abi import CONTACT_DT, SHAPE_DT, XFORM_DT
+    from collision_rs_b200.host import Context
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback "
+                         "(use --impl reference for the CPU oracle port)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Context(local)
+
+    # ---- inputs: shape table from rank 0 over NCCL, pair shard per rank --------------------
+    n = a.pairs
+    w = W.cfg3_polyhedron_pairs(n, shard=rank)
+    shapes, verts = w["shapes"], w["verts"]
+    if world > 1:
+        ts = torch.from_numpy(shapes.view(np.uint8).reshape(-1).copy()).to(dev)
+        tv = torch.from_numpy(verts.reshape(-1).copy()).to(dev)
+        if rank != 0:
+            ts.zero_()
+            tv.zero_()
+        dist.broadcast(ts, 0)
+        dist.broadcast(tv, 0)
+        shapes = ts.cpu().numpy().view(SHAPE_DT)
+        verts = tv.cpu().numpy().reshape(-1, 3)
+        assert np.array_equal(shapes, w["shapes"]) and np.array_equal(verts, w["verts"])
+    ctx.upload_shapes(shapes, verts)
+
+    def pinned(arr):
+        t = torch.from_numpy(arr.view(np.uint8).reshape(-1)).pin_memory()
+        return t
+
+    h_in = {k: pinned(w[k]) for k in ("l_shape", "r_shape", "l_t", "r_t")}
+    d_in = {k: v.to(dev, non_blocking=True) for k, v in h_in.items()}
+    d_out = torch.empty(n * CONTACT_DT.itemsize, dtype=torch.uint8, device=dev)
+    d_st = torch.empty(n, dtype=torch.uint8, device=dev)
+    h_out = torch.empty(n * CONTACT_DT.itemsize, dtype=torch.uint8).pin_memory()
+    h_st = torch.empty(n, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+
+    def step_dev():
+        ctx.intersection_dev(0, d_in["l_shape"].data_ptr(), d_in["r_shape"].data_ptr(),
+                             d_in["l_t"].data_ptr(), d_in["r_t"].data_ptr(), n,
+                             d_out.data_ptr(), d_st.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ------------------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.kernel_launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    ev[0].record(stream)
+    for k in range(a.steps):
+        step_dev()
+        ev[k + 1].record(stream)
+    barrier()
+    launches = ctx.kernel_launches - l0
+    ms_total = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    value = n * world * a.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI (pinned host in, pinned host out) -----------------
+    from collision_rs_b200.abi import Settings
+    W_SETTINGS = Settings.default()
+
+    def step_e2e():
+        ctx._ck(ctx.lib.cb2_gjk3_intersection(
+            ctx.h, 0, C.byref(W_SETTINGS), h_in["l_shape"].data_ptr(), h_in["r_shape"].data_ptr(),
+            h_in["l_t"].data_ptr(), h_in["r_t"].data_ptr(), n, h_out.data_ptr(), h_st.data_ptr()))
+
+    step_e2e()
+    barrier()
+    e2e_steps = max(2, min(a.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * e2e_steps / float(t_e.item())
+    h2d = sum(int(v.numel()) for v in h_in.values())
+    d2h = int(h_out.numel() + h_st.numel())
+    # the host path and the device path must agree bit for bit
+    assert torch.equal(h_st, d_st.cpu()) and torch.equal(h_out, d_out.cpu())
+    hits = int((h_st == 1).sum())
+    bad = int((h_st > 1).sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    flops_pair = algorithmic_flops_per_pair(w)
+    kernel_ms = float(np.mean(per_step))  # one intersection pass per step; events bracket it
+    achieved = flops_pair * n / (kernel_ms * 1e-3) / 1e12
+    peak_lib = C.CDLL(os.path.join(ROOT, "collision_rs_b200", "libcb2_peak.so"))
+    peak_lib.cb2_peak_fp32_tflops.restype = C.c_double
+    fp32_peak = float(peak_lib.cb2_peak_fp32_tflops(local))
+    hbm_peak, hbm_src = peaks()
+    bytes_pair = 2 * 4 + 2 * XFORM_DT.itemsize + CONTACT_DT.itemsize + 1
+    hbm_achieved = bytes_pair * n / (kernel_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+        "peak_source": "FFMA micro-benchmark measured in this run (libcb2_peak.so); "
+                       "parity forbids FMA so the reachable ceiling is peak/2",
+        "frac_of_unfused_peak": 2 * achieved / fp32_peak if fp32_peak > 0 else None,
+        "algorithmic_flops_per_pair": flops_pair, "kernel_ms": kernel_ms,
+        "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_achieved / hbm_peak, "bytes_per_pair": bytes_pair,
+                "peak_source": hbm_src},
+    }
+    cpu = cpu_baseline(w, a.cpu_sample)
+
+    extra = {}
+    if not a.no_extra and world == 1:
+        extra = extras(ctx, torch, dev, stream)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": n, "seed": 777,
+                   "hit_fraction": hits / n, "non_ok_status": bad,
+                   "l2": "inputs+outputs 436 MB per step > 126 MB L2 (no flush needed)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "how": "cb2_gjk3_intersection on pinned host buffers: chunked H2D, kernel, D2H "
+                       "inside the timed call"},
+        "gpu_launches": launches,
+        "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(ctx, torch, dev, stream):
+    """Secondary configs (N=1): cfg1 cuboids, cfg2 mixed, cfg4 SAP (+ chained narrow phase), cfg5 TOI.
+    Device-resident, CUDA-event timed, 3 warm-ups + 5 timed passes each."""
+    from collision_rs_b200 import workloads as W
+    from collision_rs_b200.abi import AABB_DT, CONTACT_DT
+
+    def dv(arr):
+        return torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(dev)
+
+    def timed(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    res = {}
+    s = stream.cuda_stream
+    # cfg1 at GPU scale: 4M cuboid pairs, FullResolution
+    n = 4_000_000
+    w = W.cfg1_cuboid_pairs(n)
+    ctx.upload_shapes(w["shapes"])
+    d = {k: dv(w[k]) for k in ("l_shape", "r_shape", "l_t", "r_t")}
+    out = torch.empty(n * CONTACT_DT.itemsize, dtype=torch.uint8, device=dev)
+    st = torch.empty(n, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: ctx.intersection_dev(0, d["l_shape"].data_ptr(), d["r_shape"].data_ptr(),
+                                            d["l_t"].data_ptr(), d["r_t"].data_ptr(), n,
+                                            out.data_ptr(), st.data_ptr(), s))
+    res["cfg1_cuboid_full_resolution"] = {"pairs": n, "ms": ms, "pairs_per_s": n / ms * 1e3}
+    # cfg2: 1M mixed, CollisionOnly + distance
+    n = 1_000_000
+    w = W.cfg2_mixed_pairs(n)
+    ctx.upload_shapes(w["shapes"])
+    d = {k: dv(w[k]) for k in ("l_shape", "r_shape", "l_t", "r_t")}
+    dist_out = torch.empty(n, dtype=torch.float32, device=dev)
+    ms_c = timed(lambda: ctx.intersection_dev(1, d["l_shape"].data_ptr(), d["r_shape"].data_ptr(),
+                                              d["l_t"].data_ptr(), d["r_t"].data_ptr(), n,
+                                              out.data_ptr(), st.data_ptr(), s))
+    ms_d = timed(lambda: ctx.distance_dev(d["l_shape"].data_ptr(), d["r_shape"].data_ptr(),
+                                          d["l_t"].data_ptr(), d["r_t"].data_ptr(), n,
+                                          dist_out.data_ptr(), st.data_ptr(), s))
+    res["cfg2_mixed_collision_only"] = {"pairs": n, "ms": ms_c, "pairs_per_s": n / ms_c * 1e3}
+    res["cfg2_mixed_distance"] = {"pairs": n, "ms": ms_d, "pairs_per_s": n / ms_d * 1e3}
+    # cfg4: SAP on 1M AABBs feeding the narrow phase
+    n = 1_000_000
+    w = W.cfg4_aabbs(n)
+    ctx.upload_shapes(w["shapes"])
+    boxes = dv(w["aabbs"])
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    cap = 8 * n
+    pairs = torch.empty(2 * cap, dtype=torch.int32, device=dev)
+    box_sorted = torch.empty_like(boxes)
+    np_holder = {}
+
+    def sap():
+        rc, cnt = ctx.sap3_dev(boxes.data_ptr(), n, 0, perm.data_ptr(), pairs.data_ptr(), cap, s)
+        np_holder["n"] = cnt
+        assert rc == 0
+
+    ms_sap = timed(sap)
+    npairs = np_holder["n"]
+    hbm_peak, _ = peaks()
+    alg_bytes = 24 * n + 4 * n + 8 * npairs
+    res["cfg4_sap"] = {"aabbs": n, "pairs": npairs, "ms": ms_sap, "aabbs_per_s": n / ms_sap * 1e3,
+                       "algorithmic_bytes": alg_bytes,
+                       "hbm_frac": alg_bytes / (ms_sap * 1e-3) / 1e9 / hbm_peak}
+    body_shape = dv(np.arange(n, dtype=np.uint32))
+    body_t = dv(w["body_t"])
+    # bodies indexed in SORTED order: permute shapes / transforms once, like the reference's slice
+    p64 = perm.long()
+    body_shape_s = body_shape.view(torch.int32)[p64].contiguous()
+    body_t_s = body_t.view(-1, 32)[p64].contiguous()
+    outp = torch.empty(npairs * CONTACT_DT.itemsize, dtype=torch.uint8, device=dev)
+    stp = torch.empty(npairs, dtype=torch.uint8, device=dev)
+    ms_np = timed(lambda: ctx.intersection_bodies_dev(0, body_shape_s.data_ptr(),
+                                                      body_t_s.data_ptr(), pairs.data_ptr(),
+                                                      npairs, outp.data_ptr(), stp.data_ptr(), s))
+    res["cfg4_narrow_on_sap_pairs"] = {"pairs": npairs, "ms": ms_np,
+                                       "pairs_per_s": npairs / ms_np * 1e3,
+                                       "contacts": int((stp == 1).sum())}
+    # cfg5: TOI, 8M cuboid pairs on one GPU (64M over 8)
+    n = 8_000_000
+    w = W.cfg5_toi_pairs(n)
+    ctx.upload_shapes(w["shapes"])
+    d = {k: dv(w[k]) for k in ("l_shape", "r_shape", "l_t0", "l_t1", "r_t0", "r_t1")}
+    out = torch.empty(n * CONTACT_DT.itemsize, dtype=torch.uint8, device=dev)
+    st = torch.empty(n, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: ctx.time_of_impact_dev(d["l_shape"].data_ptr(), d["r_shape"].data_ptr(),
+                                              d["l_t0"].data_ptr(), d["l_t1"].data_ptr(),
+                                              d["r_t0"].data_ptr(), d["r_t1"].data_ptr(), n,
+                                              out.data_ptr(), st.data_ptr(), s), reps=3, warm=1)
+    res["cfg5_time_of_impact"] = {"pairs": n, "ms": ms, "pairs_per_s": n / ms * 1e3,
+                                  "nonconverged": int((st == 5).sum()), "iter_cap": 1024}
+    return res
+
+
+if __name__ == "__main__":
+    main()

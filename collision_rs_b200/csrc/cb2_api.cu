@@ -35,6 +35,11 @@ struct cb2_ctx {
     sap_workspace* sap = nullptr;
     void* d_misc = nullptr;  // host-API SAP / AABB buffers
     size_t misc_cap = 0;
+    // classified (polyhedron) narrow phase workspaces: [0..NS) follow the host-API streams,
+    // device-API calls use ws[0] (one submitting stream at a time per ctx)
+    narrow_ws ws[NS] = {};
+    uint64_t ws_cap[NS] = {0, 0};
+    bool has_poly = false;
 };
 
 static std::string g_create_err;
@@ -118,6 +123,12 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_shapes) cudaFree(c->d_shapes);
     if (c->d_verts) cudaFree(c->d_verts);
     if (c->d_misc) cudaFree(c->d_misc);
+    for (int i = 0; i < cb2_ctx::NS; ++i) {
+        if (c->ws[i].cls) cudaFree(c->ws[i].cls);
+        if (c->ws[i].perm) cudaFree(c->ws[i].perm);
+        if (c->ws[i].counts) cudaFree(c->ws[i].counts);
+        if (c->ws[i].spill) cudaFree(c->ws[i].spill);
+    }
     sap_workspace_destroy(c->sap);
     delete c;
 }
@@ -169,6 +180,8 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
         CK(c, cudaMemcpy(c->d_verts, hv.data(), sizeof(float4) * n_verts, cudaMemcpyHostToDevice));
     c->n_shapes = n_shapes;
     c->n_verts = n_verts;
+    c->has_poly = false;
+    for (uint32_t i = 0; i < n_shapes; ++i) c->has_poly |= (shapes[i].kind == CB2_POLYHEDRON);
     return CB2_OK;
 }
 
@@ -184,10 +197,41 @@ static int check_settings(cb2_ctx* c, const cb2_settings* s) {
     return CB2_OK;
 }
 
-static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, cudaStream_t st) {
+static int ensure_ws(cb2_ctx* c, int slot, uint64_t n) {
+    narrow_ws& w = c->ws[slot];
+    if (!w.counts) CK(c, cudaMalloc(&w.counts, sizeof(uint32_t) * 3 * NUM_CLASSES));
+    if (!w.spill) CK(c, cudaMalloc(&w.spill, coop_spill_bytes(c->sm_count)));
+    if (c->ws_cap[slot] < n) {
+        if (w.cls) cudaFree(w.cls);
+        if (w.perm) cudaFree(w.perm);
+        w.cls = nullptr;
+        w.perm = nullptr;
+        c->ws_cap[slot] = 0;
+        CK(c, cudaMalloc(&w.cls, n));
+        CK(c, cudaMalloc(&w.perm, n * sizeof(uint32_t)));
+        c->ws_cap[slot] = n;
+    }
+    return CB2_OK;
+}
+
+static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, cudaStream_t st,
+                     int ws_slot = 0) {
     A.shapes = c->d_shapes;
     A.verts = c->d_verts;
     cudaError_t e;
+    if (op == OP_INTERSECTION && c->has_poly) {
+        // polyhedra in the table: bucket pairs by size class, sub-warp cooperative kernels
+        if (A.n > 0xFFFFFFFFull) return fail(c, CB2_ERR_ARG, "more than 2^32-1 pairs in one batch");
+        int rc = ensure_ws(c, ws_slot, A.n);
+        if (rc) return rc;
+        e = launch_intersection_classified(A, strategy == CB2_FULL_RESOLUTION, c->ws[ws_slot],
+                                           c->sm_count, st, &c->launches);
+        if (e != cudaSuccess) {
+            c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
+            return CB2_ERR_CUDA;
+        }
+        return CB2_OK;
+    }
     if (op == OP_INTERSECTION) e = launch_intersection(A, strategy == CB2_FULL_RESOLUTION, st);
     else if (op == OP_DISTANCE) e = launch_distance(A, st);
     else e = launch_time_of_impact(A, st);
@@ -304,7 +348,7 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
         A.out_contact = reinterpret_cast<cb2_contact*>(base + o_out);
         A.out_distance = reinterpret_cast<float*>(base + o_out);
         A.out_status = reinterpret_cast<uint8_t*>(base + o_st);
-        rc = launch_op(c, op, strategy, A, st);
+        rc = launch_op(c, op, strategy, A, st, s);
         if (rc) return rc;
         if (op == OP_DISTANCE)
             CK(c, cudaMemcpyAsync(out_d + b, base + o_out, m * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -8,6 +8,7 @@
 // symmetry of IEEE rounding — all while producing the same bits as the reference.
 #pragma once
 #include "cb2_math.cuh"
+#include "../../include/collision_b200.h"
 
 namespace cb2 {
 
@@ -277,6 +278,35 @@ CB2_DI f3 closest_point_to_origin(simplex<false>& s, uint8_t& status) {
     if (s.n == 1) return s.v[0];
     if (s.n == 2) return closest_point_on_edge_to_origin(s.v[1], s.v[0]);
     return closest_point_on_face(s.v[2], s.v[1], s.v[0], d, status);
+}
+
+// ---- output record ----------------------------------------------------------------------------
+struct contact_out {
+    f3 normal;
+    float depth;
+    f3 point;
+    float toi;
+};
+CB2_DI contact_out zero_contact() {
+    contact_out c;
+    c.normal = zero3();
+    c.depth = 0.0f;
+    c.point = zero3();
+    c.toi = 0.0f;
+    return c;
+}
+CB2_DI void store_contact(cb2_contact* __restrict__ out, uint64_t i, uint32_t strategy,
+                          const contact_out& c) {
+    float* o = reinterpret_cast<float*>(out + i);
+    o[0] = __uint_as_float(strategy);
+    o[1] = c.normal.x;
+    o[2] = c.normal.y;
+    o[3] = c.normal.z;
+    o[4] = c.depth;
+    o[5] = c.point.x;
+    o[6] = c.point.y;
+    o[7] = c.point.z;
+    o[8] = c.toi;
 }
 
 }  // namespace cb2

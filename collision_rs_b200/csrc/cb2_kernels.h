@@ -20,6 +20,8 @@ struct narrow_args {
     const float4* l_t1;       // end poses (time of impact only)
     const float4* r_t1;
     const uint32_t* pair_body;  // optional 2 x n body indices (then l_t == r_t == body_t)
+    const uint32_t* perm;       // optional: process pairs perm[0 .. *dev_count) (classified batches)
+    const uint32_t* dev_count;
     uint64_t n;
     cb2_settings settings;
     uint32_t iter_cap;
@@ -38,6 +40,18 @@ struct aabb_args {
 };
 
 cudaError_t launch_intersection(const narrow_args& A, bool full, cudaStream_t st);
+
+// ---- classified (polyhedron-aware) intersection, cb2_poly.cu ----------------------------------
+constexpr int NUM_CLASSES = 7;
+struct narrow_ws {       // per-stream device workspace, owned by the ctx
+    uint8_t* cls;        // n bytes
+    uint32_t* perm;      // n words
+    uint32_t* counts;    // 3 * NUM_CLASSES words: counts | scatter cursors | queue cursors
+    float* spill;        // coop_spill_bytes()
+};
+size_t coop_spill_bytes(int sm_count);
+cudaError_t launch_intersection_classified(const narrow_args& A, bool full, const narrow_ws& W,
+                                           int sm_count, cudaStream_t st, uint64_t* launches);
 cudaError_t launch_distance(const narrow_args& A, cudaStream_t st);
 cudaError_t launch_time_of_impact(const narrow_args& A, cudaStream_t st);
 cudaError_t launch_world_aabbs(const aabb_args& A, cudaStream_t st);

@@ -87,13 +87,6 @@ CB2_DI void face_new(polytope& P, int slot, uint32_t a, uint32_t b, uint32_t c) 
     P.fidx[slot] = a | (b << 8) | (c << 16);
 }
 
-struct contact_out {
-    f3 normal;
-    float depth;
-    f3 point;
-    float toi;
-};
-
 // EPA3::process, epa3d.rs:27-65 (+ Polytope::add :147-175, contact :84-114)
 __device__ __noinline__ uint8_t epa_process(const pair_in& p, const simplex<true>& s, float tol,
                                             uint32_t max_iterations, contact_out& out) {
@@ -185,28 +178,6 @@ __device__ __noinline__ uint8_t epa_process(const pair_in& p, const simplex<true
     }
 }
 
-CB2_DI void store_contact(cb2_contact* __restrict__ out, uint64_t i, uint32_t strategy,
-                          const contact_out& c) {
-    float* o = reinterpret_cast<float*>(out + i);
-    o[0] = __uint_as_float(strategy);
-    o[1] = c.normal.x;
-    o[2] = c.normal.y;
-    o[3] = c.normal.z;
-    o[4] = c.depth;
-    o[5] = c.point.x;
-    o[6] = c.point.y;
-    o[7] = c.point.z;
-    o[8] = c.toi;
-}
-CB2_DI contact_out zero_contact() {
-    contact_out c;
-    c.normal = zero3();
-    c.depth = 0.0f;
-    c.point = zero3();
-    c.toi = 0.0f;
-    return c;
-}
-
 CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const float4* rt,
                       pair_in& p) {
     uint32_t li, ri;
@@ -234,8 +205,12 @@ CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const 
 // ---- kernels -----------------------------------------------------------------------------------
 template <bool FULL>
 __global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
+    if (A.perm) {  // class-0 slice of a classified batch (cb2_poly.cu)
+        if (i >= __ldg(A.dev_count)) return;
+        i = __ldg(A.perm + i);
+    }
     pair_in p;
     contact_out c = zero_contact();
     uint8_t st = ST_NONE;

@@ -177,6 +177,27 @@ def test_cfg3_odd_vertex_counts(ctx, oracle):
     assert_contacts_equal(got, gst, exp, est, "ragged polyhedra")
 
 
+def test_mixed_table_all_classes(ctx, oracle):
+    """One shape table with spheres, cuboids and polyhedra of 4..1500 vertices: every size class
+    of the classified dispatch (thread-per-pair, staged sub-warp groups of 4/8/16, unstaged 32)."""
+    rng = np.random.default_rng(31)
+    ps, pv = W.polyhedron_table(96, seed=9, sizes=(4, 20, 40, 90, 200, 400, 700, 1500))
+    prim = W.mixed_shapes(rng, 64)
+    shapes = np.concatenate([ps, prim])
+    n = 6_000
+    l = rng.integers(0, len(shapes), n).astype(np.uint32)
+    r = rng.integers(0, len(shapes), n).astype(np.uint32)
+    lt, rt = W.random_xforms(rng, n, 0.8), W.random_xforms(rng, n, 0.8)
+    lt["scale"][::5] = rng.uniform(0.5, 1.5, len(lt["scale"][::5])).astype(np.float32)
+    rt["scale"][::131] = 0.0
+    ctx.upload_shapes(shapes, pv)
+    for strategy in (0, 1):
+        exp, est = oracle.intersection(strategy, shapes, pv, l, r, lt, rt, nthreads=8)
+        got, gst = ctx.intersection(strategy, l, r, lt, rt)
+        assert_contacts_equal(got, gst, exp, est, f"mixed table strategy {strategy}")
+    assert (est == 4).sum() > 0 and (est == 1).sum() > 1000
+
+
 def test_cfg5_time_of_impact(ctx, oracle):
     w = W.cfg5_toi_pairs(40_000)
     _upload(ctx, w)
