@@ -39,6 +39,7 @@ struct cb2_ctx {
     // device-API calls use ws[0] (one submitting stream at a time per ctx)
     narrow_ws ws[NS] = {};
     uint64_t ws_cap[NS] = {0, 0};
+    retry_ws retry[NS] = {};
     bool has_poly = false;
 };
 
@@ -128,6 +129,9 @@ void cb2_destroy(cb2_ctx* c) {
         if (c->ws[i].perm) cudaFree(c->ws[i].perm);
         if (c->ws[i].counts) cudaFree(c->ws[i].counts);
         if (c->ws[i].spill) cudaFree(c->ws[i].spill);
+        if (c->retry[i].list) cudaFree(c->retry[i].list);
+        if (c->retry[i].count) cudaFree(c->retry[i].count);
+        if (c->retry[i].scratch) cudaFree(c->retry[i].scratch);
     }
     sap_workspace_destroy(c->sap);
     delete c;
@@ -214,8 +218,35 @@ static int ensure_ws(cb2_ctx* c, int slot, uint64_t n) {
     return CB2_OK;
 }
 
+static int ensure_retry(cb2_ctx* c, int slot) {
+    retry_ws& r = c->retry[slot];
+    if (!r.list) CK(c, cudaMalloc(&r.list, sizeof(uint32_t) * RETRY_LIST_CAP));
+    if (!r.count) CK(c, cudaMalloc(&r.count, 2 * sizeof(uint32_t)));
+    if (!r.scratch) CK(c, cudaMalloc(&r.scratch, retry_scratch_bytes()));
+    return CB2_OK;
+}
+
+static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A,
+                           cudaStream_t st, int ws_slot);
+
 static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, cudaStream_t st,
                      int ws_slot = 0) {
+    int rc = launch_op_inner(c, op, strategy, A, st, ws_slot);
+    if (rc || op != OP_INTERSECTION || strategy != CB2_FULL_RESOLUTION) return rc;
+    // redo the rare pairs whose polytope outgrew the fast kernels' scratch
+    rc = ensure_retry(c, ws_slot);
+    if (rc) return rc;
+    cudaError_t e = launch_overflow_retry(A, c->retry[ws_slot], st);
+    c->launches += 2;
+    if (e != cudaSuccess) {
+        c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
+        return CB2_ERR_CUDA;
+    }
+    return CB2_OK;
+}
+
+static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A,
+                           cudaStream_t st, int ws_slot) {
     A.shapes = c->d_shapes;
     A.verts = c->d_verts;
     cudaError_t e;

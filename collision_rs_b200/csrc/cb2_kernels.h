@@ -41,6 +41,21 @@ struct aabb_args {
 
 cudaError_t launch_intersection(const narrow_args& A, bool full, cudaStream_t st);
 
+// ---- second chance for pairs whose EPA polytope outgrew the fast kernels' scratch ----------------
+constexpr int RETRY_FACES = 16384;
+constexpr int RETRY_EDGES = 4096;
+constexpr int RETRY_BLOCKS = 64;
+constexpr uint32_t RETRY_LIST_CAP = 1u << 16;
+constexpr size_t RETRY_BYTES_PER_BLOCK =
+    (size_t)RETRY_FACES * 20 + 2 * 104 * 12 + (size_t)RETRY_EDGES * 2 + 64;
+struct retry_ws {
+    uint32_t* list;   // RETRY_LIST_CAP
+    uint32_t* count;  // [0] = overflow count, [1] = work cursor
+    char* scratch;    // retry_scratch_bytes()
+};
+size_t retry_scratch_bytes();
+cudaError_t launch_overflow_retry(const narrow_args& A, const retry_ws& R, cudaStream_t st);
+
 // ---- classified (polyhedron-aware) intersection, cb2_poly.cu ----------------------------------
 constexpr int NUM_CLASSES = 7;
 struct narrow_ws {       // per-stream device workspace, owned by the ctx

@@ -62,87 +62,115 @@ CB2_DI bool gjk_intersect(const pair_in& p, uint32_t max_iterations, simplex<WIT
     return false;
 }
 
-// ---- EPA3 (epa3d.rs) with the polytope in per-thread local memory ---------------------------
+// ---- EPA3 (epa3d.rs) over a polytope store ------------------------------------------------------
+// local_store: per-thread local memory (the hardware interleaves it per lane, so a warp walking
+// the face list in lockstep reads coalesced 128-byte lines out of L1).  Sized for the manifold
+// bound (2V-4 = 202 faces at the 100-iteration cap) plus slack.  About 5 pairs per million
+// (curved shapes) grow a NON-manifold polytope past that (observed up to 1050 faces); those
+// return ST_SCRATCH_OVERFLOW here and are redone by k_retry_overflow over a global_store.
 constexpr int EPA_MAX_VERTS = 104;   // 4 + (CB2_MAX_ITERATIONS - 1) adds = 103
-constexpr int EPA_MAX_FACES = 256;   // manifold bound 2V-4 = 202; slack for odd horizons
+constexpr int EPA_MAX_FACES = 256;
 constexpr int EPA_MAX_EDGES = 192;
 
-struct polytope {
-    float4 fnd[EPA_MAX_FACES];    // normal.xyz, distance
-    uint32_t fidx[EPA_MAX_FACES]; // v0 | v1<<8 | v2<<16
-    f3 pv[EPA_MAX_VERTS];         // SupportPoint.v
-    f3 pa[EPA_MAX_VERTS];         // SupportPoint.sup_a
-    uint16_t edges[EPA_MAX_EDGES];// a | b<<8, horizon list in reference order
-    int nf, nv;
+struct local_store {
+    float4 fnd_[EPA_MAX_FACES];     // normal.xyz, distance
+    uint32_t fidx_[EPA_MAX_FACES];  // v0 | v1<<8 | v2<<16
+    f3 pv_[EPA_MAX_VERTS];          // SupportPoint.v
+    f3 pa_[EPA_MAX_VERTS];          // SupportPoint.sup_a
+    uint16_t edges_[EPA_MAX_EDGES]; // a | b<<8, horizon list in reference order
+    CB2_DI float4& fnd(int i) { return fnd_[i]; }
+    CB2_DI uint32_t& fidx(int i) { return fidx_[i]; }
+    CB2_DI f3& pv(int i) { return pv_[i]; }
+    CB2_DI f3& pa(int i) { return pa_[i]; }
+    CB2_DI uint16_t& edge(int i) { return edges_[i]; }
+    CB2_DI int fcap() const { return EPA_MAX_FACES; }
+    CB2_DI int vcap() const { return EPA_MAX_VERTS; }
+    CB2_DI int ecap() const { return EPA_MAX_EDGES; }
+};
+struct global_store {
+    float4* fnd_;
+    uint32_t* fidx_;
+    f3* pv_;
+    f3* pa_;
+    uint16_t* edges_;
+    CB2_DI float4& fnd(int i) { return fnd_[i]; }
+    CB2_DI uint32_t& fidx(int i) { return fidx_[i]; }
+    CB2_DI f3& pv(int i) { return pv_[i]; }
+    CB2_DI f3& pa(int i) { return pa_[i]; }
+    CB2_DI uint16_t& edge(int i) { return edges_[i]; }
+    CB2_DI int fcap() const { return RETRY_FACES; }
+    CB2_DI int vcap() const { return EPA_MAX_VERTS; }
+    CB2_DI int ecap() const { return RETRY_EDGES; }
 };
 
 // Face::new_impl, epa3d.rs:189-199
-CB2_DI void face_new(polytope& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
-    const f3 va = P.pv[a];
-    const f3 ab = P.pv[b] - va;
-    const f3 ac = P.pv[c] - va;
+template <class S>
+CB2_DI void face_new(S& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
+    const f3 va = P.pv(a);
+    const f3 ab = P.pv(b) - va;
+    const f3 ac = P.pv(c) - va;
     const f3 n = normalize(cross(ab, ac));
     const float dist = dot(n, va);
-    P.fnd[slot] = make_float4(n.x, n.y, n.z, dist);
-    P.fidx[slot] = a | (b << 8) | (c << 16);
+    P.fnd(slot) = make_float4(n.x, n.y, n.z, dist);
+    P.fidx(slot) = a | (b << 8) | (c << 16);
 }
 
 // EPA3::process, epa3d.rs:27-65 (+ Polytope::add :147-175, contact :84-114)
-__device__ __noinline__ uint8_t epa_process(const pair_in& p, const simplex<true>& s, float tol,
-                                            uint32_t max_iterations, contact_out& out) {
-    polytope P;
+template <class S>
+CB2_DI uint8_t epa_process(S& P, const pair_in& p, const simplex<true>& s, float tol,
+                           uint32_t max_iterations, contact_out& out) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        P.pv[i] = s.v[i];
-        P.pa[i] = s.a[i];
+        P.pv(i) = s.v[i];
+        P.pa(i) = s.a[i];
     }
-    P.nv = 4;
+    int nv = 4;
     face_new(P, 0, 3, 2, 1);  // Face::new, epa3d.rs:201-208
     face_new(P, 1, 3, 1, 0);
     face_new(P, 2, 3, 0, 2);
     face_new(P, 3, 2, 0, 1);
-    P.nf = 4;
+    int nf = 4;
     uint32_t it = 1;
     for (;;) {
-        if (P.nf == 0) return ST_PANIC_EPA_EMPTY;
+        if (nf == 0) return ST_PANIC_EPA_EMPTY;
         // closest_face_to_origin: first strictly smallest distance (:137-145)
         int best = 0;
-        float best_d = P.fnd[0].w;
-        for (int f = 1; f < P.nf; ++f) {
-            const float d = P.fnd[f].w;
+        float best_d = P.fnd(0).w;
+        for (int f = 1; f < nf; ++f) {
+            const float d = P.fnd(f).w;
             if (d < best_d) {
                 best_d = d;
                 best = f;
             }
         }
-        const float4 fb = P.fnd[best];
+        const float4 fb = P.fnd(best);
         const f3 n = mk3(fb.x, fb.y, fb.z);
         f3 sv, sa;
         minkowski<true>(p, n, sv, sa);
         const float d = dot(sv, n);
         if (fsub(d, fb.w) < tol || it >= max_iterations) {
             // contact(): barycentric of normal*distance on the face, blend sup_a (:84-114)
-            const uint32_t idx = P.fidx[best];
+            const uint32_t idx = P.fidx(best);
             const uint32_t i0 = idx & 255u, i1 = (idx >> 8) & 255u, i2 = (idx >> 16) & 255u;
             float u, v, w;
-            barycentric_vector(n * fb.w, P.pv[i0], P.pv[i1], P.pv[i2], u, v, w);
+            barycentric_vector(n * fb.w, P.pv(i0), P.pv(i1), P.pv(i2), u, v, w);
             out.normal = n;
             out.depth = fb.w;
-            out.point = (P.pa[i0] * u + P.pa[i1] * v) + P.pa[i2] * w;
+            out.point = (P.pa(i0) * u + P.pa(i1) * v) + P.pa(i2) * w;
             out.toi = 0.0f;
             return ST_SOME;
         }
         // Polytope::add: remove visible faces (swap_remove, no i++ on removal), toggle edges
         int ne = 0;
         int f = 0;
-        while (f < P.nf) {
-            const float4 fn = P.fnd[f];
-            const uint32_t idx = P.fidx[f];
-            const float vis = dot(mk3(fn.x, fn.y, fn.z), sv - P.pv[idx & 255u]);
+        while (f < nf) {
+            const float4 fn = P.fnd(f);
+            const uint32_t idx = P.fidx(f);
+            const float vis = dot(mk3(fn.x, fn.y, fn.z), sv - P.pv(idx & 255u));
             if (vis > 0.0f) {
-                --P.nf;
-                P.fnd[f] = P.fnd[P.nf];
-                P.fidx[f] = P.fidx[P.nf];
+                --nf;
+                P.fnd(f) = P.fnd(nf);
+                P.fidx(f) = P.fidx(nf);
                 const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
 #pragma unroll
                 for (int e = 0; e < 3; ++e) {
@@ -151,31 +179,38 @@ __device__ __noinline__ uint8_t epa_process(const pair_in& p, const simplex<true
                     const uint32_t eb = e == 0 ? v1 : (e == 1 ? v2 : v0);
                     const uint16_t rev = (uint16_t)(eb | (ea << 8));
                     int k = 0;
-                    while (k < ne && P.edges[k] != rev) ++k;
+                    while (k < ne && P.edge(k) != rev) ++k;
                     if (k < ne) {
-                        for (int m = k; m + 1 < ne; ++m) P.edges[m] = P.edges[m + 1];
+                        for (int m = k; m + 1 < ne; ++m) P.edge(m) = P.edge(m + 1);
                         --ne;
                     } else {
-                        if (ne >= EPA_MAX_EDGES) return ST_SCRATCH_OVERFLOW;
-                        P.edges[ne++] = (uint16_t)(ea | (eb << 8));
+                        if (ne >= P.ecap()) return ST_SCRATCH_OVERFLOW;
+                        P.edge(ne++) = (uint16_t)(ea | (eb << 8));
                     }
                 }
             } else {
                 ++f;
             }
         }
-        if (P.nv >= EPA_MAX_VERTS || P.nf + ne > EPA_MAX_FACES) return ST_SCRATCH_OVERFLOW;
-        const uint32_t nn = (uint32_t)P.nv;
-        P.pv[nn] = sv;
-        P.pa[nn] = sa;
-        ++P.nv;
+        if (nv >= P.vcap() || nf + ne > P.fcap()) return ST_SCRATCH_OVERFLOW;
+        const uint32_t nn = (uint32_t)nv;
+        P.pv(nn) = sv;
+        P.pa(nn) = sa;
+        ++nv;
         for (int k = 0; k < ne; ++k) {
-            const uint32_t e = P.edges[k];
-            face_new(P, P.nf + k, nn, e & 255u, e >> 8);
+            const uint32_t e = P.edge(k);
+            face_new(P, nf + k, nn, e & 255u, e >> 8);
         }
-        P.nf += ne;
+        nf += ne;
         ++it;
     }
+}
+
+__device__ __noinline__ uint8_t epa_process_local(const pair_in& p, const simplex<true>& s,
+                                                  float tol, uint32_t max_iterations,
+                                                  contact_out& out) {
+    local_store P;
+    return epa_process(P, p, s, tol, max_iterations, out);
 }
 
 CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const float4* rt,
@@ -220,8 +255,8 @@ __global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
         simplex<FULL> s;
         if (gjk_intersect<FULL>(p, A.settings.max_iterations, s)) {
             if constexpr (FULL) {
-                st = epa_process(p, reinterpret_cast<const simplex<true>&>(s),
-                                 A.settings.epa_tolerance, A.settings.max_iterations, c);
+                st = epa_process_local(p, reinterpret_cast<const simplex<true>&>(s),
+                                       A.settings.epa_tolerance, A.settings.max_iterations, c);
                 if (st != ST_SOME) c = zero_contact();
             } else {
                 st = ST_SOME;
@@ -348,6 +383,55 @@ __global__ void __launch_bounds__(128) k_time_of_impact(narrow_args A) {
     A.out_status[i] = st;
 }
 
+// ---- second chance for ST_SCRATCH_OVERFLOW pairs ---------------------------------------------------
+// Collect the (few per million) pairs whose polytope outgrew the fast kernels' scratch and redo
+// them, one pair per block leader, over a large global scratch.  Same arithmetic, same order.
+__global__ void __launch_bounds__(256) k_collect_overflow(const uint8_t* __restrict__ status,
+                                                         uint64_t n, uint32_t* __restrict__ list,
+                                                         uint32_t* __restrict__ count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (status[i] == ST_SCRATCH_OVERFLOW) {
+        const uint32_t k = atomicAdd(count, 1u);
+        if (k < RETRY_LIST_CAP) list[k] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_retry_overflow(narrow_args A, const uint32_t* __restrict__ list,
+                                                      const uint32_t* __restrict__ count,
+                                                      uint32_t* __restrict__ cursor,
+                                                      char* __restrict__ scratch) {
+    if (threadIdx.x != 0) return;
+    uint32_t total = *count;
+    if (total > RETRY_LIST_CAP) total = RETRY_LIST_CAP;
+    global_store P;
+    char* base = scratch + (size_t)blockIdx.x * RETRY_BYTES_PER_BLOCK;
+    P.fnd_ = reinterpret_cast<float4*>(base);
+    P.fidx_ = reinterpret_cast<uint32_t*>(base + (size_t)RETRY_FACES * 16);
+    P.pv_ = reinterpret_cast<f3*>(base + (size_t)RETRY_FACES * 20);
+    P.pa_ = P.pv_ + EPA_MAX_VERTS;
+    P.edges_ = reinterpret_cast<uint16_t*>(P.pa_ + EPA_MAX_VERTS);
+    for (;;) {
+        const uint32_t k = atomicAdd(cursor, 1u);
+        if (k >= total) return;
+        const uint64_t i = list[k];
+        pair_in p;
+        contact_out c = zero_contact();
+        uint8_t st = ST_NONE;
+        if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+            st = ST_PANIC_INV_SCALE;
+        } else {
+            simplex<true> s;
+            if (gjk_intersect<true>(p, A.settings.max_iterations, s)) {
+                st = epa_process(P, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
+                if (st != ST_SOME) c = zero_contact();
+            }
+        }
+        store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, c);
+        A.out_status[i] = st;
+    }
+}
+
 // ---- world AABBs: shape.compute_bound().transform_volume(&t) ------------------------------------
 // ComputeBound: sphere.rs:41-51, cuboid.rs:82-92, polyhedron.rs:113-115 (fold from Aabb3::zero(),
 // so the bound always contains the origin); Aabb3::transform: aabb3.rs:39-50,90-100.
@@ -408,6 +492,17 @@ cudaError_t launch_intersection(const narrow_args& A, bool full, cudaStream_t st
     else k_intersection<false><<<grid_for(A.n, 128), 128, 0, st>>>(A);
     return cudaGetLastError();
 }
+size_t retry_scratch_bytes() { return (size_t)RETRY_BLOCKS * RETRY_BYTES_PER_BLOCK; }
+
+cudaError_t launch_overflow_retry(const narrow_args& A, const retry_ws& R, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(R.count, 0, 2 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    k_collect_overflow<<<grid_for(A.n, 256), 256, 0, st>>>(A.out_status, A.n, R.list, R.count);
+    k_retry_overflow<<<RETRY_BLOCKS, 32, 0, st>>>(A, R.list, R.count, R.count + 1, R.scratch);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_distance(const narrow_args& A, cudaStream_t st) {
     if (A.n == 0) return cudaSuccess;
     k_distance<<<grid_for(A.n, 128), 128, 0, st>>>(A);

@@ -419,6 +419,7 @@ static std::vector<Face> face_new(const std::vector<Sup>& s) {  // :201-208
     f.push_back(face_new_impl(s, 2, 0, 1));
     return f;
 }
+static thread_local uint32_t t_peak_edges = 0;  // instrumentation only
 typedef std::pair<size_t, size_t> Edge;
 static void remove_or_add_edge(std::vector<Edge>& edges, Edge e) {  // :212-219
     for (size_t i = 0; i < edges.size(); ++i) {
@@ -452,6 +453,7 @@ static void polytope_add(Polytope& p, const Sup& sup) {  // :147-175
             remove_or_add_edge(edges, Edge(face.vertices[0], face.vertices[1]));
             remove_or_add_edge(edges, Edge(face.vertices[1], face.vertices[2]));
             remove_or_add_edge(edges, Edge(face.vertices[2], face.vertices[0]));
+            if (edges.size() > t_peak_edges) t_peak_edges = (uint32_t)edges.size();
         } else {
             ++i;
         }
@@ -482,6 +484,7 @@ static void epa_contact(const Polytope& p, const Face& face, cb2_contact* out) {
 }
 struct EpaStats {
     uint32_t iterations, faces, verts;
+    uint32_t peak_faces, peak_edges;  // scratch the device kernels must provision
 };
 // EPA3::process, :27-65. Returns false for None.
 static bool epa_process(std::vector<Sup>& simplex, const Shape& l, const Xf& lt, const Shape& r,
@@ -492,7 +495,10 @@ static bool epa_process(std::vector<Sup>& simplex, const Shape& l, const Xf& lt,
     poly.vertices = &simplex;
     poly.faces = face_new(simplex);
     uint32_t i = 1;
+    uint32_t peak_faces = 4;
+    t_peak_edges = 0;
     for (;;) {
+        if (poly.faces.size() > peak_faces) peak_faces = (uint32_t)poly.faces.size();
         size_t fi = closest_face_to_origin(poly);
         Face face = poly.faces[fi];
         Sup p = from_minkowski(l, lt, r, rt, face.normal);
@@ -503,6 +509,8 @@ static bool epa_process(std::vector<Sup>& simplex, const Shape& l, const Xf& lt,
                 st->iterations = i;
                 st->faces = (uint32_t)poly.faces.size();
                 st->verts = (uint32_t)simplex.size();
+                st->peak_faces = peak_faces;
+                st->peak_edges = t_peak_edges;
             }
             return true;
         }
@@ -879,7 +887,8 @@ int orc_aabb3_intersects(const cb2_aabb3* a, const cb2_aabb3* b) {
 }
 
 // ---- batch entry points: same array contract as include/collision_b200.h ----------------
-// stats (optional, may be NULL): per pair u32 x 4 = {gjk iterations, epa iterations, faces, verts}
+// stats (optional, may be NULL): per pair u32 x 4 = {gjk iterations, epa iterations, peak faces,
+// verts | peak horizon edges << 16}
 void orc_gjk3_intersection_batch(uint32_t strategy, const cb2_settings* st, const cb2_shape* shapes,
                                  const float* verts_xyz, const uint32_t* l_shape,
                                  const uint32_t* r_shape, const cb2_xform* l_t,
@@ -888,15 +897,15 @@ void orc_gjk3_intersection_batch(uint32_t strategy, const cb2_settings* st, cons
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
         for (uint64_t i = b; i < e; ++i) {
             uint32_t gi = 0;
-            EpaStats es = {0, 0, 0};
+            EpaStats es = {0, 0, 0, 0, 0};
             status[i] = gjk_intersection(strategy, *st, load_shape(shapes[l_shape[i]], verts_xyz),
                                          load_xf(l_t[i]), load_shape(shapes[r_shape[i]], verts_xyz),
                                          load_xf(r_t[i]), &out[i], &gi, &es);
             if (stats) {
                 stats[4 * i] = gi;
                 stats[4 * i + 1] = es.iterations;
-                stats[4 * i + 2] = es.faces;
-                stats[4 * i + 3] = es.verts;
+                stats[4 * i + 2] = es.peak_faces;
+                stats[4 * i + 3] = es.verts | (es.peak_edges << 16);
             }
         }
     });

@@ -198,6 +198,19 @@ def test_mixed_table_all_classes(ctx, oracle):
     assert (est == 4).sum() > 0 and (est == 1).sum() > 1000
 
 
+def test_non_manifold_polytopes_are_retried(ctx, oracle):
+    """~5 curved pairs per million grow a non-manifold EPA polytope far past 2V-4 faces (this
+    sample peaks at 1050 faces): the fast kernels flag them and k_retry_overflow redoes them."""
+    w = W.cfg2_mixed_pairs(500_000, seed=1, spread=0.8)
+    _upload(ctx, w)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    exp, est, stats = oracle.intersection(0, w["shapes"], None, *args, nthreads=8, want_stats=True)
+    assert stats[:, 2].max() > 256
+    got, gst = ctx.intersection(0, *args)
+    assert_contacts_equal(got, gst, exp, est, "non-manifold retry")
+    assert (gst == 7).sum() == 0
+
+
 def test_cfg5_time_of_impact(ctx, oracle):
     w = W.cfg5_toi_pairs(40_000)
     _upload(ctx, w)
