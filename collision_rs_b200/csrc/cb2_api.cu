@@ -41,9 +41,21 @@ struct cb2_ctx {
     uint64_t ws_cap[NS] = {0, 0};
     retry_ws retry[NS] = {};
     bool has_poly = false;
+    uint32_t max_vcnt = 0;  // largest polyhedron in the table
 };
 
 static std::string g_create_err;
+
+static void free_ws(narrow_ws& w) {  // everything but the counters
+    if (w.key) cudaFree(w.key);
+    if (w.perm) cudaFree(w.perm);
+    if (w.hits) cudaFree(w.hits);
+    if (w.over) cudaFree(w.over);
+    if (w.simplex) cudaFree(w.simplex);
+    w.key = nullptr;
+    w.perm = w.hits = w.over = nullptr;
+    w.simplex = nullptr;
+}
 
 #define CK(ctx, x)                                                                     \
     do {                                                                               \
@@ -125,10 +137,8 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_verts) cudaFree(c->d_verts);
     if (c->d_misc) cudaFree(c->d_misc);
     for (int i = 0; i < cb2_ctx::NS; ++i) {
-        if (c->ws[i].cls) cudaFree(c->ws[i].cls);
-        if (c->ws[i].perm) cudaFree(c->ws[i].perm);
-        if (c->ws[i].counts) cudaFree(c->ws[i].counts);
-        if (c->ws[i].spill) cudaFree(c->ws[i].spill);
+        free_ws(c->ws[i]);
+        if (c->ws[i].PC) cudaFree(c->ws[i].PC);
         if (c->retry[i].list) cudaFree(c->retry[i].list);
         if (c->retry[i].count) cudaFree(c->retry[i].count);
         if (c->retry[i].scratch) cudaFree(c->retry[i].scratch);
@@ -185,7 +195,12 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
     c->n_shapes = n_shapes;
     c->n_verts = n_verts;
     c->has_poly = false;
-    for (uint32_t i = 0; i < n_shapes; ++i) c->has_poly |= (shapes[i].kind == CB2_POLYHEDRON);
+    c->max_vcnt = 0;
+    for (uint32_t i = 0; i < n_shapes; ++i) {
+        if (shapes[i].kind != CB2_POLYHEDRON) continue;
+        c->has_poly = true;
+        if (shapes[i].vtx_cnt > c->max_vcnt) c->max_vcnt = shapes[i].vtx_cnt;
+    }
     return CB2_OK;
 }
 
@@ -203,16 +218,15 @@ static int check_settings(cb2_ctx* c, const cb2_settings* s) {
 
 static int ensure_ws(cb2_ctx* c, int slot, uint64_t n) {
     narrow_ws& w = c->ws[slot];
-    if (!w.counts) CK(c, cudaMalloc(&w.counts, sizeof(uint32_t) * 3 * NUM_CLASSES));
-    if (!w.spill) CK(c, cudaMalloc(&w.spill, coop_spill_bytes(c->sm_count)));
+    if (!w.PC) CK(c, cudaMalloc(&w.PC, sizeof(poly_counters)));
     if (c->ws_cap[slot] < n) {
-        if (w.cls) cudaFree(w.cls);
-        if (w.perm) cudaFree(w.perm);
-        w.cls = nullptr;
-        w.perm = nullptr;
+        free_ws(w);
         c->ws_cap[slot] = 0;
-        CK(c, cudaMalloc(&w.cls, n));
+        CK(c, cudaMalloc(&w.key, n));
         CK(c, cudaMalloc(&w.perm, n * sizeof(uint32_t)));
+        CK(c, cudaMalloc(&w.hits, n * sizeof(uint32_t)));
+        CK(c, cudaMalloc(&w.over, n * sizeof(uint32_t)));
+        CK(c, cudaMalloc(&w.simplex, n * 6 * sizeof(float4)));
         c->ws_cap[slot] = n;
     }
     return CB2_OK;
@@ -256,7 +270,7 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
         int rc = ensure_ws(c, ws_slot, A.n);
         if (rc) return rc;
         e = launch_intersection_classified(A, strategy == CB2_FULL_RESOLUTION, c->ws[ws_slot],
-                                           c->sm_count, st, &c->launches);
+                                           c->sm_count, c->max_vcnt, st, &c->launches);
         if (e != cudaSuccess) {
             c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
             return CB2_ERR_CUDA;

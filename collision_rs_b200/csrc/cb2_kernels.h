@@ -57,16 +57,31 @@ size_t retry_scratch_bytes();
 cudaError_t launch_overflow_retry(const narrow_args& A, const retry_ws& R, cudaStream_t st);
 
 // ---- classified (polyhedron-aware) intersection, cb2_poly.cu ----------------------------------
-constexpr int NUM_CLASSES = 7;
-struct narrow_ws {       // per-stream device workspace, owned by the ctx
-    uint8_t* cls;        // n bytes
-    uint32_t* perm;      // n words
-    uint32_t* counts;    // 3 * NUM_CLASSES words: counts | scatter cursors | queue cursors
-    float* spill;        // coop_spill_bytes()
+constexpr int POLY_NC = 11;                  // size classes (0 = no polyhedron in the pair)
+constexpr int POLY_SUB = 16;                 // (Vl, Vr) sub-buckets per class
+constexpr int POLY_NB = POLY_NC * POLY_SUB;  // counting-sort buckets (fits the u8 key)
+struct poly_counters {                       // device-side bookkeeping, zeroed per batch
+    uint32_t hist[POLY_NB];
+    uint32_t start[POLY_NB];
+    uint32_t cursor[POLY_NB];
+    uint32_t class_begin[POLY_NC + 1];
+    uint32_t gjk_next[POLY_NC];              // work-queue cursors
+    uint32_t hit_count[POLY_NC];
+    uint32_t epa_next[POLY_NC];
+    uint32_t over_count;
+    uint32_t over_next;
 };
-size_t coop_spill_bytes(int sm_count);
+struct narrow_ws {       // per-stream device workspace, owned by the ctx
+    uint8_t* key;        // n bytes: bucket of each pair
+    uint32_t* perm;      // n words: pairs sorted by bucket
+    uint32_t* hits;      // n words: queue positions of FullResolution hits, per class range
+    uint32_t* over;      // n words: queue positions whose polytope outgrew the tier-1 scratch
+    float4* simplex;     // 6 x float4 per queue position (GJK terminal simplex -> EPA)
+    poly_counters* PC;
+};
 cudaError_t launch_intersection_classified(const narrow_args& A, bool full, const narrow_ws& W,
-                                           int sm_count, cudaStream_t st, uint64_t* launches);
+                                           int sm_count, uint32_t max_vcnt, cudaStream_t st,
+                                           uint64_t* launches);
 cudaError_t launch_distance(const narrow_args& A, cudaStream_t st);
 cudaError_t launch_time_of_impact(const narrow_args& A, cudaStream_t st);
 cudaError_t launch_world_aabbs(const aabb_args& A, cudaStream_t st);
