@@ -6,7 +6,9 @@
 // enqueue kernels on the caller's stream.  No CPU fallback anywhere.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -24,6 +26,9 @@ struct cb2_ctx {
     // shape table
     dshape* d_shapes = nullptr;
     float4* d_verts = nullptr;
+    uint4* d_cells = nullptr;        // support cells of all polyhedra (cb2_cells.cuh)
+    uint16_t* d_cell_ext = nullptr;  // their extension pool
+    uint32_t* d_cell_cursor = nullptr;
     uint32_t n_shapes = 0;
     uint64_t n_verts = 0;
     // host-API staging
@@ -41,19 +46,18 @@ struct cb2_ctx {
     uint64_t ws_cap[NS] = {0, 0};
     retry_ws retry[NS] = {};
     bool has_poly = false;
-    uint32_t max_vcnt = 0;  // largest polyhedron in the table
+    bool legacy_epa = false;  // CB2_LEGACY_EPA=1: thread-per-pair EPA in local memory (A/B testing)
+    bool no_cells = false;    // CB2_NO_CELLS=1: polyhedron support by full vertex scan (A/B testing)
 };
 
 static std::string g_create_err;
 
-static void free_ws(narrow_ws& w) {  // everything but the counters
-    if (w.key) cudaFree(w.key);
-    if (w.perm) cudaFree(w.perm);
+static void free_ws(narrow_ws& w) {  // the per-pair buffers
     if (w.hits) cudaFree(w.hits);
-    if (w.over) cudaFree(w.over);
+    if (w.over2) cudaFree(w.over2);
+    if (w.over3) cudaFree(w.over3);
     if (w.simplex) cudaFree(w.simplex);
-    w.key = nullptr;
-    w.perm = w.hits = w.over = nullptr;
+    w.hits = w.over2 = w.over3 = nullptr;
     w.simplex = nullptr;
 }
 
@@ -114,6 +118,12 @@ int cb2_create(int device, cb2_ctx** out) {
             return CB2_ERR_CUDA;
         }
     }
+    {
+        const char* e1 = std::getenv("CB2_LEGACY_EPA");
+        const char* e2 = std::getenv("CB2_NO_CELLS");
+        c->legacy_epa = e1 && e1[0] == '1';
+        c->no_cells = e2 && e2[0] == '1';
+    }
     c->sap = sap_workspace_create();
     if (!c->sap) {
         g_create_err = "pinned allocation failed";
@@ -135,10 +145,14 @@ void cb2_destroy(cb2_ctx* c) {
     }
     if (c->d_shapes) cudaFree(c->d_shapes);
     if (c->d_verts) cudaFree(c->d_verts);
+    if (c->d_cells) cudaFree(c->d_cells);
+    if (c->d_cell_ext) cudaFree(c->d_cell_ext);
+    if (c->d_cell_cursor) cudaFree(c->d_cell_cursor);
     if (c->d_misc) cudaFree(c->d_misc);
     for (int i = 0; i < cb2_ctx::NS; ++i) {
         free_ws(c->ws[i]);
-        if (c->ws[i].PC) cudaFree(c->ws[i].PC);
+        if (c->ws[i].EC) cudaFree(c->ws[i].EC);
+        if (c->ws[i].pa) cudaFree(c->ws[i].pa);
         if (c->retry[i].list) cudaFree(c->retry[i].list);
         if (c->retry[i].count) cudaFree(c->retry[i].count);
         if (c->retry[i].scratch) cudaFree(c->retry[i].scratch);
@@ -156,6 +170,9 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
     if (!c || (!shapes && n_shapes) || (!verts_xyz && n_verts)) return fail(c, CB2_ERR_ARG, "null argument");
     CK(c, cudaSetDevice(c->device));
     std::vector<dshape> hs(n_shapes);
+    uint64_t total_cells = 0;
+    uint32_t max_N = 0;
+    c->has_poly = false;
     for (uint32_t i = 0; i < n_shapes; ++i) {
         const cb2_shape& s = shapes[i];
         dshape d;
@@ -173,6 +190,22 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
                 return fail(c, CB2_ERR_ARG, "polyhedron vertex range outside the vertex table");
             d.voff = s.vtx_off;
             d.vcnt = s.vtx_cnt;
+            c->has_poly = true;
+            // support cells (cb2_cells.cuh): R = max |vertex| rounded up, cube-map resolution N
+            double r2 = 0.0;
+            for (uint32_t k = 0; k < s.vtx_cnt; ++k) {
+                const float* v = verts_xyz + 3 * ((uint64_t)s.vtx_off + k);
+                const double q = (double)v[0] * v[0] + (double)v[1] * v[1] + (double)v[2] * v[2];
+                if (!(q <= r2)) r2 = q;  // NaN sticks: the lookup then always takes the full scan
+            }
+            d.hx = std::nextafter((float)std::sqrt(r2), INFINITY);
+            const uint32_t N = c->no_cells ? 0u : cells_resolution(s.vtx_cnt);
+            if (N && total_cells + 6ull * N * N > 0xFFFFFFFFull)
+                return fail(c, CB2_ERR_ARG, "support-cell table exceeds 2^32 records");
+            d.cell_off = (uint32_t)total_cells;
+            d.cell_cfg = N | ((s.vtx_cnt > 256 ? 1u : 0u) << 8);
+            total_cells += 6ull * N * N;
+            if (N > max_N) max_N = N;
         } else {
             return fail(c, CB2_ERR_ARG, "unknown shape kind");
         }
@@ -184,8 +217,12 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
     CK(c, cudaDeviceSynchronize());
     if (c->d_shapes) cudaFree(c->d_shapes);
     if (c->d_verts) cudaFree(c->d_verts);
+    if (c->d_cells) cudaFree(c->d_cells);
+    if (c->d_cell_ext) cudaFree(c->d_cell_ext);
     c->d_shapes = nullptr;
     c->d_verts = nullptr;
+    c->d_cells = nullptr;
+    c->d_cell_ext = nullptr;
     CK(c, cudaMalloc(&c->d_shapes, sizeof(dshape) * (n_shapes ? n_shapes : 1)));
     CK(c, cudaMalloc(&c->d_verts, sizeof(float4) * (n_verts ? n_verts : 1)));
     if (n_shapes)
@@ -194,12 +231,21 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
         CK(c, cudaMemcpy(c->d_verts, hv.data(), sizeof(float4) * n_verts, cudaMemcpyHostToDevice));
     c->n_shapes = n_shapes;
     c->n_verts = n_verts;
-    c->has_poly = false;
-    c->max_vcnt = 0;
-    for (uint32_t i = 0; i < n_shapes; ++i) {
-        if (shapes[i].kind != CB2_POLYHEDRON) continue;
-        c->has_poly = true;
-        if (shapes[i].vtx_cnt > c->max_vcnt) c->max_vcnt = shapes[i].vtx_cnt;
+    // build the support cells on the device (one thread per cell)
+    const uint64_t ext_cap64 = total_cells * 4 + (1u << 16);
+    const uint32_t ext_cap = ext_cap64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ext_cap64;
+    CK(c, cudaMalloc(&c->d_cells, sizeof(uint4) * (total_cells ? total_cells : 1)));
+    CK(c, cudaMalloc(&c->d_cell_ext, sizeof(uint16_t) * (size_t)ext_cap));
+    if (!c->d_cell_cursor) CK(c, cudaMalloc(&c->d_cell_cursor, sizeof(uint32_t)));
+    if (total_cells) {
+        cudaError_t e = build_support_cells(c->d_shapes, c->d_verts, n_shapes, max_N, c->d_cells,
+                                            c->d_cell_ext, ext_cap, c->d_cell_cursor, nullptr);
+        ++c->launches;
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            c->err = std::string("support-cell build: ") + cudaGetErrorString(e);
+            return CB2_ERR_CUDA;
+        }
     }
     return CB2_OK;
 }
@@ -218,15 +264,15 @@ static int check_settings(cb2_ctx* c, const cb2_settings* s) {
 
 static int ensure_ws(cb2_ctx* c, int slot, uint64_t n) {
     narrow_ws& w = c->ws[slot];
-    if (!w.PC) CK(c, cudaMalloc(&w.PC, sizeof(poly_counters)));
+    if (!w.EC) CK(c, cudaMalloc(&w.EC, sizeof(epa_counters)));
+    if (!w.pa) CK(c, cudaMalloc(&w.pa, epa_pa_scratch_bytes(c->sm_count)));
     if (c->ws_cap[slot] < n) {
         free_ws(w);
         c->ws_cap[slot] = 0;
-        CK(c, cudaMalloc(&w.key, n));
-        CK(c, cudaMalloc(&w.perm, n * sizeof(uint32_t)));
         CK(c, cudaMalloc(&w.hits, n * sizeof(uint32_t)));
-        CK(c, cudaMalloc(&w.over, n * sizeof(uint32_t)));
-        CK(c, cudaMalloc(&w.simplex, n * 6 * sizeof(float4)));
+        CK(c, cudaMalloc(&w.over2, n * sizeof(uint32_t)));
+        CK(c, cudaMalloc(&w.over3, n * sizeof(uint32_t)));
+        CK(c, cudaMalloc(&w.simplex, n * 8 * sizeof(float4)));
         c->ws_cap[slot] = n;
     }
     return CB2_OK;
@@ -261,16 +307,22 @@ static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, 
 
 static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A,
                            cudaStream_t st, int ws_slot) {
-    A.shapes = c->d_shapes;
-    A.verts = c->d_verts;
+    A.T.shapes = c->d_shapes;
+    A.T.verts = c->d_verts;
+    A.T.cells = c->d_cells;
+    A.T.ext = c->d_cell_ext;
     cudaError_t e;
-    if (op == OP_INTERSECTION && c->has_poly) {
-        // polyhedra in the table: bucket pairs by size class, sub-warp cooperative kernels
+    if (op == OP_INTERSECTION && !c->legacy_epa) {
+        // GJK (thread per pair) -> compacted hit list -> cooperative EPA tiers
         if (A.n > 0xFFFFFFFFull) return fail(c, CB2_ERR_ARG, "more than 2^32-1 pairs in one batch");
+        const bool full = strategy == CB2_FULL_RESOLUTION;
         int rc = ensure_ws(c, ws_slot, A.n);
         if (rc) return rc;
-        e = launch_intersection_classified(A, strategy == CB2_FULL_RESOLUTION, c->ws[ws_slot],
-                                           c->sm_count, c->max_vcnt, st, &c->launches);
+        const narrow_ws& W = c->ws[ws_slot];
+        CK(c, cudaMemsetAsync(W.EC, 0, sizeof(epa_counters), st));
+        e = launch_gjk_hits(A, full, W, st);
+        ++c->launches;
+        if (e == cudaSuccess && full) e = launch_epa_tiers(A, W, c->sm_count, st, &c->launches);
         if (e != cudaSuccess) {
             c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
             return CB2_ERR_CUDA;
@@ -530,8 +582,10 @@ int cb2_world_aabbs_dev(cb2_ctx* c, const uint32_t* shape, const cb2_xform* t, u
     if (!c->d_shapes) return fail(c, CB2_ERR_ARG, "cb2_shapes_upload has not been called");
     CK(c, cudaSetDevice(c->device));
     aabb_args A;
-    A.shapes = c->d_shapes;
-    A.verts = c->d_verts;
+    A.T.shapes = c->d_shapes;
+    A.T.verts = c->d_verts;
+    A.T.cells = c->d_cells;
+    A.T.ext = c->d_cell_ext;
     A.shape = shape;
     A.t = reinterpret_cast<const float4*>(t);
     A.n = n;

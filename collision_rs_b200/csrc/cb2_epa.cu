@@ -1,0 +1,473 @@
+// cb2_epa.cu — sub-warp cooperative EPA3 (EPA3::process, epa3d.rs:27-65): the second stage of
+// GJK3::intersection(FullResolution) (gjk/mod.rs:362-391) for every shape kind.
+//
+// Design (B200-first, not a translation of the reference's per-pair loop):
+//  * k_gjk_hits (cb2_narrow.cu, thread per pair) has already run GJK::intersect and queued the
+//    hits with their terminal simplex.  Here a GROUP of G lanes owns one hit; a warp holds 32/G
+//    groups and is persistent: a group that finishes pulls the next hit from a device-side queue,
+//    so lanes never idle behind the slowest pair of a warp.
+//  * Support points cost one thread a cube-map lookup plus a handful of vertex dots (support
+//    cells, cb2_cells.cuh), so nothing is staged in shared memory and the group splits the two
+//    support calls of SupportPoint::from_minkowski (minkowski/mod.rs:39-60) by lane parity: even
+//    lanes evaluate the left shape, odd lanes the right one, one shuffle exchanges the results.
+//    Each lane therefore keeps only ITS shape and transform in registers.
+//  * The O(F) work of Polytope::add (epa3d.rs:147-175) is split across the G lanes: visibility
+//    tests, horizon extraction, Face::new of the new faces, and the closest-face search (:137-145).
+//  * Polytope::add is reproduced in ORDER without replaying it serially: face visibility becomes
+//    a register bit mask (ballot), the swap_remove sweep is a two-pointer walk over that mask
+//    (which faces are examined in which order, which tail face lands in which hole), and the
+//    horizon list is "edges of visible faces, in examination order, whose reverse edge is not an
+//    edge of a visible face" — evaluated in parallel through a vertex-adjacency bit matrix in
+//    shared memory.  That equals remove_or_add_edge's list (epa3d.rs:212-219) whenever no directed
+//    edge occurs twice; the (non-manifold) exception is detected by the same atomicOr and the
+//    pair goes to the serial second-chance kernel (cb2_narrow.cu).
+//  * The polytope lives in per-group shared memory in three tiers (48/28, 96/52, 208/104 faces /
+//    vertices; the last is the manifold worst case 2V-4 at the 100-iteration cap).  A pair that
+//    outgrows its tier is re-queued for the next one.  sup_a of each polytope vertex is only read
+//    by the final contact (epa3d.rs:84-114), so it lives in a global scratch, not shared memory.
+#include "cb2_gjk.cuh"
+#include "cb2_kernels.h"
+
+namespace cb2 {
+
+CB2_DI shape_table table_of(const shape_table_args& a) {
+    shape_table t;
+    t.shapes = a.shapes;
+    t.verts = a.verts;
+    t.cells = a.cells;
+    t.ext = a.ext;
+    return t;
+}
+
+// per-group polytope scratch in shared memory
+template <int FCAP, int VCAP, int OCAP>
+struct poly_smem {
+    static constexpr int AW = (VCAP + 31) / 32;  // adjacency words per vertex row
+    float4 fnd[FCAP];          // normal.xyz, distance
+    float4 pv[VCAP];           // SupportPoint.v (x,y,z,-)
+    uint32_t fidx[FCAP];       // v0 | v1<<8 | v2<<16
+    uint32_t adj[VCAP * AW];   // directed-edge bit matrix (all zero between iterations)
+    uint16_t elist[OCAP];      // horizon edges a | b<<8 in reference order
+    uint8_t order[OCAP];       // visible faces in the order Polytope::add examines them
+    uint8_t mv_dst[OCAP];      // swap_remove: tail face mv_src lands in hole mv_dst
+    uint8_t mv_src[OCAP];
+};
+
+template <class PS>
+CB2_DI f3 ps_pv(const PS& P, uint32_t i) {
+    const float4 v = P.pv[i];
+    return mk3(v.x, v.y, v.z);
+}
+
+// Face::new_impl (epa3d.rs:189-199) into slot
+template <class PS>
+CB2_DI void ps_face_new(PS& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
+    const f3 va = ps_pv(P, a);
+    const f3 ab = ps_pv(P, b) - va;
+    const f3 ac = ps_pv(P, c) - va;
+    const f3 n = normalize(cross(ab, ac));
+    const float dist = dot(n, va);
+    P.fnd[slot] = make_float4(n.x, n.y, n.z, dist);
+    P.fidx[slot] = a | (b << 8) | (c << 16);
+}
+
+// fixed-size bit mask in registers (fully unrolled accessors)
+template <int W>
+struct bitmask {
+    uint32_t w[W];
+    CB2_DI void clear() {
+#pragma unroll
+        for (int k = 0; k < W; ++k) w[k] = 0u;
+    }
+    CB2_DI void or_bits(int pos, uint32_t bits) {  // pos is a multiple of the group width (<= 32)
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+            if ((pos >> 5) == k) w[k] |= bits << (pos & 31);
+    }
+    CB2_DI bool test(int i) const {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+            if ((i >> 5) == k) v = w[k];
+        return (v >> (i & 31)) & 1u;
+    }
+    CB2_DI void reset(int i) {
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+            if ((i >> 5) == k) w[k] &= ~(1u << (i & 31));
+    }
+    // lowest set bit at position >= from, or -1
+    CB2_DI int next(int from) const {
+        int r = -1;
+#pragma unroll
+        for (int k = W - 1; k >= 0; --k) {
+            uint32_t v = w[k];
+            if ((from >> 5) == k) v &= 0xFFFFFFFFu << (from & 31);
+            else if ((from >> 5) > k) v = 0u;
+            if (v) r = k * 32 + (__ffs(v) - 1);
+        }
+        return r;
+    }
+};
+
+struct epa_args {
+    narrow_args A;
+    narrow_ws W;
+    uint32_t tier;  // 0, 1, 2
+};
+
+enum : int { S_FETCH = 0, S_RUN = 1, S_EXIT = 2 };
+
+template <int G, int FCAP, int VCAP, int OCAP>
+__global__ void __launch_bounds__(32) k_epa(epa_args C) {
+    static_assert(G == 2 || G == 4 || G == 8, "3*G edge-keep bits must fit one word");
+    using PS = poly_smem<FCAP, VCAP, OCAP>;
+    constexpr int FW = (FCAP + 31) / 32;
+    constexpr int AW = PS::AW;
+    constexpr int NG = 32 / G;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x;
+    const int gl = lane & (G - 1);
+    const int gw = lane / G;
+    const unsigned gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (gw * G);
+    const uint32_t gbits = (1u << G) - 1u;
+    const bool right = gl & 1;  // this lane evaluates the right shape's support
+    const narrow_args& A = C.A;
+    const shape_table T = table_of(A.T);
+    PS& P = reinterpret_cast<PS*>(smem)[gw];
+    float4* pa = C.W.pa + ((size_t)blockIdx.x * NG + gw) * VCAP;
+
+    const uint32_t* list;
+    uint32_t count;
+    uint32_t* over_list;
+    uint32_t* over_count;
+    if (C.tier == 0) {
+        list = C.W.hits; count = C.W.EC->n_hits;
+        over_list = C.W.over2; over_count = &C.W.EC->n_over2;
+    } else if (C.tier == 1) {
+        list = C.W.over2; count = C.W.EC->n_over2;
+        over_list = C.W.over3; over_count = &C.W.EC->n_over3;
+    } else {
+        list = C.W.over3; count = C.W.EC->n_over3;
+        over_list = nullptr; over_count = nullptr;
+    }
+    uint32_t* cursor = &C.W.EC->next[C.tier];
+    const uint32_t max_it = A.settings.max_iterations;
+    const float epa_tol = A.settings.epa_tolerance;
+
+    // the adjacency matrix is kept all-zero between iterations
+    for (int k = gl; k < VCAP * AW; k += G) P.adj[k] = 0u;
+    __syncwarp(gmask);
+
+    int state = S_FETCH;
+    uint32_t pair = 0;
+    // this lane's side of the pair
+    shape sh;
+    sh.kind = K_CUBOID;
+    sh.h = zero3();
+    sh.poly.verts = nullptr; sh.poly.vcnt = 0; sh.poly.cells = nullptr; sh.poly.ext = nullptr;
+    sh.poly.N = 0; sh.poly.wide = false; sh.poly.R = 0.f;
+    xform xf = make_xform(make_float4(1.f, 1.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
+    f3 d = zero3();
+    uint32_t it = 0;
+    int nf = 0, nv = 0, best_face = 0;
+
+    for (;;) {
+        if (state == S_FETCH) {
+            uint32_t k = 0;
+            if (gl == 0) k = atomicAdd(cursor, 1u);
+            k = __shfl_sync(gmask, k, gw * G);
+            if (k >= count) {
+                state = S_EXIT;
+                nf = 0;
+                sh.kind = K_CUBOID;
+                sh.h = zero3();
+            } else {
+                pair = list[k];
+                uint32_t si;
+                uint64_t xi;
+                if (A.pair_body) {
+                    const uint2 b = __ldg(reinterpret_cast<const uint2*>(A.pair_body) + pair);
+                    xi = right ? b.y : b.x;
+                    si = __ldg(A.l_shape + xi);
+                } else {
+                    xi = pair;
+                    si = __ldg((right ? A.r_shape : A.l_shape) + pair);
+                }
+                sh = load_shape(T, si);
+                const float4* tp = (right ? A.r_t : A.l_t) + 2 * xi;
+                xf = make_xform(__ldg(tp), __ldg(tp + 1));
+                __syncwarp(gmask);  // previous pair's readers are done
+                // Polytope::new (epa3d.rs:41-45, 129-135): the 4 simplex points ...
+                for (int j = gl; j < 8; j += G) {
+                    const float4 r = C.W.simplex[(size_t)pair * 8 + j];
+                    if (j < 4) P.pv[j] = r;
+                    else pa[j - 4] = r;
+                }
+                __syncwarp(gmask);
+                // ... and Face::new (3,2,1) (3,1,0) (3,0,2) (2,0,1), epa3d.rs:201-208
+                for (int j = gl; j < 4; j += G) {
+                    const uint32_t tri = j == 0 ? 0x010203u : (j == 1 ? 0x000103u : (j == 2 ? 0x020003u : 0x010002u));
+                    ps_face_new(P, j, tri & 255u, (tri >> 8) & 255u, tri >> 16);
+                }
+                __syncwarp(gmask);
+                nv = 4;
+                nf = 4;
+                it = 1;
+                state = S_RUN;
+            }
+        }
+        if (__all_sync(0xffffffffu, state == S_EXIT)) break;
+
+        // closest_face_to_origin (epa3d.rs:137-145): first strictly smallest distance; a NaN at
+        // index 0 sticks.  Its normal is the next support direction.
+        {
+            float bd = INFINITY;
+            uint32_t bi = 0xFFFFFFFFu;
+            for (int f = gl; f < nf; f += G) {
+                float dd = P.fnd[f].w;
+                if (dd != dd) dd = INFINITY;  // NaN never compares smaller
+                if (dd < bd) { bd = dd; bi = (uint32_t)f; }  // f ascends: ties keep the first
+            }
+#pragma unroll
+            for (int off = G / 2; off >= 1; off >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, bd, off);
+                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ob < bd || (ob == bd && oi < bi)) { bd = ob; bi = oi; }
+            }
+            if (state == S_RUN) {
+                const float d0 = P.fnd[0].w;
+                best_face = (d0 != d0 || bi == 0xFFFFFFFFu) ? 0 : (int)bi;
+                const float4 fb = P.fnd[best_face];
+                d = mk3(fb.x, fb.y, fb.z);
+            }
+        }
+
+        // SupportPoint::from_minkowski(d), minkowski/mod.rs:39-60: even lanes left, odd lanes right
+        f3 sup_v, sup_a;
+        {
+            const f3 w = support_point(sh, xf, right ? -d : d);
+            const f3 o = mk3(__shfl_xor_sync(0xffffffffu, w.x, 1), __shfl_xor_sync(0xffffffffu, w.y, 1),
+                             __shfl_xor_sync(0xffffffffu, w.z, 1));
+            sup_a = right ? o : w;
+            sup_v = sup_a - (right ? w : o);
+        }
+
+        bool finished = false;
+        uint8_t result = ST_NONE;
+        contact_out co = zero_contact();
+        if (state == S_RUN) {  // epa3d.rs:46-64 with d == faces[best_face].normal
+            const float4 fb = P.fnd[best_face];
+            const f3 n = mk3(fb.x, fb.y, fb.z);
+            const float dd = dot(sup_v, n);
+            if (fsub(dd, fb.w) < epa_tol || it >= max_it) {
+                // contact(), epa3d.rs:84-114
+                const uint32_t idx = P.fidx[best_face];
+                const uint32_t i0 = idx & 255u, i1 = (idx >> 8) & 255u, i2 = (idx >> 16) & 255u;
+                float u, v, w;
+                barycentric_vector(n * fb.w, ps_pv(P, i0), ps_pv(P, i1), ps_pv(P, i2), u, v, w);
+                const float4 a0 = pa[i0], a1 = pa[i1], a2 = pa[i2];
+                co.normal = n;
+                co.depth = fb.w;
+                co.point = (mk3(a0.x, a0.y, a0.z) * u + mk3(a1.x, a1.y, a1.z) * v) +
+                           mk3(a2.x, a2.y, a2.z) * w;
+                finished = true;
+                result = ST_SOME;
+            } else {
+                // ---- Polytope::add (epa3d.rs:147-175) ------------------------------------------------
+                // (1) visibility of every face -> bit mask (uniform across the group)
+                bitmask<FW> vis;
+                vis.clear();
+                for (int f0 = 0; f0 < nf; f0 += G) {
+                    const int f = f0 + gl;
+                    bool v = false;
+                    if (f < nf) {
+                        const float4 fn = P.fnd[f];
+                        const uint32_t idx = P.fidx[f];
+                        v = dot(mk3(fn.x, fn.y, fn.z), sup_v - ps_pv(P, idx & 255u)) > 0.0f;
+                    }
+                    const uint32_t bits = (__ballot_sync(gmask, v) >> (gw * G)) & gbits;
+                    vis.or_bits(f0, bits);
+                }
+                // (2) the swap_remove sweep as a two-pointer walk over the mask: `i` climbs from the
+                //     front, `len` shrinks from the back; a visible face at slot i is examined, then
+                //     the tail face dropped into slot i is examined next, and so on.
+                int len = nf, nvis = 0, nmv = 0;
+                bool overflow = false;
+                {
+                    int i = vis.next(0);
+                    int cur = i;
+                    while (i >= 0 && i < len) {
+                        if (nvis >= OCAP) { overflow = true; break; }
+                        if (gl == 0) P.order[nvis] = (uint8_t)cur;
+                        ++nvis;
+                        vis.reset(cur);
+                        --len;
+                        if (i == len) break;
+                        if (vis.test(len)) {
+                            cur = len;
+                            continue;
+                        }
+                        if (gl == 0) {
+                            P.mv_dst[nmv] = (uint8_t)i;
+                            P.mv_src[nmv] = (uint8_t)len;
+                        }
+                        ++nmv;
+                        i = vis.next(i + 1);
+                        cur = i;
+                    }
+                }
+                __syncwarp(gmask);
+                // (3) horizon = edges of the examined faces, in examination order, whose reverse edge
+                //     is not an edge of an examined face (remove_or_add_edge, epa3d.rs:212-219).
+                //     One examined face per lane; its edges are (v0,v1) (v1,v2) (v2,v0).
+                bool dup = false;
+                if (!overflow) {
+                    for (int k = gl; k < nvis; k += G) {
+                        const uint32_t idx = P.fidx[P.order[k]];
+                        const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
+                        const uint32_t o0 = atomicOr(&P.adj[v0 * AW + (v1 >> 5)], 1u << (v1 & 31));
+                        const uint32_t o1 = atomicOr(&P.adj[v1 * AW + (v2 >> 5)], 1u << (v2 & 31));
+                        const uint32_t o2 = atomicOr(&P.adj[v2 * AW + (v0 >> 5)], 1u << (v0 & 31));
+                        dup |= ((o0 >> (v1 & 31)) | (o1 >> (v2 & 31)) | (o2 >> (v0 & 31))) & 1u;
+                    }
+                }
+                __syncwarp(gmask);
+                int ne = 0;
+                if (!overflow) {
+                    for (int k0 = 0; k0 < nvis; k0 += G) {
+                        const int k = k0 + gl;
+                        uint32_t keep = 0, v0 = 0, v1 = 0, v2 = 0;
+                        if (k < nvis) {
+                            const uint32_t idx = P.fidx[P.order[k]];
+                            v0 = idx & 255u; v1 = (idx >> 8) & 255u; v2 = (idx >> 16) & 255u;
+                            keep = (~(P.adj[v1 * AW + (v0 >> 5)] >> (v0 & 31)) & 1u) |
+                                   ((~(P.adj[v2 * AW + (v1 >> 5)] >> (v1 & 31)) & 1u) << 1) |
+                                   ((~(P.adj[v0 * AW + (v2 >> 5)] >> (v2 & 31)) & 1u) << 2);
+                        }
+                        uint32_t all = keep << (3 * gl);
+#pragma unroll
+                        for (int off = G / 2; off >= 1; off >>= 1) all |= __shfl_xor_sync(gmask, all, off);
+                        const uint32_t below = all & ((1u << (3 * gl)) - 1u);
+                        int pos = ne + __popc(below);
+                        if (keep & 1u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v0 | (v1 << 8)); ++pos; }
+                        if (keep & 2u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v1 | (v2 << 8)); ++pos; }
+                        if (keep & 4u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v2 | (v0 << 8)); }
+                        ne += __popc(all);
+                    }
+                }
+                dup = __any_sync(gmask, dup);
+                __syncwarp(gmask);
+                // (4) clear the adjacency bits again
+                for (int k = gl; k < nvis; k += G) {
+                    const uint32_t idx = P.fidx[P.order[k]];
+                    const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
+#pragma unroll
+                    for (int q = 0; q < AW; ++q) {
+                        P.adj[v0 * AW + q] = 0u;
+                        P.adj[v1 * AW + q] = 0u;
+                        P.adj[v2 * AW + q] = 0u;
+                    }
+                }
+                __syncwarp(gmask);
+                if (overflow || dup || ne > OCAP || nv >= VCAP || len + ne > FCAP) {
+                    finished = true;
+                    result = ST_SCRATCH_OVERFLOW;
+                } else {
+                    // (5) apply the swap_remove moves, append the vertex
+                    for (int m = gl; m < nmv; m += G) {
+                        const int dst = P.mv_dst[m], src = P.mv_src[m];
+                        P.fnd[dst] = P.fnd[src];
+                        P.fidx[dst] = P.fidx[src];
+                    }
+                    const uint32_t nn = (uint32_t)nv;
+                    if (gl == 0) {
+                        P.pv[nn] = make_float4(sup_v.x, sup_v.y, sup_v.z, 0.f);
+                        pa[nn] = make_float4(sup_a.x, sup_a.y, sup_a.z, 0.f);
+                    }
+                    ++nv;
+                    __syncwarp(gmask);
+                    // (6) build the new faces (one horizon edge per lane)
+                    for (int k = gl; k < ne; k += G) {
+                        const uint32_t e = P.elist[k];
+                        ps_face_new(P, len + k, nn, e & 255u, e >> 8);
+                    }
+                    nf = len + ne;
+                    ++it;
+                    __syncwarp(gmask);
+                    if (nf == 0) {  // faces[0] on an empty Vec panics (epa3d.rs:138)
+                        finished = true;
+                        result = ST_PANIC_EPA_EMPTY;
+                    }
+                }
+            }
+        }
+
+        if (finished) {
+            if (gl == 0) {
+                if (result == ST_SCRATCH_OVERFLOW && over_list) {
+                    const uint32_t h = atomicAdd(over_count, 1u);
+                    over_list[h] = pair;
+                } else {
+                    store_contact(A.out_contact, pair, CB2_FULL_RESOLUTION, co);
+                    A.out_status[pair] = result;
+                }
+            }
+            state = S_FETCH;
+            nf = 0;
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+constexpr int EPA_G = 4;
+constexpr int T0_F = 48, T0_V = 28, T0_O = 24;
+constexpr int T1_F = 96, T1_V = 52, T1_O = 48;
+constexpr int T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
+
+template <int G, int F, int V, int O>
+static int epa_blocks(int sm_count) {
+    auto kern = k_epa<G, F, V, O>;
+    const size_t smem = (size_t)(32 / G) * sizeof(poly_smem<F, V, O>);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    return per_sm * sm_count;
+}
+
+template <int G, int F, int V, int O>
+static cudaError_t launch_tier(const epa_args& C, int sm_count, cudaStream_t st) {
+    const size_t smem = (size_t)(32 / G) * sizeof(poly_smem<F, V, O>);
+    k_epa<G, F, V, O><<<epa_blocks<G, F, V, O>(sm_count), 32, smem, st>>>(C);
+    return cudaGetLastError();
+}
+
+size_t epa_pa_scratch_bytes(int sm_count) {
+    size_t m = 0;
+    const size_t a = (size_t)epa_blocks<EPA_G, T0_F, T0_V, T0_O>(sm_count) * (32 / EPA_G) * T0_V;
+    const size_t b = (size_t)epa_blocks<EPA_G, T1_F, T1_V, T1_O>(sm_count) * (32 / EPA_G) * T1_V;
+    const size_t c = (size_t)epa_blocks<EPA_G, T2_F, T2_V, T2_O>(sm_count) * (32 / EPA_G) * T2_V;
+    m = a > b ? a : b;
+    m = m > c ? m : c;
+    return m * sizeof(float4);
+}
+
+cudaError_t launch_epa_tiers(const narrow_args& A, const narrow_ws& W, int sm_count,
+                             cudaStream_t st, uint64_t* launches) {
+    epa_args C;
+    C.A = A;
+    C.W = W;
+    C.tier = 0;
+    cudaError_t e = launch_tier<EPA_G, T0_F, T0_V, T0_O>(C, sm_count, st);
+    if (e != cudaSuccess) return e;
+    C.tier = 1;
+    e = launch_tier<EPA_G, T1_F, T1_V, T1_O>(C, sm_count, st);
+    if (e != cudaSuccess) return e;
+    C.tier = 2;
+    e = launch_tier<EPA_G, T2_F, T2_V, T2_O>(C, sm_count, st);
+    *launches += 3;
+    return e;
+}
+
+}  // namespace cb2

@@ -8,6 +8,7 @@
 // symmetry of IEEE rounding — all while producing the same bits as the reference.
 #pragma once
 #include "cb2_math.cuh"
+#include "cb2_cells.cuh"
 #include "../../include/collision_b200.h"
 
 namespace cb2 {
@@ -25,30 +26,44 @@ enum : uint8_t {
 };
 
 // Device shape-table entry (32 B, two 128-bit loads).  h = half_dim for a Cuboid
-// (dim / 2, cuboid.rs:36 — exact), h.x = radius for a Sphere.
+// (dim / 2, cuboid.rs:36 — exact), h.x = radius for a Sphere, h.x = max |vertex| (rounded up)
+// for a ConvexPolyhedron.  cell_off / cell_cfg locate the polyhedron's support cells
+// (cb2_cells.cuh): cell_cfg = N | wide << 8.
 struct __align__(16) dshape {
     uint32_t kind;
     float hx, hy, hz;
-    uint32_t voff, vcnt, pad0, pad1;
+    uint32_t voff, vcnt, cell_off, cell_cfg;
+};
+
+// the device-resident shape table every narrow-phase kernel reads
+struct shape_table {
+    const dshape* shapes;
+    const float4* verts;   // polyhedron vertices, (x,y,z,0)
+    const uint4* cells;    // support-cell records of all polyhedra
+    const uint16_t* ext;   // support-cell extension pool
 };
 
 struct shape {
     uint32_t kind;
     f3 h;
-    const float4* verts;  // polyhedron vertices (x,y,z,0), 16-byte records
-    uint32_t vcnt;
+    poly_ref poly;
 };
 
-CB2_DI shape load_shape(const dshape* __restrict__ tab, const float4* __restrict__ verts,
-                        uint32_t idx) {
-    const float4* p = reinterpret_cast<const float4*>(tab + idx);
-    float4 a = __ldg(p);
-    float4 b = __ldg(p + 1);
+CB2_DI shape load_shape(const shape_table& T, uint32_t idx) {
+    const float4* p = reinterpret_cast<const float4*>(T.shapes + idx);
+    const float4 a = __ldg(p);
+    const float4 b = __ldg(p + 1);
     shape s;
     s.kind = __float_as_uint(a.x);
     s.h = mk3(a.y, a.z, a.w);
-    s.verts = verts + __float_as_uint(b.x);
-    s.vcnt = __float_as_uint(b.y);
+    s.poly.verts = T.verts + __float_as_uint(b.x);
+    s.poly.vcnt = __float_as_uint(b.y);
+    s.poly.cells = T.cells + __float_as_uint(b.z);
+    s.poly.ext = T.ext;
+    const uint32_t cfg = __float_as_uint(b.w);
+    s.poly.N = cfg & 0xFFu;
+    s.poly.wide = (cfg >> 8) & 1u;
+    s.poly.R = a.y;
     return s;
 }
 
@@ -80,30 +95,15 @@ CB2_DI f3 cuboid_local_support(f3 h, f3 d) {
 }
 // Sphere: sphere.rs:32-38
 CB2_DI f3 sphere_local_support(float r, f3 d) { return normalize_to(d, r); }
-// ConvexPolyhedron VertexOnly: polyhedron.rs:160-176 (one thread scans; the cooperative
-// kernel in cb2_poly.cu replaces this with a sub-warp scan + shuffle argmax)
-CB2_DI f3 poly_local_support_serial(const float4* __restrict__ verts, uint32_t n, f3 d) {
-    f3 best = zero3();
-    float best_dot = -INFINITY;
-    for (uint32_t i = 0; i < n; ++i) {
-        float4 v = __ldg(verts + i);
-        f3 p = mk3(v.x, v.y, v.z);
-        float dt = dot(p, d);
-        if (dt > best_dot) {
-            best_dot = dt;
-            best = p;
-        }
-    }
-    return best;
+// ConvexPolyhedron VertexOnly: polyhedron.rs:160-176 through the support cells (cb2_cells.cuh)
+CB2_DI f3 local_support(const shape& s, f3 d) {
+    if (s.kind == K_CUBOID) return cuboid_local_support(s.h, d);
+    if (s.kind == K_SPHERE) return sphere_local_support(s.h.x, d);
+    return poly_local_support(s.poly, d);
 }
 
 CB2_DI f3 support_point(const shape& s, const xform& t, f3 dir) {
-    f3 d = inverse_transform_vector(t, dir);
-    f3 p;
-    if (s.kind == K_CUBOID) p = cuboid_local_support(s.h, d);
-    else if (s.kind == K_SPHERE) p = sphere_local_support(s.h.x, d);
-    else p = poly_local_support_serial(s.verts, s.vcnt, d);
-    return transform_point(t, p);
+    return transform_point(t, local_support(s, inverse_transform_vector(t, dir)));
 }
 
 // ---- simplex in registers -----------------------------------------------------------------

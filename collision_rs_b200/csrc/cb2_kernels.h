@@ -9,10 +9,17 @@ namespace cb2 {
 
 struct dshape;
 
+// the device-resident shape table (mirrors cb2::shape_table in cb2_gjk.cuh)
+struct shape_table_args {
+    const dshape* shapes;     // 32-byte entries
+    const float4* verts;      // polyhedron vertices, (x,y,z,0)
+    const uint4* cells;       // support-cell records (cb2_cells.cuh)
+    const uint16_t* ext;      // support-cell extension pool
+};
+
 // All pointers are device pointers.
 struct narrow_args {
-    const dshape* shapes;     // device shape table (32-byte entries)
-    const float4* verts;      // polyhedron vertices, (x,y,z,0)
+    shape_table_args T;
     const uint32_t* l_shape;  // per pair; per BODY when pair_body != nullptr
     const uint32_t* r_shape;
     const float4* l_t;        // cb2_xform records as 2 x float4 (start pose for time of impact)
@@ -31,8 +38,7 @@ struct narrow_args {
 };
 
 struct aabb_args {
-    const dshape* shapes;
-    const float4* verts;
+    shape_table_args T;
     const uint32_t* shape;
     const float4* t;
     uint64_t n;
@@ -56,32 +62,31 @@ struct retry_ws {
 size_t retry_scratch_bytes();
 cudaError_t launch_overflow_retry(const narrow_args& A, const retry_ws& R, cudaStream_t st);
 
-// ---- classified (polyhedron-aware) intersection, cb2_poly.cu ----------------------------------
-constexpr int POLY_NC = 11;                  // size classes (0 = no polyhedron in the pair)
-constexpr int POLY_SUB = 16;                 // (Vl, Vr) sub-buckets per class
-constexpr int POLY_NB = POLY_NC * POLY_SUB;  // counting-sort buckets (fits the u8 key)
-struct poly_counters {                       // device-side bookkeeping, zeroed per batch
-    uint32_t hist[POLY_NB];
-    uint32_t start[POLY_NB];
-    uint32_t cursor[POLY_NB];
-    uint32_t class_begin[POLY_NC + 1];
-    uint32_t gjk_next[POLY_NC];              // work-queue cursors
-    uint32_t hit_count[POLY_NC];
-    uint32_t epa_next[POLY_NC];
-    uint32_t over_count;
-    uint32_t over_next;
+// ---- GJK -> EPA pipeline (cb2_narrow.cu: k_gjk_hits, cb2_epa.cu: k_epa) ------------------------
+struct epa_counters {        // device-side bookkeeping, zeroed per batch
+    uint32_t n_hits;         // FullResolution hits queued for tier 1
+    uint32_t n_over2;        // ... whose polytope outgrew tier 1
+    uint32_t n_over3;        // ... outgrew tier 2, plus curved pairs (queued here by k_gjk_hits)
+    uint32_t next[3];        // work-queue cursors of the three tiers
 };
-struct narrow_ws {       // per-stream device workspace, owned by the ctx
-    uint8_t* key;        // n bytes: bucket of each pair
-    uint32_t* perm;      // n words: pairs sorted by bucket
-    uint32_t* hits;      // n words: queue positions of FullResolution hits, per class range
-    uint32_t* over;      // n words: queue positions whose polytope outgrew the tier-1 scratch
-    float4* simplex;     // 6 x float4 per queue position (GJK terminal simplex -> EPA)
-    poly_counters* PC;
+struct narrow_ws {           // per-stream device workspace, owned by the ctx
+    uint32_t* hits;          // n words each: pair indices
+    uint32_t* over2;
+    uint32_t* over3;
+    float4* simplex;         // 8 x float4 per pair: GJK terminal simplex v[0..3], sup_a[0..3]
+    float4* pa;              // SupportPoint.sup_a scratch, per resident EPA group
+    epa_counters* EC;
 };
-cudaError_t launch_intersection_classified(const narrow_args& A, bool full, const narrow_ws& W,
-                                           int sm_count, uint32_t max_vcnt, cudaStream_t st,
-                                           uint64_t* launches);
+size_t epa_pa_scratch_bytes(int sm_count);
+cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, cudaStream_t st);
+cudaError_t launch_epa_tiers(const narrow_args& A, const narrow_ws& W, int sm_count,
+                             cudaStream_t st, uint64_t* launches);
+
+// ---- support cells (cb2_cells.cu) ---------------------------------------------------------------
+uint32_t cells_resolution(uint32_t vertex_count);
+cudaError_t build_support_cells(const dshape* d_shapes, const float4* d_verts, uint32_t n_shapes,
+                                uint32_t max_N, uint4* d_cells, uint16_t* d_ext, uint32_t ext_cap,
+                                uint32_t* d_ext_cursor, cudaStream_t st);
 cudaError_t launch_distance(const narrow_args& A, cudaStream_t st);
 cudaError_t launch_time_of_impact(const narrow_args& A, cudaStream_t st);
 cudaError_t launch_world_aabbs(const aabb_args& A, cudaStream_t st);

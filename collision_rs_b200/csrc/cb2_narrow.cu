@@ -15,6 +15,15 @@
 
 namespace cb2 {
 
+CB2_DI shape_table table_of(const shape_table_args& a) {
+    shape_table t;
+    t.shapes = a.shapes;
+    t.verts = a.verts;
+    t.cells = a.cells;
+    t.ext = a.ext;
+    return t;
+}
+
 struct pair_in {
     shape ls, rs;
     xform lt, rt;
@@ -228,8 +237,8 @@ CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const 
         li = __ldg(A.l_shape + i);
         ri = __ldg(A.r_shape + i);
     }
-    p.ls = load_shape(A.shapes, A.verts, li);
-    p.rs = load_shape(A.shapes, A.verts, ri);
+    p.ls = load_shape(table_of(A.T), li);
+    p.rs = load_shape(table_of(A.T), ri);
     p.lt = load_xform(lt, lx);
     p.rt = load_xform(rt, rx);
     // inverse_transform_vector(..).unwrap() panics when ulps_eq(scale, 0); every entry point
@@ -240,12 +249,8 @@ CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const 
 // ---- kernels -----------------------------------------------------------------------------------
 template <bool FULL>
 __global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
-    if (A.perm) {  // class-0 slice of a classified batch (cb2_poly.cu)
-        if (i >= __ldg(A.dev_count)) return;
-        i = __ldg(A.perm + i);
-    }
     pair_in p;
     contact_out c = zero_contact();
     uint8_t st = ST_NONE;
@@ -265,6 +270,60 @@ __global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
     }
     store_contact(A.out_contact, i, FULL ? CB2_FULL_RESOLUTION : CB2_COLLISION_ONLY, c);
     A.out_status[i] = st;
+}
+
+// GJK::intersect (gjk/mod.rs:101-146), thread per pair, as the first stage of the GJK -> EPA
+// pipeline: misses (and CollisionOnly hits) are final here; FullResolution hits hand their
+// terminal simplex to the cooperative EPA kernel (cb2_epa.cu) through a compacted work list.
+// Pairs with a Sphere go straight to the largest polytope tier (curved shapes run EPA to the
+// iteration cap: ~137 faces).
+template <bool FULL>
+__global__ void __launch_bounds__(128) k_gjk_hits(narrow_args A, narrow_ws W) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false, curved = false;
+    if (i < A.n) {
+        pair_in p;
+        uint8_t st = ST_NONE;
+        if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+            st = ST_PANIC_INV_SCALE;
+        } else {
+            simplex<FULL> s;
+            if (gjk_intersect<FULL>(p, A.settings.max_iterations, s)) {
+                st = ST_SOME;
+                if constexpr (FULL) {
+                    hit = true;
+                    curved = p.ls.kind == K_SPHERE || p.rs.kind == K_SPHERE;
+                    float4* o = W.simplex + i * 8;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        o[k] = make_float4(s.v[k].x, s.v[k].y, s.v[k].z, 0.f);
+                        o[4 + k] = make_float4(s.a[k].x, s.a[k].y, s.a[k].z, 0.f);
+                    }
+                }
+            }
+        }
+        if (!hit) {
+            store_contact(A.out_contact, i, FULL ? CB2_FULL_RESOLUTION : CB2_COLLISION_ONLY,
+                          zero_contact());
+            A.out_status[i] = st;
+        }
+    }
+    if constexpr (FULL) {
+        // warp-aggregated append to the tier-1 / tier-3 work lists
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned m1 = __ballot_sync(0xffffffffu, hit && !curved);
+        const unsigned m3 = __ballot_sync(0xffffffffu, hit && curved);
+        uint32_t b1 = 0, b3 = 0;
+        if (lane == 0) {
+            if (m1) b1 = atomicAdd(&W.EC->n_hits, __popc(m1));
+            if (m3) b3 = atomicAdd(&W.EC->n_over3, __popc(m3));
+        }
+        b1 = __shfl_sync(0xffffffffu, b1, 0);
+        b3 = __shfl_sync(0xffffffffu, b3, 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (hit && !curved) W.hits[b1 + __popc(m1 & below)] = (uint32_t)i;
+        if (hit && curved) W.over3[b3 + __popc(m3 & below)] = (uint32_t)i;
+    }
 }
 
 // GJK::distance, gjk/mod.rs:271-321
@@ -441,7 +500,7 @@ CB2_DI float rmax(float l, float r) { return (l < r) ? r : l; }  // aabb/mod.rs:
 __global__ void __launch_bounds__(256) k_world_aabbs(aabb_args A) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
-    const shape s = load_shape(A.shapes, A.verts, __ldg(A.shape + i));
+    const shape s = load_shape(table_of(A.T), __ldg(A.shape + i));
     const xform t = load_xform(A.t, i);
     f3 mn, mx;
     if (s.kind == K_SPHERE) {
@@ -454,8 +513,8 @@ __global__ void __launch_bounds__(256) k_world_aabbs(aabb_args A) {
     } else {
         mn = zero3();
         mx = zero3();
-        for (uint32_t k = 0; k < s.vcnt; ++k) {
-            const float4 v = __ldg(s.verts + k);
+        for (uint32_t k = 0; k < s.poly.vcnt; ++k) {
+            const float4 v = __ldg(s.poly.verts + k);
             // grow(): Aabb::new(min(self.min,p), max(self.max,p)) then Aabb3::new re-sorts
             const f3 a = mk3(rmin(mn.x, v.x), rmin(mn.y, v.y), rmin(mn.z, v.z));
             const f3 b = mk3(rmax(mx.x, v.x), rmax(mx.y, v.y), rmax(mx.z, v.z));
@@ -490,6 +549,12 @@ cudaError_t launch_intersection(const narrow_args& A, bool full, cudaStream_t st
     if (A.n == 0) return cudaSuccess;
     if (full) k_intersection<true><<<grid_for(A.n, 128), 128, 0, st>>>(A);
     else k_intersection<false><<<grid_for(A.n, 128), 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    if (full) k_gjk_hits<true><<<grid_for(A.n, 128), 128, 0, st>>>(A, W);
+    else k_gjk_hits<false><<<grid_for(A.n, 128), 128, 0, st>>>(A, W);
     return cudaGetLastError();
 }
 size_t retry_scratch_bytes() { return (size_t)RETRY_BLOCKS * RETRY_BYTES_PER_BLOCK; }

@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --page source --csv` SASS dump by CUDA source line.
 
-usage: ncu_by_line.py <ncu_sass.csv> <cubin> <mangled-kernel-substring> [top]
-The SASS instruction order of the report is aligned with `nvdisasm -g` line markers."""
+usage: ncu_by_line.py <ncu_sass.csv> <cubin> <mangled-kernel-substring> [top] [outer]
+The SASS instruction order of the report is aligned with `nvdisasm -gi` line markers.  With
+`outer`, an instruction is charged to the OUTERMOST line of its inline chain (the line of the
+kernel body that the inlined helper was called from) instead of the innermost one."""
 import csv
 import re
 import subprocess
@@ -11,7 +13,8 @@ from collections import defaultdict
 
 sass_csv, cubin, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+outer = len(sys.argv) > 5 and sys.argv[5] == "outer"
+dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
 # isolate the function
 m = re.search(r"\.text\.[^\n]*" + re.escape(kern) + r"[^\n]*:\n", dis)
 start = m.end()
@@ -19,10 +22,14 @@ nxt = re.search(r"\n\s*\.section|\n\.text\.", dis[start:])
 body = dis[start:start + nxt.start()] if nxt else dis[start:]
 lines = []  # (file, line) per instruction
 cur = ("?", 0)
+chain_open = False
 for ln in body.splitlines():
-    mm = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+    mm = re.search(r'//## File "([^"]+)", line (\d+)( inlined at)?', ln)
     if mm:
-        cur = (mm.group(1).split("/")[-1], int(mm.group(2)))
+        # a chain is printed innermost first; each entry but the last says "inlined at"
+        if outer or not chain_open:
+            cur = (mm.group(1).split("/")[-1], int(mm.group(2)))
+        chain_open = bool(mm.group(3))
         continue
     if re.search(r"/\*[0-9a-f]{4,}\*/\s+", ln) and ";" in ln:
         lines.append(cur)
