@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
     int nf = 0, nv = 0, best_face = 0;
 
     for (;;) {
+        // ================= FETCH (divergent: only groups that finished) ================================
         if (state == S_FETCH) {
             uint32_t k = 0;
             if (gl == 0) k = atomicAdd(cursor, 1u);
@@ -197,7 +198,6 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                 sh = load_shape(T, si);
                 const float4* tp = (right ? A.r_t : A.l_t) + 2 * xi;
                 xf = make_xform(__ldg(tp), __ldg(tp + 1));
-                __syncwarp(gmask);  // previous pair's readers are done
                 // Polytope::new (epa3d.rs:41-45, 129-135): the 4 simplex points ...
                 for (int j = gl; j < 8; j += G) {
                     const float4 r = C.W.simplex[(size_t)pair * 8 + j];
@@ -210,7 +210,6 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                     const uint32_t tri = j == 0 ? 0x010203u : (j == 1 ? 0x000103u : (j == 2 ? 0x020003u : 0x010002u));
                     ps_face_new(P, j, tri & 255u, (tri >> 8) & 255u, tri >> 16);
                 }
-                __syncwarp(gmask);
                 nv = 4;
                 nf = 4;
                 it = 1;
@@ -218,16 +217,25 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
             }
         }
         if (__all_sync(0xffffffffu, state == S_EXIT)) break;
+        __syncwarp();
+        // From here to the end of the iteration every phase is executed by the WHOLE warp in
+        // lockstep (trip counts are warp maxima, per-group work is predicated), so the 32/G
+        // groups share one instruction stream.
+        const bool run = state == S_RUN;
 
-        // closest_face_to_origin (epa3d.rs:137-145): first strictly smallest distance; a NaN at
-        // index 0 sticks.  Its normal is the next support direction.
+        // ================= closest_face_to_origin (epa3d.rs:137-145) ====================================
+        // first strictly smallest distance; a NaN at index 0 sticks.  Its normal is the next
+        // support direction.
         {
+            const int nf_max = __reduce_max_sync(0xffffffffu, nf);
             float bd = INFINITY;
             uint32_t bi = 0xFFFFFFFFu;
-            for (int f = gl; f < nf; f += G) {
-                float dd = P.fnd[f].w;
-                if (dd != dd) dd = INFINITY;  // NaN never compares smaller
-                if (dd < bd) { bd = dd; bi = (uint32_t)f; }  // f ascends: ties keep the first
+            for (int f = gl; f < nf_max; f += G) {
+                if (f < nf) {
+                    float dd = P.fnd[f].w;
+                    if (dd != dd) dd = INFINITY;  // NaN never compares smaller
+                    if (dd < bd) { bd = dd; bi = (uint32_t)f; }  // f ascends: ties keep the first
+                }
             }
 #pragma unroll
             for (int off = G / 2; off >= 1; off >>= 1) {
@@ -235,32 +243,176 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                 const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
                 if (ob < bd || (ob == bd && oi < bi)) { bd = ob; bi = oi; }
             }
-            if (state == S_RUN) {
+            if (run) {
                 const float d0 = P.fnd[0].w;
                 best_face = (d0 != d0 || bi == 0xFFFFFFFFu) ? 0 : (int)bi;
-                const float4 fb = P.fnd[best_face];
-                d = mk3(fb.x, fb.y, fb.z);
             }
         }
+        const float4 fb = run ? P.fnd[best_face] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const f3 n = mk3(fb.x, fb.y, fb.z);
 
-        // SupportPoint::from_minkowski(d), minkowski/mod.rs:39-60: even lanes left, odd lanes right
+        // ================= SupportPoint::from_minkowski(n), minkowski/mod.rs:39-60 ======================
+        // even lanes evaluate the left shape, odd lanes the right one
         f3 sup_v, sup_a;
         {
-            const f3 w = support_point(sh, xf, right ? -d : d);
+            const f3 w = support_point(sh, xf, right ? -n : n);
             const f3 o = mk3(__shfl_xor_sync(0xffffffffu, w.x, 1), __shfl_xor_sync(0xffffffffu, w.y, 1),
                              __shfl_xor_sync(0xffffffffu, w.z, 1));
             sup_a = right ? o : w;
             sup_v = sup_a - (right ? w : o);
         }
+        // epa3d.rs:46-64: stop when the new point is within tolerance of the face, or at the cap
+        const bool conv = run && (fsub(dot(sup_v, n), fb.w) < epa_tol || it >= max_it);
+        const bool add = run && !conv;
 
-        bool finished = false;
+        // ================= Polytope::add (epa3d.rs:147-175) =============================================
+        // (1) visibility of every face -> bit mask (uniform across the group)
+        bitmask<FW> vis;
+        vis.clear();
+        {
+            const int nf_max = __reduce_max_sync(0xffffffffu, add ? nf : 0);
+            for (int f0 = 0; f0 < nf_max; f0 += G) {
+                const int f = f0 + gl;
+                bool v = false;
+                if (add && f < nf) {
+                    const float4 fn = P.fnd[f];
+                    const uint32_t idx = P.fidx[f];
+                    v = dot(mk3(fn.x, fn.y, fn.z), sup_v - ps_pv(P, idx & 255u)) > 0.0f;
+                }
+                const uint32_t bits = (__ballot_sync(0xffffffffu, v) >> (gw * G)) & gbits;
+                vis.or_bits(f0, bits);
+            }
+        }
+        // (2) the swap_remove sweep as a two-pointer walk over the mask: `i` climbs from the front,
+        //     `len` shrinks from the back; a visible face at slot i is examined, then the tail face
+        //     dropped into slot i is examined next, and so on.  One walk step per warp iteration.
+        int len = nf, nvis = 0, nmv = 0;
+        bool overflow = false;
+        {
+            int i = vis.next(0);
+            int cur = i;
+            bool walking = add && i >= 0;
+            while (__any_sync(0xffffffffu, walking)) {
+                if (walking) {
+                    if (nvis >= OCAP) {
+                        overflow = true;
+                        walking = false;
+                    } else {
+                        if (gl == 0) P.order[nvis] = (uint8_t)cur;
+                        ++nvis;
+                        vis.reset(cur);
+                        --len;
+                        if (i == len) {
+                            walking = false;
+                        } else if (vis.test(len)) {
+                            cur = len;
+                        } else {
+                            if (gl == 0) {
+                                P.mv_dst[nmv] = (uint8_t)i;
+                                P.mv_src[nmv] = (uint8_t)len;
+                            }
+                            ++nmv;
+                            i = vis.next(i + 1);
+                            cur = i;
+                            walking = i >= 0 && i < len;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // (3) horizon = edges of the examined faces, in examination order, whose reverse edge is not
+        //     an edge of an examined face (remove_or_add_edge, epa3d.rs:212-219).  One examined face
+        //     per lane; its edges are (v0,v1) (v1,v2) (v2,v0).
+        const bool edges = add && !overflow;
+        const int nvis_max = __reduce_max_sync(0xffffffffu, edges ? nvis : 0);
+        bool dup = false;
+        for (int k = gl; k < nvis_max; k += G) {
+            if (edges && k < nvis) {
+                const uint32_t idx = P.fidx[P.order[k]];
+                const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
+                const uint32_t o0 = atomicOr(&P.adj[v0 * AW + (v1 >> 5)], 1u << (v1 & 31));
+                const uint32_t o1 = atomicOr(&P.adj[v1 * AW + (v2 >> 5)], 1u << (v2 & 31));
+                const uint32_t o2 = atomicOr(&P.adj[v2 * AW + (v0 >> 5)], 1u << (v0 & 31));
+                dup |= ((o0 >> (v1 & 31)) | (o1 >> (v2 & 31)) | (o2 >> (v0 & 31))) & 1u;
+            }
+        }
+        __syncwarp();
+        int ne = 0;
+        for (int k0 = 0; k0 < nvis_max; k0 += G) {
+            const int k = k0 + gl;
+            uint32_t keep = 0, v0 = 0, v1 = 0, v2 = 0;
+            if (edges && k < nvis) {
+                const uint32_t idx = P.fidx[P.order[k]];
+                v0 = idx & 255u; v1 = (idx >> 8) & 255u; v2 = (idx >> 16) & 255u;
+                keep = (~(P.adj[v1 * AW + (v0 >> 5)] >> (v0 & 31)) & 1u) |
+                       ((~(P.adj[v2 * AW + (v1 >> 5)] >> (v1 & 31)) & 1u) << 1) |
+                       ((~(P.adj[v0 * AW + (v2 >> 5)] >> (v2 & 31)) & 1u) << 2);
+            }
+            uint32_t all = keep << (3 * gl);
+#pragma unroll
+            for (int off = G / 2; off >= 1; off >>= 1) all |= __shfl_xor_sync(0xffffffffu, all, off);
+            int pos = ne + __popc(all & ((1u << (3 * gl)) - 1u));
+            if (keep & 1u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v0 | (v1 << 8)); ++pos; }
+            if (keep & 2u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v1 | (v2 << 8)); ++pos; }
+            if (keep & 4u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v2 | (v0 << 8)); }
+            ne += __popc(all);
+        }
+        dup = (__ballot_sync(0xffffffffu, dup) & gmask) != 0u;
+        __syncwarp();
+        // (4) clear the adjacency bits again
+        for (int k = gl; k < nvis_max; k += G) {
+            if (edges && k < nvis) {
+                const uint32_t idx = P.fidx[P.order[k]];
+                const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
+#pragma unroll
+                for (int q = 0; q < AW; ++q) {
+                    P.adj[v0 * AW + q] = 0u;
+                    P.adj[v1 * AW + q] = 0u;
+                    P.adj[v2 * AW + q] = 0u;
+                }
+            }
+        }
+        const bool spill = add && (overflow || dup || ne > OCAP || nv >= VCAP || len + ne > FCAP);
+        const bool grow = add && !spill;
+        __syncwarp();
+        // (5) apply the swap_remove moves, append the vertex
+        if (grow) {
+            for (int m = gl; m < nmv; m += G) {
+                const int dst = P.mv_dst[m], src = P.mv_src[m];
+                P.fnd[dst] = P.fnd[src];
+                P.fidx[dst] = P.fidx[src];
+            }
+            if (gl == 0) {
+                P.pv[nv] = make_float4(sup_v.x, sup_v.y, sup_v.z, 0.f);
+                pa[nv] = make_float4(sup_a.x, sup_a.y, sup_a.z, 0.f);
+            }
+        }
+        __syncwarp();
+        // (6) build the new faces (one horizon edge per lane)
+        {
+            const int ne_max = __reduce_max_sync(0xffffffffu, grow ? ne : 0);
+            for (int k = gl; k < ne_max; k += G) {
+                if (grow && k < ne) {
+                    const uint32_t e = P.elist[k];
+                    ps_face_new(P, len + k, (uint32_t)nv, e & 255u, e >> 8);
+                }
+            }
+        }
         uint8_t result = ST_NONE;
-        contact_out co = zero_contact();
-        if (state == S_RUN) {  // epa3d.rs:46-64 with d == faces[best_face].normal
-            const float4 fb = P.fnd[best_face];
-            const f3 n = mk3(fb.x, fb.y, fb.z);
-            const float dd = dot(sup_v, n);
-            if (fsub(dd, fb.w) < epa_tol || it >= max_it) {
+        if (grow) {
+            ++nv;
+            nf = len + ne;
+            ++it;
+            if (nf == 0) result = ST_PANIC_EPA_EMPTY;  // faces[0] on an empty Vec (epa3d.rs:138)
+        }
+        if (spill) result = ST_SCRATCH_OVERFLOW;
+        if (conv) result = ST_SOME;
+
+        // ================= finished pairs (divergent) ====================================================
+        if (result != ST_NONE) {
+            contact_out co = zero_contact();
+            if (conv) {
                 // contact(), epa3d.rs:84-114
                 const uint32_t idx = P.fidx[best_face];
                 const uint32_t i0 = idx & 255u, i1 = (idx >> 8) & 255u, i2 = (idx >> 16) & 255u;
@@ -271,139 +423,7 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                 co.depth = fb.w;
                 co.point = (mk3(a0.x, a0.y, a0.z) * u + mk3(a1.x, a1.y, a1.z) * v) +
                            mk3(a2.x, a2.y, a2.z) * w;
-                finished = true;
-                result = ST_SOME;
-            } else {
-                // ---- Polytope::add (epa3d.rs:147-175) ------------------------------------------------
-                // (1) visibility of every face -> bit mask (uniform across the group)
-                bitmask<FW> vis;
-                vis.clear();
-                for (int f0 = 0; f0 < nf; f0 += G) {
-                    const int f = f0 + gl;
-                    bool v = false;
-                    if (f < nf) {
-                        const float4 fn = P.fnd[f];
-                        const uint32_t idx = P.fidx[f];
-                        v = dot(mk3(fn.x, fn.y, fn.z), sup_v - ps_pv(P, idx & 255u)) > 0.0f;
-                    }
-                    const uint32_t bits = (__ballot_sync(gmask, v) >> (gw * G)) & gbits;
-                    vis.or_bits(f0, bits);
-                }
-                // (2) the swap_remove sweep as a two-pointer walk over the mask: `i` climbs from the
-                //     front, `len` shrinks from the back; a visible face at slot i is examined, then
-                //     the tail face dropped into slot i is examined next, and so on.
-                int len = nf, nvis = 0, nmv = 0;
-                bool overflow = false;
-                {
-                    int i = vis.next(0);
-                    int cur = i;
-                    while (i >= 0 && i < len) {
-                        if (nvis >= OCAP) { overflow = true; break; }
-                        if (gl == 0) P.order[nvis] = (uint8_t)cur;
-                        ++nvis;
-                        vis.reset(cur);
-                        --len;
-                        if (i == len) break;
-                        if (vis.test(len)) {
-                            cur = len;
-                            continue;
-                        }
-                        if (gl == 0) {
-                            P.mv_dst[nmv] = (uint8_t)i;
-                            P.mv_src[nmv] = (uint8_t)len;
-                        }
-                        ++nmv;
-                        i = vis.next(i + 1);
-                        cur = i;
-                    }
-                }
-                __syncwarp(gmask);
-                // (3) horizon = edges of the examined faces, in examination order, whose reverse edge
-                //     is not an edge of an examined face (remove_or_add_edge, epa3d.rs:212-219).
-                //     One examined face per lane; its edges are (v0,v1) (v1,v2) (v2,v0).
-                bool dup = false;
-                if (!overflow) {
-                    for (int k = gl; k < nvis; k += G) {
-                        const uint32_t idx = P.fidx[P.order[k]];
-                        const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
-                        const uint32_t o0 = atomicOr(&P.adj[v0 * AW + (v1 >> 5)], 1u << (v1 & 31));
-                        const uint32_t o1 = atomicOr(&P.adj[v1 * AW + (v2 >> 5)], 1u << (v2 & 31));
-                        const uint32_t o2 = atomicOr(&P.adj[v2 * AW + (v0 >> 5)], 1u << (v0 & 31));
-                        dup |= ((o0 >> (v1 & 31)) | (o1 >> (v2 & 31)) | (o2 >> (v0 & 31))) & 1u;
-                    }
-                }
-                __syncwarp(gmask);
-                int ne = 0;
-                if (!overflow) {
-                    for (int k0 = 0; k0 < nvis; k0 += G) {
-                        const int k = k0 + gl;
-                        uint32_t keep = 0, v0 = 0, v1 = 0, v2 = 0;
-                        if (k < nvis) {
-                            const uint32_t idx = P.fidx[P.order[k]];
-                            v0 = idx & 255u; v1 = (idx >> 8) & 255u; v2 = (idx >> 16) & 255u;
-                            keep = (~(P.adj[v1 * AW + (v0 >> 5)] >> (v0 & 31)) & 1u) |
-                                   ((~(P.adj[v2 * AW + (v1 >> 5)] >> (v1 & 31)) & 1u) << 1) |
-                                   ((~(P.adj[v0 * AW + (v2 >> 5)] >> (v2 & 31)) & 1u) << 2);
-                        }
-                        uint32_t all = keep << (3 * gl);
-#pragma unroll
-                        for (int off = G / 2; off >= 1; off >>= 1) all |= __shfl_xor_sync(gmask, all, off);
-                        const uint32_t below = all & ((1u << (3 * gl)) - 1u);
-                        int pos = ne + __popc(below);
-                        if (keep & 1u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v0 | (v1 << 8)); ++pos; }
-                        if (keep & 2u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v1 | (v2 << 8)); ++pos; }
-                        if (keep & 4u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v2 | (v0 << 8)); }
-                        ne += __popc(all);
-                    }
-                }
-                dup = __any_sync(gmask, dup);
-                __syncwarp(gmask);
-                // (4) clear the adjacency bits again
-                for (int k = gl; k < nvis; k += G) {
-                    const uint32_t idx = P.fidx[P.order[k]];
-                    const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
-#pragma unroll
-                    for (int q = 0; q < AW; ++q) {
-                        P.adj[v0 * AW + q] = 0u;
-                        P.adj[v1 * AW + q] = 0u;
-                        P.adj[v2 * AW + q] = 0u;
-                    }
-                }
-                __syncwarp(gmask);
-                if (overflow || dup || ne > OCAP || nv >= VCAP || len + ne > FCAP) {
-                    finished = true;
-                    result = ST_SCRATCH_OVERFLOW;
-                } else {
-                    // (5) apply the swap_remove moves, append the vertex
-                    for (int m = gl; m < nmv; m += G) {
-                        const int dst = P.mv_dst[m], src = P.mv_src[m];
-                        P.fnd[dst] = P.fnd[src];
-                        P.fidx[dst] = P.fidx[src];
-                    }
-                    const uint32_t nn = (uint32_t)nv;
-                    if (gl == 0) {
-                        P.pv[nn] = make_float4(sup_v.x, sup_v.y, sup_v.z, 0.f);
-                        pa[nn] = make_float4(sup_a.x, sup_a.y, sup_a.z, 0.f);
-                    }
-                    ++nv;
-                    __syncwarp(gmask);
-                    // (6) build the new faces (one horizon edge per lane)
-                    for (int k = gl; k < ne; k += G) {
-                        const uint32_t e = P.elist[k];
-                        ps_face_new(P, len + k, nn, e & 255u, e >> 8);
-                    }
-                    nf = len + ne;
-                    ++it;
-                    __syncwarp(gmask);
-                    if (nf == 0) {  // faces[0] on an empty Vec panics (epa3d.rs:138)
-                        finished = true;
-                        result = ST_PANIC_EPA_EMPTY;
-                    }
-                }
             }
-        }
-
-        if (finished) {
             if (gl == 0) {
                 if (result == ST_SCRATCH_OVERFLOW && over_list) {
                     const uint32_t h = atomicAdd(over_count, 1u);
@@ -416,6 +436,7 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
             state = S_FETCH;
             nf = 0;
         }
+        __syncwarp();
     }
 }
 
