@@ -54,11 +54,12 @@ static std::string g_create_err;
 
 static void free_ws(narrow_ws& w) {  // the per-pair buffers
     if (w.hits) cudaFree(w.hits);
-    if (w.over2) cudaFree(w.over2);
-    if (w.over3) cudaFree(w.over3);
+    if (w.over) cudaFree(w.over);
     if (w.simplex) cudaFree(w.simplex);
-    w.hits = w.over2 = w.over3 = nullptr;
-    w.simplex = nullptr;
+    if (w.dump) cudaFree(w.dump);
+    w.hits = w.over = nullptr;
+    w.simplex = w.dump = nullptr;
+    w.dump_cap = 0;
 }
 
 #define CK(ctx, x)                                                                     \
@@ -270,9 +271,12 @@ static int ensure_ws(cb2_ctx* c, int slot, uint64_t n) {
         free_ws(w);
         c->ws_cap[slot] = 0;
         CK(c, cudaMalloc(&w.hits, n * sizeof(uint32_t)));
-        CK(c, cudaMalloc(&w.over2, n * sizeof(uint32_t)));
-        CK(c, cudaMalloc(&w.over3, n * sizeof(uint32_t)));
+        CK(c, cudaMalloc(&w.over, n * sizeof(uint32_t)));
         CK(c, cudaMalloc(&w.simplex, n * 8 * sizeof(float4)));
+        // room for 1 pair in 8 to hand its polytope to tier 1 (more than that restart instead)
+        const uint64_t dc = n / 8 > 4096 ? n / 8 : (n < 4096 ? n : 4096);
+        CK(c, cudaMalloc(&w.dump, dc * epa_dump_record_bytes()));
+        w.dump_cap = (uint32_t)dc;
         c->ws_cap[slot] = n;
     }
     return CB2_OK;
@@ -314,7 +318,7 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
     cudaError_t e;
     if (op == OP_INTERSECTION && !c->legacy_epa) {
         // GJK (thread per pair) -> compacted hit list -> cooperative EPA tiers
-        if (A.n > 0xFFFFFFFFull) return fail(c, CB2_ERR_ARG, "more than 2^32-1 pairs in one batch");
+        if (A.n > 0x7FFFFFFFull) return fail(c, CB2_ERR_ARG, "more than 2^31-1 pairs in one batch");
         const bool full = strategy == CB2_FULL_RESOLUTION;
         int rc = ensure_ws(c, ws_slot, A.n);
         if (rc) return rc;

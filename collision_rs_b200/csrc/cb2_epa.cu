@@ -21,10 +21,12 @@
 //    shared memory.  That equals remove_or_add_edge's list (epa3d.rs:212-219) whenever no directed
 //    edge occurs twice; the (non-manifold) exception is detected by the same atomicOr and the
 //    pair goes to the serial second-chance kernel (cb2_narrow.cu).
-//  * The polytope lives in per-group shared memory in three tiers (48/28, 96/52, 208/104 faces /
-//    vertices; the last is the manifold worst case 2V-4 at the 100-iteration cap).  A pair that
-//    outgrows its tier is re-queued for the next one.  sup_a of each polytope vertex is only read
-//    by the final contact (epa3d.rs:84-114), so it lives in a global scratch, not shared memory.
+//  * The polytope lives in per-group shared memory in two tiers: 48 faces / 28 vertices (4 lanes
+//    per pair; covers ~92 % of pairs) and 208 / 104 (8 lanes per pair; the manifold worst case
+//    2V-4 at the 100-iteration cap).  A pair that outgrows tier 0 dumps its polytope to global
+//    memory and tier 1 RESUMES it at the same iteration (nothing is recomputed).  sup_a of each
+//    polytope vertex is only read by the final contact (epa3d.rs:84-114), so it lives in a
+//    global scratch, not shared memory.
 #include "cb2_gjk.cuh"
 #include "cb2_kernels.h"
 
@@ -110,17 +112,43 @@ struct bitmask {
     }
 };
 
+// up to 64 faces: one 64-bit register pair (the generic version above ends up in local memory,
+// nvcc turns its unrolled selects back into a dynamically indexed array)
+template <>
+struct bitmask<2> {
+    unsigned long long m;
+    CB2_DI void clear() { m = 0ull; }
+    CB2_DI void or_bits(int pos, uint32_t bits) { m |= (unsigned long long)bits << pos; }
+    CB2_DI bool test(int i) const { return (m >> i) & 1ull; }
+    CB2_DI void reset(int i) { m &= ~(1ull << i); }
+    CB2_DI int next(int from) const {
+        const unsigned long long v = from < 64 ? (m >> from) << from : 0ull;
+        return v ? __ffsll((long long)v) - 1 : -1;
+    }
+};
+template <>
+struct bitmask<1> : bitmask<2> {};
+
 struct epa_args {
     narrow_args A;
     narrow_ws W;
-    uint32_t tier;  // 0, 1, 2
+    uint32_t tier;  // 0, 1
+};
+
+// tier-0 polytope dump record, in float4 units: header (nf, nv, it) | fnd | pv | pa | fidx
+constexpr uint32_t OVER_RESUME = 0x80000000u;  // over-list entry flag: a dump record exists
+template <int F, int V>
+struct dump_layout {
+    static constexpr int FND = 1, PV = FND + F, PA = PV + V, FIDX = PA + V, SIZE = FIDX + (F + 3) / 4;
 };
 
 enum : int { S_FETCH = 0, S_RUN = 1, S_EXIT = 2 };
 
-template <int G, int FCAP, int VCAP, int OCAP>
+// RF/RV: caps of the tier whose dumps this instantiation resumes (0 = none)
+template <int G, int FCAP, int VCAP, int OCAP, int RF, int RV>
 __global__ void __launch_bounds__(32) k_epa(epa_args C) {
     static_assert(G == 2 || G == 4 || G == 8, "3*G edge-keep bits must fit one word");
+    static_assert(RF <= FCAP && RV <= VCAP, "a resumed polytope must fit");
     using PS = poly_smem<FCAP, VCAP, OCAP>;
     constexpr int FW = (FCAP + 31) / 32;
     constexpr int AW = PS::AW;
@@ -143,12 +171,9 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
     uint32_t* over_count;
     if (C.tier == 0) {
         list = C.W.hits; count = C.W.EC->n_hits;
-        over_list = C.W.over2; over_count = &C.W.EC->n_over2;
-    } else if (C.tier == 1) {
-        list = C.W.over2; count = C.W.EC->n_over2;
-        over_list = C.W.over3; over_count = &C.W.EC->n_over3;
+        over_list = C.W.over; over_count = &C.W.EC->n_over;
     } else {
-        list = C.W.over3; count = C.W.EC->n_over3;
+        list = C.W.over; count = C.W.EC->n_over;
         over_list = nullptr; over_count = nullptr;
     }
     uint32_t* cursor = &C.W.EC->next[C.tier];
@@ -184,7 +209,8 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                 sh.kind = K_CUBOID;
                 sh.h = zero3();
             } else {
-                pair = list[k];
+                const uint32_t entry = list[k];
+                pair = entry & ~OVER_RESUME;
                 uint32_t si;
                 uint64_t xi;
                 if (A.pair_body) {
@@ -198,21 +224,38 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                 sh = load_shape(T, si);
                 const float4* tp = (right ? A.r_t : A.l_t) + 2 * xi;
                 xf = make_xform(__ldg(tp), __ldg(tp + 1));
-                // Polytope::new (epa3d.rs:41-45, 129-135): the 4 simplex points ...
-                for (int j = gl; j < 8; j += G) {
-                    const float4 r = C.W.simplex[(size_t)pair * 8 + j];
-                    if (j < 4) P.pv[j] = r;
-                    else pa[j - 4] = r;
-                }
-                __syncwarp(gmask);
-                // ... and Face::new (3,2,1) (3,1,0) (3,0,2) (2,0,1), epa3d.rs:201-208
-                for (int j = gl; j < 4; j += G) {
-                    const uint32_t tri = j == 0 ? 0x010203u : (j == 1 ? 0x000103u : (j == 2 ? 0x020003u : 0x010002u));
-                    ps_face_new(P, j, tri & 255u, (tri >> 8) & 255u, tri >> 16);
-                }
                 nv = 4;
                 nf = 4;
                 it = 1;
+                if (RF > 0 && (entry & OVER_RESUME)) {
+                    // resume a polytope that outgrew the previous tier, at the same iteration
+                    using DL = dump_layout<RF, RV>;
+                    const float4* rec = C.W.dump + (size_t)k * DL::SIZE;
+                    const float4 h = rec[0];
+                    nf = (int)__float_as_uint(h.x);
+                    nv = (int)__float_as_uint(h.y);
+                    it = __float_as_uint(h.z);
+                    for (int j = gl; j < nf; j += G) P.fnd[j] = rec[DL::FND + j];
+                    for (int j = gl; j < nv; j += G) {
+                        P.pv[j] = rec[DL::PV + j];
+                        pa[j] = rec[DL::PA + j];
+                    }
+                    const uint32_t* fi = reinterpret_cast<const uint32_t*>(rec + DL::FIDX);
+                    for (int j = gl; j < nf; j += G) P.fidx[j] = fi[j];
+                } else {
+                    // Polytope::new (epa3d.rs:41-45, 129-135): the 4 simplex points ...
+                    for (int j = gl; j < 8; j += G) {
+                        const float4 r = C.W.simplex[(size_t)pair * 8 + j];
+                        if (j < 4) P.pv[j] = r;
+                        else pa[j - 4] = r;
+                    }
+                    __syncwarp(gmask);
+                    // ... and Face::new (3,2,1) (3,1,0) (3,0,2) (2,0,1), epa3d.rs:201-208
+                    for (int j = gl; j < 4; j += G) {
+                        const uint32_t tri = j == 0 ? 0x010203u : (j == 1 ? 0x000103u : (j == 2 ? 0x020003u : 0x010002u));
+                        ps_face_new(P, j, tri & 255u, (tri >> 8) & 255u, tri >> 16);
+                    }
+                }
                 state = S_RUN;
             }
         }
@@ -424,14 +467,31 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                 co.point = (mk3(a0.x, a0.y, a0.z) * u + mk3(a1.x, a1.y, a1.z) * v) +
                            mk3(a2.x, a2.y, a2.z) * w;
             }
-            if (gl == 0) {
-                if (result == ST_SCRATCH_OVERFLOW && over_list) {
-                    const uint32_t h = atomicAdd(over_count, 1u);
-                    over_list[h] = pair;
-                } else {
-                    store_contact(A.out_contact, pair, CB2_FULL_RESOLUTION, co);
-                    A.out_status[pair] = result;
+            if (result == ST_SCRATCH_OVERFLOW && over_list) {
+                // re-queue for the next tier, with the polytope as it stands (this iteration has
+                // not modified it) so that tier resumes instead of starting over
+                using DL = dump_layout<FCAP, VCAP>;
+                uint32_t h = 0;
+                if (gl == 0) h = atomicAdd(over_count, 1u);
+                h = __shfl_sync(gmask, h, gw * G);
+                const bool room = h < C.W.dump_cap;
+                if (room) {
+                    float4* rec = C.W.dump + (size_t)h * DL::SIZE;
+                    if (gl == 0)
+                        rec[0] = make_float4(__uint_as_float((uint32_t)nf), __uint_as_float((uint32_t)nv),
+                                             __uint_as_float(it), 0.f);
+                    for (int j = gl; j < nf; j += G) rec[DL::FND + j] = P.fnd[j];
+                    for (int j = gl; j < nv; j += G) {
+                        rec[DL::PV + j] = P.pv[j];
+                        rec[DL::PA + j] = pa[j];
+                    }
+                    uint32_t* fi = reinterpret_cast<uint32_t*>(rec + DL::FIDX);
+                    for (int j = gl; j < nf; j += G) fi[j] = P.fidx[j];
                 }
+                if (gl == 0) over_list[h] = pair | (room ? OVER_RESUME : 0u);
+            } else if (gl == 0) {
+                store_contact(A.out_contact, pair, CB2_FULL_RESOLUTION, co);
+                A.out_status[pair] = result;
             }
             state = S_FETCH;
             nf = 0;
@@ -441,14 +501,12 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-constexpr int EPA_G = 4;
-constexpr int T0_F = 48, T0_V = 28, T0_O = 24;
-constexpr int T1_F = 96, T1_V = 52, T1_O = 48;
-constexpr int T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
+constexpr int T0_G = 4, T0_F = 48, T0_V = 28, T0_O = 24;
+constexpr int T1_G = 8, T1_F = 208, T1_V = 104, T1_O = 96;  // manifold worst case at 100 iterations
 
-template <int G, int F, int V, int O>
+template <int G, int F, int V, int O, int RF, int RV>
 static int epa_blocks(int sm_count) {
-    auto kern = k_epa<G, F, V, O>;
+    auto kern = k_epa<G, F, V, O, RF, RV>;
     const size_t smem = (size_t)(32 / G) * sizeof(poly_smem<F, V, O>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
@@ -457,22 +515,19 @@ static int epa_blocks(int sm_count) {
     return per_sm * sm_count;
 }
 
-template <int G, int F, int V, int O>
+template <int G, int F, int V, int O, int RF, int RV>
 static cudaError_t launch_tier(const epa_args& C, int sm_count, cudaStream_t st) {
     const size_t smem = (size_t)(32 / G) * sizeof(poly_smem<F, V, O>);
-    k_epa<G, F, V, O><<<epa_blocks<G, F, V, O>(sm_count), 32, smem, st>>>(C);
+    k_epa<G, F, V, O, RF, RV><<<epa_blocks<G, F, V, O, RF, RV>(sm_count), 32, smem, st>>>(C);
     return cudaGetLastError();
 }
 
 size_t epa_pa_scratch_bytes(int sm_count) {
-    size_t m = 0;
-    const size_t a = (size_t)epa_blocks<EPA_G, T0_F, T0_V, T0_O>(sm_count) * (32 / EPA_G) * T0_V;
-    const size_t b = (size_t)epa_blocks<EPA_G, T1_F, T1_V, T1_O>(sm_count) * (32 / EPA_G) * T1_V;
-    const size_t c = (size_t)epa_blocks<EPA_G, T2_F, T2_V, T2_O>(sm_count) * (32 / EPA_G) * T2_V;
-    m = a > b ? a : b;
-    m = m > c ? m : c;
-    return m * sizeof(float4);
+    const size_t a = (size_t)epa_blocks<T0_G, T0_F, T0_V, T0_O, 0, 0>(sm_count) * (32 / T0_G) * T0_V;
+    const size_t b = (size_t)epa_blocks<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(sm_count) * (32 / T1_G) * T1_V;
+    return (a > b ? a : b) * sizeof(float4);
 }
+size_t epa_dump_record_bytes() { return dump_layout<T0_F, T0_V>::SIZE * sizeof(float4); }
 
 cudaError_t launch_epa_tiers(const narrow_args& A, const narrow_ws& W, int sm_count,
                              cudaStream_t st, uint64_t* launches) {
@@ -480,14 +535,11 @@ cudaError_t launch_epa_tiers(const narrow_args& A, const narrow_ws& W, int sm_co
     C.A = A;
     C.W = W;
     C.tier = 0;
-    cudaError_t e = launch_tier<EPA_G, T0_F, T0_V, T0_O>(C, sm_count, st);
+    cudaError_t e = launch_tier<T0_G, T0_F, T0_V, T0_O, 0, 0>(C, sm_count, st);
     if (e != cudaSuccess) return e;
     C.tier = 1;
-    e = launch_tier<EPA_G, T1_F, T1_V, T1_O>(C, sm_count, st);
-    if (e != cudaSuccess) return e;
-    C.tier = 2;
-    e = launch_tier<EPA_G, T2_F, T2_V, T2_O>(C, sm_count, st);
-    *launches += 3;
+    e = launch_tier<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(C, sm_count, st);
+    *launches += 2;
     return e;
 }
 

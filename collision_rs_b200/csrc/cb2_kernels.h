@@ -64,19 +64,21 @@ cudaError_t launch_overflow_retry(const narrow_args& A, const retry_ws& R, cudaS
 
 // ---- GJK -> EPA pipeline (cb2_narrow.cu: k_gjk_hits, cb2_epa.cu: k_epa) ------------------------
 struct epa_counters {        // device-side bookkeeping, zeroed per batch
-    uint32_t n_hits;         // FullResolution hits queued for tier 1
-    uint32_t n_over2;        // ... whose polytope outgrew tier 1
-    uint32_t n_over3;        // ... outgrew tier 2, plus curved pairs (queued here by k_gjk_hits)
-    uint32_t next[3];        // work-queue cursors of the three tiers
+    uint32_t n_hits;         // FullResolution hits queued for tier 0
+    uint32_t n_over;         // ... whose polytope outgrew tier 0, plus curved pairs (queued here
+                             //     directly by k_gjk_hits)
+    uint32_t next[2];        // work-queue cursors of the two tiers
 };
 struct narrow_ws {           // per-stream device workspace, owned by the ctx
     uint32_t* hits;          // n words each: pair indices
-    uint32_t* over2;
-    uint32_t* over3;
+    uint32_t* over;
     float4* simplex;         // 8 x float4 per pair: GJK terminal simplex v[0..3], sup_a[0..3]
     float4* pa;              // SupportPoint.sup_a scratch, per resident EPA group
+    float4* dump;            // tier-0 polytope dumps (dump_cap records), resumed by tier 1
+    uint32_t dump_cap;
     epa_counters* EC;
 };
+size_t epa_dump_record_bytes();
 size_t epa_pa_scratch_bytes(int sm_count);
 cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, cudaStream_t st);
 cudaError_t launch_epa_tiers(const narrow_args& A, const narrow_ws& W, int sm_count,
