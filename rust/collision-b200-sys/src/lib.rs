@@ -1,0 +1,153 @@
+//! Raw `extern "C"` declarations of `include/collision_b200.h` (ABI version 1).
+//!
+//! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Rust toolchain.  The structs are
+//! `#[repr(C)]` mirrors of the header; `tests/test_abi_cpu.py` checks the same sizes/offsets
+//! against the numpy dtypes the Python host uses, so the three views of the ABI stay in step.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const CB2_ABI_VERSION: u32 = 1;
+pub const CB2_MAX_ITERATIONS: u32 = 100;
+
+// cb2_error
+pub const CB2_OK: c_int = 0;
+pub const CB2_ERR_NO_DEVICE: c_int = -1;
+pub const CB2_ERR_CUDA: c_int = -2;
+pub const CB2_ERR_ARG: c_int = -3;
+pub const CB2_ERR_NOSPC: c_int = -4;
+pub const CB2_ERR_UNSUPPORTED: c_int = -5;
+pub const CB2_ERR_NAN: c_int = -6;
+
+// cb2_status (one byte per pair)
+pub const CB2_NONE: u8 = 0;
+pub const CB2_SOME: u8 = 1;
+pub const CB2_PANIC_UNWRAP_PLANE: u8 = 2;
+pub const CB2_PANIC_ASSERT_RANGE: u8 = 3;
+pub const CB2_PANIC_INV_SCALE: u8 = 4;
+pub const CB2_NONCONVERGED: u8 = 5;
+pub const CB2_PANIC_EPA_EMPTY: u8 = 6;
+pub const CB2_SCRATCH_OVERFLOW: u8 = 7;
+
+// cb2_strategy: contact.rs:16-22 discriminants in declaration order
+pub const CB2_FULL_RESOLUTION: u32 = 0;
+pub const CB2_COLLISION_ONLY: u32 = 1;
+
+// cb2_shape_kind
+pub const CB2_SPHERE: u32 = 0;
+pub const CB2_CUBOID: u32 = 1;
+pub const CB2_POLYHEDRON: u32 = 2;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct cb2_shape {
+    pub kind: u32,
+    pub p: [f32; 3],
+    pub vtx_off: u32,
+    pub vtx_cnt: u32,
+}
+
+/// cgmath `Decomposed<Vector3<f32>, Quaternion<f32>>` flattened (32 B).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct cb2_xform {
+    pub scale: f32,
+    pub qs: f32,
+    pub qx: f32,
+    pub qy: f32,
+    pub qz: f32,
+    pub dx: f32,
+    pub dy: f32,
+    pub dz: f32,
+}
+
+/// `Contact<Point3<f32>>` (contact.rs:30-46), 36 B.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct cb2_contact {
+    pub strategy: u32,
+    pub normal: [f32; 3],
+    pub penetration_depth: f32,
+    pub contact_point: [f32; 3],
+    pub time_of_impact: f32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct cb2_settings {
+    pub distance_tolerance: f32,
+    pub continuous_tolerance: f32,
+    pub epa_tolerance: f32,
+    pub max_iterations: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct cb2_aabb3 {
+    pub min: [f32; 3],
+    pub max: [f32; 3],
+}
+
+#[repr(C)]
+pub struct cb2_ctx {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn cb2_abi_version() -> u32;
+    pub fn cb2_default_settings(out: *mut cb2_settings);
+    pub fn cb2_create(device: c_int, out: *mut *mut cb2_ctx) -> c_int;
+    pub fn cb2_destroy(ctx: *mut cb2_ctx);
+    pub fn cb2_last_error(ctx: *const cb2_ctx) -> *const c_char;
+    pub fn cb2_device_sm_count(ctx: *const cb2_ctx) -> c_int;
+    pub fn cb2_kernel_launches(ctx: *const cb2_ctx) -> u64;
+
+    pub fn cb2_shapes_upload(ctx: *mut cb2_ctx, shapes: *const cb2_shape, n_shapes: u32,
+                             verts_xyz: *const f32, n_verts: u64) -> c_int;
+
+    pub fn cb2_gjk3_intersection(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                 l_shape: *const u32, r_shape: *const u32,
+                                 l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                 out: *mut cb2_contact, status: *mut u8) -> c_int;
+    pub fn cb2_gjk3_distance(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                             l_shape: *const u32, r_shape: *const u32,
+                             l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                             out: *mut f32, status: *mut u8) -> c_int;
+    pub fn cb2_gjk3_time_of_impact(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                   l_shape: *const u32, r_shape: *const u32,
+                                   l_t0: *const cb2_xform, l_t1: *const cb2_xform,
+                                   r_t0: *const cb2_xform, r_t1: *const cb2_xform, n: u64,
+                                   iter_cap: u32, out: *mut cb2_contact, status: *mut u8) -> c_int;
+
+    pub fn cb2_gjk3_intersection_dev(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                     l_shape: *const u32, r_shape: *const u32,
+                                     l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                     out: *mut cb2_contact, status: *mut u8, stream: *mut c_void) -> c_int;
+    pub fn cb2_gjk3_distance_dev(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                 l_shape: *const u32, r_shape: *const u32,
+                                 l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                 out: *mut f32, status: *mut u8, stream: *mut c_void) -> c_int;
+    pub fn cb2_gjk3_time_of_impact_dev(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                       l_shape: *const u32, r_shape: *const u32,
+                                       l_t0: *const cb2_xform, l_t1: *const cb2_xform,
+                                       r_t0: *const cb2_xform, r_t1: *const cb2_xform, n: u64,
+                                       iter_cap: u32, out: *mut cb2_contact, status: *mut u8,
+                                       stream: *mut c_void) -> c_int;
+    pub fn cb2_gjk3_intersection_bodies_dev(ctx: *mut cb2_ctx, strategy: u32,
+                                            settings: *const cb2_settings,
+                                            body_shape: *const u32, body_t: *const cb2_xform,
+                                            pair_body: *const u32, n: u64,
+                                            out: *mut cb2_contact, status: *mut u8,
+                                            stream: *mut c_void) -> c_int;
+
+    pub fn cb2_sap3_find_collider_pairs(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
+                                        axis_inout: *mut u32, perm_out: *mut u32,
+                                        pairs_out: *mut u32, cap: u64, n_pairs: *mut u64) -> c_int;
+    pub fn cb2_sap3_find_collider_pairs_dev(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
+                                            axis: u32, perm_out: *mut u32, pairs_out: *mut u32,
+                                            cap: u64, n_pairs: *mut u64, stream: *mut c_void) -> c_int;
+
+    pub fn cb2_world_aabbs(ctx: *mut cb2_ctx, shape: *const u32, t: *const cb2_xform, n: u64,
+                           out: *mut cb2_aabb3) -> c_int;
+    pub fn cb2_world_aabbs_dev(ctx: *mut cb2_ctx, shape: *const u32, t: *const cb2_xform, n: u64,
+                               out: *mut cb2_aabb3, stream: *mut c_void) -> c_int;
+}

@@ -7,6 +7,7 @@ order, so these tests assert the STRONGER property: every f32 bit-identical (NaN
 import numpy as np
 import pytest
 
+from collision_rs_b200 import abi as host_abi
 from collision_rs_b200 import workloads as W
 from collision_rs_b200.host import (Cb2Error, CollisionStrategy, ConvexPolyhedron, Cuboid,
                                     Decomposed, GJK3, ReferencePanic, Sphere, SweepAndPrune3)
@@ -374,3 +375,92 @@ def test_sap_nan_is_rejected_loudly(ctx):
     with pytest.raises(Cb2Error) as e:
         ctx.sap3(w["aabbs"], axis=0)
     assert e.value.code == -6
+
+
+# ---- support cells (csrc/cb2_cells.cuh) against the plain vertex scan ---------------------------
+def _ctx_with_env(**env):
+    """A second context created under environment toggles the C ABI reads in cb2_create."""
+    import os
+    from collision_rs_b200 import host
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return host.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_support_cells_match_full_scan_on_a_million_pairs(ctx):
+    """The cube-map candidate lists must return the very vertex the O(V) scan returns: compare
+    the whole pipeline with CB2_NO_CELLS=1 (every polyhedron support = full scan) on 1M pairs
+    (~25M support queries; the oracle can only afford a few thousand pairs)."""
+    w = W.cfg3_polyhedron_pairs(1_000_000, seed=4321)
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    ctx.upload_shapes(w["shapes"], w["verts"])
+    got, gst = ctx.intersection(0, *args)
+    gd, gdst = ctx.distance(*args)
+    plain = _ctx_with_env(CB2_NO_CELLS=1)
+    try:
+        plain.upload_shapes(w["shapes"], w["verts"])
+        exp, est = plain.intersection(0, *args)
+        ed, edst = plain.distance(*args)
+    finally:
+        plain.close()
+    assert_contacts_equal(got, gst, exp, est, "cells vs full scan")
+    assert np.array_equal(gdst, edst)
+    assert bits_equal(gd[edst == 1], ed[edst == 1]).all()
+
+
+def test_degenerate_polyhedra(ctx, oracle):
+    """Hulls the cell construction must not trip over: interior points, duplicated vertices,
+    coplanar and collinear point sets, a single point, tiny and huge coordinates."""
+    rng = np.random.default_rng(77)
+    verts, shapes = [], []
+
+    def add(p):
+        s = np.zeros(1, host_abi.SHAPE_DT)
+        s["kind"] = host_abi.POLYHEDRON
+        s["vtx_off"] = sum(len(v) for v in verts)
+        s["vtx_cnt"] = len(p)
+        verts.append(np.asarray(p, np.float32))
+        shapes.append(s)
+
+    sph = rng.standard_normal((60, 3))
+    sph /= np.linalg.norm(sph, axis=1, keepdims=True)
+    add(np.concatenate([sph, 0.3 * sph[:20], np.zeros((3, 3))]))            # interior points
+    add(np.concatenate([sph[:30], sph[:30]]))                                # every vertex twice
+    add(np.c_[rng.uniform(-1, 1, (40, 2)), np.zeros(40)])                    # coplanar
+    add(np.c_[np.linspace(-1, 1, 20), np.zeros(20), np.zeros(20)])           # collinear
+    add(np.zeros((12, 3)))                                                   # all at the origin
+    add(sph[:48] * 1e-12)                                                    # tiny
+    add(sph[:48] * 1e12)                                                     # huge
+    cube = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], float)
+    add(np.concatenate([cube, cube * 0.999999, rng.uniform(-1, 1, (30, 3))]))  # near-ties
+    add(rng.integers(-2, 3, (300, 3)).astype(float))                         # lattice: exact ties, u16
+    shapes = np.concatenate(shapes)
+    pv = np.concatenate(verts)
+    n = 3_000
+    l = rng.integers(0, len(shapes), n).astype(np.uint32)
+    r = rng.integers(0, len(shapes), n).astype(np.uint32)
+    lt, rt = W.random_xforms(rng, n, 0.6), W.random_xforms(rng, n, 0.6)
+    ctx.upload_shapes(shapes, pv)
+    exp, est = oracle.intersection(1, shapes, pv, l, r, lt, rt, nthreads=8)
+    got, gst = ctx.intersection(1, l, r, lt, rt)
+    assert_contacts_equal(got, gst, exp, est, "degenerate hulls CollisionOnly")
+    # FullResolution: flat / collinear hulls make EPA grow non-manifold polytopes without bound
+    # (the reference's Vec reaches 32k faces here).  The device keeps at most 16384 faces in its
+    # second-chance scratch; past that it must say CB2_SCRATCH_OVERFLOW, never a wrong contact.
+    exp, est, stats = oracle.intersection(0, shapes, pv, l, r, lt, rt, nthreads=8, want_stats=True)
+    got, gst = ctx.intersection(0, l, r, lt, rt)
+    fits = stats[:, 2] <= 16384
+    assert (gst[~fits] == 7).all()
+    assert fits.sum() > 0.99 * n
+    assert_contacts_equal(got[fits], gst[fits], exp[fits], est[fits], "degenerate hulls FullResolution")
+    ed, est = oracle.distance(shapes, pv, l, r, lt, rt, nthreads=8)
+    gd, gst = ctx.distance(l, r, lt, rt)
+    assert np.array_equal(gst, est)
+    assert bits_equal(gd[est == 1], ed[est == 1]).all()
