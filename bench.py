@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=4_000_000, help="pairs per GPU per step")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs")
-    ap.add_argument("--cpu-sample", type=int, default=150_000)
+    ap.add_argument("--cpu-sample", type=int, default=4_000_000,
+                    help="pairs of the workload the CPU oracle port is timed on")
     return ap.parse_args()
 
 
@@ -99,14 +100,28 @@ class ClockSampler:
 
 def algorithmic_flops_per_pair(w, sample=20_000):
     """Algorithmic flops = f32 + - * / sqrt the REFERENCE algorithm executes (oracle op counter),
-    measured on a prefix sample of this very workload."""
+    measured on a prefix sample of this very workload.  Returns (whole pass, GJK stage only):
+    the CollisionOnly strategy stops after GJK::intersect, so the difference is EPA3::process."""
     from oracle.binding import Oracle
     oc = Oracle(count_ops=True)
     m = min(sample, len(w["l_shape"]))
-    oc.ops_reset()
-    oc.intersection(0, w["shapes"], w["verts"], w["l_shape"][:m], w["r_shape"][:m],
-                    w["l_t"][:m], w["r_t"][:m], nthreads=1)
-    return oc.ops_reset() / m
+    out = []
+    for strategy in (0, 1):
+        oc.ops_reset()
+        oc.intersection(strategy, w["shapes"], w["verts"], w["l_shape"][:m], w["r_shape"][:m],
+                        w["l_t"][:m], w["r_t"][:m], nthreads=1)
+        out.append(oc.ops_reset() / m)
+    return out[0], out[1]
+
+
+def profiled_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json: bytes per pair), scaled to this launch."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["k_epa_dram_bytes_per_pair"] * n
 
 
 def cpu_baseline(w, sample, threads=None):
@@ -190,15 +205,11 @@ def main():
     w = W.cfg3_polyhedron_pairs(n, shard=rank)
     shapes, verts = w["shapes"], w["verts"]
     if world > 1:
-        ts = torch.from_numpy(shapes.view(np.uint8).reshape(-1).copy()).to(dev)
-        tv = torch.from_numpy(verts.reshape(-1).copy()).to(dev)
-        if rank != 0:
-            ts.zero_()
-            tv.zero_()
-        dist.broadcast(ts, 0)
-        dist.broadcast(tv, 0)
-        shapes = ts.cpu().numpy().view(SHAPE_DT)
-        verts = tv.cpu().numpy().reshape(-1, 3)
+        # the shape / vertex tables travel once over NCCL (NVLink); every rank rebuilds its
+        # support cells from them.  No collective on the data path (collision_rs_b200/sharding.py).
+        from collision_rs_b200.sharding import broadcast_shape_table
+        shapes, verts = broadcast_shape_table(shapes if rank == 0 else None,
+                                              verts if rank == 0 else None, src=0, device=dev)
         assert np.array_equal(shapes, w["shapes"]) and np.array_equal(verts, w["verts"])
     ctx.upload_shapes(shapes, verts)
 
@@ -229,6 +240,16 @@ def main():
     # ---- device-resident timing (value) ------------------------------------------------------------
     for _ in range(max(a.warmup, 3)):
         step_dev()
+    barrier()
+    # per-stage CUDA events (on the launching stream) of one more untimed pass: the dominant
+    # kernel's live duration for the roofline
+    ctx.set_stage_timing(True)
+    stage_runs = []
+    for _ in range(3):
+        step_dev()
+        stage_runs.append(ctx.last_stage_ms())
+    ctx.set_stage_timing(False)
+    stage_ms = [float(x) for x in np.mean(np.asarray(stage_runs), axis=0)]
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.kernel_launches
@@ -281,23 +302,36 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------
-    flops_pair = algorithmic_flops_per_pair(w)
-    kernel_ms = float(np.mean(per_step))  # one intersection pass per step; events bracket it
-    achieved = flops_pair * n / (kernel_ms * 1e-3) / 1e12
+    # ---- roofline of the dominant kernel: k_epa (EPA3::process, both shared-memory tiers) -------------
+    flops_pair, flops_gjk_pair = algorithmic_flops_per_pair(w)
+    step_ms = float(np.mean(per_step))  # one intersection pass per step; events bracket it
+    epa_ms = stage_ms[1] + stage_ms[2]
+    epa_flops = (flops_pair - flops_gjk_pair) * n
+    achieved = epa_flops / (epa_ms * 1e-3) / 1e12
     peak_lib = C.CDLL(os.path.join(ROOT, "collision_rs_b200", "libcb2_peak.so"))
     peak_lib.cb2_peak_fp32_tflops.restype = C.c_double
     fp32_peak = float(peak_lib.cb2_peak_fp32_tflops(local))
     hbm_peak, hbm_src = peaks()
     bytes_pair = 2 * 4 + 2 * XFORM_DT.itemsize + CONTACT_DT.itemsize + 1
-    hbm_achieved = bytes_pair * n / (kernel_ms * 1e-3) / 1e9
+    hbm_achieved = bytes_pair * n / (step_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": None,
-        "peak_source": "FFMA micro-benchmark measured in this run (libcb2_peak.so); "
-                       "parity forbids FMA so the reachable ceiling is peak/2",
+        "bound": "fp32", "kernel": "k_epa (EPA3::process; tier 0 + tier 1 launches)",
+        "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": achieved / fp32_peak if fp32_peak > 0 else None,
+        "traffic": profiled_traffic(n),
+        "peak_source": "FFMA micro-benchmark measured in this run (libcb2_peak.so; "
+                       "MEASURED_PEAKS.json has no FP32 figure); parity forbids FMA so the "
+                       "reachable ceiling is peak/2",
         "frac_of_unfused_peak": 2 * achieved / fp32_peak if fp32_peak > 0 else None,
-        "algorithmic_flops_per_pair": flops_pair, "kernel_ms": kernel_ms,
+        "algorithmic_flops_per_pair": {"pass": flops_pair, "gjk": flops_gjk_pair,
+                                       "epa": flops_pair - flops_gjk_pair},
+        "how": "algorithmic flops = f32 + - * / sqrt the reference executes for these pairs "
+               "(oracle op counter, incl. its O(V) vertex scans that the support cells avoid)",
+        "kernel_ms": epa_ms,
+        "stage_ms": {"k_gjk_hits": stage_ms[0], "k_epa_tier0": stage_ms[1],
+                     "k_epa_tier1": stage_ms[2], "second_chance": stage_ms[3]},
+        "step": {"ms": step_ms, "achieved": flops_pair * n / (step_ms * 1e-3) / 1e12,
+                 "frac": flops_pair * n / (step_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak > 0 else None},
         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_achieved / hbm_peak, "bytes_per_pair": bytes_pair,
                 "peak_source": hbm_src},

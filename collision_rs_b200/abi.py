@@ -42,7 +42,8 @@ class Settings(C.Structure):
 # every symbol include/collision_b200.h declares
 SYMBOLS = [
     "cb2_abi_version", "cb2_default_settings", "cb2_create", "cb2_destroy", "cb2_last_error",
-    "cb2_device_sm_count", "cb2_kernel_launches", "cb2_shapes_upload",
+    "cb2_device_sm_count", "cb2_kernel_launches", "cb2_set_stage_timing", "cb2_last_stage_ms",
+    "cb2_shapes_upload",
     "cb2_gjk3_intersection", "cb2_gjk3_distance", "cb2_gjk3_time_of_impact",
     "cb2_gjk3_intersection_dev", "cb2_gjk3_distance_dev", "cb2_gjk3_time_of_impact_dev",
     "cb2_gjk3_intersection_bodies_dev",
@@ -75,6 +76,8 @@ def load():
     lib.cb2_device_sm_count.argtypes = [vp]
     lib.cb2_kernel_launches.argtypes = [vp]
     lib.cb2_kernel_launches.restype = u64
+    lib.cb2_set_stage_timing.argtypes = [vp, i32]
+    lib.cb2_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     lib.cb2_shapes_upload.argtypes = [vp, vp, u32, vp, u64]
     sp = C.POINTER(Settings)
     lib.cb2_gjk3_intersection.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp]

@@ -45,6 +45,13 @@ struct cb2_ctx {
     narrow_ws ws[NS] = {};
     uint64_t ws_cap[NS] = {0, 0};
     retry_ws retry[NS] = {};
+    // optional stage timing (cb2_set_stage_timing): events around GJK | EPA tier 0 | EPA tier 1 |
+    // second-chance, recorded on the launching stream of the LAST device-buffer intersection
+    bool stage_timing = false;
+    cudaEvent_t stage_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stage_stream = nullptr;
+    bool stage_valid = false;
+    uint64_t chunk_pairs = 1u << 19;  // host-API pipeline granularity (CB2_CHUNK_PAIRS overrides)
     bool has_poly = false;
     bool legacy_epa = false;  // CB2_LEGACY_EPA=1: thread-per-pair EPA in local memory (A/B testing)
     bool no_cells = false;    // CB2_NO_CELLS=1: polyhedron support by full vertex scan (A/B testing)
@@ -122,6 +129,8 @@ int cb2_create(int device, cb2_ctx** out) {
     {
         const char* e1 = std::getenv("CB2_LEGACY_EPA");
         const char* e2 = std::getenv("CB2_NO_CELLS");
+        const char* e3 = std::getenv("CB2_CHUNK_PAIRS");
+        if (e3 && std::atoll(e3) > 0) c->chunk_pairs = (uint64_t)std::atoll(e3);
         c->legacy_epa = e1 && e1[0] == '1';
         c->no_cells = e2 && e2[0] == '1';
     }
@@ -139,6 +148,8 @@ void cb2_destroy(cb2_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    for (int k = 0; k < 5; ++k)
+        if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     for (int i = 0; i < cb2_ctx::NS; ++i) {
         if (c->d_stage[i]) cudaFree(c->d_stage[i]);
         if (c->done[i]) cudaEventDestroy(c->done[i]);
@@ -165,6 +176,26 @@ void cb2_destroy(cb2_ctx* c) {
 const char* cb2_last_error(const cb2_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
 int cb2_device_sm_count(const cb2_ctx* c) { return c ? c->sm_count : 0; }
 uint64_t cb2_kernel_launches(const cb2_ctx* c) { return c ? c->launches : 0; }
+
+int cb2_set_stage_timing(cb2_ctx* c, int on) {
+    if (!c) return CB2_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    if (on)
+        for (int k = 0; k < 5; ++k)
+            if (!c->stage_ev[k]) CK(c, cudaEventCreate(&c->stage_ev[k]));
+    c->stage_timing = on != 0;
+    c->stage_valid = false;
+    return CB2_OK;
+}
+
+int cb2_last_stage_ms(cb2_ctx* c, float* out4) {
+    if (!c || !out4) return CB2_ERR_ARG;
+    if (!c->stage_valid) return fail(c, CB2_ERR_ARG, "no timed FullResolution intersection yet");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaEventSynchronize(c->stage_ev[4]));
+    for (int k = 0; k < 4; ++k) CK(c, cudaEventElapsedTime(&out4[k], c->stage_ev[k], c->stage_ev[k + 1]));
+    return CB2_OK;
+}
 
 int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
                       const float* verts_xyz, uint64_t n_verts) {
@@ -293,6 +324,10 @@ static int ensure_retry(cb2_ctx* c, int slot) {
 static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A,
                            cudaStream_t st, int ws_slot);
 
+static void mark_stage(cb2_ctx* c, int k, cudaStream_t st) {
+    if (c->stage_timing && c->stage_ev[k]) cudaEventRecord(c->stage_ev[k], st);
+}
+
 static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, cudaStream_t st,
                      int ws_slot = 0) {
     int rc = launch_op_inner(c, op, strategy, A, st, ws_slot);
@@ -302,6 +337,11 @@ static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, 
     if (rc) return rc;
     cudaError_t e = launch_overflow_retry(A, c->retry[ws_slot], st);
     c->launches += 2;
+    mark_stage(c, 4, st);
+    if (c->stage_timing) {
+        c->stage_stream = st;
+        c->stage_valid = !c->legacy_epa;
+    }
     if (e != cudaSuccess) {
         c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
         return CB2_ERR_CUDA;
@@ -324,9 +364,17 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
         if (rc) return rc;
         const narrow_ws& W = c->ws[ws_slot];
         CK(c, cudaMemsetAsync(W.EC, 0, sizeof(epa_counters), st));
+        mark_stage(c, 0, st);
         e = launch_gjk_hits(A, full, W, st);
         ++c->launches;
-        if (e == cudaSuccess && full) e = launch_epa_tiers(A, W, c->sm_count, st, &c->launches);
+        mark_stage(c, 1, st);
+        if (e == cudaSuccess && full) {
+            e = launch_epa_tier(0, A, W, c->sm_count, st);
+            mark_stage(c, 2, st);
+            if (e == cudaSuccess) e = launch_epa_tier(1, A, W, c->sm_count, st);
+            mark_stage(c, 3, st);
+            c->launches += 2;
+        }
         if (e != cudaSuccess) {
             c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
             return CB2_ERR_CUDA;
@@ -398,7 +446,7 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
         if (l_shape[i] >= c->n_shapes || r_shape[i] >= c->n_shapes)
             return fail(c, CB2_ERR_ARG, "shape index out of range");
     CK(c, cudaSetDevice(c->device));
-    const uint64_t chunk = n < (1u << 19) ? n : (1u << 19);
+    const uint64_t chunk = n < c->chunk_pairs ? n : c->chunk_pairs;
     const int n_xf = op == OP_TOI ? 4 : 2;
     const size_t out_rec = op == OP_DISTANCE ? sizeof(float) : sizeof(cb2_contact);
     // staging layout per stream: xforms | l_shape | r_shape | out | status   (256-byte aligned)

@@ -529,18 +529,14 @@ size_t epa_pa_scratch_bytes(int sm_count) {
 }
 size_t epa_dump_record_bytes() { return dump_layout<T0_F, T0_V>::SIZE * sizeof(float4); }
 
-cudaError_t launch_epa_tiers(const narrow_args& A, const narrow_ws& W, int sm_count,
-                             cudaStream_t st, uint64_t* launches) {
+cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, int sm_count,
+                            cudaStream_t st) {
     epa_args C;
     C.A = A;
     C.W = W;
-    C.tier = 0;
-    cudaError_t e = launch_tier<T0_G, T0_F, T0_V, T0_O, 0, 0>(C, sm_count, st);
-    if (e != cudaSuccess) return e;
-    C.tier = 1;
-    e = launch_tier<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(C, sm_count, st);
-    *launches += 2;
-    return e;
+    C.tier = (uint32_t)tier;
+    if (tier == 0) return launch_tier<T0_G, T0_F, T0_V, T0_O, 0, 0>(C, sm_count, st);
+    return launch_tier<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(C, sm_count, st);
 }
 
 }  // namespace cb2

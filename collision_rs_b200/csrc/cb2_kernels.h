@@ -81,8 +81,8 @@ struct narrow_ws {           // per-stream device workspace, owned by the ctx
 size_t epa_dump_record_bytes();
 size_t epa_pa_scratch_bytes(int sm_count);
 cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, cudaStream_t st);
-cudaError_t launch_epa_tiers(const narrow_args& A, const narrow_ws& W, int sm_count,
-                             cudaStream_t st, uint64_t* launches);
+cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, int sm_count,
+                            cudaStream_t st);
 
 // ---- support cells (cb2_cells.cu) ---------------------------------------------------------------
 uint32_t cells_resolution(uint32_t vertex_count);

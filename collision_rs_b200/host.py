@@ -72,6 +72,15 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.cb2_kernel_launches(self.h))
 
+    def set_stage_timing(self, on=True):
+        self._ck(self.lib.cb2_set_stage_timing(self.h, 1 if on else 0))
+
+    def last_stage_ms(self):
+        """ms of {GJK, EPA tier 0, EPA tier 1, second chance} of the last timed device call."""
+        out = (C.c_float * 4)()
+        self._ck(self.lib.cb2_last_stage_ms(self.h, C.byref(out)))
+        return [float(x) for x in out]
+
     # ---- shape table --------------------------------------------------------------------
     def upload_shapes(self, shapes, verts=None):
         shapes = np.ascontiguousarray(shapes, SHAPE_DT)

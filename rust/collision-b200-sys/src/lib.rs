@@ -100,6 +100,8 @@ extern "C" {
     pub fn cb2_last_error(ctx: *const cb2_ctx) -> *const c_char;
     pub fn cb2_device_sm_count(ctx: *const cb2_ctx) -> c_int;
     pub fn cb2_kernel_launches(ctx: *const cb2_ctx) -> u64;
+    pub fn cb2_set_stage_timing(ctx: *mut cb2_ctx, on: c_int) -> c_int;
+    pub fn cb2_last_stage_ms(ctx: *mut cb2_ctx, out4: *mut f32) -> c_int;
 
     pub fn cb2_shapes_upload(ctx: *mut cb2_ctx, shapes: *const cb2_shape, n_shapes: u32,
                              verts_xyz: *const f32, n_verts: u64) -> c_int;

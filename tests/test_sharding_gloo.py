@@ -1,0 +1,71 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: pair sharding, shape-table
+broadcast, contact gather.  The per-shard compute is the CPU oracle here (test infrastructure);
+on the GPUs the same plumbing carries the CUDA path's records (bench.py --gpus N)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions_exactly():
+    from collision_rs_b200.sharding import shard_range
+    for n in (0, 1, 7, 8, 1000, 4_000_001):
+        for world in (1, 2, 3, 8):
+            edges = [shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+            sizes = [e - b for b, e in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from collision_rs_b200 import workloads as W
+    from collision_rs_b200.sharding import broadcast_shape_table, gather_contacts, shard_range
+    from oracle.binding import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = W.cfg3_polyhedron_pairs(n, n_shapes=64)
+        # only rank 0 owns the shape table; the others receive it
+        shapes, verts = broadcast_shape_table(w["shapes"] if rank == 0 else None,
+                                              w["verts"] if rank == 0 else None, src=0)
+        assert np.array_equal(shapes, w["shapes"]) and np.array_equal(verts, w["verts"])
+        b, e = shard_range(n, rank, world)
+        o = Oracle()
+        c, s = o.intersection(0, shapes, verts, w["l_shape"][b:e], w["r_shape"][b:e],
+                              w["l_t"][b:e], w["r_t"][b:e], nthreads=2)
+        allc, alls = gather_contacts(c, s, n)
+        if rank == 0:
+            ec, es = o.intersection(0, shapes, verts, w["l_shape"], w["r_shape"], w["l_t"],
+                                    w["r_t"], nthreads=2)
+            ok = np.array_equal(alls, es) and allc.tobytes() == ec.tobytes()
+            q.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_shard_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n = 1001  # odd: ragged shards
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
