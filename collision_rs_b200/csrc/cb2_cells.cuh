@@ -57,11 +57,28 @@ struct poly_ref {
     float R;                 // max |vertex|, rounded up
 };
 
-CB2_DI f3 poly_full_scan(const float4* __restrict__ verts, uint32_t n, f3 d) {
+// kept out of line: it is the rare path, and inlining it (three call sites) bloats the hot loops
+static __device__ __noinline__ f3 poly_full_scan(const float4* __restrict__ verts, uint32_t n, f3 d) {
     f3 best = zero3();
     float best_dot = -INFINITY;
     for (uint32_t i = 0; i < n; ++i) {
         const float4 v = __ldg(verts + i);
+        const f3 p = mk3(v.x, v.y, v.z);
+        const float dt = dot(p, d);
+        if (dt > best_dot) {
+            best_dot = dt;
+            best = p;
+        }
+    }
+    return best;
+}
+
+static __device__ __noinline__ f3 poly_ext_scan(const float4* __restrict__ verts,
+                                         const uint16_t* __restrict__ e, uint32_t n, f3 d) {
+    f3 best = zero3();
+    float best_dot = -INFINITY;
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 v = __ldg(verts + __ldg(e + k));
         const f3 p = mk3(v.x, v.y, v.z);
         const float dt = dot(p, d);
         if (dt > best_dot) {
@@ -80,46 +97,43 @@ CB2_DI f3 poly_local_support(const poly_ref& s, f3 d) {
     const float scale = m * s.R;
     // outside this window (or NaN) the rounding argument does not hold: full scan
     if (!(scale >= 1.0e-30f && scale <= 1.0e30f)) return poly_full_scan(s.verts, s.vcnt, d);
-    uint4 rec = __ldg(s.cells + cell);
-    float best_dot = -INFINITY;
-    uint32_t best = 0xFFFFFFFFu;
+    const uint4 rec = __ldg(s.cells + cell);
     const uint32_t bits = s.wide ? 16u : 8u;
     const uint32_t mask = s.wide ? 0xFFFFu : 0xFFu;
-    uint32_t cnt = rec.x & mask;
-    if (cnt <= (s.wide ? CELL_INLINE16 : CELL_INLINE8)) {
-        // the record is a 128-bit little-endian string [count | idx0 | idx1 | ...]: shift it down
-        // one entry per iteration (4 funnel shifts) instead of indexing it dynamically
-        for (; cnt > 0; --cnt) {
-            rec.x = __funnelshift_r(rec.x, rec.y, bits);
-            rec.y = __funnelshift_r(rec.y, rec.z, bits);
-            rec.z = __funnelshift_r(rec.z, rec.w, bits);
-            rec.w >>= bits;
-            const uint32_t idx = rec.x & mask;
-            const float4 v = __ldg(s.verts + idx);
-            const float dt = dot(mk3(v.x, v.y, v.z), d);
-            if (dt > best_dot) {
-                best_dot = dt;
-                best = idx;
-            }
-        }
-    } else if (cnt == (mask & (0xFF00u | CELL_FULL))) {
-        return poly_full_scan(s.verts, s.vcnt, d);
-    } else {
-        // extension list: rec.y = offset into the pool, rec.z = count
-        const uint16_t* __restrict__ e = s.ext + rec.y;
-        for (uint32_t k = 0; k < rec.z; ++k) {
-            const uint32_t idx = __ldg(e + k);
-            const float4 v = __ldg(s.verts + idx);
-            const float dt = dot(mk3(v.x, v.y, v.z), d);
-            if (dt > best_dot) {
-                best_dot = dt;
-                best = idx;
-            }
-        }
+    const uint32_t cnt = rec.x & mask;
+    if (cnt > (s.wide ? CELL_INLINE16 : CELL_INLINE8)) {
+        if (cnt == (mask & (0xFF00u | CELL_FULL))) return poly_full_scan(s.verts, s.vcnt, d);
+        return poly_ext_scan(s.verts, s.ext + rec.y, rec.z, d);  // rec.y = pool offset, rec.z = count
     }
-    if (best == 0xFFFFFFFFu) return zero3();  // no dot > -inf: P::origin() (polyhedron.rs:163)
-    const float4 v = __ldg(s.verts + best);
-    return mk3(v.x, v.y, v.z);
+    // The record is a 128-bit little-endian string [count | idx0 | idx1 | ...].  Drop the count,
+    // then take FOUR candidates per round with their vertex loads issued back to back, so a
+    // round costs one memory latency instead of four (the loads are the support call's cost).
+    // Unused slots hold index 0: a valid address whose value is ignored.
+    uint32_t x = __funnelshift_r(rec.x, rec.y, bits), y = __funnelshift_r(rec.y, rec.z, bits),
+             z = __funnelshift_r(rec.z, rec.w, bits), w = rec.w >> bits;
+    f3 best = zero3();  // no dot > -inf: P::origin() (polyhedron.rs:163)
+    float best_dot = -INFINITY;
+    for (uint32_t base = 0; base < cnt; base += 4u) {
+        uint32_t i0, i1, i2, i3;
+        if (!s.wide) {
+            i0 = x & 0xFFu; i1 = (x >> 8) & 0xFFu; i2 = (x >> 16) & 0xFFu; i3 = x >> 24;
+            x = y; y = z; z = w; w = 0u;
+        } else {
+            i0 = x & 0xFFFFu; i1 = x >> 16; i2 = y & 0xFFFFu; i3 = y >> 16;
+            x = z; y = w; z = 0u; w = 0u;
+        }
+        const float4 v0 = __ldg(s.verts + i0), v1 = __ldg(s.verts + i1);
+        const float4 v2 = __ldg(s.verts + i2), v3 = __ldg(s.verts + i3);
+        const uint32_t rem = cnt - base;
+        const float d0 = dot(mk3(v0.x, v0.y, v0.z), d), d1 = dot(mk3(v1.x, v1.y, v1.z), d);
+        const float d2 = dot(mk3(v2.x, v2.y, v2.z), d), d3 = dot(mk3(v3.x, v3.y, v3.z), d);
+        // ascending index order + strict '>' = the reference's first-strict-max rule
+        if (d0 > best_dot) { best_dot = d0; best = mk3(v0.x, v0.y, v0.z); }
+        if (rem > 1u && d1 > best_dot) { best_dot = d1; best = mk3(v1.x, v1.y, v1.z); }
+        if (rem > 2u && d2 > best_dot) { best_dot = d2; best = mk3(v2.x, v2.y, v2.z); }
+        if (rem > 3u && d3 > best_dot) { best_dot = d3; best = mk3(v3.x, v3.y, v3.z); }
+    }
+    return best;
 }
 
 }  // namespace cb2
