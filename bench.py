@@ -315,7 +315,7 @@ def main():
     bytes_pair = 2 * 4 + 2 * XFORM_DT.itemsize + CONTACT_DT.itemsize + 1
     hbm_achieved = bytes_pair * n / (step_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "fp32", "kernel": "k_epa (EPA3::process; tier 0 + tier 1 launches)",
+        "bound": "fp32", "kernel": "k_epa (EPA3::process; its three shared-memory tier launches)",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": achieved / fp32_peak if fp32_peak > 0 else None,
         "traffic": profiled_traffic(n),
@@ -329,7 +329,7 @@ def main():
                "(oracle op counter, incl. its O(V) vertex scans that the support cells avoid)",
         "kernel_ms": epa_ms,
         "stage_ms": {"k_gjk_hits": stage_ms[0], "k_epa_tier0": stage_ms[1],
-                     "k_epa_tier1": stage_ms[2], "second_chance": stage_ms[3]},
+                     "k_epa_tiers1_2": stage_ms[2], "second_chance": stage_ms[3]},
         "step": {"ms": step_ms, "achieved": flops_pair * n / (step_ms * 1e-3) / 1e12,
                  "frac": flops_pair * n / (step_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak > 0 else None},
         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -60,13 +60,17 @@ struct cb2_ctx {
 static std::string g_create_err;
 
 static void free_ws(narrow_ws& w) {  // the per-pair buffers
-    if (w.hits) cudaFree(w.hits);
-    if (w.over) cudaFree(w.over);
+    for (int k = 0; k < EPA_TIERS; ++k) {
+        if (w.list[k]) cudaFree(w.list[k]);
+        w.list[k] = nullptr;
+    }
+    for (int k = 0; k + 1 < EPA_TIERS; ++k) {
+        if (w.dump[k]) cudaFree(w.dump[k]);
+        w.dump[k] = nullptr;
+        w.dump_cap[k] = 0;
+    }
     if (w.simplex) cudaFree(w.simplex);
-    if (w.dump) cudaFree(w.dump);
-    w.hits = w.over = nullptr;
-    w.simplex = w.dump = nullptr;
-    w.dump_cap = 0;
+    w.simplex = nullptr;
 }
 
 #define CK(ctx, x)                                                                     \
@@ -301,13 +305,16 @@ static int ensure_ws(cb2_ctx* c, int slot, uint64_t n) {
     if (c->ws_cap[slot] < n) {
         free_ws(w);
         c->ws_cap[slot] = 0;
-        CK(c, cudaMalloc(&w.hits, n * sizeof(uint32_t)));
-        CK(c, cudaMalloc(&w.over, n * sizeof(uint32_t)));
+        for (int k = 0; k < EPA_TIERS; ++k) CK(c, cudaMalloc(&w.list[k], n * sizeof(uint32_t)));
         CK(c, cudaMalloc(&w.simplex, n * 8 * sizeof(float4)));
-        // room for 1 pair in 8 to hand its polytope to tier 1 (more than that restart instead)
-        const uint64_t dc = n / 8 > 4096 ? n / 8 : (n < 4096 ? n : 4096);
-        CK(c, cudaMalloc(&w.dump, dc * epa_dump_record_bytes()));
-        w.dump_cap = (uint32_t)dc;
+        // room for 1 pair in 4 (tier 0 -> 1) and 1 in 32 (tier 1 -> 2) to hand their polytope
+        // over; beyond that a pair restarts in the next tier instead of resuming
+        for (int k = 0; k + 1 < EPA_TIERS; ++k) {
+            const uint64_t frac = k == 0 ? n / 4 : n / 32;
+            const uint64_t dc = frac > 4096 ? frac : (n < 4096 ? n : 4096);
+            CK(c, cudaMalloc(&w.dump[k], dc * epa_dump_record_bytes(k)));
+            w.dump_cap[k] = (uint32_t)dc;
+        }
         c->ws_cap[slot] = n;
     }
     return CB2_OK;
@@ -371,9 +378,10 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
         if (e == cudaSuccess && full) {
             e = launch_epa_tier(0, A, W, c->sm_count, st);
             mark_stage(c, 2, st);
-            if (e == cudaSuccess) e = launch_epa_tier(1, A, W, c->sm_count, st);
+            for (int k = 1; k < EPA_TIERS && e == cudaSuccess; ++k)
+                e = launch_epa_tier(k, A, W, c->sm_count, st);
             mark_stage(c, 3, st);
-            c->launches += 2;
+            c->launches += EPA_TIERS;
         }
         if (e != cudaSuccess) {
             c->err = std::string("kernel launch: ") + cudaGetErrorString(e);

@@ -21,12 +21,13 @@
 //    shared memory.  That equals remove_or_add_edge's list (epa3d.rs:212-219) whenever no directed
 //    edge occurs twice; the (non-manifold) exception is detected by the same atomicOr and the
 //    pair goes to the serial second-chance kernel (cb2_narrow.cu).
-//  * The polytope lives in per-group shared memory in two tiers: 48 faces / 28 vertices (4 lanes
-//    per pair; covers ~92 % of pairs) and 208 / 104 (8 lanes per pair; the manifold worst case
-//    2V-4 at the 100-iteration cap).  A pair that outgrows tier 0 dumps its polytope to global
-//    memory and tier 1 RESUMES it at the same iteration (nothing is recomputed).  sup_a of each
-//    polytope vertex is only read by the final contact (epa3d.rs:84-114), so it lives in a
-//    global scratch, not shared memory.
+//  * The polytope lives in per-group shared memory in three tiers: 40 faces / 24 vertices and
+//    72 / 40 (4 lanes per pair; ~86 % and ~99.5 % of pairs) and 208 / 104 (8 lanes per pair; the
+//    manifold worst case 2V-4 at the 100-iteration cap).  Small tiers buy residency: tier 0 runs
+//    20 warps per SM.  A pair that outgrows its tier dumps its polytope to global memory and the
+//    next tier RESUMES it at the same iteration (nothing is recomputed).  sup_a of each polytope
+//    vertex is only read by the final contact (epa3d.rs:84-114), so it lives in a global
+//    scratch, not shared memory.
 #include "cb2_gjk.cuh"
 #include "cb2_kernels.h"
 
@@ -128,11 +129,37 @@ struct bitmask<2> {
 };
 template <>
 struct bitmask<1> : bitmask<2> {};
+// up to 128 faces: two 64-bit halves
+template <>
+struct bitmask<4> {
+    unsigned long long lo, hi;
+    CB2_DI void clear() { lo = hi = 0ull; }
+    CB2_DI void or_bits(int pos, uint32_t bits) {  // a group's bits never straddle bit 64
+        if (pos < 64) lo |= (unsigned long long)bits << pos;
+        else hi |= (unsigned long long)bits << (pos - 64);
+    }
+    CB2_DI bool test(int i) const { return ((i < 64 ? lo >> i : hi >> (i - 64)) & 1ull) != 0ull; }
+    CB2_DI void reset(int i) {
+        if (i < 64) lo &= ~(1ull << i);
+        else hi &= ~(1ull << (i - 64));
+    }
+    CB2_DI int next(int from) const {
+        if (from < 64) {
+            const unsigned long long v = (lo >> from) << from;
+            if (v) return __ffsll((long long)v) - 1;
+            return hi ? 64 + __ffsll((long long)hi) - 1 : -1;
+        }
+        const unsigned long long v = from < 128 ? (hi >> (from - 64)) << (from - 64) : 0ull;
+        return v ? 64 + __ffsll((long long)v) - 1 : -1;
+    }
+};
+template <>
+struct bitmask<3> : bitmask<4> {};
 
 struct epa_args {
     narrow_args A;
     narrow_ws W;
-    uint32_t tier;  // 0, 1
+    uint32_t tier;  // 0 .. EPA_TIERS-1
 };
 
 // tier-0 polytope dump record, in float4 units: header (nf, nv, it) | fnd | pv | pa | fidx
@@ -169,12 +196,14 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
     uint32_t count;
     uint32_t* over_list;
     uint32_t* over_count;
-    if (C.tier == 0) {
-        list = C.W.hits; count = C.W.EC->n_hits;
-        over_list = C.W.over; over_count = &C.W.EC->n_over;
+    list = C.W.list[C.tier];
+    count = C.W.EC->n_list[C.tier];
+    if (C.tier + 1 < EPA_TIERS) {
+        over_list = C.W.list[C.tier + 1];
+        over_count = &C.W.EC->n_list[C.tier + 1];
     } else {
-        list = C.W.over; count = C.W.EC->n_over;
-        over_list = nullptr; over_count = nullptr;
+        over_list = nullptr;
+        over_count = nullptr;
     }
     uint32_t* cursor = &C.W.EC->next[C.tier];
     const uint32_t max_it = A.settings.max_iterations;
@@ -230,7 +259,7 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                 if (RF > 0 && (entry & OVER_RESUME)) {
                     // resume a polytope that outgrew the previous tier, at the same iteration
                     using DL = dump_layout<RF, RV>;
-                    const float4* rec = C.W.dump + (size_t)k * DL::SIZE;
+                    const float4* rec = C.W.dump[C.tier - 1] + (size_t)k * DL::SIZE;
                     const float4 h = rec[0];
                     nf = (int)__float_as_uint(h.x);
                     nv = (int)__float_as_uint(h.y);
@@ -474,9 +503,9 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
                 uint32_t h = 0;
                 if (gl == 0) h = atomicAdd(over_count, 1u);
                 h = __shfl_sync(gmask, h, gw * G);
-                const bool room = h < C.W.dump_cap;
+                const bool room = h < C.W.dump_cap[C.tier];
                 if (room) {
-                    float4* rec = C.W.dump + (size_t)h * DL::SIZE;
+                    float4* rec = C.W.dump[C.tier] + (size_t)h * DL::SIZE;
                     if (gl == 0)
                         rec[0] = make_float4(__uint_as_float((uint32_t)nf), __uint_as_float((uint32_t)nv),
                                              __uint_as_float(it), 0.f);
@@ -501,8 +530,10 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-constexpr int T0_G = 4, T0_F = 48, T0_V = 28, T0_O = 24;
-constexpr int T1_G = 8, T1_F = 208, T1_V = 104, T1_O = 96;  // manifold worst case at 100 iterations
+// tier:            G   faces  verts  examined/horizon cap
+constexpr int T0_G = 4, T0_F = 40, T0_V = 24, T0_O = 24;
+constexpr int T1_G = 4, T1_F = 72, T1_V = 40, T1_O = 32;
+constexpr int T2_G = 8, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
 
 template <int G, int F, int V, int O, int RF, int RV>
 static int epa_blocks(int sm_count) {
@@ -525,9 +556,14 @@ static cudaError_t launch_tier(const epa_args& C, int sm_count, cudaStream_t st)
 size_t epa_pa_scratch_bytes(int sm_count) {
     const size_t a = (size_t)epa_blocks<T0_G, T0_F, T0_V, T0_O, 0, 0>(sm_count) * (32 / T0_G) * T0_V;
     const size_t b = (size_t)epa_blocks<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(sm_count) * (32 / T1_G) * T1_V;
-    return (a > b ? a : b) * sizeof(float4);
+    const size_t c = (size_t)epa_blocks<T2_G, T2_F, T2_V, T2_O, T1_F, T1_V>(sm_count) * (32 / T2_G) * T2_V;
+    size_t m = a > b ? a : b;
+    m = m > c ? m : c;
+    return m * sizeof(float4);
 }
-size_t epa_dump_record_bytes() { return dump_layout<T0_F, T0_V>::SIZE * sizeof(float4); }
+size_t epa_dump_record_bytes(int tier) {
+    return (tier == 0 ? dump_layout<T0_F, T0_V>::SIZE : dump_layout<T1_F, T1_V>::SIZE) * sizeof(float4);
+}
 
 cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, int sm_count,
                             cudaStream_t st) {
@@ -536,7 +572,8 @@ cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, 
     C.W = W;
     C.tier = (uint32_t)tier;
     if (tier == 0) return launch_tier<T0_G, T0_F, T0_V, T0_O, 0, 0>(C, sm_count, st);
-    return launch_tier<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(C, sm_count, st);
+    if (tier == 1) return launch_tier<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(C, sm_count, st);
+    return launch_tier<T2_G, T2_F, T2_V, T2_O, T1_F, T1_V>(C, sm_count, st);
 }
 
 }  // namespace cb2

@@ -63,22 +63,21 @@ size_t retry_scratch_bytes();
 cudaError_t launch_overflow_retry(const narrow_args& A, const retry_ws& R, cudaStream_t st);
 
 // ---- GJK -> EPA pipeline (cb2_narrow.cu: k_gjk_hits, cb2_epa.cu: k_epa) ------------------------
-struct epa_counters {        // device-side bookkeeping, zeroed per batch
-    uint32_t n_hits;         // FullResolution hits queued for tier 0
-    uint32_t n_over;         // ... whose polytope outgrew tier 0, plus curved pairs (queued here
-                             //     directly by k_gjk_hits)
-    uint32_t next[2];        // work-queue cursors of the two tiers
+constexpr int EPA_TIERS = 3;
+struct epa_counters {             // device-side bookkeeping, zeroed per batch
+    uint32_t n_list[EPA_TIERS];   // entries queued for each tier ([0] = FullResolution hits; the
+                                  // last tier also receives curved pairs straight from k_gjk_hits)
+    uint32_t next[EPA_TIERS];     // work-queue cursors
 };
-struct narrow_ws {           // per-stream device workspace, owned by the ctx
-    uint32_t* hits;          // n words each: pair indices
-    uint32_t* over;
-    float4* simplex;         // 8 x float4 per pair: GJK terminal simplex v[0..3], sup_a[0..3]
-    float4* pa;              // SupportPoint.sup_a scratch, per resident EPA group
-    float4* dump;            // tier-0 polytope dumps (dump_cap records), resumed by tier 1
-    uint32_t dump_cap;
+struct narrow_ws {                // per-stream device workspace, owned by the ctx
+    uint32_t* list[EPA_TIERS];    // n words each: pair indices (| OVER_RESUME when a dump exists)
+    float4* simplex;              // 8 x float4 per pair: GJK terminal simplex v[0..3], sup_a[0..3]
+    float4* pa;                   // SupportPoint.sup_a scratch, per resident EPA group
+    float4* dump[EPA_TIERS - 1];  // polytope dumps of tier k, resumed by tier k+1
+    uint32_t dump_cap[EPA_TIERS - 1];
     epa_counters* EC;
 };
-size_t epa_dump_record_bytes();
+size_t epa_dump_record_bytes(int tier);
 size_t epa_pa_scratch_bytes(int sm_count);
 cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, cudaStream_t st);
 cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, int sm_count,

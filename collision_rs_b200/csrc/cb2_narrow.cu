@@ -309,20 +309,20 @@ __global__ void __launch_bounds__(128) k_gjk_hits(narrow_args A, narrow_ws W) {
         }
     }
     if constexpr (FULL) {
-        // warp-aggregated append to the tier-0 / tier-1 work lists
+        // warp-aggregated append to the first / last tier's work list
         const unsigned lane = threadIdx.x & 31u;
         const unsigned m1 = __ballot_sync(0xffffffffu, hit && !curved);
         const unsigned m3 = __ballot_sync(0xffffffffu, hit && curved);
         uint32_t b1 = 0, b3 = 0;
         if (lane == 0) {
-            if (m1) b1 = atomicAdd(&W.EC->n_hits, __popc(m1));
-            if (m3) b3 = atomicAdd(&W.EC->n_over, __popc(m3));
+            if (m1) b1 = atomicAdd(&W.EC->n_list[0], __popc(m1));
+            if (m3) b3 = atomicAdd(&W.EC->n_list[EPA_TIERS - 1], __popc(m3));
         }
         b1 = __shfl_sync(0xffffffffu, b1, 0);
         b3 = __shfl_sync(0xffffffffu, b3, 0);
         const unsigned below = (1u << lane) - 1u;
-        if (hit && !curved) W.hits[b1 + __popc(m1 & below)] = (uint32_t)i;
-        if (hit && curved) W.over[b3 + __popc(m3 & below)] = (uint32_t)i;
+        if (hit && !curved) W.list[0][b1 + __popc(m1 & below)] = (uint32_t)i;
+        if (hit && curved) W.list[EPA_TIERS - 1][b3 + __popc(m3 & below)] = (uint32_t)i;
     }
 }
 

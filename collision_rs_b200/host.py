@@ -76,7 +76,7 @@ class Context:
         self._ck(self.lib.cb2_set_stage_timing(self.h, 1 if on else 0))
 
     def last_stage_ms(self):
-        """ms of {GJK, EPA tier 0, EPA tier 1, second chance} of the last timed device call."""
+        """ms of {GJK, EPA tier 0, EPA tiers 1+2, second chance} of the last timed device call."""
         out = (C.c_float * 4)()
         self._ck(self.lib.cb2_last_stage_ms(self.h, C.byref(out)))
         return [float(x) for x in out]

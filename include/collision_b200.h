@@ -132,7 +132,7 @@ uint64_t cb2_kernel_launches(const cb2_ctx* ctx);
 
 /* Stage timing of the narrow phase (measurement aid for bench.py's roofline: CUDA events on the
  * launching stream around the stages of the LAST FullResolution cb2_gjk3_intersection*_dev call).
- * out4 = milliseconds of { GJK (k_gjk_hits), EPA tier 0 (k_epa), EPA tier 1 (k_epa),
+ * out4 = milliseconds of { GJK (k_gjk_hits), EPA tier 0 (k_epa), EPA higher tiers (k_epa x2),
  * second-chance (k_collect_overflow + k_retry_overflow) }.  cb2_last_stage_ms synchronises.     */
 int cb2_set_stage_timing(cb2_ctx* ctx, int on);
 int cb2_last_stage_ms(cb2_ctx* ctx, float* out4);
