@@ -7,15 +7,29 @@
 // sweep_axis <- 0 afterwards (Variance3 accumulates nothing, sweep_prune.rs:254-277).
 // The reference's `active.retain(max_a >= min_b)` prune is implied by the strict test.
 //
-// Device pipeline:
-//   k_sap_keys    64-bit radix keys ord(min[axis]) : ord(max[axis]) (−0 canonicalised)
-//   radix sort    stable LSD sort of (key, index)            -> perm
-//   k_sap_gather  sorted SoA: U=(min_u,max_u) V=(min_v,max_v) S=(min_s,max_s); upper(a) by
-//                 binary search = first b with min_s[b] >= max_s[a] (monotone early exit)
-//   k_sap_sweep   (count, then emit) block = 256 consecutive a's; the window of b's they
-//                 share is staged tile by tile in shared memory and broadcast-read
-//   exclusive scan of the per-a counts; emit gives (a asc, b asc); one stable radix sort
-//   of the pairs by b yields the reference Vec order (b asc, a asc).
+// Device pipeline (B200-first: the reference's O(N * active-window) sweep — 1e10 box tests for
+// 1 M boxes — is replaced by a sweep INSIDE the cells of a 2-D grid over the two other axes, which
+// finds the identical pair set with ~30 tests per box):
+//   k_sap_keys     64-bit radix keys ord(min[axis]) : ord(max[axis]) (−0 canonicalised)
+//   radix sort     stable LSD sort of (key, index)                       -> perm (sorted positions)
+//   k_sap_gather   sorted SoA: S=(min_s,max_s) U=(min_u,max_u) V=(min_v,max_v)
+//   k_grid_stats   origin / extent of the (u,v) domain, log2 histogram of box extents
+//   k_grid_params  cell size = 2^ceil(log2) of the 99.9 % extent quantile (most boxes touch <= 4
+//                  cells), grid clamped to 2048 x 2048
+//   k_grid_emit    one (cell, position) entry per cell a box touches (<= 9; boxes touching more are
+//                  "large" and go to k_sap_large), written at box-major offsets
+//   radix sort     stable sort of the entries by cell        -> per cell: positions ascending
+//   k_grid_sweep   one thread per entry (cell C, a): walk forward through C's entries b while
+//                  min_s[b] < max_s[a]; strict Aabb3 test (aabb3.rs:246-253); a pair is reported only
+//                  in its canonical cell (max of the two boxes' first cells), so exactly once
+//   k_sap_large    the rare large boxes against every box of their sweep window
+//   radix sort     of the u64 keys (b << 32 | a): the sorted array IS the interleaved (a, b) u32
+//                  pair list in the reference's Vec order (b ascending, then a ascending)
+// Monotone cell mapping (floor of a monotone f32 expression) guarantees that two boxes that overlap
+// strictly on u and v share their canonical cell, so no pair is missed.  The old tiled sweep is kept
+// behind CB2_SAP_LEGACY=1 for A/B tests.
+#include <cstdlib>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -160,6 +174,233 @@ __global__ void __launch_bounds__(SAP_BLOCK) k_sap_sweep(
     if (!EMIT && live) counts[a] = cnt;
 }
 
+// ---- grid-accelerated sweep -------------------------------------------------------------------------
+constexpr int GRID_MAX = 2048;        // cells per axis at most
+constexpr int LARGE_CELLS = 9;        // a box touching more cells than this is "large"
+constexpr int EXT_BUCKETS = 64;       // log2 histogram of extents: bucket = exponent + 32, clamped
+
+struct grid_params {
+    // written by k_grid_stats (ordered-uint encodings so atomicMin/Max work on floats)
+    uint32_t min_u, min_v, max_u, max_v;
+    uint32_t hist_u[EXT_BUCKETS], hist_v[EXT_BUCKETS];
+    // written by k_grid_params
+    float org_u, org_v, inv_u, inv_v;
+    int nu, nv, bits;
+    // counters
+    uint32_t n_large;
+    unsigned long long n_pairs;
+};
+
+__device__ __forceinline__ uint32_t ford(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float funord(uint32_t k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+__device__ __forceinline__ int ext_bucket(float e) {
+    if (!(e > 0.0f)) return 0;
+    int ex;
+    frexpf(e, &ex);  // e = m * 2^ex, m in [0.5, 1)  =>  e <= 2^ex
+    ex += 32;
+    return ex < 0 ? 0 : (ex >= EXT_BUCKETS ? EXT_BUCKETS - 1 : ex);
+}
+
+__global__ void __launch_bounds__(256) k_grid_stats(const float2* __restrict__ U,
+                                                   const float2* __restrict__ V, uint64_t n,
+                                                   grid_params* __restrict__ G) {
+    __shared__ uint32_t hu[EXT_BUCKETS], hv[EXT_BUCKETS], mn[2], mx[2];
+    if (threadIdx.x < EXT_BUCKETS) hu[threadIdx.x] = hv[threadIdx.x] = 0;
+    if (threadIdx.x < 2) { mn[threadIdx.x] = 0xFFFFFFFFu; mx[threadIdx.x] = 0u; }
+    __syncthreads();
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (uint64_t)gridDim.x * blockDim.x) {
+        const float2 u = __ldg(U + k), v = __ldg(V + k);
+        // only finite coordinates shape the grid (the cell mapping clamps the others)
+        if (isfinite(u.x)) atomicMin(&mn[0], ford(u.x));
+        if (isfinite(v.x)) atomicMin(&mn[1], ford(v.x));
+        if (isfinite(u.y)) atomicMax(&mx[0], ford(u.y));
+        if (isfinite(v.y)) atomicMax(&mx[1], ford(v.y));
+        atomicAdd(&hu[ext_bucket(u.y - u.x)], 1u);
+        atomicAdd(&hv[ext_bucket(v.y - v.x)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < EXT_BUCKETS) {
+        if (hu[threadIdx.x]) atomicAdd(&G->hist_u[threadIdx.x], hu[threadIdx.x]);
+        if (hv[threadIdx.x]) atomicAdd(&G->hist_v[threadIdx.x], hv[threadIdx.x]);
+    }
+    if (threadIdx.x == 0) {
+        atomicMin(&G->min_u, mn[0]); atomicMin(&G->min_v, mn[1]);
+        atomicMax(&G->max_u, mx[0]); atomicMax(&G->max_v, mx[1]);
+    }
+}
+
+__device__ void grid_axis(const uint32_t* hist, uint64_t n, float lo, float hi, float& org,
+                          float& inv, int& cells) {
+    // cell = 2^e with e the bucket that covers 99.9 % of the extents (e <= 2^bucket)
+    const uint64_t want = n - n / 1000;
+    uint64_t acc = 0;
+    int b = 0;
+    for (; b < EXT_BUCKETS; ++b) {
+        acc += hist[b];
+        if (acc >= want) break;
+    }
+    if (b >= EXT_BUCKETS) b = EXT_BUCKETS - 1;
+    float cell = ldexpf(1.0f, b - 32);
+    float span = hi - lo;
+    if (!(span > 0.0f) || !isfinite(span)) span = 0.0f;
+    if (!(cell > 0.0f)) cell = 1.0f;
+    if (span / cell > (float)(GRID_MAX - 1)) cell = span / (float)(GRID_MAX - 1);
+    org = isfinite(lo) ? lo : 0.0f;
+    inv = 1.0f / cell;
+    cells = (int)(span * inv) + 1;
+    if (cells < 1) cells = 1;
+    if (cells > GRID_MAX) cells = GRID_MAX;
+}
+
+__global__ void k_grid_params(grid_params* __restrict__ G, uint64_t n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float lo_u = funord(G->min_u), hi_u = funord(G->max_u);
+    float lo_v = funord(G->min_v), hi_v = funord(G->max_v);
+    if (G->min_u == 0xFFFFFFFFu || G->max_u == 0u) lo_u = hi_u = 0.0f;  // no finite coordinate
+    if (G->min_v == 0xFFFFFFFFu || G->max_v == 0u) lo_v = hi_v = 0.0f;
+    grid_axis(G->hist_u, n, lo_u, hi_u, G->org_u, G->inv_u, G->nu);
+    grid_axis(G->hist_v, n, lo_v, hi_v, G->org_v, G->inv_v, G->nv);
+    int bits = 1;
+    while ((1 << bits) < G->nu * G->nv + 1) ++bits;  // +1: the sentinel cell of unused slots
+    G->bits = bits;
+}
+
+// monotone non-decreasing in x (fsub, fmul, floor, clamp are): overlapping intervals share a cell
+__device__ __forceinline__ int cell_coord(float x, float org, float inv, int cells) {
+    const float t = floorf(__fmul_rn(__fsub_rn(x, org), inv));
+    if (!(t > 0.0f)) return 0;  // also NaN (rejected elsewhere) and -inf
+    return t >= (float)(cells - 1) ? cells - 1 : (int)t;
+}
+
+struct cell_range {
+    int u0, u1, v0, v1;
+};
+__device__ __forceinline__ cell_range box_cells(const grid_params* __restrict__ G, float2 u, float2 v) {
+    cell_range r;
+    r.u0 = cell_coord(u.x, G->org_u, G->inv_u, G->nu);
+    r.u1 = cell_coord(u.y, G->org_u, G->inv_u, G->nu);
+    r.v0 = cell_coord(v.x, G->org_v, G->inv_v, G->nv);
+    r.v1 = cell_coord(v.y, G->org_v, G->inv_v, G->nv);
+    return r;
+}
+
+// entries at box-major slots [k * LARGE_CELLS, +LARGE_CELLS); unused slots carry the sentinel cell
+__global__ void __launch_bounds__(256) k_grid_emit(const float2* __restrict__ U,
+                                                  const float2* __restrict__ V, uint64_t n,
+                                                  grid_params* __restrict__ G,
+                                                  uint32_t* __restrict__ ecell,
+                                                  uint32_t* __restrict__ epos,
+                                                  uint32_t* __restrict__ large_list) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const cell_range r = box_cells(G, __ldg(U + k), __ldg(V + k));
+    const uint32_t sentinel = (uint32_t)(G->nu * G->nv);
+    const int cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
+    uint32_t* c = ecell + k * LARGE_CELLS;
+    uint32_t* p = epos + k * LARGE_CELLS;
+    int j = 0;
+    if (cnt <= LARGE_CELLS) {
+        for (int iu = r.u0; iu <= r.u1; ++iu)
+            for (int iv = r.v0; iv <= r.v1; ++iv) {
+                c[j] = (uint32_t)(iu * G->nv + iv);
+                p[j] = (uint32_t)k;
+                ++j;
+            }
+    } else {
+        large_list[atomicAdd(&G->n_large, 1u)] = (uint32_t)k;
+    }
+    for (; j < LARGE_CELLS; ++j) {
+        c[j] = sentinel;
+        p[j] = (uint32_t)k;
+    }
+}
+
+__device__ __forceinline__ void emit_pair(grid_params* __restrict__ G, unsigned long long* __restrict__ keys,
+                                          uint64_t cap, uint32_t a, uint32_t b) {
+    // warp-aggregated would save atomics; pairs per thread are few, keep it simple
+    const unsigned long long w = atomicAdd(&G->n_pairs, 1ull);
+    if (w < cap) keys[w] = ((unsigned long long)b << 32) | a;
+}
+
+__global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ S,
+                                                   const float2* __restrict__ U,
+                                                   const float2* __restrict__ V,
+                                                   const uint32_t* __restrict__ ecell,
+                                                   const uint32_t* __restrict__ epos, uint64_t n_entries,
+                                                   grid_params* __restrict__ G,
+                                                   unsigned long long* __restrict__ keys, uint64_t cap) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const uint32_t cell = __ldg(ecell + e);
+    if (cell >= (uint32_t)(G->nu * G->nv)) return;  // sentinel slot
+    const uint32_t a = __ldg(epos + e);
+    const float2 as = __ldg(S + a), au = __ldg(U + a), av = __ldg(V + a);
+    const int au0 = cell_coord(au.x, G->org_u, G->inv_u, G->nu);
+    const int av0 = cell_coord(av.x, G->org_v, G->inv_v, G->nv);
+    const int cu = (int)(cell / (uint32_t)G->nv), cv = (int)(cell % (uint32_t)G->nv);
+    for (uint64_t f = e + 1; f < n_entries; ++f) {
+        if (__ldg(ecell + f) != cell) break;
+        const uint32_t b = __ldg(epos + f);  // b > a: entries of a cell ascend by position
+        const float2 bs = __ldg(S + b);
+        if (!(bs.x < as.y)) break;           // min_s ascends with position: window closed
+        // Aabb3::intersects (aabb3.rs:246-253), strict on all three axes
+        if (!(as.x < bs.y)) continue;
+        const float2 bu = __ldg(U + b);
+        if (!(au.y > bu.x && au.x < bu.y)) continue;
+        const float2 bv = __ldg(V + b);
+        if (!(av.y > bv.x && av.x < bv.y)) continue;
+        // report only in the canonical cell of the pair
+        const int bu0 = cell_coord(bu.x, G->org_u, G->inv_u, G->nu);
+        const int bv0 = cell_coord(bv.x, G->org_v, G->inv_v, G->nv);
+        if ((au0 > bu0 ? au0 : bu0) != cu || (av0 > bv0 ? av0 : bv0) != cv) continue;
+        emit_pair(G, keys, cap, a, b);
+    }
+}
+
+// large boxes (not in the grid): forward against every b of their window, backward against every
+// non-large a whose window reaches them
+__global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
+                                                  const float2* __restrict__ U,
+                                                  const float2* __restrict__ V, uint64_t n,
+                                                  const uint32_t* __restrict__ large_list,
+                                                  grid_params* __restrict__ G,
+                                                  unsigned long long* __restrict__ keys, uint64_t cap) {
+    const uint32_t nl = G->n_large;
+    for (uint32_t li = 0; li < nl; ++li) {
+        const uint32_t p = __ldg(large_list + li);
+        const float2 ps = __ldg(S + p), pu = __ldg(U + p), pv = __ldg(V + p);
+        for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+             q += (uint64_t)gridDim.x * blockDim.x) {
+            if (q == p) continue;
+            const float2 qs = __ldg(S + q), qu = __ldg(U + q), qv = __ldg(V + q);
+            if (!(ps.y > qs.x && ps.x < qs.y && pu.y > qu.x && pu.x < qu.y && pv.y > qv.x && pv.x < qv.y))
+                continue;
+            if (q > p) {
+                emit_pair(G, keys, cap, p, (uint32_t)q);
+            } else {
+                // (q, p) with q < p: if q is large too, q's own forward pass reports it
+                const cell_range r = box_cells(G, qu, qv);
+                if ((r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1) <= LARGE_CELLS)
+                    emit_pair(G, keys, cap, (uint32_t)q, p);
+            }
+        }
+    }
+}
+
+__global__ void k_grid_total(const grid_params* __restrict__ G, const uint32_t* __restrict__ nan_flag,
+                             uint64_t* __restrict__ h_total) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        h_total[0] = G->n_pairs;
+        h_total[1] = *nan_flag;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_sap_total(const uint64_t* __restrict__ counts,
                                                   const uint64_t* __restrict__ offsets, uint64_t n,
                                                   const uint32_t* __restrict__ nan_flag,
@@ -195,9 +436,10 @@ static inline unsigned nblk(uint64_t n, unsigned b) { return (unsigned)((n + b -
         }                                           \
     } while (0)
 
-int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
-                   uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
-                   cudaStream_t st, uint64_t* launches, const char** err) {
+static int sap_find_pairs_legacy(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
+                                 uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap,
+                                 uint64_t* n_pairs, cudaStream_t st, uint64_t* launches,
+                                 const char** err) {
     *n_pairs = 0;
     if (n == 0) return CB2_OK;
     if (n <= 1) {  // sweep_prune.rs:83-85: nothing sorted
@@ -311,6 +553,130 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
     *launches += 3;
     SAP_CK(cudaGetLastError());
     return CB2_OK;
+}
+
+
+static int ensure_cap(sap_workspace* w, size_t bytes, const char** err) {
+    if (w->cap >= bytes) return CB2_OK;
+    if (w->buf) cudaFree(w->buf);
+    w->buf = nullptr;
+    w->cap = 0;
+    SAP_CK(cudaMalloc(&w->buf, bytes + (bytes >> 2)));
+    w->cap = bytes + (bytes >> 2);
+    return CB2_OK;
+}
+
+int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
+                   uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
+                   cudaStream_t st, uint64_t* launches, const char** err) {
+    {
+        const char* e = std::getenv("CB2_SAP_LEGACY");
+        if (e && e[0] == '1')
+            return sap_find_pairs_legacy(w, aabbs, n, axis, perm_out, pairs_out, cap, n_pairs, st,
+                                         launches, err);
+    }
+    *n_pairs = 0;
+    if (n == 0) return CB2_OK;
+    if (n <= 1) {  // sweep_prune.rs:83-85: nothing sorted
+        k_iota<<<nblk(n, 256), 256, 0, st>>>(perm_out, n);
+        ++*launches;
+        SAP_CK(cudaGetLastError());
+        return CB2_OK;
+    }
+    if (n > 0x7FFFFFFFull / LARGE_CELLS) {
+        *err = "too many boxes for one call";
+        return CB2_ERR_ARG;
+    }
+    if (cap && (reinterpret_cast<uintptr_t>(pairs_out) & 7u)) {
+        *err = "pairs_out must be 8-byte aligned";
+        return CB2_ERR_ARG;
+    }
+    const float* boxes = reinterpret_cast<const float*>(aabbs);
+    const uint64_t ne = n * LARGE_CELLS;
+    const int cell_bits = 23;  // GRID_MAX^2 cells + the sentinel
+    int pos_bits = 1;
+    while (((uint64_t)1 << pos_bits) < n) ++pos_bits;
+    // internal pair buffer: the caller's cap, but start no larger than 16 pairs per box
+    uint64_t kcap = cap < 16 * n + 1024 ? cap : 16 * n + 1024;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t sort1 = 0, sort2 = 0, sort3 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort1, (uint64_t*)nullptr, (uint64_t*)nullptr,
+                                        (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)n, 0, 64, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, sort2, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                        (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)ne, 0,
+                                        cell_bits, st);
+        cub::DeviceRadixSort::SortKeys(nullptr, sort3, (unsigned long long*)nullptr,
+                                       (unsigned long long*)nullptr, (int64_t)(kcap ? kcap : 1), 0,
+                                       32 + pos_bits, st);
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+        const size_t o_keys0 = take(8 * n), o_keys1 = take(8 * n), o_idx0 = take(4 * n);
+        const size_t o_S = take(8 * n), o_U = take(8 * n), o_V = take(8 * n);
+        const size_t o_c0 = take(4 * ne), o_c1 = take(4 * ne), o_p0 = take(4 * ne), o_p1 = take(4 * ne);
+        const size_t o_large = take(4 * n), o_G = take(sizeof(grid_params)), o_flag = take(256);
+        const size_t o_pk = take(8 * (kcap ? kcap : 1));
+        size_t tmpsz = sort1 > sort2 ? sort1 : sort2;
+        tmpsz = tmpsz > sort3 ? tmpsz : sort3;
+        const size_t o_tmp = take(tmpsz);
+        int rc = ensure_cap(w, off, err);
+        if (rc) return rc;
+        char* base = static_cast<char*>(w->buf);
+        uint64_t* keys0 = (uint64_t*)(base + o_keys0);
+        uint64_t* keys1 = (uint64_t*)(base + o_keys1);
+        uint32_t* idx0 = (uint32_t*)(base + o_idx0);
+        float2* S = (float2*)(base + o_S);
+        float2* U = (float2*)(base + o_U);
+        float2* V = (float2*)(base + o_V);
+        uint32_t* c0 = (uint32_t*)(base + o_c0);
+        uint32_t* c1 = (uint32_t*)(base + o_c1);
+        uint32_t* p0 = (uint32_t*)(base + o_p0);
+        uint32_t* p1 = (uint32_t*)(base + o_p1);
+        uint32_t* large = (uint32_t*)(base + o_large);
+        grid_params* G = (grid_params*)(base + o_G);
+        uint32_t* flag = (uint32_t*)(base + o_flag);
+        unsigned long long* pk = (unsigned long long*)(base + o_pk);
+        void* tmp = base + o_tmp;
+
+        SAP_CK(cudaMemsetAsync(flag, 0, 4, st));
+        SAP_CK(cudaMemsetAsync(G, 0, sizeof(grid_params), st));
+        SAP_CK(cudaMemsetAsync(G, 0xFF, 2 * sizeof(uint32_t), st));  // min_u, min_v = +max
+        k_sap_keys<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, keys0, idx0, flag);
+        size_t tb = sort1;
+        SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, idx0, perm_out, (int64_t)n, 0,
+                                               64, st));
+        k_sap_gather<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, perm_out, S, U, V);
+        k_grid_stats<<<592, 256, 0, st>>>(U, V, n, G);
+        k_grid_params<<<1, 32, 0, st>>>(G, n);
+        k_grid_emit<<<nblk(n, 256), 256, 0, st>>>(U, V, n, G, c0, p0, large);
+        tb = sort2;
+        SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, p0, p1, (int64_t)ne, 0, cell_bits, st));
+        k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(S, U, V, c1, p1, ne, G, pk, kcap);
+        k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, G, pk, kcap);
+        k_grid_total<<<1, 32, 0, st>>>(G, flag, w->h_total);
+        *launches += 10;
+        SAP_CK(cudaGetLastError());
+        SAP_CK(cudaStreamSynchronize(st));
+        if (w->h_total[1]) {
+            *err = "NaN extent on the sweep axis";
+            return CB2_ERR_NAN;
+        }
+        const uint64_t np = w->h_total[0];
+        *n_pairs = np;
+        if (np == 0) return CB2_OK;
+        if (np > cap) return CB2_ERR_NOSPC;
+        if (np > kcap) {  // denser than 16 pairs per box: run again with the exact room
+            kcap = np;
+            continue;
+        }
+        // the sorted u64 keys (b << 32 | a) ARE the interleaved (a, b) u32 pairs, in Vec order
+        tb = sort3;
+        SAP_CK(cub::DeviceRadixSort::SortKeys(tmp, tb, pk, reinterpret_cast<unsigned long long*>(pairs_out),
+                                              (int64_t)np, 0, 32 + pos_bits, st));
+        *launches += 1;
+        return CB2_OK;
+    }
+    *err = "pair count changed between passes";
+    return CB2_ERR_CUDA;
 }
 
 }  // namespace cb2
