@@ -17,14 +17,15 @@
 //   k_grid_params  cell size = 2^ceil(log2) of the 99.9 % extent quantile (most boxes touch <= 4
 //                  cells), grid clamped to 2048 x 2048
 //   k_grid_emit    one (cell, position) entry per cell a box touches (<= 9; boxes touching more are
-//                  "large" and go to k_sap_large), written at box-major offsets
+//                  "large" and go to k_sap_large): 4 box-major slots plus a spill tail
 //   radix sort     stable sort of the entries by cell        -> per cell: positions ascending
+//   k_grid_pack    boxes in entry order, so the sweep reads memory sequentially
 //   k_grid_sweep   one thread per entry (cell C, a): walk forward through C's entries b while
 //                  min_s[b] < max_s[a]; strict Aabb3 test (aabb3.rs:246-253); a pair is reported only
 //                  in its canonical cell (max of the two boxes' first cells), so exactly once
 //   k_sap_large    the rare large boxes against every box of their sweep window
-//   radix sort     of the u64 keys (b << 32 | a): the sorted array IS the interleaved (a, b) u32
-//                  pair list in the reference's Vec order (b ascending, then a ascending)
+//   radix sort     of the packed keys (b << bits | a), then k_sap_unpack: the (a, b) u32 pair list
+//                  in the reference's Vec order (b ascending, then a ascending)
 // Monotone cell mapping (floor of a monotone f32 expression) guarantees that two boxes that overlap
 // strictly on u and v share their canonical cell, so no pair is missed.  The old tiled sweep is kept
 // behind CB2_SAP_LEGACY=1 for A/B tests.
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(SAP_BLOCK) k_sap_sweep(
 // ---- grid-accelerated sweep -------------------------------------------------------------------------
 constexpr int GRID_MAX = 2048;        // cells per axis at most
 constexpr int LARGE_CELLS = 9;        // a box touching more cells than this is "large"
+constexpr int SLOT_CELLS = 4;         // entry array = n * SLOT_CELLS + n/4 records
 constexpr int EXT_BUCKETS = 64;       // log2 histogram of extents: bucket = exponent + 32, clamped
 
 struct grid_params {
@@ -290,76 +292,148 @@ __device__ __forceinline__ cell_range box_cells(const grid_params* __restrict__ 
     return r;
 }
 
-// entries at box-major slots [k * LARGE_CELLS, +LARGE_CELLS); unused slots carry the sentinel cell
+// Entries (cell, position), compacted in POSITION order through an exclusive scan of the per-box
+// cell counts: the stable sort by cell then leaves every cell's entries ascending by position.
+// The entry array holds n * SLOT_CELLS + n/4 records (the cell size covers the 99.9 % extent
+// quantile, so nearly every box touches <= 2 x 2 cells); a box that does not fit is treated as large.
+__global__ void __launch_bounds__(256) k_grid_count(const float2* __restrict__ U,
+                                                   const float2* __restrict__ V, uint64_t n,
+                                                   const grid_params* __restrict__ G,
+                                                   uint32_t* __restrict__ counts) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const cell_range r = box_cells(G, __ldg(U + k), __ldg(V + k));
+    const int cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
+    counts[k] = cnt > LARGE_CELLS ? 0u : (uint32_t)cnt;
+}
+
 __global__ void __launch_bounds__(256) k_grid_emit(const float2* __restrict__ U,
                                                   const float2* __restrict__ V, uint64_t n,
                                                   grid_params* __restrict__ G,
+                                                  const uint32_t* __restrict__ offs, uint64_t n_entries,
                                                   uint32_t* __restrict__ ecell,
                                                   uint32_t* __restrict__ epos,
                                                   uint32_t* __restrict__ large_list) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const cell_range r = box_cells(G, __ldg(U + k), __ldg(V + k));
-    const uint32_t sentinel = (uint32_t)(G->nu * G->nv);
     const int cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
-    uint32_t* c = ecell + k * LARGE_CELLS;
-    uint32_t* p = epos + k * LARGE_CELLS;
-    int j = 0;
-    if (cnt <= LARGE_CELLS) {
-        for (int iu = r.u0; iu <= r.u1; ++iu)
-            for (int iv = r.v0; iv <= r.v1; ++iv) {
-                c[j] = (uint32_t)(iu * G->nv + iv);
-                p[j] = (uint32_t)k;
-                ++j;
-            }
-    } else {
+    const uint64_t o = offs[k];
+    if (cnt > LARGE_CELLS || o + (uint64_t)cnt > n_entries) {
         large_list[atomicAdd(&G->n_large, 1u)] = (uint32_t)k;
+        return;
     }
-    for (; j < LARGE_CELLS; ++j) {
-        c[j] = sentinel;
-        p[j] = (uint32_t)k;
-    }
+    uint32_t* c = ecell + o;
+    uint32_t* p = epos + o;
+    for (int iu = r.u0; iu <= r.u1; ++iu)
+        for (int iv = r.v0; iv <= r.v1; ++iv) {
+            *c++ = (uint32_t)(iu * G->nv + iv);
+            *p++ = (uint32_t)k;
+        }
 }
 
+// after the sort by cell: the boxes of each entry, in entry order, so the sweep reads them
+// sequentially instead of gathering
+__global__ void __launch_bounds__(256) k_grid_pack(const float2* __restrict__ S,
+                                                  const float2* __restrict__ U,
+                                                  const float2* __restrict__ V,
+                                                  const uint32_t* __restrict__ ecell,
+                                                  const uint32_t* __restrict__ epos, uint64_t n_entries,
+                                                  const grid_params* __restrict__ G,
+                                                  float2* __restrict__ eS, float2* __restrict__ eU,
+                                                  float2* __restrict__ eV) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    if (__ldg(ecell + e) >= (uint32_t)(G->nu * G->nv)) return;  // sentinel slots sort to the end
+    const uint32_t b = __ldg(epos + e);
+    eS[e] = __ldg(S + b);
+    eU[e] = __ldg(U + b);
+    eV[e] = __ldg(V + b);
+}
+
+// pair key = b << pos_bits | a: sorting it gives the reference's Vec order (b asc, then a asc)
 __device__ __forceinline__ void emit_pair(grid_params* __restrict__ G, unsigned long long* __restrict__ keys,
-                                          uint64_t cap, uint32_t a, uint32_t b) {
-    // warp-aggregated would save atomics; pairs per thread are few, keep it simple
+                                          uint64_t cap, int pos_bits, uint32_t a, uint32_t b) {
     const unsigned long long w = atomicAdd(&G->n_pairs, 1ull);
-    if (w < cap) keys[w] = ((unsigned long long)b << 32) | a;
+    if (w < cap) keys[w] = ((unsigned long long)b << pos_bits) | a;
 }
 
-__global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ S,
-                                                   const float2* __restrict__ U,
-                                                   const float2* __restrict__ V,
+__global__ void __launch_bounds__(256) k_sap_unpack(const unsigned long long* __restrict__ keys,
+                                                   uint64_t np, int pos_bits,
+                                                   uint32_t* __restrict__ pairs) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const unsigned long long k = keys[p];
+    reinterpret_cast<uint2*>(pairs)[p] =
+        make_uint2((uint32_t)(k & ((1ull << pos_bits) - 1ull)), (uint32_t)(k >> pos_bits));
+}
+
+__global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ eS,
+                                                   const float2* __restrict__ eU,
+                                                   const float2* __restrict__ eV,
                                                    const uint32_t* __restrict__ ecell,
                                                    const uint32_t* __restrict__ epos, uint64_t n_entries,
                                                    grid_params* __restrict__ G,
-                                                   unsigned long long* __restrict__ keys, uint64_t cap) {
+                                                   unsigned long long* __restrict__ keys, uint64_t cap,
+                                                   int pos_bits) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_entries) return;
-    const uint32_t cell = __ldg(ecell + e);
-    if (cell >= (uint32_t)(G->nu * G->nv)) return;  // sentinel slot
-    const uint32_t a = __ldg(epos + e);
-    const float2 as = __ldg(S + a), au = __ldg(U + a), av = __ldg(V + a);
-    const int au0 = cell_coord(au.x, G->org_u, G->inv_u, G->nu);
-    const int av0 = cell_coord(av.x, G->org_v, G->inv_v, G->nv);
-    const int cu = (int)(cell / (uint32_t)G->nv), cv = (int)(cell % (uint32_t)G->nv);
-    for (uint64_t f = e + 1; f < n_entries; ++f) {
-        if (__ldg(ecell + f) != cell) break;
-        const uint32_t b = __ldg(epos + f);  // b > a: entries of a cell ascend by position
-        const float2 bs = __ldg(S + b);
-        if (!(bs.x < as.y)) break;           // min_s ascends with position: window closed
-        // Aabb3::intersects (aabb3.rs:246-253), strict on all three axes
-        if (!(as.x < bs.y)) continue;
-        const float2 bu = __ldg(U + b);
-        if (!(au.y > bu.x && au.x < bu.y)) continue;
-        const float2 bv = __ldg(V + b);
-        if (!(av.y > bv.x && av.x < bv.y)) continue;
-        // report only in the canonical cell of the pair
-        const int bu0 = cell_coord(bu.x, G->org_u, G->inv_u, G->nu);
-        const int bv0 = cell_coord(bv.x, G->org_v, G->inv_v, G->nv);
-        if ((au0 > bu0 ? au0 : bu0) != cu || (av0 > bv0 ? av0 : bv0) != cv) continue;
-        emit_pair(G, keys, cap, a, b);
+    const float org_u = G->org_u, inv_u = G->inv_u, org_v = G->org_v, inv_v = G->inv_v;
+    const int nu = G->nu, nv = G->nv;
+    // no early return: every lane takes part in the warp-wide reservation below
+    uint32_t cell = 0xFFFFFFFFu;
+    if (e < n_entries) cell = __ldg(ecell + e);
+    const bool valid = cell < (uint32_t)(nu * nv);  // not a sentinel slot
+    float2 as = make_float2(0.f, 0.f), au = as, av = as;
+    if (valid) {
+        as = __ldg(eS + e);
+        au = __ldg(eU + e);
+        av = __ldg(eV + e);
+    }
+    const int au0 = cell_coord(au.x, org_u, inv_u, nu);
+    const int av0 = cell_coord(av.x, org_v, inv_v, nv);
+    const int cu = (int)(cell / (uint32_t)nv), cv = (int)(cell % (uint32_t)nv);
+    // two passes over the (short) window: count, reserve output room once per WARP (a single
+    // counter cannot take one atomic per pair), then write
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t mine = 0;
+    unsigned long long w = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t a = (pass == 1 && mine) ? __ldg(epos + e) : 0u;
+        if (valid && (pass == 0 || mine)) {
+            for (uint64_t f = e + 1; f < n_entries; ++f) {
+                if (__ldg(ecell + f) != cell) break;
+                const float2 bs = __ldg(eS + f);  // entries of a cell ascend by position, so by min_s
+                if (!(bs.x < as.y)) break;        // window closed
+                // Aabb3::intersects (aabb3.rs:246-253), strict on all three axes
+                if (!(as.x < bs.y)) continue;
+                const float2 bu = __ldg(eU + f);
+                if (!(au.y > bu.x && au.x < bu.y)) continue;
+                const float2 bv = __ldg(eV + f);
+                if (!(av.y > bv.x && av.x < bv.y)) continue;
+                // report only in the canonical cell of the pair
+                const int bu0 = cell_coord(bu.x, org_u, inv_u, nu);
+                const int bv0 = cell_coord(bv.x, org_v, inv_v, nv);
+                if ((au0 > bu0 ? au0 : bu0) != cu || (av0 > bv0 ? av0 : bv0) != cv) continue;
+                if (pass == 0) {
+                    ++mine;
+                } else {
+                    if (w < cap) keys[w] = ((unsigned long long)__ldg(epos + f) << pos_bits) | a;
+                    ++w;
+                }
+            }
+        }
+        if (pass == 0) {
+            uint32_t incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= (unsigned)off) incl += o;
+            }
+            unsigned long long base = 0;
+            if (lane == 31u && incl) base = atomicAdd(&G->n_pairs, (unsigned long long)incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            w = base + (incl - mine);
+        }
     }
 }
 
@@ -369,8 +443,10 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
                                                   const float2* __restrict__ U,
                                                   const float2* __restrict__ V, uint64_t n,
                                                   const uint32_t* __restrict__ large_list,
+                                                  const uint32_t* __restrict__ offs, uint64_t n_entries,
                                                   grid_params* __restrict__ G,
-                                                  unsigned long long* __restrict__ keys, uint64_t cap) {
+                                                  unsigned long long* __restrict__ keys, uint64_t cap,
+                                                  int pos_bits) {
     const uint32_t nl = G->n_large;
     for (uint32_t li = 0; li < nl; ++li) {
         const uint32_t p = __ldg(large_list + li);
@@ -382,12 +458,13 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
             if (!(ps.y > qs.x && ps.x < qs.y && pu.y > qu.x && pu.x < qu.y && pv.y > qv.x && pv.x < qv.y))
                 continue;
             if (q > p) {
-                emit_pair(G, keys, cap, p, (uint32_t)q);
+                emit_pair(G, keys, cap, pos_bits, p, (uint32_t)q);
             } else {
                 // (q, p) with q < p: if q is large too, q's own forward pass reports it
                 const cell_range r = box_cells(G, qu, qv);
-                if ((r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1) <= LARGE_CELLS)
-                    emit_pair(G, keys, cap, (uint32_t)q, p);
+                const int cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
+                if (cnt <= LARGE_CELLS && (uint64_t)__ldg(offs + q) + (uint64_t)cnt <= n_entries)
+                    emit_pair(G, keys, cap, pos_bits, (uint32_t)q, p);
             }
         }
     }
@@ -583,7 +660,7 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         SAP_CK(cudaGetLastError());
         return CB2_OK;
     }
-    if (n > 0x7FFFFFFFull / LARGE_CELLS) {
+    if (n > 0x7FFFFFFFull / (SLOT_CELLS + 1)) {
         *err = "too many boxes for one call";
         return CB2_ERR_ARG;
     }
@@ -592,7 +669,7 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         return CB2_ERR_ARG;
     }
     const float* boxes = reinterpret_cast<const float*>(aabbs);
-    const uint64_t ne = n * LARGE_CELLS;
+    const uint64_t ne = n * SLOT_CELLS + n / 4 + 1024;
     const int cell_bits = 23;  // GRID_MAX^2 cells + the sentinel
     int pos_bits = 1;
     while (((uint64_t)1 << pos_bits) < n) ++pos_bits;
@@ -605,18 +682,24 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         cub::DeviceRadixSort::SortPairs(nullptr, sort2, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                         (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)ne, 0,
                                         cell_bits, st);
+        size_t scan_tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                      (int64_t)n, st);
         cub::DeviceRadixSort::SortKeys(nullptr, sort3, (unsigned long long*)nullptr,
                                        (unsigned long long*)nullptr, (int64_t)(kcap ? kcap : 1), 0,
-                                       32 + pos_bits, st);
+                                       2 * pos_bits, st);
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
         const size_t o_keys0 = take(8 * n), o_keys1 = take(8 * n), o_idx0 = take(4 * n);
         const size_t o_S = take(8 * n), o_U = take(8 * n), o_V = take(8 * n);
         const size_t o_c0 = take(4 * ne), o_c1 = take(4 * ne), o_p0 = take(4 * ne), o_p1 = take(4 * ne);
         const size_t o_large = take(4 * n), o_G = take(sizeof(grid_params)), o_flag = take(256);
-        const size_t o_pk = take(8 * (kcap ? kcap : 1));
+        const size_t o_cnt = take(4 * n), o_offs = take(4 * n);
+        const size_t o_eS = take(8 * ne), o_eU = take(8 * ne), o_eV = take(8 * ne);
+        const size_t o_pk = take(8 * (kcap ? kcap : 1)), o_pk2 = take(8 * (kcap ? kcap : 1));
         size_t tmpsz = sort1 > sort2 ? sort1 : sort2;
         tmpsz = tmpsz > sort3 ? tmpsz : sort3;
+        tmpsz = tmpsz > scan_tmp ? tmpsz : scan_tmp;
         const size_t o_tmp = take(tmpsz);
         int rc = ensure_cap(w, off, err);
         if (rc) return rc;
@@ -634,12 +717,19 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         uint32_t* large = (uint32_t*)(base + o_large);
         grid_params* G = (grid_params*)(base + o_G);
         uint32_t* flag = (uint32_t*)(base + o_flag);
+        uint32_t* cnts = (uint32_t*)(base + o_cnt);
+        uint32_t* offs = (uint32_t*)(base + o_offs);
+        float2* eS = (float2*)(base + o_eS);
+        float2* eU = (float2*)(base + o_eU);
+        float2* eV = (float2*)(base + o_eV);
         unsigned long long* pk = (unsigned long long*)(base + o_pk);
+        unsigned long long* pk2 = (unsigned long long*)(base + o_pk2);
         void* tmp = base + o_tmp;
 
         SAP_CK(cudaMemsetAsync(flag, 0, 4, st));
         SAP_CK(cudaMemsetAsync(G, 0, sizeof(grid_params), st));
         SAP_CK(cudaMemsetAsync(G, 0xFF, 2 * sizeof(uint32_t), st));  // min_u, min_v = +max
+        SAP_CK(cudaMemsetAsync(c0, 0xFF, 4 * ne, st));  // unused entry records = sentinel cells
         k_sap_keys<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, keys0, idx0, flag);
         size_t tb = sort1;
         SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, idx0, perm_out, (int64_t)n, 0,
@@ -647,13 +737,17 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         k_sap_gather<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, perm_out, S, U, V);
         k_grid_stats<<<592, 256, 0, st>>>(U, V, n, G);
         k_grid_params<<<1, 32, 0, st>>>(G, n);
-        k_grid_emit<<<nblk(n, 256), 256, 0, st>>>(U, V, n, G, c0, p0, large);
+        k_grid_count<<<nblk(n, 256), 256, 0, st>>>(U, V, n, G, cnts);
+        tb = scan_tmp;
+        SAP_CK(cub::DeviceScan::ExclusiveSum(tmp, tb, cnts, offs, (int64_t)n, st));
+        k_grid_emit<<<nblk(n, 256), 256, 0, st>>>(U, V, n, G, offs, ne, c0, p0, large);
         tb = sort2;
         SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, p0, p1, (int64_t)ne, 0, cell_bits, st));
-        k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(S, U, V, c1, p1, ne, G, pk, kcap);
-        k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, G, pk, kcap);
+        k_grid_pack<<<nblk(ne, 256), 256, 0, st>>>(S, U, V, c1, p1, ne, G, eS, eU, eV);
+        k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, ne, G, pk, kcap, pos_bits);
+        k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, offs, ne, G, pk, kcap, pos_bits);
         k_grid_total<<<1, 32, 0, st>>>(G, flag, w->h_total);
-        *launches += 10;
+        *launches += 13;
         SAP_CK(cudaGetLastError());
         SAP_CK(cudaStreamSynchronize(st));
         if (w->h_total[1]) {
@@ -668,11 +762,11 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
             kcap = np;
             continue;
         }
-        // the sorted u64 keys (b << 32 | a) ARE the interleaved (a, b) u32 pairs, in Vec order
+        // sort the packed keys (b << pos_bits | a): the reference's Vec order, then unpack
         tb = sort3;
-        SAP_CK(cub::DeviceRadixSort::SortKeys(tmp, tb, pk, reinterpret_cast<unsigned long long*>(pairs_out),
-                                              (int64_t)np, 0, 32 + pos_bits, st));
-        *launches += 1;
+        SAP_CK(cub::DeviceRadixSort::SortKeys(tmp, tb, pk, pk2, (int64_t)np, 0, 2 * pos_bits, st));
+        k_sap_unpack<<<nblk(np, 256), 256, 0, st>>>(pk2, np, pos_bits, pairs_out);
+        *launches += 2;
         return CB2_OK;
     }
     *err = "pair count changed between passes";
