@@ -47,6 +47,8 @@ SYMBOLS = [
     "cb2_gjk3_intersection", "cb2_gjk3_distance", "cb2_gjk3_time_of_impact",
     "cb2_gjk3_intersection_dev", "cb2_gjk3_distance_dev", "cb2_gjk3_time_of_impact_dev",
     "cb2_gjk3_intersection_bodies_dev",
+    "cb2_composites_upload", "cb2_gjk3_intersection_complex", "cb2_gjk3_distance_complex",
+    "cb2_gjk3_time_of_impact_complex",
     "cb2_sap3_find_collider_pairs", "cb2_sap3_find_collider_pairs_dev",
     "cb2_world_aabbs", "cb2_world_aabbs_dev",
 ]
@@ -87,6 +89,11 @@ def load():
     lib.cb2_gjk3_distance_dev.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp, vp]
     lib.cb2_gjk3_time_of_impact_dev.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp]
     lib.cb2_gjk3_intersection_bodies_dev.argtypes = [vp, u32, sp, vp, vp, vp, u64, vp, vp, vp]
+    lib.cb2_composites_upload.argtypes = [vp, vp, vp, vp, u32]
+    lib.cb2_gjk3_intersection_complex.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_gjk3_distance_complex.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_gjk3_time_of_impact_complex.argtypes = [vp, u32, sp, vp, vp, vp, vp, vp, vp, u64, u32,
+                                                    vp, vp]
     lib.cb2_sap3_find_collider_pairs.argtypes = [vp, vp, u64, C.POINTER(u32), vp, vp, u64,
                                                  C.POINTER(u64)]
     lib.cb2_sap3_find_collider_pairs_dev.argtypes = [vp, vp, u64, u32, vp, vp, u64,

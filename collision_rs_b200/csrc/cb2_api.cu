@@ -38,6 +38,14 @@ struct cb2_ctx {
     char* d_stage[NS] = {nullptr, nullptr};
     size_t stage_cap = 0;
     sap_workspace* sap = nullptr;
+    // composite table (cb2_composites_upload) and the composite-call workspace
+    uint32_t* d_comp_off = nullptr;
+    uint32_t* d_comp_shape = nullptr;
+    float4* d_comp_local = nullptr;
+    uint32_t n_comp = 0;
+    std::vector<uint32_t> h_comp_off;
+    void* d_cx = nullptr;
+    size_t cx_cap = 0;
     void* d_misc = nullptr;  // host-API SAP / AABB buffers
     size_t misc_cap = 0;
     // classified (polyhedron) narrow phase workspaces: [0..NS) follow the host-API streams,
@@ -165,6 +173,10 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_cell_ext) cudaFree(c->d_cell_ext);
     if (c->d_cell_cursor) cudaFree(c->d_cell_cursor);
     if (c->d_misc) cudaFree(c->d_misc);
+    if (c->d_comp_off) cudaFree(c->d_comp_off);
+    if (c->d_comp_shape) cudaFree(c->d_comp_shape);
+    if (c->d_comp_local) cudaFree(c->d_comp_local);
+    if (c->d_cx) cudaFree(c->d_cx);
     for (int i = 0; i < cb2_ctx::NS; ++i) {
         free_ws(c->ws[i]);
         if (c->ws[i].EC) cudaFree(c->ws[i].EC);
@@ -685,3 +697,178 @@ int cb2_world_aabbs(cb2_ctx* c, const uint32_t* shape, const cb2_xform* t, uint6
 }
 
 }  // extern "C"
+
+// ---- composite shapes (gjk/mod.rs:412-588) ------------------------------------------------------------
+extern "C" int cb2_composites_upload(cb2_ctx* c, const uint32_t* part_off, const uint32_t* part_shape,
+                                     const cb2_xform* part_local, uint32_t n_comp) {
+    if (!c || !part_off || (n_comp && part_off[n_comp] && (!part_shape || !part_local)))
+        return fail(c, CB2_ERR_ARG, "null argument");
+    if (!c->d_shapes) return fail(c, CB2_ERR_ARG, "cb2_shapes_upload has not been called");
+    const uint32_t n_parts = part_off[n_comp];
+    if (part_off[0] != 0) return fail(c, CB2_ERR_ARG, "part_off[0] must be 0");
+    for (uint32_t k = 0; k < n_comp; ++k)
+        if (part_off[k] > part_off[k + 1]) return fail(c, CB2_ERR_ARG, "part_off must not decrease");
+    for (uint32_t k = 0; k < n_parts; ++k)
+        if (part_shape[k] >= c->n_shapes) return fail(c, CB2_ERR_ARG, "part shape index out of range");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaDeviceSynchronize());
+    if (c->d_comp_off) cudaFree(c->d_comp_off);
+    if (c->d_comp_shape) cudaFree(c->d_comp_shape);
+    if (c->d_comp_local) cudaFree(c->d_comp_local);
+    c->d_comp_off = c->d_comp_shape = nullptr;
+    c->d_comp_local = nullptr;
+    CK(c, cudaMalloc(&c->d_comp_off, sizeof(uint32_t) * ((size_t)n_comp + 1)));
+    CK(c, cudaMalloc(&c->d_comp_shape, sizeof(uint32_t) * (n_parts ? n_parts : 1)));
+    CK(c, cudaMalloc(&c->d_comp_local, sizeof(cb2_xform) * (n_parts ? n_parts : 1)));
+    CK(c, cudaMemcpy(c->d_comp_off, part_off, sizeof(uint32_t) * ((size_t)n_comp + 1), cudaMemcpyHostToDevice));
+    if (n_parts) {
+        CK(c, cudaMemcpy(c->d_comp_shape, part_shape, sizeof(uint32_t) * n_parts, cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->d_comp_local, part_local, sizeof(cb2_xform) * n_parts, cudaMemcpyHostToDevice));
+    }
+    c->n_comp = n_comp;
+    c->h_comp_off.assign(part_off, part_off + n_comp + 1);
+    return CB2_OK;
+}
+
+static int complex_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_settings* settings,
+                        const uint32_t* l_comp, const uint32_t* r_comp, const cb2_xform* l_t0,
+                        const cb2_xform* l_t1, const cb2_xform* r_t0, const cb2_xform* r_t1,
+                        uint64_t n, uint32_t iter_cap, cb2_contact* out_c, float* out_d,
+                        uint8_t* status) {
+    if (!c) return CB2_ERR_ARG;
+    int rc = check_settings(c, settings);
+    if (rc) return rc;
+    if (op != OP_DISTANCE && strategy > CB2_COLLISION_ONLY) return fail(c, CB2_ERR_ARG, "bad strategy");
+    if (n == 0) return CB2_OK;
+    if (!c->d_comp_off) return fail(c, CB2_ERR_ARG, "cb2_composites_upload has not been called");
+    if (!l_comp || !r_comp || !l_t0 || !r_t0 || !status) return fail(c, CB2_ERR_ARG, "null argument");
+    if (op == OP_DISTANCE ? !out_d : !out_c) return fail(c, CB2_ERR_ARG, "null output");
+    if (op == OP_TOI && (!l_t1 || !r_t1)) return fail(c, CB2_ERR_ARG, "null end transform");
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (l_comp[i] >= c->n_comp || r_comp[i] >= c->n_comp)
+            return fail(c, CB2_ERR_ARG, "composite index out of range");
+        total += (uint64_t)(c->h_comp_off[l_comp[i] + 1] - c->h_comp_off[l_comp[i]]) *
+                 (c->h_comp_off[r_comp[i] + 1] - c->h_comp_off[r_comp[i]]);
+    }
+    if (total > 0x7FFFFFFFull) return fail(c, CB2_ERR_ARG, "more than 2^31-1 part pairs in one call");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream[0];
+    const int n_xf = op == OP_TOI ? 4 : 2;
+    const size_t out_rec = op == OP_DISTANCE ? sizeof(float) : sizeof(cb2_contact);
+    const uint64_t T = total ? total : 1;
+    size_t scan_tmp = 0;
+    cx_scan(nullptr, &scan_tmp, nullptr, nullptr, n, st);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
+    const size_t o_lc = take(4 * n), o_rc = take(4 * n);
+    size_t o_t[4];
+    for (int x = 0; x < n_xf; ++x) o_t[x] = take(sizeof(cb2_xform) * n);
+    const size_t o_cnt = take(8 * n), o_off = take(8 * n), o_scan = take(scan_tmp);
+    const size_t o_sl = take(4 * T), o_sr = take(4 * T);
+    size_t o_st[4];
+    for (int x = 0; x < n_xf; ++x) o_st[x] = take(sizeof(cb2_xform) * T);
+    const size_t o_sout = take(out_rec * T), o_sstat = take(T);
+    const size_t o_out = take(out_rec * n), o_stat = take(n);
+    if (c->cx_cap < off) {
+        if (c->d_cx) cudaFree(c->d_cx);
+        c->d_cx = nullptr;
+        c->cx_cap = 0;
+        CK(c, cudaMalloc(&c->d_cx, off));
+        c->cx_cap = off;
+    }
+    char* base = static_cast<char*>(c->d_cx);
+    // order of the transform slots: l_t0, r_t0, l_t1, r_t1
+    const cb2_xform* src[4] = {l_t0, r_t0, l_t1, r_t1};
+    CK(c, cudaMemcpyAsync(base + o_lc, l_comp, 4 * n, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + o_rc, r_comp, 4 * n, cudaMemcpyHostToDevice, st));
+    for (int x = 0; x < n_xf; ++x)
+        CK(c, cudaMemcpyAsync(base + o_t[x], src[x], sizeof(cb2_xform) * n, cudaMemcpyHostToDevice, st));
+    complex_args X;
+    std::memset(&X, 0, sizeof(X));
+    X.comp_off = c->d_comp_off;
+    X.comp_shape = c->d_comp_shape;
+    X.comp_local = c->d_comp_local;
+    X.l_comp = reinterpret_cast<uint32_t*>(base + o_lc);
+    X.r_comp = reinterpret_cast<uint32_t*>(base + o_rc);
+    X.l_t0 = reinterpret_cast<float4*>(base + o_t[0]);
+    X.r_t0 = reinterpret_cast<float4*>(base + o_t[1]);
+    if (op == OP_TOI) {
+        X.l_t1 = reinterpret_cast<float4*>(base + o_t[2]);
+        X.r_t1 = reinterpret_cast<float4*>(base + o_t[3]);
+    }
+    X.n = n;
+    X.sub_count = reinterpret_cast<uint64_t*>(base + o_cnt);
+    X.sub_off = reinterpret_cast<uint64_t*>(base + o_off);
+    X.sub_l_shape = reinterpret_cast<uint32_t*>(base + o_sl);
+    X.sub_r_shape = reinterpret_cast<uint32_t*>(base + o_sr);
+    X.sub_l_t0 = reinterpret_cast<float4*>(base + o_st[0]);
+    X.sub_r_t0 = reinterpret_cast<float4*>(base + o_st[1]);
+    if (op == OP_TOI) {
+        X.sub_l_t1 = reinterpret_cast<float4*>(base + o_st[2]);
+        X.sub_r_t1 = reinterpret_cast<float4*>(base + o_st[3]);
+    }
+    X.sub_contact = reinterpret_cast<cb2_contact*>(base + o_sout);
+    X.sub_distance = reinterpret_cast<float*>(base + o_sout);
+    X.sub_status = reinterpret_cast<uint8_t*>(base + o_sstat);
+    X.out_contact = reinterpret_cast<cb2_contact*>(base + o_out);
+    X.out_distance = reinterpret_cast<float*>(base + o_out);
+    X.out_status = reinterpret_cast<uint8_t*>(base + o_stat);
+    CK(c, launch_cx_count(X, st));
+    size_t tb = scan_tmp;
+    CK(c, cx_scan(base + o_scan, &tb, X.sub_count, X.sub_off, n, st));
+    CK(c, launch_cx_expand(X, st));
+    c->launches += 3;
+    if (total) {
+        narrow_args A;
+        std::memset(&A, 0, sizeof(A));
+        A.l_shape = X.sub_l_shape;
+        A.r_shape = X.sub_r_shape;
+        A.l_t = X.sub_l_t0;
+        A.r_t = X.sub_r_t0;
+        A.l_t1 = X.sub_l_t1;
+        A.r_t1 = X.sub_r_t1;
+        A.n = total;
+        A.settings = *settings;
+        A.iter_cap = iter_cap ? iter_cap : 1024u;
+        A.out_contact = reinterpret_cast<cb2_contact*>(base + o_sout);
+        A.out_distance = reinterpret_cast<float*>(base + o_sout);
+        A.out_status = reinterpret_cast<uint8_t*>(base + o_sstat);
+        rc = launch_op(c, op, op == OP_INTERSECTION ? strategy : CB2_FULL_RESOLUTION, A, st, 0);
+        if (rc) return rc;
+    }
+    CK(c, launch_cx_reduce(X, op == OP_INTERSECTION ? 0u : (op == OP_DISTANCE ? 1u : 2u), strategy, st));
+    ++c->launches;
+    if (op == OP_DISTANCE)
+        CK(c, cudaMemcpyAsync(out_d, base + o_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    else
+        CK(c, cudaMemcpyAsync(out_c, base + o_out, sizeof(cb2_contact) * n, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(status, base + o_stat, n, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return CB2_OK;
+}
+
+extern "C" {
+int cb2_gjk3_intersection_complex(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                                  const uint32_t* l_comp, const uint32_t* r_comp,
+                                  const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                                  cb2_contact* out, uint8_t* status) {
+    return complex_host(c, OP_INTERSECTION, strategy, settings, l_comp, r_comp, l_t, nullptr, r_t,
+                        nullptr, n, 0, out, nullptr, status);
+}
+int cb2_gjk3_distance_complex(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_comp,
+                              const uint32_t* r_comp, const cb2_xform* l_t, const cb2_xform* r_t,
+                              uint64_t n, float* out, uint8_t* status) {
+    return complex_host(c, OP_DISTANCE, 0, settings, l_comp, r_comp, l_t, nullptr, r_t, nullptr, n, 0,
+                        nullptr, out, status);
+}
+int cb2_gjk3_time_of_impact_complex(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                                    const uint32_t* l_comp, const uint32_t* r_comp,
+                                    const cb2_xform* l_t0, const cb2_xform* l_t1,
+                                    const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
+                                    uint32_t iter_cap, cb2_contact* out, uint8_t* status) {
+    return complex_host(c, OP_TOI, strategy, settings, l_comp, r_comp, l_t0, l_t1, r_t0, r_t1, n,
+                        iter_cap, out, nullptr, status);
+}
+}

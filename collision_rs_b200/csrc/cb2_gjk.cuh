@@ -22,7 +22,8 @@ enum : uint8_t {
     ST_PANIC_INV_SCALE = 4,
     ST_NONCONVERGED = 5,
     ST_PANIC_EPA_EMPTY = 6,
-    ST_SCRATCH_OVERFLOW = 7
+    ST_SCRATCH_OVERFLOW = 7,
+    ST_PANIC_CMP_NAN = 8
 };
 
 // Device shape-table entry (32 B, two 128-bit loads).  h = half_dim for a Cuboid

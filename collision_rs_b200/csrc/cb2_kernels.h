@@ -83,6 +83,44 @@ cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W,
 cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, int sm_count,
                             cudaStream_t st);
 
+// ---- composite shapes (cb2_complex.cu) -----------------------------------------------------------
+struct complex_args {
+    // composite table: parts [comp_off[c], comp_off[c+1]) = (comp_shape, comp_local)
+    const uint32_t* comp_off;
+    const uint32_t* comp_shape;
+    const float4* comp_local;
+    // composite pairs
+    const uint32_t* l_comp;
+    const uint32_t* r_comp;
+    const float4* l_t0;
+    const float4* r_t0;
+    const float4* l_t1;  // time of impact only (else nullptr)
+    const float4* r_t1;
+    uint64_t n;
+    // expansion
+    uint64_t* sub_count;  // n
+    uint64_t* sub_off;    // n (exclusive scan of sub_count)
+    uint32_t* sub_l_shape;
+    uint32_t* sub_r_shape;
+    float4* sub_l_t0;
+    float4* sub_r_t0;
+    float4* sub_l_t1;
+    float4* sub_r_t1;
+    // sub-pair results
+    const cb2_contact* sub_contact;
+    const float* sub_distance;
+    const uint8_t* sub_status;
+    // composite results
+    cb2_contact* out_contact;
+    float* out_distance;
+    uint8_t* out_status;
+};
+cudaError_t cx_scan(void* tmp, size_t* tmp_bytes, const uint64_t* in, uint64_t* out, uint64_t n,
+                    cudaStream_t st);
+cudaError_t launch_cx_count(const complex_args& X, cudaStream_t st);
+cudaError_t launch_cx_expand(const complex_args& X, cudaStream_t st);
+cudaError_t launch_cx_reduce(const complex_args& X, uint32_t op, uint32_t strategy, cudaStream_t st);
+
 // ---- support cells (cb2_cells.cu) ---------------------------------------------------------------
 uint32_t cells_resolution(uint32_t vertex_count);
 cudaError_t build_support_cells(const dshape* d_shapes, const float4* d_verts, uint32_t n_shapes,

@@ -30,7 +30,8 @@ class ReferencePanic(RuntimeError):
                  4: "inverse_transform_vector(..).unwrap() (util.rs:18)",
                  5: "time-of-impact loop did not converge (gjk/mod.rs:204 has no cap)",
                  6: "faces[0] on an empty polytope (epa3d.rs:138)",
-                 7: "device EPA scratch overflow"}
+                 7: "device EPA scratch overflow",
+                 8: "max_by(partial_cmp(..).unwrap()) on a NaN depth (gjk/mod.rs:455-459)"}
         super().__init__(names.get(status, f"status {status}"))
         self.status = status
 
@@ -161,6 +162,50 @@ class Context:
         self._ck(self.lib.cb2_world_aabbs_dev(self.h, shape, t, int(n), out, stream))
 
     # ---- broad phase ------------------------------------------------------------------------------
+    # ---- composite shapes: &[(Primitive, local transform)] (gjk/mod.rs:412-588) -----------------
+    def upload_composites(self, part_off, part_shape, part_local):
+        part_off = np.ascontiguousarray(part_off, np.uint32)
+        part_shape = np.ascontiguousarray(part_shape, np.uint32)
+        part_local = np.ascontiguousarray(part_local, XFORM_DT)
+        assert len(part_shape) == len(part_local) == int(part_off[-1])
+        self._ck(self.lib.cb2_composites_upload(self.h, ptr(part_off), ptr(part_shape),
+                                                ptr(part_local), len(part_off) - 1))
+
+    def intersection_complex(self, strategy, l_comp, r_comp, l_t, r_t, settings=None):
+        n = len(l_comp)
+        s = settings or Settings.default()
+        out = np.zeros(n, CONTACT_DT)
+        st = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk3_intersection_complex(
+            self.h, int(strategy), C.byref(s), ptr(np.ascontiguousarray(l_comp, np.uint32)),
+            ptr(np.ascontiguousarray(r_comp, np.uint32)), ptr(np.ascontiguousarray(l_t, XFORM_DT)),
+            ptr(np.ascontiguousarray(r_t, XFORM_DT)), n, ptr(out), ptr(st)))
+        return out, st
+
+    def distance_complex(self, l_comp, r_comp, l_t, r_t, settings=None):
+        n = len(l_comp)
+        s = settings or Settings.default()
+        out = np.zeros(n, np.float32)
+        st = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk3_distance_complex(
+            self.h, C.byref(s), ptr(np.ascontiguousarray(l_comp, np.uint32)),
+            ptr(np.ascontiguousarray(r_comp, np.uint32)), ptr(np.ascontiguousarray(l_t, XFORM_DT)),
+            ptr(np.ascontiguousarray(r_t, XFORM_DT)), n, ptr(out), ptr(st)))
+        return out, st
+
+    def time_of_impact_complex(self, strategy, l_comp, r_comp, l_t0, l_t1, r_t0, r_t1,
+                               settings=None, iter_cap=1024):
+        n = len(l_comp)
+        s = settings or Settings.default()
+        out = np.zeros(n, CONTACT_DT)
+        st = np.zeros(n, np.uint8)
+        a = [np.ascontiguousarray(x, XFORM_DT) for x in (l_t0, l_t1, r_t0, r_t1)]
+        self._ck(self.lib.cb2_gjk3_time_of_impact_complex(
+            self.h, int(strategy), C.byref(s), ptr(np.ascontiguousarray(l_comp, np.uint32)),
+            ptr(np.ascontiguousarray(r_comp, np.uint32)), ptr(a[0]), ptr(a[1]), ptr(a[2]),
+            ptr(a[3]), n, int(iter_cap), ptr(out), ptr(st)))
+        return out, st
+
     def sap3(self, aabbs, axis=0, cap=None):
         """Host-buffer SweepAndPrune3::find_collider_pairs. Returns (perm, pairs, axis_next)."""
         aabbs = np.ascontiguousarray(aabbs, AABB_DT)

@@ -55,9 +55,11 @@ typedef enum cb2_status {
                                    loop (gjk/mod.rs:204) has no cap and would hang */
     CB2_PANIC_EPA_EMPTY = 6,    /* Polytope::closest_face_to_origin indexes
                                    faces[0] of an empty Vec, epa/epa3d.rs:138    */
-    CB2_SCRATCH_OVERFLOW = 7    /* device EPA scratch exhausted (non-manifold horizon
+    CB2_SCRATCH_OVERFLOW = 7,   /* device EPA scratch exhausted (non-manifold horizon
                                    grew the polytope past 2V-4 faces): result NOT
                                    computed — loud, never a silent wrong answer  */
+    CB2_PANIC_CMP_NAN = 8       /* intersection_complex: max_by(partial_cmp(..).unwrap())
+                                   met a NaN penetration depth, gjk/mod.rs:455-459 */
 } cb2_status;
 
 /* ---- CollisionStrategy (contact.rs:16-22); discriminants in declaration order */
@@ -191,6 +193,36 @@ int cb2_gjk3_intersection_bodies_dev(cb2_ctx* ctx, uint32_t strategy,
                                      const uint32_t* pair_body /* 2 x n, interleaved */,
                                      uint64_t n, cb2_contact* out, uint8_t* status,
                                      void* stream);
+
+/* ---- composite shapes ----------------------------------------------------------
+ * A composite is the reference's `&[(Primitive, local transform)]`: parts
+ * [part_off[c], part_off[c+1]) of (part_shape[k] = index into the shape table, part_local[k]).
+ * cb2_composites_upload replaces building those slices; host pointers, copied to the device.
+ *
+ * cb2_gjk3_intersection_complex      replaces GJK3::intersection_complex      (gjk/mod.rs:412-461)
+ * cb2_gjk3_distance_complex          replaces GJK3::distance_complex          (gjk/mod.rs:477-516)
+ * cb2_gjk3_time_of_impact_complex    replaces GJK3::intersection_complex_time_of_impact (:538-588)
+ * l_comp / r_comp index the composite table; l_t / r_t are the model-to-world transforms.  Each
+ * part pair runs as one sub-pair of the ordinary kernels with Transform::concat applied; the
+ * reduction replays the reference's loop order (first hit for CollisionOnly; max depth — last
+ * among equals, Iterator::max_by; min distance; min time of impact — first among equals), incl.
+ * its early returns and panics.  Host buffers.                                                 */
+int cb2_composites_upload(cb2_ctx* ctx, const uint32_t* part_off /* n_comp + 1 */,
+                          const uint32_t* part_shape, const cb2_xform* part_local,
+                          uint32_t n_comp);
+int cb2_gjk3_intersection_complex(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                                  const uint32_t* l_comp, const uint32_t* r_comp,
+                                  const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                                  cb2_contact* out, uint8_t* status);
+int cb2_gjk3_distance_complex(cb2_ctx* ctx, const cb2_settings* settings,
+                              const uint32_t* l_comp, const uint32_t* r_comp,
+                              const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                              float* out, uint8_t* status);
+int cb2_gjk3_time_of_impact_complex(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                                    const uint32_t* l_comp, const uint32_t* r_comp,
+                                    const cb2_xform* l_t0, const cb2_xform* l_t1,
+                                    const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
+                                    uint32_t iter_cap, cb2_contact* out, uint8_t* status);
 
 /* ---- broad phase ---------------------------------------------------------------
  * cb2_sap3_find_collider_pairs replaces SweepAndPrune3::find_collider_pairs

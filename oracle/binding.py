@@ -191,6 +191,22 @@ class Oracle:
             _p(status), _p(iters), int(nthreads))
         return (out, status, iters) if want_iters else (out, status)
 
+    def complex(self, op, strategy, shapes, verts, comp_off, comp_shape, comp_local, l_comp, r_comp,
+                l_t0, r_t0, l_t1=None, r_t1=None, settings=None, iter_cap=1024, nthreads=1):
+        """op 0: intersection_complex, 1: distance_complex, 2: intersection_complex_time_of_impact
+        (gjk/mod.rs:412-588). Returns (contacts | distances, status)."""
+        settings = settings or Settings.default()
+        n = len(l_comp)
+        out_c = np.zeros(n, CONTACT_DT)
+        out_d = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        self.lib.orc_gjk3_complex_batch(
+            C.c_uint32(op), C.c_uint32(strategy), C.byref(settings), _p(shapes), _p(verts),
+            _p(comp_off), _p(comp_shape), _p(comp_local), _p(l_comp), _p(r_comp), _p(l_t0),
+            _p(l_t1 if l_t1 is not None else l_t0), _p(r_t0), _p(r_t1 if r_t1 is not None else r_t0),
+            C.c_uint64(n), C.c_uint32(iter_cap), _p(out_c), _p(out_d), _p(status), int(nthreads))
+        return (out_d if op == 1 else out_c), status
+
     def world_aabbs(self, shapes, verts, shape, t, nthreads=1):
         n = len(shape)
         out = np.zeros(n, AABB_DT)

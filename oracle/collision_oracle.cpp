@@ -143,6 +143,24 @@ static inline Xf translation_interpolate(const Xf& self, const Xf& other, R amou
     return r;
 }
 
+// Quaternion * Quaternion, cgmath 0.18 quaternion.rs (restated; left-to-right evaluation)
+static inline Quat quat_mul(const Quat& a, const Quat& b) {
+    Quat r;
+    r.s = a.s * b.s - a.v.x * b.v.x - a.v.y * b.v.y - a.v.z * b.v.z;
+    r.v.x = a.s * b.v.x + a.v.x * b.s + a.v.y * b.v.z - a.v.z * b.v.y;
+    r.v.y = a.s * b.v.y + a.v.y * b.s + a.v.z * b.v.x - a.v.x * b.v.z;
+    r.v.z = a.s * b.v.z + a.v.z * b.s + a.v.x * b.v.y - a.v.y * b.v.x;
+    return r;
+}
+// Transform::concat for Decomposed (cgmath 0.18 transform.rs): self then-applied-after other
+static inline Xf concat(const Xf& self, const Xf& other) {
+    Xf r;
+    r.scale = self.scale * other.scale;
+    r.rot = quat_mul(self.rot, other.rot);
+    r.disp = rotate(self.rot, other.disp * self.scale) + self.disp;
+    return r;
+}
+
 struct Panic {
     uint8_t status;
 };
@@ -672,6 +690,116 @@ static inline int partial_cmp(float a, float b) {
     if (a == b) return 0;
     return 2;
 }
+// ---- composite shapes: gjk/mod.rs:412-588 ------------------------------------------------------
+struct Composite {  // &[(Primitive, local transform)]
+    const uint32_t* shape;
+    const cb2_xform* local;
+    uint32_t n;
+};
+#define CB2_PANIC_CMP_NAN 8  // max_by(partial_cmp(..).unwrap()) on a NaN depth, gjk/mod.rs:455-459
+
+// GJK::intersection_complex, :412-461
+static uint8_t gjk_intersection_complex(uint32_t strategy, const cb2_settings& st,
+                                        const cb2_shape* shapes, const float* verts_xyz,
+                                        const Composite& L, const Xf& lt, const Composite& Rc,
+                                        const Xf& rt, cb2_contact* out) {
+    contact_zero(out, strategy);
+    bool have = false;
+    cb2_contact best;
+    for (uint32_t a = 0; a < L.n; ++a) {
+        const Xf left_transform = concat(lt, load_xf(L.local[a]));
+        for (uint32_t b = 0; b < Rc.n; ++b) {
+            const Xf right_transform = concat(rt, load_xf(Rc.local[b]));
+            cb2_contact c;
+            const uint8_t s = gjk_intersection(strategy, st, load_shape(shapes[L.shape[a]], verts_xyz),
+                                               left_transform, load_shape(shapes[Rc.shape[b]], verts_xyz),
+                                               right_transform, &c, nullptr, nullptr);
+            if (s == CB2_NONE) continue;
+            if (s != CB2_SOME) return s;  // the reference panics right here
+            if (strategy == CB2_COLLISION_ONLY) {
+                *out = c;
+                return CB2_SOME;
+            }
+            if (!have) {
+                best = c;
+                have = true;
+            } else {
+                // Iterator::max_by: compare(best, c) == Greater keeps best, otherwise takes c
+                const int o = partial_cmp(best.penetration_depth, c.penetration_depth);
+                if (o == 2) return CB2_PANIC_CMP_NAN;
+                if (o != 1) best = c;
+            }
+        }
+    }
+    if (!have) return CB2_NONE;
+    *out = best;
+    return CB2_SOME;
+}
+
+// GJK::distance_complex, :477-516
+static uint8_t gjk_distance_complex(const cb2_settings& st, const cb2_shape* shapes,
+                                    const float* verts_xyz, const Composite& L, const Xf& lt,
+                                    const Composite& Rc, const Xf& rt, float* out) {
+    *out = 0.0f;
+    bool have = false;
+    float m = 0.0f;
+    for (uint32_t a = 0; a < L.n; ++a) {
+        const Xf left_transform = concat(lt, load_xf(L.local[a]));
+        for (uint32_t b = 0; b < Rc.n; ++b) {
+            const Xf right_transform = concat(rt, load_xf(Rc.local[b]));
+            float d;
+            const uint8_t s = gjk_distance(st, load_shape(shapes[L.shape[a]], verts_xyz), left_transform,
+                                           load_shape(shapes[Rc.shape[b]], verts_xyz), right_transform,
+                                           &d, nullptr);
+            if (s != CB2_SOME) return s;  // None => return None (colliding); panic => panic
+            m = have ? std::fmin(d, m) : d;  // f32::min: a NaN operand yields the other one
+            have = true;
+        }
+    }
+    if (!have) return CB2_NONE;
+    *out = m;
+    return CB2_SOME;
+}
+
+// GJK::intersection_complex_time_of_impact, :538-588
+static uint8_t gjk_toi_complex(uint32_t strategy, const cb2_settings& st, const cb2_shape* shapes,
+                               const float* verts_xyz, const Composite& L, const Xf& lt0,
+                               const Xf& lt1, const Composite& Rc, const Xf& rt0, const Xf& rt1,
+                               uint32_t iter_cap, cb2_contact* out) {
+    contact_zero(out, strategy);
+    bool have = false;
+    cb2_contact best;
+    for (uint32_t a = 0; a < L.n; ++a) {
+        const Xf l0 = concat(lt0, load_xf(L.local[a]));
+        const Xf l1 = concat(lt1, load_xf(L.local[a]));
+        for (uint32_t b = 0; b < Rc.n; ++b) {
+            const Xf r0 = concat(rt0, load_xf(Rc.local[b]));
+            const Xf r1 = concat(rt1, load_xf(Rc.local[b]));
+            cb2_contact c;
+            const uint8_t s = gjk_toi(st, load_shape(shapes[L.shape[a]], verts_xyz), l0, l1,
+                                      load_shape(shapes[Rc.shape[b]], verts_xyz), r0, r1, iter_cap, &c,
+                                      nullptr);
+            if (s == CB2_NONE) continue;
+            if (s != CB2_SOME) return s;
+            if (strategy == CB2_COLLISION_ONLY) {
+                c.strategy = CB2_COLLISION_ONLY;
+                *out = c;
+                return CB2_SOME;
+            }
+            if (!have) {
+                best = c;
+                have = true;
+            } else {
+                // Iterator::min_by with unwrap_or(Equal): only Greater replaces the current best
+                if (partial_cmp(best.time_of_impact, c.time_of_impact) == 1) best = c;
+            }
+        }
+    }
+    if (!have) return CB2_NONE;
+    *out = best;
+    return CB2_SOME;
+}
+
 static int sap_cmp(const float* a, const float* b, uint32_t axis) {  // :87-97, returns Ordering
     int c = partial_cmp(a[axis], b[axis]);
     if (c == 0) {
@@ -938,6 +1066,36 @@ void orc_gjk3_toi_batch(const cb2_settings* st, const cb2_shape* shapes, const f
                                 load_xf(l_t1[i]), load_shape(shapes[r_shape[i]], verts_xyz),
                                 load_xf(r_t0[i]), load_xf(r_t1[i]), iter_cap, &out[i], &it);
             if (iters) iters[i] = it;
+        }
+    });
+}
+// composite batch entry points: comp_off[n_comp+1] indexes comp_shape / comp_local
+void orc_gjk3_complex_batch(uint32_t op, uint32_t strategy, const cb2_settings* st,
+                            const cb2_shape* shapes, const float* verts_xyz,
+                            const uint32_t* comp_off, const uint32_t* comp_shape,
+                            const cb2_xform* comp_local, const uint32_t* l_comp,
+                            const uint32_t* r_comp, const cb2_xform* l_t0, const cb2_xform* l_t1,
+                            const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
+                            uint32_t iter_cap, cb2_contact* out_c, float* out_d, uint8_t* status,
+                            int nthreads) {
+    if (iter_cap == 0) iter_cap = 1024;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            const uint32_t lc = l_comp[i], rc = r_comp[i];
+            const Composite L = {comp_shape + comp_off[lc], comp_local + comp_off[lc],
+                                 comp_off[lc + 1] - comp_off[lc]};
+            const Composite Rc = {comp_shape + comp_off[rc], comp_local + comp_off[rc],
+                                  comp_off[rc + 1] - comp_off[rc]};
+            if (op == 0)
+                status[i] = gjk_intersection_complex(strategy, *st, shapes, verts_xyz, L, load_xf(l_t0[i]),
+                                                     Rc, load_xf(r_t0[i]), &out_c[i]);
+            else if (op == 1)
+                status[i] = gjk_distance_complex(*st, shapes, verts_xyz, L, load_xf(l_t0[i]), Rc,
+                                                 load_xf(r_t0[i]), &out_d[i]);
+            else
+                status[i] = gjk_toi_complex(strategy, *st, shapes, verts_xyz, L, load_xf(l_t0[i]),
+                                            load_xf(l_t1[i]), Rc, load_xf(r_t0[i]), load_xf(r_t1[i]),
+                                            iter_cap, &out_c[i]);
         }
     });
 }

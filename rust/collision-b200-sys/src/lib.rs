@@ -27,6 +27,7 @@ pub const CB2_PANIC_INV_SCALE: u8 = 4;
 pub const CB2_NONCONVERGED: u8 = 5;
 pub const CB2_PANIC_EPA_EMPTY: u8 = 6;
 pub const CB2_SCRATCH_OVERFLOW: u8 = 7;
+pub const CB2_PANIC_CMP_NAN: u8 = 8;
 
 // cb2_strategy: contact.rs:16-22 discriminants in declaration order
 pub const CB2_FULL_RESOLUTION: u32 = 0;
@@ -140,6 +141,22 @@ extern "C" {
                                             pair_body: *const u32, n: u64,
                                             out: *mut cb2_contact, status: *mut u8,
                                             stream: *mut c_void) -> c_int;
+
+    pub fn cb2_composites_upload(ctx: *mut cb2_ctx, part_off: *const u32, part_shape: *const u32,
+                                 part_local: *const cb2_xform, n_comp: u32) -> c_int;
+    pub fn cb2_gjk3_intersection_complex(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                         l_comp: *const u32, r_comp: *const u32,
+                                         l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                         out: *mut cb2_contact, status: *mut u8) -> c_int;
+    pub fn cb2_gjk3_distance_complex(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                     l_comp: *const u32, r_comp: *const u32,
+                                     l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                     out: *mut f32, status: *mut u8) -> c_int;
+    pub fn cb2_gjk3_time_of_impact_complex(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                           l_comp: *const u32, r_comp: *const u32,
+                                           l_t0: *const cb2_xform, l_t1: *const cb2_xform,
+                                           r_t0: *const cb2_xform, r_t1: *const cb2_xform, n: u64,
+                                           iter_cap: u32, out: *mut cb2_contact, status: *mut u8) -> c_int;
 
     pub fn cb2_sap3_find_collider_pairs(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
                                         axis_inout: *mut u32, perm_out: *mut u32,

@@ -489,3 +489,50 @@ def test_grid_sap_matches_tiled_sweep_on_a_million_boxes(ctx):
                 del os.environ["CB2_SAP_LEGACY"]
             assert np.array_equal(perm, perm_e) and ax == ax_e
             assert pairs.shape == pairs_e.shape and np.array_equal(pairs, pairs_e)
+
+
+# ---- composite shapes: *_complex (gjk/mod.rs:412-588) ----------------------------------------------
+def test_complex_callers_match_the_oracle(ctx, oracle):
+    from helpers_complex import composite_workload
+    cw = composite_workload(20_000, seed=11)
+    ctx.upload_shapes(cw["shapes"], cw["verts"])
+    ctx.upload_composites(cw["comp_off"], cw["comp_shape"], cw["comp_local"])
+    oargs = (cw["shapes"], cw["verts"], cw["comp_off"], cw["comp_shape"], cw["comp_local"],
+             cw["l_comp"], cw["r_comp"], cw["l_t0"], cw["r_t0"], cw["l_t1"], cw["r_t1"])
+    for strategy in (0, 1):
+        exp, est = oracle.complex(0, strategy, *oargs, nthreads=8)
+        got, gst = ctx.intersection_complex(strategy, cw["l_comp"], cw["r_comp"], cw["l_t0"], cw["r_t0"])
+        assert_contacts_equal(got, gst, exp, est, f"intersection_complex strategy {strategy}")
+        assert (est == 1).sum() > 1000
+        exp, est = oracle.complex(2, strategy, *oargs, nthreads=8)
+        got, gst = ctx.time_of_impact_complex(strategy, cw["l_comp"], cw["r_comp"], cw["l_t0"],
+                                              cw["l_t1"], cw["r_t0"], cw["r_t1"])
+        assert_contacts_equal(got, gst, exp, est, f"toi_complex strategy {strategy}")
+        assert (est == 1).sum() > 1000
+    ed, est = oracle.complex(1, 0, *oargs, nthreads=8)
+    gd, gst = ctx.distance_complex(cw["l_comp"], cw["r_comp"], cw["l_t0"], cw["r_t0"])
+    assert np.array_equal(gst, est)
+    assert bits_equal(gd[est == 1], ed[est == 1]).all() and (est == 1).sum() > 500
+
+
+def test_complex_empty_composites_and_errors(ctx, oracle):
+    shapes = W.cuboid_shapes(np.random.default_rng(0), 3)
+    ctx.upload_shapes(shapes)
+    ident = np.zeros(3, host_abi.XFORM_DT)
+    ident["scale"] = 1
+    ident["q"][:, 0] = 1
+    # composite 0 is empty, composite 1 has one part, composite 2 has two
+    ctx.upload_composites(np.array([0, 0, 1, 3], np.uint32), np.array([0, 1, 2], np.uint32), ident)
+    t = ident[:3].copy()
+    l = np.array([0, 1, 0], np.uint32)
+    r = np.array([1, 2, 0], np.uint32)
+    out, st = ctx.intersection_complex(0, l, r, t, t)
+    assert list(st) == [0, 1, 0]            # an empty side yields None; coincident cuboids collide
+    d, st = ctx.distance_complex(l, r, t, t)
+    # empty -> None; two coincident cuboids: whatever the reference does (it panics in
+    # get_closest_point_on_face), the oracle says
+    _, est = oracle.complex(1, 0, shapes, None, np.array([0, 0, 1, 3], np.uint32),
+                            np.array([0, 1, 2], np.uint32), ident, l, r, t, t)
+    assert st[0] == 0 and st[2] == 0 and np.array_equal(st, est)
+    with pytest.raises(Cb2Error):
+        ctx.intersection_complex(0, np.array([7], np.uint32), np.array([0], np.uint32), t[:1], t[:1])
