@@ -21,7 +21,7 @@ AABB_DT = np.dtype([("min", "<f4", (3,)), ("max", "<f4", (3,))])
 assert SHAPE_DT.itemsize == 24 and XFORM_DT.itemsize == 32
 assert CONTACT_DT.itemsize == 36 and AABB_DT.itemsize == 24
 
-SPHERE, CUBOID, POLYHEDRON = 0, 1, 2
+SPHERE, CUBOID, POLYHEDRON, PARTICLE, QUAD, CYLINDER, CAPSULE, CUBE = 0, 1, 2, 3, 4, 5, 6, 7
 FULL_RESOLUTION, COLLISION_ONLY = 0, 1
 (NONE, SOME, PANIC_UNWRAP_PLANE, PANIC_ASSERT_RANGE, PANIC_INV_SCALE, NONCONVERGED,
  PANIC_EPA_EMPTY) = range(7)

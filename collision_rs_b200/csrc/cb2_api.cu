@@ -233,6 +233,17 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
             d.hx = s.p[0] / 2.0f;
             d.hy = s.p[1] / 2.0f;
             d.hz = s.p[2] / 2.0f;
+        } else if (s.kind == CB2_CUBE) {  // Cuboid::new(dim, dim, dim), cuboid.rs:151-157
+            d.kind = CB2_CUBOID;
+            d.hx = d.hy = d.hz = s.p[0] / 2.0f;
+        } else if (s.kind == CB2_QUAD) {  // half_dim = dim / 2, quad.rs:36-42
+            d.hx = s.p[0] / 2.0f;
+            d.hy = s.p[1] / 2.0f;
+        } else if (s.kind == CB2_CYLINDER || s.kind == CB2_CAPSULE) {
+            d.hx = s.p[0];  // half_height
+            d.hy = s.p[1];  // radius
+        } else if (s.kind == CB2_PARTICLE) {
+            // no parameters
         } else if (s.kind == CB2_POLYHEDRON) {
             if ((uint64_t)s.vtx_off + s.vtx_cnt > n_verts)
                 return fail(c, CB2_ERR_ARG, "polyhedron vertex range outside the vertex table");

@@ -13,7 +13,9 @@
 
 namespace cb2 {
 
-enum : uint32_t { K_SPHERE = 0, K_CUBOID = 1, K_POLY = 2 };
+enum : uint32_t {
+    K_SPHERE = 0, K_CUBOID = 1, K_POLY = 2, K_PARTICLE = 3, K_QUAD = 4, K_CYLINDER = 5, K_CAPSULE = 6
+};  // a Cube is uploaded as a Cuboid
 enum : uint8_t {
     ST_NONE = 0,
     ST_SOME = 1,
@@ -27,8 +29,9 @@ enum : uint8_t {
 };
 
 // Device shape-table entry (32 B, two 128-bit loads).  h = half_dim for a Cuboid
-// (dim / 2, cuboid.rs:36 — exact), h.x = radius for a Sphere, h.x = max |vertex| (rounded up)
-// for a ConvexPolyhedron.  cell_off / cell_cfg locate the polyhedron's support cells
+// (dim / 2, cuboid.rs:36 — exact) and (x, y) of a Quad, h.x = radius for a Sphere, (h.x, h.y) =
+// (half_height, radius) for a Cylinder / Capsule, h.x = max |vertex| (rounded up) for a
+// ConvexPolyhedron.  cell_off / cell_cfg locate the polyhedron's support cells
 // (cb2_cells.cuh): cell_cfg = N | wide << 8.
 struct __align__(16) dshape {
     uint32_t kind;
@@ -96,16 +99,64 @@ CB2_DI f3 cuboid_local_support(f3 h, f3 d) {
 }
 // Sphere: sphere.rs:32-38
 CB2_DI f3 sphere_local_support(float r, f3 d) { return normalize_to(d, r); }
-// ConvexPolyhedron VertexOnly: polyhedron.rs:160-176 through the support cells (cb2_cells.cuh)
+// Quad: quad.rs:46-57,65-77 — get_max_point over (+,+,0) (-,+,0) (-,-,0) (+,-,0).  With
+// px = hx*dx, py = hy*dy, z = 0*dz the four dots ((cx*dx) + (cy*dy)) + 0*dz are
+//   (px+py)+z   (py-px)+z   -(px+py)+z   -(py-px)+z      bit for bit.
+CB2_DI f3 quad_local_support(f3 h, f3 d) {
+    const float px = fmul(h.x, d.x), py = fmul(h.y, d.y), z = fmul(0.0f, d.z);
+    const float a = fadd(px, py), b = fsub(py, px);
+    const float d0 = fadd(a, z), d1 = fadd(b, z), d2 = fadd(-a, z), d3 = fadd(-b, z);
+    float best = -INFINITY;
+    int idx = -1;
+    if (d0 > best) { best = d0; idx = 0; }
+    if (d1 > best) { best = d1; idx = 1; }
+    if (d2 > best) { best = d2; idx = 2; }
+    if (d3 > best) { best = d3; idx = 3; }
+    if (idx < 0) return zero3();
+    const bool nx = idx == 1 || idx == 2, ny = idx >= 2;
+    return mk3(nx ? -h.x : h.x, ny ? -h.y : h.y, 0.0f);
+}
+// Cylinder (axis y; h.x = half_height, h.y = radius): cylinder.rs:45-78
+CB2_DI f3 cylinder_local_support(f3 h, f3 d) {
+    const bool negative = (__float_as_uint(d.y) >> 31) != 0u;  // is_sign_negative
+    f3 r = mk3(d.x, 0.0f, d.z);
+    if (magnitude2(r) == 0.0f) {
+        r = zero3();
+    } else {
+        r = normalize(r);
+        if (r.x == 0.0f && r.y == 0.0f && r.z == 0.0f) r = zero3();
+        else r = r * h.y;
+    }
+    r.y = negative ? -h.x : h.x;
+    return r;
+}
+// Capsule (axis y; h.x = half_height, h.y = radius): capsule.rs:45-61
+CB2_DI f3 capsule_local_support(f3 h, f3 d) {
+    // f32::signum: 1 for +0 and positive, -1 for -0 and negative, NaN for NaN
+    const float sg = (d.y != d.y) ? d.y : ((__float_as_uint(d.y) >> 31) ? -1.0f : 1.0f);
+    const f3 p = mk3(0.0f, fmul(sg, h.x), 0.0f);
+    return p + normalize_to(d, h.y);
+}
+
+// Primitive3 dispatch (primitive3.rs:153-176); ConvexPolyhedron VertexOnly (polyhedron.rs:160-176)
+// goes through the support cells (cb2_cells.cuh)
 CB2_DI f3 local_support(const shape& s, f3 d) {
     if (s.kind == K_CUBOID) return cuboid_local_support(s.h, d);
     if (s.kind == K_SPHERE) return sphere_local_support(s.h.x, d);
-    return poly_local_support(s.poly, d);
+    if (s.kind == K_POLY) return poly_local_support(s.poly, d);
+    if (s.kind == K_QUAD) return quad_local_support(s.h, d);
+    if (s.kind == K_CYLINDER) return cylinder_local_support(s.h, d);
+    return capsule_local_support(s.h, d);
 }
 
 CB2_DI f3 support_point(const shape& s, const xform& t, f3 dir) {
+    // Particle: transform.transform_point(origin) — no inverse transform (primitive3.rs:164)
+    if (s.kind == K_PARTICLE) return transform_point(t, zero3());
     return transform_point(t, local_support(s, inverse_transform_vector(t, dir)));
 }
+// does support_point call inverse_transform_vector(..).unwrap() (the zero-scale panic site)?
+CB2_DI bool needs_inverse(uint32_t kind) { return kind != K_PARTICLE; }
+CB2_DI bool is_curved(uint32_t kind) { return kind == K_SPHERE || kind == K_CYLINDER || kind == K_CAPSULE; }
 
 // ---- simplex in registers -----------------------------------------------------------------
 // v[i] = SupportPoint.v, a[i] = SupportPoint.sup_a (only kept when the EPA contact needs it;

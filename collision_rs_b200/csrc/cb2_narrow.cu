@@ -243,7 +243,8 @@ CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const 
     p.rt = load_xform(rt, rx);
     // inverse_transform_vector(..).unwrap() panics when ulps_eq(scale, 0); every entry point
     // reaches a support call before anything else can return (util.rs:18, sphere.rs:36)
-    return !(ulps_eq_zero(p.lt.scale) || ulps_eq_zero(p.rt.scale));
+    return !((needs_inverse(p.ls.kind) && ulps_eq_zero(p.lt.scale)) ||
+             (needs_inverse(p.rs.kind) && ulps_eq_zero(p.rt.scale)));
 }
 
 // ---- kernels -----------------------------------------------------------------------------------
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(128) k_gjk_hits(narrow_args A, narrow_ws W) {
                 st = ST_SOME;
                 if constexpr (FULL) {
                     hit = true;
-                    curved = p.ls.kind == K_SPHERE || p.rs.kind == K_SPHERE;
+                    curved = is_curved(p.ls.kind) || is_curved(p.rs.kind);
                     float4* o = W.simplex + i * 8;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -503,13 +504,25 @@ __global__ void __launch_bounds__(256) k_world_aabbs(aabb_args A) {
     const shape s = load_shape(table_of(A.T), __ldg(A.shape + i));
     const xform t = load_xform(A.t, i);
     f3 mn, mx;
+    // Aabb3::new(p1, p2) orders each component with the reference's min/max (aabb/mod.rs:21-33)
+    auto ordered = [&](f3 a, f3 b) {
+        mn = mk3(rmin(a.x, b.x), rmin(a.y, b.y), rmin(a.z, b.z));
+        mx = mk3(rmax(a.x, b.x), rmax(a.y, b.y), rmax(a.z, b.z));
+    };
     if (s.kind == K_SPHERE) {
         const float r = s.h.x;
-        mn = mk3(rmin(-r, r), rmin(-r, r), rmin(-r, r));
-        mx = mk3(rmax(-r, r), rmax(-r, r), rmax(-r, r));
+        ordered(mk3(-r, -r, -r), mk3(r, r, r));
     } else if (s.kind == K_CUBOID) {
-        mn = mk3(rmin(-s.h.x, s.h.x), rmin(-s.h.y, s.h.y), rmin(-s.h.z, s.h.z));
-        mx = mk3(rmax(-s.h.x, s.h.x), rmax(-s.h.y, s.h.y), rmax(-s.h.z, s.h.z));
+        ordered(-s.h, s.h);
+    } else if (s.kind == K_PARTICLE) {  // Aabb3::zero(), primitive3.rs:120
+        mn = zero3();
+        mx = zero3();
+    } else if (s.kind == K_QUAD) {  // quad.rs:80-90
+        ordered(mk3(-s.h.x, -s.h.y, 0.0f), mk3(s.h.x, s.h.y, 0.0f));
+    } else if (s.kind == K_CYLINDER) {  // cylinder.rs:81-91
+        ordered(mk3(-s.h.y, -s.h.x, -s.h.y), mk3(s.h.y, s.h.x, s.h.y));
+    } else if (s.kind == K_CAPSULE) {  // capsule.rs:64-74
+        ordered(mk3(-s.h.y, fsub(-s.h.x, s.h.y), -s.h.y), mk3(s.h.y, fadd(s.h.x, s.h.y), s.h.y));
     } else {
         mn = zero3();
         mx = zero3();

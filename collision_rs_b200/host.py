@@ -11,8 +11,9 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import abi
-from .abi import (AABB_DT, COLLISION_ONLY, CONTACT_DT, CUBOID, FULL_RESOLUTION, POLYHEDRON,
-                  SHAPE_DT, SPHERE, XFORM_DT, Settings, ptr)
+from .abi import (AABB_DT, CAPSULE, COLLISION_ONLY, CONTACT_DT, CUBE, CUBOID, CYLINDER,
+                  FULL_RESOLUTION, PARTICLE, POLYHEDRON, QUAD, SHAPE_DT, SPHERE, XFORM_DT, Settings,
+                  ptr)
 
 
 class Cb2Error(RuntimeError):
@@ -272,6 +273,38 @@ class Cuboid:
     z: float
 
 
+@dataclass
+class Cube:
+    """primitive/cuboid.rs:144-158: Cuboid::new(dim, dim, dim)"""
+    dim: float
+
+
+@dataclass
+class Quad:
+    """primitive/quad.rs:24-57: rectangle in the z = 0 plane (dim = full extents)"""
+    x: float
+    y: float
+
+
+@dataclass
+class Cylinder:
+    """primitive/cylinder.rs:21-36 (axis y)"""
+    half_height: float
+    radius: float
+
+
+@dataclass
+class Capsule:
+    """primitive/capsule.rs:22-37 (axis y)"""
+    half_height: float
+    radius: float
+
+
+@dataclass
+class Particle3:
+    """primitive/particle.rs: a point; Primitive3::Particle (primitive3.rs:24-25)"""
+
+
 class ConvexPolyhedron:
     """primitive/polyhedron.rs:100-122, VertexOnly mode (ConvexPolyhedron::new)."""
 
@@ -305,6 +338,20 @@ def _shape_table(prims):
         elif isinstance(p, Cuboid):
             shapes[i]["kind"] = CUBOID
             shapes[i]["p"] = (p.x, p.y, p.z)
+        elif isinstance(p, Cube):
+            shapes[i]["kind"] = CUBE
+            shapes[i]["p"] = (p.dim, 0, 0)
+        elif isinstance(p, Quad):
+            shapes[i]["kind"] = QUAD
+            shapes[i]["p"] = (p.x, p.y, 0)
+        elif isinstance(p, Cylinder):
+            shapes[i]["kind"] = CYLINDER
+            shapes[i]["p"] = (p.half_height, p.radius, 0)
+        elif isinstance(p, Capsule):
+            shapes[i]["kind"] = CAPSULE
+            shapes[i]["p"] = (p.half_height, p.radius, 0)
+        elif isinstance(p, Particle3):
+            shapes[i]["kind"] = PARTICLE
         elif isinstance(p, ConvexPolyhedron):
             shapes[i]["kind"] = POLYHEDRON
             shapes[i]["vtx_off"] = off

@@ -123,3 +123,14 @@ def cfg5_toi_pairs(n=1_000_000, seed=99, shard=0):
     r1["d"] = r0["d"] + rng.uniform(-1, 1, (n, 3)).astype(np.float32)
     return dict(shapes=shapes, verts=None, l_shape=l_shape, r_shape=r_shape,
                 l_t0=l0, l_t1=l1, r_t0=r0, r_t1=r1)
+
+
+def all_primitive3_shapes(rng, n):
+    """Every Primitive3 variant but the polyhedron: Sphere, Cuboid, Particle, Quad, Cylinder,
+    Capsule, Cube in equal shares (kinds 0,1,3..7 of include/collision_b200.h)."""
+    s = np.zeros(n, SHAPE_DT)
+    kinds = np.array([0, 1, 3, 4, 5, 6, 7], np.uint32)
+    s["kind"] = kinds[rng.integers(0, len(kinds), n)]
+    a = rng.uniform(0.4, 1.6, (n, 3)).astype(np.float32)
+    s["p"] = a
+    return s

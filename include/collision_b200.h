@@ -6,7 +6,8 @@
  * reference has no FFI of its own (it is safe, generic Rust); each entry point
  * below replaces one generic method specialised to
  *     S = f32, P = Point3<f32>, T = Decomposed<Vector3<f32>, Quaternion<f32>>,
- *     shapes in {Sphere, Cuboid, ConvexPolyhedron(VertexOnly)} (a subset of Primitive3<f32>)
+ *     shapes = Primitive3<f32>: Particle, Quad, Sphere, Cuboid, Cube, Cylinder, Capsule,
+ *     ConvexPolyhedron (VertexOnly mode)
  * and batched (one record per pair instead of one call per pair).
  * Citations are relative to the reference tree (src/...).
  *
@@ -68,12 +69,17 @@ typedef enum cb2_strategy {
     CB2_COLLISION_ONLY = 1
 } cb2_strategy;
 
-/* ---- shape kinds: the Primitive3 variants on the path (primitive3.rs:20-40) */
+/* ---- shape kinds: every Primitive3 variant (primitive3.rs:20-40) --------------- */
 typedef enum cb2_shape_kind {
     CB2_SPHERE = 0,     /* p[0] = radius                        (sphere.rs:14-24)   */
     CB2_CUBOID = 1,     /* p[0..3] = dim (full extents)         (cuboid.rs:18-42)   */
-    CB2_POLYHEDRON = 2  /* vertices [vtx_off, vtx_off+vtx_cnt), VertexOnly mode
+    CB2_POLYHEDRON = 2, /* vertices [vtx_off, vtx_off+vtx_cnt), VertexOnly mode
                            (polyhedron.rs:100-122)                                   */
+    CB2_PARTICLE = 3,   /* Particle3: no parameters             (primitive3.rs:164) */
+    CB2_QUAD = 4,       /* p[0..2] = dim x, y (in the z = 0 plane)  (quad.rs:24-57)  */
+    CB2_CYLINDER = 5,   /* p[0] = half_height, p[1] = radius (axis y) (cylinder.rs:21-36) */
+    CB2_CAPSULE = 6,    /* p[0] = half_height, p[1] = radius (axis y) (capsule.rs:22-37)  */
+    CB2_CUBE = 7        /* p[0] = dim: Cuboid::new(dim, dim, dim)   (cuboid.rs:144-158)  */
 } cb2_shape_kind;
 
 /* One entry of the shape table (24 B). */

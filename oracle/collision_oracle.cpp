@@ -195,22 +195,62 @@ static void cuboid_corners(const Shape& s, V3 c[8]) {
     c[7] = V3(h.x, -h.y, -h.z);
 }
 
-// Primitive::support_point for the three shapes:
-//   Cuboid  -> util.rs:11-30 get_max_point over the 8 cached corners
-//   Sphere  -> sphere.rs:32-38
+// Primitive::support_point, Primitive3 dispatch (primitive3.rs:153-176):
+//   Particle -> transform_point(origin)                         (primitive3.rs:164)
+//   Cuboid / Cube -> util.rs:11-30 get_max_point over the 8 cached corners (cuboid.rs:74-79,170-182)
+//   Quad     -> get_max_point over 4 corners in the z = 0 plane  (quad.rs:46-57, 65-77)
+//   Sphere   -> sphere.rs:32-38
+//   Cylinder -> cylinder.rs:45-78;  Capsule -> capsule.rs:45-61
 //   ConvexPolyhedron (VertexOnly) -> polyhedron.rs:160-176, 388-400
+static inline R signum(R x) {  // f32::signum: 1 for +0 and positive, -1 for -0 and negative, NaN
+    if (x.f != x.f) return x;
+    return R(std::signbit(x.f) ? -1.0f : 1.0f);
+}
 static V3 support_point(const Shape& s, V3 direction, const Xf& t) {
+    if (s.kind == CB2_PARTICLE) return transform_point(t, zero3());
     V3 d;
     if (!inverse_transform_vector(t, direction, &d)) throw Panic{CB2_PANIC_INV_SCALE};
     if (s.kind == CB2_SPHERE) {
         return transform_point(t, normalize_to(d, s.p.x));
     }
+    if (s.kind == CB2_CAPSULE) {  // p.x = half_height, p.y = radius
+        V3 result = zero3();
+        result.y = signum(d.y) * s.p.x;
+        return transform_point(t, result + normalize_to(d, s.p.y));
+    }
+    if (s.kind == CB2_CYLINDER) {
+        V3 result = d;
+        const bool negative = std::signbit(result.y.f);  // is_sign_negative
+        result.y = R(0.0f);
+        if (magnitude2(result).f == 0.0f) {
+            result = zero3();
+        } else {
+            result = normalize(result);
+            if (result.x.f == 0.0f && result.y.f == 0.0f && result.z.f == 0.0f) result = zero3();
+            else result = result * s.p.y;
+        }
+        result.y = negative ? -s.p.x : s.p.x;
+        return transform_point(t, result);
+    }
     V3 best = zero3();  // P::origin()
     R best_dot = R(-std::numeric_limits<float>::infinity());
-    if (s.kind == CB2_CUBOID) {
+    if (s.kind == CB2_CUBOID || s.kind == CB2_CUBE) {
+        Shape cs = s;
+        if (s.kind == CB2_CUBE) cs.p = V3(s.p.x, s.p.x, s.p.x);
         V3 c[8];
-        cuboid_corners(s, c);
+        cuboid_corners(cs, c);
         for (int i = 0; i < 8; ++i) {
+            R dt = dot(c[i], d);
+            if (dt > best_dot) {
+                best = c[i];
+                best_dot = dt;
+            }
+        }
+    } else if (s.kind == CB2_QUAD) {
+        const R hx = s.p.x / (R(1.0f) + R(1.0f)), hy = s.p.y / (R(1.0f) + R(1.0f));
+        const V3 c[4] = {V3(hx, hy, R(0.0f)), V3(-hx, hy, R(0.0f)), V3(-hx, -hy, R(0.0f)),
+                         V3(hx, -hy, R(0.0f))};
+        for (int i = 0; i < 4; ++i) {
             R dt = dot(c[i], d);
             if (dt > best_dot) {
                 best = c[i];
@@ -252,9 +292,23 @@ static Aabb compute_bound(const Shape& s) {
         R r = s.p.x;
         return aabb_new(V3(-r, -r, -r), V3(r, r, r));
     }
-    if (s.kind == CB2_CUBOID) {  // cuboid.rs:82-92
-        V3 h = s.p / (R(1.0f) + R(1.0f));
+    if (s.kind == CB2_CUBOID || s.kind == CB2_CUBE) {  // cuboid.rs:82-92, 184-191
+        V3 dim = s.kind == CB2_CUBE ? V3(s.p.x, s.p.x, s.p.x) : s.p;
+        V3 h = dim / (R(1.0f) + R(1.0f));
         return aabb_new(-h, h);
+    }
+    if (s.kind == CB2_PARTICLE) return aabb_new(zero3(), zero3());  // Aabb3::zero(), primitive3.rs:120
+    if (s.kind == CB2_QUAD) {  // quad.rs:80-90
+        const R hx = s.p.x / (R(1.0f) + R(1.0f)), hy = s.p.y / (R(1.0f) + R(1.0f));
+        return aabb_new(V3(-hx, -hy, R(0.0f)), V3(hx, hy, R(0.0f)));
+    }
+    if (s.kind == CB2_CYLINDER) {  // cylinder.rs:81-91
+        const R hh = s.p.x, r = s.p.y;
+        return aabb_new(V3(-r, -hh, -r), V3(r, hh, r));
+    }
+    if (s.kind == CB2_CAPSULE) {  // capsule.rs:64-74
+        const R hh = s.p.x, r = s.p.y;
+        return aabb_new(V3(-r, -hh - r, -r), V3(r, hh + r, r));
     }
     // polyhedron.rs:113-115: fold(Aabb3::zero(), grow) — always contains the origin
     Aabb b = aabb_new(zero3(), zero3());

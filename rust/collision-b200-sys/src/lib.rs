@@ -37,6 +37,11 @@ pub const CB2_COLLISION_ONLY: u32 = 1;
 pub const CB2_SPHERE: u32 = 0;
 pub const CB2_CUBOID: u32 = 1;
 pub const CB2_POLYHEDRON: u32 = 2;
+pub const CB2_PARTICLE: u32 = 3;
+pub const CB2_QUAD: u32 = 4;      // p = [dim.x, dim.y, _]
+pub const CB2_CYLINDER: u32 = 5;  // p = [half_height, radius, _]
+pub const CB2_CAPSULE: u32 = 6;   // p = [half_height, radius, _]
+pub const CB2_CUBE: u32 = 7;      // p = [dim, _, _]
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]

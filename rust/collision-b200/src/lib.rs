@@ -24,10 +24,15 @@ pub struct Error(pub i32, pub String);
 #[derive(Clone, Copy, Debug, PartialEq, Eq)]
 pub struct ShapeId(pub u32);
 
-/// The shapes of `Primitive3<f32>` this path supports (primitive3.rs:20-40).
+/// `Primitive3<f32>` (primitive3.rs:20-40).
 pub enum Shape<'a> {
+    Particle,
+    Quad { dim_x: f32, dim_y: f32 },
     Sphere { radius: f32 },
     Cuboid { dim: Vector3<f32> },
+    Cube { dim: f32 },
+    Cylinder { half_height: f32, radius: f32 },
+    Capsule { half_height: f32, radius: f32 },
     /// `ConvexPolyhedron::new(vertices)` — VertexOnly mode (polyhedron.rs:100-122).  The crate
     /// keeps the vertices private, so the caller passes the same slice it built the shape from.
     ConvexPolyhedron { vertices: &'a [Point3<f32>] },
@@ -89,6 +94,11 @@ impl Context {
         let mut verts: Vec<f32> = Vec::new();
         for s in shapes {
             recs.push(match s {
+                Shape::Particle => sys::cb2_shape { kind: sys::CB2_PARTICLE, p: [0.0; 3], vtx_off: 0, vtx_cnt: 0 },
+                Shape::Quad { dim_x, dim_y } => sys::cb2_shape { kind: sys::CB2_QUAD, p: [*dim_x, *dim_y, 0.0], vtx_off: 0, vtx_cnt: 0 },
+                Shape::Cube { dim } => sys::cb2_shape { kind: sys::CB2_CUBE, p: [*dim, 0.0, 0.0], vtx_off: 0, vtx_cnt: 0 },
+                Shape::Cylinder { half_height, radius } => sys::cb2_shape { kind: sys::CB2_CYLINDER, p: [*half_height, *radius, 0.0], vtx_off: 0, vtx_cnt: 0 },
+                Shape::Capsule { half_height, radius } => sys::cb2_shape { kind: sys::CB2_CAPSULE, p: [*half_height, *radius, 0.0], vtx_off: 0, vtx_cnt: 0 },
                 Shape::Sphere { radius } => sys::cb2_shape { kind: sys::CB2_SPHERE, p: [*radius, 0.0, 0.0], vtx_off: 0, vtx_cnt: 0 },
                 Shape::Cuboid { dim } => sys::cb2_shape { kind: sys::CB2_CUBOID, p: [dim.x, dim.y, dim.z], vtx_off: 0, vtx_cnt: 0 },
                 Shape::ConvexPolyhedron { vertices } => {

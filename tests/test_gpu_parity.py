@@ -536,3 +536,58 @@ def test_complex_empty_composites_and_errors(ctx, oracle):
     assert st[0] == 0 and st[2] == 0 and np.array_equal(st, est)
     with pytest.raises(Cb2Error):
         ctx.intersection_complex(0, np.array([7], np.uint32), np.array([0], np.uint32), t[:1], t[:1])
+
+
+def test_every_primitive3_variant(ctx, oracle):
+    """Particle, Quad, Cylinder, Capsule and Cube next to Sphere / Cuboid / ConvexPolyhedron
+    (primitive3.rs:153-176): intersection (both strategies), distance, time of impact and world
+    bounds, bit for bit against the oracle; zero scale panics only where the reference's
+    support_point inverts the transform (a Particle never does)."""
+    rng = np.random.default_rng(99)
+    ps, pv = W.polyhedron_table(16, seed=3, sizes=(12, 40))
+    shapes = np.concatenate([W.all_primitive3_shapes(rng, 140), ps])
+    n = 60_000
+    l = rng.integers(0, len(shapes), n).astype(np.uint32)
+    r = rng.integers(0, len(shapes), n).astype(np.uint32)
+    lt, rt = W.random_xforms(rng, n, 0.9), W.random_xforms(rng, n, 0.9)
+    lt["scale"][::9] = rng.uniform(0.5, 1.5, len(lt["scale"][::9])).astype(np.float32)
+    rt["scale"][::211] = 0.0
+    lt["scale"][::307] = 0.0
+    ctx.upload_shapes(shapes, pv)
+    exp, est = oracle.intersection(1, shapes, pv, l, r, lt, rt, nthreads=8)
+    got, gst = ctx.intersection(1, l, r, lt, rt)
+    assert_contacts_equal(got, gst, exp, est, "Primitive3 mix, CollisionOnly")
+    # FullResolution: a Particle inside a Cylinder makes EPA grow non-manifold polytopes without
+    # bound (the reference's Vec reaches 430k faces and ~10 s per pair), so those pairs are checked
+    # on a handful only.  Past the 16384 faces of the second-chance scratch the device must answer
+    # CB2_SCRATCH_OVERFLOW, never a wrong contact.
+    kk = shapes["kind"]
+    slow = ((kk[l] == 3) & (kk[r] == 5)) | ((kk[l] == 5) & (kk[r] == 3))
+    few = np.nonzero(slow)[0][:12]
+    for sel in (np.nonzero(~slow)[0], few):
+        e0, s0, stats = oracle.intersection(0, shapes, pv, l[sel], r[sel], lt[sel], rt[sel],
+                                            nthreads=8, want_stats=True)
+        g0, gs0 = ctx.intersection(0, l[sel], r[sel], lt[sel], rt[sel])
+        fits = stats[:, 2] <= 16384
+        assert (gs0[~fits] == 7).all() and fits.sum() > 0.5 * len(sel)
+        assert_contacts_equal(g0[fits], gs0[fits], e0[fits], s0[fits], "Primitive3 mix, FullResolution")
+    kinds = shapes["kind"]
+    particle_zero = ((kinds[l] == 3) & (lt["scale"] == 0)) | ((kinds[r] == 3) & (rt["scale"] == 0))
+    assert particle_zero.sum() > 5 and (est == 4).sum() > 50
+    # a zero-scale Particle alone must not panic
+    alone = particle_zero & ~(((kinds[l] != 3) & (lt["scale"] == 0)) | ((kinds[r] != 3) & (rt["scale"] == 0)))
+    assert alone.sum() > 0 and (est[alone] != 4).all()
+    ed, est = oracle.distance(shapes, pv, l, r, lt, rt, nthreads=8)
+    gd, gst = ctx.distance(l, r, lt, rt)
+    assert np.array_equal(gst, est)
+    assert bits_equal(gd[est == 1], ed[est == 1]).all()
+    m = 20_000
+    lt1, rt1 = lt[:m].copy(), rt[:m].copy()
+    lt1["d"] += rng.uniform(-1, 1, (m, 3)).astype(np.float32)
+    rt1["d"] += ((lt["d"][:m] - rt["d"][:m]) * rng.uniform(0.5, 1.5, (m, 1))).astype(np.float32)
+    exp, est = oracle.time_of_impact(shapes, pv, l[:m], r[:m], lt[:m], lt1, rt[:m], rt1, nthreads=8)
+    got, gst = ctx.time_of_impact(l[:m], r[:m], lt[:m], lt1, rt[:m], rt1)
+    assert_contacts_equal(got, gst, exp, est, "Primitive3 mix, time of impact")
+    eb = oracle.world_aabbs(shapes, pv, l, lt, nthreads=8)
+    gb = ctx.world_aabbs(l, lt)
+    assert gb.tobytes() == eb.tobytes()

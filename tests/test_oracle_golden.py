@@ -333,3 +333,76 @@ def test_sweep_prune(oracle, boxes, exp):
     # the slice ends up sorted by min.x
     xs = [boxes[i][0] for i in perm]
     assert xs == sorted(xs)
+
+
+# ---- the remaining Primitive3 variants (capsule.rs:213-265, cylinder.rs:243-295, quad.rs:143-153)
+def _norm(v):
+    v = np.asarray(v, np.float32)
+    # InnerSpace::normalize = v * (1 / |v|), f32 one operation at a time
+    m = np.sqrt(np.float32(np.float32(v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]))
+    return (v * np.float32(np.float32(1) / m)).astype(np.float32)
+
+
+def test_capsule_and_cylinder_bounds(oracle):
+    # capsule.rs:214-220 test_capsule_aabb; cylinder.rs:244-250 test_cylinder_aabb
+    from helpers import shape
+    shapes = np.concatenate([shape(6, (2.0, 1.0, 0)), shape(5, (2.0, 1.0, 0)), shape(3),
+                             shape(4, (2.0, 4.0, 0)), shape(7, (10.0, 0, 0))])
+    t = np.concatenate([IDENT] * 5)
+    b = oracle.world_aabbs(shapes, None, np.arange(5, dtype=np.uint32), t)
+    assert tuple(b[0]["min"]) == (-1, -3, -1) and tuple(b[0]["max"]) == (1, 3, 1)
+    assert tuple(b[1]["min"]) == (-1, -2, -1) and tuple(b[1]["max"]) == (1, 2, 1)
+    assert tuple(b[2]["min"]) == (0, 0, 0) and tuple(b[2]["max"]) == (0, 0, 0)      # Aabb3::zero()
+    assert tuple(b[3]["min"]) == (-1, -2, 0) and tuple(b[3]["max"]) == (1, 2, 0)
+    assert tuple(b[4]["min"]) == (-5, -5, -5) and tuple(b[4]["max"]) == (5, 5, 5)
+
+
+@pytest.mark.parametrize("d,t,exp", [
+    ((1, 0, 0), (0, 0, 0, 0.0), (1, 2, 0)),                                  # test_capsule_support_1
+    (_norm((0.5, -1, 0)), (0, 0, 0, 0.0), (0.447_213_65, -2.894_427_3, 0)),  # _2
+    ((0, 1, 0), (0, 0, 0, 0.0), (0, 3, 0)),                                  # _3
+    ((1, 0, 0), (10, 0, 0, 0.0), (11, 2, 0)),                                # _4
+    ((1, 0, 0), (0, 0, 0, np.pi), (1, -2, 0)),                               # _5
+])
+def test_capsule_support(oracle, d, t, exp):
+    from helpers import shape
+    p, st = oracle.support_point(shape(6, (2.0, 1.0, 0)), None, transform_3d(*t), d)
+    assert st == 1 and ulps_eq(p, exp)
+
+
+@pytest.mark.parametrize("d,t,exp", [
+    ((1, 0, 0), (0, 0, 0, 0.0), (1, 2, 0)),                 # test_cylinder_support_1
+    (_norm((0.5, -1, 0)), (0, 0, 0, 0.0), (1, -2, 0)),      # _2
+    ((0, 1, 0), (0, 0, 0, 0.0), (0, 2, 0)),                 # _3
+    ((1, 0, 0), (10, 0, 0, 0.0), (11, 2, 0)),               # _4
+    ((1, 0, 0), (0, 0, 0, np.pi), (1, -2, 0)),              # _5
+])
+def test_cylinder_support(oracle, d, t, exp):
+    from helpers import shape
+    p, st = oracle.support_point(shape(5, (2.0, 1.0, 0)), None, transform_3d(*t), d)
+    assert st == 1 and ulps_eq(p, exp)
+
+
+def test_quad_cuboid_intersect(oracle):
+    # quad.rs:143-153 test_plane_cuboid_intersect: Quad(2,2) at z=1 against Cuboid(1,1,1) at z=1.1
+    from helpers import shape
+    shapes = np.concatenate([shape(4, (2.0, 2.0, 0)), cuboid(1, 1, 1)])
+    out, st = oracle.intersection(1, shapes, None, np.array([0], np.uint32), np.array([1], np.uint32),
+                                  transform_3d(0, 0, 1.0), transform_3d(0, 0, 1.1))
+    assert st[0] == 1
+
+
+def test_particle_support_ignores_direction_and_scale(oracle):
+    # primitive3.rs:164: transform.transform_point(origin) — no inverse transform, so no panic
+    # even when scale is 0
+    from helpers import shape
+    p, st = oracle.support_point(shape(3), None, transform_3d(1, 2, 3, 0.3, scale=0.0), (0, 1, 0))
+    assert st == 1 and tuple(p) == (1, 2, 3)
+
+
+def test_cube_is_a_cuboid(oracle):
+    from helpers import shape
+    for d in ((1, 0.2, -0.3), (-1, -1, 1), (0, 0, 0)):
+        a, _ = oracle.support_point(shape(7, (3.0, 0, 0)), None, transform_3d(1, 0, 0, 0.7), d)
+        b, _ = oracle.support_point(cuboid(3, 3, 3), None, transform_3d(1, 0, 0, 0.7), d)
+        assert np.array_equal(a, b)
