@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcollision_b200.so")
+# CB2_LIB_PATH: an alternative build of the same library (A/B experiments, tools/ab_variants.sh)
+LIB_PATH = os.environ.get("CB2_LIB_PATH") or os.path.join(_HERE, "libcollision_b200.so")
 
 # ---- POD mirrors (numpy structured dtypes; layouts asserted against sizeof in tests) ----
 SHAPE_DT = np.dtype([("kind", "<u4"), ("p", "<f4", (3,)), ("vtx_off", "<u4"), ("vtx_cnt", "<u4")])

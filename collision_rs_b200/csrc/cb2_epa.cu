@@ -31,6 +31,14 @@
 #include "cb2_gjk.cuh"
 #include "cb2_kernels.h"
 
+#ifndef CB2_T0_F  // build-time overrides for A/B experiments (tools/ab_variants.sh)
+#define CB2_T0_F 40
+#define CB2_T0_V 24
+#define CB2_T0_O 24
+#endif
+#ifndef CB2_EPA_MIN_BLOCKS
+#define CB2_EPA_MIN_BLOCKS 20
+#endif
 namespace cb2 {
 
 CB2_DI shape_table table_of(const shape_table_args& a) {
@@ -173,7 +181,7 @@ enum : int { S_FETCH = 0, S_RUN = 1, S_EXIT = 2 };
 
 // RF/RV: caps of the tier whose dumps this instantiation resumes (0 = none)
 template <int G, int FCAP, int VCAP, int OCAP, int RF, int RV>
-__global__ void __launch_bounds__(32) k_epa(epa_args C) {
+__global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
     static_assert(G == 2 || G == 4 || G == 8, "3*G edge-keep bits must fit one word");
     static_assert(RF <= FCAP && RV <= VCAP, "a resumed polytope must fit");
     using PS = poly_smem<FCAP, VCAP, OCAP>;
@@ -531,7 +539,7 @@ __global__ void __launch_bounds__(32) k_epa(epa_args C) {
 
 // ---- host side ----------------------------------------------------------------------------------------
 // tier:            G   faces  verts  examined/horizon cap
-constexpr int T0_G = 4, T0_F = 40, T0_V = 24, T0_O = 24;
+constexpr int T0_G = 4, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O;
 constexpr int T1_G = 4, T1_F = 72, T1_V = 40, T1_O = 32;
 constexpr int T2_G = 8, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
 

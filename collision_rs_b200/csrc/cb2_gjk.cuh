@@ -138,15 +138,20 @@ CB2_DI f3 capsule_local_support(f3 h, f3 d) {
     return p + normalize_to(d, h.y);
 }
 
+// the less common variants stay out of line so that they do not bloat the hot loops
+static __device__ __noinline__ f3 other_local_support(uint32_t kind, f3 h, f3 d) {
+    if (kind == K_QUAD) return quad_local_support(h, d);
+    if (kind == K_CYLINDER) return cylinder_local_support(h, d);
+    return capsule_local_support(h, d);
+}
+
 // Primitive3 dispatch (primitive3.rs:153-176); ConvexPolyhedron VertexOnly (polyhedron.rs:160-176)
 // goes through the support cells (cb2_cells.cuh)
 CB2_DI f3 local_support(const shape& s, f3 d) {
     if (s.kind == K_CUBOID) return cuboid_local_support(s.h, d);
-    if (s.kind == K_SPHERE) return sphere_local_support(s.h.x, d);
     if (s.kind == K_POLY) return poly_local_support(s.poly, d);
-    if (s.kind == K_QUAD) return quad_local_support(s.h, d);
-    if (s.kind == K_CYLINDER) return cylinder_local_support(s.h, d);
-    return capsule_local_support(s.h, d);
+    if (s.kind == K_SPHERE) return sphere_local_support(s.h.x, d);
+    return other_local_support(s.kind, s.h, d);
 }
 
 CB2_DI f3 support_point(const shape& s, const xform& t, f3 dir) {

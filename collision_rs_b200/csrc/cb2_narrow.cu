@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
 // Pairs with a Sphere go straight to the largest polytope tier (curved shapes run EPA to the
 // iteration cap: ~137 faces).
 template <bool FULL>
-__global__ void __launch_bounds__(128) k_gjk_hits(narrow_args A, narrow_ws W) {
+__global__ void __launch_bounds__(128, 4) k_gjk_hits(narrow_args A, narrow_ws W) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool hit = false, curved = false;
     if (i < A.n) {
