@@ -22,7 +22,7 @@ AABB_DT = np.dtype([("min", "<f4", (3,)), ("max", "<f4", (3,))])
 assert SHAPE_DT.itemsize == 24 and XFORM_DT.itemsize == 32
 assert CONTACT_DT.itemsize == 36 and AABB_DT.itemsize == 24
 
-SPHERE, CUBOID, POLYHEDRON, PARTICLE, QUAD, CYLINDER, CAPSULE, CUBE = 0, 1, 2, 3, 4, 5, 6, 7
+SPHERE, CUBOID, POLYHEDRON, PARTICLE, QUAD, CYLINDER, CAPSULE, CUBE, POLYHEDRON_HE = range(9)
 FULL_RESOLUTION, COLLISION_ONLY = 0, 1
 (NONE, SOME, PANIC_UNWRAP_PLANE, PANIC_ASSERT_RANGE, PANIC_INV_SCALE, NONCONVERGED,
  PANIC_EPA_EMPTY) = range(7)
@@ -44,7 +44,7 @@ class Settings(C.Structure):
 SYMBOLS = [
     "cb2_abi_version", "cb2_default_settings", "cb2_create", "cb2_destroy", "cb2_last_error",
     "cb2_device_sm_count", "cb2_kernel_launches", "cb2_set_stage_timing", "cb2_last_stage_ms",
-    "cb2_shapes_upload",
+    "cb2_shapes_upload", "cb2_shapes_upload_faces",
     "cb2_gjk3_intersection", "cb2_gjk3_distance", "cb2_gjk3_time_of_impact",
     "cb2_gjk3_intersection_dev", "cb2_gjk3_distance_dev", "cb2_gjk3_time_of_impact_dev",
     "cb2_gjk3_intersection_bodies_dev",
@@ -82,6 +82,7 @@ def load():
     lib.cb2_set_stage_timing.argtypes = [vp, i32]
     lib.cb2_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     lib.cb2_shapes_upload.argtypes = [vp, vp, u32, vp, u64]
+    lib.cb2_shapes_upload_faces.argtypes = [vp, vp, u32, vp, u64, vp, u64]
     sp = C.POINTER(Settings)
     lib.cb2_gjk3_intersection.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp]
     lib.cb2_gjk3_distance.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp]

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,8 @@ struct cb2_ctx {
     // shape table
     dshape* d_shapes = nullptr;
     float4* d_verts = nullptr;
+    uint32_t* d_ring_off = nullptr;  // HalfEdge polyhedra: ring CSR (cb2_cells.cuh)
+    uint32_t* d_ring_idx = nullptr;
     uint4* d_cells = nullptr;        // support cells of all polyhedra (cb2_cells.cuh)
     uint16_t* d_cell_ext = nullptr;  // their extension pool
     uint32_t* d_cell_cursor = nullptr;
@@ -172,6 +175,8 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_cells) cudaFree(c->d_cells);
     if (c->d_cell_ext) cudaFree(c->d_cell_ext);
     if (c->d_cell_cursor) cudaFree(c->d_cell_cursor);
+    if (c->d_ring_off) cudaFree(c->d_ring_off);
+    if (c->d_ring_idx) cudaFree(c->d_ring_idx);
     if (c->d_misc) cudaFree(c->d_misc);
     if (c->d_comp_off) cudaFree(c->d_comp_off);
     if (c->d_comp_shape) cudaFree(c->d_comp_shape);
@@ -213,11 +218,89 @@ int cb2_last_stage_ms(cb2_ctx* c, float* out4) {
     return CB2_OK;
 }
 
-int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
-                      const float* verts_xyz, uint64_t n_verts) {
+}  // extern "C"
+
+// ConvexPolyhedron::new_with_faces: build_half_edges (polyhedron.rs:282-380) on the host, reduced
+// to what hill_climb_support_point reads: per vertex, the targets of its ring walk in walk order.
+// Appends to ring_idx and fills ring_off[voff + v .. ] with per-vertex counts (prefix-summed later).
+static const char* build_rings(const cb2_shape& s, const float* verts_xyz, const uint32_t* faces,
+                               uint64_t n_faces, std::vector<uint32_t>& ring_cnt,
+                               std::vector<std::vector<uint32_t>>& rings) {
+    uint32_t f_off, f_cnt;
+    std::memcpy(&f_off, &s.p[0], 4);
+    std::memcpy(&f_cnt, &s.p[1], 4);
+    const uint32_t V = s.vtx_cnt;
+    if (V == 0 || f_cnt == 0) return "HalfEdge polyhedron without vertices or faces";
+    if (!faces || (uint64_t)f_off + f_cnt > n_faces) return "face range outside the face table";
+    std::vector<uint32_t> vedge(V, 0), target, twin, next;
+    std::vector<char> vready(V, 0);
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> edge_map;
+    const float* vb = verts_xyz + 3ull * s.vtx_off;
+    for (uint32_t f = 0; f < f_cnt; ++f) {
+        const uint32_t* fv = faces + 3ull * (f_off + f);
+        for (int k = 0; k < 3; ++k)
+            if (fv[k] >= V) return "face vertex index out of range";
+        {   // Plane::from_points(a, b, c).unwrap() (plane.rs:78-95): cross ~ 0 panics.  f32, unfused.
+            volatile float e[6];
+            for (int k = 0; k < 3; ++k) {
+                e[k] = vb[3 * fv[1] + k] - vb[3 * fv[0] + k];
+                e[3 + k] = vb[3 * fv[2] + k] - vb[3 * fv[0] + k];
+            }
+            volatile float m0 = e[1] * e[5], m1 = e[2] * e[4], m2 = e[2] * e[3], m3 = e[0] * e[5],
+                           m4 = e[0] * e[4], m5 = e[1] * e[3];
+            const float nx = m0 - m1, ny = m2 - m3, nz = m4 - m5;
+            const float eps = 1.1920929e-7f;
+            if (std::fabs(nx) <= eps && std::fabs(ny) <= eps && std::fabs(nz) <= eps)
+                return "degenerate face: ConvexPolyhedron::new_with_faces panics (plane.rs:78-95)";
+        }
+        uint32_t face_edge[3] = {0, 0, 0};
+        for (int j = 0; j < 3; ++j) {
+            const int i = j == 0 ? 2 : j - 1;
+            const uint32_t v0 = fv[i], v1 = fv[j];
+            uint32_t e01, e10;
+            auto it = edge_map.find({v0, v1});
+            if (it != edge_map.end()) {
+                e01 = it->second;
+                e10 = twin[e01];
+            } else {
+                e01 = (uint32_t)target.size();
+                e10 = e01 + 1;
+                target.push_back(v1); twin.push_back(e10); next.push_back(0);
+                target.push_back(v0); twin.push_back(e01); next.push_back(0);
+            }
+            edge_map[{v0, v1}] = e01;
+            edge_map[{v1, v0}] = e10;
+            if (!vready[v0]) {
+                vedge[v0] = e01;
+                vready[v0] = 1;
+            }
+            face_edge[i] = e01;
+        }
+        for (int j = 0; j < 3; ++j) next[face_edge[j == 0 ? 2 : j - 1]] = face_edge[j];
+    }
+    const size_t E = target.size();
+    for (uint32_t v = 0; v < V; ++v) {
+        std::vector<uint32_t> ring;
+        uint32_t e = vedge[v];
+        do {
+            ring.push_back(target[e]);
+            e = next[twin[e]];
+            if (ring.size() > E) return "a vertex ring does not close (not a closed 2-manifold)";
+        } while (e != vedge[v]);
+        ring_cnt[s.vtx_off + v] = (uint32_t)ring.size();
+        rings[s.vtx_off + v] = std::move(ring);
+    }
+    return nullptr;
+}
+
+static int shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
+                         const float* verts_xyz, uint64_t n_verts, const uint32_t* faces,
+                         uint64_t n_faces) {
     if (!c || (!shapes && n_shapes) || (!verts_xyz && n_verts)) return fail(c, CB2_ERR_ARG, "null argument");
     CK(c, cudaSetDevice(c->device));
     std::vector<dshape> hs(n_shapes);
+    std::vector<uint32_t> ring_cnt;                // HalfEdge rings, per global vertex
+    std::vector<std::vector<uint32_t>> rings;
     uint64_t total_cells = 0;
     uint32_t max_N = 0;
     c->has_poly = false;
@@ -244,6 +327,17 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
             d.hy = s.p[1];  // radius
         } else if (s.kind == CB2_PARTICLE) {
             // no parameters
+        } else if (s.kind == CB2_POLYHEDRON_HE) {
+            if ((uint64_t)s.vtx_off + s.vtx_cnt > n_verts)
+                return fail(c, CB2_ERR_ARG, "polyhedron vertex range outside the vertex table");
+            if (ring_cnt.empty()) {
+                ring_cnt.assign(n_verts + 1, 0);
+                rings.resize(n_verts);
+            }
+            const char* why = build_rings(s, verts_xyz, faces, n_faces, ring_cnt, rings);
+            if (why) return fail(c, CB2_ERR_ARG, why);
+            d.voff = s.vtx_off;
+            d.vcnt = s.vtx_cnt;
         } else if (s.kind == CB2_POLYHEDRON) {
             if ((uint64_t)s.vtx_off + s.vtx_cnt > n_verts)
                 return fail(c, CB2_ERR_ARG, "polyhedron vertex range outside the vertex table");
@@ -290,6 +384,23 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
         CK(c, cudaMemcpy(c->d_verts, hv.data(), sizeof(float4) * n_verts, cudaMemcpyHostToDevice));
     c->n_shapes = n_shapes;
     c->n_verts = n_verts;
+    {   // HalfEdge ring CSR over the global vertex numbering (empty without HalfEdge shapes)
+        std::vector<uint32_t> off(n_verts + 1, 0), idx;
+        if (!ring_cnt.empty()) {
+            for (uint64_t v = 0; v < n_verts; ++v) {
+                off[v + 1] = off[v] + ring_cnt[v];
+                idx.insert(idx.end(), rings[v].begin(), rings[v].end());
+            }
+        }
+        if (c->d_ring_off) cudaFree(c->d_ring_off);
+        if (c->d_ring_idx) cudaFree(c->d_ring_idx);
+        c->d_ring_off = c->d_ring_idx = nullptr;
+        CK(c, cudaMalloc(&c->d_ring_off, sizeof(uint32_t) * off.size()));
+        CK(c, cudaMalloc(&c->d_ring_idx, sizeof(uint32_t) * (idx.empty() ? 1 : idx.size())));
+        CK(c, cudaMemcpy(c->d_ring_off, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice));
+        if (!idx.empty())
+            CK(c, cudaMemcpy(c->d_ring_idx, idx.data(), sizeof(uint32_t) * idx.size(), cudaMemcpyHostToDevice));
+    }
     // build the support cells on the device (one thread per cell)
     const uint64_t ext_cap64 = total_cells * 4 + (1u << 16);
     const uint32_t ext_cap = ext_cap64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ext_cap64;
@@ -309,6 +420,16 @@ int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
     return CB2_OK;
 }
 
+extern "C" {
+int cb2_shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
+                      const float* verts_xyz, uint64_t n_verts) {
+    return shapes_upload(c, shapes, n_shapes, verts_xyz, n_verts, nullptr, 0);
+}
+int cb2_shapes_upload_faces(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
+                            const float* verts_xyz, uint64_t n_verts, const uint32_t* faces,
+                            uint64_t n_faces) {
+    return shapes_upload(c, shapes, n_shapes, verts_xyz, n_verts, faces, n_faces);
+}
 }  // extern "C"
 
 // ---- narrow phase ---------------------------------------------------------------------------------
@@ -362,6 +483,7 @@ static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, 
                      int ws_slot = 0) {
     int rc = launch_op_inner(c, op, strategy, A, st, ws_slot);
     if (rc || op != OP_INTERSECTION || strategy != CB2_FULL_RESOLUTION) return rc;
+    if (std::getenv("CB2_NO_RETRY")) return CB2_OK;  // diagnosis: leave CB2_SCRATCH_OVERFLOW visible
     // redo the rare pairs whose polytope outgrew the fast kernels' scratch
     rc = ensure_retry(c, ws_slot);
     if (rc) return rc;
@@ -385,6 +507,8 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
     A.T.verts = c->d_verts;
     A.T.cells = c->d_cells;
     A.T.ext = c->d_cell_ext;
+    A.T.ring_off = c->d_ring_off;
+    A.T.ring_idx = c->d_ring_idx;
     cudaError_t e;
     if (op == OP_INTERSECTION && !c->legacy_epa) {
         // GJK (thread per pair) -> compacted hit list -> cooperative EPA tiers
@@ -669,6 +793,8 @@ int cb2_world_aabbs_dev(cb2_ctx* c, const uint32_t* shape, const cb2_xform* t, u
     A.T.verts = c->d_verts;
     A.T.cells = c->d_cells;
     A.T.ext = c->d_cell_ext;
+    A.T.ring_off = c->d_ring_off;
+    A.T.ring_idx = c->d_ring_idx;
     A.shape = shape;
     A.t = reinterpret_cast<const float4*>(t);
     A.n = n;

@@ -50,6 +50,7 @@ CB2_DI uint32_t cell_index(f3 d, uint32_t N, float& m) {
 struct poly_ref {
     const float4* verts;     // (x,y,z,0)
     uint32_t vcnt;
+    uint32_t voff;           // first vertex in the global table (HalfEdge ring lookup)
     const uint4* cells;      // this shape's 6*N*N records (nullptr when N == 0)
     const uint16_t* ext;     // extension pool
     uint32_t N;              // 0 => no cells
@@ -87,6 +88,36 @@ static __device__ __noinline__ f3 poly_ext_scan(const float4* __restrict__ verts
         }
     }
     return best;
+}
+
+// HalfEdge mode (ConvexPolyhedron::new_with_faces): hill_climb_support_point, polyhedron.rs:179-209.
+// ring_off / ring_idx hold, per vertex, the target vertices of the reference's ring walk
+// (edges[twin].next_edge from vertices[v].edge) in walk order.  Returns (point, hang): the
+// reference's loop `while best_dot != previous_best_dot` never ends once best_dot is NaN.
+static __device__ __noinline__ float4 poly_hill_climb(const float4* __restrict__ verts,
+                                                      const uint32_t* __restrict__ ring_off,
+                                                      const uint32_t* __restrict__ ring_idx,
+                                                      uint32_t vcnt, f3 d) {
+    uint32_t best = 0;
+    float4 bv = __ldg(verts);
+    float best_dot = dot(mk3(bv.x, bv.y, bv.z), d);
+    // the dot strictly grows every round, so a climb takes fewer than vcnt rounds
+    for (uint32_t round = 0; round <= vcnt; ++round) {
+        const float previous = best_dot;
+        const uint32_t k1 = __ldg(ring_off + best + 1);
+        for (uint32_t k = __ldg(ring_off + best); k < k1; ++k) {
+            const uint32_t nb = __ldg(ring_idx + k);
+            const float4 v = __ldg(verts + nb);
+            const float dt = dot(mk3(v.x, v.y, v.z), d);
+            if (dt > best_dot) {
+                best = nb;
+                best_dot = dt;
+                bv = v;
+            }
+        }
+        if (best_dot == previous) return make_float4(bv.x, bv.y, bv.z, 0.0f);
+    }
+    return make_float4(bv.x, bv.y, bv.z, 1.0f);
 }
 
 // local-space support point of a polyhedron for direction d (already in model space)

@@ -47,6 +47,8 @@ CB2_DI shape_table table_of(const shape_table_args& a) {
     t.verts = a.verts;
     t.cells = a.cells;
     t.ext = a.ext;
+    t.ring_off = a.ring_off;
+    t.ring_idx = a.ring_idx;
     return t;
 }
 
@@ -228,7 +230,8 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
     sh.kind = K_CUBOID;
     sh.h = zero3();
     sh.poly.verts = nullptr; sh.poly.vcnt = 0; sh.poly.cells = nullptr; sh.poly.ext = nullptr;
-    sh.poly.N = 0; sh.poly.wide = false; sh.poly.R = 0.f;
+    sh.poly.N = 0; sh.poly.wide = false; sh.poly.R = 0.f; sh.poly.voff = 0;
+    sh.ring_off = nullptr; sh.ring_idx = nullptr; sh.hang = 0u;
     xform xf = make_xform(make_float4(1.f, 1.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
     f3 d = zero3();
     uint32_t it = 0;
@@ -341,9 +344,14 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
             sup_a = right ? o : w;
             sup_v = sup_a - (right ? w : o);
         }
+        // a HalfEdge polyhedron's hill climb met a NaN direction: the reference never returns
+        // (the vote is taken by every lane BEFORE it is combined with `run`: `run && vote(..)`
+        // would let the lanes of idle groups skip a full-mask vote)
+        const unsigned hang_votes = __ballot_sync(0xffffffffu, sh.hang != 0u);
+        const bool hung = run && (hang_votes & gmask) != 0u;
         // epa3d.rs:46-64: stop when the new point is within tolerance of the face, or at the cap
-        const bool conv = run && (fsub(dot(sup_v, n), fb.w) < epa_tol || it >= max_it);
-        const bool add = run && !conv;
+        const bool conv = run && !hung && (fsub(dot(sup_v, n), fb.w) < epa_tol || it >= max_it);
+        const bool add = run && !hung && !conv;
 
         // ================= Polytope::add (epa3d.rs:147-175) =============================================
         // (1) visibility of every face -> bit mask (uniform across the group)
@@ -488,6 +496,7 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
         }
         if (spill) result = ST_SCRATCH_OVERFLOW;
         if (conv) result = ST_SOME;
+        if (hung) result = ST_NONCONVERGED;
 
         // ================= finished pairs (divergent) ====================================================
         if (result != ST_NONE) {

@@ -14,8 +14,9 @@
 namespace cb2 {
 
 enum : uint32_t {
-    K_SPHERE = 0, K_CUBOID = 1, K_POLY = 2, K_PARTICLE = 3, K_QUAD = 4, K_CYLINDER = 5, K_CAPSULE = 6
-};  // a Cube is uploaded as a Cuboid
+    K_SPHERE = 0, K_CUBOID = 1, K_POLY = 2, K_PARTICLE = 3, K_QUAD = 4, K_CYLINDER = 5, K_CAPSULE = 6,
+    K_POLY_HE = 8
+};  // a Cube (7) is uploaded as a Cuboid
 enum : uint8_t {
     ST_NONE = 0,
     ST_SOME = 1,
@@ -45,12 +46,17 @@ struct shape_table {
     const float4* verts;   // polyhedron vertices, (x,y,z,0)
     const uint4* cells;    // support-cell records of all polyhedra
     const uint16_t* ext;   // support-cell extension pool
+    const uint32_t* ring_off;  // HalfEdge polyhedra: per GLOBAL vertex, its ring in ring_idx
+    const uint32_t* ring_idx;  // ring targets (vertex indices local to the shape), walk order
 };
 
 struct shape {
     uint32_t kind;
     f3 h;
     poly_ref poly;
+    const uint32_t* ring_off;  // ring_off + voff of this shape (HalfEdge mode only)
+    const uint32_t* ring_idx;
+    mutable uint32_t hang;     // set when a support call hit the reference's endless hill climb
 };
 
 CB2_DI shape load_shape(const shape_table& T, uint32_t idx) {
@@ -62,6 +68,10 @@ CB2_DI shape load_shape(const shape_table& T, uint32_t idx) {
     s.h = mk3(a.y, a.z, a.w);
     s.poly.verts = T.verts + __float_as_uint(b.x);
     s.poly.vcnt = __float_as_uint(b.y);
+    s.poly.voff = __float_as_uint(b.x);
+    s.ring_off = T.ring_off + __float_as_uint(b.x);
+    s.ring_idx = T.ring_idx;
+    s.hang = 0u;
     s.poly.cells = T.cells + __float_as_uint(b.z);
     s.poly.ext = T.ext;
     const uint32_t cfg = __float_as_uint(b.w);
@@ -151,6 +161,11 @@ CB2_DI f3 local_support(const shape& s, f3 d) {
     if (s.kind == K_CUBOID) return cuboid_local_support(s.h, d);
     if (s.kind == K_POLY) return poly_local_support(s.poly, d);
     if (s.kind == K_SPHERE) return sphere_local_support(s.h.x, d);
+    if (s.kind == K_POLY_HE) {
+        const float4 r = poly_hill_climb(s.poly.verts, s.ring_off, s.ring_idx, s.poly.vcnt, d);
+        if (r.w != 0.0f) s.hang = 1u;
+        return mk3(r.x, r.y, r.z);
+    }
     return other_local_support(s.kind, s.h, d);
 }
 

@@ -15,6 +15,8 @@ struct shape_table_args {
     const float4* verts;      // polyhedron vertices, (x,y,z,0)
     const uint4* cells;       // support-cell records (cb2_cells.cuh)
     const uint16_t* ext;      // support-cell extension pool
+    const uint32_t* ring_off; // HalfEdge polyhedra: ring CSR over the global vertex numbering
+    const uint32_t* ring_idx;
 };
 
 // All pointers are device pointers.

@@ -21,6 +21,8 @@ CB2_DI shape_table table_of(const shape_table_args& a) {
     t.verts = a.verts;
     t.cells = a.cells;
     t.ext = a.ext;
+    t.ring_off = a.ring_off;
+    t.ring_idx = a.ring_idx;
     return t;
 }
 
@@ -268,6 +270,10 @@ __global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
                 st = ST_SOME;
             }
         }
+        if (p.ls.hang | p.rs.hang) {  // the reference's hill climb never returned
+            st = ST_NONCONVERGED;
+            c = zero_contact();
+        }
     }
     store_contact(A.out_contact, i, FULL ? CB2_FULL_RESOLUTION : CB2_COLLISION_ONLY, c);
     A.out_status[i] = st;
@@ -289,7 +295,10 @@ __global__ void __launch_bounds__(128, 4) k_gjk_hits(narrow_args A, narrow_ws W)
             st = ST_PANIC_INV_SCALE;
         } else {
             simplex<FULL> s;
-            if (gjk_intersect<FULL>(p, A.settings.max_iterations, s)) {
+            const bool inside = gjk_intersect<FULL>(p, A.settings.max_iterations, s);
+            if (p.ls.hang | p.rs.hang) {  // the reference's hill climb never returned
+                st = ST_NONCONVERGED;
+            } else if (inside) {
                 st = ST_SOME;
                 if constexpr (FULL) {
                     hit = true;
@@ -363,6 +372,10 @@ __global__ void __launch_bounds__(128) k_distance(narrow_args A) {
                 break;
             }
             s.push(v, a);
+        }
+        if (p.ls.hang | p.rs.hang) {
+            st = ST_NONCONVERGED;
+            result = 0.0f;
         }
     }
     A.out_distance[i] = result;
@@ -438,6 +451,10 @@ __global__ void __launch_bounds__(128) k_time_of_impact(narrow_args A) {
             c.toi = lambda;
             st = ST_SOME;
         }
+        if (p.ls.hang | p.rs.hang) {
+            st = ST_NONCONVERGED;
+            c = zero_contact();
+        }
     }
     store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, c);
     A.out_status[i] = st;
@@ -485,6 +502,10 @@ __global__ void __launch_bounds__(32) k_retry_overflow(narrow_args A, const uint
             if (gjk_intersect<true>(p, A.settings.max_iterations, s)) {
                 st = epa_process(P, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
                 if (st != ST_SOME) c = zero_contact();
+            }
+            if (p.ls.hang | p.rs.hang) {
+                st = ST_NONCONVERGED;
+                c = zero_contact();
             }
         }
         store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, c);

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import abi
 from .abi import (AABB_DT, CAPSULE, COLLISION_ONLY, CONTACT_DT, CUBE, CUBOID, CYLINDER,
-                  FULL_RESOLUTION, PARTICLE, POLYHEDRON, QUAD, SHAPE_DT, SPHERE, XFORM_DT, Settings,
+                  FULL_RESOLUTION, PARTICLE, POLYHEDRON, POLYHEDRON_HE, QUAD, SHAPE_DT, SPHERE, XFORM_DT, Settings,
                   ptr)
 
 
@@ -84,13 +84,20 @@ class Context:
         return [float(x) for x in out]
 
     # ---- shape table --------------------------------------------------------------------
-    def upload_shapes(self, shapes, verts=None):
+    def upload_shapes(self, shapes, verts=None, faces=None):
+        """faces: (F, 3) uint32 for HalfEdge polyhedra (kind POLYHEDRON_HE; their face range is
+        stored in p[0], p[1] as uint32 bit patterns), vertex indices local to the owning shape."""
         shapes = np.ascontiguousarray(shapes, SHAPE_DT)
         nv = 0
         if verts is not None:
             verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
             nv = len(verts)
-        self._ck(self.lib.cb2_shapes_upload(self.h, ptr(shapes), len(shapes), ptr(verts), nv))
+        if faces is None:
+            self._ck(self.lib.cb2_shapes_upload(self.h, ptr(shapes), len(shapes), ptr(verts), nv))
+        else:
+            faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+            self._ck(self.lib.cb2_shapes_upload_faces(self.h, ptr(shapes), len(shapes), ptr(verts),
+                                                      nv, ptr(faces), len(faces)))
         self.n_shapes = len(shapes)
 
     # ---- narrow phase, host buffers --------------------------------------------------------
@@ -306,10 +313,16 @@ class Particle3:
 
 
 class ConvexPolyhedron:
-    """primitive/polyhedron.rs:100-122, VertexOnly mode (ConvexPolyhedron::new)."""
+    """primitive/polyhedron.rs:100-139: ConvexPolyhedron::new(vertices) (VertexOnly mode) or
+    ConvexPolyhedron::new_with_faces(vertices, faces) (HalfEdge mode: hill-climb support)."""
 
-    def __init__(self, vertices):
+    def __init__(self, vertices, faces=None):
         self.vertices = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        self.faces = None if faces is None else np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+
+    @staticmethod
+    def new_with_faces(vertices, faces):
+        return ConvexPolyhedron(vertices, faces)
 
 
 @dataclass
@@ -329,8 +342,8 @@ class Decomposed:
 
 def _shape_table(prims):
     shapes = np.zeros(len(prims), SHAPE_DT)
-    verts = []
-    off = 0
+    verts, faces = [], []
+    off = foff = 0
     for i, p in enumerate(prims):
         if isinstance(p, Sphere):
             shapes[i]["kind"] = SPHERE
@@ -356,12 +369,19 @@ def _shape_table(prims):
             shapes[i]["kind"] = POLYHEDRON
             shapes[i]["vtx_off"] = off
             shapes[i]["vtx_cnt"] = len(p.vertices)
+            if p.faces is not None:
+                shapes[i]["kind"] = POLYHEDRON_HE
+                shapes[i:i + 1]["p"].view(np.uint32)[0, 0] = foff
+                shapes[i:i + 1]["p"].view(np.uint32)[0, 1] = len(p.faces)
+                faces.append(p.faces)
+                foff += len(p.faces)
             verts.append(p.vertices)
             off += len(p.vertices)
         else:
             raise TypeError(f"unsupported primitive {type(p).__name__}")
     v = np.concatenate(verts) if verts else None
-    return shapes, v
+    f = np.concatenate(faces) if faces else None
+    return shapes, v, f
 
 
 _I0 = np.array([0], np.uint32)
@@ -387,8 +407,8 @@ class GJK3:
         return GJK3(ctx, distance_tolerance, continuous_tolerance, epa_tolerance, max_iterations)
 
     def _upload(self, left, right):
-        shapes, verts = _shape_table([left, right])
-        self.ctx.upload_shapes(shapes, verts)
+        shapes, verts, faces = _shape_table([left, right])
+        self.ctx.upload_shapes(shapes, verts, faces)
 
     def intersection(self, strategy, left, left_transform, right, right_transform):
         """gjk/mod.rs:362-391 -> Option<Contact>"""

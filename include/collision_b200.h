@@ -7,7 +7,7 @@
  * below replaces one generic method specialised to
  *     S = f32, P = Point3<f32>, T = Decomposed<Vector3<f32>, Quaternion<f32>>,
  *     shapes = Primitive3<f32>: Particle, Quad, Sphere, Cuboid, Cube, Cylinder, Capsule,
- *     ConvexPolyhedron (VertexOnly mode)
+ *     ConvexPolyhedron (VertexOnly and HalfEdge mode)
  * and batched (one record per pair instead of one call per pair).
  * Citations are relative to the reference tree (src/...).
  *
@@ -52,8 +52,10 @@ typedef enum cb2_status {
     CB2_PANIC_INV_SCALE = 4,    /* inverse_transform_vector(..).unwrap() with
                                    scale ~ 0, primitive/util.rs:18, sphere.rs:36,
                                    polyhedron.rs:394                             */
-    CB2_NONCONVERGED = 5,       /* time-of-impact loop hit iter_cap; the reference
-                                   loop (gjk/mod.rs:204) has no cap and would hang */
+    CB2_NONCONVERGED = 5,       /* the reference would never return: the time-of-impact
+                                   loop (gjk/mod.rs:204, no cap) hit iter_cap, or a HalfEdge
+                                   polyhedron's hill climb met a NaN direction
+                                   (polyhedron.rs:184-206 loops while best_dot != previous) */
     CB2_PANIC_EPA_EMPTY = 6,    /* Polytope::closest_face_to_origin indexes
                                    faces[0] of an empty Vec, epa/epa3d.rs:138    */
     CB2_SCRATCH_OVERFLOW = 7,   /* device EPA scratch exhausted (non-manifold horizon
@@ -79,7 +81,13 @@ typedef enum cb2_shape_kind {
     CB2_QUAD = 4,       /* p[0..2] = dim x, y (in the z = 0 plane)  (quad.rs:24-57)  */
     CB2_CYLINDER = 5,   /* p[0] = half_height, p[1] = radius (axis y) (cylinder.rs:21-36) */
     CB2_CAPSULE = 6,    /* p[0] = half_height, p[1] = radius (axis y) (capsule.rs:22-37)  */
-    CB2_CUBE = 7        /* p[0] = dim: Cuboid::new(dim, dim, dim)   (cuboid.rs:144-158)  */
+    CB2_CUBE = 7,       /* p[0] = dim: Cuboid::new(dim, dim, dim)   (cuboid.rs:144-158)  */
+    CB2_POLYHEDRON_HE = 8 /* ConvexPolyhedron::new_with_faces (polyhedron.rs:124-139), HalfEdge
+                           mode: support_point is the reference's hill climb over the half-edge
+                           rings (:179-209), which can return a different vertex than the scan on
+                           ties.  Vertices [vtx_off, +vtx_cnt); faces [f_off, +f_cnt) of the face
+                           table passed to cb2_shapes_upload_faces, with f_off / f_cnt stored as
+                           the uint32 BIT PATTERNS of p[0] / p[1].  Needs cb2_shapes_upload_faces. */
 } cb2_shape_kind;
 
 /* One entry of the shape table (24 B). */
@@ -151,6 +159,16 @@ int cb2_last_stage_ms(cb2_ctx* ctx, float* out4);
  * n_verts x 3 floats.  Host pointers; copied to the device.                      */
 int cb2_shapes_upload(cb2_ctx* ctx, const cb2_shape* shapes, uint32_t n_shapes,
                       const float* verts_xyz, uint64_t n_verts);
+/* Same, with a face table for CB2_POLYHEDRON_HE shapes: faces = n_faces x 3 vertex indices, local
+ * to the owning shape's vertex range, in the order given to ConvexPolyhedron::new_with_faces (the
+ * half-edge numbering, hence the hill climb's tie behaviour, depends on it).  The half-edge
+ * structure is built on the host exactly as build_half_edges does (polyhedron.rs:282-380).
+ * CB2_ERR_ARG where the reference would panic or misbehave at construction: a degenerate face
+ * (Plane::from_points(..).unwrap(), :306-311), an index out of range, a vertex ring that does not
+ * close (not a closed 2-manifold), a HalfEdge shape without faces.                              */
+int cb2_shapes_upload_faces(cb2_ctx* ctx, const cb2_shape* shapes, uint32_t n_shapes,
+                            const float* verts_xyz, uint64_t n_verts, const uint32_t* faces,
+                            uint64_t n_faces);
 
 /* ---- narrow phase, HOST buffers (H2D, kernels, D2H inside the call) -----------
  * out / status hold n records; out[i] is valid only where status[i] == CB2_SOME.

@@ -152,6 +152,16 @@ class Oracle:
         b = np.asarray(b, np.float32).reshape(6)
         return bool(self.lib.orc_aabb3_intersects(_p(a), _p(b)))
 
+    def build_half_edges(self, shapes, verts, faces):
+        """ConvexPolyhedron::new_with_faces for every kind-8 shape (call before any batch that
+        uses them). faces: (F, 3) uint32, vertex indices local to the owning shape."""
+        faces = np.ascontiguousarray(faces, np.uint32)
+        self._faces = faces  # keep alive
+        rc = self.lib.orc_build_half_edges(_p(shapes), C.c_uint32(len(shapes)), _p(verts),
+                                           C.c_uint64(0 if verts is None else len(verts)), _p(faces))
+        if rc != 0:
+            raise ValueError("half-edge construction failed (degenerate face / open ring)")
+
     # ---- batch ---------------------------------------------------------------------
     def intersection(self, strategy, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None,
                      nthreads=1, want_stats=False):

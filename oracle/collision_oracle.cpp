@@ -38,6 +38,7 @@
 #include <cstring>
 #include <limits>
 #include <thread>
+#include <map>
 #include <vector>
 
 #include "../include/collision_b200.h"
@@ -171,7 +172,19 @@ struct Shape {
     V3 p;                 // Sphere: p.x = radius; Cuboid: dim
     const float* verts;   // polyhedron vertices (xyz interleaved)
     uint32_t nverts;
+    uint32_t voff;        // first vertex in the global table (HalfEdge ring lookup)
 };
+
+// HalfEdge polyhedra (ConvexPolyhedron::new_with_faces): the half-edge structure of every such
+// shape, built once by orc_build_half_edges exactly as build_half_edges does (polyhedron.rs:
+// 282-380).  Only what hill_climb_support_point reads is kept: per vertex its `edge`, per edge
+// its target_vertex / twin_edge / next_edge.  Indexed by the GLOBAL vertex number.
+struct HalfEdges {
+    std::vector<uint32_t> vertex_edge;            // per global vertex: index into the shape's edges
+    std::vector<uint32_t> shape_edge_base;        // per global vertex: first edge of its shape
+    std::vector<uint32_t> target, twin, next;     // per edge (all shapes concatenated)
+};
+static HalfEdges g_he;
 
 static Shape load_shape(const cb2_shape& s, const float* verts_xyz) {
     Shape r;
@@ -179,6 +192,7 @@ static Shape load_shape(const cb2_shape& s, const float* verts_xyz) {
     r.p = V3(R(s.p[0]), R(s.p[1]), R(s.p[2]));
     r.verts = verts_xyz ? verts_xyz + 3ull * s.vtx_off : nullptr;
     r.nverts = s.vtx_cnt;
+    r.voff = s.vtx_off;
     return r;
 }
 
@@ -231,6 +245,32 @@ static V3 support_point(const Shape& s, V3 direction, const Xf& t) {
         }
         result.y = negative ? -s.p.x : s.p.x;
         return transform_point(t, result);
+    }
+    if (s.kind == CB2_POLYHEDRON_HE) {  // hill_climb_support_point, polyhedron.rs:179-209
+        auto pos = [&](uint32_t i) { return V3(R(s.verts[3 * i]), R(s.verts[3 * i + 1]), R(s.verts[3 * i + 2])); };
+        const uint32_t ebase = g_he.shape_edge_base[s.voff];
+        uint32_t best_index = 0;
+        R best_dot = dot(pos(0), d);
+        for (uint64_t guard = 0;; ++guard) {
+            // the dot strictly grows each round, so a climb makes fewer than nverts rounds; only
+            // a NaN best_dot (NaN != NaN) keeps the reference's loop alive forever
+            if (guard > (uint64_t)s.nverts + 1) throw Panic{CB2_NONCONVERGED};
+            const R previous_best_dot = best_dot;
+            uint32_t edge_index = g_he.vertex_edge[s.voff + best_index];
+            const uint32_t start_edge_index = edge_index;
+            for (;;) {
+                const uint32_t vertex_index = g_he.target[ebase + edge_index];
+                const R dt = dot(pos(vertex_index), d);
+                if (dt > best_dot) {
+                    best_index = vertex_index;
+                    best_dot = dt;
+                }
+                edge_index = g_he.next[ebase + g_he.twin[ebase + edge_index]];
+                if (start_edge_index == edge_index) break;
+            }
+            if (best_dot == previous_best_dot) break;
+        }
+        return transform_point(t, pos(best_index));
     }
     V3 best = zero3();  // P::origin()
     R best_dot = R(-std::numeric_limits<float>::infinity());
@@ -894,6 +934,89 @@ using namespace orc;
 extern "C" {
 
 int orc_hw_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+// build_half_edges (polyhedron.rs:282-380) for every CB2_POLYHEDRON_HE shape of the table; faces
+// hold vertex indices local to the shape; the shape's face range is (bits of p[0], bits of p[1]).
+// Returns 0, or -1 where the reference panics at construction (degenerate face) / a ring of the
+// structure does not close.
+int orc_build_half_edges(const cb2_shape* shapes, uint32_t n_shapes, const float* verts_xyz,
+                         uint64_t n_verts, const uint32_t* faces) {
+    g_he = HalfEdges();
+    g_he.vertex_edge.assign(n_verts, 0);
+    g_he.shape_edge_base.assign(n_verts, 0);
+    for (uint32_t si = 0; si < n_shapes; ++si) {
+        const cb2_shape& s = shapes[si];
+        if (s.kind != CB2_POLYHEDRON_HE) continue;
+        uint32_t f_off, f_cnt;
+        std::memcpy(&f_off, &s.p[0], 4);
+        std::memcpy(&f_cnt, &s.p[1], 4);
+        const uint32_t ebase = (uint32_t)g_he.target.size();
+        const uint32_t V = s.vtx_cnt;
+        if (V == 0 || f_cnt == 0) return -1;
+        std::vector<uint32_t> vedge(V, 0);
+        std::vector<char> vready(V, 0), eready;
+        std::map<std::pair<uint32_t, uint32_t>, uint32_t> edge_map;
+        std::vector<uint32_t> target, twin, next;
+        for (uint32_t f = 0; f < f_cnt; ++f) {
+            const uint32_t fv[3] = {faces[3 * (f_off + f)], faces[3 * (f_off + f) + 1],
+                                    faces[3 * (f_off + f) + 2]};
+            for (int k = 0; k < 3; ++k)
+                if (fv[k] >= V) return -1;
+            {   // Plane::from_points(a, b, c).unwrap(), plane.rs:78-95
+                const float* b0 = verts_xyz + 3ull * s.vtx_off;
+                V3 a = v3p(b0 + 3 * fv[0]), b = v3p(b0 + 3 * fv[1]), c = v3p(b0 + 3 * fv[2]);
+                V3 n = cross(b - a, c - a);
+                if (ulps_eq_zero(n)) return -1;
+            }
+            uint32_t face_edge[3] = {0, 0, 0};
+            for (int j = 0; j < 3; ++j) {
+                const int i = j == 0 ? 2 : j - 1;
+                const uint32_t v0 = fv[i], v1 = fv[j];
+                uint32_t e01, e10;
+                auto it = edge_map.find({v0, v1});
+                if (it != edge_map.end()) {
+                    e01 = it->second;
+                    e10 = twin[e01];
+                } else {
+                    e01 = (uint32_t)target.size();
+                    e10 = e01 + 1;
+                    target.push_back(v1); twin.push_back(e10); next.push_back(0); eready.push_back(0);
+                    target.push_back(v0); twin.push_back(e01); next.push_back(0); eready.push_back(0);
+                }
+                edge_map[{v0, v1}] = e01;
+                edge_map[{v1, v0}] = e10;
+                if (!eready[e01]) eready[e01] = 1;
+                if (!vready[v0]) {
+                    vedge[v0] = e01;
+                    vready[v0] = 1;
+                }
+                face_edge[i] = e01;
+            }
+            for (int j = 0; j < 3; ++j) {
+                const int i = j == 0 ? 2 : j - 1;
+                next[face_edge[i]] = face_edge[j];
+            }
+        }
+        // every ring the hill climb can walk must close (else the reference never returns)
+        const size_t E = target.size();
+        for (uint32_t v = 0; v < V; ++v) {
+            uint32_t e = vedge[v];
+            size_t steps = 0;
+            do {
+                e = next[twin[e]];
+                if (++steps > E) return -1;
+            } while (e != vedge[v]);
+        }
+        for (uint32_t v = 0; v < V; ++v) {
+            g_he.vertex_edge[s.vtx_off + v] = vedge[v];
+            g_he.shape_edge_base[s.vtx_off + v] = ebase;
+        }
+        g_he.target.insert(g_he.target.end(), target.begin(), target.end());
+        g_he.twin.insert(g_he.twin.end(), twin.begin(), twin.end());
+        g_he.next.insert(g_he.next.end(), next.begin(), next.end());
+    }
+    return 0;
+}
 
 // ---- unit-level hooks for the golden tests ---------------------------------------------
 void orc_support_point(const cb2_shape* shape, const float* verts_xyz, const cb2_xform* t,

@@ -42,6 +42,7 @@ pub const CB2_QUAD: u32 = 4;      // p = [dim.x, dim.y, _]
 pub const CB2_CYLINDER: u32 = 5;  // p = [half_height, radius, _]
 pub const CB2_CAPSULE: u32 = 6;   // p = [half_height, radius, _]
 pub const CB2_CUBE: u32 = 7;      // p = [dim, _, _]
+pub const CB2_POLYHEDRON_HE: u32 = 8; // new_with_faces; p[0], p[1] = f32::from_bits(face_off / face_cnt)
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -111,6 +112,10 @@ extern "C" {
 
     pub fn cb2_shapes_upload(ctx: *mut cb2_ctx, shapes: *const cb2_shape, n_shapes: u32,
                              verts_xyz: *const f32, n_verts: u64) -> c_int;
+
+    pub fn cb2_shapes_upload_faces(ctx: *mut cb2_ctx, shapes: *const cb2_shape, n_shapes: u32,
+                                   verts_xyz: *const f32, n_verts: u64, faces: *const u32,
+                                   n_faces: u64) -> c_int;
 
     pub fn cb2_gjk3_intersection(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
                                  l_shape: *const u32, r_shape: *const u32,

@@ -51,3 +51,12 @@ def aabb(mn, mx):
     a["min"] = mn
     a["max"] = mx
     return a
+
+
+def polyhedron_he(off, cnt, f_off, f_cnt):
+    """ConvexPolyhedron::new_with_faces (kind 8): the face range rides in p[0], p[1] as uint32
+    bit patterns (include/collision_b200.h)."""
+    s = shape(8, (0, 0, 0), off, cnt)
+    s["p"].view(np.uint32)[0, 0] = f_off
+    s["p"].view(np.uint32)[0, 1] = f_cnt
+    return s

@@ -591,3 +591,81 @@ def test_every_primitive3_variant(ctx, oracle):
     eb = oracle.world_aabbs(shapes, pv, l, lt, nthreads=8)
     gb = ctx.world_aabbs(l, lt)
     assert gb.tobytes() == eb.tobytes()
+
+
+# ---- HalfEdge polyhedra: ConvexPolyhedron::new_with_faces, hill-climb support ----------------------
+def _he_table(n_shapes, seed, sizes=(8, 20, 60, 150)):
+    """Random convex hulls given BOTH ways: shape 2k is HalfEdge mode (kind 8, oriented hull
+    triangles), shape 2k+1 the same vertices in VertexOnly mode."""
+    from test_oracle_golden import oriented_hull_faces
+    from helpers import polyhedron, polyhedron_he
+    rng = np.random.default_rng(seed)
+    shapes, verts, faces = [], [], []
+    voff = foff = 0
+    for k in range(n_shapes):
+        v = rng.standard_normal((sizes[k % len(sizes)], 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        v = (v * rng.uniform(0.5, 1.0, 3)).astype(np.float32)
+        f = oriented_hull_faces(v)
+        shapes.append(polyhedron_he(voff, len(v), foff, len(f)))
+        shapes.append(polyhedron(voff, len(v)))
+        verts.append(v)
+        faces.append(f)
+        voff += len(v)
+        foff += len(f)
+    return np.concatenate(shapes), np.concatenate(verts), np.concatenate(faces)
+
+
+def test_half_edge_polyhedra(ctx, oracle):
+    shapes, verts, faces = _he_table(24, seed=21)
+    prim = W.mixed_shapes(np.random.default_rng(2), 8)
+    shapes = np.concatenate([shapes, prim])
+    oracle.build_half_edges(shapes, verts, faces)
+    ctx.upload_shapes(shapes, verts, faces)
+    rng = np.random.default_rng(22)
+    n = 40_000
+    l = rng.integers(0, len(shapes), n).astype(np.uint32)
+    r = rng.integers(0, len(shapes), n).astype(np.uint32)
+    lt, rt = W.random_xforms(rng, n, 0.7), W.random_xforms(rng, n, 0.7)
+    lt["scale"][::6] = rng.uniform(0.5, 1.5, len(lt["scale"][::6])).astype(np.float32)
+    for strategy in (0, 1):
+        exp, est = oracle.intersection(strategy, shapes, verts, l, r, lt, rt, nthreads=8)
+        got, gst = ctx.intersection(strategy, l, r, lt, rt)
+        assert_contacts_equal(got, gst, exp, est, f"HalfEdge polyhedra, strategy {strategy}")
+    assert (est == 1).sum() > 5000
+    ed, est = oracle.distance(shapes, verts, l, r, lt, rt, nthreads=8)
+    gd, gst = ctx.distance(l, r, lt, rt)
+    assert np.array_equal(gst, est) and bits_equal(gd[est == 1], ed[est == 1]).all()
+    eb = oracle.world_aabbs(shapes, verts, l, lt, nthreads=8)
+    assert ctx.world_aabbs(l, lt).tobytes() == eb.tobytes()
+
+
+def test_half_edge_nan_direction_is_a_hang(ctx, oracle):
+    """A NaN support direction makes the reference's hill climb spin forever (best_dot != previous
+    is always true for NaN): both sides must report status 5."""
+    shapes, verts, faces = _he_table(2, seed=5, sizes=(20,))
+    oracle.build_half_edges(shapes, verts, faces)
+    ctx.upload_shapes(shapes, verts, faces)
+    t = np.zeros(1, host_abi.XFORM_DT)
+    t["scale"] = 1
+    t["q"][:, 0] = 1
+    tn = t.copy()
+    tn["d"][0, 0] = np.nan  # NaN displacement -> NaN seed direction
+    l = np.array([0], np.uint32)
+    r = np.array([2], np.uint32)
+    exp, est = oracle.intersection(0, shapes, verts, l, r, t, tn)
+    got, gst = ctx.intersection(0, l, r, t, tn)
+    assert est[0] == 5 and gst[0] == 5
+    ed, est = oracle.distance(shapes, verts, l, r, t, tn)
+    gd, gst = ctx.distance(l, r, t, tn)
+    assert est[0] == gst[0]
+
+
+def test_half_edge_upload_errors(ctx):
+    from helpers import polyhedron_he
+    pts = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0, 1, 0]], np.float32)
+    faces = np.array([(0, 1, 2), (0, 1, 3), (1, 2, 3), (0, 2, 3)], np.uint32)  # collinear face
+    with pytest.raises(Cb2Error):
+        ctx.upload_shapes(polyhedron_he(0, 4, 0, 4), pts, faces)
+    with pytest.raises(Cb2Error):
+        ctx.upload_shapes(polyhedron_he(0, 4, 0, 4), pts)  # HalfEdge shape without a face table

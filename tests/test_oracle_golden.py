@@ -406,3 +406,63 @@ def test_cube_is_a_cuboid(oracle):
         a, _ = oracle.support_point(shape(7, (3.0, 0, 0)), None, transform_3d(1, 0, 0, 0.7), d)
         b, _ = oracle.support_point(cuboid(3, 3, 3), None, transform_3d(1, 0, 0, 0.7), d)
         assert np.array_equal(a, b)
+
+
+# ---- HalfEdge polyhedra: polyhedron.rs:604-660 (test_polytope_half_edge, test_polytope_bound) ----
+TETRA_FACES = np.array([(1, 3, 2), (3, 1, 0), (2, 0, 1), (0, 2, 3)], np.uint32)
+
+
+def test_polytope_half_edge(oracle):
+    from helpers import polyhedron_he
+    s = polyhedron_he(0, 4, 0, 4)
+    oracle.build_half_edges(s, TETRA, TETRA_FACES)
+    for d in ((1, 0, 0), (0, 1, 0)):
+        p, st = oracle.support_point(s, TETRA, IDENT, d)
+        assert st == 1 and tuple(p) == d
+        q, _ = oracle.support_point(polyhedron(0, 4), TETRA, IDENT, d)
+        assert tuple(q) == d
+    b = oracle.world_aabbs(s, TETRA, np.array([0], np.uint32), IDENT)
+    assert tuple(b[0]["min"]) == (0, 0, 0) and tuple(b[0]["max"]) == (1, 1, 1)
+
+
+def oriented_hull_faces(pts):
+    """Triangles of the convex hull, all wound counter-clockwise seen from outside (the half-edge
+    rings only close on a consistently oriented closed mesh)."""
+    from scipy.spatial import ConvexHull
+    hull = ConvexHull(np.asarray(pts, np.float64))
+    faces = hull.simplices.copy()
+    p = np.asarray(pts, np.float64)
+    n = np.cross(p[faces[:, 1]] - p[faces[:, 0]], p[faces[:, 2]] - p[faces[:, 0]])
+    flip = np.einsum("ij,ij->i", n, hull.equations[:, :3]) < 0
+    faces[flip] = faces[flip][:, [0, 2, 1]]
+    return faces.astype(np.uint32)
+
+
+def test_half_edge_hill_climb_vs_scan_on_random_hulls(oracle):
+    """The hill climb reaches the same DOT as the scan on a convex hull (it may stop on another
+    vertex when dots tie), and a NaN direction never returns in the reference -> status 5."""
+    from scipy.spatial import ConvexHull
+    from helpers import polyhedron_he
+    rng = np.random.default_rng(8)
+    pts = rng.standard_normal((60, 3))
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    pts = pts.astype(np.float32)
+    faces = oriented_hull_faces(pts)
+    s = polyhedron_he(0, len(pts), 0, len(faces))
+    oracle.build_half_edges(s, pts, faces)
+    for _ in range(300):
+        d = rng.standard_normal(3).astype(np.float32)
+        p, st = oracle.support_point(s, pts, IDENT, d)
+        q, _ = oracle.support_point(polyhedron(0, len(pts)), pts, IDENT, d)
+        assert st == 1
+        assert np.float32(np.dot(p, d)) == np.float32(np.dot(q, d)) or np.allclose(np.dot(p, d), np.dot(q, d), rtol=1e-6)
+    p, st = oracle.support_point(s, pts, IDENT, (np.nan, 0, 0))
+    assert st == 5
+
+
+def test_half_edge_rejects_degenerate_faces(oracle):
+    from helpers import polyhedron_he
+    pts = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0, 1, 0]], np.float32)
+    faces = np.array([(0, 1, 2), (0, 1, 3), (1, 2, 3), (0, 2, 3)], np.uint32)  # first face collinear
+    with pytest.raises(ValueError):
+        oracle.build_half_edges(polyhedron_he(0, 4, 0, 4), pts, faces)
