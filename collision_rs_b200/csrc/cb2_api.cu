@@ -27,8 +27,6 @@ struct cb2_ctx {
     // shape table
     dshape* d_shapes = nullptr;
     float4* d_verts = nullptr;
-    uint32_t* d_ring_off = nullptr;  // HalfEdge polyhedra: ring CSR (cb2_cells.cuh)
-    uint32_t* d_ring_idx = nullptr;
     uint4* d_cells = nullptr;        // support cells of all polyhedra (cb2_cells.cuh)
     uint16_t* d_cell_ext = nullptr;  // their extension pool
     uint32_t* d_cell_cursor = nullptr;
@@ -175,8 +173,6 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_cells) cudaFree(c->d_cells);
     if (c->d_cell_ext) cudaFree(c->d_cell_ext);
     if (c->d_cell_cursor) cudaFree(c->d_cell_cursor);
-    if (c->d_ring_off) cudaFree(c->d_ring_off);
-    if (c->d_ring_idx) cudaFree(c->d_ring_idx);
     if (c->d_misc) cudaFree(c->d_misc);
     if (c->d_comp_off) cudaFree(c->d_comp_off);
     if (c->d_comp_shape) cudaFree(c->d_comp_shape);
@@ -222,7 +218,7 @@ int cb2_last_stage_ms(cb2_ctx* c, float* out4) {
 
 // ConvexPolyhedron::new_with_faces: build_half_edges (polyhedron.rs:282-380) on the host, reduced
 // to what hill_climb_support_point reads: per vertex, the targets of its ring walk in walk order.
-// Appends to ring_idx and fills ring_off[voff + v .. ] with per-vertex counts (prefix-summed later).
+// Fills rings[voff + v] (and ring_cnt) for the vertices of shape s.
 static const char* build_rings(const cb2_shape& s, const float* verts_xyz, const uint32_t* faces,
                                uint64_t n_faces, std::vector<uint32_t>& ring_cnt,
                                std::vector<std::vector<uint32_t>>& rings) {
@@ -364,9 +360,29 @@ static int shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
         }
         hs[i] = d;
     }
+    // vertex table: float4 (x, y, z, w) with w = offset of the vertex's HalfEdge ring record (in
+    // uint32 units from the owning shape's first vertex); ring records [count, targets...] live
+    // behind the vertices in the same buffer (cb2_cells.cuh: poly_hill_climb)
     std::vector<float4> hv(n_verts);
     for (uint64_t i = 0; i < n_verts; ++i)
         hv[i] = make_float4(verts_xyz[3 * i], verts_xyz[3 * i + 1], verts_xyz[3 * i + 2], 0.0f);
+    std::vector<uint32_t> ring_data;
+    if (!rings.empty()) {
+        for (uint32_t i = 0; i < n_shapes; ++i) {
+            if (shapes[i].kind != CB2_POLYHEDRON_HE) continue;
+            const uint64_t v0 = shapes[i].vtx_off;
+            for (uint32_t k = 0; k < shapes[i].vtx_cnt; ++k) {
+                // uint32 index of this record, counted from the shape's first vertex
+                const uint64_t rel = (n_verts - v0) * 4 + ring_data.size();
+                if (rel > 0xFFFFFFFFull) return fail(c, CB2_ERR_ARG, "HalfEdge ring table exceeds 2^32 words");
+                const uint32_t rel32 = (uint32_t)rel;
+                std::memcpy(&hv[v0 + k].w, &rel32, 4);
+                const std::vector<uint32_t>& ring = rings[v0 + k];
+                ring_data.push_back((uint32_t)ring.size());
+                ring_data.insert(ring_data.end(), ring.begin(), ring.end());
+            }
+        }
+    }
     CK(c, cudaDeviceSynchronize());
     if (c->d_shapes) cudaFree(c->d_shapes);
     if (c->d_verts) cudaFree(c->d_verts);
@@ -377,30 +393,16 @@ static int shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
     c->d_cells = nullptr;
     c->d_cell_ext = nullptr;
     CK(c, cudaMalloc(&c->d_shapes, sizeof(dshape) * (n_shapes ? n_shapes : 1)));
-    CK(c, cudaMalloc(&c->d_verts, sizeof(float4) * (n_verts ? n_verts : 1)));
+    CK(c, cudaMalloc(&c->d_verts, sizeof(float4) * (n_verts ? n_verts : 1) + sizeof(uint32_t) * ring_data.size()));
     if (n_shapes)
         CK(c, cudaMemcpy(c->d_shapes, hs.data(), sizeof(dshape) * n_shapes, cudaMemcpyHostToDevice));
     if (n_verts)
         CK(c, cudaMemcpy(c->d_verts, hv.data(), sizeof(float4) * n_verts, cudaMemcpyHostToDevice));
+    if (!ring_data.empty())
+        CK(c, cudaMemcpy(reinterpret_cast<char*>(c->d_verts) + sizeof(float4) * n_verts, ring_data.data(),
+                         sizeof(uint32_t) * ring_data.size(), cudaMemcpyHostToDevice));
     c->n_shapes = n_shapes;
     c->n_verts = n_verts;
-    {   // HalfEdge ring CSR over the global vertex numbering (empty without HalfEdge shapes)
-        std::vector<uint32_t> off(n_verts + 1, 0), idx;
-        if (!ring_cnt.empty()) {
-            for (uint64_t v = 0; v < n_verts; ++v) {
-                off[v + 1] = off[v] + ring_cnt[v];
-                idx.insert(idx.end(), rings[v].begin(), rings[v].end());
-            }
-        }
-        if (c->d_ring_off) cudaFree(c->d_ring_off);
-        if (c->d_ring_idx) cudaFree(c->d_ring_idx);
-        c->d_ring_off = c->d_ring_idx = nullptr;
-        CK(c, cudaMalloc(&c->d_ring_off, sizeof(uint32_t) * off.size()));
-        CK(c, cudaMalloc(&c->d_ring_idx, sizeof(uint32_t) * (idx.empty() ? 1 : idx.size())));
-        CK(c, cudaMemcpy(c->d_ring_off, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice));
-        if (!idx.empty())
-            CK(c, cudaMemcpy(c->d_ring_idx, idx.data(), sizeof(uint32_t) * idx.size(), cudaMemcpyHostToDevice));
-    }
     // build the support cells on the device (one thread per cell)
     const uint64_t ext_cap64 = total_cells * 4 + (1u << 16);
     const uint32_t ext_cap = ext_cap64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ext_cap64;
@@ -507,8 +509,6 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
     A.T.verts = c->d_verts;
     A.T.cells = c->d_cells;
     A.T.ext = c->d_cell_ext;
-    A.T.ring_off = c->d_ring_off;
-    A.T.ring_idx = c->d_ring_idx;
     cudaError_t e;
     if (op == OP_INTERSECTION && !c->legacy_epa) {
         // GJK (thread per pair) -> compacted hit list -> cooperative EPA tiers
@@ -793,8 +793,6 @@ int cb2_world_aabbs_dev(cb2_ctx* c, const uint32_t* shape, const cb2_xform* t, u
     A.T.verts = c->d_verts;
     A.T.cells = c->d_cells;
     A.T.ext = c->d_cell_ext;
-    A.T.ring_off = c->d_ring_off;
-    A.T.ring_idx = c->d_ring_idx;
     A.shape = shape;
     A.t = reinterpret_cast<const float4*>(t);
     A.n = n;

@@ -47,15 +47,19 @@ CB2_DI uint32_t cell_index(f3 d, uint32_t N, float& m) {
     return (face * N + (uint32_t)iu) * N + (uint32_t)iv;
 }
 
-struct poly_ref {
-    const float4* verts;     // (x,y,z,0)
-    uint32_t vcnt;
-    uint32_t voff;           // first vertex in the global table (HalfEdge ring lookup)
-    const uint4* cells;      // this shape's 6*N*N records (nullptr when N == 0)
+// the table-wide base pointers (uniform across a launch: they stay in uniform registers / the
+// constant bank) ...
+struct poly_tables {
+    const float4* verts;     // (x, y, z, HalfEdge ring offset)
+    const uint4* cells;      // support-cell records of all polyhedra
     const uint16_t* ext;     // extension pool
-    uint32_t N;              // 0 => no cells
-    bool wide;               // u16 indices
-    float R;                 // max |vertex|, rounded up
+};
+// ... and the four words a thread keeps per polyhedron
+struct poly_ref {
+    uint32_t voff;           // first vertex in the table
+    uint32_t vcnt;
+    uint32_t cell_off;       // first cell record
+    uint32_t cfg;            // N | wide << 8 (N = 0: no cells)
 };
 
 // kept out of line: it is the rare path, and inlining it (three call sites) bloats the hot loops
@@ -91,26 +95,24 @@ static __device__ __noinline__ f3 poly_ext_scan(const float4* __restrict__ verts
 }
 
 // HalfEdge mode (ConvexPolyhedron::new_with_faces): hill_climb_support_point, polyhedron.rs:179-209.
-// ring_off / ring_idx hold, per vertex, the target vertices of the reference's ring walk
-// (edges[twin].next_edge from vertices[v].edge) in walk order.  Returns (point, hang): the
+// The ring of a vertex — the target vertices of the reference's walk edges[twin].next_edge from
+// vertices[v].edge, in walk order — is a record [count, t0, t1, ...] of uint32 stored behind the
+// vertex table; the vertex's own float4 carries its offset (in uint32 units from the shape's first
+// vertex) in .w, so the climb needs no pointer beyond `verts`.  Returns (point, hang): the
 // reference's loop `while best_dot != previous_best_dot` never ends once best_dot is NaN.
-static __device__ __noinline__ float4 poly_hill_climb(const float4* __restrict__ verts,
-                                                      const uint32_t* __restrict__ ring_off,
-                                                      const uint32_t* __restrict__ ring_idx,
-                                                      uint32_t vcnt, f3 d) {
-    uint32_t best = 0;
+static __device__ __noinline__ float4 poly_hill_climb(const float4* __restrict__ verts, uint32_t vcnt,
+                                                      f3 d) {
     float4 bv = __ldg(verts);
     float best_dot = dot(mk3(bv.x, bv.y, bv.z), d);
     // the dot strictly grows every round, so a climb takes fewer than vcnt rounds
     for (uint32_t round = 0; round <= vcnt; ++round) {
         const float previous = best_dot;
-        const uint32_t k1 = __ldg(ring_off + best + 1);
-        for (uint32_t k = __ldg(ring_off + best); k < k1; ++k) {
-            const uint32_t nb = __ldg(ring_idx + k);
-            const float4 v = __ldg(verts + nb);
+        const uint32_t* __restrict__ ring = reinterpret_cast<const uint32_t*>(verts) + __float_as_uint(bv.w);
+        const uint32_t cnt = __ldg(ring);
+        for (uint32_t k = 1; k <= cnt; ++k) {
+            const float4 v = __ldg(verts + __ldg(ring + k));
             const float dt = dot(mk3(v.x, v.y, v.z), d);
             if (dt > best_dot) {
-                best = nb;
                 best_dot = dt;
                 bv = v;
             }
@@ -120,21 +122,25 @@ static __device__ __noinline__ float4 poly_hill_climb(const float4* __restrict__
     return make_float4(bv.x, bv.y, bv.z, 1.0f);
 }
 
-// local-space support point of a polyhedron for direction d (already in model space)
-CB2_DI f3 poly_local_support(const poly_ref& s, f3 d) {
-    if (s.N == 0) return poly_full_scan(s.verts, s.vcnt, d);
+// local-space support point of a polyhedron for direction d (already in model space);
+// R = max |vertex| of the shape, rounded up
+CB2_DI f3 poly_local_support(const poly_tables& T, const poly_ref& s, float R, f3 d) {
+    const float4* __restrict__ verts = T.verts + s.voff;
+    const uint32_t N = s.cfg & 0xFFu;
+    const bool wide = (s.cfg >> 8) & 1u;
+    if (N == 0) return poly_full_scan(verts, s.vcnt, d);
     float m;
-    const uint32_t cell = cell_index(d, s.N, m);
-    const float scale = m * s.R;
+    const uint32_t cell = cell_index(d, N, m);
+    const float scale = m * R;
     // outside this window (or NaN) the rounding argument does not hold: full scan
-    if (!(scale >= 1.0e-30f && scale <= 1.0e30f)) return poly_full_scan(s.verts, s.vcnt, d);
-    const uint4 rec = __ldg(s.cells + cell);
-    const uint32_t bits = s.wide ? 16u : 8u;
-    const uint32_t mask = s.wide ? 0xFFFFu : 0xFFu;
+    if (!(scale >= 1.0e-30f && scale <= 1.0e30f)) return poly_full_scan(verts, s.vcnt, d);
+    const uint4 rec = __ldg(T.cells + s.cell_off + cell);
+    const uint32_t bits = wide ? 16u : 8u;
+    const uint32_t mask = wide ? 0xFFFFu : 0xFFu;
     const uint32_t cnt = rec.x & mask;
-    if (cnt > (s.wide ? CELL_INLINE16 : CELL_INLINE8)) {
-        if (cnt == (mask & (0xFF00u | CELL_FULL))) return poly_full_scan(s.verts, s.vcnt, d);
-        return poly_ext_scan(s.verts, s.ext + rec.y, rec.z, d);  // rec.y = pool offset, rec.z = count
+    if (cnt > (wide ? CELL_INLINE16 : CELL_INLINE8)) {
+        if (cnt == (mask & (0xFF00u | CELL_FULL))) return poly_full_scan(verts, s.vcnt, d);
+        return poly_ext_scan(verts, T.ext + rec.y, rec.z, d);  // rec.y = pool offset, rec.z = count
     }
     // The record is a 128-bit little-endian string [count | idx0 | idx1 | ...].  Drop the count,
     // then take FOUR candidates per round with their vertex loads issued back to back, so a
@@ -146,15 +152,15 @@ CB2_DI f3 poly_local_support(const poly_ref& s, f3 d) {
     float best_dot = -INFINITY;
     for (uint32_t base = 0; base < cnt; base += 4u) {
         uint32_t i0, i1, i2, i3;
-        if (!s.wide) {
+        if (!wide) {
             i0 = x & 0xFFu; i1 = (x >> 8) & 0xFFu; i2 = (x >> 16) & 0xFFu; i3 = x >> 24;
             x = y; y = z; z = w; w = 0u;
         } else {
             i0 = x & 0xFFFFu; i1 = x >> 16; i2 = y & 0xFFFFu; i3 = y >> 16;
             x = z; y = w; z = 0u; w = 0u;
         }
-        const float4 v0 = __ldg(s.verts + i0), v1 = __ldg(s.verts + i1);
-        const float4 v2 = __ldg(s.verts + i2), v3 = __ldg(s.verts + i3);
+        const float4 v0 = __ldg(verts + i0), v1 = __ldg(verts + i1);
+        const float4 v2 = __ldg(verts + i2), v3 = __ldg(verts + i3);
         const uint32_t rem = cnt - base;
         const float d0 = dot(mk3(v0.x, v0.y, v0.z), d), d1 = dot(mk3(v1.x, v1.y, v1.z), d);
         const float d2 = dot(mk3(v2.x, v2.y, v2.z), d), d3 = dot(mk3(v3.x, v3.y, v3.z), d);

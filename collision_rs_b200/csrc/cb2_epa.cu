@@ -44,11 +44,9 @@ namespace cb2 {
 CB2_DI shape_table table_of(const shape_table_args& a) {
     shape_table t;
     t.shapes = a.shapes;
-    t.verts = a.verts;
-    t.cells = a.cells;
-    t.ext = a.ext;
-    t.ring_off = a.ring_off;
-    t.ring_idx = a.ring_idx;
+    t.poly.verts = a.verts;
+    t.poly.cells = a.cells;
+    t.poly.ext = a.ext;
     return t;
 }
 
@@ -229,9 +227,8 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
     shape sh;
     sh.kind = K_CUBOID;
     sh.h = zero3();
-    sh.poly.verts = nullptr; sh.poly.vcnt = 0; sh.poly.cells = nullptr; sh.poly.ext = nullptr;
-    sh.poly.N = 0; sh.poly.wide = false; sh.poly.R = 0.f; sh.poly.voff = 0;
-    sh.ring_off = nullptr; sh.ring_idx = nullptr; sh.hang = 0u;
+    sh.poly.voff = 0; sh.poly.vcnt = 0; sh.poly.cell_off = 0; sh.poly.cfg = 0;
+    sh.hang = 0u;
     xform xf = make_xform(make_float4(1.f, 1.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
     f3 d = zero3();
     uint32_t it = 0;
@@ -338,7 +335,7 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
         // even lanes evaluate the left shape, odd lanes the right one
         f3 sup_v, sup_a;
         {
-            const f3 w = support_point(sh, xf, right ? -n : n);
+            const f3 w = support_point(T, sh, xf, right ? -n : n);
             const f3 o = mk3(__shfl_xor_sync(0xffffffffu, w.x, 1), __shfl_xor_sync(0xffffffffu, w.y, 1),
                              __shfl_xor_sync(0xffffffffu, w.z, 1));
             sup_a = right ? o : w;

@@ -43,20 +43,14 @@ struct __align__(16) dshape {
 // the device-resident shape table every narrow-phase kernel reads
 struct shape_table {
     const dshape* shapes;
-    const float4* verts;   // polyhedron vertices, (x,y,z,0)
-    const uint4* cells;    // support-cell records of all polyhedra
-    const uint16_t* ext;   // support-cell extension pool
-    const uint32_t* ring_off;  // HalfEdge polyhedra: per GLOBAL vertex, its ring in ring_idx
-    const uint32_t* ring_idx;  // ring targets (vertex indices local to the shape), walk order
+    poly_tables poly;      // vertices (+ HalfEdge ring records behind), support cells, extension pool
 };
 
 struct shape {
     uint32_t kind;
-    f3 h;
+    f3 h;                   // poly: h.x = R
     poly_ref poly;
-    const uint32_t* ring_off;  // ring_off + voff of this shape (HalfEdge mode only)
-    const uint32_t* ring_idx;
-    mutable uint32_t hang;     // set when a support call hit the reference's endless hill climb
+    mutable uint32_t hang;  // set when a support call hit the reference's endless hill climb
 };
 
 CB2_DI shape load_shape(const shape_table& T, uint32_t idx) {
@@ -66,18 +60,11 @@ CB2_DI shape load_shape(const shape_table& T, uint32_t idx) {
     shape s;
     s.kind = __float_as_uint(a.x);
     s.h = mk3(a.y, a.z, a.w);
-    s.poly.verts = T.verts + __float_as_uint(b.x);
-    s.poly.vcnt = __float_as_uint(b.y);
     s.poly.voff = __float_as_uint(b.x);
-    s.ring_off = T.ring_off + __float_as_uint(b.x);
-    s.ring_idx = T.ring_idx;
+    s.poly.vcnt = __float_as_uint(b.y);
+    s.poly.cell_off = __float_as_uint(b.z);
+    s.poly.cfg = __float_as_uint(b.w);
     s.hang = 0u;
-    s.poly.cells = T.cells + __float_as_uint(b.z);
-    s.poly.ext = T.ext;
-    const uint32_t cfg = __float_as_uint(b.w);
-    s.poly.N = cfg & 0xFFu;
-    s.poly.wide = (cfg >> 8) & 1u;
-    s.poly.R = a.y;
     return s;
 }
 
@@ -157,22 +144,22 @@ static __device__ __noinline__ f3 other_local_support(uint32_t kind, f3 h, f3 d)
 
 // Primitive3 dispatch (primitive3.rs:153-176); ConvexPolyhedron VertexOnly (polyhedron.rs:160-176)
 // goes through the support cells (cb2_cells.cuh)
-CB2_DI f3 local_support(const shape& s, f3 d) {
+CB2_DI f3 local_support(const shape_table& T, const shape& s, f3 d) {
     if (s.kind == K_CUBOID) return cuboid_local_support(s.h, d);
-    if (s.kind == K_POLY) return poly_local_support(s.poly, d);
+    if (s.kind == K_POLY) return poly_local_support(T.poly, s.poly, s.h.x, d);
     if (s.kind == K_SPHERE) return sphere_local_support(s.h.x, d);
     if (s.kind == K_POLY_HE) {
-        const float4 r = poly_hill_climb(s.poly.verts, s.ring_off, s.ring_idx, s.poly.vcnt, d);
+        const float4 r = poly_hill_climb(T.poly.verts + s.poly.voff, s.poly.vcnt, d);
         if (r.w != 0.0f) s.hang = 1u;
         return mk3(r.x, r.y, r.z);
     }
     return other_local_support(s.kind, s.h, d);
 }
 
-CB2_DI f3 support_point(const shape& s, const xform& t, f3 dir) {
+CB2_DI f3 support_point(const shape_table& T, const shape& s, const xform& t, f3 dir) {
     // Particle: transform.transform_point(origin) — no inverse transform (primitive3.rs:164)
     if (s.kind == K_PARTICLE) return transform_point(t, zero3());
-    return transform_point(t, local_support(s, inverse_transform_vector(t, dir)));
+    return transform_point(t, local_support(T, s, inverse_transform_vector(t, dir)));
 }
 // does support_point call inverse_transform_vector(..).unwrap() (the zero-scale panic site)?
 CB2_DI bool needs_inverse(uint32_t kind) { return kind != K_PARTICLE; }

@@ -12,11 +12,9 @@ struct dshape;
 // the device-resident shape table (mirrors cb2::shape_table in cb2_gjk.cuh)
 struct shape_table_args {
     const dshape* shapes;     // 32-byte entries
-    const float4* verts;      // polyhedron vertices, (x,y,z,0)
+    const float4* verts;      // polyhedron vertices (x,y,z,ring offset) + HalfEdge ring records
     const uint4* cells;       // support-cell records (cb2_cells.cuh)
     const uint16_t* ext;      // support-cell extension pool
-    const uint32_t* ring_off; // HalfEdge polyhedra: ring CSR over the global vertex numbering
-    const uint32_t* ring_idx;
 };
 
 // All pointers are device pointers.

@@ -18,23 +18,22 @@ namespace cb2 {
 CB2_DI shape_table table_of(const shape_table_args& a) {
     shape_table t;
     t.shapes = a.shapes;
-    t.verts = a.verts;
-    t.cells = a.cells;
-    t.ext = a.ext;
-    t.ring_off = a.ring_off;
-    t.ring_idx = a.ring_idx;
+    t.poly.verts = a.verts;
+    t.poly.cells = a.cells;
+    t.poly.ext = a.ext;
     return t;
 }
 
 struct pair_in {
+    shape_table T;  // launch-uniform base pointers
     shape ls, rs;
     xform lt, rt;
 };
 
 template <bool WITH_A>
 CB2_DI void minkowski(const pair_in& p, f3 dir, f3& v, f3& a) {
-    const f3 l = support_point(p.ls, p.lt, dir);
-    const f3 r = support_point(p.rs, p.rt, -dir);
+    const f3 l = support_point(p.T, p.ls, p.lt, dir);
+    const f3 r = support_point(p.T, p.rs, p.rt, -dir);
     v = l - r;
     if (WITH_A) a = l;
 }
@@ -239,8 +238,9 @@ CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const 
         li = __ldg(A.l_shape + i);
         ri = __ldg(A.r_shape + i);
     }
-    p.ls = load_shape(table_of(A.T), li);
-    p.rs = load_shape(table_of(A.T), ri);
+    p.T = table_of(A.T);
+    p.ls = load_shape(p.T, li);
+    p.rs = load_shape(p.T, ri);
     p.lt = load_xform(lt, lx);
     p.rt = load_xform(rt, rx);
     // inverse_transform_vector(..).unwrap() panics when ulps_eq(scale, 0); every entry point
@@ -284,8 +284,11 @@ __global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
 // terminal simplex to the cooperative EPA kernel (cb2_epa.cu) through a compacted work list.
 // Pairs with a Sphere go straight to the largest polytope tier (curved shapes run EPA to the
 // iteration cap: ~137 faces).
+#ifndef CB2_GJK_FULL_MINB
+#define CB2_GJK_FULL_MINB 4
+#endif
 template <bool FULL>
-__global__ void __launch_bounds__(128, 4) k_gjk_hits(narrow_args A, narrow_ws W) {
+__global__ void __launch_bounds__(128, FULL ? CB2_GJK_FULL_MINB : 4) k_gjk_hits(narrow_args A, narrow_ws W) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool hit = false, curved = false;
     if (i < A.n) {
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(256) k_world_aabbs(aabb_args A) {
         mn = zero3();
         mx = zero3();
         for (uint32_t k = 0; k < s.poly.vcnt; ++k) {
-            const float4 v = __ldg(s.poly.verts + k);
+            const float4 v = __ldg(A.T.verts + s.poly.voff + k);
             // grow(): Aabb::new(min(self.min,p), max(self.max,p)) then Aabb3::new re-sorts
             const f3 a = mk3(rmin(mn.x, v.x), rmin(mn.y, v.y), rmin(mn.z, v.z));
             const f3 b = mk3(rmax(mx.x, v.x), rmax(mx.y, v.y), rmax(mx.z, v.z));
