@@ -22,7 +22,7 @@
 //    edge occurs twice; the (non-manifold) exception is detected by the same atomicOr and the
 //    pair goes to the serial second-chance kernel (cb2_narrow.cu).
 //  * The polytope lives in per-group shared memory in three tiers: 40 faces / 24 vertices and
-//    72 / 40 (4 lanes per pair; ~86 % and ~99.5 % of pairs) and 208 / 104 (8 lanes per pair; the
+//    72 / 40 (4 and 8 lanes per pair; ~86 % and ~99.5 % of pairs) and 208 / 104 (8 lanes; the
 //    manifold worst case 2V-4 at the 100-iteration cap).  Small tiers buy residency: tier 0 runs
 //    20 warps per SM.  A pair that outgrows its tier dumps its polytope to global memory and the
 //    next tier RESUMES it at the same iteration (nothing is recomputed).  sup_a of each polytope
@@ -546,7 +546,10 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
 // ---- host side ----------------------------------------------------------------------------------------
 // tier:            G   faces  verts  examined/horizon cap
 constexpr int T0_G = 4, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O;
-constexpr int T1_G = 4, T1_F = 72, T1_V = 40, T1_O = 32;
+#ifndef CB2_T1_G
+#define CB2_T1_G 8
+#endif
+constexpr int T1_G = CB2_T1_G, T1_F = 72, T1_V = 40, T1_O = 32;
 constexpr int T2_G = 8, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
 
 template <int G, int F, int V, int O, int RF, int RV>
