@@ -745,6 +745,48 @@ int cb2_sap3_find_collider_pairs_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_
     return rc;
 }
 
+// BruteForce::find_collider_pairs (brute_force.rs:20-39): same pair SET as the sweep, reported in
+// the caller's own indices, left ascending then right ascending.
+int cb2_brute_force_find_collider_pairs_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n,
+                                            uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
+                                            void* stream) {
+    if (!c || !n_pairs) return fail(c, CB2_ERR_ARG, "null argument");
+    *n_pairs = 0;
+    if (n == 0) return CB2_OK;
+    if (!aabbs || (!pairs_out && cap)) return fail(c, CB2_ERR_ARG, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    const char* err = "";
+    int rc = sap_find_pairs(c->sap, aabbs, n, 0, nullptr, pairs_out, cap, n_pairs,
+                            static_cast<cudaStream_t>(stream), &c->launches, &err, true);
+    if (rc == CB2_ERR_NOSPC) c->err = "pairs_out too small; *n_pairs holds the required capacity";
+    else if (rc) c->err = err;
+    return rc;
+}
+
+int cb2_brute_force_find_collider_pairs(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n,
+                                        uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs) {
+    if (!c || !n_pairs) return fail(c, CB2_ERR_ARG, "null argument");
+    *n_pairs = 0;
+    if (n == 0) return CB2_OK;
+    if (!aabbs || (!pairs_out && cap)) return fail(c, CB2_ERR_ARG, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_box = 0, o_pairs = al(sizeof(cb2_aabb3) * n);
+    int rc = ensure_misc(c, o_pairs + al(8 * (cap ? cap : 1)));
+    if (rc) return rc;
+    char* base = static_cast<char*>(c->d_misc);
+    cudaStream_t st = c->stream[0];
+    CK(c, cudaMemcpyAsync(base + o_box, aabbs, sizeof(cb2_aabb3) * n, cudaMemcpyHostToDevice, st));
+    rc = cb2_brute_force_find_collider_pairs_dev(c, reinterpret_cast<cb2_aabb3*>(base + o_box), n,
+                                                 reinterpret_cast<uint32_t*>(base + o_pairs), cap,
+                                                 n_pairs, st);
+    if (rc) return rc;
+    if (*n_pairs)
+        CK(c, cudaMemcpyAsync(pairs_out, base + o_pairs, 8 * (*n_pairs), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return CB2_OK;
+}
+
 int cb2_sap3_find_collider_pairs(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n,
                                  uint32_t* axis_inout, uint32_t* perm_out, uint32_t* pairs_out,
                                  uint64_t cap, uint64_t* n_pairs) {

@@ -138,6 +138,6 @@ void sap_workspace_destroy(sap_workspace* w);
 // true pair count (pairs beyond cap are not written).  launches += kernels launched.
 int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
                    uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
-                   cudaStream_t st, uint64_t* launches, const char** err);
+                   cudaStream_t st, uint64_t* launches, const char** err, bool brute_force = false);
 
 }  // namespace cb2

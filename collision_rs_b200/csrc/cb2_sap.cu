@@ -351,21 +351,33 @@ __global__ void __launch_bounds__(256) k_grid_pack(const float2* __restrict__ S,
     eV[e] = __ldg(V + b);
 }
 
-// pair key = b << pos_bits | a: sorting it gives the reference's Vec order (b asc, then a asc)
+// SweepAndPrune: key = b << pos_bits | a over sorted positions a < b; sorting it gives the
+// reference's Vec order (b asc, then a asc).  BruteForce (remap = the sort permutation): the pair in
+// ORIGINAL indices lo < hi, key = lo << pos_bits | hi, i.e. (left asc, right asc) (brute_force.rs:28-35)
+__device__ __forceinline__ unsigned long long pair_key(uint32_t a, uint32_t b, int pos_bits,
+                                                       const uint32_t* __restrict__ remap) {
+    if (remap) {
+        const uint32_t x = __ldg(remap + a), y = __ldg(remap + b);
+        const uint32_t lo = x < y ? x : y, hi = x < y ? y : x;
+        return ((unsigned long long)lo << pos_bits) | hi;
+    }
+    return ((unsigned long long)b << pos_bits) | a;
+}
 __device__ __forceinline__ void emit_pair(grid_params* __restrict__ G, unsigned long long* __restrict__ keys,
-                                          uint64_t cap, int pos_bits, uint32_t a, uint32_t b) {
+                                          uint64_t cap, int pos_bits, uint32_t a, uint32_t b,
+                                          const uint32_t* __restrict__ remap) {
     const unsigned long long w = atomicAdd(&G->n_pairs, 1ull);
-    if (w < cap) keys[w] = ((unsigned long long)b << pos_bits) | a;
+    if (w < cap) keys[w] = pair_key(a, b, pos_bits, remap);
 }
 
 __global__ void __launch_bounds__(256) k_sap_unpack(const unsigned long long* __restrict__ keys,
-                                                   uint64_t np, int pos_bits,
+                                                   uint64_t np, int pos_bits, bool high_first,
                                                    uint32_t* __restrict__ pairs) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     const unsigned long long k = keys[p];
-    reinterpret_cast<uint2*>(pairs)[p] =
-        make_uint2((uint32_t)(k & ((1ull << pos_bits) - 1ull)), (uint32_t)(k >> pos_bits));
+    const uint32_t low = (uint32_t)(k & ((1ull << pos_bits) - 1ull)), high = (uint32_t)(k >> pos_bits);
+    reinterpret_cast<uint2*>(pairs)[p] = high_first ? make_uint2(high, low) : make_uint2(low, high);
 }
 
 __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ eS,
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
                                                    const uint32_t* __restrict__ epos, uint64_t n_entries,
                                                    grid_params* __restrict__ G,
                                                    unsigned long long* __restrict__ keys, uint64_t cap,
-                                                   int pos_bits) {
+                                                   int pos_bits, const uint32_t* __restrict__ remap) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const float org_u = G->org_u, inv_u = G->inv_u, org_v = G->org_v, inv_v = G->inv_v;
     const int nu = G->nu, nv = G->nv;
@@ -417,7 +429,7 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
                 if (pass == 0) {
                     ++mine;
                 } else {
-                    if (w < cap) keys[w] = ((unsigned long long)__ldg(epos + f) << pos_bits) | a;
+                    if (w < cap) keys[w] = pair_key(a, __ldg(epos + f), pos_bits, remap);
                     ++w;
                 }
             }
@@ -446,7 +458,7 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
                                                   const uint32_t* __restrict__ offs, uint64_t n_entries,
                                                   grid_params* __restrict__ G,
                                                   unsigned long long* __restrict__ keys, uint64_t cap,
-                                                  int pos_bits) {
+                                                  int pos_bits, const uint32_t* __restrict__ remap) {
     const uint32_t nl = G->n_large;
     for (uint32_t li = 0; li < nl; ++li) {
         const uint32_t p = __ldg(large_list + li);
@@ -458,13 +470,13 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
             if (!(ps.y > qs.x && ps.x < qs.y && pu.y > qu.x && pu.x < qu.y && pv.y > qv.x && pv.x < qv.y))
                 continue;
             if (q > p) {
-                emit_pair(G, keys, cap, pos_bits, p, (uint32_t)q);
+                emit_pair(G, keys, cap, pos_bits, p, (uint32_t)q, remap);
             } else {
                 // (q, p) with q < p: if q is large too, q's own forward pass reports it
                 const cell_range r = box_cells(G, qu, qv);
                 const int cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
                 if (cnt <= LARGE_CELLS && (uint64_t)__ldg(offs + q) + (uint64_t)cnt <= n_entries)
-                    emit_pair(G, keys, cap, pos_bits, (uint32_t)q, p);
+                    emit_pair(G, keys, cap, pos_bits, (uint32_t)q, p, remap);
             }
         }
     }
@@ -645,19 +657,21 @@ static int ensure_cap(sap_workspace* w, size_t bytes, const char** err) {
 
 int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
                    uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
-                   cudaStream_t st, uint64_t* launches, const char** err) {
+                   cudaStream_t st, uint64_t* launches, const char** err, bool brute_force) {
     {
         const char* e = std::getenv("CB2_SAP_LEGACY");
-        if (e && e[0] == '1')
+        if (e && e[0] == '1' && !brute_force)
             return sap_find_pairs_legacy(w, aabbs, n, axis, perm_out, pairs_out, cap, n_pairs, st,
                                          launches, err);
     }
     *n_pairs = 0;
     if (n == 0) return CB2_OK;
-    if (n <= 1) {  // sweep_prune.rs:83-85: nothing sorted
-        k_iota<<<nblk(n, 256), 256, 0, st>>>(perm_out, n);
-        ++*launches;
-        SAP_CK(cudaGetLastError());
+    if (n <= 1) {  // sweep_prune.rs:83-85: nothing sorted (brute_force.rs:22-24: no pairs)
+        if (!brute_force) {
+            k_iota<<<nblk(n, 256), 256, 0, st>>>(perm_out, n);
+            ++*launches;
+            SAP_CK(cudaGetLastError());
+        }
         return CB2_OK;
     }
     if (n > 0x7FFFFFFFull / (SLOT_CELLS + 1)) {
@@ -694,7 +708,7 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         const size_t o_S = take(8 * n), o_U = take(8 * n), o_V = take(8 * n);
         const size_t o_c0 = take(4 * ne), o_c1 = take(4 * ne), o_p0 = take(4 * ne), o_p1 = take(4 * ne);
         const size_t o_large = take(4 * n), o_G = take(sizeof(grid_params)), o_flag = take(256);
-        const size_t o_cnt = take(4 * n), o_offs = take(4 * n);
+        const size_t o_cnt = take(4 * n), o_offs = take(4 * n), o_perm = take(4 * n);
         const size_t o_eS = take(8 * ne), o_eU = take(8 * ne), o_eV = take(8 * ne);
         const size_t o_pk = take(8 * (kcap ? kcap : 1)), o_pk2 = take(8 * (kcap ? kcap : 1));
         size_t tmpsz = sort1 > sort2 ? sort1 : sort2;
@@ -719,6 +733,8 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         uint32_t* flag = (uint32_t*)(base + o_flag);
         uint32_t* cnts = (uint32_t*)(base + o_cnt);
         uint32_t* offs = (uint32_t*)(base + o_offs);
+        if (brute_force) perm_out = (uint32_t*)(base + o_perm);  // BruteForce keeps the caller's order
+        const uint32_t* remap = brute_force ? perm_out : nullptr;
         float2* eS = (float2*)(base + o_eS);
         float2* eU = (float2*)(base + o_eU);
         float2* eV = (float2*)(base + o_eV);
@@ -744,8 +760,8 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         tb = sort2;
         SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, p0, p1, (int64_t)ne, 0, cell_bits, st));
         k_grid_pack<<<nblk(ne, 256), 256, 0, st>>>(S, U, V, c1, p1, ne, G, eS, eU, eV);
-        k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, ne, G, pk, kcap, pos_bits);
-        k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, offs, ne, G, pk, kcap, pos_bits);
+        k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, ne, G, pk, kcap, pos_bits, remap);
+        k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, offs, ne, G, pk, kcap, pos_bits, remap);
         k_grid_total<<<1, 32, 0, st>>>(G, flag, w->h_total);
         *launches += 13;
         SAP_CK(cudaGetLastError());
@@ -765,7 +781,7 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         // sort the packed keys (b << pos_bits | a): the reference's Vec order, then unpack
         tb = sort3;
         SAP_CK(cub::DeviceRadixSort::SortKeys(tmp, tb, pk, pk2, (int64_t)np, 0, 2 * pos_bits, st));
-        k_sap_unpack<<<nblk(np, 256), 256, 0, st>>>(pk2, np, pos_bits, pairs_out);
+        k_sap_unpack<<<nblk(np, 256), 256, 0, st>>>(pk2, np, pos_bits, brute_force, pairs_out);
         *launches += 2;
         return CB2_OK;
     }

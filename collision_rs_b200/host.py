@@ -233,6 +233,23 @@ class Context:
             self._ck(rc)
             return perm[:n], pairs[:npairs.value], ax.value
 
+    def brute_force(self, aabbs, cap=None):
+        """BruteForce::find_collider_pairs (brute_force.rs:20-39): (left, right) in the caller's
+        indices, left ascending then right ascending."""
+        aabbs = np.ascontiguousarray(aabbs, AABB_DT)
+        n = len(aabbs)
+        cap = int(cap) if cap is not None else max(16, 8 * n)
+        while True:
+            pairs = np.zeros((max(cap, 1), 2), np.uint32)
+            npairs = C.c_uint64(0)
+            rc = self.lib.cb2_brute_force_find_collider_pairs(self.h, ptr(aabbs), n, ptr(pairs), cap,
+                                                              C.byref(npairs))
+            if rc == abi.ERR_NOSPC:
+                cap = int(npairs.value)
+                continue
+            self._ck(rc)
+            return pairs[:npairs.value]
+
     def sap3_dev(self, aabbs, n, axis, perm_out, pairs_out, cap, stream=0):
         npairs = C.c_uint64(0)
         rc = self.lib.cb2_sap3_find_collider_pairs_dev(self.h, aabbs, int(n), int(axis), perm_out,
@@ -437,6 +454,16 @@ class GJK3:
         if st[0] > 1:
             raise ReferencePanic(int(st[0]))
         return Contact.from_record(out[0]) if st[0] == 1 else None
+
+
+class BruteForce:
+    """algorithm/broad_phase/brute_force.rs:8-39"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def find_collider_pairs(self, aabbs):
+        return [tuple(int(x) for x in p) for p in self.ctx.brute_force(aabbs)]
 
 
 class SweepAndPrune3:

@@ -271,6 +271,17 @@ int cb2_sap3_find_collider_pairs_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint6
                                      uint32_t* pairs_out, uint64_t cap,
                                      uint64_t* n_pairs, void* stream);
 
+/* BruteForce::find_collider_pairs (algorithm/broad_phase/brute_force.rs:20-39): every (left, right),
+ * left < right in the CALLER's indices, whose boxes overlap strictly; order = left ascending, then
+ * right ascending.  Same machinery as the sweep (the O(n^2) double loop is not reproduced).
+ * NaN extents -> CB2_ERR_NAN.                                                                   */
+int cb2_brute_force_find_collider_pairs(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint64_t n,
+                                        uint32_t* pairs_out /* 2 x cap */, uint64_t cap,
+                                        uint64_t* n_pairs);
+int cb2_brute_force_find_collider_pairs_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint64_t n,
+                                            uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
+                                            void* stream);
+
 /* ---- world bounds (the step before the broad phase) -----------------------------
  * out[i] = shape.compute_bound().transform_volume(&t[i])
  * (ComputeBound: sphere.rs:41-51, cuboid.rs:82-92, polyhedron.rs:113-115,403-410;

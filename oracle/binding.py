@@ -51,6 +51,7 @@ class Oracle:
         self.lib = C.CDLL(os.path.join(_BUILD, name))
         self.lib.orc_sap3_find_collider_pairs.restype = C.c_uint64
         self.lib.orc_brute_force_count.restype = C.c_uint64
+        self.lib.orc_brute_force_pairs.restype = C.c_uint64
         self.lib.orc_ops_reset.restype = C.c_uint64
         self.lib.orc_closest_point_to_origin.restype = C.c_uint8
         self.lib.orc_epa3_process.restype = C.c_uint8
@@ -240,6 +241,13 @@ class Oracle:
 
     def brute_force_count(self, aabbs):
         return int(self.lib.orc_brute_force_count(_p(aabbs), C.c_uint64(len(aabbs))))
+
+    def brute_force_pairs(self, aabbs):
+        """BruteForce::find_collider_pairs (brute_force.rs:20-39)."""
+        n = int(self.lib.orc_brute_force_pairs(_p(aabbs), C.c_uint64(len(aabbs)), None, C.c_uint64(0)))
+        pairs = np.zeros((max(n, 1), 2), np.uint32)
+        self.lib.orc_brute_force_pairs(_p(aabbs), C.c_uint64(len(aabbs)), _p(pairs), C.c_uint64(n))
+        return pairs[:n]
 
     def ops_reset(self):
         return int(self.lib.orc_ops_reset())

@@ -1342,6 +1342,21 @@ uint64_t orc_brute_force_count(const cb2_aabb3* aabbs, uint64_t n) {
     return c;
 }
 
+// the pairs themselves, in the reference's order (left asc, right asc); returns the count
+uint64_t orc_brute_force_pairs(const cb2_aabb3* aabbs, uint64_t n, uint32_t* pairs, uint64_t cap) {
+    uint64_t c = 0;
+    for (uint64_t i = 0; i + 1 < n; ++i)
+        for (uint64_t j = i + 1; j < n; ++j)
+            if (aabb_intersects(aabbs[i].min, aabbs[j].min)) {
+                if (pairs && c < cap) {
+                    pairs[2 * c] = (uint32_t)i;
+                    pairs[2 * c + 1] = (uint32_t)j;
+                }
+                ++c;
+            }
+    return c;
+}
+
 // algorithmic flops of the last batch call on this thread (COUNT_OPS builds; single-thread)
 uint64_t orc_ops_reset(void) {
 #ifdef COUNT_OPS

@@ -175,6 +175,12 @@ extern "C" {
                                             axis: u32, perm_out: *mut u32, pairs_out: *mut u32,
                                             cap: u64, n_pairs: *mut u64, stream: *mut c_void) -> c_int;
 
+    pub fn cb2_brute_force_find_collider_pairs(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
+                                               pairs_out: *mut u32, cap: u64, n_pairs: *mut u64) -> c_int;
+    pub fn cb2_brute_force_find_collider_pairs_dev(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
+                                                   pairs_out: *mut u32, cap: u64, n_pairs: *mut u64,
+                                                   stream: *mut c_void) -> c_int;
+
     pub fn cb2_world_aabbs(ctx: *mut cb2_ctx, shape: *const u32, t: *const cb2_xform, n: u64,
                            out: *mut cb2_aabb3) -> c_int;
     pub fn cb2_world_aabbs_dev(ctx: *mut cb2_ctx, shape: *const u32, t: *const cb2_xform, n: u64,

@@ -669,3 +669,25 @@ def test_half_edge_upload_errors(ctx):
         ctx.upload_shapes(polyhedron_he(0, 4, 0, 4), pts, faces)
     with pytest.raises(Cb2Error):
         ctx.upload_shapes(polyhedron_he(0, 4, 0, 4), pts)  # HalfEdge shape without a face table
+
+
+def test_brute_force_broad_phase(ctx, oracle):
+    """BruteForce::find_collider_pairs (brute_force.rs:20-39): the O(n^2) double loop's pair list,
+    in the caller's indices and order, out of the grid machinery."""
+    rng = np.random.default_rng(17)
+    for n, extent in ((1, 5.0), (2, 1.0), (3000, 30.0)):
+        c = rng.uniform(0, extent, (n, 3)).astype(np.float32)
+        h = rng.uniform(0.2, 1.5, (n, 3)).astype(np.float32)
+        b = np.zeros(n, host_abi.AABB_DT)
+        b["min"], b["max"] = c - h, c + h
+        b["min"][::7] = np.round(b["min"][::7])  # ties and touching boxes
+        exp = oracle.brute_force_pairs(b)
+        got = ctx.brute_force(b)
+        assert got.shape == exp.shape and np.array_equal(got, exp)
+    # at scale: the same pair set as SweepAndPrune3 mapped back through its permutation
+    boxes = W.cfg4_aabbs(300_000, extent=200.0 * 0.3 ** (1 / 3))["aabbs"]
+    perm, pairs, _ = ctx.sap3(boxes)
+    orig = np.sort(perm[pairs.astype(np.int64)], axis=1)
+    key = np.lexsort((orig[:, 1], orig[:, 0]))
+    got = ctx.brute_force(boxes)
+    assert np.array_equal(got, orig[key])
