@@ -54,6 +54,7 @@ struct cb2_ctx {
     narrow_ws ws[NS] = {};
     uint64_t ws_cap[NS] = {0, 0};
     retry_ws retry[NS] = {};
+    uint32_t* d_queue[NS] = {nullptr, nullptr};  // work-queue cursors of the lane-refill kernels
     // optional stage timing (cb2_set_stage_timing): events around GJK | EPA tier 0 | EPA tier 1 |
     // second-chance, recorded on the launching stream of the LAST device-buffer intersection
     bool stage_timing = false;
@@ -180,6 +181,7 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_cx) cudaFree(c->d_cx);
     for (int i = 0; i < cb2_ctx::NS; ++i) {
         free_ws(c->ws[i]);
+        if (c->d_queue[i]) cudaFree(c->d_queue[i]);
         if (c->ws[i].EC) cudaFree(c->ws[i].EC);
         if (c->ws[i].pa) cudaFree(c->ws[i].pa);
         if (c->retry[i].list) cudaFree(c->retry[i].list);
@@ -536,9 +538,13 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
         }
         return CB2_OK;
     }
+    if (op != OP_INTERSECTION) {
+        if (!c->d_queue[ws_slot]) CK(c, cudaMalloc(&c->d_queue[ws_slot], 64));
+        A.queue = c->d_queue[ws_slot];
+    }
     if (op == OP_INTERSECTION) e = launch_intersection(A, strategy == CB2_FULL_RESOLUTION, st);
-    else if (op == OP_DISTANCE) e = launch_distance(A, st);
-    else e = launch_time_of_impact(A, st);
+    else if (op == OP_DISTANCE) e = launch_distance(A, c->sm_count, st);
+    else e = launch_time_of_impact(A, c->sm_count, st);
     ++c->launches;
     if (e != cudaSuccess) {
         c->err = std::string("kernel launch: ") + cudaGetErrorString(e);

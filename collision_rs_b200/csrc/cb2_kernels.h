@@ -30,6 +30,7 @@ struct narrow_args {
     const uint32_t* perm;       // optional: process pairs perm[0 .. *dev_count) (classified batches)
     const uint32_t* dev_count;
     uint64_t n;
+    uint32_t* queue;            // device work-queue cursor of the persistent (lane-refill) kernels
     cb2_settings settings;
     uint32_t iter_cap;
     cb2_contact* out_contact;
@@ -126,8 +127,8 @@ uint32_t cells_resolution(uint32_t vertex_count);
 cudaError_t build_support_cells(const dshape* d_shapes, const float4* d_verts, uint32_t n_shapes,
                                 uint32_t max_N, uint4* d_cells, uint16_t* d_ext, uint32_t ext_cap,
                                 uint32_t* d_ext_cursor, cudaStream_t st);
-cudaError_t launch_distance(const narrow_args& A, cudaStream_t st);
-cudaError_t launch_time_of_impact(const narrow_args& A, cudaStream_t st);
+cudaError_t launch_distance(const narrow_args& A, int sm_count, cudaStream_t st);
+cudaError_t launch_time_of_impact(const narrow_args& A, int sm_count, cudaStream_t st);
 cudaError_t launch_world_aabbs(const aabb_args& A, cudaStream_t st);
 
 // ---- broad phase (cb2_sap.cu) ---------------------------------------------------------------

@@ -10,6 +10,8 @@
 // is held in registers.  The EPA polytope (<= 104 vertices, <= 256 faces) is per-thread local
 // memory: the hardware interleaves local memory per lane, so a warp walking the face list in
 // lockstep reads 128-byte coalesced lines out of L1.
+#include <cstdlib>
+
 #include "cb2_gjk.cuh"
 #include "cb2_kernels.h"
 
@@ -463,6 +465,244 @@ __global__ void __launch_bounds__(128) k_time_of_impact(narrow_args A) {
     A.out_status[i] = st;
 }
 
+// ---- persistent thread-per-pair kernels with lane refill --------------------------------------------
+// GJK::distance runs 2..100 support evaluations per pair (Sphere-Cuboid pairs mostly to the cap) and
+// the time-of-impact loop 1..iter_cap; in a one-thread-per-pair grid a warp is as slow as its slowest
+// lane (~25 % lane utilisation on cfg 2; one never-converging pair in 500 holds its warp for 1024
+// rounds on cfg 5).  Here every loop round is exactly ONE Minkowski support per lane plus the
+// state's pre/post step, and a lane whose pair finished pulls the next pair from a device queue
+// (warp-aggregated atomic), so the lanes stay busy whatever their pairs' trip counts.
+CB2_DI bool refill_lane(const narrow_args& A, bool want, uint64_t& i) {
+    const unsigned need = __ballot_sync(0xffffffffu, want);
+    if (!need) return false;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == (unsigned)(__ffs(need) - 1)) base = atomicAdd(A.queue, (uint32_t)__popc(need));
+    base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+    i = (uint64_t)base + __popc(need & ((1u << lane) - 1u));
+    return want;
+}
+
+// GJK::distance, gjk/mod.rs:271-321
+__global__ void __launch_bounds__(128, 4) k_distance_p(narrow_args A) {
+    const uint32_t max_it = A.settings.max_iterations;
+    const float tol = A.settings.distance_tolerance;
+    bool active = false, done = false;
+    uint64_t i = 0;
+    pair_in p;
+    p.T = table_of(A.T);
+    simplex<false> s;
+    s.n = 0;
+    f3 d0 = zero3();
+    int state = 0;
+    uint32_t it = 0;
+    for (;;) {
+        // ---- refill ---------------------------------------------------------------------------------
+        uint64_t ni;
+        if (refill_lane(A, !active && !done, ni)) {
+            if (ni >= A.n) {
+                done = true;
+            } else {
+                i = ni;
+                if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+                    A.out_distance[i] = 0.0f;
+                    A.out_status[i] = ST_PANIC_INV_SCALE;
+                } else {
+                    d0 = seed_direction(p.lt, p.rt);
+                    s.n = 0;
+                    state = 0;
+                    active = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, done && !active)) break;
+        // ---- pre: the direction of this round's support ---------------------------------------------
+        bool go = active;
+        uint8_t st = ST_NONE;
+        float result = 0.0f;
+        f3 dir = zero3();
+        if (active) {
+            if (state == 0) {
+                dir = d0;
+            } else if (state == 1) {
+                dir = -d0;
+            } else if (it >= max_it) {
+                go = false;  // loop exhausted => None
+            } else {
+                uint8_t panic = 0;
+                const f3 d = closest_point_to_origin(s, panic);
+                if (panic) {
+                    st = panic;
+                    go = false;
+                } else if (ulps_eq_zero(d)) {
+                    go = false;  // None
+                } else {
+                    dir = -d;
+                }
+            }
+        }
+        // ---- one Minkowski support ---------------------------------------------------------------------
+        f3 v = zero3(), a;
+        if (go) minkowski<false>(p, dir, v, a);
+        // ---- post ---------------------------------------------------------------------------------------
+        bool finished = active && !go;
+        if (go) {
+            if (state < 2) {
+                s.push(v, a);
+                ++state;
+                it = 0;
+            } else {
+                const float dp = dot(v, dir);
+                const float dz = dot(s.v[0], dir);
+                if (fsub(dp, dz) < tol) {
+                    result = magnitude(dir);
+                    st = ST_SOME;
+                    finished = true;
+                } else {
+                    s.push(v, a);
+                    ++it;
+                }
+            }
+        }
+        if (finished) {
+            if (p.ls.hang | p.rs.hang) {
+                st = ST_NONCONVERGED;
+                result = 0.0f;
+            }
+            A.out_distance[i] = result;
+            A.out_status[i] = st;
+            active = false;
+        }
+    }
+}
+
+// GJK::intersection_time_of_impact, gjk/mod.rs:163-256 (+ iter_cap -> ST_NONCONVERGED)
+__global__ void __launch_bounds__(128, 4) k_time_of_impact_p(narrow_args A) {
+    const float tol = A.settings.continuous_tolerance;
+    bool active = false, done = false;
+    uint64_t i = 0;
+    pair_in p;
+    p.T = table_of(A.T);
+    simplex<false> s;
+    s.n = 0;
+    // right.end's rotation/scale and displacement (translation_interpolate, traits.rs:233-246)
+    quat r1q = {1.f, 0.f, 0.f, 0.f};
+    float r1scale = 1.f;
+    f3 r1disp = zero3();
+    f3 ray = zero3(), normal = zero3(), ray_origin = zero3(), v = zero3();
+    float lambda = 0.0f;
+    int state = 0;
+    uint32_t it = 0;
+    for (;;) {
+        uint64_t ni;
+        if (refill_lane(A, !active && !done, ni)) {
+            if (ni >= A.n) {
+                done = true;
+            } else {
+                i = ni;
+                if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+                    store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, zero_contact());
+                    A.out_status[i] = ST_PANIC_INV_SCALE;
+                } else {
+                    const xform lt1 = load_xform(A.l_t1, i);
+                    const xform rt1 = load_xform(A.r_t1, i);
+                    const f3 left_lin_vel = transform_point(lt1, zero3()) - transform_point(p.lt, zero3());
+                    const f3 right_lin_vel = transform_point(rt1, zero3()) - transform_point(p.rt, zero3());
+                    ray = right_lin_vel - left_lin_vel;
+                    r1q = rt1.q;
+                    r1scale = rt1.scale;
+                    r1disp = rt1.disp;
+                    lambda = 0.0f;
+                    normal = zero3();
+                    ray_origin = zero3();
+                    s.n = 0;
+                    it = 0;
+                    state = 0;
+                    active = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, done && !active)) break;
+        // ---- pre ---------------------------------------------------------------------------------------
+        bool go = active;
+        uint8_t st = ST_NONE;
+        contact_out c = zero_contact();
+        f3 dir = zero3();
+        if (active) {
+            if (state == 0) {
+                dir = -ray;
+            } else {
+                const float m2 = magnitude2(v);
+                if (!(m2 > tol)) {  // the while loop ends
+                    go = false;
+                    if (m2 <= tol) {
+                        xform t;
+                        t.q = r1q;
+                        t.scale = r1scale;
+                        t.unit = (r1scale == 1.0f);
+                        t.disp = lerp(p.rt.disp, r1disp, lambda);
+                        c.normal = -normalize(normal);
+                        c.depth = magnitude(v);
+                        c.point = transform_point(t, ray_origin);
+                        c.toi = lambda;
+                        st = ST_SOME;
+                    }
+                } else if (it >= A.iter_cap) {
+                    st = ST_NONCONVERGED;
+                    go = false;
+                } else {
+                    ++it;
+                    dir = -v;
+                }
+            }
+        }
+        // ---- one Minkowski support ---------------------------------------------------------------------
+        f3 pv = zero3(), a;
+        if (go) minkowski<false>(p, dir, pv, a);
+        // ---- post ---------------------------------------------------------------------------------------
+        bool finished = active && !go;
+        if (go) {
+            if (state == 0) {
+                v = pv;
+                state = 1;
+            } else {
+                const float vp = dot(v, pv);
+                const float vr = dot(v, ray);
+                if (vp > fmul(lambda, vr)) {
+                    if (vr > 0.0f) {
+                        lambda = fdiv(vp, vr);
+                        if (lambda > 1.0f) {
+                            finished = true;  // None
+                        } else {
+                            ray_origin = ray * lambda;
+                            s.n = 0;
+                            normal = -v;
+                        }
+                    } else {
+                        finished = true;  // None
+                    }
+                }
+                if (!finished) {
+                    s.push(pv - ray_origin, a);
+                    uint8_t panic = 0;
+                    v = closest_point_to_origin(s, panic);
+                    if (panic) {
+                        st = panic;
+                        finished = true;
+                    }
+                }
+            }
+        }
+        if (finished) {
+            if (p.ls.hang | p.rs.hang) st = ST_NONCONVERGED;
+            if (st != ST_SOME) c = zero_contact();
+            store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, c);
+            A.out_status[i] = st;
+            active = false;
+        }
+    }
+}
+
 // ---- second chance for ST_SCRATCH_OVERFLOW pairs ---------------------------------------------------
 // Collect the (few per million) pairs whose polytope outgrew the fast kernels' scratch and redo
 // them, one pair per block leader, over a large global scratch.  Same arithmetic, same order.
@@ -605,15 +845,39 @@ cudaError_t launch_overflow_retry(const narrow_args& A, const retry_ws& R, cudaS
     return cudaGetLastError();
 }
 
-cudaError_t launch_distance(const narrow_args& A, cudaStream_t st) {
-    if (A.n == 0) return cudaSuccess;
-    k_distance<<<grid_for(A.n, 128), 128, 0, st>>>(A);
+// persistent launch: as many blocks as fit, the pairs come from the device queue A.queue (zeroed here)
+template <class K>
+static cudaError_t launch_refill(K kern, const narrow_args& A, int sm_count, cudaStream_t st) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    cudaError_t e = cudaMemsetAsync(A.queue, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    uint64_t blocks = (uint64_t)per_sm * sm_count;
+    const uint64_t needed = (A.n + 127) / 128;
+    if (blocks > needed) blocks = needed;
+    kern<<<(unsigned)blocks, 128, 0, st>>>(A);
     return cudaGetLastError();
 }
-cudaError_t launch_time_of_impact(const narrow_args& A, cudaStream_t st) {
+static bool no_refill() {
+    static const bool v = [] { const char* e = std::getenv("CB2_NO_REFILL"); return e && e[0] == '1'; }();
+    return v;
+}
+cudaError_t launch_distance(const narrow_args& A, int sm_count, cudaStream_t st) {
     if (A.n == 0) return cudaSuccess;
-    k_time_of_impact<<<grid_for(A.n, 128), 128, 0, st>>>(A);
-    return cudaGetLastError();
+    if (no_refill() || !A.queue || A.n > 0xFFFFFF00ull) {
+        k_distance<<<grid_for(A.n, 128), 128, 0, st>>>(A);
+        return cudaGetLastError();
+    }
+    return launch_refill(k_distance_p, A, sm_count, st);
+}
+cudaError_t launch_time_of_impact(const narrow_args& A, int sm_count, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    if (no_refill() || !A.queue || A.n > 0xFFFFFF00ull) {
+        k_time_of_impact<<<grid_for(A.n, 128), 128, 0, st>>>(A);
+        return cudaGetLastError();
+    }
+    return launch_refill(k_time_of_impact_p, A, sm_count, st);
 }
 cudaError_t launch_world_aabbs(const aabb_args& A, cudaStream_t st) {
     if (A.n == 0) return cudaSuccess;
