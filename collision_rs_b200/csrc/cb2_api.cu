@@ -520,8 +520,10 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
         if (rc) return rc;
         const narrow_ws& W = c->ws[ws_slot];
         CK(c, cudaMemsetAsync(W.EC, 0, sizeof(epa_counters), st));
+        if (!c->d_queue[ws_slot]) CK(c, cudaMalloc(&c->d_queue[ws_slot], 64));
+        A.queue = c->d_queue[ws_slot];
         mark_stage(c, 0, st);
-        e = launch_gjk_hits(A, full, W, st);
+        e = launch_gjk_hits(A, full, W, c->sm_count, st);
         ++c->launches;
         mark_stage(c, 1, st);
         if (e == cudaSuccess && full) {

@@ -80,7 +80,8 @@ struct narrow_ws {                // per-stream device workspace, owned by the c
 };
 size_t epa_dump_record_bytes(int tier);
 size_t epa_pa_scratch_bytes(int sm_count);
-cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, cudaStream_t st);
+cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, int sm_count,
+                            cudaStream_t st);
 cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, int sm_count,
                             cudaStream_t st);
 

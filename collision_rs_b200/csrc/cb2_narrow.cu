@@ -483,6 +483,107 @@ CB2_DI bool refill_lane(const narrow_args& A, bool want, uint64_t& i) {
     return want;
 }
 
+// GJK::intersect (gjk/mod.rs:101-146) as the first stage of the GJK -> EPA pipeline, lane-refill form
+// of k_gjk_hits: misses exit after 1-2 supports, hits after ~4, so a refilled lane is worth ~2x.
+template <bool FULL>
+__global__ void __launch_bounds__(128, 4) k_gjk_hits_p(narrow_args A, narrow_ws W) {
+    const uint32_t max_it = A.settings.max_iterations;
+    bool active = false, done = false;
+    uint64_t i = 0;
+    pair_in p;
+    p.T = table_of(A.T);
+    simplex<FULL> s;
+    s.n = 0;
+    f3 d = zero3();
+    int state = 0;
+    uint32_t it = 0;
+    for (;;) {
+        uint64_t ni;
+        if (refill_lane(A, !active && !done, ni)) {
+            if (ni >= A.n) {
+                done = true;
+            } else {
+                i = ni;
+                if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+                    store_contact(A.out_contact, i, FULL ? CB2_FULL_RESOLUTION : CB2_COLLISION_ONLY,
+                                  zero_contact());
+                    A.out_status[i] = ST_PANIC_INV_SCALE;
+                } else {
+                    d = seed_direction(p.lt, p.rt);
+                    state = 0;
+                    active = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, done && !active)) break;
+        // ---- one Minkowski support, then the state's step ---------------------------------------------
+        f3 v = zero3(), a = zero3();
+        if (active) minkowski<FULL>(p, d, v, a);
+        bool finished = false, inside = false;
+        if (active) {
+            if (dot(v, d) <= 0.0f) {
+                finished = true;  // gjk/mod.rs:124, 132: no intersection
+            } else if (state == 0) {
+                s.n = 0;
+                s.push(v, a);
+                d = -d;
+                it = 0;
+                state = 1;
+                finished = max_it == 0;  // `for _ in 0..0` => None
+            } else {
+                s.push(v, a);
+                if (reduce_to_closest_feature(s, d)) {
+                    finished = true;
+                    inside = true;
+                } else {
+                    ++it;
+                    finished = it >= max_it;  // loop exhausted => None
+                }
+            }
+        }
+        bool hit = false, curved = false;
+        if (finished) {
+            uint8_t st = inside ? ST_SOME : ST_NONE;
+            if (p.ls.hang | p.rs.hang) st = ST_NONCONVERGED;  // the reference's hill climb never returned
+            if (FULL && st == ST_SOME) {
+                if constexpr (FULL) {
+                    hit = true;
+                    curved = is_curved(p.ls.kind) || is_curved(p.rs.kind);
+                    float4* o = W.simplex + i * 8;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        o[k] = make_float4(s.v[k].x, s.v[k].y, s.v[k].z, 0.f);
+                        o[4 + k] = make_float4(s.a[k].x, s.a[k].y, s.a[k].z, 0.f);
+                    }
+                }
+            } else {
+                store_contact(A.out_contact, i, FULL ? CB2_FULL_RESOLUTION : CB2_COLLISION_ONLY,
+                              zero_contact());
+                A.out_status[i] = st;
+            }
+            active = false;
+        }
+        if constexpr (FULL) {
+            // warp-aggregated append of this round's hits to the first / last tier's work list
+            const unsigned lane = threadIdx.x & 31u;
+            const unsigned m1 = __ballot_sync(0xffffffffu, hit && !curved);
+            const unsigned m3 = __ballot_sync(0xffffffffu, hit && curved);
+            if (m1 | m3) {
+                uint32_t b1 = 0, b3 = 0;
+                if (lane == 0) {
+                    if (m1) b1 = atomicAdd(&W.EC->n_list[0], __popc(m1));
+                    if (m3) b3 = atomicAdd(&W.EC->n_list[EPA_TIERS - 1], __popc(m3));
+                }
+                b1 = __shfl_sync(0xffffffffu, b1, 0);
+                b3 = __shfl_sync(0xffffffffu, b3, 0);
+                const unsigned below = (1u << lane) - 1u;
+                if (hit && !curved) W.list[0][b1 + __popc(m1 & below)] = (uint32_t)i;
+                if (hit && curved) W.list[EPA_TIERS - 1][b3 + __popc(m3 & below)] = (uint32_t)i;
+            }
+        }
+    }
+}
+
 // GJK::distance, gjk/mod.rs:271-321
 __global__ void __launch_bounds__(128, 4) k_distance_p(narrow_args A) {
     const uint32_t max_it = A.settings.max_iterations;
@@ -828,11 +929,31 @@ cudaError_t launch_intersection(const narrow_args& A, bool full, cudaStream_t st
     else k_intersection<false><<<grid_for(A.n, 128), 128, 0, st>>>(A);
     return cudaGetLastError();
 }
-cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, cudaStream_t st) {
-    if (A.n == 0) return cudaSuccess;
-    if (full) k_gjk_hits<true><<<grid_for(A.n, 128), 128, 0, st>>>(A, W);
-    else k_gjk_hits<false><<<grid_for(A.n, 128), 128, 0, st>>>(A, W);
+template <class K>
+static cudaError_t launch_refill2(K kern, const narrow_args& A, const narrow_ws& W, int sm_count,
+                                  cudaStream_t st) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    cudaError_t e = cudaMemsetAsync(A.queue, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    uint64_t blocks = (uint64_t)per_sm * sm_count;
+    const uint64_t needed = (A.n + 127) / 128;
+    if (blocks > needed) blocks = needed;
+    kern<<<(unsigned)blocks, 128, 0, st>>>(A, W);
     return cudaGetLastError();
+}
+static bool no_refill();
+cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, int sm_count,
+                            cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    if (no_refill() || !A.queue) {
+        if (full) k_gjk_hits<true><<<grid_for(A.n, 128), 128, 0, st>>>(A, W);
+        else k_gjk_hits<false><<<grid_for(A.n, 128), 128, 0, st>>>(A, W);
+        return cudaGetLastError();
+    }
+    if (full) return launch_refill2(k_gjk_hits_p<true>, A, W, sm_count, st);
+    return launch_refill2(k_gjk_hits_p<false>, A, W, sm_count, st);
 }
 size_t retry_scratch_bytes() { return (size_t)RETRY_BLOCKS * RETRY_BYTES_PER_BLOCK; }
 
