@@ -264,7 +264,11 @@ def main():
     per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
     clocks = sampler.stop() if sampler else None
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    per_rank_ms = [ms_total / a.steps]
     if world > 1:
+        allt = [torch.zeros_like(t_ms) for _ in range(world)]
+        dist.all_gather(allt, t_ms)
+        per_rank_ms = [float(x.item()) / a.steps for x in allt]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_total = float(t_ms.item())
     value = n * world * a.steps / (ms_total * 1e-3)
@@ -348,6 +352,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": n, "seed": 777,
                    "hit_fraction": hits / n, "non_ok_status": bad,
+                   "ms_per_step_per_rank": per_rank_ms,
                    "l2": "inputs+outputs 436 MB per step > 126 MB L2 (no flush needed)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
