@@ -753,6 +753,28 @@ int cb2_sap3_find_collider_pairs_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_
     return rc;
 }
 
+// SweepAndPrune2::find_collider_pairs (sweep_prune.rs:18, 76-136 with Variance2 :171-224): the 2-D
+// boxes are lifted to z in [0, 1] — the strict z test 1 > 0 && 0 < 1 always holds — and go through
+// the 3-D path; Variance2 discards its sums exactly like Variance3, so the next axis is 0 as well.
+int cb2_sap2_find_collider_pairs(cb2_ctx* c, const cb2_aabb2* aabbs, uint64_t n, uint32_t* axis_inout,
+                                 uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap,
+                                 uint64_t* n_pairs) {
+    if (!c || !axis_inout || !n_pairs) return fail(c, CB2_ERR_ARG, "null argument");
+    if (*axis_inout > 1) return fail(c, CB2_ERR_ARG, "sweep axis must be 0 or 1");
+    if (n && !aabbs) return fail(c, CB2_ERR_ARG, "null argument");
+    std::vector<cb2_aabb3> lifted(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        lifted[i].min[0] = aabbs[i].min[0];
+        lifted[i].min[1] = aabbs[i].min[1];
+        lifted[i].min[2] = 0.0f;
+        lifted[i].max[0] = aabbs[i].max[0];
+        lifted[i].max[1] = aabbs[i].max[1];
+        lifted[i].max[2] = 1.0f;
+    }
+    return cb2_sap3_find_collider_pairs(c, lifted.data(), n, axis_inout, perm_out, pairs_out, cap,
+                                        n_pairs);
+}
+
 // BruteForce::find_collider_pairs (brute_force.rs:20-39): same pair SET as the sweep, reported in
 // the caller's own indices, left ascending then right ascending.
 int cb2_brute_force_find_collider_pairs_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n,

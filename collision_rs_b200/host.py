@@ -233,6 +233,24 @@ class Context:
             self._ck(rc)
             return perm[:n], pairs[:npairs.value], ax.value
 
+    def sap2(self, aabbs2, axis=0, cap=None):
+        """SweepAndPrune2::find_collider_pairs; aabbs2: (n, 4) f32 rows (min.x, min.y, max.x, max.y)."""
+        b = np.ascontiguousarray(aabbs2, np.float32).reshape(-1, 4)
+        n = len(b)
+        perm = np.zeros(max(n, 1), np.uint32)
+        cap = int(cap) if cap is not None else max(16, 8 * n)
+        while True:
+            pairs = np.zeros((max(cap, 1), 2), np.uint32)
+            ax = C.c_uint32(axis)
+            npairs = C.c_uint64(0)
+            rc = self.lib.cb2_sap2_find_collider_pairs(self.h, ptr(b), n, C.byref(ax), ptr(perm),
+                                                       ptr(pairs), cap, C.byref(npairs))
+            if rc == abi.ERR_NOSPC:
+                cap = int(npairs.value)
+                continue
+            self._ck(rc)
+            return perm[:n], pairs[:npairs.value], ax.value
+
     def brute_force(self, aabbs, cap=None):
         """BruteForce::find_collider_pairs (brute_force.rs:20-39): (left, right) in the caller's
         indices, left ascending then right ascending."""

@@ -134,6 +134,12 @@ typedef struct cb2_aabb3 {
     float max[3];
 } cb2_aabb3;
 
+/* Aabb2<f32> (volume/aabb/aabb2.rs): min.xy, max.xy (16 B). */
+typedef struct cb2_aabb2 {
+    float min[2];
+    float max[2];
+} cb2_aabb2;
+
 typedef struct cb2_ctx cb2_ctx;
 
 /* ---- context ---------------------------------------------------------------- */
@@ -270,6 +276,13 @@ int cb2_sap3_find_collider_pairs_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint6
                                      uint32_t axis, uint32_t* perm_out,
                                      uint32_t* pairs_out, uint64_t cap,
                                      uint64_t* n_pairs, void* stream);
+
+/* SweepAndPrune2::find_collider_pairs (sweep_prune.rs:18,76-136; Variance2 :171-224): the 2-D alias
+ * of the same algorithm (the one the reference's own tests exercise, :317-361).  Same contract as
+ * cb2_sap3_find_collider_pairs with axis in {0, 1}.  Host buffers.                              */
+int cb2_sap2_find_collider_pairs(cb2_ctx* ctx, const cb2_aabb2* aabbs, uint64_t n,
+                                 uint32_t* axis_inout, uint32_t* perm_out,
+                                 uint32_t* pairs_out /* 2 x cap */, uint64_t cap, uint64_t* n_pairs);
 
 /* BruteForce::find_collider_pairs (algorithm/broad_phase/brute_force.rs:20-39): every (left, right),
  * left < right in the CALLER's indices, whose boxes overlap strictly; order = left ascending, then

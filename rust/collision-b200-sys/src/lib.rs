@@ -95,6 +95,13 @@ pub struct cb2_aabb3 {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct cb2_aabb2 {
+    pub min: [f32; 2],
+    pub max: [f32; 2],
+}
+
+#[repr(C)]
 pub struct cb2_ctx {
     _private: [u8; 0],
 }
@@ -175,6 +182,9 @@ extern "C" {
                                             axis: u32, perm_out: *mut u32, pairs_out: *mut u32,
                                             cap: u64, n_pairs: *mut u64, stream: *mut c_void) -> c_int;
 
+    pub fn cb2_sap2_find_collider_pairs(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb2, n: u64,
+                                        axis_inout: *mut u32, perm_out: *mut u32,
+                                        pairs_out: *mut u32, cap: u64, n_pairs: *mut u64) -> c_int;
     pub fn cb2_brute_force_find_collider_pairs(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
                                                pairs_out: *mut u32, cap: u64, n_pairs: *mut u64) -> c_int;
     pub fn cb2_brute_force_find_collider_pairs_dev(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,

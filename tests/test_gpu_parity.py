@@ -691,3 +691,32 @@ def test_brute_force_broad_phase(ctx, oracle):
     key = np.lexsort((orig[:, 1], orig[:, 0]))
     got = ctx.brute_force(boxes)
     assert np.array_equal(got, orig[key])
+
+
+def test_sweep_and_prune2(ctx, oracle):
+    """SweepAndPrune2 (the alias the reference's own tests use, sweep_prune.rs:317-361): the four
+    reference cases through cb2_sap2_find_collider_pairs, then random 2-D boxes against the 3-D
+    oracle on the lifted boxes."""
+    def run(boxes, axis=0):
+        perm, pairs, ax = ctx.sap2(np.asarray(boxes, np.float32), axis)
+        return [tuple(int(x) for x in p) for p in pairs], perm, ax
+
+    assert run([(8, 8, 10, 11), (12, 13, 18, 18)])[0] == []
+    assert run([(12, 13, 18, 18), (8, 8, 10, 11)])[0] == []
+    assert run([(8, 8, 10, 11), (9, 10, 18, 18)])[0] == [(0, 1)]
+    pairs, perm, ax = run([(9, 10, 18, 18), (8, 8, 10, 11)])
+    assert pairs == [(0, 1)] and ax == 0 and list(perm) == [1, 0]
+    rng = np.random.default_rng(4)
+    n = 20_000
+    c = rng.uniform(0, 150, (n, 2)).astype(np.float32)
+    h = rng.uniform(0.3, 1.5, (n, 2)).astype(np.float32)
+    b2 = np.concatenate([c - h, c + h], axis=1)
+    b3 = np.zeros(n, host_abi.AABB_DT)
+    b3["min"][:, :2], b3["max"][:, :2] = c - h, c + h
+    b3["max"][:, 2] = 1.0
+    for axis in (0, 1):
+        perm, pairs, ax = ctx.sap2(b2, axis)
+        perm_e, pairs_e, cnt, ax_e = oracle.sap3(b3, axis=axis)
+        assert np.array_equal(perm, perm_e) and np.array_equal(pairs, pairs_e) and ax == ax_e
+    with pytest.raises(Cb2Error):
+        ctx.sap2(b2, axis=2)
