@@ -1,7 +1,8 @@
 // cb2_api.cu — the extern "C" boundary declared in include/collision_b200.h.
 //
 // One ctx per GPU.  Host-buffer entry points stream the batch through the device in chunks on
-// two CUDA streams (H2D of chunk k+1 overlaps the kernel of chunk k and the D2H of chunk k-1;
+// four CUDA streams (H2D of later chunks overlaps the kernels of chunk k and the D2H of earlier
+// ones, and the low-occupancy tail of one chunk's EPA tiers overlaps the next chunk's kernels;
 // truly asynchronous when the caller's buffers are pinned).  Device-buffer entry points only
 // enqueue kernels on the caller's stream.  No CPU fallback anywhere.
 #include <cuda_runtime.h>
@@ -33,10 +34,13 @@ struct cb2_ctx {
     uint32_t n_shapes = 0;
     uint64_t n_verts = 0;
     // host-API staging
-    static constexpr int NS = 2;
-    cudaStream_t stream[NS] = {nullptr, nullptr};
-    cudaEvent_t done[NS] = {nullptr, nullptr};
-    char* d_stage[NS] = {nullptr, nullptr};
+#ifndef CB2_NS
+#define CB2_NS 4
+#endif
+    static constexpr int NS = CB2_NS;  // host-API pipeline depth (streams / staging buffers)
+    cudaStream_t stream[NS] = {};
+    cudaEvent_t done[NS] = {};
+    char* d_stage[NS] = {};
     size_t stage_cap = 0;
     sap_workspace* sap = nullptr;
     // composite table (cb2_composites_upload) and the composite-call workspace
@@ -52,9 +56,9 @@ struct cb2_ctx {
     // classified (polyhedron) narrow phase workspaces: [0..NS) follow the host-API streams,
     // device-API calls use ws[0] (one submitting stream at a time per ctx)
     narrow_ws ws[NS] = {};
-    uint64_t ws_cap[NS] = {0, 0};
+    uint64_t ws_cap[NS] = {};
     retry_ws retry[NS] = {};
-    uint32_t* d_queue[NS] = {nullptr, nullptr};  // work-queue cursors of the lane-refill kernels
+    uint32_t* d_queue[NS] = {};  // work-queue cursors of the lane-refill kernels
     // optional stage timing (cb2_set_stage_timing): events around GJK | EPA tier 0 | EPA tier 1 |
     // second-chance, recorded on the launching stream of the LAST device-buffer intersection
     bool stage_timing = false;

@@ -1,3 +1,4 @@
+"""End-to-end (host buffers) timing of cb2_gjk3_intersection on cfg 3 for a few chunk sizes."""
 import os, sys, time, ctypes as C
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
@@ -11,7 +12,7 @@ h_in = {k: pinned(w[k]) for k in ("l_shape", "r_shape", "l_t", "r_t")}
 h_out = torch.empty(n * CONTACT_DT.itemsize, dtype=torch.uint8).pin_memory()
 h_st = torch.empty(n, dtype=torch.uint8).pin_memory()
 S = Settings.default()
-for chunk in (1<<18, 1<<19, 1<<20, 1<<21, 1<<22):
+for chunk in [int(x) for x in sys.argv[1:]] or [1 << 19]:
     os.environ["CB2_CHUNK_PAIRS"] = str(chunk)
     from collision_rs_b200.host import Context
     ctx = Context(0)
@@ -20,13 +21,8 @@ for chunk in (1<<18, 1<<19, 1<<20, 1<<21, 1<<22):
         ctx._ck(ctx.lib.cb2_gjk3_intersection(ctx.h, 0, C.byref(S), h_in["l_shape"].data_ptr(), h_in["r_shape"].data_ptr(),
             h_in["l_t"].data_ptr(), h_in["r_t"].data_ptr(), n, h_out.data_ptr(), h_st.data_ptr()))
     step(); step()
-    t=time.perf_counter()
-    for _ in range(3): step()
-    dt=(time.perf_counter()-t)/3
-    print(f"chunk {chunk}: {dt*1e3:.1f} ms/step -> {n/dt/1e6:.1f} M pairs/s", flush=True)
+    t = time.perf_counter()
+    for _ in range(4): step()
+    dt = (time.perf_counter() - t) / 4
+    print(f"{os.environ.get('CB2_LIB_PATH','default').split('_')[-1]} chunk {chunk}: {dt*1e3:.1f} ms/step -> {n/dt/1e6:.1f} M pairs/s", flush=True)
     ctx.close()
-# raw PCIe
-d = torch.empty(288_000_000, dtype=torch.uint8, device="cuda")
-hbuf = torch.empty(288_000_000, dtype=torch.uint8).pin_memory()
-torch.cuda.synchronize(); t=time.perf_counter(); d.copy_(hbuf, non_blocking=True); torch.cuda.synchronize(); print("H2D GB/s", 0.288/(time.perf_counter()-t))
-t=time.perf_counter(); hbuf.copy_(d, non_blocking=True); torch.cuda.synchronize(); print("D2H GB/s", 0.288/(time.perf_counter()-t))
