@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=4_000_000, help="pairs per GPU per step")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs")
+    ap.add_argument("--shard", type=int, default=None,
+                    help="pair-stream shard to generate (default: the rank); diagnosis only")
     ap.add_argument("--cpu-sample", type=int, default=4_000_000,
                     help="pairs of the workload the CPU oracle port is timed on")
     return ap.parse_args()
@@ -165,7 +167,7 @@ def run_reference(a):
     v = m * a.steps / dt
     sample = (f"{m} pairs/step of the same workload (bounded sample of the 4M-pair batch), "
               f"oracle port on {threads} host threads")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -173,12 +175,27 @@ def run_reference(a):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 # ---------------------------------------------------------------------------------------------
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter)
+    was rerouted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    # keep stdout clean for the single JSON line: libraries (NCCL prints its version banner on
+    # stdout) write to fd 1, so fd 1 is pointed at stderr and the JSON goes to a saved copy
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         return run_reference(a)
 
@@ -202,7 +219,7 @@ def main():
 
     # ---- inputs: shape table from rank 0 over NCCL, pair shard per rank --------------------
     n = a.pairs
-    w = W.cfg3_polyhedron_pairs(n, shard=rank)
+    w = W.cfg3_polyhedron_pairs(n, shard=rank if a.shard is None else a.shard)
     shapes, verts = w["shapes"], w["verts"]
     if world > 1:
         # the shape / vertex tables travel once over NCCL (NVLink); every rank rebuilds its
@@ -362,7 +379,7 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
