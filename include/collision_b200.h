@@ -304,6 +304,96 @@ int cb2_world_aabbs(cb2_ctx* ctx, const uint32_t* shape, const cb2_xform* t, uin
 int cb2_world_aabbs_dev(cb2_ctx* ctx, const uint32_t* shape, const cb2_xform* t, uint64_t n,
                         cb2_aabb3* out, void* stream);
 
+/* ==== 2-D narrow phase: GJK2 (+EPA2) — SURVEY §8 row N4 ============================================
+ * The same generic GJK (gjk/mod.rs:101-391) instantiated with SimplexProcessor2
+ * (gjk/simplex/simplex2d.rs:17-97) and EPA2 (epa/epa2d.rs:21-157), specialised to
+ *     S = f32, P = Point2<f32>, T = Decomposed<Vector2<f32>, Basis2<f32>>,
+ *     shapes = Primitive2<f32>: Particle, Line, Circle, Rectangle, Square, ConvexPolygon.
+ * Status bytes as above; two panic sites exist only here:                                         */
+#define CB2_PANIC_EPA2_EDGE 9u    /* closest_edge: assert_ulps_ne!(inf, edge.distance) — no edge had
+                                     a distance below infinity (NaN simplex), epa/epa2d.rs:154      */
+#define CB2_PANIC_INV_ROT 10u     /* Basis2::invert = Matrix2::invert().unwrap() on a singular (or
+                                     non-finite-determinant-zero) rotation matrix (cgmath 0.18
+                                     rotation.rs; called by Decomposed::inverse_transform_vector)   */
+
+/* Primitive2 variants in declaration order (primitive/primitive2.rs:20-33). */
+typedef enum cb2_shape2_kind {
+    CB2_PARTICLE2 = 0, /* support = transform_point(origin)              (primitive2.rs:96)       */
+    CB2_LINE2 = 1,     /* p[0..2] = origin.xy, p[2..4] = dest.xy          (primitive/line.rs:7-26)  */
+    CB2_CIRCLE = 2,    /* p[0] = radius                                   (circle.rs:14-41)         */
+    CB2_RECTANGLE = 3, /* p[0..2] = dim (full extents)                    (rectangle.rs:18-77)      */
+    CB2_SQUARE = 4,    /* p[0] = dim: Rectangle::new(dim, dim)            (rectangle.rs:122-160)    */
+    CB2_POLYGON = 5    /* vertices [vtx_off, +vtx_cnt) of the 2-D vertex table: get_max_point scan
+                          below 10 vertices, the neighbour walk from 10 up (polygon.rs:26-43,122-190) */
+} cb2_shape2_kind;
+
+/* One entry of the 2-D shape table (32 B). */
+typedef struct cb2_shape2 {
+    uint32_t kind; /* cb2_shape2_kind */
+    float p[4];
+    uint32_t vtx_off;
+    uint32_t vtx_cnt;
+    uint32_t reserved; /* 0 */
+} cb2_shape2;
+
+/* cgmath Decomposed<Vector2<f32>, Basis2<f32>> flattened (32 B).  Basis2 wraps a column-major
+ * Matrix2: Rotation2::from_angle(t) = [c0 = (cos t, sin t), c1 = (-sin t, cos t)];
+ * transform_point(p) = mat * (p * scale) + disp.                                                 */
+typedef struct cb2_xform2 {
+    float scale;
+    float c0x, c0y, c1x, c1y;
+    float dx, dy;
+    float reserved; /* 0 */
+} cb2_xform2;
+
+/* Contact<Point2<f32>> (contact.rs:30-46), 28 B. */
+typedef struct cb2_contact2 {
+    uint32_t strategy; /* cb2_strategy */
+    float normal[2];
+    float penetration_depth;
+    float contact_point[2];
+    float time_of_impact;
+} cb2_contact2;
+
+/* Replaces constructing Circle::new / Rectangle::new / Square::new / ConvexPolygon::new /
+ * Line2::new values.  verts_xy is n_verts x 2 floats.  Host pointers; copied to the device.
+ * The 2-D table is independent of the 3-D one.                                                    */
+int cb2_shapes2_upload(cb2_ctx* ctx, const cb2_shape2* shapes, uint32_t n_shapes,
+                       const float* verts_xy, uint64_t n_verts);
+
+/* cb2_gjk2_intersection    replaces GJK2::intersection (gjk/mod.rs:362-391 -> EPA2::process)
+ * cb2_gjk2_distance        replaces GJK2::distance     (gjk/mod.rs:271-321)
+ * cb2_gjk2_time_of_impact  replaces GJK2::intersection_time_of_impact (gjk/mod.rs:163-256)
+ * Host buffers; same record/status contract as the 3-D entry points.                              */
+int cb2_gjk2_intersection(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                          const uint32_t* l_shape, const uint32_t* r_shape,
+                          const cb2_xform2* l_t, const cb2_xform2* r_t, uint64_t n,
+                          cb2_contact2* out, uint8_t* status);
+int cb2_gjk2_distance(cb2_ctx* ctx, const cb2_settings* settings,
+                      const uint32_t* l_shape, const uint32_t* r_shape,
+                      const cb2_xform2* l_t, const cb2_xform2* r_t, uint64_t n,
+                      float* out, uint8_t* status);
+int cb2_gjk2_time_of_impact(cb2_ctx* ctx, const cb2_settings* settings,
+                            const uint32_t* l_shape, const uint32_t* r_shape,
+                            const cb2_xform2* l_t0, const cb2_xform2* l_t1,
+                            const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
+                            uint32_t iter_cap, cb2_contact2* out, uint8_t* status);
+/* Device-pointer variants: enqueued on `stream`, not synchronised. */
+int cb2_gjk2_intersection_dev(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                              const uint32_t* l_shape, const uint32_t* r_shape,
+                              const cb2_xform2* l_t, const cb2_xform2* r_t, uint64_t n,
+                              cb2_contact2* out, uint8_t* status, void* stream);
+int cb2_gjk2_distance_dev(cb2_ctx* ctx, const cb2_settings* settings,
+                          const uint32_t* l_shape, const uint32_t* r_shape,
+                          const cb2_xform2* l_t, const cb2_xform2* r_t, uint64_t n,
+                          float* out, uint8_t* status, void* stream);
+int cb2_gjk2_time_of_impact_dev(cb2_ctx* ctx, const cb2_settings* settings,
+                                const uint32_t* l_shape, const uint32_t* r_shape,
+                                const cb2_xform2* l_t0, const cb2_xform2* l_t1,
+                                const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
+                                uint32_t iter_cap, cb2_contact2* out, uint8_t* status,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,8 +31,11 @@ class Settings(C.Structure):
 def build(force=False):
     """make -C oracle (gcc only). Building the checker is not using it."""
     out = os.path.join(_BUILD, "liboracle.so")
-    src = os.path.join(_HERE, "collision_oracle.cpp")
-    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+    stale = force
+    for lib, src in (("liboracle.so", "collision_oracle.cpp"), ("liboracle2d.so", "collision_oracle2d.cpp")):
+        o, c = os.path.join(_BUILD, lib), os.path.join(_HERE, src)
+        stale = stale or not os.path.exists(o) or os.path.getmtime(o) < os.path.getmtime(c)
+    if stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return out
 
@@ -251,3 +254,112 @@ class Oracle:
 
     def ops_reset(self):
         return int(self.lib.orc_ops_reset())
+
+
+# ---- 2-D narrow phase (oracle/collision_oracle2d.cpp) ------------------------------------------------
+SHAPE2_DT = np.dtype([("kind", "<u4"), ("p", "<f4", (4,)), ("vtx_off", "<u4"), ("vtx_cnt", "<u4"),
+                      ("reserved", "<u4")])
+XFORM2_DT = np.dtype([("scale", "<f4"), ("m", "<f4", (4,)), ("d", "<f4", (2,)), ("reserved", "<f4")])
+CONTACT2_DT = np.dtype([("strategy", "<u4"), ("normal", "<f4", (2,)), ("depth", "<f4"),
+                        ("point", "<f4", (2,)), ("toi", "<f4")])
+
+
+class Oracle2D:
+    """GJK2 / EPA2 restatement; same array contract as the cb2_gjk2_* entry points."""
+
+    def __init__(self):
+        build()
+        self.lib = C.CDLL(os.path.join(_BUILD, "liboracle2d.so"))
+        for f in ("orc2_closest_edge", "orc2_epa2_process", "orc2_gjk2_intersect"):
+            getattr(self.lib, f).restype = C.c_uint8
+
+    # unit hooks
+    def support_point(self, shape, verts, xform, direction):
+        out = np.zeros(2, np.float32)
+        st = C.c_uint8(0)
+        d = np.asarray(direction, np.float32)
+        self.lib.orc2_support_point(_p(shape), _p(verts), _p(xform), _p(d), _p(out), C.byref(st))
+        return out, st.value
+
+    def reduce_to_closest_feature(self, pts, d=(0, 0)):
+        buf = np.zeros((8, 2), np.float32)
+        pts = np.asarray(pts, np.float32).reshape(-1, 2)
+        buf[:len(pts)] = pts
+        n = C.c_uint32(len(pts))
+        dd = np.asarray(d, np.float32).copy()
+        hit = self.lib.orc2_reduce_to_closest_feature(_p(buf), C.byref(n), _p(dd))
+        return bool(hit), buf[:n.value].copy(), dd
+
+    def closest_point_to_origin(self, pts):
+        buf = np.zeros((8, 2), np.float32)
+        pts = np.asarray(pts, np.float32).reshape(-1, 2)
+        buf[:len(pts)] = pts
+        n = C.c_uint32(len(pts))
+        out = np.zeros(2, np.float32)
+        self.lib.orc2_closest_point_to_origin(_p(buf), C.byref(n), _p(out))
+        return out, buf[:n.value].copy()
+
+    def closest_point_on_edge(self, start, end, point):
+        out = np.zeros(2, np.float32)
+        self.lib.orc2_closest_point_on_edge(_p(np.asarray(start, np.float32)), _p(np.asarray(end, np.float32)),
+                                            _p(np.asarray(point, np.float32)), _p(out))
+        return out
+
+    def closest_edge(self, pts):
+        pts = np.ascontiguousarray(np.asarray(pts, np.float32).reshape(-1, 2))
+        out = np.zeros(3, np.float32)
+        idx = C.c_uint32(0)
+        st = self.lib.orc2_closest_edge(_p(pts), C.c_uint32(len(pts)), _p(out), C.byref(idx))
+        return st, out[:2].copy(), float(out[2]), idx.value
+
+    def epa2_process(self, simplex, l, lt, r, rt, verts=None, settings=None):
+        settings = settings or Settings.default()
+        pts = np.ascontiguousarray(np.asarray(simplex, np.float32).reshape(-1, 2))
+        out = np.zeros(1, CONTACT2_DT)
+        st = self.lib.orc2_epa2_process(_p(pts), C.c_uint32(len(pts)), _p(l), _p(lt), _p(r), _p(rt),
+                                        _p(verts), C.byref(settings), _p(out))
+        return st, out[0]
+
+    def gjk2_intersect(self, l, lt, r, rt, verts=None, settings=None):
+        settings = settings or Settings.default()
+        buf = np.zeros((8, 2), np.float32)
+        n = C.c_uint32(0)
+        st = self.lib.orc2_gjk2_intersect(_p(l), _p(lt), _p(r), _p(rt), _p(verts), C.byref(settings),
+                                          _p(buf), C.byref(n))
+        return st, buf[:n.value].copy()
+
+    # batches
+    def intersection(self, strategy, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None,
+                     nthreads=1, iters=False):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT2_DT)
+        status = np.zeros(n, np.uint8)
+        it = np.zeros((n, 2), np.uint32) if iters else None
+        self.lib.orc2_gjk2_intersection_batch(C.c_uint32(strategy), C.byref(settings), _p(shapes), _p(verts),
+                                              _p(l_shape), _p(r_shape), _p(l_t), _p(r_t), C.c_uint64(n),
+                                              _p(out), _p(status), _p(it), C.c_int(nthreads))
+        return (out, status, it) if iters else (out, status)
+
+    def distance(self, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None, nthreads=1, iters=False):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        it = np.zeros(n, np.uint32) if iters else None
+        self.lib.orc2_gjk2_distance_batch(C.byref(settings), _p(shapes), _p(verts), _p(l_shape), _p(r_shape),
+                                          _p(l_t), _p(r_t), C.c_uint64(n), _p(out), _p(status), _p(it),
+                                          C.c_int(nthreads))
+        return (out, status, it) if iters else (out, status)
+
+    def time_of_impact(self, shapes, verts, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, settings=None,
+                       iter_cap=0, nthreads=1, iters=False):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT2_DT)
+        status = np.zeros(n, np.uint8)
+        it = np.zeros(n, np.uint32) if iters else None
+        self.lib.orc2_gjk2_toi_batch(C.byref(settings), _p(shapes), _p(verts), _p(l_shape), _p(r_shape),
+                                     _p(l_t0), _p(l_t1), _p(r_t0), _p(r_t1), C.c_uint64(n),
+                                     C.c_uint32(iter_cap), _p(out), _p(status), _p(it), C.c_int(nthreads))
+        return (out, status, it) if iters else (out, status)

@@ -60,3 +60,51 @@ def polyhedron_he(off, cnt, f_off, f_cnt):
     s["p"].view(np.uint32)[0, 0] = f_off
     s["p"].view(np.uint32)[0, 1] = f_cnt
     return s
+
+
+# ---- 2-D fixtures (transform: gjk/mod.rs:600-606, epa2d.rs:271-277, circle.rs:187-193) ----------
+def shape2(kind, p=(0, 0, 0, 0), off=0, cnt=0):
+    from oracle.binding import SHAPE2_DT
+    s = np.zeros(1, SHAPE2_DT)
+    s["kind"] = kind
+    s["p"] = np.asarray(tuple(p) + (0,) * (4 - len(p)), np.float32)
+    s["vtx_off"] = off
+    s["vtx_cnt"] = cnt
+    return s
+
+
+def particle2():
+    return shape2(0)
+
+
+def line2(ox, oy, dx, dy):
+    return shape2(1, (ox, oy, dx, dy))
+
+
+def circle(r):
+    return shape2(2, (r,))
+
+
+def rectangle(x, y):
+    return shape2(3, (x, y))
+
+
+def square(d):
+    return shape2(4, (d,))
+
+
+def polygon(off, cnt):
+    return shape2(5, (), off, cnt)
+
+
+def transform_2d(x, y, angle=0.0, scale=1.0):
+    """Decomposed{disp:(x,y), rot: Rotation2::from_angle(Rad(angle)), scale}.
+    cgmath: Matrix2::from_angle(t) = Matrix2::new(cos, sin, -sin, cos) (column major), f32 libm."""
+    from oracle.binding import XFORM2_DT
+    a = np.float32(angle)
+    s, c = _libm.sinf(a), _libm.cosf(a)
+    t = np.zeros(1, XFORM2_DT)
+    t["scale"] = scale
+    t["m"] = (c, s, -s, c)
+    t["d"] = (x, y)
+    return t
