@@ -21,6 +21,15 @@ CONTACT_DT = np.dtype([("strategy", "<u4"), ("normal", "<f4", (3,)), ("depth", "
 AABB_DT = np.dtype([("min", "<f4", (3,)), ("max", "<f4", (3,))])
 assert SHAPE_DT.itemsize == 24 and XFORM_DT.itemsize == 32
 assert CONTACT_DT.itemsize == 36 and AABB_DT.itemsize == 24
+# 2-D narrow phase (cb2_shape2 / cb2_xform2 / cb2_contact2); m = Basis2 columns (c0x, c0y, c1x, c1y)
+SHAPE2_DT = np.dtype([("kind", "<u4"), ("p", "<f4", (4,)), ("vtx_off", "<u4"), ("vtx_cnt", "<u4"),
+                      ("reserved", "<u4")])
+XFORM2_DT = np.dtype([("scale", "<f4"), ("m", "<f4", (4,)), ("d", "<f4", (2,)), ("reserved", "<f4")])
+CONTACT2_DT = np.dtype([("strategy", "<u4"), ("normal", "<f4", (2,)), ("depth", "<f4"),
+                        ("point", "<f4", (2,)), ("toi", "<f4")])
+assert SHAPE2_DT.itemsize == 32 and XFORM2_DT.itemsize == 32 and CONTACT2_DT.itemsize == 28
+PARTICLE2, LINE2, CIRCLE, RECTANGLE, SQUARE, POLYGON = range(6)
+PANIC_EPA2_EDGE, PANIC_INV_ROT = 9, 10
 
 SPHERE, CUBOID, POLYHEDRON, PARTICLE, QUAD, CYLINDER, CAPSULE, CUBE, POLYHEDRON_HE = range(9)
 FULL_RESOLUTION, COLLISION_ONLY = 0, 1
@@ -54,6 +63,8 @@ SYMBOLS = [
     "cb2_sap2_find_collider_pairs",
     "cb2_brute_force_find_collider_pairs", "cb2_brute_force_find_collider_pairs_dev",
     "cb2_world_aabbs", "cb2_world_aabbs_dev",
+    "cb2_shapes2_upload", "cb2_gjk2_intersection", "cb2_gjk2_distance", "cb2_gjk2_time_of_impact",
+    "cb2_gjk2_intersection_dev", "cb2_gjk2_distance_dev", "cb2_gjk2_time_of_impact_dev",
 ]
 
 _lib = None
@@ -108,6 +119,13 @@ def load():
     lib.cb2_brute_force_find_collider_pairs_dev.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), vp]
     lib.cb2_world_aabbs.argtypes = [vp, vp, vp, u64, vp]
     lib.cb2_world_aabbs_dev.argtypes = [vp, vp, vp, u64, vp, vp]
+    lib.cb2_shapes2_upload.argtypes = [vp, vp, u32, vp, u64]
+    lib.cb2_gjk2_intersection.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_gjk2_distance.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_gjk2_time_of_impact.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp]
+    lib.cb2_gjk2_intersection_dev.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp, vp]
+    lib.cb2_gjk2_distance_dev.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp, vp]
+    lib.cb2_gjk2_time_of_impact_dev.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp]
     _lib = lib
     return lib
 

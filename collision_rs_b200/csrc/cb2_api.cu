@@ -20,6 +20,7 @@
 
 using namespace cb2;
 
+#define CB2_NS_MAX 8
 struct cb2_ctx {
     int device = 0;
     int sm_count = 0;
@@ -33,6 +34,15 @@ struct cb2_ctx {
     uint32_t* d_cell_cursor = nullptr;
     uint32_t n_shapes = 0;
     uint64_t n_verts = 0;
+    // 2-D shape table (cb2_shapes2_upload), independent of the 3-D one
+    cb2_shape2* d_shapes2 = nullptr;
+    float* d_verts2 = nullptr;
+    uint32_t n_shapes2 = 0;
+    // GJK2 -> EPA2 hand-off, one per host-API stream (device-API calls use slot 0)
+    uint32_t* d_cnt2[CB2_NS_MAX] = {};
+    uint32_t* d_hits2[CB2_NS_MAX] = {};
+    void* d_sx2[CB2_NS_MAX] = {};
+    uint64_t ws2_cap[CB2_NS_MAX] = {};
     // host-API staging
 #ifndef CB2_NS
 #define CB2_NS 4
@@ -175,6 +185,13 @@ void cb2_destroy(cb2_ctx* c) {
     }
     if (c->d_shapes) cudaFree(c->d_shapes);
     if (c->d_verts) cudaFree(c->d_verts);
+    if (c->d_shapes2) cudaFree(c->d_shapes2);
+    if (c->d_verts2) cudaFree(c->d_verts2);
+    for (int i = 0; i < CB2_NS_MAX; ++i) {
+        if (c->d_cnt2[i]) cudaFree(c->d_cnt2[i]);
+        if (c->d_hits2[i]) cudaFree(c->d_hits2[i]);
+        if (c->d_sx2[i]) cudaFree(c->d_sx2[i]);
+    }
     if (c->d_cells) cudaFree(c->d_cells);
     if (c->d_cell_ext) cudaFree(c->d_cell_ext);
     if (c->d_cell_cursor) cudaFree(c->d_cell_cursor);
@@ -1083,3 +1100,206 @@ int cb2_gjk3_time_of_impact_complex(cb2_ctx* c, uint32_t strategy, const cb2_set
                         iter_cap, out, nullptr, status);
 }
 }
+
+// ==== 2-D narrow phase: GJK2 / EPA2 (cb2_narrow2d.cu) ================================================
+static int narrow2_check(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings* settings,
+                         const void* l_shape, const void* r_shape, const void* l_t0, const void* l_t1,
+                         const void* r_t0, const void* r_t1, const void* out, const void* status) {
+    if (!c) return CB2_ERR_ARG;
+    int rc = check_settings(c, settings);
+    if (rc) return rc;
+    if (op == 0 && strategy > CB2_COLLISION_ONLY) return fail(c, CB2_ERR_ARG, "bad strategy");
+    if (!c->d_shapes2) return fail(c, CB2_ERR_ARG, "cb2_shapes2_upload has not been called");
+    if (!l_shape || !r_shape || !l_t0 || !r_t0 || !status || !out) return fail(c, CB2_ERR_ARG, "null argument");
+    if (op == 2 && (!l_t1 || !r_t1)) return fail(c, CB2_ERR_ARG, "null end transform");
+    return CB2_OK;
+}
+
+static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings* settings,
+                       const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t0,
+                       const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
+                       uint32_t iter_cap, cb2_contact2* out_c, float* out_d, uint8_t* status,
+                       cudaStream_t st, int slot = 0) {
+    narrow2_args A;
+    std::memset(&A, 0, sizeof(A));
+    const bool epa = op == 0 && strategy == CB2_FULL_RESOLUTION;
+    if (epa) {
+        if (!c->d_cnt2[slot]) CK(c, cudaMalloc(&c->d_cnt2[slot], 2 * sizeof(uint32_t)));
+        if (c->ws2_cap[slot] < n) {
+            if (c->d_hits2[slot]) cudaFree(c->d_hits2[slot]);
+            if (c->d_sx2[slot]) cudaFree(c->d_sx2[slot]);
+            c->d_hits2[slot] = nullptr;
+            c->d_sx2[slot] = nullptr;
+            c->ws2_cap[slot] = 0;
+            CK(c, cudaMalloc(&c->d_hits2[slot], n * sizeof(uint32_t)));
+            CK(c, cudaMalloc(&c->d_sx2[slot], n * 48));
+            c->ws2_cap[slot] = n;
+        }
+        A.counters = c->d_cnt2[slot];
+        A.hits = c->d_hits2[slot];
+        A.simplex = c->d_sx2[slot];
+    }
+    A.shapes = c->d_shapes2;
+    A.verts = c->d_verts2;
+    A.l_shape = l_shape;
+    A.r_shape = r_shape;
+    A.l_t = l_t0;
+    A.r_t = r_t0;
+    A.l_t1 = l_t1;
+    A.r_t1 = r_t1;
+    A.n = n;
+    A.settings = *settings;
+    A.iter_cap = iter_cap ? iter_cap : 1024u;
+    A.strategy = strategy;
+    A.out_contact = out_c;
+    A.out_distance = out_d;
+    A.out_status = status;
+    CK(c, launch_narrow2(op, A, c->sm_count, st));
+    c->launches += epa ? 2 : 1;
+    return CB2_OK;
+}
+
+// Host-buffer path: the same chunked multi-stream pipeline as narrow_host.
+static int narrow2_host(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings* settings,
+                        const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t0,
+                        const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1,
+                        uint64_t n, uint32_t iter_cap, cb2_contact2* out_c, float* out_d,
+                        uint8_t* status) {
+    int rc = narrow2_check(c, op, strategy, settings, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1,
+                           op == 1 ? (const void*)out_d : (const void*)out_c, status);
+    if (rc) return rc;
+    if (n == 0) return CB2_OK;
+    for (uint64_t i = 0; i < n; ++i)
+        if (l_shape[i] >= c->n_shapes2 || r_shape[i] >= c->n_shapes2)
+            return fail(c, CB2_ERR_ARG, "shape index out of range");
+    CK(c, cudaSetDevice(c->device));
+    const uint64_t chunk = n < c->chunk_pairs ? n : c->chunk_pairs;
+    const int n_xf = op == 2 ? 4 : 2;
+    const size_t out_rec = op == 1 ? sizeof(float) : sizeof(cb2_contact2);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t xf_bytes = al(chunk * sizeof(cb2_xform2));
+    const size_t o_ls = n_xf * xf_bytes;
+    const size_t o_rs = o_ls + al(chunk * 4);
+    const size_t o_out = o_rs + al(chunk * 4);
+    const size_t o_st = o_out + al(chunk * out_rec);
+    const size_t need = o_st + al(chunk);
+    if (c->stage_cap < need) {
+        for (int i = 0; i < cb2_ctx::NS; ++i) {
+            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+            c->d_stage[i] = nullptr;
+        }
+        c->stage_cap = 0;
+        for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaMalloc(&c->d_stage[i], need));
+        c->stage_cap = need;
+    }
+    const cb2_xform2* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
+    int k = 0;
+    for (uint64_t b = 0; b < n; b += chunk, ++k) {
+        const uint64_t m = (n - b < chunk) ? n - b : chunk;
+        const int s = k % cb2_ctx::NS;
+        cudaStream_t st = c->stream[s];
+        char* base = c->d_stage[s];
+        for (int x = 0; x < n_xf; ++x)
+            CK(c, cudaMemcpyAsync(base + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform2),
+                                  cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemcpyAsync(base + o_ls, l_shape + b, m * 4, cudaMemcpyHostToDevice, st));
+        CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
+        const cb2_xform2* X = reinterpret_cast<const cb2_xform2*>(base);
+        const size_t xs = xf_bytes / sizeof(cb2_xform2);
+        rc = narrow2_dev(c, op, strategy, settings, reinterpret_cast<const uint32_t*>(base + o_ls),
+                         reinterpret_cast<const uint32_t*>(base + o_rs), X, X + 2 * xs, X + xs, X + 3 * xs,
+                         m, iter_cap, reinterpret_cast<cb2_contact2*>(base + o_out),
+                         reinterpret_cast<float*>(base + o_out), reinterpret_cast<uint8_t*>(base + o_st), st, s);
+        if (rc) return rc;
+        if (op == 1)
+            CK(c, cudaMemcpyAsync(out_d + b, base + o_out, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+        else
+            CK(c, cudaMemcpyAsync(out_c + b, base + o_out, m * sizeof(cb2_contact2),
+                                  cudaMemcpyDeviceToHost, st));
+        CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaStreamSynchronize(c->stream[i]));
+    return CB2_OK;
+}
+
+extern "C" {
+
+int cb2_shapes2_upload(cb2_ctx* c, const cb2_shape2* shapes, uint32_t n_shapes, const float* verts_xy,
+                       uint64_t n_verts) {
+    if (!c) return CB2_ERR_ARG;
+    if (!shapes || n_shapes == 0) return fail(c, CB2_ERR_ARG, "empty shape table");
+    for (uint32_t i = 0; i < n_shapes; ++i) {
+        const cb2_shape2& s = shapes[i];
+        if (s.kind > CB2_POLYGON) return fail(c, CB2_ERR_ARG, "unknown 2-D shape kind");
+        if (s.kind == CB2_POLYGON) {
+            if ((uint64_t)s.vtx_off + s.vtx_cnt > n_verts || (s.vtx_cnt && !verts_xy))
+                return fail(c, CB2_ERR_ARG, "polygon vertex range out of bounds");
+        }
+    }
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaDeviceSynchronize());
+    if (c->d_shapes2) cudaFree(c->d_shapes2);
+    if (c->d_verts2) cudaFree(c->d_verts2);
+    c->d_shapes2 = nullptr;
+    c->d_verts2 = nullptr;
+    c->n_shapes2 = 0;
+    CK(c, cudaMalloc(&c->d_shapes2, sizeof(cb2_shape2) * n_shapes));
+    CK(c, cudaMemcpy(c->d_shapes2, shapes, sizeof(cb2_shape2) * n_shapes, cudaMemcpyHostToDevice));
+    // at least one (unused) vertex so polygon-free tables still have a valid pointer
+    CK(c, cudaMalloc(&c->d_verts2, sizeof(float) * 2 * (n_verts ? n_verts : 1)));
+    if (n_verts)
+        CK(c, cudaMemcpy(c->d_verts2, verts_xy, sizeof(float) * 2 * n_verts, cudaMemcpyHostToDevice));
+    c->n_shapes2 = n_shapes;
+    return CB2_OK;
+}
+
+int cb2_gjk2_intersection(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                          const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t,
+                          const cb2_xform2* r_t, uint64_t n, cb2_contact2* out, uint8_t* status) {
+    return narrow2_host(c, 0, strategy, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, n, 0, out,
+                        nullptr, status);
+}
+int cb2_gjk2_distance(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                      const uint32_t* r_shape, const cb2_xform2* l_t, const cb2_xform2* r_t, uint64_t n,
+                      float* out, uint8_t* status) {
+    return narrow2_host(c, 1, 0, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, n, 0, nullptr, out,
+                        status);
+}
+int cb2_gjk2_time_of_impact(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                            const uint32_t* r_shape, const cb2_xform2* l_t0, const cb2_xform2* l_t1,
+                            const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n, uint32_t iter_cap,
+                            cb2_contact2* out, uint8_t* status) {
+    return narrow2_host(c, 2, 0, settings, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, iter_cap, out,
+                        nullptr, status);
+}
+int cb2_gjk2_intersection_dev(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                              const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t,
+                              const cb2_xform2* r_t, uint64_t n, cb2_contact2* out, uint8_t* status,
+                              void* stream) {
+    int rc = narrow2_check(c, 0, strategy, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, out, status);
+    if (rc || n == 0) return rc;
+    CK(c, cudaSetDevice(c->device));
+    return narrow2_dev(c, 0, strategy, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, n, 0, out,
+                       nullptr, status, static_cast<cudaStream_t>(stream));
+}
+int cb2_gjk2_distance_dev(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                          const uint32_t* r_shape, const cb2_xform2* l_t, const cb2_xform2* r_t,
+                          uint64_t n, float* out, uint8_t* status, void* stream) {
+    int rc = narrow2_check(c, 1, 0, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, out, status);
+    if (rc || n == 0) return rc;
+    CK(c, cudaSetDevice(c->device));
+    return narrow2_dev(c, 1, 0, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, n, 0, nullptr, out,
+                       status, static_cast<cudaStream_t>(stream));
+}
+int cb2_gjk2_time_of_impact_dev(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                                const uint32_t* r_shape, const cb2_xform2* l_t0, const cb2_xform2* l_t1,
+                                const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
+                                uint32_t iter_cap, cb2_contact2* out, uint8_t* status, void* stream) {
+    int rc = narrow2_check(c, 2, 0, settings, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, out, status);
+    if (rc || n == 0) return rc;
+    CK(c, cudaSetDevice(c->device));
+    return narrow2_dev(c, 2, 0, settings, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, iter_cap, out,
+                       nullptr, status, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -142,4 +142,29 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
                    uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
                    cudaStream_t st, uint64_t* launches, const char** err, bool brute_force = false);
 
+// ---- 2-D narrow phase (cb2_narrow2d.cu): GJK2 / EPA2, one thread per pair -------------------------
+struct narrow2_args {           // all device pointers
+    const cb2_shape2* shapes;   // 32-byte entries
+    const float* verts;         // x,y pairs
+    const uint32_t* l_shape;
+    const uint32_t* r_shape;
+    const cb2_xform2* l_t;      // start poses for time of impact
+    const cb2_xform2* r_t;
+    const cb2_xform2* l_t1;     // end poses (time of impact only)
+    const cb2_xform2* r_t1;
+    uint64_t n;
+    cb2_settings settings;
+    uint32_t iter_cap;
+    uint32_t strategy;
+    cb2_contact2* out_contact;
+    float* out_distance;
+    uint8_t* out_status;
+    // GJK -> EPA2 hand-off workspace (FullResolution intersection only; owned by the ctx)
+    uint32_t* counters;  // 2 words
+    uint32_t* hits;      // n words
+    void* simplex;       // n x 48 bytes
+};
+// op: 0 intersection (k_gjk2_intersection [+ k_epa2]), 1 distance, 2 time of impact
+cudaError_t launch_narrow2(int op, const narrow2_args& A, int sm_count, cudaStream_t st);
+
 }  // namespace cb2

@@ -32,7 +32,9 @@ class ReferencePanic(RuntimeError):
                  5: "time-of-impact loop did not converge (gjk/mod.rs:204 has no cap)",
                  6: "faces[0] on an empty polytope (epa3d.rs:138)",
                  7: "device EPA scratch overflow",
-                 8: "max_by(partial_cmp(..).unwrap()) on a NaN depth (gjk/mod.rs:455-459)"}
+                 8: "max_by(partial_cmp(..).unwrap()) on a NaN depth (gjk/mod.rs:455-459)",
+                 9: "assert_ulps_ne!(inf, edge.distance) (epa2d.rs:154)",
+                 10: "Basis2::invert(): Matrix2::invert().unwrap() on a singular matrix"}
         super().__init__(names.get(status, f"status {status}"))
         self.status = status
 
@@ -99,6 +101,66 @@ class Context:
             self._ck(self.lib.cb2_shapes_upload_faces(self.h, ptr(shapes), len(shapes), ptr(verts),
                                                       nv, ptr(faces), len(faces)))
         self.n_shapes = len(shapes)
+
+    # ---- 2-D narrow phase (GJK2 / EPA2) ---------------------------------------------------
+    def upload_shapes2(self, shapes, verts=None):
+        shapes = np.ascontiguousarray(shapes, abi.SHAPE2_DT)
+        nv = 0
+        if verts is not None:
+            verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 2)
+            nv = len(verts)
+        self._ck(self.lib.cb2_shapes2_upload(self.h, ptr(shapes), len(shapes), ptr(verts), nv))
+        self.n_shapes2 = len(shapes)
+
+    def intersection2(self, strategy, l_shape, r_shape, l_t, r_t, settings=None):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, abi.CONTACT2_DT)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk2_intersection(
+            self.h, int(strategy), C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t),
+            ptr(r_t), n, ptr(out), ptr(status)))
+        return out, status
+
+    def distance2(self, l_shape, r_shape, l_t, r_t, settings=None):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk2_distance(
+            self.h, C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t), ptr(r_t), n,
+            ptr(out), ptr(status)))
+        return out, status
+
+    def time_of_impact2(self, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, settings=None,
+                        iter_cap=1024):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, abi.CONTACT2_DT)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk2_time_of_impact(
+            self.h, C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t0), ptr(l_t1),
+            ptr(r_t0), ptr(r_t1), n, int(iter_cap), ptr(out), ptr(status)))
+        return out, status
+
+    def intersection2_dev(self, strategy, l_shape, r_shape, l_t, r_t, n, out, status, stream=0,
+                          settings=None):
+        settings = settings or Settings.default()
+        self._ck(self.lib.cb2_gjk2_intersection_dev(
+            self.h, int(strategy), C.byref(settings), l_shape, r_shape, l_t, r_t, n, out, status,
+            stream))
+
+    def distance2_dev(self, l_shape, r_shape, l_t, r_t, n, out, status, stream=0, settings=None):
+        settings = settings or Settings.default()
+        self._ck(self.lib.cb2_gjk2_distance_dev(
+            self.h, C.byref(settings), l_shape, r_shape, l_t, r_t, n, out, status, stream))
+
+    def time_of_impact2_dev(self, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, out, status,
+                            stream=0, settings=None, iter_cap=1024):
+        settings = settings or Settings.default()
+        self._ck(self.lib.cb2_gjk2_time_of_impact_dev(
+            self.h, C.byref(settings), l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, int(iter_cap),
+            out, status, stream))
 
     # ---- narrow phase, host buffers --------------------------------------------------------
     def intersection(self, strategy, l_shape, r_shape, l_t, r_t, settings=None, out=None,
@@ -472,6 +534,173 @@ class GJK3:
         if st[0] > 1:
             raise ReferencePanic(int(st[0]))
         return Contact.from_record(out[0]) if st[0] == 1 else None
+
+
+# ---- 2-D mirror: Primitive2 (primitive/primitive2.rs:20-33), Decomposed<Vector2, Basis2>, GJK2 --------
+@dataclass
+class Particle2:
+    """primitive/particle.rs:39"""
+
+
+@dataclass
+class Line2:
+    """line.rs:21-28 as a Primitive (primitive/line.rs:7-26)"""
+    origin: tuple
+    dest: tuple
+
+
+@dataclass
+class Circle:
+    """primitive/circle.rs:14-24"""
+    radius: float
+
+
+@dataclass
+class Rectangle:
+    """primitive/rectangle.rs:18-42 (full extents)"""
+    x: float
+    y: float
+
+
+@dataclass
+class Square:
+    """primitive/rectangle.rs:122-134"""
+    dim: float
+
+
+class ConvexPolygon:
+    """primitive/polygon.rs:17-24: vertices in order around the polygon"""
+
+    def __init__(self, vertices):
+        self.vertices = np.ascontiguousarray(vertices, np.float32).reshape(-1, 2)
+
+
+@dataclass
+class Basis2:
+    """cgmath Basis2<f32>: a column-major Matrix2 (c0x, c0y, c1x, c1y)."""
+    mat: tuple = (1.0, 0.0, 0.0, 1.0)
+
+    @staticmethod
+    def from_angle(rad):
+        """Rotation2::from_angle(Rad(t)) = Matrix2::new(cos t, sin t, -sin t, cos t), in f32."""
+        s, c = np.sin(np.float32(rad), dtype=np.float32), np.cos(np.float32(rad), dtype=np.float32)
+        return Basis2((c, s, -s, c))
+
+
+@dataclass
+class Decomposed2:
+    """cgmath Decomposed<Vector2<f32>, Basis2<f32>>"""
+    disp: tuple = (0.0, 0.0)
+    rot: Basis2 = None
+    scale: float = 1.0
+
+    def record(self):
+        t = np.zeros(1, abi.XFORM2_DT)
+        t["scale"] = self.scale
+        t["m"] = (self.rot or Basis2()).mat
+        t["d"] = self.disp
+        return t
+
+
+def _shape_table2(prims):
+    shapes = np.zeros(len(prims), abi.SHAPE2_DT)
+    verts = []
+    off = 0
+    for i, p in enumerate(prims):
+        if isinstance(p, Particle2):
+            shapes[i]["kind"] = abi.PARTICLE2
+        elif isinstance(p, Line2):
+            shapes[i]["kind"] = abi.LINE2
+            shapes[i]["p"] = tuple(p.origin) + tuple(p.dest)
+        elif isinstance(p, Circle):
+            shapes[i]["kind"] = abi.CIRCLE
+            shapes[i]["p"] = (p.radius, 0, 0, 0)
+        elif isinstance(p, Rectangle):
+            shapes[i]["kind"] = abi.RECTANGLE
+            shapes[i]["p"] = (p.x, p.y, 0, 0)
+        elif isinstance(p, Square):
+            shapes[i]["kind"] = abi.SQUARE
+            shapes[i]["p"] = (p.dim, 0, 0, 0)
+        elif isinstance(p, ConvexPolygon):
+            shapes[i]["kind"] = abi.POLYGON
+            shapes[i]["vtx_off"] = off
+            shapes[i]["vtx_cnt"] = len(p.vertices)
+            verts.append(p.vertices)
+            off += len(p.vertices)
+        else:
+            raise TypeError(f"unsupported 2-D primitive {type(p).__name__}")
+    return shapes, (np.concatenate(verts) if verts else None)
+
+
+@dataclass
+class Contact2:
+    """Contact<Point2<f32>> (contact.rs:30-46)"""
+    strategy: int
+    normal: tuple
+    penetration_depth: float
+    contact_point: tuple
+    time_of_impact: float
+
+    @staticmethod
+    def from_record(r):
+        return Contact2(int(r["strategy"]), tuple(np.float32(x) for x in r["normal"]),
+                        np.float32(r["depth"]), tuple(np.float32(x) for x in r["point"]),
+                        np.float32(r["toi"]))
+
+
+class GJK2:
+    """GJK<SimplexProcessor2<f32>, EPA2<f32>, f32> (gjk/mod.rs:27,44-84), batch-of-1 wrappers."""
+
+    def __init__(self, ctx, distance_tolerance=1e-6, continuous_tolerance=1e-6,
+                 epa_tolerance=1e-5, max_iterations=100):
+        self.ctx = ctx
+        self.settings = Settings(np.float32(distance_tolerance), np.float32(continuous_tolerance),
+                                 np.float32(epa_tolerance), int(max_iterations))
+
+    @staticmethod
+    def new(ctx):
+        return GJK2(ctx)
+
+    @staticmethod
+    def new_with_settings(ctx, distance_tolerance, continuous_tolerance, epa_tolerance,
+                          max_iterations):
+        return GJK2(ctx, distance_tolerance, continuous_tolerance, epa_tolerance, max_iterations)
+
+    def _upload(self, left, right):
+        self.ctx.upload_shapes2(*_shape_table2([left, right]))
+
+    def intersect(self, left, left_transform, right, right_transform):
+        """gjk/mod.rs:101-146 -> whether Some(simplex) (the simplex itself stays on the device)"""
+        return self.intersection(CollisionStrategy.CollisionOnly, left, left_transform, right,
+                                 right_transform) is not None
+
+    def intersection(self, strategy, left, left_transform, right, right_transform):
+        """gjk/mod.rs:362-391 -> Option<Contact>"""
+        self._upload(left, right)
+        out, st = self.ctx.intersection2(strategy, _I0, _I1, left_transform.record(),
+                                         right_transform.record(), self.settings)
+        if st[0] > 1:
+            raise ReferencePanic(int(st[0]))
+        return Contact2.from_record(out[0]) if st[0] == 1 else None
+
+    def distance(self, left, left_transform, right, right_transform):
+        """gjk/mod.rs:271-321 -> Option<f32>"""
+        self._upload(left, right)
+        out, st = self.ctx.distance2(_I0, _I1, left_transform.record(), right_transform.record(),
+                                     self.settings)
+        if st[0] > 1:
+            raise ReferencePanic(int(st[0]))
+        return np.float32(out[0]) if st[0] == 1 else None
+
+    def intersection_time_of_impact(self, left, left_range, right, right_range, iter_cap=1024):
+        """gjk/mod.rs:163-256; ranges are (start, end) pairs -> Option<Contact>"""
+        self._upload(left, right)
+        out, st = self.ctx.time_of_impact2(_I0, _I1, left_range[0].record(), left_range[1].record(),
+                                           right_range[0].record(), right_range[1].record(),
+                                           self.settings, iter_cap)
+        if st[0] > 1:
+            raise ReferencePanic(int(st[0]))
+        return Contact2.from_record(out[0]) if st[0] == 1 else None
 
 
 class BruteForce:

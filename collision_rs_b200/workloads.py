@@ -134,3 +134,72 @@ def all_primitive3_shapes(rng, n):
     a = rng.uniform(0.4, 1.6, (n, 3)).astype(np.float32)
     s["p"] = a
     return s
+
+
+# ---- 2-D narrow phase (GJK2 / EPA2; SURVEY §8 row N4, not a BASELINE config) ------------------------
+def random_xforms2(rng, n, spread, scale=1.0):
+    from .abi import XFORM2_DT
+    t = np.zeros(n, XFORM2_DT)
+    a = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    s, c = np.sin(a, dtype=np.float32), np.cos(a, dtype=np.float32)
+    t["scale"] = scale
+    t["m"] = np.stack([c, s, -s, c], axis=1)  # Rotation2::from_angle: columns (cos, sin), (-sin, cos)
+    t["d"] = rng.uniform(-spread, spread, (n, 2)).astype(np.float32)
+    return t
+
+
+def shapes2_table(n_shapes=4096, seed=31, kinds=(0, 1, 2, 3, 4, 5), poly_sizes=(3, 5, 9, 10, 17, 64)):
+    """A table of Primitive2 values of every kind; polygons are convex, counter-clockwise, with
+    vertex counts on both sides of the reference's 10-vertex switch (polygon.rs:37)."""
+    from .abi import SHAPE2_DT
+    rng = np.random.default_rng(seed)
+    shapes = np.zeros(n_shapes, SHAPE2_DT)
+    kind = rng.choice(np.asarray(kinds, np.uint32), n_shapes)
+    shapes["kind"] = kind
+    shapes["p"] = 0
+    verts = []
+    off = 0
+    for i in range(n_shapes):
+        k = kind[i]
+        if k == 1:  # Line2(origin, dest)
+            shapes[i]["p"] = rng.uniform(-1, 1, 4).astype(np.float32)
+        elif k == 2:  # Circle(radius)
+            shapes[i]["p"][0] = np.float32(rng.uniform(0.25, 1.0))
+        elif k == 3:  # Rectangle(dim)
+            shapes[i]["p"][:2] = rng.uniform(0.5, 2.0, 2).astype(np.float32)
+        elif k == 4:  # Square(dim)
+            shapes[i]["p"][0] = np.float32(rng.uniform(0.5, 2.0))
+        elif k == 5:
+            v = int(rng.choice(poly_sizes))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, v))
+            rad = rng.uniform(0.5, 1.0, 2)
+            pts = np.stack([np.cos(ang) * rad[0], np.sin(ang) * rad[1]], axis=1).astype(np.float32)
+            shapes[i]["vtx_off"] = off
+            shapes[i]["vtx_cnt"] = v
+            verts.append(pts)
+            off += v
+    return shapes, (np.concatenate(verts) if verts else None)
+
+
+def cfg2d_mixed_pairs(n=1_000_000, seed=32, spread=1.0, n_shapes=4096, kinds=(0, 1, 2, 3, 4, 5),
+                      scale=1.0):
+    """Random pairs over a mixed Primitive2 table, Decomposed<Vector2, Basis2> transforms."""
+    rng = np.random.default_rng(seed)
+    shapes, verts = shapes2_table(n_shapes, seed + 1, kinds)
+    return dict(shapes=shapes, verts=verts,
+                l_shape=rng.integers(0, n_shapes, n, dtype=np.uint32),
+                r_shape=rng.integers(0, n_shapes, n, dtype=np.uint32),
+                l_t=random_xforms2(rng, n, spread, scale), r_t=random_xforms2(rng, n, spread, scale))
+
+
+def cfg2d_toi_pairs(n=1_000_000, seed=33, n_shapes=4096, kinds=(0, 1, 2, 3, 4, 5)):
+    """Start poses 3 apart on average, the left body moves towards the right one (cfg 5's recipe)."""
+    rng = np.random.default_rng(seed)
+    w = cfg2d_mixed_pairs(n, seed, 3.0, n_shapes, kinds)
+    l0, r0 = w.pop("l_t"), w.pop("r_t")
+    l1, r1 = l0.copy(), r0.copy()
+    gap = r0["d"] - l0["d"]
+    l1["d"] = (l0["d"] + gap * rng.uniform(0.5, 1.5, (n, 1)) + rng.uniform(-1, 1, (n, 2))).astype(np.float32)
+    r1["d"] = (r0["d"] + rng.uniform(-1, 1, (n, 2))).astype(np.float32)
+    w.update(l_t0=l0, l_t1=l1, r_t0=r0, r_t1=r1)
+    return w
