@@ -774,6 +774,35 @@ int cb2_sap3_find_collider_pairs_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_
     return rc;
 }
 
+// One GPU's shard of the pair list: every GPU sorts the whole table (the exact stable
+// permutation, 24 MB at 1 M boxes) and sweeps it, but reports only the pairs whose later box sits at
+// a sorted position in shard `shard` of `n_shards` equal position ranges.  The reference's Vec is
+// ordered by that position, so the shards concatenated in rank order ARE the reference's Vec.
+int cb2_sap3_find_collider_pairs_shard_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n,
+                                           uint32_t axis, uint32_t shard, uint32_t n_shards,
+                                           uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap,
+                                           uint64_t* n_pairs, void* stream) {
+    if (!c || !n_pairs) return fail(c, CB2_ERR_ARG, "null argument");
+    *n_pairs = 0;
+    if (axis > 2) return fail(c, CB2_ERR_ARG, "sweep axis must be 0, 1 or 2");
+    if (n_shards == 0 || shard >= n_shards) return fail(c, CB2_ERR_ARG, "shard out of range");
+    if (n == 0) return CB2_OK;
+    if (!aabbs || !perm_out || (!pairs_out && cap)) return fail(c, CB2_ERR_ARG, "null argument");
+    // the same split as collision_rs_b200/sharding.py shard_range(): the first n % n_shards ranks
+    // hold one more position
+    const uint64_t per = n / n_shards, rem = n % n_shards;
+    const uint64_t lo = shard * per + (shard < rem ? shard : rem);
+    const uint64_t hi = lo + per + (shard < rem ? 1 : 0);
+    CK(c, cudaSetDevice(c->device));
+    const char* err = "";
+    int rc = sap_find_pairs(c->sap, aabbs, n, axis, perm_out, pairs_out, cap, n_pairs,
+                            static_cast<cudaStream_t>(stream), &c->launches, &err, false,
+                            (uint32_t)lo, shard + 1 == n_shards ? 0xFFFFFFFFu : (uint32_t)hi);
+    if (rc == CB2_ERR_NOSPC) c->err = "pairs_out too small; *n_pairs holds the required capacity";
+    else if (rc) c->err = err;
+    return rc;
+}
+
 // SweepAndPrune2::find_collider_pairs (sweep_prune.rs:18, 76-136 with Variance2 :171-224): the 2-D
 // boxes are lifted to z in [0, 1] — the strict z test 1 > 0 && 0 < 1 always holds — and go through
 // the 3-D path; Variance2 discards its sums exactly like Variance3, so the next axis is 0 as well.

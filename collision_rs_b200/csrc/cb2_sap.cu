@@ -387,7 +387,11 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
                                                    const uint32_t* __restrict__ epos, uint64_t n_entries,
                                                    grid_params* __restrict__ G,
                                                    unsigned long long* __restrict__ keys, uint64_t cap,
-                                                   int pos_bits, const uint32_t* __restrict__ remap) {
+                                                   int pos_bits, const uint32_t* __restrict__ remap,
+                                                   uint32_t b_lo, uint32_t b_hi) {
+    // b_lo/b_hi: this GPU's shard of the pair list — only pairs whose LATER box (the `b` the
+    // reference's Vec is ordered by) sits at a sorted position in [b_lo, b_hi) are reported
+    const bool sharded = b_lo != 0u || b_hi != 0xFFFFFFFFu;
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const float org_u = G->org_u, inv_u = G->inv_u, org_v = G->org_v, inv_v = G->inv_v;
     const int nu = G->nu, nv = G->nv;
@@ -426,6 +430,10 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
                 const int bu0 = cell_coord(bu.x, org_u, inv_u, nu);
                 const int bv0 = cell_coord(bv.x, org_v, inv_v, nv);
                 if ((au0 > bu0 ? au0 : bu0) != cu || (av0 > bv0 ? av0 : bv0) != cv) continue;
+                if (sharded) {
+                    const uint32_t bp = __ldg(epos + f);
+                    if (bp < b_lo || bp >= b_hi) continue;
+                }
                 if (pass == 0) {
                     ++mine;
                 } else {
@@ -458,7 +466,8 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
                                                   const uint32_t* __restrict__ offs, uint64_t n_entries,
                                                   grid_params* __restrict__ G,
                                                   unsigned long long* __restrict__ keys, uint64_t cap,
-                                                  int pos_bits, const uint32_t* __restrict__ remap) {
+                                                  int pos_bits, const uint32_t* __restrict__ remap,
+                                                  uint32_t b_lo, uint32_t b_hi) {
     const uint32_t nl = G->n_large;
     for (uint32_t li = 0; li < nl; ++li) {
         const uint32_t p = __ldg(large_list + li);
@@ -469,6 +478,8 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
             const float2 qs = __ldg(S + q), qu = __ldg(U + q), qv = __ldg(V + q);
             if (!(ps.y > qs.x && ps.x < qs.y && pu.y > qu.x && pu.x < qu.y && pv.y > qv.x && pv.x < qv.y))
                 continue;
+            const uint32_t later = q > p ? (uint32_t)q : p;
+            if (later < b_lo || later >= b_hi) continue;  // another GPU's shard
             if (q > p) {
                 emit_pair(G, keys, cap, pos_bits, p, (uint32_t)q, remap);
             } else {
@@ -657,10 +668,11 @@ static int ensure_cap(sap_workspace* w, size_t bytes, const char** err) {
 
 int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
                    uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
-                   cudaStream_t st, uint64_t* launches, const char** err, bool brute_force) {
+                   cudaStream_t st, uint64_t* launches, const char** err, bool brute_force,
+                   uint32_t b_lo, uint32_t b_hi) {
     {
         const char* e = std::getenv("CB2_SAP_LEGACY");
-        if (e && e[0] == '1' && !brute_force)
+        if (e && e[0] == '1' && !brute_force && b_lo == 0u && b_hi == 0xFFFFFFFFu)
             return sap_find_pairs_legacy(w, aabbs, n, axis, perm_out, pairs_out, cap, n_pairs, st,
                                          launches, err);
     }
@@ -760,8 +772,10 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         tb = sort2;
         SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, p0, p1, (int64_t)ne, 0, cell_bits, st));
         k_grid_pack<<<nblk(ne, 256), 256, 0, st>>>(S, U, V, c1, p1, ne, G, eS, eU, eV);
-        k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, ne, G, pk, kcap, pos_bits, remap);
-        k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, offs, ne, G, pk, kcap, pos_bits, remap);
+        k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, ne, G, pk, kcap, pos_bits, remap,
+                                                      b_lo, b_hi);
+        k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, offs, ne, G, pk, kcap, pos_bits, remap, b_lo,
+                                         b_hi);
         k_grid_total<<<1, 32, 0, st>>>(G, flag, w->h_total);
         *launches += 13;
         SAP_CK(cudaGetLastError());

@@ -71,3 +71,49 @@ def gather_contacts(contacts, status, n_total, device="cpu", group=None):
         out_c[rb:re] = cs[r].cpu().numpy()[:(re - rb) * CONTACT_DT.itemsize].view(CONTACT_DT)
         out_s[rb:re] = ss[r].cpu().numpy()[:re - rb]
     return out_c, out_s
+
+
+# ---- broad phase: shard the sweep, not the sort ------------------------------------------
+def broadcast_aabbs(aabbs, src=0, device="cpu", group=None):
+    """Rank `src` passes the AABB table (AABB_DT array); every rank returns it."""
+    from .abi import AABB_DT
+    rank = dist.get_rank(group)
+    hdr = torch.zeros(1, dtype=torch.int64, device=device)
+    if rank == src:
+        hdr[0] = len(aabbs)
+    dist.broadcast(hdr, src, group=group)
+    n = int(hdr[0])
+    t = (_bytes_tensor(np.ascontiguousarray(aabbs, AABB_DT), device) if rank == src
+         else torch.zeros(n * AABB_DT.itemsize, dtype=torch.uint8, device=device))
+    if n:
+        dist.broadcast(t, src, group=group)
+    return t.cpu().numpy().view(AABB_DT).copy()
+
+
+def pairs_of_shard(pairs, n_boxes, rank, world):
+    """The slice of a full (a, b)-pair list (reference order: b ascending, then a) that belongs to
+    `rank`: pairs whose later box b sits at a sorted position in shard_range(n_boxes, rank, world).
+    This is what cb2_sap3_find_collider_pairs_shard_dev computes directly on each GPU."""
+    lo, hi = shard_range(n_boxes, rank, world)
+    pairs = np.asarray(pairs).reshape(-1, 2)
+    b = pairs[:, 1]
+    return pairs[(b >= lo) & (b < hi)]
+
+
+def gather_pairs(pairs, device="cpu", group=None):
+    """All-gather the per-rank pair lists (ragged) and concatenate them in rank order: the
+    reference's Vec.  One count exchange, then equal-size padded slots."""
+    world = dist.get_world_size(group)
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    cnt = torch.tensor([len(pairs)], dtype=torch.int64, device=device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    cnts = [int(c[0]) for c in cnts]
+    slot = max(max(cnts), 1)
+    buf = torch.zeros(slot * 2, dtype=torch.int32, device=device)
+    if len(pairs):
+        buf[:2 * len(pairs)] = torch.from_numpy(pairs.reshape(-1).view(np.int32).copy()).to(device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)
+    out = [bufs[r].cpu().numpy().view(np.uint32)[:2 * cnts[r]].reshape(-1, 2) for r in range(world)]
+    return np.concatenate(out) if out else np.zeros((0, 2), np.uint32)

@@ -277,6 +277,17 @@ int cb2_sap3_find_collider_pairs_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint6
                                      uint32_t* pairs_out, uint64_t cap,
                                      uint64_t* n_pairs, void* stream);
 
+/* Multi-GPU broad phase (one process per GPU): the same call restricted to shard
+ * `shard` of `n_shards`.  Every GPU holds the whole AABB table and computes the whole (identical)
+ * permutation; pairs are split by the sorted position of their LATER box into n_shards equal
+ * position ranges (the first n % n_shards ranges hold one more), so pairs_out of shards
+ * 0 .. n_shards-1 concatenated in order is exactly the reference's Vec and each shard can feed its
+ * own GPU's narrow phase with no exchange.  *n_pairs / CB2_ERR_NOSPC refer to this shard only.    */
+int cb2_sap3_find_collider_pairs_shard_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint64_t n,
+                                           uint32_t axis, uint32_t shard, uint32_t n_shards,
+                                           uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap,
+                                           uint64_t* n_pairs, void* stream);
+
 /* SweepAndPrune2::find_collider_pairs (sweep_prune.rs:18,76-136; Variance2 :171-224): the 2-D alias
  * of the same algorithm (the one the reference's own tests exercise, :317-361).  Same contract as
  * cb2_sap3_find_collider_pairs with axis in {0, 1}.  Host buffers.                              */

@@ -491,6 +491,43 @@ def test_grid_sap_matches_tiled_sweep_on_a_million_boxes(ctx):
             assert pairs.shape == pairs_e.shape and np.array_equal(pairs, pairs_e)
 
 
+def test_sap_shards_concatenate_to_the_full_pair_list(ctx, oracle):
+    """cb2_sap3_find_collider_pairs_shard_dev: for every world size the shards, each
+    computed on its own (here: the same) GPU, concatenated in rank order are byte-identical to the
+    single-GPU list; heavy-tailed box sizes exercise the large-box path too."""
+    import torch
+    from collision_rs_b200.sharding import pairs_of_shard
+    rng = np.random.default_rng(6)
+    n = 150_000
+    c = rng.uniform(0, 90, (n, 3)).astype(np.float32)
+    h = (0.2 * rng.pareto(1.5, (n, 3)) + 0.05).astype(np.float32)
+    heavy = np.zeros(n, host_abi.AABB_DT)
+    heavy["min"], heavy["max"] = c - h, c + h
+    dev = torch.device("cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    for boxes in (W.cfg4_aabbs(n, extent=200.0 * (n / 1e6) ** (1 / 3))["aabbs"], heavy):
+        perm_e, pairs_e, _ = ctx.sap3(boxes, axis=0)
+        d_boxes = torch.from_numpy(boxes.view(np.uint8).reshape(-1).copy()).to(dev)
+        perm = torch.zeros(n, dtype=torch.int32, device=dev)
+        cap = len(pairs_e) + 16
+        out = torch.zeros(2 * cap, dtype=torch.int32, device=dev)
+        for world in (1, 2, 3, 8):
+            parts = []
+            for r in range(world):
+                rc, cnt = ctx.sap3_shard_dev(d_boxes.data_ptr(), n, 0, r, world, perm.data_ptr(),
+                                             out.data_ptr(), cap, s)
+                assert rc == 0
+                torch.cuda.synchronize()
+                got = out[:2 * cnt].cpu().numpy().view(np.uint32).reshape(-1, 2)
+                assert np.array_equal(got, pairs_of_shard(pairs_e, n, r, world))
+                assert np.array_equal(perm.cpu().numpy().view(np.uint32), perm_e)
+                parts.append(got)
+            assert np.array_equal(np.concatenate(parts), pairs_e)
+    # a shard that does not fit reports its own required capacity
+    rc, cnt = ctx.sap3_shard_dev(d_boxes.data_ptr(), n, 0, 0, 2, perm.data_ptr(), out.data_ptr(), 8, s)
+    assert rc == -4 and cnt == len(pairs_of_shard(pairs_e, n, 0, 2))
+
+
 # ---- composite shapes: *_complex (gjk/mod.rs:412-588) ----------------------------------------------
 def test_complex_callers_match_the_oracle(ctx, oracle):
     from helpers_complex import composite_workload

@@ -69,3 +69,52 @@ def test_broadcast_shard_gather_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _sap_worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from collision_rs_b200 import workloads as W
+    from collision_rs_b200.sharding import broadcast_aabbs, gather_pairs, pairs_of_shard
+    from oracle.binding import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        w = W.cfg4_aabbs(n, extent=12.0)
+        boxes = broadcast_aabbs(w["aabbs"] if rank == 0 else None, src=0)
+        assert boxes.tobytes() == w["aabbs"].tobytes()
+        o = Oracle()
+        perm, pairs, _, _ = o.sap3(boxes, 0)
+        # every rank sorts redundantly (identical perm) and keeps its own slice of the pair list
+        mine = pairs_of_shard(pairs, n, rank, world)
+        allp = gather_pairs(mine)
+        if rank == 0:
+            q.put(bool(np.array_equal(allp, pairs) and 0 < len(mine) < len(pairs)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sap_shards_concatenate_to_the_reference_vec_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sap_worker, args=(r, 2, port, 3001, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+def test_pairs_of_shard_partitions_any_world():
+    from collision_rs_b200.sharding import pairs_of_shard
+    rng = np.random.default_rng(5)
+    n = 1000
+    b = np.sort(rng.integers(1, n, 5000))
+    a = (rng.random(5000) * b).astype(np.uint32)
+    pairs = np.stack([a, b.astype(np.uint32)], axis=1)
+    for world in (1, 2, 3, 8):
+        parts = [pairs_of_shard(pairs, n, r, world) for r in range(world)]
+        assert np.array_equal(np.concatenate(parts), pairs)
