@@ -1,3 +1,41 @@
+/// One entry of the 2-D shape table (32 B); `kind` = Primitive2 variant in declaration order
+/// (0 Particle, 1 Line, 2 Circle, 3 Rectangle, 4 Square, 5 ConvexPolygon).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct cb2_shape2 {
+    pub kind: u32,
+    pub p: [f32; 4],
+    pub vtx_off: u32,
+    pub vtx_cnt: u32,
+    pub reserved: u32,
+}
+
+/// `Decomposed<Vector2<f32>, Basis2<f32>>` flattened (32 B): scale, the column-major Matrix2
+/// behind `Basis2` (`AsRef<Matrix2<f32>>`: c0.x, c0.y, c1.x, c1.y), displacement.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct cb2_xform2 {
+    pub scale: f32,
+    pub c0x: f32,
+    pub c0y: f32,
+    pub c1x: f32,
+    pub c1y: f32,
+    pub dx: f32,
+    pub dy: f32,
+    pub reserved: f32,
+}
+
+/// `Contact<Point2<f32>>` (28 B).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct cb2_contact2 {
+    pub strategy: u32,
+    pub normal: [f32; 2],
+    pub penetration_depth: f32,
+    pub contact_point: [f32; 2],
+    pub time_of_impact: f32,
+}
+
 //! Raw `extern "C"` declarations of `include/collision_b200.h` (ABI version 1).
 //!
 //! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Rust toolchain.  The structs are
@@ -195,4 +233,39 @@ extern "C" {
                            out: *mut cb2_aabb3) -> c_int;
     pub fn cb2_world_aabbs_dev(ctx: *mut cb2_ctx, shape: *const u32, t: *const cb2_xform, n: u64,
                                out: *mut cb2_aabb3, stream: *mut c_void) -> c_int;
+    pub fn cb2_sap3_find_collider_pairs_shard_dev(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
+                                                  axis: u32, shard: u32, n_shards: u32,
+                                                  perm_out: *mut u32, pairs_out: *mut u32, cap: u64,
+                                                  n_pairs: *mut u64, stream: *mut c_void) -> c_int;
+
+    // ---- 2-D narrow phase: GJK2 / EPA2 over Primitive2 and Decomposed<Vector2, Basis2> ----
+    pub fn cb2_shapes2_upload(ctx: *mut cb2_ctx, shapes: *const cb2_shape2, n_shapes: u32,
+                              verts_xy: *const f32, n_verts: u64) -> c_int;
+    pub fn cb2_gjk2_intersection(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                 l_shape: *const u32, r_shape: *const u32,
+                                 l_t: *const cb2_xform2, r_t: *const cb2_xform2, n: u64,
+                                 out: *mut cb2_contact2, status: *mut u8) -> c_int;
+    pub fn cb2_gjk2_distance(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                             l_shape: *const u32, r_shape: *const u32,
+                             l_t: *const cb2_xform2, r_t: *const cb2_xform2, n: u64,
+                             out: *mut f32, status: *mut u8) -> c_int;
+    pub fn cb2_gjk2_time_of_impact(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                   l_shape: *const u32, r_shape: *const u32,
+                                   l_t0: *const cb2_xform2, l_t1: *const cb2_xform2,
+                                   r_t0: *const cb2_xform2, r_t1: *const cb2_xform2, n: u64,
+                                   iter_cap: u32, out: *mut cb2_contact2, status: *mut u8) -> c_int;
+    pub fn cb2_gjk2_intersection_dev(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                     l_shape: *const u32, r_shape: *const u32,
+                                     l_t: *const cb2_xform2, r_t: *const cb2_xform2, n: u64,
+                                     out: *mut cb2_contact2, status: *mut u8, stream: *mut c_void) -> c_int;
+    pub fn cb2_gjk2_distance_dev(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                 l_shape: *const u32, r_shape: *const u32,
+                                 l_t: *const cb2_xform2, r_t: *const cb2_xform2, n: u64,
+                                 out: *mut f32, status: *mut u8, stream: *mut c_void) -> c_int;
+    pub fn cb2_gjk2_time_of_impact_dev(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                       l_shape: *const u32, r_shape: *const u32,
+                                       l_t0: *const cb2_xform2, l_t1: *const cb2_xform2,
+                                       r_t0: *const cb2_xform2, r_t1: *const cb2_xform2, n: u64,
+                                       iter_cap: u32, out: *mut cb2_contact2, status: *mut u8,
+                                       stream: *mut c_void) -> c_int;
 }
