@@ -1,41 +1,3 @@
-/// One entry of the 2-D shape table (32 B); `kind` = Primitive2 variant in declaration order
-/// (0 Particle, 1 Line, 2 Circle, 3 Rectangle, 4 Square, 5 ConvexPolygon).
-#[repr(C)]
-#[derive(Clone, Copy, Debug, Default, PartialEq)]
-pub struct cb2_shape2 {
-    pub kind: u32,
-    pub p: [f32; 4],
-    pub vtx_off: u32,
-    pub vtx_cnt: u32,
-    pub reserved: u32,
-}
-
-/// `Decomposed<Vector2<f32>, Basis2<f32>>` flattened (32 B): scale, the column-major Matrix2
-/// behind `Basis2` (`AsRef<Matrix2<f32>>`: c0.x, c0.y, c1.x, c1.y), displacement.
-#[repr(C)]
-#[derive(Clone, Copy, Debug, Default, PartialEq)]
-pub struct cb2_xform2 {
-    pub scale: f32,
-    pub c0x: f32,
-    pub c0y: f32,
-    pub c1x: f32,
-    pub c1y: f32,
-    pub dx: f32,
-    pub dy: f32,
-    pub reserved: f32,
-}
-
-/// `Contact<Point2<f32>>` (28 B).
-#[repr(C)]
-#[derive(Clone, Copy, Debug, Default, PartialEq)]
-pub struct cb2_contact2 {
-    pub strategy: u32,
-    pub normal: [f32; 2],
-    pub penetration_depth: f32,
-    pub contact_point: [f32; 2],
-    pub time_of_impact: f32,
-}
-
 //! Raw `extern "C"` declarations of `include/collision_b200.h` (ABI version 1).
 //!
 //! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Rust toolchain.  The structs are
@@ -142,6 +104,44 @@ pub struct cb2_aabb2 {
 #[repr(C)]
 pub struct cb2_ctx {
     _private: [u8; 0],
+}
+
+/// One entry of the 2-D shape table (32 B); `kind` = Primitive2 variant in declaration order
+/// (0 Particle, 1 Line, 2 Circle, 3 Rectangle, 4 Square, 5 ConvexPolygon).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct cb2_shape2 {
+    pub kind: u32,
+    pub p: [f32; 4],
+    pub vtx_off: u32,
+    pub vtx_cnt: u32,
+    pub reserved: u32,
+}
+
+/// `Decomposed<Vector2<f32>, Basis2<f32>>` flattened (32 B): scale, the column-major Matrix2
+/// behind `Basis2` (`AsRef<Matrix2<f32>>`: c0.x, c0.y, c1.x, c1.y), displacement.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct cb2_xform2 {
+    pub scale: f32,
+    pub c0x: f32,
+    pub c0y: f32,
+    pub c1x: f32,
+    pub c1y: f32,
+    pub dx: f32,
+    pub dy: f32,
+    pub reserved: f32,
+}
+
+/// `Contact<Point2<f32>>` (28 B).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct cb2_contact2 {
+    pub strategy: u32,
+    pub normal: [f32; 2],
+    pub penetration_depth: f32,
+    pub contact_point: [f32; 2],
+    pub time_of_impact: f32,
 }
 
 extern "C" {
