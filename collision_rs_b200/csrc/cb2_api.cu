@@ -1,10 +1,10 @@
 // cb2_api.cu — the extern "C" boundary declared in include/collision_b200.h.
 //
-// One ctx per GPU.  Host-buffer entry points stream the batch through the device in chunks on
-// four CUDA streams (H2D of later chunks overlaps the kernels of chunk k and the D2H of earlier
-// ones, and the low-occupancy tail of one chunk's EPA tiers overlaps the next chunk's kernels;
-// truly asynchronous when the caller's buffers are pinned).  Device-buffer entry points only
-// enqueue kernels on the caller's stream.  No CPU fallback anywhere.
+// One ctx per GPU.  Host-buffer entry points stream the batch through the device in chunks: one
+// copy-in stream, three compute streams taking the chunks in turn, one copy-out stream, tied by
+// per-buffer events (see host_pipeline below; truly asynchronous when the caller's buffers are
+// pinned).  Device-buffer entry points only enqueue kernels on the caller's stream.  No CPU
+// fallback anywhere.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -50,6 +50,11 @@ struct cb2_ctx {
     static constexpr int NS = CB2_NS;  // host-API pipeline depth (streams / staging buffers)
     cudaStream_t stream[NS] = {};
     cudaEvent_t done[NS] = {};
+    // host-API pipeline events per staging buffer: inputs landed | kernels finished | buffer free
+    cudaEvent_t ev_in[NS] = {}, ev_k[NS] = {}, ev_free[NS] = {};
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // the pipeline's copy-in / copy-out streams
+    int n_cstreams = 3;  // compute streams the pipeline rotates over (CB2_NC overrides, <= NS)
+    bool ramp = true;  // short chunks at both ends of a batch (CB2_RAMP=0 disables)
     char* d_stage[NS] = {};
     size_t stage_cap = 0;
     sap_workspace* sap = nullptr;
@@ -159,6 +164,10 @@ int cb2_create(int device, cb2_ctx** out) {
         const char* e2 = std::getenv("CB2_NO_CELLS");
         const char* e3 = std::getenv("CB2_CHUNK_PAIRS");
         if (e3 && std::atoll(e3) > 0) c->chunk_pairs = (uint64_t)std::atoll(e3);
+        const char* e4 = std::getenv("CB2_NC");
+        if (e4 && std::atoi(e4) >= 1 && std::atoi(e4) <= cb2_ctx::NS) c->n_cstreams = std::atoi(e4);
+        const char* e5 = std::getenv("CB2_RAMP");
+        if (e5 && e5[0] == '0') c->ramp = false;
         c->legacy_epa = e1 && e1[0] == '1';
         c->no_cells = e2 && e2[0] == '1';
     }
@@ -181,6 +190,11 @@ void cb2_destroy(cb2_ctx* c) {
     for (int i = 0; i < cb2_ctx::NS; ++i) {
         if (c->d_stage[i]) cudaFree(c->d_stage[i]);
         if (c->done[i]) cudaEventDestroy(c->done[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+        if (i == 0 && c->s_in) cudaStreamDestroy(c->s_in);
+        if (i == 0 && c->s_out) cudaStreamDestroy(c->s_out);
         if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
     }
     if (c->d_shapes) cudaFree(c->d_shapes);
@@ -610,7 +624,149 @@ static int narrow_dev(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_setti
     return launch_op(c, op, strategy, A, static_cast<cudaStream_t>(stream));
 }
 
-// Host-buffer path: chunked, double-buffered over two streams.
+// ---- host-buffer pipeline ------------------------------------------------------------------------------
+// A batch streams through the device in chunks over ROLES, not peers: one copy-in stream that runs
+// ahead as far as the four staging buffers allow, three compute streams that take the chunks in
+// turn (the low-occupancy tail of chunk k's EPA tiers overlaps chunks k+1, k+2, while chunks still
+// finish one after the other), and one copy-out stream.  Staggered completion is the point: with
+// four equal peers (copy-in, kernels and copy-out of a chunk all on that chunk's stream) the four
+// chunks of a wave finished together and the wave's copies sat outside the compute — CB2_TRACE=1
+// showed the SMs idle for ~3 ms of a 24.4 ms call; this arrangement takes the same call to 21.3 ms.
+//   in(k):   wait free[buf]  -> H2D          -> record in[buf]
+//   comp(k): wait in[buf]    -> kernels      -> record k[buf]
+//   out(k):  wait k[buf]     -> D2H          -> record free[buf]
+struct host_pipeline {
+    cb2_ctx* c;
+    cudaStream_t s_in, s_out, s_comp[2];
+    static constexpr int NB = cb2_ctx::NS;  // staging buffers
+};
+static int pipeline_prepare(cb2_ctx* c, size_t stage_bytes) {
+    if (c->stage_cap < stage_bytes) {
+        for (int i = 0; i < cb2_ctx::NS; ++i) {
+            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+            c->d_stage[i] = nullptr;
+        }
+        c->stage_cap = 0;
+        for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaMalloc(&c->d_stage[i], stage_bytes));
+        c->stage_cap = stage_bytes;
+    }
+    if (!c->s_in) CK(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    if (!c->s_out) CK(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < cb2_ctx::NS; ++i) {
+        if (!c->ev_in[i]) CK(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        if (!c->ev_k[i]) CK(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+        if (!c->ev_free[i]) CK(c, cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+    }
+    return CB2_OK;
+}
+// chunk sizes: short chunks at both ends (the first copy-in and the last copy-out are the only
+// transfers nothing can hide), full chunks in between
+static std::vector<uint64_t> pipeline_chunks(uint64_t n, uint64_t chunk, bool ramped) {
+    std::vector<uint64_t> v;
+    if (!ramped) {
+        for (uint64_t b = 0; b < n; b += chunk) v.push_back(n - b < chunk ? n - b : chunk);
+        return v;
+    }
+    if (n <= chunk) {
+        v.push_back(n);
+        return v;
+    }
+    const uint64_t ramp[2] = {chunk / 4, chunk / 2};
+    uint64_t head = 0, tail = 0;
+    if (n >= 4 * chunk) {
+        for (uint64_t r : ramp) {
+            v.push_back(r);
+            head += r;
+        }
+        tail = ramp[0] + ramp[1];
+    }
+    uint64_t left = n - head - tail;
+    while (left) {
+        const uint64_t m = left < chunk ? left : chunk;
+        v.push_back(m);
+        left -= m;
+    }
+    if (tail) {
+        v.push_back(ramp[1]);
+        v.push_back(ramp[0]);
+    }
+    return v;
+}
+template <class FIn, class FComp, class FOut>
+static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut copy_out) {
+    static const bool trace = std::getenv("CB2_TRACE") && std::getenv("CB2_TRACE")[0] == '1';
+    cudaStream_t s_in = c->s_in, s_out = c->s_out;
+    const std::vector<uint64_t> sizes = pipeline_chunks(n, c->chunk_pairs, c->ramp);
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t t0 = nullptr;
+    if (trace) {
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, s_in);
+    }
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    uint64_t b = 0;
+    int rc = CB2_OK;
+    for (size_t k = 0; k < sizes.size() && rc == CB2_OK; ++k) {
+        const uint64_t m = sizes[k];
+        const int buf = (int)(k % cb2_ctx::NS), slot = (int)(k % (size_t)c->n_cstreams);
+        char* base = c->d_stage[buf];
+        cudaStream_t s_comp = c->stream[slot];
+        if (k >= (size_t)cb2_ctx::NS) CK(c, cudaStreamWaitEvent(s_in, c->ev_free[buf], 0));
+        rc = copy_in(b, m, base, s_in);
+        if (rc) break;
+        CK(c, cudaEventRecord(c->ev_in[buf], s_in));
+        mark(s_in);
+        CK(c, cudaStreamWaitEvent(s_comp, c->ev_in[buf], 0));
+        rc = compute(b, m, base, s_comp, slot);
+        if (rc) break;
+        CK(c, cudaEventRecord(c->ev_k[buf], s_comp));
+        mark(s_comp);
+        CK(c, cudaStreamWaitEvent(s_out, c->ev_k[buf], 0));
+        rc = copy_out(b, m, base, s_out);
+        if (rc) break;
+        CK(c, cudaEventRecord(c->ev_free[buf], s_out));
+        mark(s_out);
+        b += m;
+    }
+    for (int i = 0; i < cb2_ctx::NS + 2; ++i) {
+        cudaError_t e = cudaStreamSynchronize(i < cb2_ctx::NS ? c->stream[i] : (i == cb2_ctx::NS ? s_in : s_out));
+        if (e != cudaSuccess && rc == CB2_OK) {
+            c->err = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
+            rc = CB2_ERR_CUDA;
+        }
+    }
+    if (trace) {
+        for (size_t q = 0; q + 2 < tev.size(); q += 3) {
+            float a_ = 0, b_ = 0, d_ = 0;
+            cudaEventElapsedTime(&a_, t0, tev[q]);
+            cudaEventElapsedTime(&b_, t0, tev[q + 1]);
+            cudaEventElapsedTime(&d_, t0, tev[q + 2]);
+            std::fprintf(stderr, "[cb2 trace] chunk %zu (%llu pairs): in %.3f  kernels %.3f  out %.3f ms\n", q / 3,
+                         (unsigned long long)sizes[q / 3], a_, b_, d_);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(t0);
+    }
+    return rc;
+}
+// a Rust slice index would panic on an out-of-range shape index: checked chunk by chunk, while the
+// GPU works on the chunks before (the call fails as a whole; outputs of a failed call are unspecified)
+static bool indices_in_range(const uint32_t* a, const uint32_t* b, uint64_t m, uint32_t limit) {
+    uint32_t worst = 0;
+    for (uint64_t i = 0; i < m; ++i) {
+        worst = a[i] > worst ? a[i] : worst;
+        worst = b[i] > worst ? b[i] : worst;
+    }
+    return worst < limit;
+}
+
+// Host-buffer path of the 3-D narrow phase.
 static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_settings* settings,
                        const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t0,
                        const cb2_xform* l_t1, const cb2_xform* r_t0, const cb2_xform* r_t1,
@@ -625,73 +781,60 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
     if (!l_shape || !r_shape || !l_t0 || !r_t0 || !status) return fail(c, CB2_ERR_ARG, "null argument");
     if (op == OP_DISTANCE ? !out_d : !out_c) return fail(c, CB2_ERR_ARG, "null output");
     if (op == OP_TOI && (!l_t1 || !r_t1)) return fail(c, CB2_ERR_ARG, "null end transform");
-    // reject out-of-range shape indices up front (a Rust slice index would panic)
-    for (uint64_t i = 0; i < n; ++i)
-        if (l_shape[i] >= c->n_shapes || r_shape[i] >= c->n_shapes)
-            return fail(c, CB2_ERR_ARG, "shape index out of range");
     CK(c, cudaSetDevice(c->device));
     const uint64_t chunk = n < c->chunk_pairs ? n : c->chunk_pairs;
     const int n_xf = op == OP_TOI ? 4 : 2;
     const size_t out_rec = op == OP_DISTANCE ? sizeof(float) : sizeof(cb2_contact);
-    // staging layout per stream: xforms | l_shape | r_shape | out | status   (256-byte aligned)
+    // staging layout per buffer: xforms | l_shape | r_shape | out | status   (256-byte aligned)
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t o_xf = 0;
     const size_t xf_bytes = al(chunk * sizeof(cb2_xform));
-    const size_t o_ls = o_xf + n_xf * xf_bytes;
+    const size_t o_ls = n_xf * xf_bytes;
     const size_t o_rs = o_ls + al(chunk * 4);
     const size_t o_out = o_rs + al(chunk * 4);
     const size_t o_st = o_out + al(chunk * out_rec);
-    const size_t need = o_st + al(chunk);
-    if (c->stage_cap < need) {
-        for (int i = 0; i < cb2_ctx::NS; ++i) {
-            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
-            c->d_stage[i] = nullptr;
-        }
-        c->stage_cap = 0;
-        for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaMalloc(&c->d_stage[i], need));
-        c->stage_cap = need;
-    }
+    rc = pipeline_prepare(c, o_st + al(chunk));
+    if (rc) return rc;
     const cb2_xform* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
-    int k = 0;
-    for (uint64_t b = 0; b < n; b += chunk, ++k) {
-        const uint64_t m = (n - b < chunk) ? n - b : chunk;
-        const int s = k % cb2_ctx::NS;
-        cudaStream_t st = c->stream[s];
-        char* base = c->d_stage[s];
-        // the previous use of this staging buffer (chunk k-2) has been fully enqueued on the
-        // same stream, so stream order protects it.
-        for (int x = 0; x < n_xf; ++x)
-            CK(c, cudaMemcpyAsync(base + o_xf + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform),
-                                  cudaMemcpyHostToDevice, st));
-        CK(c, cudaMemcpyAsync(base + o_ls, l_shape + b, m * 4, cudaMemcpyHostToDevice, st));
-        CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
-        narrow_args A;
-        std::memset(&A, 0, sizeof(A));
-        A.l_shape = reinterpret_cast<const uint32_t*>(base + o_ls);
-        A.r_shape = reinterpret_cast<const uint32_t*>(base + o_rs);
-        A.l_t = reinterpret_cast<const float4*>(base + o_xf);
-        A.r_t = reinterpret_cast<const float4*>(base + o_xf + xf_bytes);
-        if (op == OP_TOI) {
-            A.l_t1 = reinterpret_cast<const float4*>(base + o_xf + 2 * xf_bytes);
-            A.r_t1 = reinterpret_cast<const float4*>(base + o_xf + 3 * xf_bytes);
-        }
-        A.n = m;
-        A.settings = *settings;
-        A.iter_cap = iter_cap ? iter_cap : 1024u;
-        A.out_contact = reinterpret_cast<cb2_contact*>(base + o_out);
-        A.out_distance = reinterpret_cast<float*>(base + o_out);
-        A.out_status = reinterpret_cast<uint8_t*>(base + o_st);
-        rc = launch_op(c, op, strategy, A, st, s);
-        if (rc) return rc;
-        if (op == OP_DISTANCE)
-            CK(c, cudaMemcpyAsync(out_d + b, base + o_out, m * sizeof(float), cudaMemcpyDeviceToHost, st));
-        else
-            CK(c, cudaMemcpyAsync(out_c + b, base + o_out, m * sizeof(cb2_contact),
-                                  cudaMemcpyDeviceToHost, st));
-        CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
-    }
-    for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaStreamSynchronize(c->stream[i]));
-    return CB2_OK;
+    return pipeline_run(
+        c, n,
+        [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
+            if (!indices_in_range(l_shape + b, r_shape + b, m, c->n_shapes))
+                return fail(c, CB2_ERR_ARG, "shape index out of range");
+            for (int x = 0; x < n_xf; ++x)
+                CK(c, cudaMemcpyAsync(base + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform),
+                                      cudaMemcpyHostToDevice, st));
+            CK(c, cudaMemcpyAsync(base + o_ls, l_shape + b, m * 4, cudaMemcpyHostToDevice, st));
+            CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
+            return CB2_OK;
+        },
+        [&](uint64_t, uint64_t m, char* base, cudaStream_t st, int slot) -> int {
+            narrow_args A;
+            std::memset(&A, 0, sizeof(A));
+            A.l_shape = reinterpret_cast<const uint32_t*>(base + o_ls);
+            A.r_shape = reinterpret_cast<const uint32_t*>(base + o_rs);
+            A.l_t = reinterpret_cast<const float4*>(base);
+            A.r_t = reinterpret_cast<const float4*>(base + xf_bytes);
+            if (op == OP_TOI) {
+                A.l_t1 = reinterpret_cast<const float4*>(base + 2 * xf_bytes);
+                A.r_t1 = reinterpret_cast<const float4*>(base + 3 * xf_bytes);
+            }
+            A.n = m;
+            A.settings = *settings;
+            A.iter_cap = iter_cap ? iter_cap : 1024u;
+            A.out_contact = reinterpret_cast<cb2_contact*>(base + o_out);
+            A.out_distance = reinterpret_cast<float*>(base + o_out);
+            A.out_status = reinterpret_cast<uint8_t*>(base + o_st);
+            return launch_op(c, op, strategy, A, st, slot);
+        },
+        [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
+            if (op == OP_DISTANCE)
+                CK(c, cudaMemcpyAsync(out_d + b, base + o_out, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+            else
+                CK(c, cudaMemcpyAsync(out_c + b, base + o_out, m * sizeof(cb2_contact),
+                                      cudaMemcpyDeviceToHost, st));
+            CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
+            return CB2_OK;
+        });
 }
 
 static int ensure_misc(cb2_ctx* c, size_t bytes) {
@@ -1188,7 +1331,7 @@ static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings
     return CB2_OK;
 }
 
-// Host-buffer path: the same chunked multi-stream pipeline as narrow_host.
+// Host-buffer path: the same pipeline as narrow_host.
 static int narrow2_host(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings* settings,
                         const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t0,
                         const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1,
@@ -1198,9 +1341,6 @@ static int narrow2_host(cb2_ctx* c, int op, uint32_t strategy, const cb2_setting
                            op == 1 ? (const void*)out_d : (const void*)out_c, status);
     if (rc) return rc;
     if (n == 0) return CB2_OK;
-    for (uint64_t i = 0; i < n; ++i)
-        if (l_shape[i] >= c->n_shapes2 || r_shape[i] >= c->n_shapes2)
-            return fail(c, CB2_ERR_ARG, "shape index out of range");
     CK(c, cudaSetDevice(c->device));
     const uint64_t chunk = n < c->chunk_pairs ? n : c->chunk_pairs;
     const int n_xf = op == 2 ? 4 : 2;
@@ -1211,44 +1351,39 @@ static int narrow2_host(cb2_ctx* c, int op, uint32_t strategy, const cb2_setting
     const size_t o_rs = o_ls + al(chunk * 4);
     const size_t o_out = o_rs + al(chunk * 4);
     const size_t o_st = o_out + al(chunk * out_rec);
-    const size_t need = o_st + al(chunk);
-    if (c->stage_cap < need) {
-        for (int i = 0; i < cb2_ctx::NS; ++i) {
-            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
-            c->d_stage[i] = nullptr;
-        }
-        c->stage_cap = 0;
-        for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaMalloc(&c->d_stage[i], need));
-        c->stage_cap = need;
-    }
+    rc = pipeline_prepare(c, o_st + al(chunk));
+    if (rc) return rc;
     const cb2_xform2* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
-    int k = 0;
-    for (uint64_t b = 0; b < n; b += chunk, ++k) {
-        const uint64_t m = (n - b < chunk) ? n - b : chunk;
-        const int s = k % cb2_ctx::NS;
-        cudaStream_t st = c->stream[s];
-        char* base = c->d_stage[s];
-        for (int x = 0; x < n_xf; ++x)
-            CK(c, cudaMemcpyAsync(base + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform2),
-                                  cudaMemcpyHostToDevice, st));
-        CK(c, cudaMemcpyAsync(base + o_ls, l_shape + b, m * 4, cudaMemcpyHostToDevice, st));
-        CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
-        const cb2_xform2* X = reinterpret_cast<const cb2_xform2*>(base);
-        const size_t xs = xf_bytes / sizeof(cb2_xform2);
-        rc = narrow2_dev(c, op, strategy, settings, reinterpret_cast<const uint32_t*>(base + o_ls),
-                         reinterpret_cast<const uint32_t*>(base + o_rs), X, X + 2 * xs, X + xs, X + 3 * xs,
-                         m, iter_cap, reinterpret_cast<cb2_contact2*>(base + o_out),
-                         reinterpret_cast<float*>(base + o_out), reinterpret_cast<uint8_t*>(base + o_st), st, s);
-        if (rc) return rc;
-        if (op == 1)
-            CK(c, cudaMemcpyAsync(out_d + b, base + o_out, m * sizeof(float), cudaMemcpyDeviceToHost, st));
-        else
-            CK(c, cudaMemcpyAsync(out_c + b, base + o_out, m * sizeof(cb2_contact2),
-                                  cudaMemcpyDeviceToHost, st));
-        CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
-    }
-    for (int i = 0; i < cb2_ctx::NS; ++i) CK(c, cudaStreamSynchronize(c->stream[i]));
-    return CB2_OK;
+    const size_t xs = xf_bytes / sizeof(cb2_xform2);
+    return pipeline_run(
+        c, n,
+        [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
+            if (!indices_in_range(l_shape + b, r_shape + b, m, c->n_shapes2))
+                return fail(c, CB2_ERR_ARG, "shape index out of range");
+            for (int x = 0; x < n_xf; ++x)
+                CK(c, cudaMemcpyAsync(base + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform2),
+                                      cudaMemcpyHostToDevice, st));
+            CK(c, cudaMemcpyAsync(base + o_ls, l_shape + b, m * 4, cudaMemcpyHostToDevice, st));
+            CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
+            return CB2_OK;
+        },
+        [&](uint64_t, uint64_t m, char* base, cudaStream_t st, int slot) -> int {
+            const cb2_xform2* X = reinterpret_cast<const cb2_xform2*>(base);
+            return narrow2_dev(c, op, strategy, settings, reinterpret_cast<const uint32_t*>(base + o_ls),
+                               reinterpret_cast<const uint32_t*>(base + o_rs), X, X + 2 * xs, X + xs,
+                               X + 3 * xs, m, iter_cap, reinterpret_cast<cb2_contact2*>(base + o_out),
+                               reinterpret_cast<float*>(base + o_out),
+                               reinterpret_cast<uint8_t*>(base + o_st), st, slot);
+        },
+        [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
+            if (op == 1)
+                CK(c, cudaMemcpyAsync(out_d + b, base + o_out, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+            else
+                CK(c, cudaMemcpyAsync(out_c + b, base + o_out, m * sizeof(cb2_contact2),
+                                      cudaMemcpyDeviceToHost, st));
+            CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
+            return CB2_OK;
+        });
 }
 
 extern "C" {
