@@ -374,8 +374,9 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "how": "cb2_gjk3_intersection on pinned host buffers: chunked H2D, kernel, D2H "
-                       "inside the timed call"},
+                "how": "cb2_gjk3_intersection on pinned host buffers: chunks through one copy-in "
+                       "stream, three compute streams and one copy-out stream, all inside the "
+                       "timed call"},
         "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
@@ -482,6 +483,22 @@ def extras(ctx, torch, dev, stream):
                                               out.data_ptr(), st.data_ptr(), s), reps=3, warm=1)
     res["cfg5_time_of_impact"] = {"pairs": n, "ms": ms, "pairs_per_s": n / ms * 1e3,
                                   "nonconverged": int((st == 5).sum()), "iter_cap": 1024}
+    # 2-D narrow phase (not a BASELINE config): GJK2 + EPA2 on 4M mixed Primitive2
+    # pairs and on rectangles (cfg 1's 2-D twin)
+    from collision_rs_b200.abi import CONTACT2_DT
+    n = 4_000_000
+    for name, kinds, spread in (("gjk2_mixed_primitive2", (0, 1, 2, 3, 4, 5), 1.0),
+                                ("gjk2_rectangles", (3, 4), 0.75)):
+        w = W.cfg2d_mixed_pairs(n, seed=11, spread=spread, kinds=kinds)
+        ctx.upload_shapes2(w["shapes"], w["verts"])
+        d = {k: dv(w[k]) for k in ("l_shape", "r_shape", "l_t", "r_t")}
+        out2 = torch.empty(n * CONTACT2_DT.itemsize, dtype=torch.uint8, device=dev)
+        st2 = torch.empty(n, dtype=torch.uint8, device=dev)
+        ms = timed(lambda: ctx.intersection2_dev(0, d["l_shape"].data_ptr(), d["r_shape"].data_ptr(),
+                                                 d["l_t"].data_ptr(), d["r_t"].data_ptr(), n,
+                                                 out2.data_ptr(), st2.data_ptr(), s))
+        res[name + "_full_resolution"] = {"pairs": n, "ms": ms, "pairs_per_s": n / ms * 1e3,
+                                          "hit_fraction": float((st2 == 1).float().mean())}
     return res
 
 

@@ -39,6 +39,18 @@
 #ifndef CB2_EPA_MIN_BLOCKS
 #define CB2_EPA_MIN_BLOCKS 20
 #endif
+// loop-unroll factors of the per-face loops (A/B experiments): closest face, visibility, new faces
+#define CB2_PRAGMA(x) _Pragma(#x)
+#define CB2_UNROLL(n) CB2_PRAGMA(unroll n)
+#ifndef CB2_U_CLOSEST
+#define CB2_U_CLOSEST 1
+#endif
+#ifndef CB2_U_VIS
+#define CB2_U_VIS 1
+#endif
+#ifndef CB2_U_FACE
+#define CB2_U_FACE 1
+#endif
 namespace cb2 {
 
 CB2_DI shape_table table_of(const shape_table_args& a) {
@@ -181,7 +193,7 @@ enum : int { S_FETCH = 0, S_RUN = 1, S_EXIT = 2 };
 
 // RF/RV: caps of the tier whose dumps this instantiation resumes (0 = none)
 template <int G, int FCAP, int VCAP, int OCAP, int RF, int RV>
-__global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
+__global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa(epa_args C) {
     static_assert(G == 2 || G == 4 || G == 8, "3*G edge-keep bits must fit one word");
     static_assert(RF <= FCAP && RV <= VCAP, "a resumed polytope must fit");
     using PS = poly_smem<FCAP, VCAP, OCAP>;
@@ -310,6 +322,7 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
             const int nf_max = __reduce_max_sync(0xffffffffu, nf);
             float bd = INFINITY;
             uint32_t bi = 0xFFFFFFFFu;
+            CB2_UNROLL(CB2_U_CLOSEST)
             for (int f = gl; f < nf_max; f += G) {
                 if (f < nf) {
                     float dd = P.fnd[f].w;
@@ -356,6 +369,7 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
         vis.clear();
         {
             const int nf_max = __reduce_max_sync(0xffffffffu, add ? nf : 0);
+            CB2_UNROLL(CB2_U_VIS)
             for (int f0 = 0; f0 < nf_max; f0 += G) {
                 const int f = f0 + gl;
                 bool v = false;
@@ -477,6 +491,7 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
         // (6) build the new faces (one horizon edge per lane)
         {
             const int ne_max = __reduce_max_sync(0xffffffffu, grow ? ne : 0);
+            CB2_UNROLL(CB2_U_FACE)
             for (int k = gl; k < ne_max; k += G) {
                 if (grow && k < ne) {
                     const uint32_t e = P.elist[k];
@@ -545,7 +560,10 @@ __global__ void __launch_bounds__(32, CB2_EPA_MIN_BLOCKS) k_epa(epa_args C) {
 
 // ---- host side ----------------------------------------------------------------------------------------
 // tier:            G   faces  verts  examined/horizon cap
-constexpr int T0_G = 4, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O;
+#ifndef CB2_T0_G
+#define CB2_T0_G 4
+#endif
+constexpr int T0_G = CB2_T0_G, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O;
 #ifndef CB2_T1_G
 #define CB2_T1_G 8
 #endif
