@@ -80,14 +80,15 @@ def kernels_csv(reps):
 
 
 def main():
-    launches(os.path.join(GO, f"launches_{tag}.csv"), "k_gjk_hits<1>", 4, f"{tag}_launches_cfg3.txt",
+    launches(os.path.join(GO, f"launches_{tag}.csv"), "k_gjk_hits_p", 4, f"{tag}_launches_cfg3.txt",
              "# one cfg-3 step (1 M polyhedron pairs, FullResolution): ncu --metrics "
              "gpu__time_duration.sum --clock-control none, bench.py --steps 2 --warmup 3 "
              "--pairs 1000000 --no-extra")
     launches(os.path.join(GO, f"launches_sap_{tag}.csv"), "k_sap_keys", 0, f"{tag}_launches_sap.txt",
              "# one SweepAndPrune3::find_collider_pairs call, cfg 4 (1 M boxes, 3.95 M pairs): "
              "tools/sap_probe.py under the same ncu pass")
-    reps = [os.path.join(GO, f"prof_{tag}.ncu-rep"), os.path.join(GO, f"prof_sap_{tag}.ncu-rep")]
+    reps = [os.path.join(GO, f"prof_{tag}.ncu-rep"), os.path.join(GO, f"prof_sap_{tag}.ncu-rep"),
+            os.path.join(GO, f"prof_gjk2_{tag}.ncu-rep")]
     rows = kernels_csv([r for r in reps if os.path.exists(r)])
     # dram traffic of k_epa per pair (all tier launches of one pass, 1 M pairs)
     hdr = rows[0]
@@ -95,7 +96,7 @@ def main():
         "dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
     units = rows[1]
     scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-    epa = [r for r in rows[2:] if "k_epa" in r[ki]]
+    epa = [r for r in rows[2:] if "k_epa<" in r[ki]]
     tot = sum(float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]] for r in epa)
     json.dump({"k_epa_dram_bytes_per_pair": tot / 1e6, "pairs_profiled": 1_000_000,
                "launches_summed": len(epa),
