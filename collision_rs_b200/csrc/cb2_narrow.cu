@@ -818,11 +818,212 @@ __global__ void __launch_bounds__(256) k_collect_overflow(const uint8_t* __restr
     }
 }
 
+// Warp-cooperative EPA3::process with the reference's SERIAL edge-list semantics, for the pairs the
+// tier kernels hand back (non-manifold polytopes: a directed edge occurs twice, so the parallel
+// horizon of k_epa does not apply; or polytopes past 208 faces).  One warp per pair, the polytope in
+// shared memory:
+//   closest face, visibility of every face, Face::new of the new faces   -> all 32 lanes
+//   the swap_remove sweep with remove_or_add_edge (epa3d.rs:147-175, 212-219) -> lane 0, literally,
+//     but only over the VISIBLE faces (the visibility bit mask lets it jump over the others: during
+//     the sweep every position past the cursor still holds its original face)
+// A serial single-thread version over global memory (epa_process<global_store>) took 2.3 ms for one
+// 100-iteration / 246-face pair — 12 % of a 4 M-pair step on the GPU that drew that pair; it stays
+// as the fallback for polytopes that outgrow the shared-memory store.
+constexpr int COOP_FACES = 1536;
+constexpr int COOP_EDGES = 2048;
+struct coop_store {
+    float4 fnd[COOP_FACES];
+    uint32_t fidx[COOP_FACES];
+    float4 pv[EPA_MAX_VERTS];
+    float4 pa[EPA_MAX_VERTS];
+    uint16_t edges[COOP_EDGES];
+    uint32_t vmask[COOP_FACES / 32];
+};
+CB2_DI f3 cs_pv(const coop_store& P, uint32_t i) {
+    const float4 v = P.pv[i];
+    return mk3(v.x, v.y, v.z);
+}
+CB2_DI void cs_face_new(coop_store& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
+    const f3 va = cs_pv(P, a);
+    const f3 ab = cs_pv(P, b) - va;
+    const f3 ac = cs_pv(P, c) - va;
+    const f3 n = normalize(cross(ab, ac));
+    P.fnd[slot] = make_float4(n.x, n.y, n.z, dot(n, va));
+    P.fidx[slot] = a | (b << 8) | (c << 16);
+}
+// every lane runs this with identical arguments; control flow is warp-uniform
+__device__ __noinline__ uint8_t epa_process_coop(coop_store& P, const pair_in& p, const simplex<true>& s,
+                                                 float tol, uint32_t max_iterations, contact_out& out) {
+    const int lane = threadIdx.x & 31;
+    if (lane < 4) {
+        P.pv[lane] = make_float4(s.v[lane].x, s.v[lane].y, s.v[lane].z, 0.f);
+        P.pa[lane] = make_float4(s.a[lane].x, s.a[lane].y, s.a[lane].z, 0.f);
+    }
+    __syncwarp();
+    if (lane < 4) {  // Face::new (3,2,1) (3,1,0) (3,0,2) (2,0,1), epa3d.rs:201-208
+        const uint32_t tri = lane == 0 ? 0x010203u : (lane == 1 ? 0x000103u : (lane == 2 ? 0x020003u : 0x010002u));
+        cs_face_new(P, lane, tri & 255u, (tri >> 8) & 255u, tri >> 16);
+    }
+    __syncwarp();
+    int nv = 4, nf = 4;
+    uint32_t it = 1;
+    for (;;) {
+        if (nf == 0) return ST_PANIC_EPA_EMPTY;
+        // closest_face_to_origin (:137-145): first strictly smallest distance; a NaN at index 0 sticks
+        float bd = INFINITY;
+        uint32_t bi = 0xFFFFFFFFu;
+        for (int f = lane; f < nf; f += 32) {
+            const float d = P.fnd[f].w;
+            if (d < bd) {
+                bd = d;
+                bi = (uint32_t)f;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, bd, off);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ob < bd || (ob == bd && oi < bi)) {
+                bd = ob;
+                bi = oi;
+            }
+        }
+        const float d0 = P.fnd[0].w;
+        const int best = (d0 != d0 || bi == 0xFFFFFFFFu) ? 0 : (int)bi;
+        const float4 fb = P.fnd[best];
+        const f3 n = mk3(fb.x, fb.y, fb.z);
+        f3 sv, sa;
+        minkowski<true>(p, n, sv, sa);
+        if (fsub(dot(sv, n), fb.w) < tol || it >= max_iterations) {
+            const uint32_t idx = P.fidx[best];
+            const uint32_t i0 = idx & 255u, i1 = (idx >> 8) & 255u, i2 = (idx >> 16) & 255u;
+            float u, v, w;
+            barycentric_vector(n * fb.w, cs_pv(P, i0), cs_pv(P, i1), cs_pv(P, i2), u, v, w);
+            const float4 a0 = P.pa[i0], a1 = P.pa[i1], a2 = P.pa[i2];
+            out.normal = n;
+            out.depth = fb.w;
+            out.point = (mk3(a0.x, a0.y, a0.z) * u + mk3(a1.x, a1.y, a1.z) * v) + mk3(a2.x, a2.y, a2.z) * w;
+            out.toi = 0.0f;
+            return ST_SOME;
+        }
+        // visibility of every face -> bit mask
+        unsigned any_visible = 0u;
+        for (int f0 = 0; f0 < nf; f0 += 32) {
+            const int f = f0 + lane;
+            bool vis = false;
+            if (f < nf) {
+                const float4 fn = P.fnd[f];
+                vis = dot(mk3(fn.x, fn.y, fn.z), sv - cs_pv(P, P.fidx[f] & 255u)) > 0.0f;
+            }
+            const unsigned bits = __ballot_sync(0xffffffffu, vis);
+            any_visible |= bits;
+            if (lane == 0) P.vmask[f0 >> 5] = bits;
+        }
+        if (!any_visible) {
+            // Fixed point: with no visible face Polytope::add removes nothing and adds nothing (the
+            // new vertex is referenced by no face), so every later iteration finds the same closest
+            // face, the same support point and fails the same tolerance test until `it` reaches
+            // max_iterations (epa3d.rs:46-64) — and then returns the contact of this very face.
+            // (NaN normals end here: no comparison with a NaN is ever true.)
+            max_iterations = it;
+            continue;
+        }
+        __syncwarp();
+        // Polytope::add's sweep.  Every lane walks it with the same scalars (uniform control flow);
+        // the linear search of remove_or_add_edge (:212-219) is the part spread over the lanes.
+        int ne = 0;
+        int overflow = 0;
+        {
+            const int nf0 = nf;
+            auto next_visible = [&](int from) {  // first visible ORIGINAL position in [from, nf), else nf
+                while (from < nf) {
+                    const uint32_t wbits = P.vmask[from >> 5] >> (from & 31);
+                    if (wbits) {
+                        const int q = from + __ffs((int)wbits) - 1;
+                        return q < nf ? q : nf;
+                    }
+                    from = (from | 31) + 1;
+                }
+                return nf;
+            };
+            int f = next_visible(0);
+            int orig = f;
+            while (f < nf && !overflow) {
+                if (orig < nf0 && ((P.vmask[orig >> 5] >> (orig & 31)) & 1u)) {
+                    const uint32_t idx = P.fidx[f];
+                    --nf;
+                    __syncwarp();
+                    if (lane == 0) {
+                        P.fnd[f] = P.fnd[nf];  // swap_remove: the tail face lands in the hole
+                        P.fidx[f] = P.fidx[nf];
+                    }
+                    orig = nf;  // positions past f were never written: the tail is original
+                    const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        // remove_or_add_edge: drop the FIRST stored reverse edge, else push
+                        const uint32_t ea = e == 0 ? v0 : (e == 1 ? v1 : v2);
+                        const uint32_t eb = e == 0 ? v1 : (e == 1 ? v2 : v0);
+                        const uint16_t rev = (uint16_t)(eb | (ea << 8));
+                        int k = ne;
+                        for (int k0 = 0; k0 < ne; k0 += 32) {
+                            const int q = k0 + lane;
+                            const unsigned hit = __ballot_sync(0xffffffffu, q < ne && P.edges[q] == rev);
+                            if (hit) {
+                                k = k0 + __ffs((int)hit) - 1;
+                                break;
+                            }
+                        }
+                        if (k < ne) {
+                            // erase position k, keeping the order: read, then write one slot down
+                            for (int m0 = k + 1; m0 < ne; m0 += 32) {
+                                const int m = m0 + lane;
+                                uint16_t val = 0;
+                                if (m < ne) val = P.edges[m];
+                                __syncwarp();
+                                if (m < ne) P.edges[m - 1] = val;
+                                __syncwarp();
+                            }
+                            --ne;
+                        } else if (ne >= COOP_EDGES) {
+                            overflow = 1;
+                        } else {
+                            if (lane == 0) P.edges[ne] = (uint16_t)(ea | (eb << 8));
+                            ++ne;
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    f = next_visible(f + 1);
+                    orig = f;
+                }
+            }
+        }
+        __syncwarp();
+        if (overflow || nv >= EPA_MAX_VERTS || nf + ne > COOP_FACES) return ST_SCRATCH_OVERFLOW;
+        const uint32_t nn = (uint32_t)nv;
+        if (lane == 0) {
+            P.pv[nn] = make_float4(sv.x, sv.y, sv.z, 0.f);
+            P.pa[nn] = make_float4(sa.x, sa.y, sa.z, 0.f);
+        }
+        ++nv;
+        __syncwarp();
+        for (int k = lane; k < ne; k += 32) {
+            const uint32_t e = P.edges[k];
+            cs_face_new(P, nf + k, nn, e & 255u, e >> 8);
+        }
+        nf += ne;
+        ++it;
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(32) k_retry_overflow(narrow_args A, const uint32_t* __restrict__ list,
                                                       const uint32_t* __restrict__ count,
                                                       uint32_t* __restrict__ cursor,
                                                       char* __restrict__ scratch) {
-    if (threadIdx.x != 0) return;
+    __shared__ coop_store CS;
+    const int lane = threadIdx.x;
     uint32_t total = *count;
     if (total > RETRY_LIST_CAP) total = RETRY_LIST_CAP;
     global_store P;
@@ -833,18 +1034,27 @@ __global__ void __launch_bounds__(32) k_retry_overflow(narrow_args A, const uint
     P.pa_ = P.pv_ + EPA_MAX_VERTS;
     P.edges_ = reinterpret_cast<uint16_t*>(P.pa_ + EPA_MAX_VERTS);
     for (;;) {
-        const uint32_t k = atomicAdd(cursor, 1u);
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(cursor, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= total) return;
         const uint64_t i = list[k];
         pair_in p;
         contact_out c = zero_contact();
         uint8_t st = ST_NONE;
+        // every lane loads the pair and runs GJK::intersect redundantly (uniform: same data, same path)
         if (!load_pair(A, i, A.l_t, A.r_t, p)) {
             st = ST_PANIC_INV_SCALE;
         } else {
             simplex<true> s;
             if (gjk_intersect<true>(p, A.settings.max_iterations, s)) {
-                st = epa_process(P, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
+                st = epa_process_coop(CS, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
+                if (st == ST_SCRATCH_OVERFLOW) {
+                    // past the shared-memory store: the serial version over global scratch
+                    if (lane == 0)
+                        st = epa_process(P, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
+                    st = (uint8_t)__shfl_sync(0xffffffffu, (int)st, 0);  // the contact stays on lane 0
+                }
                 if (st != ST_SOME) c = zero_contact();
             }
             if (p.ls.hang | p.rs.hang) {
@@ -852,8 +1062,11 @@ __global__ void __launch_bounds__(32) k_retry_overflow(narrow_args A, const uint
                 c = zero_contact();
             }
         }
-        store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, c);
-        A.out_status[i] = st;
+        if (lane == 0) {
+            store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, c);
+            A.out_status[i] = st;
+        }
+        __syncwarp();
     }
 }
 

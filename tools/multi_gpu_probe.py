@@ -82,5 +82,29 @@ if rank == 0:
     print(f"  sap shard ms per rank {np.round(a[:, 0], 3).tolist()}  -> {n / a[:, 0].max() / 1e3:.1f} M AABBs/s")
     print(f"  narrow phase on own shard ms per rank {np.round(a[:, 1], 3).tolist()} -> "
           f"{tot / a[:, 1].max() / 1e3:.1f} M pairs/s, contacts {int(a[:, 3].sum())}")
+# cfg 5: GJK3::intersection_time_of_impact, 8 M cuboid pairs per GPU (64 M over 8), independent shards
+from collision_rs_b200.abi import CONTACT_DT
+m = int(sys.argv[2]) if len(sys.argv) > 2 else 8_000_000
+w5 = W.cfg5_toi_pairs(m, shard=rank)
+ctx.upload_shapes(w5["shapes"])
+d5 = {k: torch.from_numpy(w5[k].view(np.uint8).reshape(-1).copy()).to(dev)
+      for k in ("l_shape", "r_shape", "l_t0", "l_t1", "r_t0", "r_t1")}
+out5 = torch.zeros(m * CONTACT_DT.itemsize, dtype=torch.uint8, device=dev)
+st5 = torch.zeros(m, dtype=torch.uint8, device=dev)
+ms_toi = timed(lambda: ctx.time_of_impact_dev(d5["l_shape"].data_ptr(), d5["r_shape"].data_ptr(),
+                                              d5["l_t0"].data_ptr(), d5["l_t1"].data_ptr(),
+                                              d5["r_t0"].data_ptr(), d5["r_t1"].data_ptr(), m,
+                                              out5.data_ptr(), st5.data_ptr(), s), reps=3, warm=2)
+r5 = torch.tensor([ms_toi, float((st5 == 1).sum()), float((st5 == 5).sum())], dtype=torch.float64, device=dev)
+all5 = [torch.zeros_like(r5) for _ in range(world)]
+if world > 1:
+    dist.all_gather(all5, r5)
+else:
+    all5 = [r5]
+if rank == 0:
+    a5 = torch.stack(all5).cpu().numpy()
+    print(f"  cfg5 time of impact: {m} pairs per GPU, ms per rank {np.round(a5[:, 0], 3).tolist()} -> "
+          f"{m * world / a5[:, 0].max() / 1e3:.1f} M pairs/s over {world} GPU(s), hits {int(a5[:, 1].sum())}, "
+          f"nonconverged (cap 1024) {int(a5[:, 2].sum())}")
 if world > 1:
     dist.destroy_process_group()
