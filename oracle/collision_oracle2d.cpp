@@ -167,7 +167,11 @@ static inline R dot_index(const Shape& s, int32_t index, V2 d) {
     if (index == -1) return dot(vtx(s, s.vcnt - 1), d);
     return dot(vtx(s, iu), d);
 }
-// polygon.rs:122-168: the neighbour walk used from 10 vertices up
+// polygon.rs:122-168: the neighbour walk used from 10 vertices up.  Reproduced INCLUDING its quirk:
+// after choosing a direction the reference pairs `current_dot = dot(start)` with
+// `index = start + add`, so the first neighbour's dot is never evaluated and the walk can stop on a
+// vertex that is not the extreme one (tests/test_oracle_properties.py shows it happening and checks
+// this restatement against an independent re-reading of the Rust).
 static V2 polygon_walk(const Shape& s, V2 direction, const Xf& t) {
     const V2 d = inverse_transform_vector_unwrap(t, direction);
     const int32_t len = (int32_t)s.vcnt;
