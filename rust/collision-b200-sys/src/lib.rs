@@ -28,6 +28,15 @@ pub const CB2_NONCONVERGED: u8 = 5;
 pub const CB2_PANIC_EPA_EMPTY: u8 = 6;
 pub const CB2_SCRATCH_OVERFLOW: u8 = 7;
 pub const CB2_PANIC_CMP_NAN: u8 = 8;
+pub const CB2_PANIC_EPA2_EDGE: u8 = 9;
+pub const CB2_PANIC_INV_ROT: u8 = 10;
+// cb2_shape2_kind: Primitive2 variants in declaration order
+pub const CB2_PARTICLE2: u32 = 0;
+pub const CB2_LINE2: u32 = 1;
+pub const CB2_CIRCLE: u32 = 2;
+pub const CB2_RECTANGLE: u32 = 3;
+pub const CB2_SQUARE: u32 = 4;
+pub const CB2_POLYGON: u32 = 5;
 
 // cb2_strategy: contact.rs:16-22 discriminants in declaration order
 pub const CB2_FULL_RESOLUTION: u32 = 0;

@@ -67,6 +67,8 @@ fn reraise(status: u8) -> ! {
         sys::CB2_PANIC_ASSERT_RANGE => panic!("assertion failed: in_range(u) && in_range(v) && in_range(w) (simplex3d.rs:150)"),
         sys::CB2_PANIC_INV_SCALE => panic!("called `Option::unwrap()` on a `None` value (primitive/util.rs:18)"),
         sys::CB2_PANIC_EPA_EMPTY => panic!("index out of bounds: the len is 0 but the index is 0 (epa3d.rs:138)"),
+        sys::CB2_PANIC_EPA2_EDGE => panic!("assert_ulps_ne!(S::infinity(), edge.distance) (epa2d.rs:154)"),
+        sys::CB2_PANIC_INV_ROT => panic!("called `Option::unwrap()` on a `None` value (Basis2::invert)"),
         s => panic!("collision-b200: device status {}", s),
     }
 }
@@ -266,5 +268,147 @@ fn apply_permutation<A>(shapes: &mut [A], perm: &[u32]) {
             shapes.swap(k, src);
             k = src;
         }
+    }
+}
+
+
+// ---- 2-D: GJK2 / EPA2 over Primitive2 and Decomposed<Vector2<f32>, Basis2<f32>> -----------------------
+pub type Transform2 = cgmath::Decomposed<cgmath::Vector2<f32>, cgmath::Basis2<f32>>;
+
+/// `Primitive2<f32>` (primitive/primitive2.rs:20-33).
+pub enum Shape2<'a> {
+    Particle,
+    Line { origin: cgmath::Point2<f32>, dest: cgmath::Point2<f32> },
+    Circle { radius: f32 },
+    Rectangle { dim: cgmath::Vector2<f32> },
+    Square { dim: f32 },
+    ConvexPolygon { vertices: &'a [cgmath::Point2<f32>] },
+}
+
+fn xf2(t: &Transform2) -> sys::cb2_xform2 {
+    let m: &cgmath::Matrix2<f32> = t.rot.as_ref();   // column major: x = c0, y = c1
+    sys::cb2_xform2 { scale: t.scale, c0x: m.x.x, c0y: m.x.y, c1x: m.y.x, c1y: m.y.y,
+                      dx: t.disp.x, dy: t.disp.y, reserved: 0.0 }
+}
+
+fn contact2(c: &sys::cb2_contact2) -> Contact<cgmath::Point2<f32>> {
+    let strategy = if c.strategy == sys::CB2_COLLISION_ONLY { CollisionStrategy::CollisionOnly }
+                   else { CollisionStrategy::FullResolution };
+    let mut out = Contact::new_with_point(strategy, cgmath::Vector2::new(c.normal[0], c.normal[1]),
+                                          c.penetration_depth,
+                                          cgmath::Point2::new(c.contact_point[0], c.contact_point[1]));
+    out.time_of_impact = c.time_of_impact;
+    out
+}
+
+impl Context {
+    /// Replaces building `Circle::new` / `Rectangle::new` / ... values; ids index the 2-D table.
+    pub fn upload_shapes2(&mut self, shapes: &[Shape2]) -> Result<Vec<ShapeId>, Error> {
+        let mut recs = Vec::with_capacity(shapes.len());
+        let mut verts: Vec<f32> = Vec::new();
+        for s in shapes {
+            let mut r = sys::cb2_shape2::default();
+            match *s {
+                Shape2::Particle => r.kind = sys::CB2_PARTICLE2,
+                Shape2::Line { origin, dest } => { r.kind = sys::CB2_LINE2; r.p = [origin.x, origin.y, dest.x, dest.y]; }
+                Shape2::Circle { radius } => { r.kind = sys::CB2_CIRCLE; r.p[0] = radius; }
+                Shape2::Rectangle { dim } => { r.kind = sys::CB2_RECTANGLE; r.p[0] = dim.x; r.p[1] = dim.y; }
+                Shape2::Square { dim } => { r.kind = sys::CB2_SQUARE; r.p[0] = dim; }
+                Shape2::ConvexPolygon { vertices } => {
+                    r.kind = sys::CB2_POLYGON;
+                    r.vtx_off = (verts.len() / 2) as u32;
+                    r.vtx_cnt = vertices.len() as u32;
+                    for v in vertices { verts.push(v.x); verts.push(v.y); }
+                }
+            }
+            recs.push(r);
+        }
+        let rc = unsafe { sys::cb2_shapes2_upload(self.raw, recs.as_ptr(), recs.len() as u32, verts.as_ptr(),
+                                                  (verts.len() / 2) as u64) };
+        self.check(rc)?;
+        Ok((0..shapes.len() as u32).map(ShapeId).collect())
+    }
+}
+
+/// `GJK2<f32>` (gjk/mod.rs:27) over a device context.
+pub struct GJK2<'c> {
+    ctx: &'c mut Context,
+    settings: sys::cb2_settings,
+}
+
+impl<'c> GJK2<'c> {
+    pub fn new(ctx: &'c mut Context) -> Self {
+        let mut s = sys::cb2_settings { distance_tolerance: 0.0, continuous_tolerance: 0.0, epa_tolerance: 0.0, max_iterations: 0 };
+        unsafe { sys::cb2_default_settings(&mut s) };
+        GJK2 { ctx, settings: s }
+    }
+
+    /// Batched `GJK2::intersection` (gjk/mod.rs:362-391 -> EPA2::process, epa2d.rs:27-67).
+    pub fn intersection_batch(&mut self, strategy: &CollisionStrategy, left: &[ShapeId], left_transform: &[Transform2],
+                              right: &[ShapeId], right_transform: &[Transform2])
+                              -> Result<Vec<Option<Contact<cgmath::Point2<f32>>>>, Error> {
+        let n = left.len();
+        assert!(right.len() == n && left_transform.len() == n && right_transform.len() == n);
+        let l: Vec<u32> = left.iter().map(|s| s.0).collect();
+        let r: Vec<u32> = right.iter().map(|s| s.0).collect();
+        let lt: Vec<sys::cb2_xform2> = left_transform.iter().map(xf2).collect();
+        let rt: Vec<sys::cb2_xform2> = right_transform.iter().map(xf2).collect();
+        let mut out = vec![sys::cb2_contact2::default(); n];
+        let mut status = vec![0u8; n];
+        let strat = match strategy { CollisionStrategy::FullResolution => sys::CB2_FULL_RESOLUTION, CollisionStrategy::CollisionOnly => sys::CB2_COLLISION_ONLY };
+        let rc = unsafe { sys::cb2_gjk2_intersection(self.ctx.raw, strat, &self.settings, l.as_ptr(), r.as_ptr(),
+                                                     lt.as_ptr(), rt.as_ptr(), n as u64, out.as_mut_ptr(), status.as_mut_ptr()) };
+        self.ctx.check(rc)?;
+        Ok(out.iter().zip(status.iter()).map(|(c, s)| match *s {
+            sys::CB2_NONE => None,
+            sys::CB2_SOME => Some(contact2(c)),
+            other => reraise(other),
+        }).collect())
+    }
+
+    /// Batched `GJK2::distance` (gjk/mod.rs:271-321).
+    pub fn distance_batch(&mut self, left: &[ShapeId], left_transform: &[Transform2],
+                          right: &[ShapeId], right_transform: &[Transform2]) -> Result<Vec<Option<f32>>, Error> {
+        let n = left.len();
+        let l: Vec<u32> = left.iter().map(|s| s.0).collect();
+        let r: Vec<u32> = right.iter().map(|s| s.0).collect();
+        let lt: Vec<sys::cb2_xform2> = left_transform.iter().map(xf2).collect();
+        let rt: Vec<sys::cb2_xform2> = right_transform.iter().map(xf2).collect();
+        let mut out = vec![0f32; n];
+        let mut status = vec![0u8; n];
+        let rc = unsafe { sys::cb2_gjk2_distance(self.ctx.raw, &self.settings, l.as_ptr(), r.as_ptr(), lt.as_ptr(),
+                                                 rt.as_ptr(), n as u64, out.as_mut_ptr(), status.as_mut_ptr()) };
+        self.ctx.check(rc)?;
+        Ok(out.iter().zip(status.iter()).map(|(d, s)| match *s {
+            sys::CB2_NONE => None,
+            sys::CB2_SOME => Some(*d),
+            other => reraise(other),
+        }).collect())
+    }
+
+    /// Batched `GJK2::intersection_time_of_impact` (gjk/mod.rs:163-256); `Err(i)` in the inner
+    /// result marks an element on which the reference's uncapped loop would never return.
+    pub fn intersection_time_of_impact_batch(&mut self, left: &[ShapeId], left_transform: &[std::ops::Range<Transform2>],
+                                             right: &[ShapeId], right_transform: &[std::ops::Range<Transform2>], iter_cap: u32)
+                                             -> Result<Vec<Result<Option<Contact<cgmath::Point2<f32>>>, usize>>, Error> {
+        let n = left.len();
+        let l: Vec<u32> = left.iter().map(|s| s.0).collect();
+        let r: Vec<u32> = right.iter().map(|s| s.0).collect();
+        let l0: Vec<sys::cb2_xform2> = left_transform.iter().map(|t| xf2(&t.start)).collect();
+        let l1: Vec<sys::cb2_xform2> = left_transform.iter().map(|t| xf2(&t.end)).collect();
+        let r0: Vec<sys::cb2_xform2> = right_transform.iter().map(|t| xf2(&t.start)).collect();
+        let r1: Vec<sys::cb2_xform2> = right_transform.iter().map(|t| xf2(&t.end)).collect();
+        let mut out = vec![sys::cb2_contact2::default(); n];
+        let mut status = vec![0u8; n];
+        let rc = unsafe { sys::cb2_gjk2_time_of_impact(self.ctx.raw, &self.settings, l.as_ptr(), r.as_ptr(), l0.as_ptr(),
+                                                       l1.as_ptr(), r0.as_ptr(), r1.as_ptr(), n as u64, iter_cap,
+                                                       out.as_mut_ptr(), status.as_mut_ptr()) };
+        self.ctx.check(rc)?;
+        Ok(out.iter().zip(status.iter()).enumerate().map(|(i, (c, s))| match *s {
+            sys::CB2_NONE => Ok(None),
+            sys::CB2_SOME => Ok(Some(contact2(c))),
+            sys::CB2_NONCONVERGED => Err(i),
+            other => reraise(other),
+        }).collect())
     }
 }
