@@ -178,6 +178,10 @@ int cb2_shapes_upload_faces(cb2_ctx* ctx, const cb2_shape* shapes, uint32_t n_sh
 
 /* ---- narrow phase, HOST buffers (H2D, kernels, D2H inside the call) -----------
  * out / status hold n records; out[i] is valid only where status[i] == CB2_SOME.
+ * The batch streams through the device in chunks (copy-in, kernels and copy-out of different chunks
+ * overlap; pinned host buffers make the copies truly asynchronous).  A shape index past the table
+ * (a Rust slice index would panic) fails the whole call with CB2_ERR_ARG; it is detected chunk by
+ * chunk, so the contents of out / status after a FAILED call are unspecified.
  *
  * cb2_gjk3_intersection  replaces GJK3::intersection      (gjk/mod.rs:362-391)
  * cb2_gjk3_distance      replaces GJK3::distance          (gjk/mod.rs:271-321)
