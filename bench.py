@@ -138,9 +138,22 @@ def cpu_baseline(w, sample, threads=None):
     t = time.perf_counter()
     o.intersection(*args, nthreads=threads)
     dt = time.perf_counter() - t
-    return {"value": m / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {m} pairs of the same workload, oracle port "
-                      f"(g++ -O2 -ffp-contract=off), {threads} threads, {dt:.2f} s"}
+    out = {"value": m / dt, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"first {m} pairs of the same workload, oracle port "
+                     f"(g++ -O2 -ffp-contract=off), {threads} threads, {dt:.2f} s"}
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case, as specified — 10 k random
+    # Cuboid-Cuboid pairs, FullResolution, ONE thread (best of 3 passes)
+    from collision_rs_b200 import workloads as W
+    w1 = W.cfg1_cuboid_pairs(10_000)
+    best = None
+    for _ in range(3):
+        t = time.perf_counter()
+        o.intersection(0, w1["shapes"], None, w1["l_shape"], w1["r_shape"], w1["l_t"], w1["r_t"], nthreads=1)
+        d1 = time.perf_counter() - t
+        best = d1 if best is None or d1 < best else best
+    out["cfg1_single_thread"] = {"pairs": 10_000, "ms": best * 1e3, "pairs_per_s": 10_000 / best,
+                                 "what": "GJK3+EPA3 FullResolution on 10k Cuboid-Cuboid pairs, oracle port, 1 thread"}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -433,6 +446,24 @@ def extras(ctx, torch, dev, stream):
                                           dist_out.data_ptr(), st.data_ptr(), s))
     res["cfg2_mixed_collision_only"] = {"pairs": n, "ms": ms_c, "pairs_per_s": n / ms_c * 1e3}
     res["cfg2_mixed_distance"] = {"pairs": n, "ms": ms_d, "pairs_per_s": n / ms_d * 1e3}
+    # ... and per type pair (Sphere-Cuboid distance is dominated by the 100-iteration cap)
+    kl, kr = w["shapes"]["kind"][w["l_shape"]], w["shapes"]["kind"][w["r_shape"]]
+    names = {0: "sphere", 1: "cuboid"}
+    for a_ in (0, 1):
+        for b_ in (0, 1):
+            sel = np.nonzero((kl == a_) & (kr == b_))[0]
+            m = len(sel)
+            db = {k: dv(np.ascontiguousarray(w[k][sel])) for k in ("l_shape", "r_shape", "l_t", "r_t")}
+            ms_c = timed(lambda: ctx.intersection_dev(1, db["l_shape"].data_ptr(), db["r_shape"].data_ptr(),
+                                                      db["l_t"].data_ptr(), db["r_t"].data_ptr(), m,
+                                                      out.data_ptr(), st.data_ptr(), s))
+            hit = float((st[:m] == 1).float().mean())
+            ms_d = timed(lambda: ctx.distance_dev(db["l_shape"].data_ptr(), db["r_shape"].data_ptr(),
+                                                  db["l_t"].data_ptr(), db["r_t"].data_ptr(), m,
+                                                  dist_out.data_ptr(), st.data_ptr(), s))
+            res[f"cfg2_{names[a_]}_{names[b_]}"] = {
+                "pairs": m, "collision_only_pairs_per_s": m / ms_c * 1e3, "hit_fraction": hit,
+                "distance_pairs_per_s": m / ms_d * 1e3, "distance_some_fraction": float((st[:m] == 1).float().mean())}
     # cfg4: SAP on 1M AABBs feeding the narrow phase
     n = 1_000_000
     w = W.cfg4_aabbs(n)
