@@ -1296,14 +1296,14 @@ static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings
     std::memset(&A, 0, sizeof(A));
     const bool epa = op == 0 && strategy == CB2_FULL_RESOLUTION;
     if (epa) {
-        if (!c->d_cnt2[slot]) CK(c, cudaMalloc(&c->d_cnt2[slot], 2 * sizeof(uint32_t)));
+        if (!c->d_cnt2[slot]) CK(c, cudaMalloc(&c->d_cnt2[slot], 8 * sizeof(uint32_t)));
         if (c->ws2_cap[slot] < n) {
             if (c->d_hits2[slot]) cudaFree(c->d_hits2[slot]);
             if (c->d_sx2[slot]) cudaFree(c->d_sx2[slot]);
             c->d_hits2[slot] = nullptr;
             c->d_sx2[slot] = nullptr;
             c->ws2_cap[slot] = 0;
-            CK(c, cudaMalloc(&c->d_hits2[slot], n * sizeof(uint32_t)));
+            CK(c, cudaMalloc(&c->d_hits2[slot], 3 * n * sizeof(uint32_t)));
             CK(c, cudaMalloc(&c->d_sx2[slot], n * 48));
             c->ws2_cap[slot] = n;
         }
@@ -1327,7 +1327,7 @@ static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings
     A.out_distance = out_d;
     A.out_status = status;
     CK(c, launch_narrow2(op, A, c->sm_count, st));
-    c->launches += epa ? 2 : 1;
+    c->launches += epa ? 3 : 1;
     return CB2_OK;
 }
 

@@ -161,11 +161,11 @@ struct narrow2_args {           // all device pointers
     float* out_distance;
     uint8_t* out_status;
     // GJK -> EPA2 hand-off workspace (FullResolution intersection only; owned by the ctx)
-    uint32_t* counters;  // 2 words
-    uint32_t* hits;      // n words
+    uint32_t* counters;  // 8 words
+    uint32_t* hits;      // 3 n words: pair per hit | small-tier queue | large-tier queue
     void* simplex;       // n x 48 bytes
 };
-// op: 0 intersection (k_gjk2_intersection [+ k_epa2]), 1 distance, 2 time of impact
+// op: 0 intersection (k_gjk2_intersection [+ the two k_epa2 tiers]), 1 distance, 2 time of impact
 cudaError_t launch_narrow2(int op, const narrow2_args& A, int sm_count, cudaStream_t st);
 
 }  // namespace cb2

@@ -130,6 +130,7 @@ __device__ __noinline__ f2 support_point2(const shape2& s, const xform2& t, f2 d
         }
     } else if (s.vcnt < 10) {  // polygon.rs:33-42: get_max_point
         float bd = -INFINITY;
+#pragma unroll 3
         for (uint32_t k = 0; k < s.vcnt; ++k) {
             const f2 c = vtx(s, k);
             const float dt = dot(c, d);
@@ -161,14 +162,32 @@ __device__ __noinline__ f2 support_point2(const shape2& s, const xform2& t, f2 d
             float current_dot = max_dot;
             if (index == len) index = 0;
             if (index == -1) index = len - 1;
+            // The walk visits consecutive vertices (mod len) and every step needs only the NEXT
+            // vertex's dot; the vertices of the next four steps are fetched together, so the chain
+            // of dependent L2 round trips is a quarter as long.  Same dots, same comparisons.
+            auto step_of = [&](int i) { i += add; return i == len ? 0 : (i == -1 ? len - 1 : i); };
+            float nb0 = 0.0f, nb1 = 0.0f, nb2 = 0.0f, nb3 = 0.0f;
+            int avail = 0;
             while (index != start_index) {
-                const float next_dot = dot_index(s, index + add, d);
+                if (avail == 0) {
+                    const int i1 = step_of(index), i2 = step_of(i1), i3 = step_of(i2), i4 = step_of(i3);
+                    const f2 v1 = vtx(s, (uint32_t)i1), v2 = vtx(s, (uint32_t)i2), v3 = vtx(s, (uint32_t)i3),
+                             v4 = vtx(s, (uint32_t)i4);
+                    nb0 = dot(v1, d);
+                    nb1 = dot(v2, d);
+                    nb2 = dot(v3, d);
+                    nb3 = dot(v4, d);
+                    avail = 4;
+                }
+                const float next_dot = nb0;  // == dot_index(vertices, index + add, direction)
                 if (current_dot > previous_dot && current_dot > next_dot) break;
                 previous_dot = current_dot;
                 current_dot = next_dot;
-                index += add;
-                if (index == len) index = 0;
-                if (index == -1) index = len - 1;
+                index = step_of(index);
+                nb0 = nb1;
+                nb1 = nb2;
+                nb2 = nb3;
+                --avail;
             }
             best = vtx(s, (uint32_t)index);
         }
@@ -269,8 +288,10 @@ struct narrow2_args_dev {
     float* out_distance;
     uint8_t* out_status;
     // GJK -> EPA2 hand-off (FullResolution intersection only)
-    uint32_t* counters;  // [0] hits queued, [1] queue cursor; zeroed per batch
-    uint32_t* hits;      // pair index per hit
+    uint32_t* counters;  // [0] hits; [2],[3] small queue length, cursor; [4],[5] large queue; zeroed per batch
+    uint32_t* hits;      // pair index per hit (slot)
+    uint32_t* queue_small;  // hit slots for the small-polygon EPA2 tier
+    uint32_t* queue_large;  // ... and for the 104-point tier (also fed by small-tier overflows)
     float4* simplex;     // 3 x (v.xy, sup_a.xy) per hit
 };
 
@@ -298,18 +319,27 @@ CB2_DI float4 edge_of(f2 a, f2 b) {
     return make_float4(n.x, n.y, dot(n, a), 0.0f);
 }
 
+// vertices a shape can contribute to the Minkowski difference's hull (a circle: unbounded)
+CB2_DI uint32_t hull_vertices(const shape2& s) {
+    return s.kind == CB2_PARTICLE2 ? 1u
+         : s.kind == CB2_LINE2 ? 2u
+         : (s.kind == CB2_RECTANGLE || s.kind == CB2_SQUARE) ? 4u
+         : s.kind == CB2_POLYGON ? s.vcnt : 1000u;
+}
+
 // GJK2::intersection (gjk/mod.rs:362-391), stage 1: GJK::intersect (:101-146), one thread per pair.
 // Misses, panics and CollisionOnly hits are final here; a FullResolution hit hands its 3-point
 // simplex to k_epa2 through the hit list (one warp-aggregated reservation per warp).
 __global__ void __launch_bounds__(128) k_gjk2_intersection(narrow2_args_dev A) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < A.n;
-    bool to_epa = false;
+    bool to_epa = false, small = false;
     simplex2 s;
     s.len = 0;
     if (valid) {
         const shape2 l = load_shape2(A.shapes, A.verts, __ldg(A.l_shape + i));
         const shape2 r = load_shape2(A.shapes, A.verts, __ldg(A.r_shape + i));
+        small = hull_vertices(l) + hull_vertices(r) <= 8u;
         const xform2 lt = load_xform2(A.l_t, i), rt = load_xform2(A.r_t, i);
         uint8_t status = CB2_NONE;
         const uint32_t panic = pair_panic(l, lt, r, rt);
@@ -347,13 +377,27 @@ __global__ void __launch_bounds__(128) k_gjk2_intersection(narrow2_args_dev A) {
         uint32_t base = 0;
         if (lane == __ffs(m) - 1) base = atomicAdd(&A.counters[0], (uint32_t)__popc(m));
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        uint32_t slot = 0;
         if (to_epa) {
-            const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+            slot = base + __popc(m & ((1u << lane) - 1u));
             A.hits[slot] = (uint32_t)i;
             float4* sx = A.simplex + 3 * (size_t)slot;
             sx[0] = make_float4(s.p0.v.x, s.p0.v.y, s.p0.a.x, s.p0.a.y);
             sx[1] = make_float4(s.p1.v.x, s.p1.v.y, s.p1.a.x, s.p1.a.y);
             sx[2] = make_float4(s.p2.v.x, s.p2.v.y, s.p2.a.x, s.p2.a.y);
+        }
+        // two EPA2 queues: pairs whose Minkowski difference has at most 8 vertices (rectangles,
+        // squares, lines, particles, tiny polygons) go to the small-polygon tier
+        const unsigned ms = __ballot_sync(0xffffffffu, to_epa && small);
+        const unsigned ml = m & ~ms;
+        uint32_t bs = 0, bl = 0;
+        if (ms && lane == __ffs(ms) - 1) bs = atomicAdd(&A.counters[2], (uint32_t)__popc(ms));
+        if (ml && lane == __ffs(ml) - 1) bl = atomicAdd(&A.counters[4], (uint32_t)__popc(ml));
+        if (ms) bs = __shfl_sync(0xffffffffu, bs, __ffs(ms) - 1);
+        if (ml) bl = __shfl_sync(0xffffffffu, bl, __ffs(ml) - 1);
+        if (to_epa) {
+            if (small) A.queue_small[bs + __popc(ms & ((1u << lane) - 1u))] = slot;
+            else A.queue_large[bl + __popc(ml & ((1u << lane) - 1u))] = slot;
         }
     }
 }
@@ -372,18 +416,34 @@ __global__ void __launch_bounds__(128) k_gjk2_intersection(narrow2_args_dev A) {
 // closest_edge's "first strictly smallest distance in Vec order" is the minimum over D in ANY
 // order unless two edges tie exactly; the scan counts ties and only then walks the ring from the
 // head (the point at Vec index 0: an insertion on the wrap-around edge becomes the new head).
+// Two tiers.  SMALL (12 points): pairs whose Minkowski difference has at most 8 hull vertices —
+// points, successors and distances all in shared memory ([k][thread], 252 B per lane: 7 blocks per
+// SM, no local memory at all); a polygon that outgrows it anyway (near-duplicate support points)
+// is re-queued for the large tier and restarts there from its simplex.  LARGE (104 points: the
+// 100-iteration cap): distances in shared memory, points and successors in local memory.
 constexpr int EPA2_THREADS = 128;
+constexpr int EPA2_SMALL_CAP = 12;
+template <int CAP, bool SMALL>
 __global__ void __launch_bounds__(EPA2_THREADS) k_epa2(narrow2_args_dev A) {
-    extern __shared__ float Dsh[];  // [EPA2_CAP][EPA2_THREADS]
-    float* D = Dsh + threadIdx.x;
+    extern __shared__ float4 smem4[];
+    // SMALL: float4 P[CAP][T] | float D[CAP][T] | uint8 nx[CAP][T];   LARGE: float D[CAP][T]
+    float4* Ps = smem4 + threadIdx.x;
+    float* D = (SMALL ? reinterpret_cast<float*>(smem4 + CAP * EPA2_THREADS) : reinterpret_cast<float*>(smem4)) +
+               threadIdx.x;
+    uint8_t* nxs = reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(smem4 + CAP * EPA2_THREADS) +
+                                              CAP * EPA2_THREADS) + threadIdx.x;
+    float4 Pl[SMALL ? 1 : CAP];
+    uint8_t nxl[SMALL ? 1 : CAP];
+    auto P = [&](int q) -> float4& { return SMALL ? Ps[q * EPA2_THREADS] : Pl[SMALL ? 0 : q]; };
+    auto nx = [&](int q) -> uint8_t& { return SMALL ? nxs[q * EPA2_THREADS] : nxl[SMALL ? 0 : q]; };
     const int lane = threadIdx.x & 31;
-    const uint32_t n_hits = A.counters[0];
-    float4 P[EPA2_CAP];
-    uint8_t nx[EPA2_CAP];
+    const uint32_t* queue = SMALL ? A.queue_small : A.queue_large;
+    const uint32_t n_hits = A.counters[SMALL ? 2 : 4];
+    uint32_t* cursor = &A.counters[SMALL ? 3 : 5];
     enum { FETCH, RUN, EXIT };
     int state = FETCH;
     int len = 0, head = 0;
-    uint32_t pair = 0, k = 0;
+    uint32_t pair = 0, k = 0, slot = 0;
     shape2 l, r;
     xform2 lt, rt;
     l.kind = r.kind = CB2_PARTICLE2;
@@ -397,14 +457,15 @@ __global__ void __launch_bounds__(EPA2_THREADS) k_epa2(narrow2_args_dev A) {
         const unsigned need = __ballot_sync(0xffffffffu, state == FETCH);
         if (need) {
             uint32_t base = 0;
-            if (lane == __ffs(need) - 1) base = atomicAdd(&A.counters[1], (uint32_t)__popc(need));
+            if (lane == __ffs(need) - 1) base = atomicAdd(cursor, (uint32_t)__popc(need));
             base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
             if (state == FETCH) {
-                const uint32_t slot = base + __popc(need & ((1u << lane) - 1u));
-                if (slot >= n_hits) {
+                const uint32_t qi = base + __popc(need & ((1u << lane) - 1u));
+                if (qi >= n_hits) {
                     state = EXIT;
                     len = 0;
                 } else {
+                    slot = queue[qi];
                     pair = A.hits[slot];
                     l = load_shape2(A.shapes, A.verts, __ldg(A.l_shape + pair));
                     r = load_shape2(A.shapes, A.verts, __ldg(A.r_shape + pair));
@@ -412,12 +473,12 @@ __global__ void __launch_bounds__(EPA2_THREADS) k_epa2(narrow2_args_dev A) {
                     rt = load_xform2(A.r_t, pair);
                     const float4* sx = A.simplex + 3 * (size_t)slot;
                     const float4 a = sx[0], b = sx[1], c = sx[2];
-                    P[0] = a;
-                    P[1] = b;
-                    P[2] = c;
-                    nx[0] = 1;
-                    nx[1] = 2;
-                    nx[2] = 0;
+                    P(0) = a;
+                    P(1) = b;
+                    P(2) = c;
+                    nx(0) = 1;
+                    nx(1) = 2;
+                    nx(2) = 0;
                     D[0 * EPA2_THREADS] = edge_of(mk2(a.x, a.y), mk2(b.x, b.y)).z;
                     D[1 * EPA2_THREADS] = edge_of(mk2(b.x, b.y), mk2(c.x, c.y)).z;
                     D[2 * EPA2_THREADS] = edge_of(mk2(c.x, c.y), mk2(a.x, a.y)).z;
@@ -450,7 +511,7 @@ __global__ void __launch_bounds__(EPA2_THREADS) k_epa2(narrow2_args_dev A) {
         }
         if (run && ties > 1) {  // exact tie: the reference takes the first in Vec order
             int q = head;
-            while (!(D[q * EPA2_THREADS] == dmin)) q = nx[q];
+            while (!(D[q * EPA2_THREADS] == dmin)) q = nx(q);
             arg = q;
             dmin = D[q * EPA2_THREADS];  // -0.0 == +0.0: keep the winner's own bits
         }
@@ -458,12 +519,12 @@ __global__ void __launch_bounds__(EPA2_THREADS) k_epa2(narrow2_args_dev A) {
         const bool step = run && !panicked && k < A.settings.max_iterations;
         bool finished = run && !step;
         // the winning edge a -> b (b is the reference's edge.index)
-        const int ea = arg, eb = run ? nx[arg] : 0;
+        const int ea = arg, eb = run ? nx(arg) : 0;
         float4 pa4 = make_float4(0.f, 0.f, 0.f, 0.f), pb4 = pa4;
         f2 en = zero2();
         if (run && !panicked) {
-            pa4 = P[ea];
-            pb4 = P[eb];
+            pa4 = P(ea);
+            pb4 = P(eb);
             const float4 e = edge_of(mk2(pa4.x, pa4.y), mk2(pb4.x, pb4.y));
             en = mk2(e.x, e.y);
         }
@@ -472,11 +533,16 @@ __global__ void __launch_bounds__(EPA2_THREADS) k_epa2(narrow2_args_dev A) {
             const sup2 p = from_minkowski2(l, lt, r, rt, en);
             if (fsub(dot(p.v, en), dmin) < A.settings.epa_tolerance) {
                 finished = true;
+            } else if (SMALL && len >= CAP) {
+                // outgrew the small tier: the large tier redoes this pair from its simplex
+                A.queue_large[atomicAdd(&A.counters[4], 1u)] = slot;
+                state = FETCH;
+                len = 0;
             } else {
                 // simplex.insert(index, p): p goes between a and b
-                P[len] = make_float4(p.v.x, p.v.y, p.a.x, p.a.y);
-                nx[len] = (uint8_t)eb;
-                nx[ea] = (uint8_t)len;
+                P(len) = make_float4(p.v.x, p.v.y, p.a.x, p.a.y);
+                nx(len) = (uint8_t)eb;
+                nx(ea) = (uint8_t)len;
                 // insertion at Vec index 0 (the wrap-around edge tail -> head): p is the new head
                 if (eb == head) head = len;
                 D[ea * EPA2_THREADS] = edge_of(mk2(pa4.x, pa4.y), p.v).z;
@@ -502,6 +568,22 @@ __global__ void __launch_bounds__(EPA2_THREADS) k_epa2(narrow2_args_dev A) {
             len = 0;
         }
     }
+}
+
+template <int CAP, bool SMALL>
+static cudaError_t launch_epa2(const narrow2_args_dev& A, uint64_t n, int sm_count, cudaStream_t st) {
+    auto kern = k_epa2<CAP, SMALL>;
+    const size_t smem = (size_t)CAP * EPA2_THREADS * (SMALL ? sizeof(float4) + sizeof(float) + 1 : sizeof(float));
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EPA2_THREADS, smem) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    unsigned eb = (unsigned)(per_sm * sm_count);
+    const unsigned want = (unsigned)((n + EPA2_THREADS - 1) / EPA2_THREADS);
+    if (eb > want) eb = want;
+    kern<<<eb, EPA2_THREADS, smem, st>>>(A);
+    return cudaGetLastError();
 }
 
 // GJK2::distance, gjk/mod.rs:271-321
@@ -627,28 +709,25 @@ cudaError_t launch_narrow2(int op, const narrow2_args& H, int sm_count, cudaStre
     A.out_status = H.out_status;
     A.counters = H.counters;
     A.hits = H.hits;
+    A.queue_small = H.hits ? H.hits + H.n : nullptr;
+    A.queue_large = H.hits ? H.hits + 2 * H.n : nullptr;
     A.simplex = reinterpret_cast<float4*>(H.simplex);
     if (H.n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((H.n + 127) / 128);
     if (op == 0) {
         const bool full = H.strategy == CB2_FULL_RESOLUTION;
         if (full) {
-            cudaError_t e = cudaMemsetAsync(H.counters, 0, 2 * sizeof(uint32_t), st);
+            cudaError_t e = cudaMemsetAsync(H.counters, 0, 8 * sizeof(uint32_t), st);
             if (e != cudaSuccess) return e;
         }
         k_gjk2_intersection<<<blocks, 128, 0, st>>>(A);
         if (full) {
-            // persistent: every SM filled to the occupancy limit, lanes refill from the hit queue
-            const size_t smem = (size_t)EPA2_CAP * EPA2_THREADS * sizeof(float);
-            cudaFuncSetAttribute(k_epa2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa2, EPA2_THREADS, smem) !=
-                    cudaSuccess || per_sm < 1)
-                per_sm = 1;
-            unsigned eb = (unsigned)(per_sm * sm_count);
-            const unsigned want = (unsigned)((H.n + EPA2_THREADS - 1) / EPA2_THREADS);
-            if (eb > want) eb = want;
-            k_epa2<<<eb, EPA2_THREADS, smem, st>>>(A);
+            // persistent lanes refilling from the two hit queues; the large tier runs second because
+            // the small tier may hand pairs over
+            cudaError_t e = launch_epa2<EPA2_SMALL_CAP, true>(A, H.n, sm_count, st);
+            if (e != cudaSuccess) return e;
+            e = launch_epa2<EPA2_CAP, false>(A, H.n, sm_count, st);
+            if (e != cudaSuccess) return e;
         }
     } else if (op == 1) k_gjk2_distance<<<blocks, 128, 0, st>>>(A);
     else k_gjk2_time_of_impact<<<blocks, 128, 0, st>>>(A);
