@@ -38,6 +38,7 @@ struct cb2_ctx {
     cb2_shape2* d_shapes2 = nullptr;
     float* d_verts2 = nullptr;
     uint32_t n_shapes2 = 0;
+    bool long_tails2 = false;  // see narrow2_args::long_tails (decided at cb2_shapes2_upload)
     // GJK2 -> EPA2 hand-off, one per host-API stream (device-API calls use slot 0)
     uint32_t* d_cnt2[CB2_NS_MAX] = {};
     uint32_t* d_hits2[CB2_NS_MAX] = {};
@@ -1295,8 +1296,10 @@ static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings
     narrow2_args A;
     std::memset(&A, 0, sizeof(A));
     const bool epa = op == 0 && strategy == CB2_FULL_RESOLUTION;
+    if (!c->d_cnt2[slot]) CK(c, cudaMalloc(&c->d_cnt2[slot], 8 * sizeof(uint32_t)));
+    A.counters = c->d_cnt2[slot];  // queue cursors of the persistent kernels
+    A.long_tails = c->long_tails2;
     if (epa) {
-        if (!c->d_cnt2[slot]) CK(c, cudaMalloc(&c->d_cnt2[slot], 8 * sizeof(uint32_t)));
         if (c->ws2_cap[slot] < n) {
             if (c->d_hits2[slot]) cudaFree(c->d_hits2[slot]);
             if (c->d_sx2[slot]) cudaFree(c->d_sx2[slot]);
@@ -1392,9 +1395,13 @@ int cb2_shapes2_upload(cb2_ctx* c, const cb2_shape2* shapes, uint32_t n_shapes, 
                        uint64_t n_verts) {
     if (!c) return CB2_ERR_ARG;
     if (!shapes || n_shapes == 0) return fail(c, CB2_ERR_ARG, "empty shape table");
+    bool has_circle = false, has_other = false, has_walk = false;
     for (uint32_t i = 0; i < n_shapes; ++i) {
         const cb2_shape2& s = shapes[i];
         if (s.kind > CB2_POLYGON) return fail(c, CB2_ERR_ARG, "unknown 2-D shape kind");
+        has_circle |= s.kind == CB2_CIRCLE;
+        has_other |= s.kind != CB2_CIRCLE;
+        has_walk |= s.kind == CB2_POLYGON && s.vtx_cnt >= 10;
         if (s.kind == CB2_POLYGON) {
             if ((uint64_t)s.vtx_off + s.vtx_cnt > n_verts || (s.vtx_cnt && !verts_xy))
                 return fail(c, CB2_ERR_ARG, "polygon vertex range out of bounds");
@@ -1414,6 +1421,7 @@ int cb2_shapes2_upload(cb2_ctx* c, const cb2_shape2* shapes, uint32_t n_shapes, 
     if (n_verts)
         CK(c, cudaMemcpy(c->d_verts2, verts_xy, sizeof(float) * 2 * n_verts, cudaMemcpyHostToDevice));
     c->n_shapes2 = n_shapes;
+    c->long_tails2 = (has_circle && has_other) || has_walk;
     return CB2_OK;
 }
 

@@ -164,6 +164,9 @@ struct narrow2_args {           // all device pointers
     uint32_t* counters;  // 8 words
     uint32_t* hits;      // 3 n words: pair per hit | small-tier queue | large-tier queue
     void* simplex;       // n x 48 bytes
+    bool long_tails;     // the shape table mixes kinds whose distance loops differ by 10-50x in length
+                         // (circles against anything else run to the iteration cap; long polygon
+                         // walks): use the lane-refill kernels.  Uniform tables finish sooner without.
 };
 // op: 0 intersection (k_gjk2_intersection [+ the two k_epa2 tiers]), 1 distance, 2 time of impact
 cudaError_t launch_narrow2(int op, const narrow2_args& A, int sm_count, cudaStream_t st);

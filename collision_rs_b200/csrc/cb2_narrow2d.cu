@@ -12,6 +12,8 @@
 // an edge's (normal, distance) is a pure function of its two end points, and an insertion replaces
 // exactly one edge by two, so the kernel caches them per edge and the per-iteration scan becomes
 // compares only — O(n) instead of O(n) sqrt+div, on pairs (circles) that run to 100 iterations.
+#include <cstdlib>
+
 #include "cb2_kernels.h"
 #include "cb2_math.cuh"
 
@@ -622,6 +624,108 @@ __global__ void __launch_bounds__(128) k_gjk2_distance(narrow2_args_dev A) {
     A.out_status[i] = status;
 }
 
+// GJK2::distance with persistent lanes: every round of the loop is ONE Minkowski support for every
+// lane (the two seed supports of gjk/mod.rs:296-297 and the loop body's support share the slot), and
+// a lane whose pair finished pulls the next pair.  Circle pairs routinely run to the 100-iteration
+// cap while boxes finish in 2-4 iterations; without the refill one such lane holds 31 others.
+__global__ void __launch_bounds__(128) k_gjk2_distance_p(narrow2_args_dev A) {
+    const int lane = threadIdx.x & 31;
+    enum { FETCH, SEED1, SEED2, ITER, EXIT };
+    int state = FETCH;
+    uint64_t i = 0;
+    uint32_t it = 0;
+    shape2 l, r;
+    xform2 lt, rt;
+    l.kind = r.kind = CB2_PARTICLE2;
+    l.p0 = l.p1 = l.p2 = l.p3 = r.p0 = r.p1 = r.p2 = r.p3 = 0.0f;
+    l.verts = r.verts = A.verts;
+    l.vcnt = r.vcnt = 0;
+    lt = load_xform2(A.l_t, 0);
+    rt = lt;
+    simplex2 s;
+    s.len = 0;
+    s.p0.v = s.p0.a = s.p1.v = s.p1.a = s.p2.v = s.p2.a = zero2();
+    f2 d0 = zero2();
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, state == FETCH);
+        if (need) {
+            unsigned long long base = 0;
+            if (lane == __ffs(need) - 1) base = atomicAdd(&A.counters[6], (uint32_t)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+            if (state == FETCH) {
+                i = base + __popc(need & ((1u << lane) - 1u));
+                if (i >= A.n) {
+                    state = EXIT;
+                } else {
+                    l = load_shape2(A.shapes, A.verts, __ldg(A.l_shape + i));
+                    r = load_shape2(A.shapes, A.verts, __ldg(A.r_shape + i));
+                    lt = load_xform2(A.l_t, i);
+                    rt = load_xform2(A.r_t, i);
+                    const uint32_t panic = pair_panic(l, lt, r, rt);
+                    if (panic) {
+                        A.out_distance[i] = 0.0f;
+                        A.out_status[i] = (uint8_t)panic;  // stays in FETCH: refilled next round
+                    } else {
+                        d0 = transform_point(rt, zero2()) - transform_point(lt, zero2());
+                        if (ulps_eq_zero(d0)) d0 = mk2(1.0f, 1.0f);
+                        s.len = 0;
+                        state = SEED1;
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, state == EXIT)) break;
+        // ---- the direction of this round's support ----
+        f2 dir = zero2();
+        bool sup = false, done = false;
+        uint8_t status = CB2_NONE;
+        float out = 0.0f;
+        if (state == SEED1) {
+            dir = d0;
+            sup = true;
+        } else if (state == SEED2) {
+            dir = -d0;
+            sup = true;
+        } else if (state == ITER) {
+            const f2 dd = closest_point_to_origin2(s);
+            if (ulps_eq_zero(dd)) {
+                done = true;  // None: the shapes touch or overlap
+            } else {
+                dir = -dd;
+                sup = true;
+            }
+        }
+        sup2 p;
+        p.v = p.a = zero2();
+        if (sup) p = from_minkowski2(l, lt, r, rt, dir);
+        if (sup) {
+            if (state == SEED1) {
+                sx_push(s, p);
+                state = SEED2;
+            } else if (state == SEED2) {
+                sx_push(s, p);
+                it = 0;
+                state = ITER;
+                if (A.settings.max_iterations == 0) done = true;
+            } else {
+                if (fsub(dot(p.v, dir), dot(s.p0.v, dir)) < A.settings.distance_tolerance) {
+                    out = magnitude(dir);
+                    status = CB2_SOME;
+                    done = true;
+                } else {
+                    sx_push(s, p);
+                    if (++it >= A.settings.max_iterations) done = true;
+                }
+            }
+        }
+        if (done) {
+            A.out_distance[i] = out;
+            A.out_status[i] = status;
+            state = FETCH;
+        }
+    }
+}
+
 // GJK2::intersection_time_of_impact, gjk/mod.rs:163-256 (+ iter_cap on the uncapped loop)
 __global__ void __launch_bounds__(128) k_gjk2_time_of_impact(narrow2_args_dev A) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -729,7 +833,22 @@ cudaError_t launch_narrow2(int op, const narrow2_args& H, int sm_count, cudaStre
             e = launch_epa2<EPA2_CAP, false>(A, H.n, sm_count, st);
             if (e != cudaSuccess) return e;
         }
-    } else if (op == 1) k_gjk2_distance<<<blocks, 128, 0, st>>>(A);
+    } else if (op == 1) {
+        static const bool plain = std::getenv("CB2_NO_REFILL") && std::getenv("CB2_NO_REFILL")[0] == '1';
+        if (plain || !H.counters || !H.long_tails) {
+            k_gjk2_distance<<<blocks, 128, 0, st>>>(A);
+        } else {
+            cudaError_t e = cudaMemsetAsync(H.counters, 0, 8 * sizeof(uint32_t), st);
+            if (e != cudaSuccess) return e;
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gjk2_distance_p, 128, 0) != cudaSuccess ||
+                per_sm < 1)
+                per_sm = 1;
+            unsigned pb = (unsigned)(per_sm * sm_count);
+            if (pb > blocks) pb = blocks;
+            k_gjk2_distance_p<<<pb, 128, 0, st>>>(A);
+        }
+    }
     else k_gjk2_time_of_impact<<<blocks, 128, 0, st>>>(A);
     return cudaGetLastError();
 }
