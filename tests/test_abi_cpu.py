@@ -47,6 +47,37 @@ def test_pod_layouts():
     assert abi.CONTACT_DT.fields["depth"][1] == 16 and abi.CONTACT_DT.fields["toi"][1] == 32
 
 
+def test_2d_pod_layouts_and_oracle_mirrors():
+    from oracle import binding as ob
+    assert abi.SHAPE2_DT.itemsize == 32 and abi.XFORM2_DT.itemsize == 32 and abi.CONTACT2_DT.itemsize == 28
+    assert abi.CONTACT2_DT.fields["depth"][1] == 12 and abi.CONTACT2_DT.fields["toi"][1] == 24
+    # the oracle's ctypes mirrors are the same layouts (the two sides never share code)
+    for a, b in ((abi.SHAPE_DT, ob.SHAPE_DT), (abi.XFORM_DT, ob.XFORM_DT), (abi.CONTACT_DT, ob.CONTACT_DT),
+                 (abi.SHAPE2_DT, ob.SHAPE2_DT), (abi.XFORM2_DT, ob.XFORM2_DT), (abi.CONTACT2_DT, ob.CONTACT2_DT)):
+        assert a == b
+
+
+def test_rust_sys_crate_declares_every_entry_point_and_pod():
+    """rust/collision-b200-sys cannot be compiled here (no toolchain); at least keep it in step with
+    the header: every function and every struct the header declares is declared there too."""
+    hdr = open(os.path.join(ROOT, "include", "collision_b200.h")).read()
+    rs = open(os.path.join(ROOT, "rust", "collision-b200-sys", "src", "lib.rs")).read()
+    for fn in set(re.findall(r"\b(cb2_[a-z0-9_]+)\s*\(", hdr)):
+        assert re.search(r"pub fn %s\s*\(" % fn, rs), fn
+    for st in set(re.findall(r"typedef struct (cb2_[a-z0-9_]+) \{", hdr)):
+        assert re.search(r"pub struct %s\b" % st, rs), st
+    # struct sizes: count the 4-byte fields of each #[repr(C)] mirror
+    sizes = {"cb2_shape": 24, "cb2_xform": 32, "cb2_contact": 36, "cb2_settings": 16, "cb2_aabb3": 24,
+             "cb2_aabb2": 16, "cb2_shape2": 32, "cb2_xform2": 32, "cb2_contact2": 28}
+    for name, size in sizes.items():
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rs, re.S).group(1)
+        n = 0
+        for ty in re.findall(r"pub \w+:\s*([^,\n]+),", body):
+            m = re.match(r"\[(\w+);\s*(\d+)\]", ty.strip())
+            n += int(m.group(2)) if m else 1
+        assert 4 * n == size, (name, n)
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
