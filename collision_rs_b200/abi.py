@@ -66,6 +66,8 @@ SYMBOLS = [
     "cb2_world_aabbs", "cb2_world_aabbs_dev",
     "cb2_shapes2_upload", "cb2_gjk2_intersection", "cb2_gjk2_distance", "cb2_gjk2_time_of_impact",
     "cb2_gjk2_intersection_dev", "cb2_gjk2_distance_dev", "cb2_gjk2_time_of_impact_dev",
+    "cb2_composites2_upload", "cb2_gjk2_intersection_complex", "cb2_gjk2_distance_complex",
+    "cb2_gjk2_time_of_impact_complex",
 ]
 
 _lib = None
@@ -129,6 +131,10 @@ def load():
     lib.cb2_gjk2_intersection_dev.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp, vp]
     lib.cb2_gjk2_distance_dev.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp, vp]
     lib.cb2_gjk2_time_of_impact_dev.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp]
+    lib.cb2_composites2_upload.argtypes = [vp, vp, vp, vp, u32]
+    lib.cb2_gjk2_intersection_complex.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_gjk2_distance_complex.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_gjk2_time_of_impact_complex.argtypes = [vp, u32, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp]
     _lib = lib
     return lib
 

@@ -65,6 +65,12 @@ struct cb2_ctx {
     float4* d_comp_local = nullptr;
     uint32_t n_comp = 0;
     std::vector<uint32_t> h_comp_off;
+    // ... and the 2-D composite table (cb2_composites2_upload)
+    uint32_t* d_comp2_off = nullptr;
+    uint32_t* d_comp2_shape = nullptr;
+    float4* d_comp2_local = nullptr;
+    uint32_t n_comp2 = 0;
+    std::vector<uint32_t> h_comp2_off;
     void* d_cx = nullptr;
     size_t cx_cap = 0;
     void* d_misc = nullptr;  // host-API SAP / AABB buffers
@@ -214,6 +220,9 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_comp_off) cudaFree(c->d_comp_off);
     if (c->d_comp_shape) cudaFree(c->d_comp_shape);
     if (c->d_comp_local) cudaFree(c->d_comp_local);
+    if (c->d_comp2_off) cudaFree(c->d_comp2_off);
+    if (c->d_comp2_shape) cudaFree(c->d_comp2_shape);
+    if (c->d_comp2_local) cudaFree(c->d_comp2_local);
     if (c->d_cx) cudaFree(c->d_cx);
     for (int i = 0; i < cb2_ctx::NS; ++i) {
         free_ws(c->ws[i]);
@@ -1131,32 +1140,47 @@ extern "C" int cb2_composites_upload(cb2_ctx* c, const uint32_t* part_off, const
     return CB2_OK;
 }
 
-static int complex_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_settings* settings,
-                        const uint32_t* l_comp, const uint32_t* r_comp, const cb2_xform* l_t0,
-                        const cb2_xform* l_t1, const cb2_xform* r_t0, const cb2_xform* r_t1,
-                        uint64_t n, uint32_t iter_cap, cb2_contact* out_c, float* out_d,
+static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings* settings,
+                       const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t0,
+                       const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
+                       uint32_t iter_cap, cb2_contact2* out_c, float* out_d, uint8_t* status,
+                       cudaStream_t st, int slot);
+
+// d2: the 2-D instantiation — cb2_xform2 transforms (same 32-byte stride as cb2_xform), cb2_contact2
+// records, the 2-D composite table and the GJK2 kernels
+static int complex_host(cb2_ctx* c, bool d2, op_kind op, uint32_t strategy, const cb2_settings* settings,
+                        const uint32_t* l_comp, const uint32_t* r_comp, const void* l_t0,
+                        const void* l_t1, const void* r_t0, const void* r_t1,
+                        uint64_t n, uint32_t iter_cap, void* out_c, float* out_d,
                         uint8_t* status) {
     if (!c) return CB2_ERR_ARG;
+    static_assert(sizeof(cb2_xform) == sizeof(cb2_xform2), "both transforms travel as 2 x float4");
+    const uint32_t* d_off = d2 ? c->d_comp2_off : c->d_comp_off;
+    const uint32_t* d_cshape = d2 ? c->d_comp2_shape : c->d_comp_shape;
+    const float4* d_clocal = d2 ? c->d_comp2_local : c->d_comp_local;
+    const uint32_t n_comp = d2 ? c->n_comp2 : c->n_comp;
+    const std::vector<uint32_t>& h_off = d2 ? c->h_comp2_off : c->h_comp_off;
+    const size_t contact_bytes = d2 ? sizeof(cb2_contact2) : sizeof(cb2_contact);
     int rc = check_settings(c, settings);
     if (rc) return rc;
     if (op != OP_DISTANCE && strategy > CB2_COLLISION_ONLY) return fail(c, CB2_ERR_ARG, "bad strategy");
     if (n == 0) return CB2_OK;
-    if (!c->d_comp_off) return fail(c, CB2_ERR_ARG, "cb2_composites_upload has not been called");
+    if (!d_off) return fail(c, CB2_ERR_ARG, "the composite table has not been uploaded");
     if (!l_comp || !r_comp || !l_t0 || !r_t0 || !status) return fail(c, CB2_ERR_ARG, "null argument");
     if (op == OP_DISTANCE ? !out_d : !out_c) return fail(c, CB2_ERR_ARG, "null output");
     if (op == OP_TOI && (!l_t1 || !r_t1)) return fail(c, CB2_ERR_ARG, "null end transform");
     uint64_t total = 0;
     for (uint64_t i = 0; i < n; ++i) {
-        if (l_comp[i] >= c->n_comp || r_comp[i] >= c->n_comp)
+        if (l_comp[i] >= n_comp || r_comp[i] >= n_comp)
             return fail(c, CB2_ERR_ARG, "composite index out of range");
-        total += (uint64_t)(c->h_comp_off[l_comp[i] + 1] - c->h_comp_off[l_comp[i]]) *
-                 (c->h_comp_off[r_comp[i] + 1] - c->h_comp_off[r_comp[i]]);
+        total += (uint64_t)(h_off[l_comp[i] + 1] - h_off[l_comp[i]]) *
+                 (h_off[r_comp[i] + 1] - h_off[r_comp[i]]);
     }
     if (total > 0x7FFFFFFFull) return fail(c, CB2_ERR_ARG, "more than 2^31-1 part pairs in one call");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream[0];
     const int n_xf = op == OP_TOI ? 4 : 2;
-    const size_t out_rec = op == OP_DISTANCE ? sizeof(float) : sizeof(cb2_contact);
+    const size_t out_rec = op == OP_DISTANCE ? sizeof(float) : contact_bytes;
     const uint64_t T = total ? total : 1;
     size_t scan_tmp = 0;
     cx_scan(nullptr, &scan_tmp, nullptr, nullptr, n, st);
@@ -1181,16 +1205,17 @@ static int complex_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_set
     }
     char* base = static_cast<char*>(c->d_cx);
     // order of the transform slots: l_t0, r_t0, l_t1, r_t1
-    const cb2_xform* src[4] = {l_t0, r_t0, l_t1, r_t1};
+    const void* src[4] = {l_t0, r_t0, l_t1, r_t1};
     CK(c, cudaMemcpyAsync(base + o_lc, l_comp, 4 * n, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(base + o_rc, r_comp, 4 * n, cudaMemcpyHostToDevice, st));
     for (int x = 0; x < n_xf; ++x)
         CK(c, cudaMemcpyAsync(base + o_t[x], src[x], sizeof(cb2_xform) * n, cudaMemcpyHostToDevice, st));
     complex_args X;
     std::memset(&X, 0, sizeof(X));
-    X.comp_off = c->d_comp_off;
-    X.comp_shape = c->d_comp_shape;
-    X.comp_local = c->d_comp_local;
+    X.dim2 = d2;
+    X.comp_off = d_off;
+    X.comp_shape = d_cshape;
+    X.comp_local = d_clocal;
     X.l_comp = reinterpret_cast<uint32_t*>(base + o_lc);
     X.r_comp = reinterpret_cast<uint32_t*>(base + o_rc);
     X.l_t0 = reinterpret_cast<float4*>(base + o_t[0]);
@@ -1210,10 +1235,10 @@ static int complex_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_set
         X.sub_l_t1 = reinterpret_cast<float4*>(base + o_st[2]);
         X.sub_r_t1 = reinterpret_cast<float4*>(base + o_st[3]);
     }
-    X.sub_contact = reinterpret_cast<cb2_contact*>(base + o_sout);
+    X.sub_contact = base + o_sout;
     X.sub_distance = reinterpret_cast<float*>(base + o_sout);
     X.sub_status = reinterpret_cast<uint8_t*>(base + o_sstat);
-    X.out_contact = reinterpret_cast<cb2_contact*>(base + o_out);
+    X.out_contact = base + o_out;
     X.out_distance = reinterpret_cast<float*>(base + o_out);
     X.out_status = reinterpret_cast<uint8_t*>(base + o_stat);
     CK(c, launch_cx_count(X, st));
@@ -1221,7 +1246,17 @@ static int complex_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_set
     CK(c, cx_scan(base + o_scan, &tb, X.sub_count, X.sub_off, n, st));
     CK(c, launch_cx_expand(X, st));
     c->launches += 3;
-    if (total) {
+    if (total && d2) {
+        rc = narrow2_dev(c, op == OP_INTERSECTION ? 0 : (op == OP_DISTANCE ? 1 : 2),
+                         op == OP_INTERSECTION ? strategy : CB2_FULL_RESOLUTION, settings, X.sub_l_shape,
+                         X.sub_r_shape, reinterpret_cast<const cb2_xform2*>(X.sub_l_t0),
+                         reinterpret_cast<const cb2_xform2*>(X.sub_l_t1),
+                         reinterpret_cast<const cb2_xform2*>(X.sub_r_t0),
+                         reinterpret_cast<const cb2_xform2*>(X.sub_r_t1), total, iter_cap,
+                         reinterpret_cast<cb2_contact2*>(base + o_sout), reinterpret_cast<float*>(base + o_sout),
+                         reinterpret_cast<uint8_t*>(base + o_sstat), st, 0);
+        if (rc) return rc;
+    } else if (total) {
         narrow_args A;
         std::memset(&A, 0, sizeof(A));
         A.l_shape = X.sub_l_shape;
@@ -1244,7 +1279,7 @@ static int complex_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_set
     if (op == OP_DISTANCE)
         CK(c, cudaMemcpyAsync(out_d, base + o_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     else
-        CK(c, cudaMemcpyAsync(out_c, base + o_out, sizeof(cb2_contact) * n, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaMemcpyAsync(out_c, base + o_out, contact_bytes * n, cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(status, base + o_stat, n, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     return CB2_OK;
@@ -1255,13 +1290,13 @@ int cb2_gjk3_intersection_complex(cb2_ctx* c, uint32_t strategy, const cb2_setti
                                   const uint32_t* l_comp, const uint32_t* r_comp,
                                   const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
                                   cb2_contact* out, uint8_t* status) {
-    return complex_host(c, OP_INTERSECTION, strategy, settings, l_comp, r_comp, l_t, nullptr, r_t,
+    return complex_host(c, false, OP_INTERSECTION, strategy, settings, l_comp, r_comp, l_t, nullptr, r_t,
                         nullptr, n, 0, out, nullptr, status);
 }
 int cb2_gjk3_distance_complex(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_comp,
                               const uint32_t* r_comp, const cb2_xform* l_t, const cb2_xform* r_t,
                               uint64_t n, float* out, uint8_t* status) {
-    return complex_host(c, OP_DISTANCE, 0, settings, l_comp, r_comp, l_t, nullptr, r_t, nullptr, n, 0,
+    return complex_host(c, false, OP_DISTANCE, 0, settings, l_comp, r_comp, l_t, nullptr, r_t, nullptr, n, 0,
                         nullptr, out, status);
 }
 int cb2_gjk3_time_of_impact_complex(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
@@ -1269,7 +1304,7 @@ int cb2_gjk3_time_of_impact_complex(cb2_ctx* c, uint32_t strategy, const cb2_set
                                     const cb2_xform* l_t0, const cb2_xform* l_t1,
                                     const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
                                     uint32_t iter_cap, cb2_contact* out, uint8_t* status) {
-    return complex_host(c, OP_TOI, strategy, settings, l_comp, r_comp, l_t0, l_t1, r_t0, r_t1, n,
+    return complex_host(c, false, OP_TOI, strategy, settings, l_comp, r_comp, l_t0, l_t1, r_t0, r_t1, n,
                         iter_cap, out, nullptr, status);
 }
 }
@@ -1292,7 +1327,7 @@ static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings
                        const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t0,
                        const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
                        uint32_t iter_cap, cb2_contact2* out_c, float* out_d, uint8_t* status,
-                       cudaStream_t st, int slot = 0) {
+                       cudaStream_t st, int slot) {
     narrow2_args A;
     std::memset(&A, 0, sizeof(A));
     const bool epa = op == 0 && strategy == CB2_FULL_RESOLUTION;
@@ -1452,7 +1487,7 @@ int cb2_gjk2_intersection_dev(cb2_ctx* c, uint32_t strategy, const cb2_settings*
     if (rc || n == 0) return rc;
     CK(c, cudaSetDevice(c->device));
     return narrow2_dev(c, 0, strategy, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, n, 0, out,
-                       nullptr, status, static_cast<cudaStream_t>(stream));
+                       nullptr, status, static_cast<cudaStream_t>(stream), 0);
 }
 int cb2_gjk2_distance_dev(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
                           const uint32_t* r_shape, const cb2_xform2* l_t, const cb2_xform2* r_t,
@@ -1461,7 +1496,7 @@ int cb2_gjk2_distance_dev(cb2_ctx* c, const cb2_settings* settings, const uint32
     if (rc || n == 0) return rc;
     CK(c, cudaSetDevice(c->device));
     return narrow2_dev(c, 1, 0, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, n, 0, nullptr, out,
-                       status, static_cast<cudaStream_t>(stream));
+                       status, static_cast<cudaStream_t>(stream), 0);
 }
 int cb2_gjk2_time_of_impact_dev(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
                                 const uint32_t* r_shape, const cb2_xform2* l_t0, const cb2_xform2* l_t1,
@@ -1471,7 +1506,61 @@ int cb2_gjk2_time_of_impact_dev(cb2_ctx* c, const cb2_settings* settings, const 
     if (rc || n == 0) return rc;
     CK(c, cudaSetDevice(c->device));
     return narrow2_dev(c, 2, 0, settings, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, iter_cap, out,
-                       nullptr, status, static_cast<cudaStream_t>(stream));
+                       nullptr, status, static_cast<cudaStream_t>(stream), 0);
 }
 
+}  // extern "C"
+
+// ---- 2-D composite shapes: GJK2::intersection_complex / distance_complex / ..._time_of_impact ----------
+extern "C" {
+int cb2_composites2_upload(cb2_ctx* c, const uint32_t* part_off, const uint32_t* part_shape,
+                           const cb2_xform2* part_local, uint32_t n_comp) {
+    if (!c || !part_off || (n_comp && part_off[n_comp] && (!part_shape || !part_local)))
+        return fail(c, CB2_ERR_ARG, "null argument");
+    if (!c->d_shapes2) return fail(c, CB2_ERR_ARG, "cb2_shapes2_upload has not been called");
+    const uint32_t n_parts = part_off[n_comp];
+    if (part_off[0] != 0) return fail(c, CB2_ERR_ARG, "part_off[0] must be 0");
+    for (uint32_t k = 0; k < n_comp; ++k)
+        if (part_off[k] > part_off[k + 1]) return fail(c, CB2_ERR_ARG, "part_off must not decrease");
+    for (uint32_t k = 0; k < n_parts; ++k)
+        if (part_shape[k] >= c->n_shapes2) return fail(c, CB2_ERR_ARG, "part shape index out of range");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaDeviceSynchronize());
+    if (c->d_comp2_off) cudaFree(c->d_comp2_off);
+    if (c->d_comp2_shape) cudaFree(c->d_comp2_shape);
+    if (c->d_comp2_local) cudaFree(c->d_comp2_local);
+    c->d_comp2_off = c->d_comp2_shape = nullptr;
+    c->d_comp2_local = nullptr;
+    c->n_comp2 = 0;
+    CK(c, cudaMalloc(&c->d_comp2_off, sizeof(uint32_t) * ((size_t)n_comp + 1)));
+    CK(c, cudaMalloc(&c->d_comp2_shape, sizeof(uint32_t) * (n_parts ? n_parts : 1)));
+    CK(c, cudaMalloc(&c->d_comp2_local, sizeof(cb2_xform2) * (n_parts ? n_parts : 1)));
+    CK(c, cudaMemcpy(c->d_comp2_off, part_off, sizeof(uint32_t) * ((size_t)n_comp + 1), cudaMemcpyHostToDevice));
+    if (n_parts) {
+        CK(c, cudaMemcpy(c->d_comp2_shape, part_shape, sizeof(uint32_t) * n_parts, cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->d_comp2_local, part_local, sizeof(cb2_xform2) * n_parts, cudaMemcpyHostToDevice));
+    }
+    c->h_comp2_off.assign(part_off, part_off + n_comp + 1);
+    c->n_comp2 = n_comp;
+    return CB2_OK;
+}
+int cb2_gjk2_intersection_complex(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                                  const uint32_t* l_comp, const uint32_t* r_comp, const cb2_xform2* l_t,
+                                  const cb2_xform2* r_t, uint64_t n, cb2_contact2* out, uint8_t* status) {
+    return complex_host(c, true, OP_INTERSECTION, strategy, settings, l_comp, r_comp, l_t, nullptr, r_t, nullptr,
+                        n, 0, out, nullptr, status);
+}
+int cb2_gjk2_distance_complex(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_comp,
+                              const uint32_t* r_comp, const cb2_xform2* l_t, const cb2_xform2* r_t,
+                              uint64_t n, float* out, uint8_t* status) {
+    return complex_host(c, true, OP_DISTANCE, 0, settings, l_comp, r_comp, l_t, nullptr, r_t, nullptr, n, 0,
+                        nullptr, out, status);
+}
+int cb2_gjk2_time_of_impact_complex(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                                    const uint32_t* l_comp, const uint32_t* r_comp, const cb2_xform2* l_t0,
+                                    const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1,
+                                    uint64_t n, uint32_t iter_cap, cb2_contact2* out, uint8_t* status) {
+    return complex_host(c, true, OP_TOI, strategy, settings, l_comp, r_comp, l_t0, l_t1, r_t0, r_t1, n, iter_cap,
+                        out, nullptr, status);
+}
 }  // extern "C"

@@ -48,6 +48,32 @@ CB2_DI void store_concat(float4* __restrict__ out, uint64_t i, const raw_xf& a, 
     out[2 * i + 1] = make_float4(q.z, d.x, d.y, d.z);
 }
 
+// ---- the 2-D instantiation: Decomposed<Vector2, Basis2> (cb2_xform2: scale, c0.xy, c1.xy | disp.xy) ----
+struct raw_xf2 {
+    float scale, c0x, c0y, c1x, c1y, dx, dy;
+};
+CB2_DI raw_xf2 load_raw2(const float4* __restrict__ t, uint64_t i) {
+    const float4 a = __ldg(t + 2 * i), b = __ldg(t + 2 * i + 1);
+    raw_xf2 r;
+    r.scale = a.x; r.c0x = a.y; r.c0y = a.z; r.c1x = a.w;
+    r.c1y = b.x; r.dx = b.y; r.dy = b.z;
+    return r;
+}
+// Matrix2 * Vector2 = (row0 . v, row1 . v) with dot(a, b) = a.x*b.x + a.y*b.y
+CB2_DI void mat2_mul(const raw_xf2& m, float vx, float vy, float& ox, float& oy) {
+    ox = fadd(fmul(m.c0x, vx), fmul(m.c1x, vy));
+    oy = fadd(fmul(m.c0y, vx), fmul(m.c1y, vy));
+}
+// concat: {s*os, rot*orot (Matrix2 * Matrix2, column by column), rot.rotate(odisp*s) + disp}
+CB2_DI void store_concat2(float4* __restrict__ out, uint64_t i, const raw_xf2& a, const raw_xf2& b) {
+    float c0x, c0y, c1x, c1y, dx, dy;
+    mat2_mul(a, b.c0x, b.c0y, c0x, c0y);
+    mat2_mul(a, b.c1x, b.c1y, c1x, c1y);
+    mat2_mul(a, fmul(b.dx, a.scale), fmul(b.dy, a.scale), dx, dy);
+    out[2 * i] = make_float4(fmul(a.scale, b.scale), c0x, c0y, c1x);
+    out[2 * i + 1] = make_float4(c1y, fadd(dx, a.dx), fadd(dy, a.dy), 0.0f);
+}
+
 __global__ void __launch_bounds__(256) k_cx_count(complex_args X) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= X.n) return;
@@ -57,19 +83,43 @@ __global__ void __launch_bounds__(256) k_cx_count(complex_args X) {
     X.sub_count[i] = nl * nr;
 }
 
+template <bool D2>
 __global__ void __launch_bounds__(128) k_cx_expand(complex_args X) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= X.n) return;
     const uint32_t lc = __ldg(X.l_comp + i), rc = __ldg(X.r_comp + i);
     const uint32_t lo = __ldg(X.comp_off + lc), le = __ldg(X.comp_off + lc + 1);
     const uint32_t ro = __ldg(X.comp_off + rc), re = __ldg(X.comp_off + rc + 1);
+    uint64_t s = X.sub_off[i];
+    if (D2) {
+        const raw_xf2 lt0 = load_raw2(X.l_t0, i), rt0 = load_raw2(X.r_t0, i);
+        raw_xf2 lt1 = lt0, rt1 = rt0;
+        if (X.l_t1) {
+            lt1 = load_raw2(X.l_t1, i);
+            rt1 = load_raw2(X.r_t1, i);
+        }
+        for (uint32_t a = lo; a < le; ++a) {
+            const raw_xf2 la = load_raw2(X.comp_local, a);
+            for (uint32_t b = ro; b < re; ++b, ++s) {
+                const raw_xf2 rb = load_raw2(X.comp_local, b);
+                X.sub_l_shape[s] = __ldg(X.comp_shape + a);
+                X.sub_r_shape[s] = __ldg(X.comp_shape + b);
+                store_concat2(X.sub_l_t0, s, lt0, la);
+                store_concat2(X.sub_r_t0, s, rt0, rb);
+                if (X.l_t1) {
+                    store_concat2(X.sub_l_t1, s, lt1, la);
+                    store_concat2(X.sub_r_t1, s, rt1, rb);
+                }
+            }
+        }
+        return;
+    }
     const raw_xf lt0 = load_raw(X.l_t0, i), rt0 = load_raw(X.r_t0, i);
     raw_xf lt1 = lt0, rt1 = rt0;
     if (X.l_t1) {
         lt1 = load_raw(X.l_t1, i);
         rt1 = load_raw(X.r_t1, i);
     }
-    uint64_t s = X.sub_off[i];
     for (uint32_t a = lo; a < le; ++a) {      // same loop order as the reference
         const raw_xf la = load_raw(X.comp_local, a);
         for (uint32_t b = ro; b < re; ++b, ++s) {
@@ -93,6 +143,7 @@ CB2_DI int partial_cmp_f(float a, float b) {  // -1 Less, 0 Equal, 1 Greater, 2 
     return 2;
 }
 
+template <bool D2>
 __global__ void __launch_bounds__(128) k_cx_reduce(complex_args X, uint32_t op, uint32_t strategy) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= X.n) return;
@@ -129,12 +180,20 @@ __global__ void __launch_bounds__(128) k_cx_reduce(complex_args X, uint32_t op, 
             have = false;
             break;
         }
-        const float* c = reinterpret_cast<const float*>(X.sub_contact + s);
         contact_out cur;
-        cur.normal = mk3(c[1], c[2], c[3]);
-        cur.depth = c[4];
-        cur.point = mk3(c[5], c[6], c[7]);
-        cur.toi = c[8];
+        if (D2) {  // cb2_contact2: strategy, normal.xy, depth, point.xy, toi
+            const float* c = reinterpret_cast<const float*>(X.sub_contact) + 7 * s;
+            cur.normal = mk3(c[1], c[2], 0.0f);
+            cur.depth = c[3];
+            cur.point = mk3(c[4], c[5], 0.0f);
+            cur.toi = c[6];
+        } else {
+            const float* c = reinterpret_cast<const float*>(X.sub_contact) + 9 * s;
+            cur.normal = mk3(c[1], c[2], c[3]);
+            cur.depth = c[4];
+            cur.point = mk3(c[5], c[6], c[7]);
+            cur.toi = c[8];
+        }
         if (strategy == CB2_COLLISION_ONLY) {  // return Some(contact) at the first hit
             best = cur;
             have = true;
@@ -160,7 +219,18 @@ __global__ void __launch_bounds__(128) k_cx_reduce(complex_args X, uint32_t op, 
         }
     }
     if (!have) best = zero_contact();
-    store_contact(X.out_contact, i, best_strategy, best);
+    if (D2) {
+        float* o = reinterpret_cast<float*>(X.out_contact) + 7 * i;
+        o[0] = __uint_as_float(best_strategy);
+        o[1] = best.normal.x;
+        o[2] = best.normal.y;
+        o[3] = best.depth;
+        o[4] = best.point.x;
+        o[5] = best.point.y;
+        o[6] = best.toi;
+    } else {
+        store_contact(reinterpret_cast<cb2_contact*>(X.out_contact), i, best_strategy, best);
+    }
     X.out_status[i] = st;
 }
 
@@ -174,11 +244,13 @@ cudaError_t launch_cx_count(const complex_args& X, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t launch_cx_expand(const complex_args& X, cudaStream_t st) {
-    k_cx_expand<<<(unsigned)((X.n + 127) / 128), 128, 0, st>>>(X);
+    if (X.dim2) k_cx_expand<true><<<(unsigned)((X.n + 127) / 128), 128, 0, st>>>(X);
+    else k_cx_expand<false><<<(unsigned)((X.n + 127) / 128), 128, 0, st>>>(X);
     return cudaGetLastError();
 }
 cudaError_t launch_cx_reduce(const complex_args& X, uint32_t op, uint32_t strategy, cudaStream_t st) {
-    k_cx_reduce<<<(unsigned)((X.n + 127) / 128), 128, 0, st>>>(X, op, strategy);
+    if (X.dim2) k_cx_reduce<true><<<(unsigned)((X.n + 127) / 128), 128, 0, st>>>(X, op, strategy);
+    else k_cx_reduce<false><<<(unsigned)((X.n + 127) / 128), 128, 0, st>>>(X, op, strategy);
     return cudaGetLastError();
 }
 

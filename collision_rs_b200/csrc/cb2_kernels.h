@@ -87,6 +87,7 @@ cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, 
 
 // ---- composite shapes (cb2_complex.cu) -----------------------------------------------------------
 struct complex_args {
+    bool dim2;  // the 2-D instantiation: cb2_xform2 transforms (same 32-byte stride), cb2_contact2 records
     // composite table: parts [comp_off[c], comp_off[c+1]) = (comp_shape, comp_local)
     const uint32_t* comp_off;
     const uint32_t* comp_shape;
@@ -109,11 +110,11 @@ struct complex_args {
     float4* sub_l_t1;
     float4* sub_r_t1;
     // sub-pair results
-    const cb2_contact* sub_contact;
+    const void* sub_contact;     // cb2_contact (36 B) or cb2_contact2 (28 B) records
     const float* sub_distance;
     const uint8_t* sub_status;
     // composite results
-    cb2_contact* out_contact;
+    void* out_contact;
     float* out_distance;
     uint8_t* out_status;
 };

@@ -162,6 +162,45 @@ class Context:
             self.h, C.byref(settings), l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, int(iter_cap),
             out, status, stream))
 
+    def upload_composites2(self, part_off, part_shape, part_local):
+        """2-D composites: parts [part_off[c], part_off[c+1]) of (part_shape -> 2-D shape table,
+        part_local: XFORM2_DT)."""
+        part_off = np.ascontiguousarray(part_off, np.uint32)
+        part_shape = np.ascontiguousarray(part_shape, np.uint32)
+        part_local = np.ascontiguousarray(part_local, abi.XFORM2_DT)
+        self._ck(self.lib.cb2_composites2_upload(self.h, ptr(part_off), ptr(part_shape), ptr(part_local),
+                                                 len(part_off) - 1))
+
+    def intersection_complex2(self, strategy, l_comp, r_comp, l_t, r_t, settings=None):
+        settings = settings or Settings.default()
+        n = len(l_comp)
+        out = np.zeros(n, abi.CONTACT2_DT)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk2_intersection_complex(
+            self.h, int(strategy), C.byref(settings), ptr(l_comp), ptr(r_comp), ptr(l_t), ptr(r_t), n,
+            ptr(out), ptr(status)))
+        return out, status
+
+    def distance_complex2(self, l_comp, r_comp, l_t, r_t, settings=None):
+        settings = settings or Settings.default()
+        n = len(l_comp)
+        out = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk2_distance_complex(
+            self.h, C.byref(settings), ptr(l_comp), ptr(r_comp), ptr(l_t), ptr(r_t), n, ptr(out), ptr(status)))
+        return out, status
+
+    def time_of_impact_complex2(self, strategy, l_comp, r_comp, l_t0, l_t1, r_t0, r_t1, settings=None,
+                                iter_cap=1024):
+        settings = settings or Settings.default()
+        n = len(l_comp)
+        out = np.zeros(n, abi.CONTACT2_DT)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk2_time_of_impact_complex(
+            self.h, int(strategy), C.byref(settings), ptr(l_comp), ptr(r_comp), ptr(l_t0), ptr(l_t1),
+            ptr(r_t0), ptr(r_t1), n, int(iter_cap), ptr(out), ptr(status)))
+        return out, status
+
     # ---- narrow phase, host buffers --------------------------------------------------------
     def intersection(self, strategy, l_shape, r_shape, l_t, r_t, settings=None, out=None,
                      status=None):

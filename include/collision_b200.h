@@ -409,6 +409,26 @@ int cb2_gjk2_time_of_impact_dev(cb2_ctx* ctx, const cb2_settings* settings,
                                 uint32_t iter_cap, cb2_contact2* out, uint8_t* status,
                                 void* stream);
 
+/* 2-D composite shapes: GJK2::intersection_complex / distance_complex /
+ * intersection_complex_time_of_impact (the same generic callers, gjk/mod.rs:412-588, over
+ * `&[(Primitive2, Decomposed<Vector2, Basis2>)]`).  Same table layout, loop-order reduction, early
+ * returns and panics as the 3-D entry points above; the table indexes the 2-D shape table.        */
+int cb2_composites2_upload(cb2_ctx* ctx, const uint32_t* part_off /* n_comp + 1 */,
+                           const uint32_t* part_shape, const cb2_xform2* part_local, uint32_t n_comp);
+int cb2_gjk2_intersection_complex(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                                  const uint32_t* l_comp, const uint32_t* r_comp,
+                                  const cb2_xform2* l_t, const cb2_xform2* r_t, uint64_t n,
+                                  cb2_contact2* out, uint8_t* status);
+int cb2_gjk2_distance_complex(cb2_ctx* ctx, const cb2_settings* settings,
+                              const uint32_t* l_comp, const uint32_t* r_comp,
+                              const cb2_xform2* l_t, const cb2_xform2* r_t, uint64_t n,
+                              float* out, uint8_t* status);
+int cb2_gjk2_time_of_impact_complex(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                                    const uint32_t* l_comp, const uint32_t* r_comp,
+                                    const cb2_xform2* l_t0, const cb2_xform2* l_t1,
+                                    const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
+                                    uint32_t iter_cap, cb2_contact2* out, uint8_t* status);
+
 #ifdef __cplusplus
 }
 #endif

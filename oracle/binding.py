@@ -363,3 +363,17 @@ class Oracle2D:
                                      _p(l_t0), _p(l_t1), _p(r_t0), _p(r_t1), C.c_uint64(n),
                                      C.c_uint32(iter_cap), _p(out), _p(status), _p(it), C.c_int(nthreads))
         return (out, status, it) if iters else (out, status)
+
+    def complex(self, op, strategy, shapes, verts, comp_off, comp_shape, comp_local, l_comp, r_comp, l_t0, r_t0,
+                l_t1=None, r_t1=None, settings=None, iter_cap=0, nthreads=1):
+        """op 0 intersection_complex, 1 distance_complex, 2 intersection_complex_time_of_impact."""
+        settings = settings or Settings.default()
+        n = len(l_comp)
+        out_c = np.zeros(n, CONTACT2_DT)
+        out_d = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        self.lib.orc2_gjk2_complex_batch(C.c_uint32(op), C.c_uint32(strategy), C.byref(settings), _p(shapes),
+                                         _p(verts), _p(comp_off), _p(comp_shape), _p(comp_local), _p(l_comp),
+                                         _p(r_comp), _p(l_t0), _p(l_t1), _p(r_t0), _p(r_t1), C.c_uint64(n),
+                                         C.c_uint32(iter_cap), _p(out_c), _p(out_d), _p(status), C.c_int(nthreads))
+        return (out_d if op == 1 else out_c), status

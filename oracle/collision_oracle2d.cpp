@@ -519,6 +519,129 @@ static uint8_t gjk_toi(const cb2_settings& st, const Shape& l, const Xf& lt0, co
     }
 }
 
+// ---- composite shapes: gjk/mod.rs:412-588 with the 2-D instantiation ---------------------------------
+// Decomposed::concat (cgmath 0.18 transform.rs): {scale: s*os, rot: rot*orot, disp: rot.rotate(odisp*s) + disp};
+// Basis2 * Basis2 = Matrix2 * Matrix2 = [lhs * rhs.c0, lhs * rhs.c1] (each a row-dot matrix-vector product)
+static inline Xf concat(const Xf& self, const Xf& other) {
+    Xf r;
+    r.scale = self.scale * other.scale;
+    r.c0 = mat_mul(self.c0, self.c1, other.c0);
+    r.c1 = mat_mul(self.c0, self.c1, other.c1);
+    r.disp = mat_mul(self.c0, self.c1, other.disp * self.scale) + self.disp;
+    return r;
+}
+static inline int partial_cmp(float a, float b) {  // -1 Less, 0 Equal, 1 Greater, 2 None
+    if (a < b) return -1;
+    if (a > b) return 1;
+    if (a == b) return 0;
+    return 2;
+}
+struct Composite {  // &[(Primitive, local transform)]
+    const uint32_t* shape;
+    const cb2_xform2* local;
+    uint32_t n;
+};
+#define CB2_PANIC_CMP_NAN 8  // max_by(partial_cmp(..).unwrap()) on a NaN depth, gjk/mod.rs:455-459
+
+// GJK::intersection_complex, :412-461
+static uint8_t gjk_intersection_complex(uint32_t strategy, const cb2_settings& st, const cb2_shape2* shapes,
+                                        const float* verts, const Composite& L, const Xf& lt,
+                                        const Composite& Rc, const Xf& rt, cb2_contact2* out) {
+    contact_zero(out, strategy);
+    bool have = false;
+    cb2_contact2 best;
+    for (uint32_t a = 0; a < L.n; ++a) {
+        const Xf left_transform = concat(lt, load_xf(L.local[a]));
+        for (uint32_t b = 0; b < Rc.n; ++b) {
+            const Xf right_transform = concat(rt, load_xf(Rc.local[b]));
+            cb2_contact2 c;
+            const uint8_t s = gjk_intersection(strategy, st, load_shape(shapes[L.shape[a]], verts), left_transform,
+                                               load_shape(shapes[Rc.shape[b]], verts), right_transform, &c,
+                                               nullptr, nullptr);
+            if (s == CB2_NONE) continue;
+            if (s != CB2_SOME) return s;  // the reference panics right here
+            if (strategy == CB2_COLLISION_ONLY) {
+                *out = c;
+                return CB2_SOME;
+            }
+            if (!have) {
+                best = c;
+                have = true;
+            } else {
+                // Iterator::max_by: compare(best, c) == Greater keeps best, otherwise takes c
+                const int o = partial_cmp(best.penetration_depth, c.penetration_depth);
+                if (o == 2) return CB2_PANIC_CMP_NAN;
+                if (o != 1) best = c;
+            }
+        }
+    }
+    if (!have) return CB2_NONE;
+    *out = best;
+    return CB2_SOME;
+}
+
+// GJK::distance_complex, :477-516
+static uint8_t gjk_distance_complex(const cb2_settings& st, const cb2_shape2* shapes, const float* verts,
+                                    const Composite& L, const Xf& lt, const Composite& Rc, const Xf& rt,
+                                    float* out) {
+    *out = 0.0f;
+    bool have = false;
+    float m = 0.0f;
+    for (uint32_t a = 0; a < L.n; ++a) {
+        const Xf left_transform = concat(lt, load_xf(L.local[a]));
+        for (uint32_t b = 0; b < Rc.n; ++b) {
+            const Xf right_transform = concat(rt, load_xf(Rc.local[b]));
+            float d;
+            const uint8_t s = gjk_distance(st, load_shape(shapes[L.shape[a]], verts), left_transform,
+                                           load_shape(shapes[Rc.shape[b]], verts), right_transform, &d, nullptr);
+            if (s != CB2_SOME) return s;  // None => return None (colliding); panic => panic
+            m = have ? std::fmin(d, m) : d;  // f32::min: a NaN operand yields the other one
+            have = true;
+        }
+    }
+    if (!have) return CB2_NONE;
+    *out = m;
+    return CB2_SOME;
+}
+
+// GJK::intersection_complex_time_of_impact, :538-588
+static uint8_t gjk_toi_complex(uint32_t strategy, const cb2_settings& st, const cb2_shape2* shapes,
+                               const float* verts, const Composite& L, const Xf& lt0, const Xf& lt1,
+                               const Composite& Rc, const Xf& rt0, const Xf& rt1, uint32_t iter_cap,
+                               cb2_contact2* out) {
+    contact_zero(out, strategy);
+    bool have = false;
+    cb2_contact2 best;
+    for (uint32_t a = 0; a < L.n; ++a) {
+        const Xf l0 = concat(lt0, load_xf(L.local[a]));
+        const Xf l1 = concat(lt1, load_xf(L.local[a]));
+        for (uint32_t b = 0; b < Rc.n; ++b) {
+            const Xf r0 = concat(rt0, load_xf(Rc.local[b]));
+            const Xf r1 = concat(rt1, load_xf(Rc.local[b]));
+            cb2_contact2 c;
+            const uint8_t s = gjk_toi(st, load_shape(shapes[L.shape[a]], verts), l0, l1,
+                                      load_shape(shapes[Rc.shape[b]], verts), r0, r1, iter_cap, &c, nullptr);
+            if (s == CB2_NONE) continue;
+            if (s != CB2_SOME) return s;
+            if (strategy == CB2_COLLISION_ONLY) {
+                c.strategy = CB2_COLLISION_ONLY;
+                *out = c;
+                return CB2_SOME;
+            }
+            if (!have) {
+                best = c;
+                have = true;
+            } else {
+                // Iterator::min_by with unwrap_or(Equal): only Greater replaces the current best
+                if (partial_cmp(best.time_of_impact, c.time_of_impact) == 1) best = c;
+            }
+        }
+    }
+    if (!have) return CB2_NONE;
+    *out = best;
+    return CB2_SOME;
+}
+
 template <typename F>
 static void parallel_for(uint64_t n, int nthreads, F fn) {
     if (nthreads <= 1 || n < 1024) {
@@ -682,6 +805,32 @@ void orc2_gjk2_toi_batch(const cb2_settings* st, const cb2_shape2* shapes, const
                                 load_xf(l_t1[i]), load_shape(shapes[r_shape[i]], verts_xy),
                                 load_xf(r_t0[i]), load_xf(r_t1[i]), iter_cap, &out[i], &it);
             if (iters) iters[i] = it;
+        }
+    });
+}
+
+// composite batch entry point: comp_off[n_comp+1] indexes comp_shape / comp_local; op 0/1/2
+void orc2_gjk2_complex_batch(uint32_t op, uint32_t strategy, const cb2_settings* st, const cb2_shape2* shapes,
+                             const float* verts_xy, const uint32_t* comp_off, const uint32_t* comp_shape,
+                             const cb2_xform2* comp_local, const uint32_t* l_comp, const uint32_t* r_comp,
+                             const cb2_xform2* l_t0, const cb2_xform2* l_t1, const cb2_xform2* r_t0,
+                             const cb2_xform2* r_t1, uint64_t n, uint32_t iter_cap, cb2_contact2* out_c,
+                             float* out_d, uint8_t* status, int nthreads) {
+    if (iter_cap == 0) iter_cap = 1024;
+    parallel_for(n, nthreads, [=](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) {
+            const uint32_t lc = l_comp[i], rc = r_comp[i];
+            const Composite L = {comp_shape + comp_off[lc], comp_local + comp_off[lc], comp_off[lc + 1] - comp_off[lc]};
+            const Composite Rc = {comp_shape + comp_off[rc], comp_local + comp_off[rc], comp_off[rc + 1] - comp_off[rc]};
+            if (op == 0)
+                status[i] = gjk_intersection_complex(strategy, *st, shapes, verts_xy, L, load_xf(l_t0[i]), Rc,
+                                                     load_xf(r_t0[i]), &out_c[i]);
+            else if (op == 1)
+                status[i] = gjk_distance_complex(*st, shapes, verts_xy, L, load_xf(l_t0[i]), Rc, load_xf(r_t0[i]),
+                                                 &out_d[i]);
+            else
+                status[i] = gjk_toi_complex(strategy, *st, shapes, verts_xy, L, load_xf(l_t0[i]), load_xf(l_t1[i]),
+                                            Rc, load_xf(r_t0[i]), load_xf(r_t1[i]), iter_cap, &out_c[i]);
         }
     });
 }

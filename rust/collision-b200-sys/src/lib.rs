@@ -277,4 +277,19 @@ extern "C" {
                                        r_t0: *const cb2_xform2, r_t1: *const cb2_xform2, n: u64,
                                        iter_cap: u32, out: *mut cb2_contact2, status: *mut u8,
                                        stream: *mut c_void) -> c_int;
+    pub fn cb2_composites2_upload(ctx: *mut cb2_ctx, part_off: *const u32, part_shape: *const u32,
+                                  part_local: *const cb2_xform2, n_comp: u32) -> c_int;
+    pub fn cb2_gjk2_intersection_complex(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                         l_comp: *const u32, r_comp: *const u32,
+                                         l_t: *const cb2_xform2, r_t: *const cb2_xform2, n: u64,
+                                         out: *mut cb2_contact2, status: *mut u8) -> c_int;
+    pub fn cb2_gjk2_distance_complex(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                     l_comp: *const u32, r_comp: *const u32,
+                                     l_t: *const cb2_xform2, r_t: *const cb2_xform2, n: u64,
+                                     out: *mut f32, status: *mut u8) -> c_int;
+    pub fn cb2_gjk2_time_of_impact_complex(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                           l_comp: *const u32, r_comp: *const u32,
+                                           l_t0: *const cb2_xform2, l_t1: *const cb2_xform2,
+                                           r_t0: *const cb2_xform2, r_t1: *const cb2_xform2, n: u64,
+                                           iter_cap: u32, out: *mut cb2_contact2, status: *mut u8) -> c_int;
 }

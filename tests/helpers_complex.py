@@ -73,7 +73,49 @@ def expand(cw):
     return np.asarray(own), np.asarray(la), np.asarray(rb)
 
 
-def reduce_reference(oracle, op, strategy, cw):
+def concat2_np(a, b):
+    """Decomposed<Vector2, Basis2>::concat in numpy f32: scale product, Matrix2 product column by
+    column (row-dot matrix-vector products), rot.rotate(other.disp * scale) + disp."""
+    from collision_rs_b200.abi import XFORM2_DT
+    out = np.zeros(len(a), XFORM2_DT)
+    m = lambda p, q: (p * q).astype(f32)
+    am = a["m"]
+
+    def matvec(vx, vy):
+        return ((m(am[:, 0], vx) + m(am[:, 2], vy)).astype(f32), (m(am[:, 1], vx) + m(am[:, 3], vy)).astype(f32))
+
+    out["scale"] = m(a["scale"], b["scale"])
+    out["m"][:, 0], out["m"][:, 1] = matvec(b["m"][:, 0], b["m"][:, 1])
+    out["m"][:, 2], out["m"][:, 3] = matvec(b["m"][:, 2], b["m"][:, 3])
+    dx, dy = matvec(m(b["d"][:, 0], a["scale"]), m(b["d"][:, 1], a["scale"]))
+    out["d"][:, 0] = (dx + a["d"][:, 0]).astype(f32)
+    out["d"][:, 1] = (dy + a["d"][:, 1]).astype(f32)
+    return out
+
+
+def composite_workload2(n, seed=0, n_comp=200, spread=1.2):
+    """2-D composites of 1-4 parts over every Primitive2 kind, random local transforms (some
+    non-unit scales), composite pairs with start/end model transforms."""
+    rng = np.random.default_rng(seed)
+    shapes, verts = W.shapes2_table(64, seed + 100)
+    counts = rng.integers(1, 5, n_comp)
+    comp_off = np.zeros(n_comp + 1, np.uint32)
+    comp_off[1:] = np.cumsum(counts)
+    n_parts = int(comp_off[-1])
+    comp_shape = rng.integers(0, len(shapes), n_parts).astype(np.uint32)
+    comp_local = W.random_xforms2(rng, n_parts, 0.6)
+    comp_local["scale"][::7] = rng.uniform(0.6, 1.4, len(comp_local["scale"][::7])).astype(f32)
+    l_comp = rng.integers(0, n_comp, n).astype(np.uint32)
+    r_comp = rng.integers(0, n_comp, n).astype(np.uint32)
+    l_t0, r_t0 = W.random_xforms2(rng, n, spread), W.random_xforms2(rng, n, spread)
+    l_t1, r_t1 = l_t0.copy(), r_t0.copy()
+    l_t1["d"] += rng.uniform(-1, 1, (n, 2)).astype(f32)
+    r_t1["d"] += ((l_t0["d"] - r_t0["d"]) * rng.uniform(0.5, 1.5, (n, 1))).astype(f32)
+    return dict(shapes=shapes, verts=verts, comp_off=comp_off, comp_shape=comp_shape, comp_local=comp_local,
+                l_comp=l_comp, r_comp=r_comp, l_t0=l_t0, r_t0=r_t0, l_t1=l_t1, r_t1=r_t1)
+
+
+def reduce_reference(oracle, op, strategy, cw, concat_np=concat_np, CONTACT_DT=CONTACT_DT):
     own, la, rb = expand(cw)
     ls, rs = cw["comp_shape"][la], cw["comp_shape"][rb]
     lt0 = concat_np(cw["l_t0"][own], cw["comp_local"][la])

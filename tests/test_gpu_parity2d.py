@@ -221,3 +221,27 @@ def test_device_api_and_million_pair_properties(ctx, o2):
     nrm = np.linalg.norm(got["normal"][hit], axis=1)
     finite = np.isfinite(nrm)
     assert np.allclose(nrm[finite], 1.0, atol=1e-5)
+
+
+def test_complex_callers_match_the_oracle(ctx, o2):
+    """GJK2::intersection_complex / distance_complex / intersection_complex_time_of_impact
+    (gjk/mod.rs:412-588): expansion with Decomposed<Vector2, Basis2>::concat, the GJK2 kernels on the
+    flat part pairs, the loop-order reduction — bit-identical to the oracle."""
+    from helpers_complex import composite_workload2
+    cw = composite_workload2(30_000, seed=9)
+    ctx.upload_shapes2(cw["shapes"], cw["verts"])
+    ctx.upload_composites2(cw["comp_off"], cw["comp_shape"], cw["comp_local"])
+    oc = (cw["shapes"], cw["verts"], cw["comp_off"], cw["comp_shape"], cw["comp_local"], cw["l_comp"],
+          cw["r_comp"], cw["l_t0"], cw["r_t0"], cw["l_t1"], cw["r_t1"])
+    for strategy in (0, 1):
+        got, gst = ctx.intersection_complex2(strategy, cw["l_comp"], cw["r_comp"], cw["l_t0"], cw["r_t0"])
+        exp, est = o2.complex(0, strategy, *oc, nthreads=8)
+        assert_contacts_equal(got, gst, exp, est, f"2-D intersection_complex strategy={strategy}")
+        got, gst = ctx.time_of_impact_complex2(strategy, cw["l_comp"], cw["r_comp"], cw["l_t0"], cw["l_t1"],
+                                               cw["r_t0"], cw["r_t1"], iter_cap=256)
+        exp, est = o2.complex(2, strategy, *oc, iter_cap=256, nthreads=8)
+        assert_contacts_equal(got, gst, exp, est, f"2-D toi_complex strategy={strategy}")
+    got, gst = ctx.distance_complex2(cw["l_comp"], cw["r_comp"], cw["l_t0"], cw["r_t0"])
+    exp, est = o2.complex(1, 0, *oc, nthreads=8)
+    assert np.array_equal(gst, est) and bits_equal(got[est == 1], exp[est == 1]).all()
+    assert (est == 1).mean() > 0.05

@@ -39,3 +39,24 @@ def test_complex_equals_expanded_double_loop(oracle):
             assert np.array_equal(got[m].view(np.uint32), exp[m].view(np.uint32))
         else:
             assert got[m].tobytes() == exp[m].tobytes()
+
+
+def test_2d_complex_equals_expanded_double_loop():
+    """The same structural pin for the 2-D instantiation (Decomposed<Vector2, Basis2>::concat)."""
+    from collision_rs_b200.abi import CONTACT2_DT
+    from helpers_complex import composite_workload2, concat2_np
+    from oracle.binding import Oracle2D
+    o2 = Oracle2D()
+    cw = composite_workload2(4000, seed=4)
+    for op, strategy in ((0, 0), (0, 1), (1, 0), (2, 0), (2, 1)):
+        got, gst = o2.complex(op, strategy, cw["shapes"], cw["verts"], cw["comp_off"], cw["comp_shape"],
+                              cw["comp_local"], cw["l_comp"], cw["r_comp"], cw["l_t0"], cw["r_t0"], cw["l_t1"],
+                              cw["r_t1"], nthreads=4)
+        exp, est = reduce_reference(o2, op, strategy, cw, concat2_np, CONTACT2_DT)
+        assert np.array_equal(gst, est), (op, strategy, np.nonzero(gst != est)[0][:5])
+        m = est == 1
+        assert m.sum() > 50
+        if op == 1:
+            assert np.array_equal(got[m].view(np.uint32), exp[m].view(np.uint32))
+        else:
+            assert got[m].tobytes() == exp[m].tobytes()
