@@ -487,6 +487,14 @@ def extras(ctx, torch, dev, stream):
     res["cfg4_sap"] = {"aabbs": n, "pairs": npairs, "ms": ms_sap, "aabbs_per_s": n / ms_sap * 1e3,
                        "algorithmic_bytes": alg_bytes,
                        "hbm_frac": alg_bytes / (ms_sap * 1e-3) / 1e9 / hbm_peak}
+    def sap_set():
+        rc, cnt = ctx.sap3_unordered_dev(boxes.data_ptr(), n, 0, perm.data_ptr(), pairs.data_ptr(), cap, s)
+        assert rc == 0 and cnt == npairs
+
+    ms_set = timed(sap_set)
+    res["cfg4_sap_pair_set"] = {"aabbs": n, "pairs": npairs, "ms": ms_set, "aabbs_per_s": n / ms_set * 1e3,
+                                "what": "same pairs, unspecified order (feeds the narrow phase): no final pair sort"}
+    sap()  # leave the ordered list in `pairs` for the chained narrow phase below
     body_shape = dv(np.arange(n, dtype=np.uint32))
     body_t = dv(w["body_t"])
     # bodies indexed in SORTED order: permute shapes / transforms once, like the reference's slice

@@ -60,7 +60,7 @@ SYMBOLS = [
     "cb2_composites_upload", "cb2_gjk3_intersection_complex", "cb2_gjk3_distance_complex",
     "cb2_gjk3_time_of_impact_complex",
     "cb2_sap3_find_collider_pairs", "cb2_sap3_find_collider_pairs_dev",
-    "cb2_sap3_find_collider_pairs_shard_dev",
+    "cb2_sap3_find_collider_pairs_shard_dev", "cb2_sap3_find_collider_pairs_unordered_dev",
     "cb2_sap2_find_collider_pairs",
     "cb2_brute_force_find_collider_pairs", "cb2_brute_force_find_collider_pairs_dev",
     "cb2_world_aabbs", "cb2_world_aabbs_dev",
@@ -118,6 +118,8 @@ def load():
                                                      C.POINTER(u64), vp]
     lib.cb2_sap3_find_collider_pairs_shard_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u64,
                                                            C.POINTER(u64), vp]
+    lib.cb2_sap3_find_collider_pairs_unordered_dev.argtypes = [vp, vp, u64, u32, vp, vp, u64,
+                                                               C.POINTER(u64), vp]
     lib.cb2_sap2_find_collider_pairs.argtypes = [vp, vp, u64, C.POINTER(u32), vp, vp, u64,
                                                  C.POINTER(u64)]
     lib.cb2_brute_force_find_collider_pairs.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64)]

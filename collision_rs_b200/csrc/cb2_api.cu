@@ -927,6 +927,27 @@ int cb2_sap3_find_collider_pairs_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_
     return rc;
 }
 
+// The pair SET without the reference's Vec order (north_star: "a bit-exact match to the reference's
+// pair set"): for callers that feed the pairs straight to the narrow phase, where order is
+// irrelevant — the final 40-bit radix sort of the pair keys (a quarter of the call) is skipped.
+int cb2_sap3_find_collider_pairs_unordered_dev(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n,
+                                               uint32_t axis, uint32_t* perm_out, uint32_t* pairs_out,
+                                               uint64_t cap, uint64_t* n_pairs, void* stream) {
+    if (!c || !n_pairs) return fail(c, CB2_ERR_ARG, "null argument");
+    *n_pairs = 0;
+    if (axis > 2) return fail(c, CB2_ERR_ARG, "sweep axis must be 0, 1 or 2");
+    if (n == 0) return CB2_OK;
+    if (!aabbs || !perm_out || (!pairs_out && cap)) return fail(c, CB2_ERR_ARG, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    const char* err = "";
+    int rc = sap_find_pairs(c->sap, aabbs, n, axis, perm_out, pairs_out, cap, n_pairs,
+                            static_cast<cudaStream_t>(stream), &c->launches, &err, false, 0u, 0xFFFFFFFFu,
+                            true);
+    if (rc == CB2_ERR_NOSPC) c->err = "pairs_out too small; *n_pairs holds the required capacity";
+    else if (rc) c->err = err;
+    return rc;
+}
+
 // One GPU's shard of the pair list: every GPU sorts the whole table (the exact stable
 // permutation, 24 MB at 1 M boxes) and sweeps it, but reports only the pairs whose later box sits at
 // a sorted position in shard `shard` of `n_shards` equal position ranges.  The reference's Vec is

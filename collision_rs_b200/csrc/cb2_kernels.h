@@ -142,7 +142,8 @@ void sap_workspace_destroy(sap_workspace* w);
 int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
                    uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
                    cudaStream_t st, uint64_t* launches, const char** err, bool brute_force = false,
-                   uint32_t b_lo = 0u, uint32_t b_hi = 0xFFFFFFFFu);  // [b_lo, b_hi): this GPU's shard
+                   uint32_t b_lo = 0u, uint32_t b_hi = 0xFFFFFFFFu,  // [b_lo, b_hi): this GPU's shard
+                   bool unordered = false);  // the pair SET in emission order: skips the final pair sort
 
 // ---- 2-D narrow phase (cb2_narrow2d.cu): GJK2 / EPA2, one thread per pair -------------------------
 struct narrow2_args {           // all device pointers

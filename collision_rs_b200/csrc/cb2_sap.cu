@@ -669,10 +669,10 @@ static int ensure_cap(sap_workspace* w, size_t bytes, const char** err) {
 int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_t axis,
                    uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
                    cudaStream_t st, uint64_t* launches, const char** err, bool brute_force,
-                   uint32_t b_lo, uint32_t b_hi) {
+                   uint32_t b_lo, uint32_t b_hi, bool unordered) {
     {
         const char* e = std::getenv("CB2_SAP_LEGACY");
-        if (e && e[0] == '1' && !brute_force && b_lo == 0u && b_hi == 0xFFFFFFFFu)
+        if (e && e[0] == '1' && !brute_force && b_lo == 0u && b_hi == 0xFFFFFFFFu && !unordered)
             return sap_find_pairs_legacy(w, aabbs, n, axis, perm_out, pairs_out, cap, n_pairs, st,
                                          launches, err);
     }
@@ -791,6 +791,12 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         if (np > kcap) {  // denser than 16 pairs per box: run again with the exact room
             kcap = np;
             continue;
+        }
+        if (unordered && !brute_force) {
+            // the caller wants the pair SET (e.g. to feed the narrow phase): no final sort
+            k_sap_unpack<<<nblk(np, 256), 256, 0, st>>>(pk, np, pos_bits, false, pairs_out);
+            *launches += 1;
+            return CB2_OK;
         }
         // sort the packed keys (b << pos_bits | a): the reference's Vec order, then unpack
         tb = sort3;

@@ -379,6 +379,16 @@ class Context:
         return 0, int(npairs.value)
 
 
+    def sap3_unordered_dev(self, aabbs, n, axis, perm_out, pairs_out, cap, stream=0):
+        """The pair SET (unspecified order) of SweepAndPrune3::find_collider_pairs (device pointers)."""
+        npairs = C.c_uint64(0)
+        rc = self.lib.cb2_sap3_find_collider_pairs_unordered_dev(self.h, aabbs, int(n), int(axis), perm_out,
+                                                                 pairs_out, int(cap), C.byref(npairs), stream)
+        if rc == abi.ERR_NOSPC:
+            return rc, int(npairs.value)
+        self._ck(rc)
+        return 0, int(npairs.value)
+
     def sap3_shard_dev(self, aabbs, n, axis, shard, n_shards, perm_out, pairs_out, cap, stream=0):
         """This GPU's shard of SweepAndPrune3::find_collider_pairs (device pointers)."""
         npairs = C.c_uint64(0)

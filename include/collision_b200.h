@@ -281,6 +281,13 @@ int cb2_sap3_find_collider_pairs_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint6
                                      uint32_t* pairs_out, uint64_t cap,
                                      uint64_t* n_pairs, void* stream);
 
+/* The same pairs as a SET: pairs_out holds exactly the reference's pairs (indices into the sorted
+ * order, a < b) but in unspecified order.  For callers that hand the pairs straight to the narrow
+ * phase (cb2_gjk3_intersection_bodies_dev), where order does not matter; skips the final sort.   */
+int cb2_sap3_find_collider_pairs_unordered_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint64_t n,
+                                               uint32_t axis, uint32_t* perm_out, uint32_t* pairs_out,
+                                               uint64_t cap, uint64_t* n_pairs, void* stream);
+
 /* Multi-GPU broad phase (one process per GPU): the same call restricted to shard
  * `shard` of `n_shards`.  Every GPU holds the whole AABB table and computes the whole (identical)
  * permutation; pairs are split by the sorted position of their LATER box into n_shards equal

@@ -292,4 +292,7 @@ extern "C" {
                                            l_t0: *const cb2_xform2, l_t1: *const cb2_xform2,
                                            r_t0: *const cb2_xform2, r_t1: *const cb2_xform2, n: u64,
                                            iter_cap: u32, out: *mut cb2_contact2, status: *mut u8) -> c_int;
+    pub fn cb2_sap3_find_collider_pairs_unordered_dev(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
+                                                      axis: u32, perm_out: *mut u32, pairs_out: *mut u32,
+                                                      cap: u64, n_pairs: *mut u64, stream: *mut c_void) -> c_int;
 }

@@ -528,6 +528,26 @@ def test_sap_shards_concatenate_to_the_full_pair_list(ctx, oracle):
     assert rc == -4 and cnt == len(pairs_of_shard(pairs_e, n, 0, 2))
 
 
+def test_sap_unordered_is_the_same_pair_set(ctx):
+    import torch
+    n = 200_000
+    boxes = W.cfg4_aabbs(n, extent=200.0 * (n / 1e6) ** (1 / 3))["aabbs"]
+    perm_e, pairs_e, _ = ctx.sap3(boxes, axis=1)
+    dev = torch.device("cuda:0")
+    d_boxes = torch.from_numpy(boxes.view(np.uint8).reshape(-1).copy()).to(dev)
+    perm = torch.zeros(n, dtype=torch.int32, device=dev)
+    cap = len(pairs_e) + 8
+    out = torch.zeros(2 * cap, dtype=torch.int32, device=dev)
+    rc, cnt = ctx.sap3_unordered_dev(d_boxes.data_ptr(), n, 1, perm.data_ptr(), out.data_ptr(), cap,
+                                     torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rc == 0 and cnt == len(pairs_e)
+    got = out[:2 * cnt].cpu().numpy().view(np.uint32).reshape(-1, 2)
+    assert np.array_equal(perm.cpu().numpy().view(np.uint32), perm_e)
+    key = lambda p: (p[:, 1].astype(np.uint64) << np.uint64(32)) | p[:, 0].astype(np.uint64)
+    assert np.array_equal(np.sort(key(got)), key(pairs_e))   # the reference order IS ascending in this key
+
+
 # ---- composite shapes: *_complex (gjk/mod.rs:412-588) ----------------------------------------------
 def test_complex_callers_match_the_oracle(ctx, oracle):
     from helpers_complex import composite_workload
