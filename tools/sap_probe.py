@@ -7,7 +7,7 @@ from collision_rs_b200.host import Context
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 ctx = Context(0)
-w = W.cfg4_aabbs(n)
+w = W.cfg4_aabbs(n, extent=200.0 * (n / 1e6) ** (1 / 3))  # cfg 4's density at any n
 dev = torch.device("cuda", 0)
 boxes = torch.from_numpy(w["aabbs"].view(np.uint8).reshape(-1).copy()).to(dev)
 perm = torch.empty(n, dtype=torch.int32, device=dev)
@@ -23,4 +23,12 @@ for _ in range(reps):
     rc, cnt = ctx.sap3_dev(boxes.data_ptr(), n, 0, perm.data_ptr(), pairs.data_ptr(), cap, s)
 e1.record()
 torch.cuda.synchronize()
-print(f"n={n} pairs={cnt} {e0.elapsed_time(e1)/reps:.3f} ms/call")
+ms = e0.elapsed_time(e1) / reps
+print(f"n={n} pairs={cnt} {ms:.3f} ms/call -> {n / ms / 1e3:.1f} M AABBs/s (ordered Vec)")
+e0.record()
+for _ in range(reps):
+    rc, cnt2 = ctx.sap3_unordered_dev(boxes.data_ptr(), n, 0, perm.data_ptr(), pairs.data_ptr(), cap, s)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"n={n} pairs={cnt2} {ms:.3f} ms/call -> {n / ms / 1e3:.1f} M AABBs/s (pair set)")
