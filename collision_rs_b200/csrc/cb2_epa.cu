@@ -567,7 +567,12 @@ constexpr int T0_G = CB2_T0_G, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O
 #ifndef CB2_T1_G
 #define CB2_T1_G 8
 #endif
-constexpr int T1_G = CB2_T1_G, T1_F = 72, T1_V = 40, T1_O = 32;
+#ifndef CB2_T1_F
+#define CB2_T1_F 72
+#define CB2_T1_V 40
+#define CB2_T1_O 32
+#endif
+constexpr int T1_G = CB2_T1_G, T1_F = CB2_T1_F, T1_V = CB2_T1_V, T1_O = CB2_T1_O;
 constexpr int T2_G = 8, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
 
 template <int G, int F, int V, int O, int RF, int RV>
