@@ -804,6 +804,13 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
     const size_t o_st = o_out + al(chunk * out_rec);
     rc = pipeline_prepare(c, o_st + al(chunk));
     if (rc) return rc;
+    // size every compute slot's workspace for the largest chunk now: growing one in mid-pipeline
+    // (the ramp starts with short chunks) would free buffers under a device-wide synchronisation
+    if (op == OP_INTERSECTION && !c->legacy_epa)
+        for (int slot = 0; slot < c->n_cstreams; ++slot) {
+            rc = ensure_ws(c, slot, chunk);
+            if (rc) return rc;
+        }
     const cb2_xform* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
     return pipeline_run(
         c, n,
@@ -1344,6 +1351,20 @@ static int narrow2_check(cb2_ctx* c, int op, uint32_t strategy, const cb2_settin
     return CB2_OK;
 }
 
+// GJK2 -> EPA2 hand-off buffers of one compute slot (hit list + two queues, 3-point simplexes)
+static int ensure_ws2(cb2_ctx* c, int slot, uint64_t n) {
+    if (c->ws2_cap[slot] >= n) return CB2_OK;
+    if (c->d_hits2[slot]) cudaFree(c->d_hits2[slot]);
+    if (c->d_sx2[slot]) cudaFree(c->d_sx2[slot]);
+    c->d_hits2[slot] = nullptr;
+    c->d_sx2[slot] = nullptr;
+    c->ws2_cap[slot] = 0;
+    CK(c, cudaMalloc(&c->d_hits2[slot], 3 * n * sizeof(uint32_t)));
+    CK(c, cudaMalloc(&c->d_sx2[slot], n * 48));
+    c->ws2_cap[slot] = n;
+    return CB2_OK;
+}
+
 static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings* settings,
                        const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t0,
                        const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
@@ -1356,16 +1377,8 @@ static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings
     A.counters = c->d_cnt2[slot];  // queue cursors of the persistent kernels
     A.long_tails = c->long_tails2;
     if (epa) {
-        if (c->ws2_cap[slot] < n) {
-            if (c->d_hits2[slot]) cudaFree(c->d_hits2[slot]);
-            if (c->d_sx2[slot]) cudaFree(c->d_sx2[slot]);
-            c->d_hits2[slot] = nullptr;
-            c->d_sx2[slot] = nullptr;
-            c->ws2_cap[slot] = 0;
-            CK(c, cudaMalloc(&c->d_hits2[slot], 3 * n * sizeof(uint32_t)));
-            CK(c, cudaMalloc(&c->d_sx2[slot], n * 48));
-            c->ws2_cap[slot] = n;
-        }
+        int rc2 = ensure_ws2(c, slot, n);
+        if (rc2) return rc2;
         A.counters = c->d_cnt2[slot];
         A.hits = c->d_hits2[slot];
         A.simplex = c->d_sx2[slot];
@@ -1412,6 +1425,11 @@ static int narrow2_host(cb2_ctx* c, int op, uint32_t strategy, const cb2_setting
     const size_t o_st = o_out + al(chunk * out_rec);
     rc = pipeline_prepare(c, o_st + al(chunk));
     if (rc) return rc;
+    if (op == 0 && strategy == CB2_FULL_RESOLUTION)
+        for (int slot = 0; slot < c->n_cstreams; ++slot) {
+            rc = ensure_ws2(c, slot, chunk);
+            if (rc) return rc;
+        }
     const cb2_xform2* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
     const size_t xs = xf_bytes / sizeof(cb2_xform2);
     return pipeline_run(
