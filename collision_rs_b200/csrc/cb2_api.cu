@@ -336,11 +336,29 @@ static const char* build_rings(const cb2_shape& s, const float* verts_xyz, const
     return nullptr;
 }
 
+// A composite table indexes the shape table it was uploaded against: a new shape table drops it
+// (the caller uploads composites again), so a stale part index can never reach a kernel.
+static void drop_composites(cb2_ctx* c, bool d2) {
+    uint32_t*& off = d2 ? c->d_comp2_off : c->d_comp_off;
+    uint32_t*& shp = d2 ? c->d_comp2_shape : c->d_comp_shape;
+    float4*& loc = d2 ? c->d_comp2_local : c->d_comp_local;
+    if (!off && !shp && !loc) return;
+    cudaDeviceSynchronize();
+    if (off) cudaFree(off);
+    if (shp) cudaFree(shp);
+    if (loc) cudaFree(loc);
+    off = shp = nullptr;
+    loc = nullptr;
+    (d2 ? c->n_comp2 : c->n_comp) = 0;
+    (d2 ? c->h_comp2_off : c->h_comp_off).clear();
+}
+
 static int shapes_upload(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shapes,
                          const float* verts_xyz, uint64_t n_verts, const uint32_t* faces,
                          uint64_t n_faces) {
     if (!c || (!shapes && n_shapes) || (!verts_xyz && n_verts)) return fail(c, CB2_ERR_ARG, "null argument");
     CK(c, cudaSetDevice(c->device));
+    drop_composites(c, false);
     std::vector<dshape> hs(n_shapes);
     std::vector<uint32_t> ring_cnt;                // HalfEdge rings, per global vertex
     std::vector<std::vector<uint32_t>> rings;
@@ -1483,6 +1501,7 @@ int cb2_shapes2_upload(cb2_ctx* c, const cb2_shape2* shapes, uint32_t n_shapes, 
     }
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaDeviceSynchronize());
+    drop_composites(c, true);
     if (c->d_shapes2) cudaFree(c->d_shapes2);
     if (c->d_verts2) cudaFree(c->d_verts2);
     c->d_shapes2 = nullptr;

@@ -241,6 +241,8 @@ int cb2_gjk3_intersection_bodies_dev(cb2_ctx* ctx, uint32_t strategy,
  * reduction replays the reference's loop order (first hit for CollisionOnly; max depth — last
  * among equals, Iterator::max_by; min distance; min time of impact — first among equals), incl.
  * its early returns and panics.  Host buffers.                                                 */
+/* The composite table refers to the shape table it was uploaded against: uploading a new shape
+ * table drops it (upload the composites again afterwards).                                        */
 int cb2_composites_upload(cb2_ctx* ctx, const uint32_t* part_off /* n_comp + 1 */,
                           const uint32_t* part_shape, const cb2_xform* part_local,
                           uint32_t n_comp);

@@ -593,6 +593,10 @@ def test_complex_empty_composites_and_errors(ctx, oracle):
     assert st[0] == 0 and st[2] == 0 and np.array_equal(st, est)
     with pytest.raises(Cb2Error):
         ctx.intersection_complex(0, np.array([7], np.uint32), np.array([0], np.uint32), t[:1], t[:1])
+    # a new shape table drops the composite table (its part indices refer to the old one)
+    ctx.upload_shapes(shapes[:1])
+    with pytest.raises(Cb2Error):
+        ctx.intersection_complex(0, l, r, t, t)
 
 
 def test_every_primitive3_variant(ctx, oracle):
