@@ -204,6 +204,9 @@ int cb2_gjk3_time_of_impact(cb2_ctx* ctx, const cb2_settings* settings,
 
 /* ---- narrow phase, DEVICE buffers (all pointers are device pointers; the work
  * is enqueued on `stream` (a cudaStream_t, may be NULL) and NOT synchronised).
+ * Shape / body indices in device memory are TRUSTED (the host-buffer entry points range-check them;
+ * here the caller is the broad phase or its own device code): an index past the table is undefined
+ * behaviour, as it would be for any CUDA library taking device index arrays.
  * With pair_body != NULL the transforms are per BODY and pair i uses bodies
  * pair_body[2i], pair_body[2i+1] (shape = body_shape[..], xform = body_t[..]):
  * this is how SweepAndPrune3 output feeds the narrow phase without a host trip. */
