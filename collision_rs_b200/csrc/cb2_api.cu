@@ -95,6 +95,25 @@ struct cb2_ctx {
 
 static std::string g_create_err;
 
+// CB2_TRACE=1: stage marks inside a host-pipeline chunk (events on the chunk's compute stream)
+struct trace_mark {
+    cudaEvent_t ev;
+    const char* what;
+};
+static std::vector<trace_mark> g_trace;
+static bool trace_on() {
+    static const bool on = std::getenv("CB2_TRACE") && std::getenv("CB2_TRACE")[0] == '1';
+    return on;
+}
+static void trace_stage(const char* what, cudaStream_t st) {
+    if (!trace_on()) return;
+    trace_mark m;
+    cudaEventCreate(&m.ev);
+    cudaEventRecord(m.ev, st);
+    m.what = what;
+    g_trace.push_back(m);
+}
+
 static void free_ws(narrow_ws& w) {  // the per-pair buffers
     for (int k = 0; k < EPA_TIERS; ++k) {
         if (w.list[k]) cudaFree(w.list[k]);
@@ -586,14 +605,19 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
         if (!c->d_queue[ws_slot]) CK(c, cudaMalloc(&c->d_queue[ws_slot], 64));
         A.queue = c->d_queue[ws_slot];
         mark_stage(c, 0, st);
+        trace_stage("begin", st);
         e = launch_gjk_hits(A, full, W, c->sm_count, st);
         ++c->launches;
         mark_stage(c, 1, st);
+        trace_stage("gjk", st);
         if (e == cudaSuccess && full) {
             e = launch_epa_tier(0, A, W, c->sm_count, st);
             mark_stage(c, 2, st);
-            for (int k = 1; k < EPA_TIERS && e == cudaSuccess; ++k)
+            trace_stage("tier0", st);
+            for (int k = 1; k < EPA_TIERS && e == cudaSuccess; ++k) {
                 e = launch_epa_tier(k, A, W, c->sm_count, st);
+                trace_stage(k == 1 ? "tier1" : "tier2", st);
+            }
             mark_stage(c, 3, st);
             c->launches += EPA_TIERS;
         }
@@ -778,6 +802,15 @@ static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut
             std::fprintf(stderr, "[cb2 trace] chunk %zu (%llu pairs): in %.3f  kernels %.3f  out %.3f ms\n", q / 3,
                          (unsigned long long)sizes[q / 3], a_, b_, d_);
         }
+        std::fprintf(stderr, "[cb2 trace] stages:");
+        for (auto& m : g_trace) {
+            float t_ = 0;
+            cudaEventElapsedTime(&t_, t0, m.ev);
+            std::fprintf(stderr, "%s %s %.3f", std::strcmp(m.what, "begin") == 0 ? "\n[cb2 trace]  " : ",", m.what, t_);
+            cudaEventDestroy(m.ev);
+        }
+        std::fprintf(stderr, "\n");
+        g_trace.clear();
         for (auto e : tev) cudaEventDestroy(e);
         cudaEventDestroy(t0);
     }
