@@ -68,6 +68,7 @@ SYMBOLS = [
     "cb2_gjk2_intersection_dev", "cb2_gjk2_distance_dev", "cb2_gjk2_time_of_impact_dev",
     "cb2_composites2_upload", "cb2_gjk2_intersection_complex", "cb2_gjk2_distance_complex",
     "cb2_gjk2_time_of_impact_complex",
+    "cb2_world_aabbs2", "cb2_world_aabbs2_dev",
 ]
 
 _lib = None
@@ -137,6 +138,8 @@ def load():
     lib.cb2_gjk2_intersection_complex.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp]
     lib.cb2_gjk2_distance_complex.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp]
     lib.cb2_gjk2_time_of_impact_complex.argtypes = [vp, u32, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp]
+    lib.cb2_world_aabbs2.argtypes = [vp, vp, vp, u64, vp]
+    lib.cb2_world_aabbs2_dev.argtypes = [vp, vp, vp, u64, vp, vp]
     _lib = lib
     return lib
 

@@ -1655,3 +1655,41 @@ int cb2_gjk2_time_of_impact_complex(cb2_ctx* c, uint32_t strategy, const cb2_set
                         out, nullptr, status);
 }
 }  // extern "C"
+
+// ---- 2-D world bounds (the step before SweepAndPrune2) ---------------------------------------------------
+extern "C" {
+int cb2_world_aabbs2_dev(cb2_ctx* c, const uint32_t* shape, const cb2_xform2* t, uint64_t n, cb2_aabb2* out,
+                         void* stream) {
+    if (!c) return CB2_ERR_ARG;
+    if (n == 0) return CB2_OK;
+    if (!shape || !t || !out) return fail(c, CB2_ERR_ARG, "null argument");
+    if (!c->d_shapes2) return fail(c, CB2_ERR_ARG, "cb2_shapes2_upload has not been called");
+    CK(c, cudaSetDevice(c->device));
+    CK(c, launch_world_aabbs2(c->d_shapes2, c->d_verts2, shape, t, n, out, static_cast<cudaStream_t>(stream)));
+    ++c->launches;
+    return CB2_OK;
+}
+int cb2_world_aabbs2(cb2_ctx* c, const uint32_t* shape, const cb2_xform2* t, uint64_t n, cb2_aabb2* out) {
+    if (!c) return CB2_ERR_ARG;
+    if (n == 0) return CB2_OK;
+    if (!shape || !t || !out) return fail(c, CB2_ERR_ARG, "null argument");
+    if (!c->d_shapes2) return fail(c, CB2_ERR_ARG, "cb2_shapes2_upload has not been called");
+    for (uint64_t i = 0; i < n; ++i)
+        if (shape[i] >= c->n_shapes2) return fail(c, CB2_ERR_ARG, "shape index out of range");
+    CK(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_sh = 0, o_t = al(4 * n), o_out = o_t + al(sizeof(cb2_xform2) * n);
+    int rc = ensure_misc(c, o_out + al(sizeof(cb2_aabb2) * n));
+    if (rc) return rc;
+    char* base = static_cast<char*>(c->d_misc);
+    cudaStream_t st = c->stream[0];
+    CK(c, cudaMemcpyAsync(base + o_sh, shape, 4 * n, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + o_t, t, sizeof(cb2_xform2) * n, cudaMemcpyHostToDevice, st));
+    rc = cb2_world_aabbs2_dev(c, reinterpret_cast<uint32_t*>(base + o_sh), reinterpret_cast<cb2_xform2*>(base + o_t),
+                              n, reinterpret_cast<cb2_aabb2*>(base + o_out), st);
+    if (rc) return rc;
+    CK(c, cudaMemcpyAsync(out, base + o_out, sizeof(cb2_aabb2) * n, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return CB2_OK;
+}
+}  // extern "C"

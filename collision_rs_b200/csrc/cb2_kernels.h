@@ -172,5 +172,7 @@ struct narrow2_args {           // all device pointers
 };
 // op: 0 intersection (k_gjk2_intersection [+ the two k_epa2 tiers]), 1 distance, 2 time of impact
 cudaError_t launch_narrow2(int op, const narrow2_args& A, int sm_count, cudaStream_t st);
+cudaError_t launch_world_aabbs2(const cb2_shape2* shapes, const float* verts, const uint32_t* shape,
+                                const cb2_xform2* t, uint64_t n, cb2_aabb2* out, cudaStream_t st);
 
 }  // namespace cb2

@@ -794,6 +794,58 @@ __global__ void __launch_bounds__(128) k_gjk2_time_of_impact(narrow2_args_dev A)
     A.out_status[i] = status;
 }
 
+// ---- world bounds: shape.compute_bound().transform_volume(&t) for Primitive2 ---------------------------
+// ComputeBound<Aabb2>: primitive2.rs:68-80 (circle.rs:47-52, rectangle.rs:83-88, line.rs:32-34,
+// polygon.rs:50-52 = fold from Aabb2::zero()); Aabb2::transform: aabb2.rs:39-46, 78-88.
+CB2_DI float rmin2(float l, float r) { return (l > r) ? r : l; }  // aabb/mod.rs:21-26
+CB2_DI float rmax2(float l, float r) { return (l < r) ? r : l; }  // aabb/mod.rs:28-33
+__global__ void __launch_bounds__(256) k_world_aabbs2(const float4* __restrict__ shapes,
+                                                      const float2* __restrict__ verts,
+                                                      const uint32_t* __restrict__ shape,
+                                                      const float4* __restrict__ t, uint64_t n,
+                                                      cb2_aabb2* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const shape2 s = load_shape2(shapes, verts, __ldg(shape + i));
+    const xform2 x = load_xform2(t, i);
+    f2 mn = zero2(), mx = zero2();
+    auto ordered = [&](f2 a, f2 b) {  // Aabb2::new
+        mn = mk2(rmin2(a.x, b.x), rmin2(a.y, b.y));
+        mx = mk2(rmax2(a.x, b.x), rmax2(a.y, b.y));
+    };
+    auto grow = [&](f2 p) {  // Aabb::grow: new(min(self.min, p), max(self.max, p))
+        ordered(mk2(rmin2(mn.x, p.x), rmin2(mn.y, p.y)), mk2(rmax2(mx.x, p.x), rmax2(mx.y, p.y)));
+    };
+    if (s.kind == CB2_LINE2) {
+        ordered(mk2(s.p0, s.p1), mk2(s.p2, s.p3));
+    } else if (s.kind == CB2_CIRCLE) {
+        ordered(mk2(-s.p0, -s.p0), mk2(s.p0, s.p0));
+    } else if (s.kind == CB2_RECTANGLE || s.kind == CB2_SQUARE) {
+        const f2 h = mk2(s.p0, s.kind == CB2_SQUARE ? s.p0 : s.p1) / 2.0f;
+        ordered(-h, h);
+    } else if (s.kind == CB2_POLYGON) {
+        for (uint32_t k = 0; k < s.vcnt; ++k) grow(vtx(s, k));
+    }  // Particle: Aabb2::zero()
+    const f2 c1 = mk2(mx.x, mn.y), c2 = mk2(mn.x, mx.y), c0 = mn, c3 = mx;
+    const f2 first = transform_point(x, c0);
+    ordered(first, first);
+    grow(transform_point(x, c1));
+    grow(transform_point(x, c2));
+    grow(transform_point(x, c3));
+    out[i].min[0] = mn.x;
+    out[i].min[1] = mn.y;
+    out[i].max[0] = mx.x;
+    out[i].max[1] = mx.y;
+}
+cudaError_t launch_world_aabbs2(const cb2_shape2* shapes, const float* verts, const uint32_t* shape,
+                                const cb2_xform2* t, uint64_t n, cb2_aabb2* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_world_aabbs2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(shapes), reinterpret_cast<const float2*>(verts), shape,
+        reinterpret_cast<const float4*>(t), n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_narrow2(int op, const narrow2_args& H, int sm_count, cudaStream_t st) {
     narrow2_args_dev A;
     A.shapes = reinterpret_cast<const float4*>(H.shapes);

@@ -162,6 +162,14 @@ class Context:
             self.h, C.byref(settings), l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, int(iter_cap),
             out, status, stream))
 
+    def world_aabbs2(self, shape, t):
+        """(n, 4) f32: min.xy, max.xy of shape.compute_bound().transform_volume(&t) per body."""
+        shape = np.ascontiguousarray(shape, np.uint32)
+        t = np.ascontiguousarray(t, abi.XFORM2_DT)
+        out = np.zeros((len(shape), 4), np.float32)
+        self._ck(self.lib.cb2_world_aabbs2(self.h, ptr(shape), ptr(t), len(shape), ptr(out)))
+        return out
+
     def upload_composites2(self, part_off, part_shape, part_local):
         """2-D composites: parts [part_off[c], part_off[c+1]) of (part_shape -> 2-D shape table,
         part_local: XFORM2_DT)."""

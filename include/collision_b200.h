@@ -441,6 +441,12 @@ int cb2_gjk2_time_of_impact_complex(cb2_ctx* ctx, uint32_t strategy, const cb2_s
                                     const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
                                     uint32_t iter_cap, cb2_contact2* out, uint8_t* status);
 
+/* 2-D world bounds, the step before SweepAndPrune2: out[i] = shape.compute_bound().transform_volume(&t[i])
+ * (ComputeBound<Aabb2> for Primitive2: primitive2.rs:68-80; Aabb2::transform: volume/aabb/aabb2.rs:78-88). */
+int cb2_world_aabbs2(cb2_ctx* ctx, const uint32_t* shape, const cb2_xform2* t, uint64_t n, cb2_aabb2* out);
+int cb2_world_aabbs2_dev(cb2_ctx* ctx, const uint32_t* shape, const cb2_xform2* t, uint64_t n,
+                         cb2_aabb2* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

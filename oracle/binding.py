@@ -377,3 +377,8 @@ class Oracle2D:
                                          _p(r_comp), _p(l_t0), _p(l_t1), _p(r_t0), _p(r_t1), C.c_uint64(n),
                                          C.c_uint32(iter_cap), _p(out_c), _p(out_d), _p(status), C.c_int(nthreads))
         return (out_d if op == 1 else out_c), status
+
+    def world_aabbs(self, shapes, verts, shape, t):
+        out = np.zeros((len(shape), 4), np.float32)  # min.xy, max.xy
+        self.lib.orc2_world_aabbs(_p(shapes), _p(verts), _p(shape), _p(t), C.c_uint64(len(shape)), _p(out))
+        return out

@@ -519,6 +519,50 @@ static uint8_t gjk_toi(const cb2_settings& st, const Shape& l, const Xf& lt0, co
     }
 }
 
+// ---- bounds: ComputeBound<Aabb2> for Primitive2 (primitive2.rs:68-80) + Aabb2::transform ------------
+static inline R rmin(R l, R r) { return (l > r) ? r : l; }  // volume/aabb/mod.rs:21-26: Less|Equal|None => lhs
+static inline R rmax(R l, R r) { return (l < r) ? r : l; }  // :28-33
+struct Box2 {
+    V2 mn, mx;
+};
+static inline Box2 box_new(V2 p1, V2 p2) {  // aabb2.rs:30-35
+    Box2 b;
+    b.mn = V2(rmin(p1.x, p2.x), rmin(p1.y, p2.y));
+    b.mx = V2(rmax(p1.x, p2.x), rmax(p1.y, p2.y));
+    return b;
+}
+static inline Box2 box_grow(const Box2& a, V2 p) {  // aabb/mod.rs:116-118: new(min(self.min, p), max(self.max, p))
+    return box_new(V2(rmin(a.mn.x, p.x), rmin(a.mn.y, p.y)), V2(rmax(a.mx.x, p.x), rmax(a.mx.y, p.y)));
+}
+static Box2 compute_bound(const Shape& s) {
+    switch (s.kind) {
+        case CB2_PARTICLE2:
+            return box_new(zero2(), zero2());  // Aabb2::zero(), primitive2.rs:70
+        case CB2_LINE2:
+            return box_new(V2(s.p[0], s.p[1]), V2(s.p[2], s.p[3]));  // primitive/line.rs:32-34
+        case CB2_CIRCLE:
+            return box_new(V2(-s.p[0], -s.p[0]), V2(s.p[0], s.p[0]));  // circle.rs:47-52
+        case CB2_RECTANGLE:
+        case CB2_SQUARE: {  // rectangle.rs:83-88
+            const V2 dim = s.kind == CB2_SQUARE ? V2(s.p[0], s.p[0]) : V2(s.p[0], s.p[1]);
+            const V2 h = dim / (R(1.0f) + R(1.0f));
+            return box_new(-h, h);
+        }
+        default: {  // polygon.rs:50-52: get_bound = fold(Aabb2::zero(), grow), util.rs:32-38
+            Box2 b = box_new(zero2(), zero2());
+            for (uint32_t i = 0; i < s.vcnt; ++i) b = box_grow(b, vtx(s, i));
+            return b;
+        }
+    }
+}
+static Box2 box_transform(const Box2& a, const Xf& t) {  // aabb2.rs:39-46, 78-88
+    const V2 c[4] = {a.mn, V2(a.mx.x, a.mn.y), V2(a.mn.x, a.mx.y), a.mx};
+    const V2 first = transform_point(t, c[0]);
+    Box2 b = box_new(first, first);
+    for (int i = 1; i < 4; ++i) b = box_grow(b, transform_point(t, c[i]));
+    return b;
+}
+
 // ---- composite shapes: gjk/mod.rs:412-588 with the 2-D instantiation ---------------------------------
 // Decomposed::concat (cgmath 0.18 transform.rs): {scale: s*os, rot: rot*orot, disp: rot.rotate(odisp*s) + disp};
 // Basis2 * Basis2 = Matrix2 * Matrix2 = [lhs * rhs.c0, lhs * rhs.c1] (each a row-dot matrix-vector product)
@@ -833,6 +877,18 @@ void orc2_gjk2_complex_batch(uint32_t op, uint32_t strategy, const cb2_settings*
                                             Rc, load_xf(r_t0[i]), load_xf(r_t1[i]), iter_cap, &out_c[i]);
         }
     });
+}
+
+// out[i] = shape.compute_bound().transform_volume(&t[i]) as min.xy, max.xy
+void orc2_world_aabbs(const cb2_shape2* shapes, const float* verts_xy, const uint32_t* shape, const cb2_xform2* t,
+                      uint64_t n, cb2_aabb2* out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const Box2 b = box_transform(compute_bound(load_shape(shapes[shape[i]], verts_xy)), load_xf(t[i]));
+        out[i].min[0] = b.mn.x.f;
+        out[i].min[1] = b.mn.y.f;
+        out[i].max[0] = b.mx.x.f;
+        out[i].max[1] = b.mx.y.f;
+    }
 }
 
 }  // extern "C"

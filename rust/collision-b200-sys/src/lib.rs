@@ -295,4 +295,8 @@ extern "C" {
     pub fn cb2_sap3_find_collider_pairs_unordered_dev(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb3, n: u64,
                                                       axis: u32, perm_out: *mut u32, pairs_out: *mut u32,
                                                       cap: u64, n_pairs: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn cb2_world_aabbs2(ctx: *mut cb2_ctx, shape: *const u32, t: *const cb2_xform2, n: u64,
+                            out: *mut cb2_aabb2) -> c_int;
+    pub fn cb2_world_aabbs2_dev(ctx: *mut cb2_ctx, shape: *const u32, t: *const cb2_xform2, n: u64,
+                                out: *mut cb2_aabb2, stream: *mut c_void) -> c_int;
 }

@@ -245,3 +245,18 @@ def test_complex_callers_match_the_oracle(ctx, o2):
     exp, est = o2.complex(1, 0, *oc, nthreads=8)
     assert np.array_equal(gst, est) and bits_equal(got[est == 1], exp[est == 1]).all()
     assert (est == 1).mean() > 0.05
+
+
+def test_world_aabbs2_match_oracle(ctx, o2):
+    rng = np.random.default_rng(11)
+    shapes, verts = W.shapes2_table(512, 77)
+    ctx.upload_shapes2(shapes, verts)
+    n = 100_000
+    shape = rng.integers(0, len(shapes), n).astype(np.uint32)
+    t = W.random_xforms2(rng, n, 5.0)
+    t["scale"] = rng.uniform(0.3, 3.0, n).astype(np.float32)
+    t["scale"][::97] = -1.5
+    t["d"][::131, 0] = np.nan
+    got = ctx.world_aabbs2(shape, t)
+    exp = o2.world_aabbs(shapes, verts, shape, t)
+    assert bits_equal(got, exp).all()

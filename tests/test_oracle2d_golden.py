@@ -225,3 +225,24 @@ def test_panic_statuses(o2):
     assert o2.support_point(circle(1.0), None, t, (1, 0))[1] == 10
     nan = np.float32(np.nan)
     assert o2.closest_edge([(nan, nan), (nan, 1), (1, nan)])[0] == 9  # assert_ulps_ne!(inf, distance)
+
+
+# ---- bounds: circle.rs:131-134, rectangle.rs:198-201, polygon.rs:245-270, util.rs:146-158, tests/aabb.rs:508-519
+def test_bounds_and_aabb2_transform(o2):
+    from oracle.binding import SHAPE2_DT
+    ident = transform_2d(0, 0, 0)
+    tri = np.array([(-1, 1), (0, -1), (1, 0)], np.float32)
+    verts = np.concatenate([GON17, tri])
+    shapes = np.concatenate([circle(10.0), rectangle(10, 10), polygon(0, 17), polygon(17, 3), rectangle(10, 20),
+                             particle2(), line2(3, -1, -2, 4)])
+    t = np.concatenate([ident] * 7)
+    b = o2.world_aabbs(shapes, verts, np.arange(7, dtype=np.uint32), t)
+    assert tuple(b[0]) == (-10, -10, 10, 10)      # test_circle_bound
+    assert tuple(b[1]) == (-5, -5, 5, 5)          # test_rectangle_bound
+    assert tuple(b[2]) == (-6, -8, 5, 7)          # polygon test_bound
+    assert tuple(b[3]) == (-1, -1, 1, 1)          # util.rs test_get_bound
+    assert tuple(b[5]) == (0, 0, 0, 0) and tuple(b[6]) == (-2, -1, 3, 4)
+    # tests/aabb.rs test_aabb2_transform: Aabb2((0,0),(10,20)) moved by (5,3) -> ((5,3),(15,23)); the same box
+    # as a Rectangle(10, 20) centred at (5, 10)
+    moved = o2.world_aabbs(shapes, verts, np.array([4], np.uint32), transform_2d(5 + 5, 3 + 10, 0))
+    assert tuple(moved[0]) == (5, 3, 15, 23)
