@@ -69,6 +69,7 @@ SYMBOLS = [
     "cb2_composites2_upload", "cb2_gjk2_intersection_complex", "cb2_gjk2_distance_complex",
     "cb2_gjk2_time_of_impact_complex",
     "cb2_world_aabbs2", "cb2_world_aabbs2_dev",
+    "cb2_sap2_find_collider_pairs_dev", "cb2_gjk2_intersection_bodies_dev",
 ]
 
 _lib = None
@@ -140,6 +141,8 @@ def load():
     lib.cb2_gjk2_time_of_impact_complex.argtypes = [vp, u32, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp]
     lib.cb2_world_aabbs2.argtypes = [vp, vp, vp, u64, vp]
     lib.cb2_world_aabbs2_dev.argtypes = [vp, vp, vp, u64, vp, vp]
+    lib.cb2_sap2_find_collider_pairs_dev.argtypes = [vp, vp, u64, u32, vp, vp, u64, C.POINTER(u64), vp]
+    lib.cb2_gjk2_intersection_bodies_dev.argtypes = [vp, u32, sp, vp, vp, vp, u64, vp, vp, vp]
     _lib = lib
     return lib
 

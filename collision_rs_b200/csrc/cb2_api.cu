@@ -73,6 +73,8 @@ struct cb2_ctx {
     std::vector<uint32_t> h_comp2_off;
     void* d_cx = nullptr;
     size_t cx_cap = 0;
+    cb2_aabb3* d_lift = nullptr;  // cb2_sap2_find_collider_pairs_dev: the boxes lifted to 3-D
+    uint64_t lift_cap = 0;
     void* d_misc = nullptr;  // host-API SAP / AABB buffers
     size_t misc_cap = 0;
     // classified (polyhedron) narrow phase workspaces: [0..NS) follow the host-API streams,
@@ -236,6 +238,7 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_cell_ext) cudaFree(c->d_cell_ext);
     if (c->d_cell_cursor) cudaFree(c->d_cell_cursor);
     if (c->d_misc) cudaFree(c->d_misc);
+    if (c->d_lift) cudaFree(c->d_lift);
     if (c->d_comp_off) cudaFree(c->d_comp_off);
     if (c->d_comp_shape) cudaFree(c->d_comp_shape);
     if (c->d_comp_local) cudaFree(c->d_comp_local);
@@ -1223,7 +1226,7 @@ static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings
                        const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t0,
                        const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
                        uint32_t iter_cap, cb2_contact2* out_c, float* out_d, uint8_t* status,
-                       cudaStream_t st, int slot);
+                       cudaStream_t st, int slot, const uint32_t* pair_body = nullptr);
 
 // d2: the 2-D instantiation — cb2_xform2 transforms (same 32-byte stride as cb2_xform), cb2_contact2
 // records, the 2-D composite table and the GJK2 kernels
@@ -1420,9 +1423,10 @@ static int narrow2_dev(cb2_ctx* c, int op, uint32_t strategy, const cb2_settings
                        const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform2* l_t0,
                        const cb2_xform2* l_t1, const cb2_xform2* r_t0, const cb2_xform2* r_t1, uint64_t n,
                        uint32_t iter_cap, cb2_contact2* out_c, float* out_d, uint8_t* status,
-                       cudaStream_t st, int slot) {
+                       cudaStream_t st, int slot, const uint32_t* pair_body) {
     narrow2_args A;
     std::memset(&A, 0, sizeof(A));
+    A.pair_body = pair_body;
     const bool epa = op == 0 && strategy == CB2_FULL_RESOLUTION;
     if (!c->d_cnt2[slot]) CK(c, cudaMalloc(&c->d_cnt2[slot], 8 * sizeof(uint32_t)));
     A.counters = c->d_cnt2[slot];  // queue cursors of the persistent kernels
@@ -1691,5 +1695,41 @@ int cb2_world_aabbs2(cb2_ctx* c, const uint32_t* shape, const cb2_xform2* t, uin
     CK(c, cudaMemcpyAsync(out, base + o_out, sizeof(cb2_aabb2) * n, cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     return CB2_OK;
+}
+}  // extern "C"
+
+// ---- the 2-D chain on the device: boxes -> SweepAndPrune2 pairs -> GJK2 on body pairs -------------------
+extern "C" {
+int cb2_sap2_find_collider_pairs_dev(cb2_ctx* c, const cb2_aabb2* aabbs, uint64_t n, uint32_t axis,
+                                     uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
+                                     void* stream) {
+    if (!c || !n_pairs) return fail(c, CB2_ERR_ARG, "null argument");
+    *n_pairs = 0;
+    if (axis > 1) return fail(c, CB2_ERR_ARG, "sweep axis must be 0 or 1");
+    if (n == 0) return CB2_OK;
+    if (!aabbs || !perm_out || (!pairs_out && cap)) return fail(c, CB2_ERR_ARG, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    if (c->lift_cap < n) {
+        if (c->d_lift) cudaFree(c->d_lift);
+        c->d_lift = nullptr;
+        c->lift_cap = 0;
+        CK(c, cudaMalloc(&c->d_lift, sizeof(cb2_aabb3) * n));
+        c->lift_cap = n;
+    }
+    CK(c, launch_lift_aabb2(aabbs, n, c->d_lift, static_cast<cudaStream_t>(stream)));
+    ++c->launches;
+    return cb2_sap3_find_collider_pairs_dev(c, c->d_lift, n, axis, perm_out, pairs_out, cap, n_pairs, stream);
+}
+int cb2_gjk2_intersection_bodies_dev(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                                     const uint32_t* body_shape, const cb2_xform2* body_t,
+                                     const uint32_t* pair_body, uint64_t n, cb2_contact2* out, uint8_t* status,
+                                     void* stream) {
+    int rc = narrow2_check(c, 0, strategy, settings, body_shape, body_shape, body_t, nullptr, body_t, nullptr, out,
+                           status);
+    if (rc || n == 0) return rc;
+    if (!pair_body) return fail(c, CB2_ERR_ARG, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    return narrow2_dev(c, 0, strategy, settings, body_shape, body_shape, body_t, nullptr, body_t, nullptr, n, 0, out,
+                       nullptr, status, static_cast<cudaStream_t>(stream), 0, pair_body);
 }
 }  // extern "C"

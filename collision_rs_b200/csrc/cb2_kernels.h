@@ -155,6 +155,7 @@ struct narrow2_args {           // all device pointers
     const cb2_xform2* r_t;
     const cb2_xform2* l_t1;     // end poses (time of impact only)
     const cb2_xform2* r_t1;
+    const uint32_t* pair_body;  // optional 2 x n body indices (intersection only): l_shape / l_t per body
     uint64_t n;
     cb2_settings settings;
     uint32_t iter_cap;
@@ -172,6 +173,7 @@ struct narrow2_args {           // all device pointers
 };
 // op: 0 intersection (k_gjk2_intersection [+ the two k_epa2 tiers]), 1 distance, 2 time of impact
 cudaError_t launch_narrow2(int op, const narrow2_args& A, int sm_count, cudaStream_t st);
+cudaError_t launch_lift_aabb2(const cb2_aabb2* in, uint64_t n, cb2_aabb3* out, cudaStream_t st);
 cudaError_t launch_world_aabbs2(const cb2_shape2* shapes, const float* verts, const uint32_t* shape,
                                 const cb2_xform2* t, uint64_t n, cb2_aabb2* out, cudaStream_t st);
 

@@ -282,6 +282,7 @@ struct narrow2_args_dev {
     const float4* r_t;
     const float4* l_t1;
     const float4* r_t1;
+    const uint32_t* pair_body;  // optional 2 x n body indices: then l_shape / l_t are per BODY
     uint64_t n;
     cb2_settings settings;
     uint32_t iter_cap;
@@ -321,6 +322,23 @@ CB2_DI float4 edge_of(f2 a, f2 b) {
     return make_float4(n.x, n.y, dot(n, a), 0.0f);
 }
 
+// pair i of an intersection batch: direct (shape / transform per pair and side) or through bodies
+// (pair_body[2i], pair_body[2i+1] index one body table: SweepAndPrune2 output feeding the narrow phase)
+CB2_DI void load_pair2(const narrow2_args_dev& A, uint64_t i, shape2& l, shape2& r, xform2& lt, xform2& rt) {
+    if (A.pair_body) {
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(A.pair_body) + i);
+        l = load_shape2(A.shapes, A.verts, __ldg(A.l_shape + b.x));
+        r = load_shape2(A.shapes, A.verts, __ldg(A.l_shape + b.y));
+        lt = load_xform2(A.l_t, b.x);
+        rt = load_xform2(A.l_t, b.y);
+    } else {
+        l = load_shape2(A.shapes, A.verts, __ldg(A.l_shape + i));
+        r = load_shape2(A.shapes, A.verts, __ldg(A.r_shape + i));
+        lt = load_xform2(A.l_t, i);
+        rt = load_xform2(A.r_t, i);
+    }
+}
+
 // vertices a shape can contribute to the Minkowski difference's hull (a circle: unbounded)
 CB2_DI uint32_t hull_vertices(const shape2& s) {
     return s.kind == CB2_PARTICLE2 ? 1u
@@ -339,10 +357,10 @@ __global__ void __launch_bounds__(128) k_gjk2_intersection(narrow2_args_dev A) {
     simplex2 s;
     s.len = 0;
     if (valid) {
-        const shape2 l = load_shape2(A.shapes, A.verts, __ldg(A.l_shape + i));
-        const shape2 r = load_shape2(A.shapes, A.verts, __ldg(A.r_shape + i));
+        shape2 l, r;
+        xform2 lt, rt;
+        load_pair2(A, i, l, r, lt, rt);
         small = hull_vertices(l) + hull_vertices(r) <= 8u;
-        const xform2 lt = load_xform2(A.l_t, i), rt = load_xform2(A.r_t, i);
         uint8_t status = CB2_NONE;
         const uint32_t panic = pair_panic(l, lt, r, rt);
         if (panic) {
@@ -469,10 +487,7 @@ __global__ void __launch_bounds__(EPA2_THREADS) k_epa2(narrow2_args_dev A) {
                 } else {
                     slot = queue[qi];
                     pair = A.hits[slot];
-                    l = load_shape2(A.shapes, A.verts, __ldg(A.l_shape + pair));
-                    r = load_shape2(A.shapes, A.verts, __ldg(A.r_shape + pair));
-                    lt = load_xform2(A.l_t, pair);
-                    rt = load_xform2(A.r_t, pair);
+                    load_pair2(A, pair, l, r, lt, rt);
                     const float4* sx = A.simplex + 3 * (size_t)slot;
                     const float4 a = sx[0], b = sx[1], c = sx[2];
                     P(0) = a;
@@ -846,6 +861,25 @@ cudaError_t launch_world_aabbs2(const cb2_shape2* shapes, const float* verts, co
     return cudaGetLastError();
 }
 
+// SweepAndPrune2 through the 3-D machinery: boxes lifted to z in [0, 1] (the strict z test always holds)
+__global__ void __launch_bounds__(256) k_lift_aabb2(const cb2_aabb2* __restrict__ in, uint64_t n,
+                                                    cb2_aabb3* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(in) + i);
+    out[i].min[0] = b.x;
+    out[i].min[1] = b.y;
+    out[i].min[2] = 0.0f;
+    out[i].max[0] = b.z;
+    out[i].max[1] = b.w;
+    out[i].max[2] = 1.0f;
+}
+cudaError_t launch_lift_aabb2(const cb2_aabb2* in, uint64_t n, cb2_aabb3* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_lift_aabb2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_narrow2(int op, const narrow2_args& H, int sm_count, cudaStream_t st) {
     narrow2_args_dev A;
     A.shapes = reinterpret_cast<const float4*>(H.shapes);
@@ -856,6 +890,7 @@ cudaError_t launch_narrow2(int op, const narrow2_args& H, int sm_count, cudaStre
     A.r_t = reinterpret_cast<const float4*>(H.r_t);
     A.l_t1 = reinterpret_cast<const float4*>(H.l_t1);
     A.r_t1 = reinterpret_cast<const float4*>(H.r_t1);
+    A.pair_body = H.pair_body;
     A.n = H.n;
     A.settings = H.settings;
     A.iter_cap = H.iter_cap;

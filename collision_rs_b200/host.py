@@ -170,6 +170,24 @@ class Context:
         self._ck(self.lib.cb2_world_aabbs2(self.h, ptr(shape), ptr(t), len(shape), ptr(out)))
         return out
 
+    def world_aabbs2_dev(self, shape, t, n, out, stream=0):
+        self._ck(self.lib.cb2_world_aabbs2_dev(self.h, shape, t, int(n), out, stream))
+
+    def sap2_dev(self, aabbs2, n, axis, perm_out, pairs_out, cap, stream=0):
+        npairs = C.c_uint64(0)
+        rc = self.lib.cb2_sap2_find_collider_pairs_dev(self.h, aabbs2, int(n), int(axis), perm_out, pairs_out,
+                                                       int(cap), C.byref(npairs), stream)
+        if rc == abi.ERR_NOSPC:
+            return rc, int(npairs.value)
+        self._ck(rc)
+        return 0, int(npairs.value)
+
+    def intersection2_bodies_dev(self, strategy, body_shape, body_t, pair_body, n, out, status, stream=0,
+                                 settings=None):
+        settings = settings or Settings.default()
+        self._ck(self.lib.cb2_gjk2_intersection_bodies_dev(
+            self.h, int(strategy), C.byref(settings), body_shape, body_t, pair_body, int(n), out, status, stream))
+
     def upload_composites2(self, part_off, part_shape, part_local):
         """2-D composites: parts [part_off[c], part_off[c+1]) of (part_shape -> 2-D shape table,
         part_local: XFORM2_DT)."""

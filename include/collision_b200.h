@@ -447,6 +447,17 @@ int cb2_world_aabbs2(cb2_ctx* ctx, const uint32_t* shape, const cb2_xform2* t, u
 int cb2_world_aabbs2_dev(cb2_ctx* ctx, const uint32_t* shape, const cb2_xform2* t, uint64_t n,
                          cb2_aabb2* out, void* stream);
 
+/* The 2-D chain on the device, mirroring cb2_sap3_find_collider_pairs_dev -> cb2_gjk3_intersection_bodies_dev:
+ * SweepAndPrune2 on device boxes (same contract as the 3-D call, axis in {0, 1}), then GJK2 on the
+ * pairs, which index one body table (shape = body_shape[..], transform = body_t[..]).              */
+int cb2_sap2_find_collider_pairs_dev(cb2_ctx* ctx, const cb2_aabb2* aabbs, uint64_t n, uint32_t axis,
+                                     uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap,
+                                     uint64_t* n_pairs, void* stream);
+int cb2_gjk2_intersection_bodies_dev(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                                     const uint32_t* body_shape, const cb2_xform2* body_t,
+                                     const uint32_t* pair_body /* 2 x n, interleaved */, uint64_t n,
+                                     cb2_contact2* out, uint8_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,4 +299,11 @@ extern "C" {
                             out: *mut cb2_aabb2) -> c_int;
     pub fn cb2_world_aabbs2_dev(ctx: *mut cb2_ctx, shape: *const u32, t: *const cb2_xform2, n: u64,
                                 out: *mut cb2_aabb2, stream: *mut c_void) -> c_int;
+    pub fn cb2_sap2_find_collider_pairs_dev(ctx: *mut cb2_ctx, aabbs: *const cb2_aabb2, n: u64, axis: u32,
+                                            perm_out: *mut u32, pairs_out: *mut u32, cap: u64,
+                                            n_pairs: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn cb2_gjk2_intersection_bodies_dev(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                            body_shape: *const u32, body_t: *const cb2_xform2,
+                                            pair_body: *const u32, n: u64, out: *mut cb2_contact2,
+                                            status: *mut u8, stream: *mut c_void) -> c_int;
 }

@@ -260,3 +260,52 @@ def test_world_aabbs2_match_oracle(ctx, o2):
     got = ctx.world_aabbs2(shape, t)
     exp = o2.world_aabbs(shapes, verts, shape, t)
     assert bits_equal(got, exp).all()
+
+
+def test_device_chain_bodies_to_boxes_to_pairs_to_contacts(ctx, o2, oracle):
+    """The 2-D pipeline without a host trip: cb2_world_aabbs2_dev -> cb2_sap2_find_collider_pairs_dev ->
+    cb2_gjk2_intersection_bodies_dev, every stage bit-identical to the oracle."""
+    import torch
+    from oracle.binding import AABB_DT
+    rng = np.random.default_rng(21)
+    shapes, verts = W.shapes2_table(256, 91)
+    ctx.upload_shapes2(shapes, verts)
+    n = 60_000
+    body_shape = rng.integers(0, len(shapes), n).astype(np.uint32)
+    body_t = W.random_xforms2(rng, n, 120.0)
+    dev = torch.device("cuda:0")
+    dv = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(dev)
+    d_shape, d_t = dv(body_shape), dv(body_t)
+    s = torch.cuda.current_stream().cuda_stream
+    boxes = torch.zeros(n * 4, dtype=torch.float32, device=dev)
+    ctx.world_aabbs2_dev(d_shape.data_ptr(), d_t.data_ptr(), n, boxes.data_ptr(), s)
+    exp_boxes = o2.world_aabbs(shapes, verts, body_shape, body_t)
+    torch.cuda.synchronize()
+    assert bits_equal(boxes.cpu().numpy().reshape(-1, 4), exp_boxes).all()
+    perm = torch.zeros(n, dtype=torch.int32, device=dev)
+    cap = 16 * n
+    pairs = torch.zeros(2 * cap, dtype=torch.int32, device=dev)
+    rc, cnt = ctx.sap2_dev(boxes.data_ptr(), n, 0, perm.data_ptr(), pairs.data_ptr(), cap, s)
+    torch.cuda.synchronize()
+    lifted = np.zeros(n, AABB_DT)
+    lifted["min"][:, :2], lifted["max"][:, :2] = exp_boxes[:, :2], exp_boxes[:, 2:]
+    lifted["max"][:, 2] = 1.0
+    perm_e, pairs_e, _, _ = oracle.sap3(lifted, 0)
+    assert rc == 0 and cnt == len(pairs_e) and cnt > 1000
+    got_pairs = pairs[:2 * cnt].cpu().numpy().view(np.uint32).reshape(-1, 2)
+    assert np.array_equal(perm.cpu().numpy().view(np.uint32), perm_e) and np.array_equal(got_pairs, pairs_e)
+    # bodies in sorted order, like the reference's permuted slice
+    p64 = perm.long()
+    s_shape = d_shape.view(torch.int32)[p64].contiguous()
+    s_t = d_t.view(-1, 32)[p64].contiguous()
+    out = torch.zeros(cnt * abi.CONTACT2_DT.itemsize, dtype=torch.uint8, device=dev)
+    st = torch.zeros(cnt, dtype=torch.uint8, device=dev)
+    ctx.intersection2_bodies_dev(0, s_shape.data_ptr(), s_t.data_ptr(), pairs.data_ptr(), cnt, out.data_ptr(),
+                                 st.data_ptr(), s)
+    torch.cuda.synchronize()
+    bs, bt = body_shape[perm_e], body_t[perm_e]
+    a, b = pairs_e[:, 0], pairs_e[:, 1]
+    exp, est = o2.intersection(0, shapes, verts, np.ascontiguousarray(bs[a]), np.ascontiguousarray(bs[b]),
+                               np.ascontiguousarray(bt[a]), np.ascontiguousarray(bt[b]), nthreads=8)
+    assert_contacts_equal(out.cpu().numpy().view(abi.CONTACT2_DT), st.cpu().numpy(), exp, est, "2-D chain")
+    assert (est == 1).mean() > 0.2
