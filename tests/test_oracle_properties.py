@@ -285,3 +285,60 @@ def test_head_on_circles_time_of_impact(o2):
     assert np.array_equal(st[clear] == 1, (travel > gap)[clear])
     hit = clear & (st == 1)
     assert np.allclose(c["toi"][hit], (gap / travel)[hit], rtol=2e-3, atol=2e-3)
+
+
+def test_head_on_spheres_time_of_impact(oracle):
+    rng = np.random.default_rng(8)
+    n = 2000
+    shapes = np.zeros(2 * n, abi.SHAPE_DT)
+    shapes["kind"] = abi.SPHERE
+    shapes["p"][:, 0] = rng.uniform(0.25, 1.0, 2 * n).astype(np.float32)
+    r1, r2 = shapes["p"][:n, 0].astype(np.float64), shapes["p"][n:, 0].astype(np.float64)
+    gap = rng.uniform(0.5, 3.0, n)
+    travel = rng.uniform(0.5, 6.0, n)
+    u = rng.standard_normal((n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)                      # approach along a random axis
+    q = _quat(rng, n)
+    l0 = _xf3(q, np.zeros((n, 3), np.float32))
+    l1 = _xf3(q, (u * travel[:, None]).astype(np.float32))
+    r0 = _xf3(_quat(rng, n), (u * (r1 + r2 + gap)[:, None]).astype(np.float32))
+    li, ri = np.arange(n, dtype=np.uint32), np.arange(n, 2 * n, dtype=np.uint32)
+    c, st = oracle.time_of_impact(shapes, None, li, ri, l0, l1, r0, r0, iter_cap=1024, nthreads=4)
+    clear = np.abs(travel - gap) > 2e-2
+    assert np.array_equal((st == 1)[clear & (st != 5)], (travel > gap)[clear & (st != 5)])
+    assert (st == 5).mean() < 0.02                                     # the reference's never-ending loops
+    hit = clear & (st == 1)
+    assert np.allclose(c["toi"][hit], (gap / travel)[hit], rtol=5e-3, atol=5e-3)
+    # the normal opposes the approach direction (Contact.normal = -normalize(normal), gjk/mod.rs:241-252)
+    assert np.all(np.abs((c["normal"][hit] * u[hit]).sum(1)) > 0.99)
+
+
+def test_capsule_of_zero_height_is_a_sphere_and_cube_is_a_cuboid(oracle):
+    """Independent cross-checks between Primitive3 variants: Capsule(half_height 0, r) supports like
+    Sphere(r) (capsule.rs:45-61 adds (0, +-0, 0)); Cube(d) is Cuboid(d, d, d) (cuboid.rs:144-158)."""
+    rng = np.random.default_rng(9)
+    n = 3000
+    r = rng.uniform(0.3, 1.0, 2 * n).astype(np.float32)
+    sph = np.zeros(2 * n, abi.SHAPE_DT)
+    sph["kind"], sph["p"][:, 0] = abi.SPHERE, r
+    cap = np.zeros(2 * n, abi.SHAPE_DT)
+    cap["kind"], cap["p"][:, 0], cap["p"][:, 1] = abi.CAPSULE, 0.0, r
+    lt = _xf3(_quat(rng, n), rng.uniform(-1, 1, (n, 3)).astype(np.float32), rng.uniform(0.5, 2, n).astype(np.float32))
+    rt = _xf3(_quat(rng, n), rng.uniform(-1, 1, (n, 3)).astype(np.float32))
+    li, ri = np.arange(n, dtype=np.uint32), np.arange(n, 2 * n, dtype=np.uint32)
+    cs, ss = oracle.intersection(1, sph, None, li, ri, lt, rt, nthreads=4)
+    cc, sc = oracle.intersection(1, cap, None, li, ri, lt, rt, nthreads=4)
+    assert (ss != sc).mean() < 0.002 and 0.2 < (ss == 1).mean() < 0.98
+    ds, sds = oracle.distance(sph, None, li, ri, lt, rt, nthreads=4)
+    dc, sdc = oracle.distance(cap, None, li, ri, lt, rt, nthreads=4)
+    both = (sds == 1) & (sdc == 1)
+    assert (sds != sdc).mean() < 0.01 and np.allclose(ds[both], dc[both], rtol=1e-4, atol=1e-5)
+    dims = rng.uniform(0.5, 2.0, 2 * n).astype(np.float32)
+    cube = np.zeros(2 * n, abi.SHAPE_DT)
+    cube["kind"], cube["p"][:, 0] = abi.CUBE, dims
+    cuboid = np.zeros(2 * n, abi.SHAPE_DT)
+    cuboid["kind"] = abi.CUBOID
+    cuboid["p"] = dims[:, None]
+    a, sa = oracle.intersection(0, cube, None, li, ri, lt, rt, nthreads=4)
+    b, sb = oracle.intersection(0, cuboid, None, li, ri, lt, rt, nthreads=4)
+    assert np.array_equal(sa, sb) and a.tobytes() == b.tobytes()
