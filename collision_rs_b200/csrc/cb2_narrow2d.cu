@@ -6,12 +6,18 @@
 // unfused f32 in cgmath's order (cb2_math.cuh), so results are bit-identical to the reference.
 //
 // Design: a pair is cheap in 2-D (a support is 10-30 flops, the simplex holds at most 3 points), so
-// one thread owns one pair and keeps the whole GJK state in registers.  EPA2 is different from the
-// reference in one respect that cannot change a bit: the reference recomputes EVERY edge's normal
-// and distance (a sqrt and a divide each) after every insertion (closest_edge, epa2d.rs:136-157);
-// an edge's (normal, distance) is a pure function of its two end points, and an insertion replaces
-// exactly one edge by two, so the kernel caches them per edge and the per-iteration scan becomes
-// compares only — O(n) instead of O(n) sqrt+div, on pairs (circles) that run to 100 iterations.
+// one thread owns one pair and keeps the whole GJK state in registers:
+//   k_gjk2_intersection      GJK::intersect; FullResolution hits go to two queues by shape kind
+//   k_epa2<12, small>        EPA2 for pairs with <= 8 hull vertices, ring entirely in shared memory
+//   k_epa2<104, large>       EPA2 for everything else (and the small tier's overflows)
+//   k_gjk2_distance[_p]      GJK::distance: thread per pair, or persistent lanes for long-tailed tables
+//   k_gjk2_time_of_impact    GJK::intersection_time_of_impact
+//   k_world_aabbs2, k_lift_aabb2   bounds and the SweepAndPrune2 lift
+// EPA2 differs from the reference in one respect that cannot change a bit: the reference recomputes
+// EVERY edge's normal and distance (a sqrt and a divide each) after every insertion (closest_edge,
+// epa2d.rs:136-157); an edge's (normal, distance) is a pure function of its two end points, and an
+// insertion replaces exactly one edge by two, so the kernels cache the distances per edge (the scan
+// becomes compares only) and keep the polygon as a linked ring (nothing is shifted).
 #include <cstdlib>
 
 #include "cb2_kernels.h"
