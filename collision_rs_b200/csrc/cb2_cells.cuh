@@ -63,7 +63,7 @@ struct poly_ref {
 };
 
 // kept out of line: it is the rare path, and inlining it (three call sites) bloats the hot loops
-static __device__ __noinline__ f3 poly_full_scan(const float4* __restrict__ verts, uint32_t n, f3 d) {
+CB2_NOINLINE_DEVICE f3 poly_full_scan(const float4* __restrict__ verts, uint32_t n, f3 d) {
     f3 best = zero3();
     float best_dot = -INFINITY;
     for (uint32_t i = 0; i < n; ++i) {
@@ -78,7 +78,7 @@ static __device__ __noinline__ f3 poly_full_scan(const float4* __restrict__ vert
     return best;
 }
 
-static __device__ __noinline__ f3 poly_ext_scan(const float4* __restrict__ verts,
+CB2_NOINLINE_DEVICE f3 poly_ext_scan(const float4* __restrict__ verts,
                                          const uint16_t* __restrict__ e, uint32_t n, f3 d) {
     f3 best = zero3();
     float best_dot = -INFINITY;
@@ -100,7 +100,7 @@ static __device__ __noinline__ f3 poly_ext_scan(const float4* __restrict__ verts
 // vertex table; the vertex's own float4 carries its offset (in uint32 units from the shape's first
 // vertex) in .w, so the climb needs no pointer beyond `verts`.  Returns (point, hang): the
 // reference's loop `while best_dot != previous_best_dot` never ends once best_dot is NaN.
-static __device__ __noinline__ float4 poly_hill_climb(const float4* __restrict__ verts, uint32_t vcnt,
+CB2_NOINLINE_DEVICE float4 poly_hill_climb(const float4* __restrict__ verts, uint32_t vcnt,
                                                       f3 d) {
     float4 bv = __ldg(verts);
     float best_dot = dot(mk3(bv.x, bv.y, bv.z), d);

@@ -28,8 +28,7 @@
 //    next tier RESUMES it at the same iteration (nothing is recomputed).  sup_a of each polytope
 //    vertex is only read by the final contact (epa3d.rs:84-114), so it lives in a global
 //    scratch, not shared memory.
-#include "cb2_gjk.cuh"
-#include "cb2_kernels.h"
+#include "cb2_epa_lane.cuh"
 
 #ifndef CB2_T0_F  // build-time overrides for A/B experiments (tools/ab_variants.sh)
 #define CB2_T0_F 40
@@ -52,15 +51,6 @@
 #define CB2_U_FACE 1
 #endif
 namespace cb2 {
-
-CB2_DI shape_table table_of(const shape_table_args& a) {
-    shape_table t;
-    t.shapes = a.shapes;
-    t.poly.verts = a.verts;
-    t.poly.cells = a.cells;
-    t.poly.ext = a.ext;
-    return t;
-}
 
 // per-group polytope scratch in shared memory
 template <int FCAP, int VCAP, int OCAP>
@@ -175,19 +165,6 @@ struct bitmask<4> {
 };
 template <>
 struct bitmask<3> : bitmask<4> {};
-
-struct epa_args {
-    narrow_args A;
-    narrow_ws W;
-    uint32_t tier;  // 0 .. EPA_TIERS-1
-};
-
-// tier-0 polytope dump record, in float4 units: header (nf, nv, it) | fnd | pv | pa | fidx
-constexpr uint32_t OVER_RESUME = 0x80000000u;  // over-list entry flag: a dump record exists
-template <int F, int V>
-struct dump_layout {
-    static constexpr int FND = 1, PV = FND + F, PA = PV + V, FIDX = PA + V, SIZE = FIDX + (F + 3) / 4;
-};
 
 enum : int { S_FETCH = 0, S_RUN = 1, S_EXIT = 2 };
 
@@ -558,12 +535,38 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     }
 }
 
+// ---- lane-per-pair tiers (cb2_epa_lane.cuh) ------------------------------------------------------------
+template <int FCAP, int VCAP, int ECAP>
+constexpr int lane_blocks_per_sm() {
+    // 227 KB of shared memory per SM, 1 KB reserved per block
+    return (int)((227u * 1024u) / (sizeof(lane_store<FCAP, VCAP, ECAP>) + 1024u));
+}
+template <int FCAP, int VCAP, int ECAP, int RF, int RV>
+__global__ void __launch_bounds__(32, (lane_blocks_per_sm<FCAP, VCAP, ECAP>()))
+k_epa_lane(epa_args C) {
+    extern __shared__ __align__(16) float smem[];
+    auto& S = *reinterpret_cast<lane_store<FCAP, VCAP, ECAP>*>(smem);
+    epa_lane_run<FCAP, VCAP, ECAP, RF, RV>(C, S, C.W.pa + (size_t)blockIdx.x * VCAP * 32, threadIdx.x);
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
-// tier:            G   faces  verts  examined/horizon cap
-#ifndef CB2_T0_G
-#define CB2_T0_G 4
+// tier 0 (and optionally tier 1): lane per pair        faces  verts  edge/move list
+#ifndef CB2_L0_F
+#define CB2_L0_F 40
+#define CB2_L0_V 24
+#define CB2_L0_E 16
 #endif
-constexpr int T0_G = CB2_T0_G, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O;
+#ifndef CB2_LANE_TIER1   // 1: tier 1 runs the lane kernel as well (caps CB2_L1_*)
+#define CB2_LANE_TIER1 0
+#endif
+#ifndef CB2_L1_F
+#define CB2_L1_F 64
+#define CB2_L1_V 36
+#define CB2_L1_E 24
+#endif
+constexpr int L0_F = CB2_L0_F, L0_V = CB2_L0_V, L0_E = CB2_L0_E;
+constexpr int L1_F = CB2_L1_F, L1_V = CB2_L1_V, L1_E = CB2_L1_E;
+// group tiers (k_epa above):      G   faces  verts  examined/horizon cap
 #ifndef CB2_T1_G
 #define CB2_T1_G 8
 #endif
@@ -572,13 +575,24 @@ constexpr int T0_G = CB2_T0_G, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O
 #define CB2_T1_V 40
 #define CB2_T1_O 32
 #endif
-constexpr int T1_G = CB2_T1_G, T1_F = CB2_T1_F, T1_V = CB2_T1_V, T1_O = CB2_T1_O;
+constexpr int T1_G = CB2_T1_G, T1_F = CB2_LANE_TIER1 ? L1_F : CB2_T1_F, T1_V = CB2_LANE_TIER1 ? L1_V : CB2_T1_V,
+              T1_O = CB2_T1_O;
 constexpr int T2_G = 8, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
 
 template <int G, int F, int V, int O, int RF, int RV>
 static int epa_blocks(int sm_count) {
     auto kern = k_epa<G, F, V, O, RF, RV>;
     const size_t smem = (size_t)(32 / G) * sizeof(poly_smem<F, V, O>);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    return per_sm * sm_count;
+}
+template <int F, int V, int E, int RF, int RV>
+static int lane_blocks(int sm_count) {
+    auto kern = k_epa_lane<F, V, E, RF, RV>;
+    const size_t smem = sizeof(lane_store<F, V, E>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1)
@@ -592,17 +606,24 @@ static cudaError_t launch_tier(const epa_args& C, int sm_count, cudaStream_t st)
     k_epa<G, F, V, O, RF, RV><<<epa_blocks<G, F, V, O, RF, RV>(sm_count), 32, smem, st>>>(C);
     return cudaGetLastError();
 }
+template <int F, int V, int E, int RF, int RV>
+static cudaError_t launch_lane_tier(const epa_args& C, int sm_count, cudaStream_t st) {
+    k_epa_lane<F, V, E, RF, RV><<<lane_blocks<F, V, E, RF, RV>(sm_count), 32, sizeof(lane_store<F, V, E>), st>>>(C);
+    return cudaGetLastError();
+}
 
 size_t epa_pa_scratch_bytes(int sm_count) {
-    const size_t a = (size_t)epa_blocks<T0_G, T0_F, T0_V, T0_O, 0, 0>(sm_count) * (32 / T0_G) * T0_V;
-    const size_t b = (size_t)epa_blocks<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(sm_count) * (32 / T1_G) * T1_V;
+    size_t m = (size_t)lane_blocks<L0_F, L0_V, L0_E, 0, 0>(sm_count) * 32 * L0_V;
+    size_t b;
+    if (CB2_LANE_TIER1) b = (size_t)lane_blocks<L1_F, L1_V, L1_E, L0_F, L0_V>(sm_count) * 32 * L1_V;
+    else b = (size_t)epa_blocks<T1_G, T1_F, T1_V, T1_O, L0_F, L0_V>(sm_count) * (32 / T1_G) * T1_V;
     const size_t c = (size_t)epa_blocks<T2_G, T2_F, T2_V, T2_O, T1_F, T1_V>(sm_count) * (32 / T2_G) * T2_V;
-    size_t m = a > b ? a : b;
+    m = m > b ? m : b;
     m = m > c ? m : c;
     return m * sizeof(float4);
 }
 size_t epa_dump_record_bytes(int tier) {
-    return (tier == 0 ? dump_layout<T0_F, T0_V>::SIZE : dump_layout<T1_F, T1_V>::SIZE) * sizeof(float4);
+    return (tier == 0 ? dump_layout<L0_F, L0_V>::SIZE : dump_layout<T1_F, T1_V>::SIZE) * sizeof(float4);
 }
 
 cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, int sm_count,
@@ -611,8 +632,11 @@ cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, 
     C.A = A;
     C.W = W;
     C.tier = (uint32_t)tier;
-    if (tier == 0) return launch_tier<T0_G, T0_F, T0_V, T0_O, 0, 0>(C, sm_count, st);
-    if (tier == 1) return launch_tier<T1_G, T1_F, T1_V, T1_O, T0_F, T0_V>(C, sm_count, st);
+    if (tier == 0) return launch_lane_tier<L0_F, L0_V, L0_E, 0, 0>(C, sm_count, st);
+    if (tier == 1) {
+        if (CB2_LANE_TIER1) return launch_lane_tier<L1_F, L1_V, L1_E, L0_F, L0_V>(C, sm_count, st);
+        return launch_tier<T1_G, T1_F, T1_V, T1_O, L0_F, L0_V>(C, sm_count, st);
+    }
     return launch_tier<T2_G, T2_F, T2_V, T2_O, T1_F, T1_V>(C, sm_count, st);
 }
 

@@ -136,7 +136,7 @@ CB2_DI f3 capsule_local_support(f3 h, f3 d) {
 }
 
 // the less common variants stay out of line so that they do not bloat the hot loops
-static __device__ __noinline__ f3 other_local_support(uint32_t kind, f3 h, f3 d) {
+CB2_NOINLINE_DEVICE f3 other_local_support(uint32_t kind, f3 h, f3 d) {
     if (kind == K_QUAD) return quad_local_support(h, d);
     if (kind == K_CYLINDER) return cylinder_local_support(h, d);
     return capsule_local_support(h, d);

@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "cb2_hostsim.h"
+
 namespace cb2 {
 
 #define CB2_DI __device__ __forceinline__
