@@ -541,12 +541,15 @@ constexpr int lane_blocks_per_sm() {
     // 227 KB of shared memory per SM, 1 KB reserved per block
     return (int)((227u * 1024u) / (sizeof(lane_store<FCAP, VCAP, ECAP>) + 1024u));
 }
+#ifndef CB2_LANE_PREFETCH
+#define CB2_LANE_PREFETCH 1
+#endif
 template <int FCAP, int VCAP, int ECAP, int RF, int RV>
 __global__ void __launch_bounds__(32, (lane_blocks_per_sm<FCAP, VCAP, ECAP>()))
 k_epa_lane(epa_args C) {
     extern __shared__ __align__(16) float smem[];
     auto& S = *reinterpret_cast<lane_store<FCAP, VCAP, ECAP>*>(smem);
-    epa_lane_run<FCAP, VCAP, ECAP, RF, RV>(C, S, C.W.pa + (size_t)blockIdx.x * VCAP * 32, threadIdx.x);
+    epa_lane_run<FCAP, VCAP, ECAP, RF, RV, CB2_LANE_PREFETCH != 0>(C, S, C.W.pa + (size_t)blockIdx.x * VCAP * 32, threadIdx.x);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------

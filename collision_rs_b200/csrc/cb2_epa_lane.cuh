@@ -71,8 +71,20 @@ CB2_DI uint32_t epa_claim(uint32_t* cursor, bool want, unsigned lane) {
 
 enum : int { L_FETCH = 0, L_RUN = 1, L_EXIT = 2 };
 
-// RF/RV: caps of the tier whose dumps this instantiation resumes (0 = none)
-template <int FCAP, int VCAP, int ECAP, int RF, int RV>
+CB2_DI void prefetch_l2(const void* p) {
+#ifndef CB2_HOST_SIM
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+// RF/RV: caps of the tier whose dumps this instantiation resumes (0 = none).
+// PF: every lane claims its NEXT work-list entry when it starts a pair and resolves the entry's
+// dependent loads (list -> shape indices) one round at a time while the current pair runs, so a
+// refill costs one memory round trip (shapes, transforms, simplex) instead of three back to back —
+// with one warp per block and 5-8 blocks per SM there are few other warps to hide them behind.
+template <int FCAP, int VCAP, int ECAP, int RF, int RV, bool PF>
 CB2_DI void epa_lane_run(const epa_args& C, lane_store<FCAP, VCAP, ECAP>& S, float4* __restrict__ pa_warp,
                          const unsigned lane) {
     static_assert(FCAP <= 64, "the visibility mask is one 64-bit word");
@@ -116,31 +128,73 @@ CB2_DI void epa_lane_run(const epa_args& C, lane_store<FCAP, VCAP, ECAP>& S, flo
     uint32_t pair = 0, it = 0, apex = 0;
     int nf = 0, nv = 0, len = 0, ne = 0;
     bool init4 = false;
+    // the claimed next entry: nx_stage 0 none, 1 list entry in flight, 2 indices in flight, 3 queue empty
+    int nx_stage = 0;
+    uint32_t nx_k = 0, nx_entry = 0, nx_a = 0, nx_b = 0;
 
     for (;;) {
         // ================= fetch (only the lanes whose pair finished) ====================================
+        if (PF && nx_stage == 1 && state == L_RUN) {
+            // second hop of the claimed entry (its first hop was issued a round ago)
+            const uint32_t np = nx_entry & ~OVER_RESUME;
+            if (A.pair_body) {
+                const uint2 b = __ldg(reinterpret_cast<const uint2*>(A.pair_body) + np);
+                nx_a = b.x;
+                nx_b = b.y;
+            } else {
+                nx_a = __ldg(A.l_shape + np);
+                nx_b = __ldg(A.r_shape + np);
+                prefetch_l2(A.l_t + 2 * (size_t)np);
+                prefetch_l2(A.r_t + 2 * (size_t)np);
+            }
+            if (!(RF > 0 && (nx_entry & OVER_RESUME))) prefetch_l2(C.W.simplex + (size_t)np * 8);
+            nx_stage = 2;
+        }
         {
             const bool want = state == L_FETCH;
-            const uint32_t k = epa_claim(cursor, want, lane);
+            uint32_t k = 0, entry = 0;
+            bool have = false;
+            {  // (with PF: only the first pair of a lane; the vote inside is taken by every lane)
+                const bool cold = want && (!PF || nx_stage == 0);
+                k = epa_claim(cursor, cold, lane);
+                if (cold && k < count) {
+                    entry = __ldg(list + k);
+                    have = true;
+                }
+            }
+            if (PF && want && nx_stage != 0) {
+                have = nx_stage != 3;
+                k = nx_k;
+                entry = nx_entry;
+            }
             if (want) {
-                if (k >= count) {
+                if (!have) {
                     state = L_EXIT;
                     nf = len = ne = 0;
                 } else {
-                    const uint32_t entry = __ldg(list + k);
                     pair = entry & ~OVER_RESUME;
                     uint32_t li, ri;
                     uint64_t lx, rx;
                     if (A.pair_body) {
-                        const uint2 b = __ldg(reinterpret_cast<const uint2*>(A.pair_body) + pair);
-                        lx = b.x;
-                        rx = b.y;
+                        if (PF && nx_stage == 2) {
+                            lx = nx_a;
+                            rx = nx_b;
+                        } else {
+                            const uint2 b = __ldg(reinterpret_cast<const uint2*>(A.pair_body) + pair);
+                            lx = b.x;
+                            rx = b.y;
+                        }
                         li = __ldg(A.l_shape + lx);
                         ri = __ldg(A.l_shape + rx);
                     } else {
                         lx = rx = pair;
-                        li = __ldg(A.l_shape + pair);
-                        ri = __ldg(A.r_shape + pair);
+                        if (PF && nx_stage == 2) {
+                            li = nx_a;
+                            ri = nx_b;
+                        } else {
+                            li = __ldg(A.l_shape + pair);
+                            ri = __ldg(A.r_shape + pair);
+                        }
                     }
                     p.ls = load_shape(p.T, li);
                     p.rs = load_shape(p.T, ri);
@@ -155,10 +209,12 @@ CB2_DI void epa_lane_run(const epa_args& C, lane_store<FCAP, VCAP, ECAP>& S, flo
                         nv = (int)__float_as_uint(h.y);
                         it = __float_as_uint(h.z);
                         const uint32_t* fi = reinterpret_cast<const uint32_t*>(rec + DL::FIDX);
+#pragma unroll 1
                         for (int j = 0; j < nf; ++j) {
                             FND(j) = rec[DL::FND + j];
                             FIDX(j) = fi[j];
                         }
+#pragma unroll 1
                         for (int j = 0; j < nv; ++j) {
                             PV(j) = rec[DL::PV + j];
                             PA(j) = rec[DL::PA + j];
@@ -188,6 +244,20 @@ CB2_DI void epa_lane_run(const epa_args& C, lane_store<FCAP, VCAP, ECAP>& S, flo
                         init4 = true;
                     }
                     state = L_RUN;
+                }
+            }
+            if (PF) {
+                // claim the entry after this one; its list word is consumed a round from now
+                const bool more = want && have;
+                const uint32_t k2 = epa_claim(cursor, more, lane);
+                if (more) {
+                    nx_k = k2;
+                    if (k2 < count) {
+                        nx_entry = __ldg(list + k2);
+                        nx_stage = 1;
+                    } else {
+                        nx_stage = 3;
+                    }
                 }
             }
         }
@@ -298,6 +368,7 @@ CB2_DI void epa_lane_run(const epa_args& C, lane_store<FCAP, VCAP, ECAP>& S, flo
                         int k = 0;
                         while (k < ne && (uint32_t)EL(k) != rev) ++k;
                         if (k < ne) {
+#pragma unroll 1
                             for (int m = k; m + 1 < ne; ++m) EL(m) = EL(m + 1);
                             --ne;
                         } else if (ne >= ECAP) {
@@ -359,10 +430,12 @@ CB2_DI void epa_lane_run(const epa_args& C, lane_store<FCAP, VCAP, ECAP>& S, flo
                     rec[0] = make_float4(__uint_as_float((uint32_t)nf), __uint_as_float((uint32_t)nv),
                                          __uint_as_float(it), 0.f);
                     uint32_t* fi = reinterpret_cast<uint32_t*>(rec + DL::FIDX);
+#pragma unroll 1
                     for (int j = 0; j < nf; ++j) {
                         rec[DL::FND + j] = FND(j);
                         fi[j] = FIDX(j);
                     }
+#pragma unroll 1
                     for (int j = 0; j < nv; ++j) {
                         rec[DL::PV + j] = PV(j);
                         rec[DL::PA + j] = PA(j);

@@ -59,14 +59,15 @@ int build_tables(const cb2_shape* shapes, uint32_t n_shapes, const float* verts_
 }
 
 template <int F, int V, int E, int RF, int RV>
-void run_tier(epa_args C, int tier, int warps) {
+void run_tier(epa_args C, int tier, int warps, bool pf) {
     C.tier = (uint32_t)tier;
     std::vector<lane_store<F, V, E>> S(warps);
     std::vector<float4> pa((size_t)warps * V * 32);
     // lanes are independent: each runs its state machine until the tier's queue is empty
     for (int w = 0; w < warps; ++w)
         for (unsigned lane = 0; lane < 32; ++lane)
-            epa_lane_run<F, V, E, RF, RV>(C, S[w], pa.data() + (size_t)w * V * 32, lane);
+            if (pf) epa_lane_run<F, V, E, RF, RV, true>(C, S[w], pa.data() + (size_t)w * V * 32, lane);
+            else epa_lane_run<F, V, E, RF, RV, false>(C, S[w], pa.data() + (size_t)w * V * 32, lane);
 }
 
 }  // namespace
@@ -81,7 +82,7 @@ extern "C" {
 int sim_gjk3_intersection_full(const cb2_shape* shapes, uint32_t n_shapes, const float* verts_xyz,
                                uint64_t n_verts, const uint32_t* l_shape, const uint32_t* r_shape,
                                const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
-                               const cb2_settings* settings, int caps, int warps, uint32_t dump_cap0,
+                               const cb2_settings* settings, int caps, int warps, uint32_t dump_cap0, int prefetch,
                                cb2_contact* out, uint8_t* status, uint32_t* tier_counts) {
     sim_tables T;
     const int rc = build_tables(shapes, n_shapes, verts_xyz, n_verts, T);
@@ -151,9 +152,9 @@ int sim_gjk3_intersection_full(const cb2_shape* shapes, uint32_t n_shapes, const
         C.W.dump_cap[0] = dump_cap0;
         C.W.dump[1] = dump1.data();
         C.W.dump_cap[1] = (uint32_t)n;
-        run_tier<F0, V0, E0, 0, 0>(C, 0, warps);
+        run_tier<F0, V0, E0, 0, 0>(C, 0, warps, prefetch != 0);
         tier_counts[1] = EC.n_list[1];
-        run_tier<F1, V1, E1, F0, V0>(C, 1, warps);
+        run_tier<F1, V1, E1, F0, V0>(C, 1, warps, prefetch != 0);
         tier_counts[2] = EC.n_list[2];
     };
     using std::integral_constant;

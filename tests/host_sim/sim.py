@@ -30,7 +30,7 @@ class Sim:
         self.lib = C.CDLL(build())
 
     def intersection_full(self, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None, caps=0,
-                          warps=3, dump_cap0=None):
+                          warps=3, dump_cap0=None, prefetch=True):
         settings = settings or Settings.default()
         n = len(l_shape)
         out = np.zeros(n, CONTACT_DT)
@@ -40,6 +40,6 @@ class Sim:
         rc = self.lib.sim_gjk3_intersection_full(
             _p(shapes), C.c_uint32(len(shapes)), _p(verts), C.c_uint64(nv), _p(l_shape), _p(r_shape),
             _p(l_t), _p(r_t), C.c_uint64(n), C.byref(settings), C.c_int(caps), C.c_int(warps),
-            C.c_uint32(n if dump_cap0 is None else dump_cap0), _p(out), _p(status), _p(tiers))
+            C.c_uint32(n if dump_cap0 is None else dump_cap0), C.c_int(int(prefetch)), _p(out), _p(status), _p(tiers))
         assert rc == 0, rc
         return out, status, tiers

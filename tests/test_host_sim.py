@@ -59,6 +59,7 @@ def test_cuboid_pairs(sim, oracle):
     for spread in (0.75, 0.05):
         w = W.cfg1_cuboid_pairs(10_000, spread=spread, seed=5)
         _check(sim, oracle, w, caps=0)
+        _check(sim, oracle, w, caps=0, prefetch=False)
 
 
 def test_settings_are_honoured(sim, oracle):

@@ -10,7 +10,7 @@ if [ "$mode" = build ]; then
   while [ $# -gt 0 ]; do
     name=$1; extra=$2; shift 2
     make -s -C collision_rs_b200/csrc BUILD=build/$name OUT=../variants/libcb2_$name.so EXTRA="$extra" ../variants/libcb2_$name.so
-    grep -A2 "k_epaILi[0-9]ELi[0-9]*ELi[0-9]*ELi[0-9]*ELi0" collision_rs_b200/csrc/build/$name/cb2_epa.ptxas.log | grep registers | sed "s/^/$name tier0: /"
+    grep -A3 "k_epa_lane" collision_rs_b200/csrc/build/$name/cb2_epa.ptxas.log | grep registers | sed "s/^/$name lane tiers: /"
   done
 else
   for name in "$@"; do
