@@ -28,7 +28,7 @@
 //    next tier RESUMES it at the same iteration (nothing is recomputed).  sup_a of each polytope
 //    vertex is only read by the final contact (epa3d.rs:84-114), so it lives in a global
 //    scratch, not shared memory.
-#include "cb2_epa_lane.cuh"
+#include "cb2_epa_team.cuh"
 
 #ifndef CB2_T0_F  // build-time overrides for A/B experiments (tools/ab_variants.sh)
 #define CB2_T0_F 40
@@ -536,23 +536,74 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
 }
 
 // ---- lane-per-pair tiers (cb2_epa_lane.cuh) ------------------------------------------------------------
-template <int FCAP, int VCAP, int ECAP>
-constexpr int lane_blocks_per_sm() {
-    // 227 KB of shared memory per SM, 1 KB reserved per block
-    return (int)((227u * 1024u) / (sizeof(lane_store<FCAP, VCAP, ECAP>) + 1024u));
-}
 #ifndef CB2_LANE_PREFETCH
 #define CB2_LANE_PREFETCH 1
 #endif
+#ifndef CB2_LANE_GLOBAL   // 1: the polytopes live in global memory (L1/L2-backed) instead of shared memory
+#define CB2_LANE_GLOBAL 0
+#endif
+#ifndef CB2_LANE_WARPS    // blocks (= warps) per SM when CB2_LANE_GLOBAL
+#define CB2_LANE_WARPS 12
+#endif
+template <int FCAP, int VCAP, int ECAP>
+constexpr int lane_blocks_per_sm() {
+    if (CB2_LANE_GLOBAL) return CB2_LANE_WARPS;
+    // 227 KB of shared memory per SM, 1 KB reserved per block
+    return (int)((227u * 1024u) / (sizeof(lane_store<FCAP, VCAP, ECAP>) + 1024u));
+}
+// per-block scratch in global memory: [lane_store when CB2_LANE_GLOBAL] sup_a[VCAP][32]
+template <int FCAP, int VCAP, int ECAP>
+struct lane_scratch {
+    static constexpr size_t BYTES =
+        (CB2_LANE_GLOBAL ? sizeof(lane_store<FCAP, VCAP, ECAP>) : 0) + (size_t)VCAP * 32 * sizeof(float4);
+};
 template <int FCAP, int VCAP, int ECAP, int RF, int RV>
 __global__ void __launch_bounds__(32, (lane_blocks_per_sm<FCAP, VCAP, ECAP>()))
 k_epa_lane(epa_args C) {
     extern __shared__ __align__(16) float smem[];
-    auto& S = *reinterpret_cast<lane_store<FCAP, VCAP, ECAP>*>(smem);
-    epa_lane_run<FCAP, VCAP, ECAP, RF, RV, CB2_LANE_PREFETCH != 0>(C, S, C.W.pa + (size_t)blockIdx.x * VCAP * 32, threadIdx.x);
+    constexpr size_t SCRATCH = lane_scratch<FCAP, VCAP, ECAP>::BYTES;
+    char* scratch = reinterpret_cast<char*>(C.W.pa) + (size_t)blockIdx.x * SCRATCH;
+    auto& S = *reinterpret_cast<lane_store<FCAP, VCAP, ECAP>*>(CB2_LANE_GLOBAL ? (void*)scratch : (void*)smem);
+    float4* pa = reinterpret_cast<float4*>(scratch + (CB2_LANE_GLOBAL ? sizeof(lane_store<FCAP, VCAP, ECAP>) : 0));
+    epa_lane_run<FCAP, VCAP, ECAP, RF, RV, CB2_LANE_PREFETCH != 0>(C, S, pa, threadIdx.x);
+}
+
+// ---- warp-team tiers (cb2_epa_team.cuh) --------------------------------------------------------------
+template <int W, int FCAP, int VCAP, int ECAP>
+constexpr int team_blocks_per_sm() {
+    return (int)((227u * 1024u) / (sizeof(team_store<W, FCAP, VCAP, ECAP>) + 1024u));
+}
+template <int W, int FCAP, int VCAP, int ECAP, int RF, int RV>
+__global__ void __launch_bounds__(32 * W, (team_blocks_per_sm<W, FCAP, VCAP, ECAP>()))
+k_epa_team(epa_args C) {
+    using T = epa_team<W, FCAP, VCAP, ECAP, RF, RV>;
+    extern __shared__ __align__(16) float smem[];
+    auto& S = *reinterpret_cast<typename T::store*>(smem);
+    float4* pa = C.W.pa + (size_t)blockIdx.x * VCAP * 32;
+    const int w = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    typename T::regs R;
+    T::init(R);
+    for (;;) {
+        T::part0(C, S, pa, R, w, lane);
+        __syncthreads();
+        T::part1(C, S, pa, R, w, lane);
+        __syncthreads();
+        T::part2(C, S, pa, R, w, lane);
+        __syncthreads();
+        T::part3(C, S, pa, R, w, lane);
+        __syncthreads();
+        T::part4(C, S, pa, R, w, lane);
+        __syncthreads();
+        T::part5(C, S, pa, R, w, lane);
+        if (__syncthreads_and(R.state == L_EXIT)) break;
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
+#ifndef CB2_TEAM_W        // warps per 32 pairs in tiers 0 (and 1); 0: the lane kernel (one warp)
+#define CB2_TEAM_W 4
+#endif
 // tier 0 (and optionally tier 1): lane per pair        faces  verts  edge/move list
 #ifndef CB2_L0_F
 #define CB2_L0_F 40
@@ -564,7 +615,7 @@ k_epa_lane(epa_args C) {
 #endif
 #ifndef CB2_L1_F
 #define CB2_L1_F 64
-#define CB2_L1_V 36
+#define CB2_L1_V 32
 #define CB2_L1_E 24
 #endif
 constexpr int L0_F = CB2_L0_F, L0_V = CB2_L0_V, L0_E = CB2_L0_E;
@@ -595,7 +646,7 @@ static int epa_blocks(int sm_count) {
 template <int F, int V, int E, int RF, int RV>
 static int lane_blocks(int sm_count) {
     auto kern = k_epa_lane<F, V, E, RF, RV>;
-    const size_t smem = sizeof(lane_store<F, V, E>);
+    const size_t smem = CB2_LANE_GLOBAL ? 0 : sizeof(lane_store<F, V, E>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1)
@@ -609,21 +660,45 @@ static cudaError_t launch_tier(const epa_args& C, int sm_count, cudaStream_t st)
     k_epa<G, F, V, O, RF, RV><<<epa_blocks<G, F, V, O, RF, RV>(sm_count), 32, smem, st>>>(C);
     return cudaGetLastError();
 }
+template <int W, int F, int V, int E, int RF, int RV>
+static int team_blocks(int sm_count) {
+    auto kern = k_epa_team<W, F, V, E, RF, RV>;
+    const size_t smem = sizeof(team_store<W, F, V, E>);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    return per_sm * sm_count;
+}
+template <int W, int F, int V, int E, int RF, int RV>
+static cudaError_t launch_team_tier(const epa_args& C, int sm_count, cudaStream_t st) {
+    k_epa_team<W, F, V, E, RF, RV><<<team_blocks<W, F, V, E, RF, RV>(sm_count), 32 * W,
+                                     sizeof(team_store<W, F, V, E>), st>>>(C);
+    return cudaGetLastError();
+}
 template <int F, int V, int E, int RF, int RV>
 static cudaError_t launch_lane_tier(const epa_args& C, int sm_count, cudaStream_t st) {
-    k_epa_lane<F, V, E, RF, RV><<<lane_blocks<F, V, E, RF, RV>(sm_count), 32, sizeof(lane_store<F, V, E>), st>>>(C);
+    k_epa_lane<F, V, E, RF, RV><<<lane_blocks<F, V, E, RF, RV>(sm_count), 32,
+                                  CB2_LANE_GLOBAL ? 0 : sizeof(lane_store<F, V, E>), st>>>(C);
     return cudaGetLastError();
 }
 
 size_t epa_pa_scratch_bytes(int sm_count) {
-    size_t m = (size_t)lane_blocks<L0_F, L0_V, L0_E, 0, 0>(sm_count) * 32 * L0_V;
-    size_t b;
-    if (CB2_LANE_TIER1) b = (size_t)lane_blocks<L1_F, L1_V, L1_E, L0_F, L0_V>(sm_count) * 32 * L1_V;
-    else b = (size_t)epa_blocks<T1_G, T1_F, T1_V, T1_O, L0_F, L0_V>(sm_count) * (32 / T1_G) * T1_V;
-    const size_t c = (size_t)epa_blocks<T2_G, T2_F, T2_V, T2_O, T1_F, T1_V>(sm_count) * (32 / T2_G) * T2_V;
+    constexpr int TW = CB2_TEAM_W ? CB2_TEAM_W : 2;
+    size_t m, b;
+    if (CB2_TEAM_W) m = (size_t)team_blocks<TW, L0_F, L0_V, L0_E, 0, 0>(sm_count) * 32 * L0_V * sizeof(float4);
+    else m = (size_t)lane_blocks<L0_F, L0_V, L0_E, 0, 0>(sm_count) * lane_scratch<L0_F, L0_V, L0_E>::BYTES;
+    if (CB2_LANE_TIER1 && CB2_TEAM_W)
+        b = (size_t)team_blocks<TW, L1_F, L1_V, L1_E, L0_F, L0_V>(sm_count) * 32 * L1_V * sizeof(float4);
+    else if (CB2_LANE_TIER1)
+        b = (size_t)lane_blocks<L1_F, L1_V, L1_E, L0_F, L0_V>(sm_count) * lane_scratch<L1_F, L1_V, L1_E>::BYTES;
+    else
+        b = (size_t)epa_blocks<T1_G, T1_F, T1_V, T1_O, L0_F, L0_V>(sm_count) * (32 / T1_G) * T1_V * sizeof(float4);
+    const size_t c = (size_t)epa_blocks<T2_G, T2_F, T2_V, T2_O, T1_F, T1_V>(sm_count) * (32 / T2_G) * T2_V *
+                     sizeof(float4);
     m = m > b ? m : b;
     m = m > c ? m : c;
-    return m * sizeof(float4);
+    return m;
 }
 size_t epa_dump_record_bytes(int tier) {
     return (tier == 0 ? dump_layout<L0_F, L0_V>::SIZE : dump_layout<T1_F, T1_V>::SIZE) * sizeof(float4);
@@ -635,8 +710,13 @@ cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, 
     C.A = A;
     C.W = W;
     C.tier = (uint32_t)tier;
-    if (tier == 0) return launch_lane_tier<L0_F, L0_V, L0_E, 0, 0>(C, sm_count, st);
+    constexpr int TW = CB2_TEAM_W ? CB2_TEAM_W : 2;
+    if (tier == 0) {
+        if (CB2_TEAM_W) return launch_team_tier<TW, L0_F, L0_V, L0_E, 0, 0>(C, sm_count, st);
+        return launch_lane_tier<L0_F, L0_V, L0_E, 0, 0>(C, sm_count, st);
+    }
     if (tier == 1) {
+        if (CB2_LANE_TIER1 && CB2_TEAM_W) return launch_team_tier<TW, L1_F, L1_V, L1_E, L0_F, L0_V>(C, sm_count, st);
         if (CB2_LANE_TIER1) return launch_lane_tier<L1_F, L1_V, L1_E, L0_F, L0_V>(C, sm_count, st);
         return launch_tier<T1_G, T1_F, T1_V, T1_O, L0_F, L0_V>(C, sm_count, st);
     }

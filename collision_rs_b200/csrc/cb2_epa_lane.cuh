@@ -430,12 +430,12 @@ CB2_DI void epa_lane_run(const epa_args& C, lane_store<FCAP, VCAP, ECAP>& S, flo
                     rec[0] = make_float4(__uint_as_float((uint32_t)nf), __uint_as_float((uint32_t)nv),
                                          __uint_as_float(it), 0.f);
                     uint32_t* fi = reinterpret_cast<uint32_t*>(rec + DL::FIDX);
-#pragma unroll 1
+#pragma unroll 4
                     for (int j = 0; j < nf; ++j) {
                         rec[DL::FND + j] = FND(j);
                         fi[j] = FIDX(j);
                     }
-#pragma unroll 1
+#pragma unroll 8
                     for (int j = 0; j < nv; ++j) {
                         rec[DL::PV + j] = PV(j);
                         rec[DL::PA + j] = PA(j);

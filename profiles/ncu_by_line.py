@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --page source --csv` SASS dump by CUDA source line.
 
-usage: ncu_by_line.py <ncu_sass.csv> <cubin> <mangled-kernel-substring> [top] [outer]
+usage: ncu_by_line.py <ncu_sass.csv> <cubin> <mangled-kernel-substring> [top] [outer | in:<file>]
 The SASS instruction order of the report is aligned with `nvdisasm -gi` line markers.  With
 `outer`, an instruction is charged to the OUTERMOST line of its inline chain (the line of the
 kernel body that the inlined helper was called from) instead of the innermost one."""
@@ -14,6 +14,8 @@ from collections import defaultdict
 sass_csv, cubin, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 outer = len(sys.argv) > 5 and sys.argv[5] == "outer"
+# "in:<file>": charge an instruction to the outermost line of its inline chain that lies in <file>
+in_file = sys.argv[5][3:] if len(sys.argv) > 5 and sys.argv[5].startswith("in:") else None
 dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
 # isolate the function
 m = re.search(r"\.text\.[^\n]*" + re.escape(kern) + r"[^\n]*:\n", dis)
@@ -27,8 +29,14 @@ for ln in body.splitlines():
     mm = re.search(r'//## File "([^"]+)", line (\d+)( inlined at)?', ln)
     if mm:
         # a chain is printed innermost first; each entry but the last says "inlined at"
-        if outer or not chain_open:
-            cur = (mm.group(1).split("/")[-1], int(mm.group(2)))
+        here = (mm.group(1).split("/")[-1], int(mm.group(2)))
+        if in_file:
+            if not chain_open:
+                cur = here  # innermost entry: the default when the chain never enters in_file
+            if here[0] == in_file:
+                cur = here
+        elif outer or not chain_open:
+            cur = here
         chain_open = bool(mm.group(3))
         continue
     if re.search(r"/\*[0-9a-f]{4,}\*/\s+", ln) and ";" in ln:

@@ -14,7 +14,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../collision_rs_b200/csrc/cb2_epa_lane.cuh"
+#include "../../collision_rs_b200/csrc/cb2_epa_team.cuh"
 
 using namespace cb2;
 
@@ -70,19 +70,53 @@ void run_tier(epa_args C, int tier, int warps, bool pf) {
             else epa_lane_run<F, V, E, RF, RV, false>(C, S[w], pa.data() + (size_t)w * V * 32, lane);
 }
 
+// the warp-team kernel: every part runs for all warps and lanes of a block before the next part
+// starts (what the block barriers of k_epa_team enforce)
+template <int W, int F, int V, int E, int RF, int RV>
+void run_team_tier(epa_args C, int tier, int blocks) {
+    using T = epa_team<W, F, V, E, RF, RV>;
+    C.tier = (uint32_t)tier;
+    std::vector<typename T::store> S(blocks);
+    std::vector<float4> pa((size_t)blocks * V * 32);
+    std::vector<typename T::regs> R((size_t)blocks * W * 32);
+    for (auto& r : R) T::init(r);
+    std::vector<char> done(blocks, 0);
+    for (int left = blocks; left > 0;) {
+        for (int b = 0; b < blocks; ++b) {
+            if (done[b]) continue;
+            float4* p = pa.data() + (size_t)b * V * 32;
+            typename T::regs* r = R.data() + (size_t)b * W * 32;
+#define PART(fn)                                                      \
+    for (int w = 0; w < W; ++w)                                       \
+        for (unsigned lane = 0; lane < 32; ++lane) T::fn(C, S[b], p, r[w * 32 + lane], w, lane);
+            PART(part0) PART(part1) PART(part2) PART(part3) PART(part4) PART(part5)
+#undef PART
+            bool all = true;
+            for (int i = 0; i < W * 32; ++i) all = all && r[i].state == L_EXIT;
+            if (all) {
+                done[b] = 1;
+                --left;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
 
+void sim_force_literal_horizon(int on) { cb2::g_sim_force_literal_horizon = on != 0; }
+
 // GJK3::intersection(FullResolution) over a batch: device GJK source, then the lane tiers.
-// caps: 0 -> tier 0 (40,24,16) + tier 1 (64,36,24); 1 -> (32,20,16) + (64,36,24);
+// caps: 0 -> tier 0 (40,24,16) + tier 1 (64,32,24); 1 -> (32,20,16) + (64,32,24);
+// team_w: 0 -> the lane kernel (cb2_epa_lane.cuh); 2..4 -> the warp-team kernel (cb2_epa_team.cuh)
 //       2 -> (12,8,8) + (24,14,8) (tiny caps: exercises overflow, dump and resume on small inputs)
 // Pairs that outgrow tier 1 come back as status 7 (the CUDA build hands those to the group tiers).
 // tier_counts[0..2] = pairs queued for tier 0 / 1 / beyond.
 int sim_gjk3_intersection_full(const cb2_shape* shapes, uint32_t n_shapes, const float* verts_xyz,
                                uint64_t n_verts, const uint32_t* l_shape, const uint32_t* r_shape,
                                const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
-                               const cb2_settings* settings, int caps, int warps, uint32_t dump_cap0, int prefetch,
+                               const cb2_settings* settings, int caps, int warps, uint32_t dump_cap0, int prefetch, int team_w,
                                cb2_contact* out, uint8_t* status, uint32_t* tier_counts) {
     sim_tables T;
     const int rc = build_tables(shapes, n_shapes, verts_xyz, n_verts, T);
@@ -152,15 +186,21 @@ int sim_gjk3_intersection_full(const cb2_shape* shapes, uint32_t n_shapes, const
         C.W.dump_cap[0] = dump_cap0;
         C.W.dump[1] = dump1.data();
         C.W.dump_cap[1] = (uint32_t)n;
-        run_tier<F0, V0, E0, 0, 0>(C, 0, warps, prefetch != 0);
+        if (team_w == 4) run_team_tier<4, F0, V0, E0, 0, 0>(C, 0, warps);
+        else if (team_w == 2) run_team_tier<2, F0, V0, E0, 0, 0>(C, 0, warps);
+        else if (team_w == 3) run_team_tier<3, F0, V0, E0, 0, 0>(C, 0, warps);
+        else run_tier<F0, V0, E0, 0, 0>(C, 0, warps, prefetch != 0);
         tier_counts[1] = EC.n_list[1];
-        run_tier<F1, V1, E1, F0, V0>(C, 1, warps, prefetch != 0);
+        if (team_w == 4) run_team_tier<4, F1, V1, E1, F0, V0>(C, 1, warps);
+        else if (team_w == 2) run_team_tier<2, F1, V1, E1, F0, V0>(C, 1, warps);
+        else if (team_w == 3) run_team_tier<3, F1, V1, E1, F0, V0>(C, 1, warps);
+        else run_tier<F1, V1, E1, F0, V0>(C, 1, warps, prefetch != 0);
         tier_counts[2] = EC.n_list[2];
     };
     using std::integral_constant;
 #define IC(x) integral_constant<int, x>()
-    if (caps == 0) tiers(IC(40), IC(24), IC(16), IC(64), IC(36), IC(24));
-    else if (caps == 1) tiers(IC(32), IC(20), IC(16), IC(64), IC(36), IC(24));
+    if (caps == 0) tiers(IC(40), IC(24), IC(16), IC(64), IC(32), IC(24));
+    else if (caps == 1) tiers(IC(32), IC(20), IC(16), IC(64), IC(32), IC(24));
     else tiers(IC(12), IC(8), IC(8), IC(24), IC(14), IC(8));
 #undef IC
     // what tier 1 could not hold

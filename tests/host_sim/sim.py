@@ -29,8 +29,12 @@ class Sim:
     def __init__(self):
         self.lib = C.CDLL(build())
 
+    def force_literal_horizon(self, on):
+        """team kernel: take the literal remove_or_add_edge replay (the non-manifold path) always"""
+        self.lib.sim_force_literal_horizon(C.c_int(int(on)))
+
     def intersection_full(self, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None, caps=0,
-                          warps=3, dump_cap0=None, prefetch=True):
+                          warps=3, dump_cap0=None, prefetch=True, team_w=0):
         settings = settings or Settings.default()
         n = len(l_shape)
         out = np.zeros(n, CONTACT_DT)
@@ -40,6 +44,6 @@ class Sim:
         rc = self.lib.sim_gjk3_intersection_full(
             _p(shapes), C.c_uint32(len(shapes)), _p(verts), C.c_uint64(nv), _p(l_shape), _p(r_shape),
             _p(l_t), _p(r_t), C.c_uint64(n), C.byref(settings), C.c_int(caps), C.c_int(warps),
-            C.c_uint32(n if dump_cap0 is None else dump_cap0), C.c_int(int(prefetch)), _p(out), _p(status), _p(tiers))
+            C.c_uint32(n if dump_cap0 is None else dump_cap0), C.c_int(int(prefetch)), C.c_int(team_w), _p(out), _p(status), _p(tiers))
         assert rc == 0, rc
         return out, status, tiers
