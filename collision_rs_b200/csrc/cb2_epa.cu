@@ -601,9 +601,18 @@ k_epa_team(epa_args C) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-#ifndef CB2_TEAM_W        // warps per 32 pairs in tiers 0 (and 1); 0: the lane kernel (one warp)
+// Which kernel runs tier 0 (and, with CB2_LANE_TIER1, tier 1).  Measured on one B200, cfg 3 at 4 M
+// pairs (profiles/README.md, round 2): the group kernel k_epa 14.6 ms, the lane kernel 29.1 ms, the
+// warp-team kernel 26.7-29.3 ms (W = 3 / 4) — all three bit-identical to the oracle.  The group
+// kernel stays the product path; the other two are kept as measured experiments (A/B builds:
+// tools/ab_epa.sh name "-DCB2_TIER0_KIND=2 -DCB2_TEAM_W=3") and as the code the host simulation runs.
+#ifndef CB2_TIER0_KIND    // 0: group kernel (4 lanes of one warp per pair), 1: lane kernel, 2: warp-team kernel
+#define CB2_TIER0_KIND 0
+#endif
+#ifndef CB2_TEAM_W        // warps per 32 pairs of the warp-team kernel
 #define CB2_TEAM_W 4
 #endif
+constexpr bool TIER0_GROUP = CB2_TIER0_KIND == 0, TIER0_TEAM = CB2_TIER0_KIND == 2;
 // tier 0 (and optionally tier 1): lane per pair        faces  verts  edge/move list
 #ifndef CB2_L0_F
 #define CB2_L0_F 40
@@ -618,7 +627,8 @@ k_epa_team(epa_args C) {
 #define CB2_L1_V 32
 #define CB2_L1_E 24
 #endif
-constexpr int L0_F = CB2_L0_F, L0_V = CB2_L0_V, L0_E = CB2_L0_E;
+constexpr int L0_F = TIER0_GROUP ? CB2_T0_F : CB2_L0_F, L0_V = TIER0_GROUP ? CB2_T0_V : CB2_L0_V, L0_E = CB2_L0_E;
+constexpr int LK_F = CB2_L0_F, LK_V = CB2_L0_V;  // caps the lane / team kernels are instantiated with
 constexpr int L1_F = CB2_L1_F, L1_V = CB2_L1_V, L1_E = CB2_L1_E;
 // group tiers (k_epa above):      G   faces  verts  examined/horizon cap
 #ifndef CB2_T1_G
@@ -629,7 +639,12 @@ constexpr int L1_F = CB2_L1_F, L1_V = CB2_L1_V, L1_E = CB2_L1_E;
 #define CB2_T1_V 40
 #define CB2_T1_O 32
 #endif
-constexpr int T1_G = CB2_T1_G, T1_F = CB2_LANE_TIER1 ? L1_F : CB2_T1_F, T1_V = CB2_LANE_TIER1 ? L1_V : CB2_T1_V,
+#ifndef CB2_T0_G
+#define CB2_T0_G 4
+#endif
+constexpr int T0_G = CB2_T0_G, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O;
+constexpr bool LANE_T1 = CB2_LANE_TIER1 && !TIER0_GROUP;
+constexpr int T1_G = CB2_T1_G, T1_F = LANE_T1 ? L1_F : CB2_T1_F, T1_V = LANE_T1 ? L1_V : CB2_T1_V,
               T1_O = CB2_T1_O;
 constexpr int T2_G = 8, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
 
@@ -684,16 +699,21 @@ static cudaError_t launch_lane_tier(const epa_args& C, int sm_count, cudaStream_
 }
 
 size_t epa_pa_scratch_bytes(int sm_count) {
-    constexpr int TW = CB2_TEAM_W ? CB2_TEAM_W : 2;
     size_t m, b;
-    if (CB2_TEAM_W) m = (size_t)team_blocks<TW, L0_F, L0_V, L0_E, 0, 0>(sm_count) * 32 * L0_V * sizeof(float4);
-    else m = (size_t)lane_blocks<L0_F, L0_V, L0_E, 0, 0>(sm_count) * lane_scratch<L0_F, L0_V, L0_E>::BYTES;
-    if (CB2_LANE_TIER1 && CB2_TEAM_W)
-        b = (size_t)team_blocks<TW, L1_F, L1_V, L1_E, L0_F, L0_V>(sm_count) * 32 * L1_V * sizeof(float4);
+#if CB2_TIER0_KIND == 0
+    m = (size_t)epa_blocks<T0_G, T0_F, T0_V, T0_O, 0, 0>(sm_count) * (32 / T0_G) * T0_V * sizeof(float4);
+    b = (size_t)epa_blocks<T1_G, T1_F, T1_V, T1_O, L0_F, L0_V>(sm_count) * (32 / T1_G) * T1_V * sizeof(float4);
+#else
+    constexpr int TW = CB2_TEAM_W;
+    if (TIER0_TEAM) m = (size_t)team_blocks<TW, LK_F, LK_V, L0_E, 0, 0>(sm_count) * 32 * LK_V * sizeof(float4);
+    else m = (size_t)lane_blocks<LK_F, LK_V, L0_E, 0, 0>(sm_count) * lane_scratch<LK_F, LK_V, L0_E>::BYTES;
+    if (CB2_LANE_TIER1 && TIER0_TEAM)
+        b = (size_t)team_blocks<TW, L1_F, L1_V, L1_E, LK_F, LK_V>(sm_count) * 32 * L1_V * sizeof(float4);
     else if (CB2_LANE_TIER1)
-        b = (size_t)lane_blocks<L1_F, L1_V, L1_E, L0_F, L0_V>(sm_count) * lane_scratch<L1_F, L1_V, L1_E>::BYTES;
+        b = (size_t)lane_blocks<L1_F, L1_V, L1_E, LK_F, LK_V>(sm_count) * lane_scratch<L1_F, L1_V, L1_E>::BYTES;
     else
         b = (size_t)epa_blocks<T1_G, T1_F, T1_V, T1_O, L0_F, L0_V>(sm_count) * (32 / T1_G) * T1_V * sizeof(float4);
+#endif
     const size_t c = (size_t)epa_blocks<T2_G, T2_F, T2_V, T2_O, T1_F, T1_V>(sm_count) * (32 / T2_G) * T2_V *
                      sizeof(float4);
     m = m > b ? m : b;
@@ -710,14 +730,21 @@ cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, 
     C.A = A;
     C.W = W;
     C.tier = (uint32_t)tier;
-    constexpr int TW = CB2_TEAM_W ? CB2_TEAM_W : 2;
     if (tier == 0) {
-        if (CB2_TEAM_W) return launch_team_tier<TW, L0_F, L0_V, L0_E, 0, 0>(C, sm_count, st);
-        return launch_lane_tier<L0_F, L0_V, L0_E, 0, 0>(C, sm_count, st);
+#if CB2_TIER0_KIND == 0
+        return launch_tier<T0_G, T0_F, T0_V, T0_O, 0, 0>(C, sm_count, st);
+#else
+        constexpr int TW = CB2_TEAM_W;
+        if (TIER0_TEAM) return launch_team_tier<TW, LK_F, LK_V, L0_E, 0, 0>(C, sm_count, st);
+        return launch_lane_tier<LK_F, LK_V, L0_E, 0, 0>(C, sm_count, st);
+#endif
     }
     if (tier == 1) {
-        if (CB2_LANE_TIER1 && CB2_TEAM_W) return launch_team_tier<TW, L1_F, L1_V, L1_E, L0_F, L0_V>(C, sm_count, st);
-        if (CB2_LANE_TIER1) return launch_lane_tier<L1_F, L1_V, L1_E, L0_F, L0_V>(C, sm_count, st);
+#if CB2_TIER0_KIND != 0
+        constexpr int TW = CB2_TEAM_W;
+        if (CB2_LANE_TIER1 && TIER0_TEAM) return launch_team_tier<TW, L1_F, L1_V, L1_E, LK_F, LK_V>(C, sm_count, st);
+        if (CB2_LANE_TIER1) return launch_lane_tier<L1_F, L1_V, L1_E, LK_F, LK_V>(C, sm_count, st);
+#endif
         return launch_tier<T1_G, T1_F, T1_V, T1_O, L0_F, L0_V>(C, sm_count, st);
     }
     return launch_tier<T2_G, T2_F, T2_V, T2_O, T1_F, T1_V>(C, sm_count, st);
