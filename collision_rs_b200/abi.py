@@ -19,6 +19,9 @@ XFORM_DT = np.dtype([("scale", "<f4"), ("q", "<f4", (4,)), ("d", "<f4", (3,))]) 
 CONTACT_DT = np.dtype([("strategy", "<u4"), ("normal", "<f4", (3,)), ("depth", "<f4"),
                        ("point", "<f4", (3,)), ("toi", "<f4")])
 AABB_DT = np.dtype([("min", "<f4", (3,)), ("max", "<f4", (3,))])
+# SupportPoint<Point3<f32>> (minkowski/mod.rs:16-23)
+SUPPORT_POINT_DT = np.dtype([("v", "<f4", (3,)), ("sup_a", "<f4", (3,)), ("sup_b", "<f4", (3,))])
+assert SUPPORT_POINT_DT.itemsize == 36
 assert SHAPE_DT.itemsize == 24 and XFORM_DT.itemsize == 32
 assert CONTACT_DT.itemsize == 36 and AABB_DT.itemsize == 24
 # 2-D narrow phase (cb2_shape2 / cb2_xform2 / cb2_contact2); m = Basis2 columns (c0x, c0y, c1x, c1y)
@@ -35,6 +38,7 @@ SPHERE, CUBOID, POLYHEDRON, PARTICLE, QUAD, CYLINDER, CAPSULE, CUBE, POLYHEDRON_
 FULL_RESOLUTION, COLLISION_ONLY = 0, 1
 (NONE, SOME, PANIC_UNWRAP_PLANE, PANIC_ASSERT_RANGE, PANIC_INV_SCALE, NONCONVERGED,
  PANIC_EPA_EMPTY) = range(7)
+BAD_INDEX = 11
 OK, ERR_NO_DEVICE, ERR_CUDA, ERR_ARG, ERR_NOSPC, ERR_UNSUPPORTED, ERR_NAN = 0, -1, -2, -3, -4, -5, -6
 
 
@@ -57,6 +61,11 @@ SYMBOLS = [
     "cb2_gjk3_intersection", "cb2_gjk3_distance", "cb2_gjk3_time_of_impact",
     "cb2_gjk3_intersection_dev", "cb2_gjk3_distance_dev", "cb2_gjk3_time_of_impact_dev",
     "cb2_gjk3_intersection_bodies_dev",
+    "cb2_gjk3_intersect", "cb2_gjk3_get_contact_manifold",
+    "cb2_gjk3_intersect_dev", "cb2_gjk3_get_contact_manifold_dev",
+    "cb2_create_multi", "cb2_destroy_multi", "cb2_multi_device_count", "cb2_multi_ctx",
+    "cb2_multi_last_error", "cb2_multi_shapes_upload", "cb2_multi_gjk3_intersection",
+    "cb2_multi_gjk3_distance", "cb2_multi_gjk3_time_of_impact", "cb2_multi_sap3_find_collider_pairs",
     "cb2_composites_upload", "cb2_gjk3_intersection_complex", "cb2_gjk3_distance_complex",
     "cb2_gjk3_time_of_impact_complex",
     "cb2_sap3_find_collider_pairs", "cb2_sap3_find_collider_pairs_dev",
@@ -109,6 +118,24 @@ def load():
     lib.cb2_gjk3_distance_dev.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp, vp]
     lib.cb2_gjk3_time_of_impact_dev.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp]
     lib.cb2_gjk3_intersection_bodies_dev.argtypes = [vp, u32, sp, vp, vp, vp, u64, vp, vp, vp]
+    lib.cb2_create_multi.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
+    lib.cb2_destroy_multi.argtypes = [vp]
+    lib.cb2_destroy_multi.restype = None
+    lib.cb2_multi_device_count.argtypes = [vp]
+    lib.cb2_multi_ctx.argtypes = [vp, i32]
+    lib.cb2_multi_ctx.restype = vp
+    lib.cb2_multi_last_error.argtypes = [vp]
+    lib.cb2_multi_last_error.restype = C.c_char_p
+    lib.cb2_multi_shapes_upload.argtypes = [vp, vp, u32, vp, u64]
+    lib.cb2_multi_gjk3_intersection.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_multi_gjk3_distance.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_multi_gjk3_time_of_impact.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp]
+    lib.cb2_multi_sap3_find_collider_pairs.argtypes = [vp, vp, u64, C.POINTER(u32), vp, vp, u64,
+                                                       C.POINTER(u64)]
+    lib.cb2_gjk3_intersect.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_gjk3_get_contact_manifold.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, vp, vp]
+    lib.cb2_gjk3_intersect_dev.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp, vp]
+    lib.cb2_gjk3_get_contact_manifold_dev.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, vp, vp, vp]
     lib.cb2_composites_upload.argtypes = [vp, vp, vp, vp, u32]
     lib.cb2_gjk3_intersection_complex.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp]
     lib.cb2_gjk3_distance_complex.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp]

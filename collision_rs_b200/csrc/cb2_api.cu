@@ -7,6 +7,7 @@
 // fallback anywhere.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,8 @@ struct cb2_ctx {
     uint4* d_cells = nullptr;        // support cells of all polyhedra (cb2_cells.cuh)
     uint16_t* d_cell_ext = nullptr;  // their extension pool
     uint32_t* d_cell_cursor = nullptr;
+    uint32_t* d_bad_index = nullptr;  // set by the kernels when a pair names a shape outside the table
+    uint32_t* h_bad_index = nullptr;  // pinned mirror the host-buffer entry points read back
     uint32_t n_shapes = 0;
     uint64_t n_verts = 0;
     // 2-D shape table (cb2_shapes2_upload), independent of the 3-D one
@@ -237,6 +240,8 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_cells) cudaFree(c->d_cells);
     if (c->d_cell_ext) cudaFree(c->d_cell_ext);
     if (c->d_cell_cursor) cudaFree(c->d_cell_cursor);
+    if (c->d_bad_index) cudaFree(c->d_bad_index);
+    if (c->h_bad_index) cudaFreeHost(c->h_bad_index);
     if (c->d_misc) cudaFree(c->d_misc);
     if (c->d_lift) cudaFree(c->d_lift);
     if (c->d_comp_off) cudaFree(c->d_comp_off);
@@ -522,7 +527,7 @@ int cb2_shapes_upload_faces(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shap
 }  // extern "C"
 
 // ---- narrow phase ---------------------------------------------------------------------------------
-enum op_kind { OP_INTERSECTION, OP_DISTANCE, OP_TOI };
+enum op_kind { OP_INTERSECTION, OP_DISTANCE, OP_TOI, OP_INTERSECT, OP_MANIFOLD };
 
 static int check_settings(cb2_ctx* c, const cb2_settings* s) {
     if (!s) return fail(c, CB2_ERR_ARG, "settings is null");
@@ -571,7 +576,7 @@ static void mark_stage(cb2_ctx* c, int k, cudaStream_t st) {
 static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, cudaStream_t st,
                      int ws_slot = 0) {
     int rc = launch_op_inner(c, op, strategy, A, st, ws_slot);
-    if (rc || op != OP_INTERSECTION || strategy != CB2_FULL_RESOLUTION) return rc;
+    if (rc || !((op == OP_INTERSECTION && strategy == CB2_FULL_RESOLUTION) || op == OP_MANIFOLD)) return rc;
     if (std::getenv("CB2_NO_RETRY")) return CB2_OK;  // diagnosis: leave CB2_SCRATCH_OVERFLOW visible
     // redo the rare pairs whose polytope outgrew the fast kernels' scratch
     rc = ensure_retry(c, ws_slot);
@@ -596,11 +601,27 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
     A.T.verts = c->d_verts;
     A.T.cells = c->d_cells;
     A.T.ext = c->d_cell_ext;
+    A.n_shapes = c->n_shapes;
+    if (!c->d_bad_index) {
+        CK(c, cudaMalloc(&c->d_bad_index, sizeof(uint32_t)));
+        CK(c, cudaMemset(c->d_bad_index, 0, sizeof(uint32_t)));
+        CK(c, cudaMallocHost(&c->h_bad_index, sizeof(uint32_t)));
+    }
+    A.bad_index = c->d_bad_index;
     cudaError_t e;
-    if (op == OP_INTERSECTION && !c->legacy_epa) {
+    if (op == OP_INTERSECT) {
+        e = launch_gjk_intersect(A, st);
+        ++c->launches;
+        if (e != cudaSuccess) {
+            c->err = std::string("kernel launch: ") + cudaGetErrorString(e);
+            return CB2_ERR_CUDA;
+        }
+        return CB2_OK;
+    }
+    if ((op == OP_INTERSECTION && !c->legacy_epa) || op == OP_MANIFOLD) {
         // GJK (thread per pair) -> compacted hit list -> cooperative EPA tiers
         if (A.n > 0x7FFFFFFFull) return fail(c, CB2_ERR_ARG, "more than 2^31-1 pairs in one batch");
-        const bool full = strategy == CB2_FULL_RESOLUTION;
+        const bool full = strategy == CB2_FULL_RESOLUTION || op == OP_MANIFOLD;
         int rc = ensure_ws(c, ws_slot, A.n);
         if (rc) return rc;
         const narrow_ws& W = c->ws[ws_slot];
@@ -609,7 +630,12 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
         A.queue = c->d_queue[ws_slot];
         mark_stage(c, 0, st);
         trace_stage("begin", st);
-        e = launch_gjk_hits(A, full, W, c->sm_count, st);
+        if (op == OP_MANIFOLD) {
+            A.seed_simplex = W.simplex;  // the second-chance kernel restarts from the caller's simplex
+            e = launch_manifold_seed(A, W, st);
+        } else {
+            e = launch_gjk_hits(A, full, W, c->sm_count, st);
+        }
         ++c->launches;
         mark_stage(c, 1, st);
         trace_stage("gjk", st);
@@ -649,7 +675,8 @@ static int narrow_dev(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_setti
                       const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t0,
                       const cb2_xform* l_t1, const cb2_xform* r_t0, const cb2_xform* r_t1,
                       const uint32_t* pair_body, uint64_t n, uint32_t iter_cap, cb2_contact* out_c,
-                      float* out_d, uint8_t* status, void* stream) {
+                      float* out_d, uint8_t* status, void* stream, cb2_support_point* out_sx = nullptr,
+                      const cb2_support_point* in_sx = nullptr, const uint32_t* in_len = nullptr) {
     if (!c) return CB2_ERR_ARG;
     int rc = check_settings(c, settings);
     if (rc) return rc;
@@ -658,11 +685,16 @@ static int narrow_dev(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_setti
     if (!c->d_shapes) return fail(c, CB2_ERR_ARG, "cb2_shapes_upload has not been called");
     if (!l_shape || !l_t0 || !status || (!pair_body && (!r_shape || !r_t0)))
         return fail(c, CB2_ERR_ARG, "null argument");
-    if (op == OP_DISTANCE ? !out_d : !out_c) return fail(c, CB2_ERR_ARG, "null output");
+    if (op == OP_INTERSECT ? !out_sx : (op == OP_DISTANCE ? !out_d : !out_c))
+        return fail(c, CB2_ERR_ARG, "null output");
+    if (op == OP_MANIFOLD && !in_sx) return fail(c, CB2_ERR_ARG, "null simplex");
     if (op == OP_TOI && (!l_t1 || !r_t1)) return fail(c, CB2_ERR_ARG, "null end transform");
     CK(c, cudaSetDevice(c->device));
     narrow_args A;
     std::memset(&A, 0, sizeof(A));
+    A.out_simplex = out_sx;
+    A.in_simplex = in_sx;
+    A.in_simplex_len = in_len;
     A.l_shape = l_shape;
     A.r_shape = r_shape;
     A.l_t = reinterpret_cast<const float4*>(l_t0);
@@ -767,28 +799,40 @@ static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut
     };
     uint64_t b = 0;
     int rc = CB2_OK;
+    // inside the loop a failed CUDA call must not return: copies into the caller's buffers may
+    // still be in flight, and every exit has to pass the stream synchronisation below
+#define CKB(x)                                                             \
+    {                                                                      \
+        cudaError_t e_ = (x);                                              \
+        if (e_ != cudaSuccess) {                                           \
+            c->err = std::string(#x) + ": " + cudaGetErrorString(e_);      \
+            rc = CB2_ERR_CUDA;                                             \
+            break;                                                         \
+        }                                                                  \
+    }
     for (size_t k = 0; k < sizes.size() && rc == CB2_OK; ++k) {
         const uint64_t m = sizes[k];
         const int buf = (int)(k % cb2_ctx::NS), slot = (int)(k % (size_t)c->n_cstreams);
         char* base = c->d_stage[buf];
         cudaStream_t s_comp = c->stream[slot];
-        if (k >= (size_t)cb2_ctx::NS) CK(c, cudaStreamWaitEvent(s_in, c->ev_free[buf], 0));
+        if (k >= (size_t)cb2_ctx::NS) CKB(cudaStreamWaitEvent(s_in, c->ev_free[buf], 0))
         rc = copy_in(b, m, base, s_in);
         if (rc) break;
-        CK(c, cudaEventRecord(c->ev_in[buf], s_in));
+        CKB(cudaEventRecord(c->ev_in[buf], s_in))
         mark(s_in);
-        CK(c, cudaStreamWaitEvent(s_comp, c->ev_in[buf], 0));
+        CKB(cudaStreamWaitEvent(s_comp, c->ev_in[buf], 0))
         rc = compute(b, m, base, s_comp, slot);
         if (rc) break;
-        CK(c, cudaEventRecord(c->ev_k[buf], s_comp));
+        CKB(cudaEventRecord(c->ev_k[buf], s_comp))
         mark(s_comp);
-        CK(c, cudaStreamWaitEvent(s_out, c->ev_k[buf], 0));
+        CKB(cudaStreamWaitEvent(s_out, c->ev_k[buf], 0))
         rc = copy_out(b, m, base, s_out);
         if (rc) break;
-        CK(c, cudaEventRecord(c->ev_free[buf], s_out));
+        CKB(cudaEventRecord(c->ev_free[buf], s_out))
         mark(s_out);
         b += m;
     }
+#undef CKB
     for (int i = 0; i < cb2_ctx::NS + 2; ++i) {
         cudaError_t e = cudaStreamSynchronize(i < cb2_ctx::NS ? c->stream[i] : (i == cb2_ctx::NS ? s_in : s_out));
         if (e != cudaSuccess && rc == CB2_OK) {
@@ -819,8 +863,8 @@ static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut
     }
     return rc;
 }
-// a Rust slice index would panic on an out-of-range shape index: checked chunk by chunk, while the
-// GPU works on the chunks before (the call fails as a whole; outputs of a failed call are unspecified)
+// the 2-D host path checks its shape indices on the host, chunk by chunk (the 3-D kernels check on
+// the device, see narrow_host)
 static bool indices_in_range(const uint32_t* a, const uint32_t* b, uint64_t m, uint32_t limit) {
     uint32_t worst = 0;
     for (uint64_t i = 0; i < m; ++i) {
@@ -866,11 +910,13 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
             if (rc) return rc;
         }
     const cb2_xform* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
-    return pipeline_run(
+    // a Rust slice index would panic on an out-of-range shape index: the kernels check every index
+    // they load (status CB2_BAD_INDEX, nothing is read through it) and raise a device flag; the call
+    // then fails as a whole (outputs of a failed call are unspecified)
+    if (c->d_bad_index) CK(c, cudaMemsetAsync(c->d_bad_index, 0, sizeof(uint32_t), c->s_in));
+    rc = pipeline_run(
         c, n,
         [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
-            if (!indices_in_range(l_shape + b, r_shape + b, m, c->n_shapes))
-                return fail(c, CB2_ERR_ARG, "shape index out of range");
             for (int x = 0; x < n_xf; ++x)
                 CK(c, cudaMemcpyAsync(base + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform),
                                       cudaMemcpyHostToDevice, st));
@@ -906,6 +952,11 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
             CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
             return CB2_OK;
         });
+    if (rc == CB2_OK && c->d_bad_index) {
+        CK(c, cudaMemcpy(c->h_bad_index, c->d_bad_index, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (*c->h_bad_index) return fail(c, CB2_ERR_ARG, "shape index out of range");
+    }
+    return rc;
 }
 
 static int ensure_misc(cb2_ctx* c, size_t bytes) {
@@ -938,6 +989,89 @@ int cb2_gjk3_time_of_impact(cb2_ctx* c, const cb2_settings* settings, const uint
                             uint32_t iter_cap, cb2_contact* out, uint8_t* status) {
     return narrow_host(c, OP_TOI, 0, settings, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, n, iter_cap,
                        out, nullptr, status);
+}
+
+int cb2_gjk3_intersect_dev(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                           const uint32_t* r_shape, const cb2_xform* l_t, const cb2_xform* r_t,
+                           uint64_t n, cb2_support_point* simplex_out, uint8_t* status, void* stream) {
+    return narrow_dev(c, OP_INTERSECT, 0, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, nullptr,
+                      n, 0, nullptr, nullptr, status, stream, simplex_out);
+}
+int cb2_gjk3_get_contact_manifold_dev(cb2_ctx* c, const cb2_settings* settings,
+                                      const cb2_support_point* simplex, const uint32_t* simplex_len,
+                                      const uint32_t* l_shape, const uint32_t* r_shape,
+                                      const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                                      cb2_contact* out, uint8_t* status, void* stream) {
+    return narrow_dev(c, OP_MANIFOLD, 0, settings, l_shape, r_shape, l_t, nullptr, r_t, nullptr, nullptr,
+                      n, 0, out, nullptr, status, stream, nullptr, simplex, simplex_len);
+}
+
+// Host-buffer versions of the two: one staged batch (these are the building blocks a caller uses
+// when it wants the simplex between the two halves of GJK::intersection; the chunked pipeline of
+// cb2_gjk3_intersection is the fast path for the whole thing).
+static int simplex_host(cb2_ctx* c, bool manifold, const cb2_settings* settings,
+                        const cb2_support_point* in_sx, const uint32_t* in_len, const uint32_t* l_shape,
+                        const uint32_t* r_shape, const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                        cb2_support_point* out_sx, cb2_contact* out_c, uint8_t* status) {
+    if (!c) return CB2_ERR_ARG;
+    if (n == 0) return CB2_OK;
+    if (!l_shape || !r_shape || !l_t || !r_t || !status || (manifold ? (!in_sx || !out_c) : !out_sx))
+        return fail(c, CB2_ERR_ARG, "null argument");
+    CK(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_lt = 0, o_rt = al(n * sizeof(cb2_xform)), o_ls = o_rt + al(n * sizeof(cb2_xform)),
+                 o_rs = o_ls + al(n * 4), o_sx = o_rs + al(n * 4),
+                 o_len = o_sx + al(n * 4 * sizeof(cb2_support_point)), o_out = o_len + al(n * 4),
+                 o_st = o_out + al(n * sizeof(cb2_contact));
+    int rc = ensure_misc(c, o_st + al(n));
+    if (rc) return rc;
+    char* base = static_cast<char*>(c->d_misc);
+    cudaStream_t st = c->stream[0];
+    CK(c, cudaMemcpyAsync(base + o_lt, l_t, n * sizeof(cb2_xform), cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + o_rt, r_t, n * sizeof(cb2_xform), cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + o_ls, l_shape, n * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(base + o_rs, r_shape, n * 4, cudaMemcpyHostToDevice, st));
+    if (manifold) {
+        CK(c, cudaMemcpyAsync(base + o_sx, in_sx, n * 4 * sizeof(cb2_support_point), cudaMemcpyHostToDevice, st));
+        if (in_len) CK(c, cudaMemcpyAsync(base + o_len, in_len, n * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (c->d_bad_index) CK(c, cudaMemsetAsync(c->d_bad_index, 0, sizeof(uint32_t), st));
+    auto* d_sx = reinterpret_cast<cb2_support_point*>(base + o_sx);
+    auto* d_ls = reinterpret_cast<uint32_t*>(base + o_ls);
+    auto* d_rs = reinterpret_cast<uint32_t*>(base + o_rs);
+    auto* d_lt = reinterpret_cast<cb2_xform*>(base + o_lt);
+    auto* d_rt = reinterpret_cast<cb2_xform*>(base + o_rt);
+    auto* d_st = reinterpret_cast<uint8_t*>(base + o_st);
+    if (manifold)
+        rc = cb2_gjk3_get_contact_manifold_dev(c, settings, d_sx,
+                                               in_len ? reinterpret_cast<uint32_t*>(base + o_len) : nullptr,
+                                               d_ls, d_rs, d_lt, d_rt, n,
+                                               reinterpret_cast<cb2_contact*>(base + o_out), d_st, st);
+    else
+        rc = cb2_gjk3_intersect_dev(c, settings, d_ls, d_rs, d_lt, d_rt, n, d_sx, d_st, st);
+    if (rc) return rc;
+    if (manifold)
+        CK(c, cudaMemcpyAsync(out_c, base + o_out, n * sizeof(cb2_contact), cudaMemcpyDeviceToHost, st));
+    else
+        CK(c, cudaMemcpyAsync(out_sx, base + o_sx, n * 4 * sizeof(cb2_support_point), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(status, base + o_st, n, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(c->h_bad_index, c->d_bad_index, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    if (*c->h_bad_index) return fail(c, CB2_ERR_ARG, "shape index out of range");
+    return CB2_OK;
+}
+int cb2_gjk3_intersect(cb2_ctx* c, const cb2_settings* settings, const uint32_t* l_shape,
+                       const uint32_t* r_shape, const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                       cb2_support_point* simplex_out, uint8_t* status) {
+    return simplex_host(c, false, settings, nullptr, nullptr, l_shape, r_shape, l_t, r_t, n, simplex_out,
+                        nullptr, status);
+}
+int cb2_gjk3_get_contact_manifold(cb2_ctx* c, const cb2_settings* settings,
+                                  const cb2_support_point* simplex, const uint32_t* simplex_len,
+                                  const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t,
+                                  const cb2_xform* r_t, uint64_t n, cb2_contact* out, uint8_t* status) {
+    return simplex_host(c, true, settings, simplex, simplex_len, l_shape, r_shape, l_t, r_t, n, nullptr, out,
+                        status);
 }
 
 int cb2_gjk3_intersection_dev(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
@@ -1087,14 +1221,21 @@ int cb2_brute_force_find_collider_pairs(cb2_ctx* c, const cb2_aabb3* aabbs, uint
     CK(c, cudaSetDevice(c->device));
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_box = 0, o_pairs = al(sizeof(cb2_aabb3) * n);
-    int rc = ensure_misc(c, o_pairs + al(8 * (cap ? cap : 1)));
-    if (rc) return rc;
-    char* base = static_cast<char*>(c->d_misc);
+    uint64_t dcap = std::min<uint64_t>(cap, 16 * n + 1024);  // see cb2_sap3_find_collider_pairs
+    int rc = CB2_OK;
     cudaStream_t st = c->stream[0];
-    CK(c, cudaMemcpyAsync(base + o_box, aabbs, sizeof(cb2_aabb3) * n, cudaMemcpyHostToDevice, st));
-    rc = cb2_brute_force_find_collider_pairs_dev(c, reinterpret_cast<cb2_aabb3*>(base + o_box), n,
-                                                 reinterpret_cast<uint32_t*>(base + o_pairs), cap,
-                                                 n_pairs, st);
+    char* base = nullptr;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = ensure_misc(c, o_pairs + al(8 * (dcap ? dcap : 1)));
+        if (rc) return rc;
+        base = static_cast<char*>(c->d_misc);
+        CK(c, cudaMemcpyAsync(base + o_box, aabbs, sizeof(cb2_aabb3) * n, cudaMemcpyHostToDevice, st));
+        rc = cb2_brute_force_find_collider_pairs_dev(c, reinterpret_cast<cb2_aabb3*>(base + o_box), n,
+                                                     reinterpret_cast<uint32_t*>(base + o_pairs), dcap,
+                                                     n_pairs, st);
+        if (rc != CB2_ERR_NOSPC || *n_pairs > cap || dcap >= cap) break;
+        dcap = *n_pairs;
+    }
     if (rc) return rc;
     if (*n_pairs)
         CK(c, cudaMemcpyAsync(pairs_out, base + o_pairs, 8 * (*n_pairs), cudaMemcpyDeviceToHost, st));
@@ -1117,15 +1258,25 @@ int cb2_sap3_find_collider_pairs(cb2_ctx* c, const cb2_aabb3* aabbs, uint64_t n,
     CK(c, cudaSetDevice(c->device));
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_box = 0, o_perm = al(n * sizeof(cb2_aabb3)), o_pairs = o_perm + al(n * 4);
-    int rc = ensure_misc(c, o_pairs + al(cap * 8));
-    if (rc) return rc;
-    char* base = static_cast<char*>(c->d_misc);
+    // the device pair buffer is sized for what the call can need, not for the caller's bound (a
+    // safe cap such as n(n-1)/2 must not turn into a multi-GB allocation): 16 pairs per box to
+    // start with, the exact count on the one retry
+    uint64_t dcap = std::min<uint64_t>(cap, 16 * n + 1024);
+    int rc = CB2_OK;
     cudaStream_t st = c->stream[0];
-    CK(c, cudaMemcpyAsync(base + o_box, aabbs, n * sizeof(cb2_aabb3), cudaMemcpyHostToDevice, st));
-    rc = cb2_sap3_find_collider_pairs_dev(c, reinterpret_cast<cb2_aabb3*>(base + o_box), n,
-                                          *axis_inout, reinterpret_cast<uint32_t*>(base + o_perm),
-                                          reinterpret_cast<uint32_t*>(base + o_pairs), cap, n_pairs,
-                                          st);
+    char* base = nullptr;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = ensure_misc(c, o_pairs + al(dcap * 8));
+        if (rc) return rc;
+        base = static_cast<char*>(c->d_misc);
+        CK(c, cudaMemcpyAsync(base + o_box, aabbs, n * sizeof(cb2_aabb3), cudaMemcpyHostToDevice, st));
+        rc = cb2_sap3_find_collider_pairs_dev(c, reinterpret_cast<cb2_aabb3*>(base + o_box), n,
+                                              *axis_inout, reinterpret_cast<uint32_t*>(base + o_perm),
+                                              reinterpret_cast<uint32_t*>(base + o_pairs), dcap, n_pairs,
+                                              st);
+        if (rc != CB2_ERR_NOSPC || *n_pairs > cap || dcap >= cap) break;
+        dcap = *n_pairs;  // fits the caller's buffer: once more with room for every pair
+    }
     if (rc && rc != CB2_ERR_NOSPC) return rc;
     CK(c, cudaMemcpyAsync(perm_out, base + o_perm, n * 4, cudaMemcpyDeviceToHost, st));
     if (rc == CB2_OK && *n_pairs)

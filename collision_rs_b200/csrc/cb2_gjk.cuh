@@ -26,7 +26,8 @@ enum : uint8_t {
     ST_NONCONVERGED = 5,
     ST_PANIC_EPA_EMPTY = 6,
     ST_SCRATCH_OVERFLOW = 7,
-    ST_PANIC_CMP_NAN = 8
+    ST_PANIC_CMP_NAN = 8,
+    ST_BAD_INDEX = 11  // (9 and 10 belong to the 2-D path)
 };
 
 // Device shape-table entry (32 B, two 128-bit loads).  h = half_dim for a Cuboid
@@ -166,20 +167,24 @@ CB2_DI bool needs_inverse(uint32_t kind) { return kind != K_PARTICLE; }
 CB2_DI bool is_curved(uint32_t kind) { return kind == K_SPHERE || kind == K_CYLINDER || kind == K_CAPSULE; }
 
 // ---- simplex in registers -----------------------------------------------------------------
-// v[i] = SupportPoint.v, a[i] = SupportPoint.sup_a (only kept when the EPA contact needs it;
-// sup_b is never read on the 3-D path).  Newest point is LAST, as in the reference.
-template <bool WITH_A>
+// v[i] = SupportPoint.v, a[i] = SupportPoint.sup_a (only kept when the EPA contact needs it),
+// b[i] = SupportPoint.sup_b (never read on the 3-D path: only kept by the exported GJK::intersect,
+// whose caller receives whole SupportPoints).  Newest point is LAST, as in the reference.
+template <bool WITH_A, bool WITH_B = false>
 struct simplex {
     f3 v[4];
     f3 a[WITH_A ? 4 : 1];
+    f3 b[WITH_B ? 4 : 1];
     int n;
-    CB2_DI void set(int i, f3 pv, f3 pa) {
+    CB2_DI void set(int i, f3 pv, f3 pa, f3 pb = zero3()) {
         v[i] = pv;
         if (WITH_A) a[i] = pa;
+        if (WITH_B) b[i] = pb;
     }
     CB2_DI void mov(int dst, int src) {
         v[dst] = v[src];
         if (WITH_A) a[dst] = a[src];
+        if (WITH_B) b[dst] = b[src];
     }
     CB2_DI void swap01() {
         f3 t = v[0];
@@ -190,12 +195,17 @@ struct simplex {
             a[0] = a[1];
             a[1] = u;
         }
+        if (WITH_B) {
+            f3 u = b[0];
+            b[0] = b[1];
+            b[1] = u;
+        }
     }
-    CB2_DI void push(f3 pv, f3 pa) {  // n <= 3 on entry
-        if (n == 0) set(0, pv, pa);
-        else if (n == 1) set(1, pv, pa);
-        else if (n == 2) set(2, pv, pa);
-        else set(3, pv, pa);
+    CB2_DI void push(f3 pv, f3 pa, f3 pb = zero3()) {  // n <= 3 on entry
+        if (n == 0) set(0, pv, pa, pb);
+        else if (n == 1) set(1, pv, pa, pb);
+        else if (n == 2) set(2, pv, pa, pb);
+        else set(3, pv, pa, pb);
         ++n;
     }
 };
@@ -204,8 +214,8 @@ struct simplex {
 // Returns true iff the origin is inside the tetrahedron.  The reference calls check_side from
 // three places (ABC / ACD / triangle); here each place only selects operands and the single
 // check below runs once for the whole warp.
-template <bool WITH_A>
-CB2_DI bool reduce_to_closest_feature(simplex<WITH_A>& s, f3& v) {
+template <bool WITH_A, bool WITH_B>
+CB2_DI bool reduce_to_closest_feature(simplex<WITH_A, WITH_B>& s, f3& v) {
     bool check = false, above = false, ignore_ab = false;
     f3 N, E1, E2, ao;
     if (s.n == 4) {

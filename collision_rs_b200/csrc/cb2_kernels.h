@@ -30,12 +30,20 @@ struct narrow_args {
     const uint32_t* perm;       // optional: process pairs perm[0 .. *dev_count) (classified batches)
     const uint32_t* dev_count;
     uint64_t n;
+    uint32_t n_shapes;          // entries of the shape table: every shape index is checked against it
+    uint32_t* bad_index;        // optional device flag, set when a pair's shape index is out of range
     uint32_t* queue;            // device work-queue cursor of the persistent (lane-refill) kernels
     cb2_settings settings;
     uint32_t iter_cap;
     cb2_contact* out_contact;
     float* out_distance;
     uint8_t* out_status;
+    // GJK::intersect / get_contact_manifold exported on their own (gjk/mod.rs:101-146, 326-344)
+    cb2_support_point* out_simplex;        // 4 records per pair
+    const cb2_support_point* in_simplex;   // 4 records per pair
+    const uint32_t* in_simplex_len;        // optional: points actually held (EPA3 returns None below 4)
+    const float4* seed_simplex;            // set for get_contact_manifold: the second-chance kernel then
+                                           // starts from ws.simplex instead of running GJK again
 };
 
 struct aabb_args {
@@ -82,6 +90,8 @@ size_t epa_dump_record_bytes(int tier);
 size_t epa_pa_scratch_bytes(int sm_count);
 cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W, int sm_count,
                             cudaStream_t st);
+cudaError_t launch_gjk_intersect(const narrow_args& A, cudaStream_t st);
+cudaError_t launch_manifold_seed(const narrow_args& A, const narrow_ws& W, cudaStream_t st);
 cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, int sm_count,
                             cudaStream_t st);
 

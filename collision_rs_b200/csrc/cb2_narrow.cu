@@ -175,11 +175,11 @@ __global__ void __launch_bounds__(128) k_intersection(narrow_args A) {
     pair_in p;
     contact_out c = zero_contact();
     uint8_t st = ST_NONE;
-    if (!load_pair(A, i, A.l_t, A.r_t, p)) {
-        st = ST_PANIC_INV_SCALE;
+    if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
+        st = bad;
     } else {
         simplex<FULL> s;
-        if (gjk_intersect<FULL>(p, A.settings.max_iterations, s)) {
+        if (gjk_intersect(p, A.settings.max_iterations, s)) {
             if constexpr (FULL) {
                 st = epa_process_local(p, reinterpret_cast<const simplex<true>&>(s),
                                        A.settings.epa_tolerance, A.settings.max_iterations, c);
@@ -212,11 +212,11 @@ __global__ void __launch_bounds__(128, FULL ? CB2_GJK_FULL_MINB : 4) k_gjk_hits(
     if (i < A.n) {
         pair_in p;
         uint8_t st = ST_NONE;
-        if (!load_pair(A, i, A.l_t, A.r_t, p)) {
-            st = ST_PANIC_INV_SCALE;
+        if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
+            st = bad;
         } else {
             simplex<FULL> s;
-            const bool inside = gjk_intersect<FULL>(p, A.settings.max_iterations, s);
+            const bool inside = gjk_intersect(p, A.settings.max_iterations, s);
             if (p.ls.hang | p.rs.hang) {  // the reference's hill climb never returned
                 st = ST_NONCONVERGED;
             } else if (inside) {
@@ -257,6 +257,76 @@ __global__ void __launch_bounds__(128, FULL ? CB2_GJK_FULL_MINB : 4) k_gjk_hits(
     }
 }
 
+// GJK::intersect on its own (gjk/mod.rs:101-146): Some(simplex) -> the tetrahedron's four
+// SupportPoints {v, sup_a, sup_b} (minkowski/mod.rs:16-23) in the reference's Vec order
+__global__ void __launch_bounds__(128) k_gjk_intersect(narrow_args A) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    pair_in p;
+    simplex<true, true> s;
+    s.n = 0;
+    uint8_t st = ST_NONE;
+    if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
+        st = bad;
+    } else {
+        const bool inside = gjk_intersect(p, A.settings.max_iterations, s);
+        if (p.ls.hang | p.rs.hang) st = ST_NONCONVERGED;  // the reference's hill climb never returned
+        else if (inside) st = ST_SOME;
+    }
+    float* o = reinterpret_cast<float*>(A.out_simplex + 4 * i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool have = st == ST_SOME;
+        const f3 v = have ? s.v[k] : zero3(), a = have ? s.a[k] : zero3(), b = have ? s.b[k] : zero3();
+        o[9 * k + 0] = v.x; o[9 * k + 1] = v.y; o[9 * k + 2] = v.z;
+        o[9 * k + 3] = a.x; o[9 * k + 4] = a.y; o[9 * k + 5] = a.z;
+        o[9 * k + 6] = b.x; o[9 * k + 7] = b.y; o[9 * k + 8] = b.z;
+    }
+    A.out_status[i] = st;
+}
+
+// GJK::get_contact_manifold (gjk/mod.rs:326-344) = EPA3::process on a caller-held simplex: this
+// kernel stands where k_gjk_hits stands in GJK::intersection — it queues every simplex of four
+// points for the EPA tiers (fewer points: None, epa3d.rs:38-40)
+__global__ void __launch_bounds__(128) k_manifold_seed(narrow_args A, narrow_ws W) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false, curved = false;
+    if (i < A.n) {
+        pair_in p;
+        uint8_t st = ST_NONE;
+        if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
+            st = bad;  // EPA's first support call is where the reference would panic
+        } else if (!A.in_simplex_len || __ldg(A.in_simplex_len + i) >= 4u) {
+            hit = true;
+            curved = is_curved(p.ls.kind) || is_curved(p.rs.kind);
+            const float* s = reinterpret_cast<const float*>(A.in_simplex + 4 * i);
+            float4* o = W.simplex + i * 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                o[k] = make_float4(__ldg(s + 9 * k), __ldg(s + 9 * k + 1), __ldg(s + 9 * k + 2), 0.f);
+                o[4 + k] = make_float4(__ldg(s + 9 * k + 3), __ldg(s + 9 * k + 4), __ldg(s + 9 * k + 5), 0.f);
+            }
+        }
+        if (!hit) {
+            store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, zero_contact());
+            A.out_status[i] = st;
+        }
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m1 = __ballot_sync(0xffffffffu, hit && !curved);
+    const unsigned m3 = __ballot_sync(0xffffffffu, hit && curved);
+    uint32_t b1 = 0, b3 = 0;
+    if (lane == 0) {
+        if (m1) b1 = atomicAdd(&W.EC->n_list[0], __popc(m1));
+        if (m3) b3 = atomicAdd(&W.EC->n_list[EPA_TIERS - 1], __popc(m3));
+    }
+    b1 = __shfl_sync(0xffffffffu, b1, 0);
+    b3 = __shfl_sync(0xffffffffu, b3, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (hit && !curved) W.list[0][b1 + __popc(m1 & below)] = (uint32_t)i;
+    if (hit && curved) W.list[EPA_TIERS - 1][b3 + __popc(m3 & below)] = (uint32_t)i;
+}
+
 // GJK::distance, gjk/mod.rs:271-321
 __global__ void __launch_bounds__(128) k_distance(narrow_args A) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,8 +334,8 @@ __global__ void __launch_bounds__(128) k_distance(narrow_args A) {
     pair_in p;
     uint8_t st = ST_NONE;
     float result = 0.0f;
-    if (!load_pair(A, i, A.l_t, A.r_t, p)) {
-        st = ST_PANIC_INV_SCALE;
+    if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
+        st = bad;
     } else {
         const f3 d0 = seed_direction(p.lt, p.rt);
         simplex<false> s;
@@ -310,8 +380,8 @@ __global__ void __launch_bounds__(128) k_time_of_impact(narrow_args A) {
     pair_in p;
     contact_out c = zero_contact();
     uint8_t st = ST_NONE;
-    if (!load_pair(A, i, A.l_t, A.r_t, p)) {
-        st = ST_PANIC_INV_SCALE;
+    if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
+        st = bad;
     } else {
         uint64_t lx = i, rx = i;
         const xform lt1 = load_xform(A.l_t1, lx);
@@ -420,10 +490,10 @@ __global__ void __launch_bounds__(128, 4) k_gjk_hits_p(narrow_args A, narrow_ws 
                 done = true;
             } else {
                 i = ni;
-                if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+                if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
                     store_contact(A.out_contact, i, FULL ? CB2_FULL_RESOLUTION : CB2_COLLISION_ONLY,
                                   zero_contact());
-                    A.out_status[i] = ST_PANIC_INV_SCALE;
+                    A.out_status[i] = bad;
                 } else {
                     d = seed_direction(p.lt, p.rt);
                     state = 0;
@@ -521,9 +591,9 @@ __global__ void __launch_bounds__(128, 4) k_distance_p(narrow_args A) {
                 done = true;
             } else {
                 i = ni;
-                if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+                if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
                     A.out_distance[i] = 0.0f;
-                    A.out_status[i] = ST_PANIC_INV_SCALE;
+                    A.out_status[i] = bad;
                 } else {
                     d0 = seed_direction(p.lt, p.rt);
                     s.n = 0;
@@ -617,9 +687,9 @@ __global__ void __launch_bounds__(128, 4) k_time_of_impact_p(narrow_args A) {
                 done = true;
             } else {
                 i = ni;
-                if (!load_pair(A, i, A.l_t, A.r_t, p)) {
+                if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
                     store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, zero_contact());
-                    A.out_status[i] = ST_PANIC_INV_SCALE;
+                    A.out_status[i] = bad;
                 } else {
                     const xform lt1 = load_xform(A.l_t1, i);
                     const xform rt1 = load_xform(A.r_t1, i);
@@ -959,11 +1029,24 @@ __global__ void __launch_bounds__(32) k_retry_overflow(narrow_args A, const uint
         contact_out c = zero_contact();
         uint8_t st = ST_NONE;
         // every lane loads the pair and runs GJK::intersect redundantly (uniform: same data, same path)
-        if (!load_pair(A, i, A.l_t, A.r_t, p)) {
-            st = ST_PANIC_INV_SCALE;
+        if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
+            st = bad;
         } else {
             simplex<true> s;
-            if (gjk_intersect<true>(p, A.settings.max_iterations, s)) {
+            bool inside;
+            if (A.seed_simplex) {  // get_contact_manifold: the caller's simplex, not a new GJK run
+                const float4* sx = A.seed_simplex + i * 8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 v = sx[k], a = sx[4 + k];
+                    s.set(k, mk3(v.x, v.y, v.z), mk3(a.x, a.y, a.z));
+                }
+                s.n = 4;
+                inside = true;
+            } else {
+                inside = gjk_intersect(p, A.settings.max_iterations, s);
+            }
+            if (inside) {
                 st = epa_process_coop(CS, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
                 if (st == ST_SCRATCH_OVERFLOW) {
                     // past the shared-memory store: the serial version over global scratch
@@ -1083,6 +1166,16 @@ cudaError_t launch_gjk_hits(const narrow_args& A, bool full, const narrow_ws& W,
     }
     if (full) return launch_refill2(k_gjk_hits_p<true>, A, W, sm_count, st);
     return launch_refill2(k_gjk_hits_p<false>, A, W, sm_count, st);
+}
+cudaError_t launch_gjk_intersect(const narrow_args& A, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    k_gjk_intersect<<<grid_for(A.n, 128), 128, 0, st>>>(A);
+    return cudaGetLastError();
+}
+cudaError_t launch_manifold_seed(const narrow_args& A, const narrow_ws& W, cudaStream_t st) {
+    if (A.n == 0) return cudaSuccess;
+    k_manifold_seed<<<grid_for(A.n, 128), 128, 0, st>>>(A, W);
+    return cudaGetLastError();
 }
 size_t retry_scratch_bytes() { return (size_t)RETRY_BLOCKS * RETRY_BYTES_PER_BLOCK; }
 

@@ -47,26 +47,33 @@ CB2_DI f3 seed_direction(const xform& lt, const xform& rt) {
 }
 
 // GJK::intersect, gjk/mod.rs:101-146
-template <bool WITH_A>
-CB2_DI bool gjk_intersect(const pair_in& p, uint32_t max_iterations, simplex<WITH_A>& s) {
+template <bool WITH_A, bool WITH_B>
+CB2_DI bool gjk_intersect(const pair_in& p, uint32_t max_iterations, simplex<WITH_A, WITH_B>& s) {
     f3 d = seed_direction(p.lt, p.rt);
-    f3 v, a;
-    minkowski<WITH_A>(p, d, v, a);
+    f3 v, a, b = zero3();
+    auto point = [&](f3 dir) {  // SupportPoint::from_minkowski
+        a = support_point(p.T, p.ls, p.lt, dir);
+        b = support_point(p.T, p.rs, p.rt, -dir);
+        v = a - b;
+    };
+    point(d);
     if (dot(v, d) <= 0.0f) return false;
     s.n = 0;
-    s.push(v, a);
+    s.push(v, a, b);
     d = -d;
     for (uint32_t i = 0; i < max_iterations; ++i) {
-        minkowski<WITH_A>(p, d, v, a);
+        point(d);
         if (dot(v, d) <= 0.0f) return false;
-        s.push(v, a);
+        s.push(v, a, b);
         if (reduce_to_closest_feature(s, d)) return true;
     }
     return false;
 }
 
-CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const float4* rt,
-                      pair_in& p) {
+// Returns 0 or the pair's final status: ST_BAD_INDEX for a shape index outside the table (a Rust
+// slice index would panic; nothing is read through it), ST_PANIC_INV_SCALE for a zero scale.
+CB2_DI uint8_t load_pair(const narrow_args& A, uint64_t i, const float4* lt, const float4* rt,
+                         pair_in& p) {
     uint32_t li, ri;
     uint64_t lx, rx;
     if (A.pair_body) {  // body-indexed pairs (SweepAndPrune3 output feeding the narrow phase)
@@ -81,14 +88,20 @@ CB2_DI bool load_pair(const narrow_args& A, uint64_t i, const float4* lt, const 
         ri = __ldg(A.r_shape + i);
     }
     p.T = table_of(A.T);
+    if (li >= A.n_shapes || ri >= A.n_shapes) {
+        if (A.bad_index) *A.bad_index = 1u;
+        return ST_BAD_INDEX;
+    }
     p.ls = load_shape(p.T, li);
     p.rs = load_shape(p.T, ri);
     p.lt = load_xform(lt, lx);
     p.rt = load_xform(rt, rx);
     // inverse_transform_vector(..).unwrap() panics when ulps_eq(scale, 0); every entry point
     // reaches a support call before anything else can return (util.rs:18, sphere.rs:36)
-    return !((needs_inverse(p.ls.kind) && ulps_eq_zero(p.lt.scale)) ||
-             (needs_inverse(p.rs.kind) && ulps_eq_zero(p.rt.scale)));
+    return ((needs_inverse(p.ls.kind) && ulps_eq_zero(p.lt.scale)) ||
+            (needs_inverse(p.rs.kind) && ulps_eq_zero(p.rt.scale)))
+               ? ST_PANIC_INV_SCALE
+               : ST_NONE;
 }
 
 }  // namespace cb2

@@ -68,13 +68,20 @@ __device__ __forceinline__ uint32_t ord_f32(float x) {
 __global__ void __launch_bounds__(256) k_sap_keys(const float* __restrict__ aabbs, uint64_t n,
                                                  uint32_t axis, uint64_t* __restrict__ keys,
                                                  uint32_t* __restrict__ idx,
-                                                 uint32_t* __restrict__ nan_flag) {
+                                                 uint32_t* __restrict__ nan_flag, bool nan_sorts_last) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float mn = __ldg(aabbs + 6 * i + axis);
     const float mx = __ldg(aabbs + 6 * i + 3 + axis);
-    if (mn != mn || mx != mx) atomicOr(nan_flag, 1u);
-    keys[i] = ((uint64_t)ord_f32(mn) << 32) | (uint64_t)ord_f32(mx);
+    uint32_t hi = ord_f32(mn);
+    if (mn != mn || mx != mx) {
+        // SweepAndPrune: the reference's sort order is unspecified for NaN keys -> loud error.
+        // BruteForce never sorts (brute_force.rs:20-39): a NaN box just intersects nothing; here it
+        // sorts behind every other box, where the window walks and the strict test leave it alone.
+        if (nan_sorts_last) hi = mn != mn ? 0xFFFFFFFFu : hi;
+        else atomicOr(nan_flag, 1u);
+    }
+    keys[i] = ((uint64_t)hi << 32) | (uint64_t)ord_f32(mx);
     idx[i] = (uint32_t)i;
 }
 
@@ -292,6 +299,28 @@ __device__ __forceinline__ cell_range box_cells(const grid_params* __restrict__ 
     return r;
 }
 
+// How a box takes part in the grid.  The reference tests every candidate with Aabb3::intersects
+// literally (aabb3.rs:246-253), so
+//  * a box with a NaN extent on a grid axis never intersects anything (every comparison is false):
+//    it stays in the permutation but is neither gridded nor swept;
+//  * a box whose extents are inverted on a grid axis (min > max) can still pass the strict test, but
+//    its cell range is empty or reversed: it goes the way of the large boxes (literal test against
+//    every box);
+//  * everything else is gridded when it touches at most LARGE_CELLS cells.
+// (Inverted extents on the SWEEP axis need nothing special: the window walk and the strict test
+// are literal there; a NaN on the sweep axis is rejected with CB2_ERR_NAN — the reference's sort
+// order is unspecified for it.)
+enum : int { BOX_GRID = 0, BOX_LARGE = 1, BOX_DEAD = 2 };
+__device__ __forceinline__ int box_class(const grid_params* __restrict__ G, float2 u, float2 v, cell_range& r,
+                                         int& cnt) {
+    cnt = 0;
+    if (u.x != u.x || u.y != u.y || v.x != v.x || v.y != v.y) return BOX_DEAD;
+    if (u.y < u.x || v.y < v.x) return BOX_LARGE;
+    r = box_cells(G, u, v);
+    cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
+    return cnt > LARGE_CELLS ? BOX_LARGE : BOX_GRID;
+}
+
 // Entries (cell, position), compacted in POSITION order through an exclusive scan of the per-box
 // cell counts: the stable sort by cell then leaves every cell's entries ascending by position.
 // The entry array holds n * SLOT_CELLS + n/4 records (the cell size covers the 99.9 % extent
@@ -302,9 +331,10 @@ __global__ void __launch_bounds__(256) k_grid_count(const float2* __restrict__ U
                                                    uint32_t* __restrict__ counts) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const cell_range r = box_cells(G, __ldg(U + k), __ldg(V + k));
-    const int cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
-    counts[k] = cnt > LARGE_CELLS ? 0u : (uint32_t)cnt;
+    cell_range r;
+    int cnt;
+    const int cls = box_class(G, __ldg(U + k), __ldg(V + k), r, cnt);
+    counts[k] = cls == BOX_GRID ? (uint32_t)cnt : 0u;
 }
 
 __global__ void __launch_bounds__(256) k_grid_emit(const float2* __restrict__ U,
@@ -316,10 +346,12 @@ __global__ void __launch_bounds__(256) k_grid_emit(const float2* __restrict__ U,
                                                   uint32_t* __restrict__ large_list) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const cell_range r = box_cells(G, __ldg(U + k), __ldg(V + k));
-    const int cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
+    cell_range r;
+    int cnt;
+    const int cls = box_class(G, __ldg(U + k), __ldg(V + k), r, cnt);
+    if (cls == BOX_DEAD) return;
     const uint64_t o = offs[k];
-    if (cnt > LARGE_CELLS || o + (uint64_t)cnt > n_entries) {
+    if (cls == BOX_LARGE || o + (uint64_t)cnt > n_entries) {
         large_list[atomicAdd(&G->n_large, 1u)] = (uint32_t)k;
         return;
     }
@@ -484,9 +516,10 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
                 emit_pair(G, keys, cap, pos_bits, p, (uint32_t)q, remap);
             } else {
                 // (q, p) with q < p: if q is large too, q's own forward pass reports it
-                const cell_range r = box_cells(G, qu, qv);
-                const int cnt = (r.u1 - r.u0 + 1) * (r.v1 - r.v0 + 1);
-                if (cnt <= LARGE_CELLS && (uint64_t)__ldg(offs + q) + (uint64_t)cnt <= n_entries)
+                cell_range r;
+                int cnt;
+                if (box_class(G, qu, qv, r, cnt) == BOX_GRID &&
+                    (uint64_t)__ldg(offs + q) + (uint64_t)cnt <= n_entries)
                     emit_pair(G, keys, cap, pos_bits, (uint32_t)q, p, remap);
             }
         }
@@ -588,7 +621,7 @@ static int sap_find_pairs_legacy(sap_workspace* w, const cb2_aabb3* aabbs, uint6
     void* tmp = base + o_tmp;
 
     SAP_CK(cudaMemsetAsync(flag, 0, 4, st));
-    k_sap_keys<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, keys0, idx0, flag);
+    k_sap_keys<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, keys0, idx0, flag, false);
     size_t tb = sort_tmp;
     SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, idx0, perm_out, (int64_t)n, 0, 64,
                                            st));
@@ -758,7 +791,7 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         SAP_CK(cudaMemsetAsync(G, 0, sizeof(grid_params), st));
         SAP_CK(cudaMemsetAsync(G, 0xFF, 2 * sizeof(uint32_t), st));  // min_u, min_v = +max
         SAP_CK(cudaMemsetAsync(c0, 0xFF, 4 * ne, st));  // unused entry records = sentinel cells
-        k_sap_keys<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, keys0, idx0, flag);
+        k_sap_keys<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, keys0, idx0, flag, brute_force);
         size_t tb = sort1;
         SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, idx0, perm_out, (int64_t)n, 0,
                                                64, st));

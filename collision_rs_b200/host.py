@@ -260,6 +260,30 @@ class Context:
             ptr(r_t0), ptr(r_t1), n, int(iter_cap), ptr(out), ptr(status)))
         return out, status
 
+    def intersect(self, l_shape, r_shape, l_t, r_t, settings=None):
+        """GJK::intersect (gjk/mod.rs:101-146): (simplex (n, 4) SupportPoints, status)."""
+        from .abi import SUPPORT_POINT_DT
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        simplex = np.zeros((n, 4), SUPPORT_POINT_DT)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk3_intersect(
+            self.h, C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t), ptr(r_t), n,
+            ptr(simplex), ptr(status)))
+        return simplex, status
+
+    def get_contact_manifold(self, simplex, l_shape, r_shape, l_t, r_t, simplex_len=None,
+                             settings=None):
+        """GJK::get_contact_manifold (gjk/mod.rs:326-344): EPA3::process on caller-held simplices."""
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT_DT)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_gjk3_get_contact_manifold(
+            self.h, C.byref(settings), ptr(simplex), ptr(simplex_len), ptr(l_shape), ptr(r_shape),
+            ptr(l_t), ptr(r_t), n, ptr(out), ptr(status)))
+        return out, status
+
     def world_aabbs(self, shape, t):
         n = len(shape)
         out = np.zeros(n, AABB_DT)
@@ -568,6 +592,93 @@ def _shape_table(prims):
     return shapes, v, f
 
 
+class MultiContext:
+    """One cb2_multi: several GPUs of one box behind one handle (cb2_create_multi).  Host-buffer
+    batch calls are split into contiguous slices, one per device; results come back in place."""
+
+    def __init__(self, devices):
+        self.lib = abi.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.cb2_create_multi(devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise Cb2Error(rc, self.lib.cb2_last_error(None).decode())
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb2_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise Cb2Error(rc, self.lib.cb2_multi_last_error(self.h).decode())
+
+    @property
+    def device_count(self):
+        return int(self.lib.cb2_multi_device_count(self.h))
+
+    def upload_shapes(self, shapes, verts=None):
+        shapes = np.ascontiguousarray(shapes, SHAPE_DT)
+        v = None if verts is None else np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+        self._ck(self.lib.cb2_multi_shapes_upload(self.h, ptr(shapes), len(shapes), ptr(v),
+                                                  0 if v is None else len(v)))
+
+    def intersection(self, strategy, l_shape, r_shape, l_t, r_t, settings=None, out=None, status=None):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT_DT) if out is None else out
+        status = np.zeros(n, np.uint8) if status is None else status
+        self._ck(self.lib.cb2_multi_gjk3_intersection(
+            self.h, int(strategy), C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t), ptr(r_t), n,
+            ptr(out), ptr(status)))
+        return out, status
+
+    def distance(self, l_shape, r_shape, l_t, r_t, settings=None):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, np.float32)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_multi_gjk3_distance(
+            self.h, C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t), ptr(r_t), n, ptr(out),
+            ptr(status)))
+        return out, status
+
+    def time_of_impact(self, l_shape, r_shape, l_t0, l_t1, r_t0, r_t1, settings=None, iter_cap=1024):
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT_DT)
+        status = np.zeros(n, np.uint8)
+        self._ck(self.lib.cb2_multi_gjk3_time_of_impact(
+            self.h, C.byref(settings), ptr(l_shape), ptr(r_shape), ptr(l_t0), ptr(l_t1), ptr(r_t0),
+            ptr(r_t1), n, int(iter_cap), ptr(out), ptr(status)))
+        return out, status
+
+    def sap3(self, aabbs, axis=0, cap=None):
+        aabbs = np.ascontiguousarray(aabbs, AABB_DT)
+        n = len(aabbs)
+        perm = np.zeros(max(n, 1), np.uint32)
+        cap = int(cap) if cap is not None else max(16, 8 * n)
+        while True:
+            pairs = np.zeros((max(cap, 1), 2), np.uint32)
+            ax = C.c_uint32(axis)
+            npairs = C.c_uint64(0)
+            rc = self.lib.cb2_multi_sap3_find_collider_pairs(self.h, ptr(aabbs), n, C.byref(ax), ptr(perm),
+                                                             ptr(pairs), cap, C.byref(npairs))
+            if rc == abi.ERR_NOSPC:
+                cap = int(npairs.value)
+                continue
+            self._ck(rc)
+            return perm[:n], pairs[:npairs.value], ax.value
+
+
 _I0 = np.array([0], np.uint32)
 _I1 = np.array([1], np.uint32)
 
@@ -599,6 +710,31 @@ class GJK3:
         self._upload(left, right)
         out, st = self.ctx.intersection(strategy, _I0, _I1, left_transform.record(),
                                         right_transform.record(), self.settings)
+        if st[0] > 1:
+            raise ReferencePanic(int(st[0]))
+        return Contact.from_record(out[0]) if st[0] == 1 else None
+
+    def intersect(self, left, left_transform, right, right_transform):
+        """gjk/mod.rs:101-146 -> Option<Simplex>: the tetrahedron's four SupportPoints as a
+        (4,) record array (fields v, sup_a, sup_b), or None"""
+        self._upload(left, right)
+        sx, st = self.ctx.intersect(_I0, _I1, left_transform.record(), right_transform.record(),
+                                    self.settings)
+        if st[0] > 1:
+            raise ReferencePanic(int(st[0]))
+        return sx[0].copy() if st[0] == 1 else None
+
+    def get_contact_manifold(self, simplex, left, left_transform, right, right_transform):
+        """gjk/mod.rs:326-344 -> Option<Contact>: EPA3::process on a simplex from `intersect`
+        (a simplex of fewer than four points gives None, epa3d.rs:38-40)"""
+        from .abi import SUPPORT_POINT_DT
+        self._upload(left, right)
+        held = np.zeros((1, 4), SUPPORT_POINT_DT)
+        k = min(len(simplex), 4)
+        held[0, :k] = simplex[:k]
+        out, st = self.ctx.get_contact_manifold(held, _I0, _I1, left_transform.record(),
+                                                right_transform.record(),
+                                                np.array([len(simplex)], np.uint32), self.settings)
         if st[0] > 1:
             raise ReferencePanic(int(st[0]))
         return Contact.from_record(out[0]) if st[0] == 1 else None

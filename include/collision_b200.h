@@ -61,8 +61,13 @@ typedef enum cb2_status {
     CB2_SCRATCH_OVERFLOW = 7,   /* device EPA scratch exhausted (non-manifold horizon
                                    grew the polytope past 2V-4 faces): result NOT
                                    computed — loud, never a silent wrong answer  */
-    CB2_PANIC_CMP_NAN = 8       /* intersection_complex: max_by(partial_cmp(..).unwrap())
+    CB2_PANIC_CMP_NAN = 8,      /* intersection_complex: max_by(partial_cmp(..).unwrap())
                                    met a NaN penetration depth, gjk/mod.rs:455-459 */
+    /* 9 and 10 are the 2-D path's CB2_PANIC_EPA2_EDGE / CB2_PANIC_INV_ROT below */
+    CB2_BAD_INDEX = 11          /* a shape index outside the uploaded table: a Rust slice index
+                                   would panic.  The *_dev entry points report it per pair (nothing
+                                   is read through the index); the host-buffer entry points fail the
+                                   whole call with CB2_ERR_ARG                                   */
 } cb2_status;
 
 /* ---- CollisionStrategy (contact.rs:16-22); discriminants in declaration order */
@@ -140,12 +145,21 @@ typedef struct cb2_aabb2 {
     float max[2];
 } cb2_aabb2;
 
+/* SupportPoint<Point3<f32>> (algorithm/minkowski/mod.rs:16-23): a point of the Minkowski difference
+ * and the two shape points it came from (36 B). */
+typedef struct cb2_support_point {
+    float v[3];
+    float sup_a[3];
+    float sup_b[3];
+} cb2_support_point;
+
 typedef struct cb2_ctx cb2_ctx;
 
 /* ---- context ---------------------------------------------------------------- */
 uint32_t cb2_abi_version(void);
 void cb2_default_settings(cb2_settings* out);         /* GJK::new(), gjk/mod.rs:60-68 */
-int cb2_create(int device, cb2_ctx** out);            /* one ctx per GPU / host thread */
+int cb2_create(int device, cb2_ctx** out);            /* one ctx per GPU / host thread; its *_dev
+                                                          calls must be ordered on one stream */
 void cb2_destroy(cb2_ctx* ctx);
 const char* cb2_last_error(const cb2_ctx* ctx);       /* ctx may be NULL: create errors */
 int cb2_device_sm_count(const cb2_ctx* ctx);
@@ -202,11 +216,31 @@ int cb2_gjk3_time_of_impact(cb2_ctx* ctx, const cb2_settings* settings,
                             const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
                             uint32_t iter_cap, cb2_contact* out, uint8_t* status);
 
+/* GJK::intersect (gjk/mod.rs:101-146) on its own: status CB2_SOME = Some(simplex), and
+ * simplex_out[4i .. 4i+3] is the tetrahedron in the reference's Vec order (zeros otherwise).
+ * GJK::get_contact_manifold (gjk/mod.rs:326-344) = EPA3::process (epa/epa3d.rs:27-65) on such a
+ * simplex: simplex[4i .. 4i+3] with simplex_len[i] points actually held (NULL: four everywhere);
+ * fewer than four -> CB2_NONE (epa3d.rs:38-40).  cb2_gjk3_intersect followed by
+ * cb2_gjk3_get_contact_manifold is bit-identical to cb2_gjk3_intersection(FULL_RESOLUTION).      */
+int cb2_gjk3_intersect(cb2_ctx* ctx, const cb2_settings* settings,
+                       const uint32_t* l_shape, const uint32_t* r_shape,
+                       const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                       cb2_support_point* simplex_out /* 4 x n */, uint8_t* status);
+int cb2_gjk3_get_contact_manifold(cb2_ctx* ctx, const cb2_settings* settings,
+                                  const cb2_support_point* simplex /* 4 x n */,
+                                  const uint32_t* simplex_len /* n, may be NULL */,
+                                  const uint32_t* l_shape, const uint32_t* r_shape,
+                                  const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                                  cb2_contact* out, uint8_t* status);
+
 /* ---- narrow phase, DEVICE buffers (all pointers are device pointers; the work
  * is enqueued on `stream` (a cudaStream_t, may be NULL) and NOT synchronised).
- * Shape / body indices in device memory are TRUSTED (the host-buffer entry points range-check them;
- * here the caller is the broad phase or its own device code): an index past the table is undefined
- * behaviour, as it would be for any CUDA library taking device index arrays.
+ * Every SHAPE index is checked on the device against the uploaded table: a pair that names a shape
+ * outside it gets status CB2_BAD_INDEX and nothing is read through the index (the host-buffer entry
+ * points fail the whole call with CB2_ERR_ARG instead).  BODY indices (pair_body) are trusted: the
+ * entry points are not told how many bodies there are.
+ * All *_dev calls on one context share its workspaces: issue them on ONE stream at a time (or order
+ * the streams with events); two calls in flight on different streams of the same context race.
  * With pair_body != NULL the transforms are per BODY and pair i uses bodies
  * pair_body[2i], pair_body[2i+1] (shape = body_shape[..], xform = body_t[..]):
  * this is how SweepAndPrune3 output feeds the narrow phase without a host trip. */
@@ -214,6 +248,15 @@ int cb2_gjk3_intersection_dev(cb2_ctx* ctx, uint32_t strategy, const cb2_setting
                               const uint32_t* l_shape, const uint32_t* r_shape,
                               const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
                               cb2_contact* out, uint8_t* status, void* stream);
+int cb2_gjk3_intersect_dev(cb2_ctx* ctx, const cb2_settings* settings,
+                           const uint32_t* l_shape, const uint32_t* r_shape,
+                           const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                           cb2_support_point* simplex_out, uint8_t* status, void* stream);
+int cb2_gjk3_get_contact_manifold_dev(cb2_ctx* ctx, const cb2_settings* settings,
+                                      const cb2_support_point* simplex, const uint32_t* simplex_len,
+                                      const uint32_t* l_shape, const uint32_t* r_shape,
+                                      const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                                      cb2_contact* out, uint8_t* status, void* stream);
 int cb2_gjk3_distance_dev(cb2_ctx* ctx, const cb2_settings* settings,
                           const uint32_t* l_shape, const uint32_t* r_shape,
                           const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
@@ -314,13 +357,48 @@ int cb2_sap2_find_collider_pairs(cb2_ctx* ctx, const cb2_aabb2* aabbs, uint64_t 
 /* BruteForce::find_collider_pairs (algorithm/broad_phase/brute_force.rs:20-39): every (left, right),
  * left < right in the CALLER's indices, whose boxes overlap strictly; order = left ascending, then
  * right ascending.  Same machinery as the sweep (the O(n^2) double loop is not reproduced).
- * NaN extents -> CB2_ERR_NAN.                                                                   */
+ * A box with a NaN extent intersects nothing, as in the reference (no error: BruteForce never sorts). */
 int cb2_brute_force_find_collider_pairs(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint64_t n,
                                         uint32_t* pairs_out /* 2 x cap */, uint64_t cap,
                                         uint64_t* n_pairs);
 int cb2_brute_force_find_collider_pairs_dev(cb2_ctx* ctx, const cb2_aabb3* aabbs, uint64_t n,
                                             uint32_t* pairs_out, uint64_t cap, uint64_t* n_pairs,
                                             void* stream);
+
+/* ---- several GPUs of one box behind one handle ---------------------------------------------------
+ * "cb2_create(devices, n_dev) with the context owning the devices".  A cb2_multi holds
+ * one cb2_ctx per device.  Its host-buffer calls split the batch into contiguous slices, one per
+ * device, and run every device's own pipeline from its own host thread (pinned to the CPUs of the
+ * GPU's NUMA node); results land in the caller's arrays exactly where a single-device call would
+ * put them.  Pairs are independent, so no data is exchanged between devices; the shape table is
+ * uploaded to each of them.  cb2_multi_sap3_find_collider_pairs gives every device one shard of
+ * the pair list (cb2_sap3_find_collider_pairs_shard_dev) and concatenates the shards, which is the
+ * reference's Vec.  cb2_multi_ctx(m, i) is device i's context for the *_dev entry points.        */
+typedef struct cb2_multi cb2_multi;
+int cb2_create_multi(const int* devices, int n_devices, cb2_multi** out);
+void cb2_destroy_multi(cb2_multi* m);
+int cb2_multi_device_count(const cb2_multi* m);
+cb2_ctx* cb2_multi_ctx(cb2_multi* m, int i);
+const char* cb2_multi_last_error(const cb2_multi* m);
+int cb2_multi_shapes_upload(cb2_multi* m, const cb2_shape* shapes, uint32_t n_shapes,
+                            const float* verts_xyz, uint64_t n_verts);
+int cb2_multi_gjk3_intersection(cb2_multi* m, uint32_t strategy, const cb2_settings* settings,
+                                const uint32_t* l_shape, const uint32_t* r_shape,
+                                const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                                cb2_contact* out, uint8_t* status);
+int cb2_multi_gjk3_distance(cb2_multi* m, const cb2_settings* settings,
+                            const uint32_t* l_shape, const uint32_t* r_shape,
+                            const cb2_xform* l_t, const cb2_xform* r_t, uint64_t n,
+                            float* out, uint8_t* status);
+int cb2_multi_gjk3_time_of_impact(cb2_multi* m, const cb2_settings* settings,
+                                  const uint32_t* l_shape, const uint32_t* r_shape,
+                                  const cb2_xform* l_t0, const cb2_xform* l_t1,
+                                  const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
+                                  uint32_t iter_cap, cb2_contact* out, uint8_t* status);
+int cb2_multi_sap3_find_collider_pairs(cb2_multi* m, const cb2_aabb3* aabbs, uint64_t n,
+                                       uint32_t* axis_inout, uint32_t* perm_out,
+                                       uint32_t* pairs_out /* 2 x cap */, uint64_t cap,
+                                       uint64_t* n_pairs);
 
 /* ---- world bounds (the step before the broad phase) -----------------------------
  * out[i] = shape.compute_bound().transform_volume(&t[i])

@@ -17,6 +17,7 @@ XFORM_DT = np.dtype([("scale", "<f4"), ("q", "<f4", (4,)), ("d", "<f4", (3,))])
 CONTACT_DT = np.dtype([("strategy", "<u4"), ("normal", "<f4", (3,)), ("depth", "<f4"),
                        ("point", "<f4", (3,)), ("toi", "<f4")])
 AABB_DT = np.dtype([("min", "<f4", (3,)), ("max", "<f4", (3,))])
+SUPPORT_POINT_DT = np.dtype([("v", "<f4", (3,)), ("sup_a", "<f4", (3,)), ("sup_b", "<f4", (3,))])
 
 
 class Settings(C.Structure):
@@ -179,6 +180,29 @@ class Oracle:
             _p(r_shape), _p(l_t), _p(r_t), C.c_uint64(n), _p(out), _p(status), _p(stats),
             int(nthreads))
         return (out, status, stats) if want_stats else (out, status)
+
+    def intersect_batch(self, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None, nthreads=1):
+        """GJK::intersect per pair: ((n, 4) SupportPoints, status)"""
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        sx = np.zeros((n, 4), SUPPORT_POINT_DT)
+        status = np.zeros(n, np.uint8)
+        self.lib.orc_gjk3_intersect_batch(C.byref(settings), _p(shapes), _p(verts), _p(l_shape),
+                                          _p(r_shape), _p(l_t), _p(r_t), C.c_uint64(n), _p(sx),
+                                          _p(status), int(nthreads))
+        return sx, status
+
+    def manifold_batch(self, simplex, shapes, verts, l_shape, r_shape, l_t, r_t, simplex_len=None,
+                       settings=None, nthreads=1):
+        """GJK::get_contact_manifold per pair: (contacts, status)"""
+        settings = settings or Settings.default()
+        n = len(l_shape)
+        out = np.zeros(n, CONTACT_DT)
+        status = np.zeros(n, np.uint8)
+        self.lib.orc_gjk3_manifold_batch(C.byref(settings), _p(simplex), _p(simplex_len), _p(shapes),
+                                         _p(verts), _p(l_shape), _p(r_shape), _p(l_t), _p(r_t),
+                                         C.c_uint64(n), _p(out), _p(status), int(nthreads))
+        return out, status
 
     def distance(self, shapes, verts, l_shape, r_shape, l_t, r_t, settings=None, nthreads=1,
                  want_iters=False):

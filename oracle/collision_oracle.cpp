@@ -1194,6 +1194,65 @@ int orc_aabb3_intersects(const cb2_aabb3* a, const cb2_aabb3* b) {
 // ---- batch entry points: same array contract as include/collision_b200.h ----------------
 // stats (optional, may be NULL): per pair u32 x 4 = {gjk iterations, epa iterations, peak faces,
 // verts | peak horizon edges << 16}
+// GJK::intersect over a batch, whole SupportPoints out (gjk/mod.rs:101-146)
+void orc_gjk3_intersect_batch(const cb2_settings* st, const cb2_shape* shapes, const float* verts_xyz,
+                              const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t,
+                              const cb2_xform* r_t, uint64_t n, cb2_support_point* simplex_out,
+                              uint8_t* status, int nthreads) {
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            std::memset(simplex_out + 4 * i, 0, 4 * sizeof(cb2_support_point));
+            try {
+                Simplex s;
+                bool hit = gjk_intersect(load_shape(shapes[l_shape[i]], verts_xyz), load_xf(l_t[i]),
+                                         load_shape(shapes[r_shape[i]], verts_xyz), load_xf(r_t[i]),
+                                         st->max_iterations, s, nullptr);
+                status[i] = hit ? CB2_SOME : CB2_NONE;
+                if (hit)
+                    for (size_t k = 0; k < s.size() && k < 4; ++k) {
+                        cb2_support_point& o = simplex_out[4 * i + k];
+                        o.v[0] = s[k].v.x.f; o.v[1] = s[k].v.y.f; o.v[2] = s[k].v.z.f;
+                        o.sup_a[0] = s[k].sup_a.x.f; o.sup_a[1] = s[k].sup_a.y.f; o.sup_a[2] = s[k].sup_a.z.f;
+                        o.sup_b[0] = s[k].sup_b.x.f; o.sup_b[1] = s[k].sup_b.y.f; o.sup_b[2] = s[k].sup_b.z.f;
+                    }
+            } catch (Panic& p) {
+                status[i] = p.status;
+            }
+        }
+    });
+}
+// GJK::get_contact_manifold over a batch (gjk/mod.rs:326-344 -> EPA3::process, epa3d.rs:27-65)
+void orc_gjk3_manifold_batch(const cb2_settings* st, const cb2_support_point* simplex,
+                             const uint32_t* simplex_len, const cb2_shape* shapes, const float* verts_xyz,
+                             const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t,
+                             const cb2_xform* r_t, uint64_t n, cb2_contact* out, uint8_t* status,
+                             int nthreads) {
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            contact_zero(&out[i], CB2_FULL_RESOLUTION);
+            try {
+                const uint32_t len = simplex_len ? simplex_len[i] : 4u;
+                std::vector<Sup> v;
+                for (uint32_t k = 0; k < len && k < 4; ++k) {
+                    const cb2_support_point& q = simplex[4 * i + k];
+                    Sup p;
+                    p.v = V3(R(q.v[0]), R(q.v[1]), R(q.v[2]));
+                    p.sup_a = V3(R(q.sup_a[0]), R(q.sup_a[1]), R(q.sup_a[2]));
+                    p.sup_b = V3(R(q.sup_b[0]), R(q.sup_b[1]), R(q.sup_b[2]));
+                    v.push_back(p);
+                }
+                bool ok = epa_process(v, load_shape(shapes[l_shape[i]], verts_xyz), load_xf(l_t[i]),
+                                      load_shape(shapes[r_shape[i]], verts_xyz), load_xf(r_t[i]),
+                                      R(st->epa_tolerance), st->max_iterations, &out[i], nullptr);
+                if (!ok) contact_zero(&out[i], CB2_FULL_RESOLUTION);
+                status[i] = ok ? CB2_SOME : CB2_NONE;
+            } catch (Panic& p) {
+                contact_zero(&out[i], CB2_FULL_RESOLUTION);
+                status[i] = p.status;
+            }
+        }
+    });
+}
 void orc_gjk3_intersection_batch(uint32_t strategy, const cb2_settings* st, const cb2_shape* shapes,
                                  const float* verts_xyz, const uint32_t* l_shape,
                                  const uint32_t* r_shape, const cb2_xform* l_t,

@@ -1,8 +1,10 @@
 //! Raw `extern "C"` declarations of `include/collision_b200.h` (ABI version 1).
 //!
-//! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Rust toolchain.  The structs are
-//! `#[repr(C)]` mirrors of the header; `tests/test_abi_cpu.py` checks the same sizes/offsets
-//! against the numpy dtypes the Python host uses, so the three views of the ABI stay in step.
+//! UNCOMPILED SKETCH: the build image of this repository has no Rust toolchain, so neither this
+//! crate nor `collision-b200` has ever been through `cargo check`.  The structs are `#[repr(C)]`
+//! mirrors of the header; `tests/test_abi_cpu.py` checks that every function and struct of the
+//! header is declared here and that the field counts give the header's sizes, and the `const _`
+//! assertions below make `rustc` refuse to build if a layout drifts.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
@@ -30,6 +32,7 @@ pub const CB2_SCRATCH_OVERFLOW: u8 = 7;
 pub const CB2_PANIC_CMP_NAN: u8 = 8;
 pub const CB2_PANIC_EPA2_EDGE: u8 = 9;
 pub const CB2_PANIC_INV_ROT: u8 = 10;
+pub const CB2_BAD_INDEX: u8 = 11;
 // cb2_shape2_kind: Primitive2 variants in declaration order
 pub const CB2_PARTICLE2: u32 = 0;
 pub const CB2_LINE2: u32 = 1;
@@ -110,10 +113,37 @@ pub struct cb2_aabb2 {
     pub max: [f32; 2],
 }
 
+/// `SupportPoint<Point3<f32>>` (algorithm/minkowski/mod.rs:16-23), 36 B.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct cb2_support_point {
+    pub v: [f32; 3],
+    pub sup_a: [f32; 3],
+    pub sup_b: [f32; 3],
+}
+
 #[repr(C)]
 pub struct cb2_ctx {
     _private: [u8; 0],
 }
+
+/// Several GPUs of one box behind one handle (`cb2_create_multi`).
+#[repr(C)]
+pub struct cb2_multi {
+    _private: [u8; 0],
+}
+
+// layouts the C header promises (include/collision_b200.h); a drift fails the build
+const _: () = assert!(std::mem::size_of::<cb2_shape>() == 24);
+const _: () = assert!(std::mem::size_of::<cb2_xform>() == 32);
+const _: () = assert!(std::mem::size_of::<cb2_contact>() == 36);
+const _: () = assert!(std::mem::size_of::<cb2_settings>() == 16);
+const _: () = assert!(std::mem::size_of::<cb2_aabb3>() == 24);
+const _: () = assert!(std::mem::size_of::<cb2_aabb2>() == 16);
+const _: () = assert!(std::mem::size_of::<cb2_support_point>() == 36);
+const _: () = assert!(std::mem::size_of::<cb2_shape2>() == 32);
+const _: () = assert!(std::mem::size_of::<cb2_xform2>() == 32);
+const _: () = assert!(std::mem::size_of::<cb2_contact2>() == 28);
 
 /// One entry of the 2-D shape table (32 B); `kind` = Primitive2 variant in declaration order
 /// (0 Particle, 1 Line, 2 Circle, 3 Rectangle, 4 Square, 5 ConvexPolygon).
@@ -205,6 +235,52 @@ extern "C" {
                                             pair_body: *const u32, n: u64,
                                             out: *mut cb2_contact, status: *mut u8,
                                             stream: *mut c_void) -> c_int;
+
+    pub fn cb2_gjk3_intersect(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                              l_shape: *const u32, r_shape: *const u32,
+                              l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                              simplex_out: *mut cb2_support_point, status: *mut u8) -> c_int;
+    pub fn cb2_gjk3_get_contact_manifold(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                         simplex: *const cb2_support_point, simplex_len: *const u32,
+                                         l_shape: *const u32, r_shape: *const u32,
+                                         l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                         out: *mut cb2_contact, status: *mut u8) -> c_int;
+    pub fn cb2_gjk3_intersect_dev(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                  l_shape: *const u32, r_shape: *const u32,
+                                  l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                  simplex_out: *mut cb2_support_point, status: *mut u8,
+                                  stream: *mut c_void) -> c_int;
+    pub fn cb2_gjk3_get_contact_manifold_dev(ctx: *mut cb2_ctx, settings: *const cb2_settings,
+                                             simplex: *const cb2_support_point, simplex_len: *const u32,
+                                             l_shape: *const u32, r_shape: *const u32,
+                                             l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                             out: *mut cb2_contact, status: *mut u8,
+                                             stream: *mut c_void) -> c_int;
+
+    // ---- several GPUs of one box behind one handle ----
+    pub fn cb2_create_multi(devices: *const c_int, n_devices: c_int, out: *mut *mut cb2_multi) -> c_int;
+    pub fn cb2_destroy_multi(m: *mut cb2_multi);
+    pub fn cb2_multi_device_count(m: *const cb2_multi) -> c_int;
+    pub fn cb2_multi_ctx(m: *mut cb2_multi, i: c_int) -> *mut cb2_ctx;
+    pub fn cb2_multi_last_error(m: *const cb2_multi) -> *const c_char;
+    pub fn cb2_multi_shapes_upload(m: *mut cb2_multi, shapes: *const cb2_shape, n_shapes: u32,
+                                   verts_xyz: *const f32, n_verts: u64) -> c_int;
+    pub fn cb2_multi_gjk3_intersection(m: *mut cb2_multi, strategy: u32, settings: *const cb2_settings,
+                                       l_shape: *const u32, r_shape: *const u32,
+                                       l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                       out: *mut cb2_contact, status: *mut u8) -> c_int;
+    pub fn cb2_multi_gjk3_distance(m: *mut cb2_multi, settings: *const cb2_settings,
+                                   l_shape: *const u32, r_shape: *const u32,
+                                   l_t: *const cb2_xform, r_t: *const cb2_xform, n: u64,
+                                   out: *mut f32, status: *mut u8) -> c_int;
+    pub fn cb2_multi_gjk3_time_of_impact(m: *mut cb2_multi, settings: *const cb2_settings,
+                                         l_shape: *const u32, r_shape: *const u32,
+                                         l_t0: *const cb2_xform, l_t1: *const cb2_xform,
+                                         r_t0: *const cb2_xform, r_t1: *const cb2_xform, n: u64,
+                                         iter_cap: u32, out: *mut cb2_contact, status: *mut u8) -> c_int;
+    pub fn cb2_multi_sap3_find_collider_pairs(m: *mut cb2_multi, aabbs: *const cb2_aabb3, n: u64,
+                                              axis_inout: *mut u32, perm_out: *mut u32,
+                                              pairs_out: *mut u32, cap: u64, n_pairs: *mut u64) -> c_int;
 
     pub fn cb2_composites_upload(ctx: *mut cb2_ctx, part_off: *const u32, part_shape: *const u32,
                                  part_local: *const cb2_xform, n_comp: u32) -> c_int;

@@ -1,10 +1,14 @@
 //! Safe wrapper that keeps the crate's own API shapes on top of `collision-b200-sys`.
 //!
-//! NOT COMPILED IN THIS REPOSITORY'S CI (no Rust toolchain in the build image); it is the
-//! binding a maintainer of collision-rs would add, see INTEGRATION.md.  Mirrors:
+//! UNCOMPILED SKETCH (no Rust toolchain in the build image: never been through `cargo check`); it
+//! is the binding a maintainer of collision-rs would add, see INTEGRATION.md.  Mirrors:
 //!   * `GJK3::{intersection, distance, intersection_time_of_impact}` (gjk/mod.rs:163-391) as
 //!     batch methods plus batch-of-1 methods with the original signatures,
 //!   * `CollisionStrategy`, `Contact<Point3<f32>>` (contact.rs:16-82),
+//!   * `GJK3::{intersect, get_contact_manifold}` (gjk/mod.rs:101-146, 326-344) with
+//!     `Vec<SupportPoint>`-shaped simplices, the `*_complex` callers (gjk/mod.rs:412-588) over
+//!     composite tables, `ConvexPolyhedron::new_with_faces` shapes, `ComputeBound` world boxes,
+//!   * `Multi`: several GPUs behind one handle (`cb2_create_multi`),
 //!   * `SweepAndPrune3::find_collider_pairs` (sweep_prune.rs:76-136): permutes the caller's
 //!     slice in place, returns `Vec<(usize, usize)>` in the reference order, resets the sweep
 //!     axis to 0 exactly as the reference's no-op `Variance3` does.
@@ -36,6 +40,18 @@ pub enum Shape<'a> {
     /// `ConvexPolyhedron::new(vertices)` — VertexOnly mode (polyhedron.rs:100-122).  The crate
     /// keeps the vertices private, so the caller passes the same slice it built the shape from.
     ConvexPolyhedron { vertices: &'a [Point3<f32>] },
+    /// `ConvexPolyhedron::new_with_faces(vertices, faces)` — HalfEdge mode (polyhedron.rs:124-139):
+    /// support points come from the reference's hill climb over the half-edge rings.
+    ConvexPolyhedronWithFaces { vertices: &'a [Point3<f32>], faces: &'a [(usize, usize, usize)] },
+}
+
+/// `SupportPoint<Point3<f32>>` (minkowski/mod.rs:16-23); the crate keeps its own type private to
+/// the algorithm module, so the wrapper hands out this mirror.
+#[derive(Clone, Copy, Debug, PartialEq)]
+pub struct SupportPoint {
+    pub v: Vector3<f32>,
+    pub sup_a: Point3<f32>,
+    pub sup_b: Point3<f32>,
 }
 
 pub struct Context {
@@ -94,8 +110,19 @@ impl Context {
     pub fn upload_shapes(&mut self, shapes: &[Shape]) -> Result<Vec<ShapeId>, Error> {
         let mut recs = Vec::with_capacity(shapes.len());
         let mut verts: Vec<f32> = Vec::new();
+        let mut faces: Vec<u32> = Vec::new();
         for s in shapes {
             recs.push(match s {
+                Shape::ConvexPolyhedronWithFaces { vertices, faces: fs } => {
+                    let off = (verts.len() / 3) as u32;
+                    for v in vertices.iter() { verts.extend_from_slice(&[v.x, v.y, v.z]); }
+                    let f_off = (faces.len() / 3) as u32;
+                    for f in fs.iter() { faces.extend_from_slice(&[f.0 as u32, f.1 as u32, f.2 as u32]); }
+                    // the face range rides in p[0], p[1] as bit patterns (include/collision_b200.h)
+                    sys::cb2_shape { kind: sys::CB2_POLYHEDRON_HE,
+                                     p: [f32::from_bits(f_off), f32::from_bits(fs.len() as u32), 0.0],
+                                     vtx_off: off, vtx_cnt: vertices.len() as u32 }
+                }
                 Shape::Particle => sys::cb2_shape { kind: sys::CB2_PARTICLE, p: [0.0; 3], vtx_off: 0, vtx_cnt: 0 },
                 Shape::Quad { dim_x, dim_y } => sys::cb2_shape { kind: sys::CB2_QUAD, p: [*dim_x, *dim_y, 0.0], vtx_off: 0, vtx_cnt: 0 },
                 Shape::Cube { dim } => sys::cb2_shape { kind: sys::CB2_CUBE, p: [*dim, 0.0, 0.0], vtx_off: 0, vtx_cnt: 0 },
@@ -110,10 +137,45 @@ impl Context {
                 }
             });
         }
-        let rc = unsafe { sys::cb2_shapes_upload(self.raw, recs.as_ptr(), recs.len() as u32,
-                                                 verts.as_ptr(), (verts.len() / 3) as u64) };
+        let rc = if faces.is_empty() {
+            unsafe { sys::cb2_shapes_upload(self.raw, recs.as_ptr(), recs.len() as u32,
+                                            verts.as_ptr(), (verts.len() / 3) as u64) }
+        } else {
+            unsafe { sys::cb2_shapes_upload_faces(self.raw, recs.as_ptr(), recs.len() as u32, verts.as_ptr(),
+                                                  (verts.len() / 3) as u64, faces.as_ptr(), (faces.len() / 3) as u64) }
+        };
         self.check(rc)?;
         Ok((0..recs.len() as u32).map(ShapeId).collect())
+    }
+
+    /// `shape.compute_bound().transform_volume(&t)` per body (ComputeBound: sphere.rs:41-51,
+    /// cuboid.rs:82-92, polyhedron.rs:403-410; Aabb3::transform: aabb3.rs:90-100): the boxes
+    /// `SweepAndPrune3` sorts.
+    pub fn world_aabbs(&mut self, shape: &[ShapeId], transform: &[Transform3]) -> Result<Vec<collision::Aabb3<f32>>, Error> {
+        let n = shape.len();
+        assert!(transform.len() == n);
+        let s: Vec<u32> = shape.iter().map(|s| s.0).collect();
+        let t: Vec<sys::cb2_xform> = transform.iter().map(xf).collect();
+        let mut out = vec![sys::cb2_aabb3::default(); n];
+        let rc = unsafe { sys::cb2_world_aabbs(self.raw, s.as_ptr(), t.as_ptr(), n as u64, out.as_mut_ptr()) };
+        self.check(rc)?;
+        Ok(out.iter().map(|b| collision::Aabb3::new(Point3::new(b.min[0], b.min[1], b.min[2]),
+                                                    Point3::new(b.max[0], b.max[1], b.max[2]))).collect())
+    }
+
+    /// Composite shapes `&[(Primitive3, Transform3)]` (gjk/mod.rs:412-588): composite c owns the
+    /// parts `parts[c]`, each an uploaded shape with its local transform.  Returns composite ids.
+    pub fn upload_composites(&mut self, parts: &[&[(ShapeId, Transform3)]]) -> Result<Vec<ShapeId>, Error> {
+        let mut off = vec![0u32];
+        let mut shape = Vec::new();
+        let mut local = Vec::new();
+        for c in parts {
+            for (s, t) in c.iter() { shape.push(s.0); local.push(xf(t)); }
+            off.push(shape.len() as u32);
+        }
+        let rc = unsafe { sys::cb2_composites_upload(self.raw, off.as_ptr(), shape.as_ptr(), local.as_ptr(), parts.len() as u32) };
+        self.check(rc)?;
+        Ok((0..parts.len() as u32).map(ShapeId).collect())
     }
 }
 
@@ -192,6 +254,147 @@ impl<'c> GJK3<'c> {
         }).collect())
     }
 
+    /// The original single-pair `GJK3::distance` signature, as a batch of one.
+    pub fn distance(&mut self, left: ShapeId, left_transform: &Transform3, right: ShapeId,
+                    right_transform: &Transform3) -> Option<f32> {
+        self.distance_batch(&[left], std::slice::from_ref(left_transform), &[right],
+                            std::slice::from_ref(right_transform)).expect("device error").pop().unwrap()
+    }
+
+    /// The original single-pair `GJK3::intersection_time_of_impact` signature, as a batch of one.
+    /// The reference's loop has no iteration cap (gjk/mod.rs:204); a pair on which it would never
+    /// return panics here after 1024 rounds instead of hanging.
+    pub fn intersection_time_of_impact(&mut self, left: ShapeId, left_transform: std::ops::Range<&Transform3>,
+                                       right: ShapeId, right_transform: std::ops::Range<&Transform3>)
+                                       -> Option<Contact<Point3<f32>>> {
+        let l = left_transform.start.clone()..left_transform.end.clone();
+        let r = right_transform.start.clone()..right_transform.end.clone();
+        match self.intersection_time_of_impact_batch(&[left], std::slice::from_ref(&l), &[right],
+                                                     std::slice::from_ref(&r), 1024).expect("device error").pop().unwrap() {
+            Ok(c) => c,
+            Err(_) => panic!("intersection_time_of_impact did not converge (the reference loops forever)"),
+        }
+    }
+
+    /// Batched `GJK3::intersect` (gjk/mod.rs:101-146): `Some(simplex)` is the tetrahedron that
+    /// encloses the origin, in the reference's Vec order.
+    pub fn intersect_batch(&mut self, left: &[ShapeId], left_transform: &[Transform3], right: &[ShapeId],
+                           right_transform: &[Transform3]) -> Result<Vec<Option<Vec<SupportPoint>>>, Error> {
+        let n = left.len();
+        assert!(right.len() == n && left_transform.len() == n && right_transform.len() == n);
+        let l: Vec<u32> = left.iter().map(|s| s.0).collect();
+        let r: Vec<u32> = right.iter().map(|s| s.0).collect();
+        let lt: Vec<sys::cb2_xform> = left_transform.iter().map(xf).collect();
+        let rt: Vec<sys::cb2_xform> = right_transform.iter().map(xf).collect();
+        let mut sx = vec![sys::cb2_support_point::default(); 4 * n];
+        let mut status = vec![0u8; n];
+        let rc = unsafe { sys::cb2_gjk3_intersect(self.ctx.raw, &self.settings, l.as_ptr(), r.as_ptr(), lt.as_ptr(),
+                                                  rt.as_ptr(), n as u64, sx.as_mut_ptr(), status.as_mut_ptr()) };
+        self.ctx.check(rc)?;
+        Ok(status.iter().enumerate().map(|(i, s)| match *s {
+            sys::CB2_NONE => None,
+            sys::CB2_SOME => Some(sx[4 * i..4 * i + 4].iter().map(|p| SupportPoint {
+                v: Vector3::new(p.v[0], p.v[1], p.v[2]),
+                sup_a: Point3::new(p.sup_a[0], p.sup_a[1], p.sup_a[2]),
+                sup_b: Point3::new(p.sup_b[0], p.sup_b[1], p.sup_b[2]) }).collect()),
+            other => reraise(other),
+        }).collect())
+    }
+
+    /// `GJK3::intersect` with the original single-pair signature.
+    pub fn intersect(&mut self, left: ShapeId, left_transform: &Transform3, right: ShapeId,
+                     right_transform: &Transform3) -> Option<Vec<SupportPoint>> {
+        self.intersect_batch(&[left], std::slice::from_ref(left_transform), &[right],
+                             std::slice::from_ref(right_transform)).expect("device error").pop().unwrap()
+    }
+
+    /// `GJK3::get_contact_manifold` (gjk/mod.rs:326-344): EPA3::process on a simplex from
+    /// [`GJK3::intersect`]; fewer than four points give `None` (epa3d.rs:38-40).
+    pub fn get_contact_manifold(&mut self, simplex: &mut Vec<SupportPoint>, left: ShapeId, left_transform: &Transform3,
+                                right: ShapeId, right_transform: &Transform3) -> Option<Contact<Point3<f32>>> {
+        let mut sx = [sys::cb2_support_point::default(); 4];
+        for (o, p) in sx.iter_mut().zip(simplex.iter()) {
+            *o = sys::cb2_support_point { v: [p.v.x, p.v.y, p.v.z], sup_a: [p.sup_a.x, p.sup_a.y, p.sup_a.z],
+                                          sup_b: [p.sup_b.x, p.sup_b.y, p.sup_b.z] };
+        }
+        let len = simplex.len() as u32;
+        let (lt, rt) = (xf(left_transform), xf(right_transform));
+        let mut out = sys::cb2_contact::default();
+        let mut status = 0u8;
+        let rc = unsafe { sys::cb2_gjk3_get_contact_manifold(self.ctx.raw, &self.settings, sx.as_ptr(), &len, &left.0,
+                                                             &right.0, &lt, &rt, 1, &mut out, &mut status) };
+        self.ctx.check(rc).expect("device error");
+        match status { sys::CB2_NONE => None, sys::CB2_SOME => Some(contact(&out)), other => reraise(other) }
+    }
+
+    /// Batched `GJK3::intersection_complex` (gjk/mod.rs:412-470) over composites uploaded with
+    /// [`Context::upload_composites`].
+    pub fn intersection_complex_batch(&mut self, strategy: &CollisionStrategy, left: &[ShapeId], left_transform: &[Transform3],
+                                      right: &[ShapeId], right_transform: &[Transform3])
+                                      -> Result<Vec<Option<Contact<Point3<f32>>>>, Error> {
+        let n = left.len();
+        let l: Vec<u32> = left.iter().map(|s| s.0).collect();
+        let r: Vec<u32> = right.iter().map(|s| s.0).collect();
+        let lt: Vec<sys::cb2_xform> = left_transform.iter().map(xf).collect();
+        let rt: Vec<sys::cb2_xform> = right_transform.iter().map(xf).collect();
+        let mut out = vec![sys::cb2_contact::default(); n];
+        let mut status = vec![0u8; n];
+        let strat = match strategy { CollisionStrategy::FullResolution => sys::CB2_FULL_RESOLUTION, CollisionStrategy::CollisionOnly => sys::CB2_COLLISION_ONLY };
+        let rc = unsafe { sys::cb2_gjk3_intersection_complex(self.ctx.raw, strat, &self.settings, l.as_ptr(), r.as_ptr(),
+                                                             lt.as_ptr(), rt.as_ptr(), n as u64, out.as_mut_ptr(), status.as_mut_ptr()) };
+        self.ctx.check(rc)?;
+        Ok(out.iter().zip(status.iter()).map(|(c, s)| match *s {
+            sys::CB2_NONE => None,
+            sys::CB2_SOME => Some(contact(c)),
+            sys::CB2_PANIC_CMP_NAN => panic!("called `Option::unwrap()` on a `None` value (gjk/mod.rs:455-459)"),
+            other => reraise(other),
+        }).collect())
+    }
+
+    /// Batched `GJK3::distance_complex` (gjk/mod.rs:518-553).
+    pub fn distance_complex_batch(&mut self, left: &[ShapeId], left_transform: &[Transform3], right: &[ShapeId],
+                                  right_transform: &[Transform3]) -> Result<Vec<Option<f32>>, Error> {
+        let n = left.len();
+        let l: Vec<u32> = left.iter().map(|s| s.0).collect();
+        let r: Vec<u32> = right.iter().map(|s| s.0).collect();
+        let lt: Vec<sys::cb2_xform> = left_transform.iter().map(xf).collect();
+        let rt: Vec<sys::cb2_xform> = right_transform.iter().map(xf).collect();
+        let mut out = vec![0f32; n];
+        let mut status = vec![0u8; n];
+        let rc = unsafe { sys::cb2_gjk3_distance_complex(self.ctx.raw, &self.settings, l.as_ptr(), r.as_ptr(), lt.as_ptr(),
+                                                         rt.as_ptr(), n as u64, out.as_mut_ptr(), status.as_mut_ptr()) };
+        self.ctx.check(rc)?;
+        Ok(out.iter().zip(status.iter()).map(|(d, s)| match *s {
+            sys::CB2_NONE => None, sys::CB2_SOME => Some(*d), other => reraise(other) }).collect())
+    }
+
+    /// Batched `GJK3::intersection_complex_time_of_impact` (gjk/mod.rs:472-516).
+    pub fn intersection_complex_time_of_impact_batch(&mut self, strategy: &CollisionStrategy, left: &[ShapeId],
+                                                     left_transform: &[std::ops::Range<Transform3>], right: &[ShapeId],
+                                                     right_transform: &[std::ops::Range<Transform3>], iter_cap: u32)
+                                                     -> Result<Vec<Result<Option<Contact<Point3<f32>>>, usize>>, Error> {
+        let n = left.len();
+        let l: Vec<u32> = left.iter().map(|s| s.0).collect();
+        let r: Vec<u32> = right.iter().map(|s| s.0).collect();
+        let l0: Vec<sys::cb2_xform> = left_transform.iter().map(|t| xf(&t.start)).collect();
+        let l1: Vec<sys::cb2_xform> = left_transform.iter().map(|t| xf(&t.end)).collect();
+        let r0: Vec<sys::cb2_xform> = right_transform.iter().map(|t| xf(&t.start)).collect();
+        let r1: Vec<sys::cb2_xform> = right_transform.iter().map(|t| xf(&t.end)).collect();
+        let mut out = vec![sys::cb2_contact::default(); n];
+        let mut status = vec![0u8; n];
+        let strat = match strategy { CollisionStrategy::FullResolution => sys::CB2_FULL_RESOLUTION, CollisionStrategy::CollisionOnly => sys::CB2_COLLISION_ONLY };
+        let rc = unsafe { sys::cb2_gjk3_time_of_impact_complex(self.ctx.raw, strat, &self.settings, l.as_ptr(), r.as_ptr(),
+                                                               l0.as_ptr(), l1.as_ptr(), r0.as_ptr(), r1.as_ptr(), n as u64,
+                                                               iter_cap, out.as_mut_ptr(), status.as_mut_ptr()) };
+        self.ctx.check(rc)?;
+        Ok(out.iter().zip(status.iter()).enumerate().map(|(i, (c, s))| match *s {
+            sys::CB2_NONE => Ok(None),
+            sys::CB2_SOME => Ok(Some(contact(c))),
+            sys::CB2_NONCONVERGED => Err(i),
+            other => reraise(other),
+        }).collect())
+    }
+
     /// Batched `GJK3::intersection_time_of_impact` (gjk/mod.rs:163-256); `Err(index)` inside the
     /// vector marks a pair whose loop did not converge within `iter_cap` (the reference hangs).
     pub fn intersection_time_of_impact_batch(&mut self, left: &[ShapeId], left_transform: &[std::ops::Range<Transform3>],
@@ -228,9 +431,17 @@ impl SweepAndPrune3 {
     pub fn with_sweep_axis(sweep_axis: usize) -> Self { SweepAndPrune3 { sweep_axis } }
     pub fn get_sweep_axis(&self) -> usize { self.sweep_axis }
 
-    /// `find_collider_pairs` (sweep_prune.rs:76-136).  `bound` extracts `HasBound::bound()`.
-    pub fn find_collider_pairs<A, F>(&mut self, ctx: &mut Context, shapes: &mut [A], bound: F)
-                                     -> Result<Vec<(usize, usize)>, Error>
+    /// `find_collider_pairs` with the reference's own bound (sweep_prune.rs:76-81:
+    /// `A: HasBound, A::Bound = Aabb3<f32>`); the extra parameter is the device context.  A NaN
+    /// extent on the sweep axis is an `Err` (the reference's sort order is unspecified for it).
+    pub fn find_collider_pairs<A>(&mut self, ctx: &mut Context, shapes: &mut [A]) -> Result<Vec<(usize, usize)>, Error>
+    where A: collision::HasBound<Bound = collision::Aabb3<f32>> {
+        self.find_collider_pairs_by(ctx, shapes, |s| s.bound().clone())
+    }
+
+    /// The same with a closure in place of `HasBound::bound()`.
+    pub fn find_collider_pairs_by<A, F>(&mut self, ctx: &mut Context, shapes: &mut [A], bound: F)
+                                        -> Result<Vec<(usize, usize)>, Error>
     where F: Fn(&A) -> collision::Aabb3<f32> {
         let n = shapes.len();
         if n <= 1 { return Ok(Vec::new()); }   // sweep_prune.rs:83-85: nothing sorted, axis unchanged
@@ -253,6 +464,61 @@ impl SweepAndPrune3 {
         self.sweep_axis = axis as usize;       // always 0 for n >= 2 (sweep_prune.rs:254-277)
         Ok((0..count as usize).map(|k| (pairs[2 * k] as usize, pairs[2 * k + 1] as usize)).collect())
     }
+}
+
+/// Several GPUs of one box behind one handle (`cb2_create_multi`): host-buffer batches are split
+/// into contiguous slices, one per device, and come back in place.
+pub struct Multi {
+    raw: *mut sys::cb2_multi,
+}
+unsafe impl Send for Multi {}
+
+impl Multi {
+    pub fn new(devices: &[i32]) -> Result<Self, Error> {
+        let mut raw = std::ptr::null_mut();
+        let rc = unsafe { sys::cb2_create_multi(devices.as_ptr(), devices.len() as i32, &mut raw) };
+        if rc != 0 {
+            let msg = unsafe { CStr::from_ptr(sys::cb2_last_error(std::ptr::null())) };
+            return Err(Error(rc, msg.to_string_lossy().into_owned()));
+        }
+        Ok(Multi { raw })
+    }
+    fn check(&self, rc: i32) -> Result<(), Error> {
+        if rc == 0 { return Ok(()); }
+        let msg = unsafe { CStr::from_ptr(sys::cb2_multi_last_error(self.raw)) };
+        Err(Error(rc, msg.to_string_lossy().into_owned()))
+    }
+    pub fn device_count(&self) -> usize { unsafe { sys::cb2_multi_device_count(self.raw) as usize } }
+
+    /// Raw shape records (as [`Context::upload_shapes`] builds them) to every device.
+    pub fn upload_shape_records(&mut self, shapes: &[sys::cb2_shape], verts_xyz: &[f32]) -> Result<(), Error> {
+        let rc = unsafe { sys::cb2_multi_shapes_upload(self.raw, shapes.as_ptr(), shapes.len() as u32,
+                                                       verts_xyz.as_ptr(), (verts_xyz.len() / 3) as u64) };
+        self.check(rc)
+    }
+
+    /// Batched `GJK3::intersection` over all devices.
+    pub fn intersection_batch(&mut self, settings: &sys::cb2_settings, strategy: &CollisionStrategy, left: &[ShapeId],
+                              left_transform: &[Transform3], right: &[ShapeId], right_transform: &[Transform3])
+                              -> Result<Vec<Option<Contact<Point3<f32>>>>, Error> {
+        let n = left.len();
+        let l: Vec<u32> = left.iter().map(|s| s.0).collect();
+        let r: Vec<u32> = right.iter().map(|s| s.0).collect();
+        let lt: Vec<sys::cb2_xform> = left_transform.iter().map(xf).collect();
+        let rt: Vec<sys::cb2_xform> = right_transform.iter().map(xf).collect();
+        let mut out = vec![sys::cb2_contact::default(); n];
+        let mut status = vec![0u8; n];
+        let strat = match strategy { CollisionStrategy::FullResolution => sys::CB2_FULL_RESOLUTION, CollisionStrategy::CollisionOnly => sys::CB2_COLLISION_ONLY };
+        let rc = unsafe { sys::cb2_multi_gjk3_intersection(self.raw, strat, settings, l.as_ptr(), r.as_ptr(), lt.as_ptr(),
+                                                           rt.as_ptr(), n as u64, out.as_mut_ptr(), status.as_mut_ptr()) };
+        self.check(rc)?;
+        Ok(out.iter().zip(status.iter()).map(|(c, s)| match *s {
+            sys::CB2_NONE => None, sys::CB2_SOME => Some(contact(c)), other => reraise(other) }).collect())
+    }
+}
+
+impl Drop for Multi {
+    fn drop(&mut self) { unsafe { sys::cb2_destroy_multi(self.raw) } }
 }
 
 /// shapes[k] <- old shapes[perm[k]] with swaps only (`A` need not be `Clone`).

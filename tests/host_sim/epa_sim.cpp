@@ -130,6 +130,7 @@ int sim_gjk3_intersection_full(const cb2_shape* shapes, uint32_t n_shapes, const
     A.l_t = reinterpret_cast<const float4*>(l_t);
     A.r_t = reinterpret_cast<const float4*>(r_t);
     A.n = n;
+    A.n_shapes = n_shapes;
     A.settings = *settings;
     A.out_contact = out;
     A.out_status = status;
@@ -150,12 +151,12 @@ int sim_gjk3_intersection_full(const cb2_shape* shapes, uint32_t n_shapes, const
         pair_in p;
         uint8_t st = ST_NONE;
         bool hit = false;
-        if (!load_pair(A, i, A.l_t, A.r_t, p)) {
-            st = ST_PANIC_INV_SCALE;
+        if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
+            st = bad;
         } else {
             cb2::simplex<true> s;
             s.n = 0;
-            const bool inside = gjk_intersect<true>(p, A.settings.max_iterations, s);
+            const bool inside = gjk_intersect(p, A.settings.max_iterations, s);
             if (inside) {
                 hit = true;
                 for (int k = 0; k < 4; ++k) {

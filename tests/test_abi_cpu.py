@@ -68,7 +68,8 @@ def test_rust_sys_crate_declares_every_entry_point_and_pod():
         assert re.search(r"pub struct %s\b" % st, rs), st
     # struct sizes: count the 4-byte fields of each #[repr(C)] mirror
     sizes = {"cb2_shape": 24, "cb2_xform": 32, "cb2_contact": 36, "cb2_settings": 16, "cb2_aabb3": 24,
-             "cb2_aabb2": 16, "cb2_shape2": 32, "cb2_xform2": 32, "cb2_contact2": 28}
+             "cb2_aabb2": 16, "cb2_shape2": 32, "cb2_xform2": 32, "cb2_contact2": 28,
+             "cb2_support_point": 36}
     for name, size in sizes.items():
         body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rs, re.S).group(1)
         n = 0

@@ -377,6 +377,49 @@ def test_sap_nan_is_rejected_loudly(ctx):
     assert e.value.code == -6
 
 
+def _odd_boxes(seed=21, n=6_000):
+    """cfg-4 boxes with NaN extents on the two grid axes and inverted (min > max) extents on every
+    axis sprinkled in: the reference tests them literally (a NaN box pairs with nothing, an inverted
+    box can still pass the strict test), sweep_prune.rs:100-118, aabb3.rs:246-253."""
+    rng = np.random.default_rng(seed)
+    a = W.cfg4_aabbs(n, seed=seed, extent=200.0 * (n / 1e6) ** (1 / 3))["aabbs"]
+    k = rng.permutation(n)
+    a["min"][k[0:40], 1] = np.nan
+    a["max"][k[40:80], 2] = np.nan
+    a["max"][k[80:100], 1] = np.nan
+    a["min"][k[100:120], 2] = -np.nan
+    for lo, hi, ax in ((120, 170, 1), (170, 220, 2), (220, 270, 0)):  # inverted extents
+        i = k[lo:hi]
+        mn, mx = a["min"][i, ax].copy(), a["max"][i, ax].copy()
+        a["min"][i, ax], a["max"][i, ax] = mx, mn
+    i = k[270:290]  # inverted AND wide: still passes the strict test against many boxes
+    a["min"][i, 1], a["max"][i, 1] = 1e3, -1e3
+    a["min"][k[290:300], 2] = np.inf
+    a["max"][k[300:310], 1] = -np.inf
+    return a
+
+
+def test_sap_nan_and_inverted_extents_off_the_sweep_axis(ctx, oracle):
+    a = _odd_boxes()
+    _check_sap(ctx, oracle, a, 0)
+    pairs = oracle.sap3(a, axis=0)[1]
+    assert len(pairs) > 1000
+    # the inverted-and-wide boxes do produce pairs in the reference: the test is not vacuous
+    perm = oracle.sap3(a, axis=0)[0]
+    odd = np.flatnonzero(a["min"][perm, 1] > a["max"][perm, 1])
+    assert np.isin(pairs, odd).any()
+
+
+def test_brute_force_accepts_nan_boxes(ctx, oracle):
+    a = _odd_boxes(seed=4, n=3_000)
+    a["min"][7, 0] = np.nan   # BruteForce never sorts: NaN anywhere is just "intersects nothing"
+    a["max"][11, 0] = np.nan
+    a["min"][13, 0] = -np.nan
+    exp = oracle.brute_force_pairs(a)
+    got = ctx.brute_force(a)
+    assert len(exp) > 500 and np.array_equal(got, exp)
+
+
 # ---- support cells (csrc/cb2_cells.cuh) against the plain vertex scan ---------------------------
 def _ctx_with_env(**env):
     """A second context created under environment toggles the C ABI reads in cb2_create."""
@@ -781,3 +824,93 @@ def test_sweep_and_prune2(ctx, oracle):
         assert np.array_equal(perm, perm_e) and np.array_equal(pairs, pairs_e) and ax == ax_e
     with pytest.raises(Cb2Error):
         ctx.sap2(b2, axis=2)
+
+
+# ---- GJK::intersect / GJK::get_contact_manifold on their own (gjk/mod.rs:101-146, 326-344) -----------
+def test_intersect_returns_the_reference_simplex(ctx, oracle):
+    w = W.cfg3_polyhedron_pairs(30_000, n_shapes=256, seed=12)
+    ctx.upload_shapes(w["shapes"], w["verts"])
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    sx, st = ctx.intersect(*args)
+    sx_e, st_e = oracle.intersect_batch(w["shapes"], w["verts"], *args, nthreads=8)
+    assert np.array_equal(st, st_e) and 0.5 < (st == 1).mean() < 0.95
+    for f in ("v", "sup_a", "sup_b"):   # every point of every tetrahedron, in the reference's Vec order
+        assert bits_equal(sx[f], sx_e[f]).all(), f
+    # a mixed table: every kind the oracle has a support function for
+    w = W.cfg2_mixed_pairs(20_000, spread=1.0)
+    ctx.upload_shapes(w["shapes"], w["verts"])
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    sx, st = ctx.intersect(*args)
+    sx_e, st_e = oracle.intersect_batch(w["shapes"], w["verts"], *args, nthreads=8)
+    assert np.array_equal(st, st_e)
+    for f in ("v", "sup_a", "sup_b"):
+        assert bits_equal(sx[f], sx_e[f]).all(), f
+
+
+def test_get_contact_manifold_completes_intersect(ctx, oracle):
+    """intersect + get_contact_manifold == intersection(FullResolution), bit for bit; a simplex of
+    fewer than four points gives None (epa3d.rs:38-40)."""
+    for w in (W.cfg3_polyhedron_pairs(30_000, n_shapes=256, seed=13), W.cfg2_mixed_pairs(8_000, spread=1.0)):
+        ctx.upload_shapes(w["shapes"], w["verts"])
+        args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+        sx, st = ctx.intersect(*args)
+        held = np.where(st == 1, 4, 0).astype(np.uint32)
+        held[::11] = np.minimum(held[::11], 3)   # some callers hold a smaller simplex: None
+        out, st2 = ctx.get_contact_manifold(sx, *args, simplex_len=held)
+        exp, est = oracle.manifold_batch(sx, w["shapes"], w["verts"], *args, simplex_len=held, nthreads=8)
+        assert np.array_equal(st2, est)
+        for f in ("strategy", "normal", "depth", "point", "toi"):
+            assert bits_equal(out[f], exp[f]).all(), f
+        full, fst = ctx.intersection(0, *args)
+        keep = held == np.where(st == 1, 4, 0)
+        assert np.array_equal(st2[keep], fst[keep])
+        assert np.array_equal(out[keep].view(np.uint8), full[keep].view(np.uint8))
+
+
+def test_gjk3_intersect_and_manifold_wrappers(ctx):
+    # gjk/mod.rs:700-725 (test_gjk_3d_hit) through the reference-shaped single-pair methods
+    gjk = GJK3.new(ctx)
+    left, right = Cuboid(10.0, 10.0, 10.0), Cuboid(10.0, 10.0, 10.0)
+    lt, rt = D(15, 0, 0), D(7, 2, 0)
+    simplex = gjk.intersect(left, lt, right, rt)
+    assert simplex is not None and len(simplex) == 4
+    contact = gjk.get_contact_manifold(simplex, left, lt, right, rt)
+    whole = gjk.intersection(CollisionStrategy.FullResolution, left, lt, right, rt)
+    assert contact is not None and contact.penetration_depth == whole.penetration_depth
+    assert tuple(contact.normal) == tuple(whole.normal)
+    assert gjk.get_contact_manifold(simplex[:3], left, lt, right, rt) is None
+    assert gjk.intersect(left, lt, right, D(-15, 0, 0)) is None
+
+
+def test_shape_index_out_of_range(ctx, oracle):
+    """A Rust slice index would panic: host-buffer calls fail as a whole (CB2_ERR_ARG), device-buffer
+    calls mark the pair CB2_BAD_INDEX and read nothing through the index."""
+    import torch
+    w = W.cfg1_cuboid_pairs(4_096)
+    ctx.upload_shapes(w["shapes"], None)
+    l_shape = w["l_shape"].copy()
+    l_shape[[5, 777]] = len(w["shapes"]) + 3
+    r_shape = w["r_shape"].copy()
+    r_shape[2048] = 0xFFFFFFFF
+    for call in (lambda: ctx.intersection(0, l_shape, r_shape, w["l_t"], w["r_t"]),
+                 lambda: ctx.distance(l_shape, r_shape, w["l_t"], w["r_t"]),
+                 lambda: ctx.intersect(l_shape, r_shape, w["l_t"], w["r_t"])):
+        with pytest.raises(Cb2Error) as e:
+            call()
+        assert e.value.code == -3
+    got, gst = ctx.intersection(0, w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])  # the ctx recovers
+    exp, est = oracle.intersection(0, w["shapes"], None, w["l_shape"], w["r_shape"], w["l_t"], w["r_t"], nthreads=4)
+    assert np.array_equal(gst, est)
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(v.view(np.uint8).reshape(-1).copy()).to(dev)
+         for k, v in (("l", l_shape), ("r", r_shape), ("lt", w["l_t"]), ("rt", w["r_t"]))}
+    n = len(l_shape)
+    d_out = torch.zeros(n * 36, dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(n, dtype=torch.uint8, device=dev)
+    ctx.intersection_dev(0, d["l"].data_ptr(), d["r"].data_ptr(), d["lt"].data_ptr(), d["rt"].data_ptr(), n,
+                         d_out.data_ptr(), d_st.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st = d_st.cpu().numpy()
+    bad = np.zeros(n, bool)
+    bad[[5, 777, 2048]] = True
+    assert (st[bad] == 11).all() and np.array_equal(st[~bad], est[~bad])
