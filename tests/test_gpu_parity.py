@@ -10,7 +10,8 @@ import pytest
 from collision_rs_b200 import abi as host_abi
 from collision_rs_b200 import workloads as W
 from collision_rs_b200.host import (Cb2Error, CollisionStrategy, ConvexPolyhedron, Cuboid,
-                                    Decomposed, GJK3, ReferencePanic, Sphere, SweepAndPrune3)
+                                    Decomposed, GJK3, MultiContext, ReferencePanic, Sphere,
+                                    SweepAndPrune3)
 from helpers import transform_3d
 
 pytestmark = pytest.mark.gpu
@@ -914,3 +915,33 @@ def test_shape_index_out_of_range(ctx, oracle):
     bad = np.zeros(n, bool)
     bad[[5, 777, 2048]] = True
     assert (st[bad] == 11).all() and np.array_equal(st[~bad], est[~bad])
+
+
+def test_multi_context_shards_one_call_over_every_gpu(oracle):
+    """cb2_create_multi: one host-buffer call, every visible GPU takes a contiguous slice (with one
+    GPU the same code runs with a single slice)."""
+    import torch
+    devices = list(range(min(torch.cuda.device_count(), 8)))
+    m = MultiContext(devices)
+    assert m.device_count == len(devices)
+    w = W.cfg3_polyhedron_pairs(40_003, n_shapes=256, seed=21)   # not a multiple of the device count
+    m.upload_shapes(w["shapes"], w["verts"])
+    args = (w["l_shape"], w["r_shape"], w["l_t"], w["r_t"])
+    got, gst = m.intersection(0, *args)
+    exp, est = oracle.intersection(0, w["shapes"], w["verts"], *args, nthreads=8)
+    assert np.array_equal(gst, est)
+    for f in ("strategy", "normal", "depth", "point", "toi"):
+        assert bits_equal(got[f], exp[f]).all(), f
+    d, dst = m.distance(*args)
+    de, dste = oracle.distance(w["shapes"], w["verts"], *args, nthreads=8)
+    assert np.array_equal(dst, dste) and bits_equal(d, de).all()
+    b = W.cfg4_aabbs(20_000, extent=200.0 * (20_000 / 1e6) ** (1 / 3))["aabbs"]
+    perm, pairs, axis = m.sap3(b, axis=1)
+    perm_e, pairs_e, cnt, axis_e = oracle.sap3(b, axis=1)
+    assert np.array_equal(perm, perm_e) and np.array_equal(pairs, pairs_e) and axis == axis_e
+    bad = w["l_shape"].copy()
+    bad[-1] = 1 << 30   # lands in the last device's slice
+    with pytest.raises(Cb2Error) as e:
+        m.intersection(0, bad, w["r_shape"], w["l_t"], w["r_t"])
+    assert e.value.code == -3
+    m.close()
