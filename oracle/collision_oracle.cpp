@@ -389,7 +389,41 @@ static Sup from_minkowski(const Shape& l, const Xf& lt, const Shape& r, const Xf
     return s;
 }
 
-typedef std::vector<Sup> Simplex;  // SmallVec<[SupportPoint; 5]>, simplex/mod.rs:12
+// SmallVec<[SupportPoint; 5]> (simplex/mod.rs:12): five points inline on the stack, the heap only
+// beyond that — the crate's GJK loops never allocate, and neither may a baseline that is timed
+// against it (a std::vector here cost a malloc per pair).
+class Simplex {
+  public:
+    Simplex() : n_(0) {}
+    size_t size() const { return n_; }
+    Sup& operator[](size_t i) { return data()[i]; }
+    const Sup& operator[](size_t i) const { return data()[i]; }
+    Sup* begin() { return data(); }
+    Sup* end() { return data() + n_; }
+    const Sup* begin() const { return data(); }
+    const Sup* end() const { return data() + n_; }
+    void clear() { n_ = 0; }
+    void push_back(const Sup& p) {
+        if (spill_.empty() && n_ == 5) spill_.assign(inl_, inl_ + 5);  // SmallVec spills to the heap
+        if (!spill_.empty()) {
+            spill_.resize(n_ + 1);
+            spill_[n_++] = p;
+        } else {
+            inl_[n_++] = p;
+        }
+    }
+    void erase(Sup* at) {  // SmallVec::remove: shift the tail down
+        for (Sup* q = at; q + 1 < end(); ++q) *q = *(q + 1);
+        --n_;
+    }
+
+  private:
+    Sup* data() { return spill_.empty() ? inl_ : spill_.data(); }
+    const Sup* data() const { return spill_.empty() ? inl_ : spill_.data(); }
+    Sup inl_[5];
+    size_t n_;
+    std::vector<Sup> spill_;  // empty (no allocation) unless a sixth point is ever pushed
+};
 
 // ---- SimplexProcessor3, simplex3d.rs ----------------------------------------------
 static inline V3 cross_aba(V3 a, V3 b) { return cross(cross(a, b), a); }  // :172-177
@@ -1132,7 +1166,8 @@ static void faces_out(const std::vector<Face>& f, uint32_t* idx, float* nd, uint
 void orc_polytope(const float* verts, uint32_t n_init, const float* add_pts, uint32_t n_add,
                   uint32_t* face_idx, float* face_nd, uint32_t* n_faces, uint32_t* closest,
                   uint32_t* n_verts) {
-    std::vector<Sup> s = simplex_from(verts, n_init);
+    const Simplex s0 = simplex_from(verts, n_init);
+    std::vector<Sup> s(s0.begin(), s0.end());
     Polytope p;
     p.vertices = &s;
     p.faces = face_new(s);
@@ -1163,7 +1198,8 @@ uint8_t orc_epa3_process(const float* simplex_v, uint32_t n, const cb2_shape* l,
                          const cb2_xform* lt, const cb2_shape* r, const cb2_xform* rt,
                          const float* verts_xyz, const cb2_settings* st, cb2_contact* out) {
     try {
-        std::vector<Sup> s = simplex_from(simplex_v, n);
+        const Simplex s0 = simplex_from(simplex_v, n);
+        std::vector<Sup> s(s0.begin(), s0.end());
         bool ok = epa_process(s, load_shape(*l, verts_xyz), load_xf(*lt), load_shape(*r, verts_xyz),
                               load_xf(*rt), R(st->epa_tolerance), st->max_iterations, out, nullptr);
         return ok ? CB2_SOME : CB2_NONE;
