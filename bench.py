@@ -7,7 +7,10 @@ Workload at every N: BASELINE.json configs[2], "GJK3+EPA3 on 4M ConvexPolyhedron
 one GJK3::intersection(FullResolution) pass over one batch of 4M pairs per GPU (weak scaling:
 every rank owns its own 4M-pair shard; the shape table is broadcast once over NCCL; no
 data-path collective).  Other configs (cfg1 cuboids, cfg2 mixed, cfg4 SAP, cfg5 TOI) are
-reported in the `extra` object of the same JSON line (N=1 only).
+reported in the `extra` object of the same JSON line at N=1; at N>1 `extra.multi` holds what only
+exists on several GPUs: the device-resident NCCL all-gather of the contact records (`gather_ms`),
+the strong-scaling pass (the 4M pairs of ONE batch split over the ranks), cfg 5 (8M time-of-impact
+pairs per GPU: 64M over 8) and cfg 4 with the pair list sharded over the GPUs.
 
   python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
   python bench.py --impl reference ...                      (CPU oracle port, all host threads)
@@ -44,6 +47,12 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=4_000_000,
                     help="pairs of the workload the CPU oracle port is timed on")
     return ap.parse_args()
+
+
+def config_of(a):
+    """The same `config` object in both arms (the driver compares them): the workload, not the run."""
+    return {"workload": WORKLOAD, "pairs_per_gpu_per_step": a.pairs, "seed": 777,
+            "l2": "inputs+outputs 109 B/pair: 436 MB per 4M-pair step > 126 MB L2 (no flush needed)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -116,6 +125,108 @@ def algorithmic_flops_per_pair(w, sample=20_000):
     return out[0], out[1]
 
 
+def counted_flops(op, w, sample=20_000):
+    """f32 + - * / sqrt per pair the reference executes for `op` on a prefix of workload `w`
+    (oracle op-counter build)."""
+    from oracle.binding import Oracle
+    oc = Oracle(count_ops=True)
+    m = min(sample, len(w["l_shape"]))
+    oc.ops_reset()
+    if op == "distance":
+        oc.distance(w["shapes"], w.get("verts"), w["l_shape"][:m], w["r_shape"][:m], w["l_t"][:m], w["r_t"][:m])
+    elif op == "toi":
+        oc.time_of_impact(w["shapes"], w.get("verts"), w["l_shape"][:m], w["r_shape"][:m], w["l_t0"][:m],
+                          w["l_t1"][:m], w["r_t0"][:m], w["r_t1"][:m])
+    else:
+        oc.intersection(1 if op == "intersection1" else 0, w["shapes"], w.get("verts"), w["l_shape"][:m],
+                        w["r_shape"][:m], w["l_t"][:m], w["r_t"][:m], nthreads=1)
+    return oc.ops_reset() / m
+
+
+def kernel_rooflines(n, stage_ms, flops_pair, flops_gjk_pair, extra, fp32_peak, hbm_peak):
+    """One roofline entry per kernel the north star names.  `ms` is measured live in this run (CUDA
+    events on the launching stream); `achieved` = ALGORITHMIC flops (what the reference executes,
+    oracle op counter) / ms; `executed` = the FP32 instructions the kernel really issues, per unit
+    from the committed ncu counters (profiles/r2_kernels.json: smsp__sass_thread_inst_executed_op_
+    {fadd,fmul,ffma}_pred_on) scaled to this run's units and time.  Parity forbids FMA, so the
+    reachable FP32 ceiling is peak / 2 (frac_of_unfused_peak)."""
+    prof = {}
+    pj = os.path.join(ROOT, "profiles", "r2_kernels.json")
+    if os.path.exists(pj):
+        prof = json.load(open(pj))
+    pk, units = prof.get("kernels", {}), prof.get("units", {})
+
+    def executed(keys, sec, live_units, ms):
+        recs = [pk[k] for k in keys if k in pk]
+        if not recs or not units.get(sec) or not ms:
+            return None
+        per_unit = sum(r["fadd"] + r["fmul"] + 2 * r["ffma"] for r in recs) / units[sec]
+        tf = per_unit * live_units / (ms * 1e-3) / 1e12
+        inst = sum(r["thread_inst_executed"] for r in recs)
+        return {"fp32_flops_per_unit": per_unit, "tflops": tf, "frac": tf / fp32_peak if fp32_peak else None,
+                "frac_of_unfused_peak": 2 * tf / fp32_peak if fp32_peak else None,
+                "fp32_share_of_thread_instructions": sum(r["fadd"] + r["fmul"] + r["ffma"] for r in recs) / inst if inst else None,
+                "threads_per_instruction": [r["threads_per_inst"] for r in recs],
+                "ipc": [r["ipc"] for r in recs], "warps_active_pct": [r["warps_active_pct"] for r in recs],
+                "dram_bytes_per_unit": sum(r["dram_bytes"] for r in recs) / units[sec],
+                "source": "profiles/r2_kernels.json (ncu counters of tools/profile_pass.py)"}
+
+    def entry(kernel, ref, workload, units_live, ms, alg_flops_unit, keys, sec):
+        if not ms:
+            return None
+        ach = alg_flops_unit * units_live / (ms * 1e-3) / 1e12 if alg_flops_unit else None
+        return {"kernel": kernel, "replaces": ref, "workload": workload, "units": units_live, "ms": ms,
+                "bound": "fp32", "unit": "TFLOP/s", "algorithmic_flops_per_unit": alg_flops_unit,
+                "achieved": ach, "peak": fp32_peak, "frac": ach / fp32_peak if ach and fp32_peak else None,
+                "frac_of_unfused_peak": 2 * ach / fp32_peak if ach and fp32_peak else None,
+                "executed": executed(keys, sec, units_live, ms)}
+
+    out = [
+        entry("k_gjk_hits_p", "GJK::intersect, gjk/mod.rs:101-146", "cfg3", n, stage_ms[0], flops_gjk_pair,
+              ["cfg3:k_gjk_hits_p<1>"], "cfg3"),
+        entry("k_epa tier 0", "EPA3::process, epa3d.rs:27-175", "cfg3", n, stage_ms[1], None,
+              ["cfg3:k_epa<4,40,24,24,0,0>"], "cfg3"),
+        entry("k_epa (all tiers)", "EPA3::process, epa3d.rs:27-175", "cfg3", n, stage_ms[1] + stage_ms[2],
+              flops_pair - flops_gjk_pair,
+              ["cfg3:k_epa<4,40,24,24,0,0>", "cfg3:k_epa<8,72,40,32,40,24>", "cfg3:k_epa<8,208,104,96,72,40>"], "cfg3"),
+    ]
+    x = extra.get("cfg2_mixed_distance")
+    if x:
+        out.append(entry("k_distance_p", "GJK::distance, gjk/mod.rs:271-321", "cfg2", x["pairs"], x["ms"],
+                         x.get("algorithmic_flops_per_pair"), ["cfg2:k_distance_p"], "cfg2"))
+    x = extra.get("cfg2_mixed_collision_only")
+    if x:
+        out.append(entry("k_gjk_hits_p (CollisionOnly)", "GJK::intersect, gjk/mod.rs:101-146", "cfg2", x["pairs"],
+                         x["ms"], x.get("algorithmic_flops_per_pair"), ["cfg2:k_gjk_hits_p<0>"], "cfg2"))
+    x = extra.get("cfg5_time_of_impact")
+    if x:
+        out.append(entry("k_time_of_impact_p", "GJK::intersection_time_of_impact, gjk/mod.rs:163-256", "cfg5",
+                         x["pairs"], x["ms"], x.get("algorithmic_flops_per_pair"), ["cfg5:k_time_of_impact_p"], "cfg5"))
+    x = extra.get("cfg4_sap")
+    if x and pk:
+        # HBM-bound: algorithmic bytes of the whole call against the live call time, and k_grid_sweep's
+        # share of the call from the ncu launch list
+        sap = {k: r for k, r in pk.items() if k.startswith("cfg4:") and ("sap" in k or "grid" in k or "Radix" in k or "Scan" in k)}
+        tot = sum(r["ms"] * r["launches_in_pass"] / 2 for r in sap.values()) or None
+        sw = pk.get("cfg4:k_grid_sweep")
+        out.append({"kernel": "SweepAndPrune3 call (sorts + k_grid_sweep)", "replaces": "sweep_prune.rs:76-136",
+                    "workload": "cfg4", "units": x["aabbs"], "ms": x["ms"], "bound": "hbm", "unit": "GB/s",
+                    "algorithmic_bytes": x["algorithmic_bytes"],
+                    "achieved": x["algorithmic_bytes"] / (x["ms"] * 1e-3) / 1e9, "peak": hbm_peak,
+                    "frac": x["hbm_frac"],
+                    "executed": {"dram_bytes_per_call": sum(r["dram_bytes"] * r["launches_in_pass"] / 2 for r in sap.values()),
+                                 "k_grid_sweep_share_of_call": (sw["ms"] / tot) if sw and tot else None,
+                                 "k_grid_sweep_ipc": sw["ipc"] if sw else None,
+                                 "radix_sort_share_of_call": (sum(r["ms"] * r["launches_in_pass"] / 2 for k, r in sap.items() if "Radix" in k) / tot) if tot else None,
+                                 "source": "profiles/r2_kernels.json"}})
+    x = extra.get("gjk2_mixed_primitive2_full_resolution")
+    if x:
+        out.append(entry("k_gjk2_intersection + k_epa2", "GJK2::intersection, gjk/mod.rs:362-391 / epa2d.rs:21-157",
+                         "gjk2", x["pairs"], x["ms"], None,
+                         ["gjk2:k_gjk2_intersection", "gjk2:k_epa2<12,1>", "gjk2:k_epa2<104,0>"], "gjk2"))
+    return [e for e in out if e]
+
+
 def profiled_traffic(n):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
     `ncu --set full` capture (profiles/r1_traffic.json: bytes per pair), scaled to this launch."""
@@ -184,7 +295,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "pairs_per_step": m},
+        "data": "synthetic", "config": config_of(a),
+        "run": {"pairs_per_step": m},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -226,6 +338,12 @@ def main():
                          "(use --impl reference for the CPU oracle port)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # staging buffers and the threads that feed them live next to the GPU (eight ranks on one socket's
+    # memory controller cost 17 % end to end in round 1)
+    from collision_rs_b200.sharding import bind_to_gpu_numa
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local)
+    numa_cpus = f"{numa[0]}-{numa[-1]} ({len(numa)})" if numa else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = Context(local)
@@ -331,6 +449,11 @@ def main():
     hits = int((h_st == 1).sum())
     bad = int((h_st > 1).sum())
 
+    # ---- N > 1: what only exists on several GPUs (every rank takes part; rank 0 reports) -------------
+    multi = {}
+    if world > 1:
+        multi = multi_gpu_extras(a, ctx, torch, dist, dev, stream, rank, world, d_out, d_st, n,
+                                 ms_total / a.steps, shapes, verts)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -370,20 +493,23 @@ def main():
                 "frac": hbm_achieved / hbm_peak, "bytes_per_pair": bytes_pair,
                 "peak_source": hbm_src},
     }
+    os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
     cpu = cpu_baseline(w, a.cpu_sample)
 
     extra = {}
     if not a.no_extra and world == 1:
         extra = extras(ctx, torch, dev, stream)
+    if multi:
+        extra["multi"] = multi
+    roofline["kernels"] = kernel_rooflines(n, stage_ms, flops_pair, flops_gjk_pair, extra, fp32_peak, hbm_peak)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": n, "seed": 777,
-                   "hit_fraction": hits / n, "non_ok_status": bad,
-                   "ms_per_step_per_rank": per_rank_ms,
-                   "l2": "inputs+outputs 436 MB per step > 126 MB L2 (no flush needed)"},
+        "config": config_of(a),
+        "run": {"hit_fraction": hits / n, "non_ok_status": bad, "ms_per_step_per_rank": per_rank_ms,
+                "numa_cpus": numa_cpus},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -396,6 +522,113 @@ def main():
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_extras(a, ctx, torch, dist, dev, stream, rank, world, d_out, d_st, n, step_ms, shapes, verts):
+    """Collective-bearing and sharded passes (all ranks call this; times are the max over ranks).
+    * gather: the per-rank contact + status records all-gathered ON THE DEVICE over NCCL — what a
+      caller pays to have the whole contact list on every GPU (north_star: "gather contact lists");
+    * strong: ONE 4M-pair batch split over the ranks (plus its gather);
+    * cfg5: 8M time-of-impact pairs per GPU (64M over 8);
+    * cfg4: the AABB table broadcast over NCCL, every GPU computes its shard of the pair list
+      (cb2_sap3_find_collider_pairs_shard_dev) and runs the narrow phase on it."""
+    from collision_rs_b200 import workloads as W
+    from collision_rs_b200.abi import AABB_DT, CONTACT_DT
+    from collision_rs_b200.sharding import gather_contacts_dev, shard_range
+    s = stream.cuda_stream
+    res = {}
+
+    def dv(arr):
+        return torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(dev)
+
+    def max_ms(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, reps=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return max_ms(e0.elapsed_time(e1) / reps)
+
+    # (a) device all-gather of this step's records: 37 B per pair from every rank to every rank
+    total = n * world
+    g_ms = timed(lambda: gather_contacts_dev(d_out, d_st, total))
+    gathered = (CONTACT_DT.itemsize + 1) * total
+    res["gather"] = {"what": "NCCL all_gather_into_tensor of contact (36 B) + status (1 B) records, device to device",
+                     "pairs": total, "bytes_received_per_rank": gathered, "gather_ms": g_ms,
+                     "algbw_gbs": gathered / (g_ms * 1e-3) / 1e9,
+                     "step_ms": step_ms, "pairs_per_s_with_gather": total / ((step_ms + g_ms) * 1e-3)}
+    # (b) strong scaling: one batch of a.pairs split over the ranks
+    tot = a.pairs
+    b, e = shard_range(tot, rank, world)
+    w = W.cfg3_polyhedron_pairs(tot, shard=0)
+    m = e - b
+    d = {k: dv(np.ascontiguousarray(w[k][b:e])) for k in ("l_shape", "r_shape", "l_t", "r_t")}
+    out = torch.empty(m * CONTACT_DT.itemsize, dtype=torch.uint8, device=dev)
+    st = torch.empty(m, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: ctx.intersection_dev(0, d["l_shape"].data_ptr(), d["r_shape"].data_ptr(),
+                                            d["l_t"].data_ptr(), d["r_t"].data_ptr(), m,
+                                            out.data_ptr(), st.data_ptr(), s), reps=5, warm=2)
+    g2 = timed(lambda: gather_contacts_dev(out, st, tot))
+    res["strong"] = {"pairs_total": tot, "pairs_per_rank": m, "ms": ms, "pairs_per_s": tot / ms * 1e3,
+                     "gather_ms": g2, "pairs_per_s_with_gather": tot / (ms + g2) * 1e3}
+    del d, out, st, w
+    # (c) cfg 5: 8M time-of-impact pairs per GPU
+    n5 = 8_000_000
+    w = W.cfg5_toi_pairs(n5, shard=rank)
+    ctx.upload_shapes(w["shapes"])
+    d = {k: dv(w[k]) for k in ("l_shape", "r_shape", "l_t0", "l_t1", "r_t0", "r_t1")}
+    out = torch.empty(n5 * CONTACT_DT.itemsize, dtype=torch.uint8, device=dev)
+    st = torch.empty(n5, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: ctx.time_of_impact_dev(d["l_shape"].data_ptr(), d["r_shape"].data_ptr(),
+                                              d["l_t0"].data_ptr(), d["l_t1"].data_ptr(),
+                                              d["r_t0"].data_ptr(), d["r_t1"].data_ptr(), n5,
+                                              out.data_ptr(), st.data_ptr(), s), reps=3, warm=1)
+    res["cfg5_time_of_impact"] = {"pairs_total": n5 * world, "pairs_per_rank": n5, "ms": ms,
+                                  "pairs_per_s": n5 * world / ms * 1e3}
+    del d, out, st, w
+    # (d) cfg 4: broadcast the AABB table, shard the pair list, narrow phase on each shard
+    nb = 1_000_000
+    w = W.cfg4_aabbs(nb)
+    boxes = dv(w["aabbs"]) if rank == 0 else torch.zeros(nb * AABB_DT.itemsize, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    b_ms = timed(lambda: dist.broadcast(boxes, 0), reps=3, warm=1)
+    ctx.upload_shapes(w["shapes"])
+    perm = torch.empty(nb, dtype=torch.int32, device=dev)
+    cap = 8 * nb
+    pairs = torch.empty(2 * cap, dtype=torch.int32, device=dev)
+    cnt = {}
+
+    def sap():
+        rc, c = ctx.sap3_shard_dev(boxes.data_ptr(), nb, 0, rank, world, perm.data_ptr(), pairs.data_ptr(), cap, s)
+        assert rc == 0
+        cnt["n"] = c
+
+    sap_ms = timed(sap, reps=5, warm=2)
+    mine = int(cnt["n"])
+    t = torch.tensor([mine], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    p64 = perm.long()
+    body_shape = dv(np.arange(nb, dtype=np.uint32)).view(torch.int32)[p64].contiguous()
+    body_t = dv(w["body_t"]).view(-1, 32)[p64].contiguous()
+    outp = torch.empty(max(mine, 1) * CONTACT_DT.itemsize, dtype=torch.uint8, device=dev)
+    stp = torch.empty(max(mine, 1), dtype=torch.uint8, device=dev)
+    np_ms = timed(lambda: ctx.intersection_bodies_dev(0, body_shape.data_ptr(), body_t.data_ptr(),
+                                                      pairs.data_ptr(), mine, outp.data_ptr(), stp.data_ptr(), s))
+    res["cfg4_sap_sharded"] = {"aabbs": nb, "pairs_total": int(t.item()), "pairs_this_rank": mine,
+                               "broadcast_ms": b_ms, "sap_shard_ms": sap_ms, "aabbs_per_s": nb / sap_ms * 1e3,
+                               "narrow_on_shard_ms": np_ms, "narrow_pairs_per_s": int(t.item()) / np_ms * 1e3}
+    return res
 
 
 def extras(ctx, torch, dev, stream):
@@ -444,8 +677,10 @@ def extras(ctx, torch, dev, stream):
     ms_d = timed(lambda: ctx.distance_dev(d["l_shape"].data_ptr(), d["r_shape"].data_ptr(),
                                           d["l_t"].data_ptr(), d["r_t"].data_ptr(), n,
                                           dist_out.data_ptr(), st.data_ptr(), s))
-    res["cfg2_mixed_collision_only"] = {"pairs": n, "ms": ms_c, "pairs_per_s": n / ms_c * 1e3}
-    res["cfg2_mixed_distance"] = {"pairs": n, "ms": ms_d, "pairs_per_s": n / ms_d * 1e3}
+    res["cfg2_mixed_collision_only"] = {"pairs": n, "ms": ms_c, "pairs_per_s": n / ms_c * 1e3,
+                                        "algorithmic_flops_per_pair": counted_flops("intersection1", w)}
+    res["cfg2_mixed_distance"] = {"pairs": n, "ms": ms_d, "pairs_per_s": n / ms_d * 1e3,
+                                  "algorithmic_flops_per_pair": counted_flops("distance", w)}
     # ... and per type pair (Sphere-Cuboid distance is dominated by the 100-iteration cap)
     kl, kr = w["shapes"]["kind"][w["l_shape"]], w["shapes"]["kind"][w["r_shape"]]
     names = {0: "sphere", 1: "cuboid"}
@@ -521,7 +756,8 @@ def extras(ctx, torch, dev, stream):
                                               d["r_t0"].data_ptr(), d["r_t1"].data_ptr(), n,
                                               out.data_ptr(), st.data_ptr(), s), reps=3, warm=1)
     res["cfg5_time_of_impact"] = {"pairs": n, "ms": ms, "pairs_per_s": n / ms * 1e3,
-                                  "nonconverged": int((st == 5).sum()), "iter_cap": 1024}
+                                  "nonconverged": int((st == 5).sum()), "iter_cap": 1024,
+                                  "algorithmic_flops_per_pair": counted_flops("toi", w)}
     # 2-D narrow phase (not a BASELINE config): GJK2 + EPA2 on 4M mixed Primitive2
     # pairs and on rectangles (cfg 1's 2-D twin)
     from collision_rs_b200.abi import CONTACT2_DT

@@ -73,6 +73,87 @@ def gather_contacts(contacts, status, n_total, device="cpu", group=None):
     return out_c, out_s
 
 
+def gather_contacts_dev(contacts, status, n_total, group=None):
+    """Device-resident all-gather of the per-shard records: `contacts` (uint8 tensor, 36 B per pair)
+    and `status` (uint8 tensor) of this rank's shard_range() slice stay on their device, travel over
+    the backend's collective (NCCL over NVLink on the GPUs) and come back as the records of the
+    whole pair stream, in pair order, on every rank — no host bounce.  Returns (contacts, status)
+    tensors on the input device."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rec = CONTACT_DT.itemsize
+    b, e = shard_range(n_total, rank, world)
+    assert contacts.numel() == (e - b) * rec and status.numel() == e - b
+    slot = shard_range(n_total, 0, world)[1]  # the largest shard: equal slots keep it one all_gather
+    dev = contacts.device
+    if (e - b) == slot:
+        c, s = contacts.view(-1), status.view(-1)
+    else:
+        c = torch.zeros(slot * rec, dtype=torch.uint8, device=dev)
+        s = torch.zeros(slot, dtype=torch.uint8, device=dev)
+        c[:contacts.numel()] = contacts.view(-1)
+        s[:status.numel()] = status.view(-1)
+    big_c = torch.empty(world * slot * rec, dtype=torch.uint8, device=dev)
+    big_s = torch.empty(world * slot, dtype=torch.uint8, device=dev)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(big_c, c, group=group)
+        dist.all_gather_into_tensor(big_s, s, group=group)
+    else:
+        dist.all_gather(list(big_c.view(world, -1).unbind(0)), c, group=group)
+        dist.all_gather(list(big_s.view(world, -1).unbind(0)), s, group=group)
+    if n_total % world == 0:
+        return big_c, big_s
+    # ragged tail: drop the padding of the shorter shards
+    keep_c = [big_c[r * slot * rec:(r * slot + (shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0])) * rec]
+              for r in range(world)]
+    keep_s = [big_s[r * slot:r * slot + (shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0])]
+              for r in range(world)]
+    return torch.cat(keep_c), torch.cat(keep_s)
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs local_cpulist), before
+    any pinned host buffer is allocated: first-touch then places the staging buffers next to the GPU
+    and eight ranks stop sharing one socket's memory controller.  Returns the CPU set or None."""
+    import os
+    bdf = None
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{int(pr.pci_domain_id):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
+    except Exception:
+        pass
+    if not bdf:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device_index]) if vis else device_index
+            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        except Exception:
+            return None
+    bdf = bdf.lower()
+    if len(bdf.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+        bdf = bdf[4:]
+    try:
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+    except OSError:
+        return None
+    cpus = set()
+    for tok in txt.split(","):
+        if "-" in tok:
+            a, b = tok.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif tok:
+            cpus.add(int(tok))
+    allowed = os.sched_getaffinity(0)
+    cpus &= allowed if allowed else cpus
+    if not cpus:
+        return None
+    os.sched_setaffinity(0, cpus)
+    return sorted(cpus)
+
+
 # ---- broad phase (SURVEY §8e): shard the sweep, not the sort ------------------------------------------
 def broadcast_aabbs(aabbs, src=0, device="cpu", group=None):
     """Rank `src` passes the AABB table (AABB_DT array); every rank returns it."""

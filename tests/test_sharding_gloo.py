@@ -48,6 +48,12 @@ def _worker(rank, world, port, n, q):
         c, s = o.intersection(0, shapes, verts, w["l_shape"][b:e], w["r_shape"][b:e],
                               w["l_t"][b:e], w["r_t"][b:e], nthreads=2)
         allc, alls = gather_contacts(c, s, n)
+        # the tensor-in / tensor-out gather bench.py times over NCCL (no host bounce on the GPUs)
+        from collision_rs_b200.sharding import gather_contacts_dev
+        import torch
+        tc, ts = gather_contacts_dev(torch.from_numpy(c.view(np.uint8).reshape(-1).copy()),
+                                     torch.from_numpy(s.copy()), n)
+        assert tc.numpy().tobytes() == allc.tobytes() and np.array_equal(ts.numpy(), alls)
         if rank == 0:
             ec, es = o.intersection(0, shapes, verts, w["l_shape"], w["r_shape"], w["l_t"],
                                     w["r_t"], nthreads=2)
