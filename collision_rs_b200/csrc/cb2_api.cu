@@ -56,6 +56,7 @@ struct cb2_ctx {
     cudaEvent_t done[NS] = {};
     // host-API pipeline events per staging buffer: inputs landed | kernels finished | buffer free
     cudaEvent_t ev_in[NS] = {}, ev_k[NS] = {}, ev_free[NS] = {};
+    cudaEvent_t ev_tail[NS] = {};  // tier 0 finished -> the tail stream may start the later tiers
     cudaStream_t s_in = nullptr, s_out = nullptr;  // the pipeline's copy-in / copy-out streams
     int n_cstreams = 3;  // compute streams the pipeline rotates over (CB2_NC overrides, <= NS)
     bool ramp = true;  // short chunks at both ends of a batch (CB2_RAMP=0 disables)
@@ -224,6 +225,7 @@ void cb2_destroy(cb2_ctx* c) {
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+        if (c->ev_tail[i]) cudaEventDestroy(c->ev_tail[i]);
         if (i == 0 && c->s_in) cudaStreamDestroy(c->s_in);
         if (i == 0 && c->s_out) cudaStreamDestroy(c->s_out);
         if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
@@ -567,23 +569,27 @@ static int ensure_retry(cb2_ctx* c, int slot) {
 }
 
 static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A,
-                           cudaStream_t st, int ws_slot);
+                           cudaStream_t st, int ws_slot, cudaStream_t tail);
 
 static void mark_stage(cb2_ctx* c, int k, cudaStream_t st) {
     if (c->stage_timing && c->stage_ev[k]) cudaEventRecord(c->stage_ev[k], st);
 }
 
+// `tail`: the stream the later EPA tiers and the second chance run on (the host pipeline gives them
+// their own, so that the next chunk on `st` does not queue behind a long tier-2 tail); by default
+// everything is issued on `st`.
 static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, cudaStream_t st,
-                     int ws_slot = 0) {
-    int rc = launch_op_inner(c, op, strategy, A, st, ws_slot);
+                     int ws_slot = 0, cudaStream_t tail = nullptr) {
+    if (!tail) tail = st;
+    int rc = launch_op_inner(c, op, strategy, A, st, ws_slot, tail);
     if (rc || !((op == OP_INTERSECTION && strategy == CB2_FULL_RESOLUTION) || op == OP_MANIFOLD)) return rc;
     if (std::getenv("CB2_NO_RETRY")) return CB2_OK;  // diagnosis: leave CB2_SCRATCH_OVERFLOW visible
     // redo the rare pairs whose polytope outgrew the fast kernels' scratch
     rc = ensure_retry(c, ws_slot);
     if (rc) return rc;
-    cudaError_t e = launch_overflow_retry(A, c->retry[ws_slot], st);
+    cudaError_t e = launch_overflow_retry(A, c->retry[ws_slot], tail);
     c->launches += 2;
-    mark_stage(c, 4, st);
+    mark_stage(c, 4, tail);
     if (c->stage_timing) {
         c->stage_stream = st;
         c->stage_valid = !c->legacy_epa;
@@ -596,7 +602,7 @@ static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, 
 }
 
 static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A,
-                           cudaStream_t st, int ws_slot) {
+                           cudaStream_t st, int ws_slot, cudaStream_t tail) {
     A.T.shapes = c->d_shapes;
     A.T.verts = c->d_verts;
     A.T.cells = c->d_cells;
@@ -643,11 +649,17 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
             e = launch_epa_tier(0, A, W, c->sm_count, st);
             mark_stage(c, 2, st);
             trace_stage("tier0", st);
-            for (int k = 1; k < EPA_TIERS && e == cudaSuccess; ++k) {
-                e = launch_epa_tier(k, A, W, c->sm_count, st);
-                trace_stage(k == 1 ? "tier1" : "tier2", st);
+            if (tail != st && e == cudaSuccess) {
+                if (!c->ev_tail[ws_slot])
+                    CK(c, cudaEventCreateWithFlags(&c->ev_tail[ws_slot], cudaEventDisableTiming));
+                CK(c, cudaEventRecord(c->ev_tail[ws_slot], st));
+                CK(c, cudaStreamWaitEvent(tail, c->ev_tail[ws_slot], 0));
             }
-            mark_stage(c, 3, st);
+            for (int k = 1; k < EPA_TIERS && e == cudaSuccess; ++k) {
+                e = launch_epa_tier(k, A, W, c->sm_count, tail);
+                trace_stage(k == 1 ? "tier1" : "tier2", tail);
+            }
+            mark_stage(c, 3, tail);
             c->launches += EPA_TIERS;
         }
         if (e != cudaSuccess) {
@@ -780,7 +792,8 @@ static std::vector<uint64_t> pipeline_chunks(uint64_t n, uint64_t chunk, bool ra
     return v;
 }
 template <class FIn, class FComp, class FOut>
-static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut copy_out) {
+static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut copy_out,
+                        bool split_tail = false) {
     static const bool trace = std::getenv("CB2_TRACE") && std::getenv("CB2_TRACE")[0] == '1';
     cudaStream_t s_in = c->s_in, s_out = c->s_out;
     const std::vector<uint64_t> sizes = pipeline_chunks(n, c->chunk_pairs, c->ramp);
@@ -812,19 +825,24 @@ static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut
     }
     for (size_t k = 0; k < sizes.size() && rc == CB2_OK; ++k) {
         const uint64_t m = sizes[k];
-        const int buf = (int)(k % cb2_ctx::NS), slot = (int)(k % (size_t)c->n_cstreams);
+        // split_tail (the GJK -> EPA pipeline): two front streams carry GJK + tier 0 of alternating
+        // chunks, two tail streams the later tiers and the second chance; the workspace slot follows
+        // the staging buffer, whose `free` event already orders its reuse
+        const int buf = (int)(k % cb2_ctx::NS);
+        const int slot = split_tail ? buf : (int)(k % (size_t)c->n_cstreams);
         char* base = c->d_stage[buf];
-        cudaStream_t s_comp = c->stream[slot];
+        cudaStream_t s_comp = split_tail ? c->stream[k % 2] : c->stream[slot];
+        cudaStream_t s_tail = split_tail ? c->stream[2 + k % 2] : s_comp;
         if (k >= (size_t)cb2_ctx::NS) CKB(cudaStreamWaitEvent(s_in, c->ev_free[buf], 0))
         rc = copy_in(b, m, base, s_in);
         if (rc) break;
         CKB(cudaEventRecord(c->ev_in[buf], s_in))
         mark(s_in);
         CKB(cudaStreamWaitEvent(s_comp, c->ev_in[buf], 0))
-        rc = compute(b, m, base, s_comp, slot);
+        rc = compute(b, m, base, s_comp, slot, s_tail);
         if (rc) break;
-        CKB(cudaEventRecord(c->ev_k[buf], s_comp))
-        mark(s_comp);
+        CKB(cudaEventRecord(c->ev_k[buf], s_tail))
+        mark(s_tail);
         CKB(cudaStreamWaitEvent(s_out, c->ev_k[buf], 0))
         rc = copy_out(b, m, base, s_out);
         if (rc) break;
@@ -904,8 +922,15 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
     if (rc) return rc;
     // size every compute slot's workspace for the largest chunk now: growing one in mid-pipeline
     // (the ramp starts with short chunks) would free buffers under a device-wide synchronisation
+    // CB2_SPLIT_TAIL=1 (experiment, measured no gain: 22.6 against 22.1 ms per 4 M-pair call): front /
+    // tail streams and one workspace per staging buffer, so that a chunk's GJK does not queue behind
+    // the tier-2 tail of the chunk three before it.  Default: every stage of a chunk on one of
+    // n_cstreams streams.
+    static const bool split_env = std::getenv("CB2_SPLIT_TAIL") && std::getenv("CB2_SPLIT_TAIL")[0] == '1';
+    const bool split = split_env && op == OP_INTERSECTION && !c->legacy_epa && strategy == CB2_FULL_RESOLUTION &&
+                       cb2_ctx::NS >= 4;
     if (op == OP_INTERSECTION && !c->legacy_epa)
-        for (int slot = 0; slot < c->n_cstreams; ++slot) {
+        for (int slot = 0; slot < (split ? cb2_ctx::NS : c->n_cstreams); ++slot) {
             rc = ensure_ws(c, slot, chunk);
             if (rc) return rc;
         }
@@ -924,7 +949,7 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
             CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
             return CB2_OK;
         },
-        [&](uint64_t, uint64_t m, char* base, cudaStream_t st, int slot) -> int {
+        [&](uint64_t, uint64_t m, char* base, cudaStream_t st, int slot, cudaStream_t tail) -> int {
             narrow_args A;
             std::memset(&A, 0, sizeof(A));
             A.l_shape = reinterpret_cast<const uint32_t*>(base + o_ls);
@@ -941,7 +966,7 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
             A.out_contact = reinterpret_cast<cb2_contact*>(base + o_out);
             A.out_distance = reinterpret_cast<float*>(base + o_out);
             A.out_status = reinterpret_cast<uint8_t*>(base + o_st);
-            return launch_op(c, op, strategy, A, st, slot);
+            return launch_op(c, op, strategy, A, st, slot, tail);
         },
         [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
             if (op == OP_DISTANCE)
@@ -951,7 +976,8 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
                                       cudaMemcpyDeviceToHost, st));
             CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
             return CB2_OK;
-        });
+        },
+        split);
     if (rc == CB2_OK && c->d_bad_index) {
         CK(c, cudaMemcpy(c->h_bad_index, c->d_bad_index, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (*c->h_bad_index) return fail(c, CB2_ERR_ARG, "shape index out of range");
@@ -1650,7 +1676,7 @@ static int narrow2_host(cb2_ctx* c, int op, uint32_t strategy, const cb2_setting
             CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
             return CB2_OK;
         },
-        [&](uint64_t, uint64_t m, char* base, cudaStream_t st, int slot) -> int {
+        [&](uint64_t, uint64_t m, char* base, cudaStream_t st, int slot, cudaStream_t) -> int {
             const cb2_xform2* X = reinterpret_cast<const cb2_xform2*>(base);
             return narrow2_dev(c, op, strategy, settings, reinterpret_cast<const uint32_t*>(base + o_ls),
                                reinterpret_cast<const uint32_t*>(base + o_rs), X, X + 2 * xs, X + xs,

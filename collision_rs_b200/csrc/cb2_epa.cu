@@ -205,7 +205,6 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     uint32_t* cursor = &C.W.EC->next[C.tier];
     const uint32_t max_it = A.settings.max_iterations;
     const float epa_tol = A.settings.epa_tolerance;
-
     // the adjacency matrix is kept all-zero between iterations
     for (int k = gl; k < VCAP * AW; k += G) P.adj[k] = 0u;
     __syncwarp(gmask);
@@ -730,6 +729,7 @@ cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, 
     C.A = A;
     C.W = W;
     C.tier = (uint32_t)tier;
+    C.sm_count = (uint32_t)sm_count;
     if (tier == 0) {
 #if CB2_TIER0_KIND == 0
         return launch_tier<T0_G, T0_F, T0_V, T0_O, 0, 0>(C, sm_count, st);

@@ -33,7 +33,8 @@ namespace cb2 {
 struct epa_args {
     narrow_args A;
     narrow_ws W;
-    uint32_t tier;  // 0 .. EPA_TIERS-1
+    uint32_t tier;      // 0 .. EPA_TIERS-1
+    uint32_t sm_count;  // SMs of the device (the later tiers size their active grid by it)
 };
 
 // polytope dump record, in float4 units: header (nf, nv, it) | fnd | pv | pa | fidx
