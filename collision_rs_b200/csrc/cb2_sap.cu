@@ -85,6 +85,57 @@ __global__ void __launch_bounds__(256) k_sap_keys(const float* __restrict__ aabb
     idx[i] = (uint32_t)i;
 }
 
+// The sort key of the reference is (min, max) on the sweep axis.  Two boxes rarely share a min, so the
+// radix sort runs on the 32-bit min alone (4 passes instead of 8) and this kernel repairs the runs of
+// equal mins: the first position of a run orders it by (max, original order) with a stable insertion
+// sort.  A run longer than FIX_RUN_MAX (quantised coordinates) raises `need_full`: the host then
+// repeats the call with the 64-bit keys.
+constexpr uint32_t FIX_RUN_MAX = 64;
+__global__ void __launch_bounds__(256) k_sap_keys32(const float* __restrict__ aabbs, uint64_t n, uint32_t axis,
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
+                                                   uint32_t* __restrict__ nan_flag, bool nan_sorts_last) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float mn = __ldg(aabbs + 6 * i + axis);
+    const float mx = __ldg(aabbs + 6 * i + 3 + axis);
+    uint32_t k = ord_f32(mn);
+    if (mn != mn || mx != mx) {
+        if (nan_sorts_last) k = mn != mn ? 0xFFFFFFFFu : k;
+        else atomicOr(nan_flag, 1u);
+    }
+    keys[i] = k;
+    idx[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(256) k_sap_fix_runs(const float* __restrict__ aabbs, uint64_t n, uint32_t axis,
+                                                     const uint32_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ perm, uint32_t* __restrict__ need_full) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k + 1 >= n) return;
+    const uint32_t key = __ldg(keys + k);
+    if (__ldg(keys + k + 1) != key || (k > 0 && __ldg(keys + k - 1) == key)) return;  // not the head of a run
+    uint64_t e = k + 2;
+    while (e < n && e - k <= FIX_RUN_MAX && __ldg(keys + e) == key) ++e;
+    const uint32_t len = (uint32_t)(e - k);
+    if (len > FIX_RUN_MAX) {
+        atomicOr(need_full, 1u);
+        return;
+    }
+    uint32_t id[FIX_RUN_MAX], mx[FIX_RUN_MAX];
+    for (uint32_t i = 0; i < len; ++i) {
+        const uint32_t p = perm[k + i];
+        const uint32_t m = ord_f32(__ldg(aabbs + 6ull * p + 3 + axis));
+        uint32_t j = i;
+        while (j > 0 && mx[j - 1] > m) {  // strict: equal (min, max) keep their original order
+            mx[j] = mx[j - 1];
+            id[j] = id[j - 1];
+            --j;
+        }
+        mx[j] = m;
+        id[j] = p;
+    }
+    for (uint32_t i = 0; i < len; ++i) perm[k + i] = id[i];
+}
+
 __global__ void __launch_bounds__(256) k_sap_gather(const float* __restrict__ aabbs, uint64_t n,
                                                    uint32_t axis, const uint32_t* __restrict__ perm,
                                                    float2* __restrict__ S, float2* __restrict__ U,
@@ -397,9 +448,117 @@ __device__ __forceinline__ unsigned long long pair_key(uint32_t a, uint32_t b, i
 }
 __device__ __forceinline__ void emit_pair(grid_params* __restrict__ G, unsigned long long* __restrict__ keys,
                                           uint64_t cap, int pos_bits, uint32_t a, uint32_t b,
-                                          const uint32_t* __restrict__ remap) {
+                                          const uint32_t* __restrict__ remap, uint32_t* __restrict__ seg_cnt) {
     const unsigned long long w = atomicAdd(&G->n_pairs, 1ull);
-    if (w < cap) keys[w] = pair_key(a, b, pos_bits, remap);
+    const unsigned long long key = pair_key(a, b, pos_bits, remap);
+    if (w < cap) keys[w] = key;
+    if (seg_cnt) atomicAdd(seg_cnt + (uint32_t)(key >> pos_bits), 1u);
+}
+
+// ---- ordering the pair list without a global sort ---------------------------------------------------
+// The reference's Vec is ordered by the later box b, then by a (BruteForce: by the lower original
+// index, then the higher).  The high part of a packed key is therefore a SEGMENT id below n, and a
+// segment holds a handful of pairs (4 on average for cfg 4).  A 40-bit radix sort of all keys moved
+// 10x the pair list through HBM; instead the emitters count pairs per segment, an exclusive scan turns
+// the counts into segment offsets, one pass scatters every key into its segment, and every segment is
+// sorted on its own: by one thread when it is short, by one block (bitonic network in shared memory)
+// when it is long.  A segment beyond SEG_BLOCK_MAX pairs sends the whole call down the radix-sort path.
+constexpr uint32_t SEG_THREAD_MAX = 32;
+constexpr uint32_t SEG_BLOCK_MAX = 4096;
+
+__global__ void __launch_bounds__(256) k_seg_max(const uint32_t* __restrict__ cnt, uint64_t n,
+                                                uint32_t* __restrict__ out_max) {
+    uint32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = __ldg(cnt + i);
+        m = c > m ? c : m;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, m, off);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31u) == 0 && m) atomicMax(out_max, m);
+}
+
+__global__ void __launch_bounds__(256) k_seg_scatter(const unsigned long long* __restrict__ keys, uint64_t np,
+                                                    int pos_bits, const uint64_t* __restrict__ off,
+                                                    uint32_t* __restrict__ fill,
+                                                    unsigned long long* __restrict__ out) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const unsigned long long k = keys[p];
+    const uint32_t seg = (uint32_t)(k >> pos_bits);
+    out[__ldg(off + seg) + atomicAdd(fill + seg, 1u)] = k;
+}
+
+// short segments: one thread each; long ones are queued for k_seg_sort_long
+__global__ void __launch_bounds__(128) k_seg_sort(const unsigned long long* __restrict__ keys,
+                                                 const uint64_t* __restrict__ off, uint64_t n, int pos_bits,
+                                                 bool high_first, uint32_t* __restrict__ pairs,
+                                                 uint32_t* __restrict__ long_list, uint32_t* __restrict__ n_long) {
+    const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n) return;
+    const uint64_t b = __ldg(off + seg), e = __ldg(off + seg + 1);
+    const uint32_t len = (uint32_t)(e - b);
+    if (len == 0) return;
+    if (len > SEG_THREAD_MAX) {
+        long_list[atomicAdd(n_long, 1u)] = (uint32_t)seg;
+        return;
+    }
+    const uint32_t mask = (uint32_t)((1ull << pos_bits) - 1ull);
+    uint32_t lo[SEG_THREAD_MAX];
+    for (uint32_t i = 0; i < len; ++i) {  // insertion sort on the low parts (all distinct)
+        const uint32_t v = (uint32_t)keys[b + i] & mask;
+        uint32_t j = i;
+        while (j > 0 && lo[j - 1] > v) {
+            lo[j] = lo[j - 1];
+            --j;
+        }
+        lo[j] = v;
+    }
+    uint2* o = reinterpret_cast<uint2*>(pairs) + b;
+    const uint32_t high = (uint32_t)seg;
+    for (uint32_t i = 0; i < len; ++i) o[i] = high_first ? make_uint2(high, lo[i]) : make_uint2(lo[i], high);
+}
+
+__global__ void __launch_bounds__(256) k_seg_sort_long(const unsigned long long* __restrict__ keys,
+                                                      const uint64_t* __restrict__ off, int pos_bits,
+                                                      bool high_first, uint32_t* __restrict__ pairs,
+                                                      const uint32_t* __restrict__ long_list,
+                                                      const uint32_t* __restrict__ n_long) {
+    __shared__ uint32_t lo[SEG_BLOCK_MAX];
+    const uint32_t mask = (uint32_t)((1ull << pos_bits) - 1ull);
+    const uint32_t total = *n_long;
+    for (uint32_t li = blockIdx.x; li < total; li += gridDim.x) {
+        const uint32_t seg = long_list[li];
+        const uint64_t b = off[seg];
+        const uint32_t len = (uint32_t)(off[seg + 1] - b);  // <= SEG_BLOCK_MAX (the host checked)
+        uint32_t m = 1;
+        while (m < len) m <<= 1;
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+            lo[i] = i < len ? ((uint32_t)keys[b + i] & mask) : 0xFFFFFFFFu;
+        __syncthreads();
+        for (uint32_t k = 2; k <= m; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                    const uint32_t x = i ^ j;
+                    if (x > i) {
+                        const uint32_t u = lo[i], v = lo[x];
+                        const bool up = (i & k) == 0;
+                        if ((u > v) == up) {
+                            lo[i] = v;
+                            lo[x] = u;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        uint2* o = reinterpret_cast<uint2*>(pairs) + b;
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x)
+            o[i] = high_first ? make_uint2(seg, lo[i]) : make_uint2(lo[i], seg);
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(256) k_sap_unpack(const unsigned long long* __restrict__ keys,
@@ -420,7 +579,8 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
                                                    grid_params* __restrict__ G,
                                                    unsigned long long* __restrict__ keys, uint64_t cap,
                                                    int pos_bits, const uint32_t* __restrict__ remap,
-                                                   uint32_t b_lo, uint32_t b_hi) {
+                                                   uint32_t b_lo, uint32_t b_hi,
+                                                   uint32_t* __restrict__ seg_cnt) {
     // b_lo/b_hi: this GPU's shard of the pair list — only pairs whose LATER box (the `b` the
     // reference's Vec is ordered by) sits at a sorted position in [b_lo, b_hi) are reported
     const bool sharded = b_lo != 0u || b_hi != 0xFFFFFFFFu;
@@ -469,7 +629,9 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
                 if (pass == 0) {
                     ++mine;
                 } else {
-                    if (w < cap) keys[w] = pair_key(a, __ldg(epos + f), pos_bits, remap);
+                    const unsigned long long key = pair_key(a, __ldg(epos + f), pos_bits, remap);
+                    if (w < cap) keys[w] = key;
+                    if (seg_cnt) atomicAdd(seg_cnt + (uint32_t)(key >> pos_bits), 1u);
                     ++w;
                 }
             }
@@ -499,7 +661,7 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
                                                   grid_params* __restrict__ G,
                                                   unsigned long long* __restrict__ keys, uint64_t cap,
                                                   int pos_bits, const uint32_t* __restrict__ remap,
-                                                  uint32_t b_lo, uint32_t b_hi) {
+                                                  uint32_t b_lo, uint32_t b_hi, uint32_t* __restrict__ seg_cnt) {
     const uint32_t nl = G->n_large;
     for (uint32_t li = 0; li < nl; ++li) {
         const uint32_t p = __ldg(large_list + li);
@@ -513,14 +675,14 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
             const uint32_t later = q > p ? (uint32_t)q : p;
             if (later < b_lo || later >= b_hi) continue;  // another GPU's shard
             if (q > p) {
-                emit_pair(G, keys, cap, pos_bits, p, (uint32_t)q, remap);
+                emit_pair(G, keys, cap, pos_bits, p, (uint32_t)q, remap, seg_cnt);
             } else {
                 // (q, p) with q < p: if q is large too, q's own forward pass reports it
                 cell_range r;
                 int cnt;
                 if (box_class(G, qu, qv, r, cnt) == BOX_GRID &&
                     (uint64_t)__ldg(offs + q) + (uint64_t)cnt <= n_entries)
-                    emit_pair(G, keys, cap, pos_bits, (uint32_t)q, p, remap);
+                    emit_pair(G, keys, cap, pos_bits, (uint32_t)q, p, remap, seg_cnt);
             }
         }
     }
@@ -530,7 +692,8 @@ __global__ void k_grid_total(const grid_params* __restrict__ G, const uint32_t* 
                              uint64_t* __restrict__ h_total) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         h_total[0] = G->n_pairs;
-        h_total[1] = *nan_flag;
+        // NaN flag (bit 0) | "a run of equal mins was too long for the 32-bit sort" (bit 1) | longest segment
+        h_total[1] = (uint64_t)(nan_flag[0] & 1u) | ((uint64_t)(nan_flag[3] & 1u) << 1) | ((uint64_t)nan_flag[1] << 32);
     }
 }
 
@@ -734,16 +897,24 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
     while (((uint64_t)1 << pos_bits) < n) ++pos_bits;
     // internal pair buffer: the caller's cap, but start no larger than 16 pairs per box
     uint64_t kcap = cap < 16 * n + 1024 ? cap : 16 * n + 1024;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        size_t sort1 = 0, sort2 = 0, sort3 = 0;
+    static const bool keys64_env = std::getenv("CB2_SAP_KEYS64") && std::getenv("CB2_SAP_KEYS64")[0] == '1';
+    bool keys64 = keys64_env;  // false: sort on the 32-bit min and repair the runs of equal mins
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        size_t sort1 = 0, sort1b = 0, sort2 = 0, sort3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, sort1, (uint64_t*)nullptr, (uint64_t*)nullptr,
                                         (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)n, 0, 64, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, sort1b, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                        (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)n, 0, 32, st);
+        if (sort1b > sort1) sort1 = sort1b;
         cub::DeviceRadixSort::SortPairs(nullptr, sort2, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                         (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)ne, 0,
                                         cell_bits, st);
-        size_t scan_tmp = 0;
+        size_t scan_tmp = 0, scan2_tmp = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                       (int64_t)n, st);
+        cub::DeviceScan::ExclusiveScan(nullptr, scan2_tmp, (uint32_t*)nullptr, (uint64_t*)nullptr, cub::Sum(),
+                                       (uint64_t)0, (int64_t)(n + 1), st);
+        if (scan2_tmp > scan_tmp) scan_tmp = scan2_tmp;
         cub::DeviceRadixSort::SortKeys(nullptr, sort3, (unsigned long long*)nullptr,
                                        (unsigned long long*)nullptr, (int64_t)(kcap ? kcap : 1), 0,
                                        2 * pos_bits, st);
@@ -756,6 +927,8 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         const size_t o_cnt = take(4 * n), o_offs = take(4 * n), o_perm = take(4 * n);
         const size_t o_eS = take(8 * ne), o_eU = take(8 * ne), o_eV = take(8 * ne);
         const size_t o_pk = take(8 * (kcap ? kcap : 1)), o_pk2 = take(8 * (kcap ? kcap : 1));
+        const size_t o_seg = take(4 * (n + 1)), o_fill = take(4 * (n + 1)), o_soff = take(8 * (n + 2));
+        const size_t o_long = take(4 * n);
         size_t tmpsz = sort1 > sort2 ? sort1 : sort2;
         tmpsz = tmpsz > sort3 ? tmpsz : sort3;
         tmpsz = tmpsz > scan_tmp ? tmpsz : scan_tmp;
@@ -786,15 +959,36 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         unsigned long long* pk = (unsigned long long*)(base + o_pk);
         unsigned long long* pk2 = (unsigned long long*)(base + o_pk2);
         void* tmp = base + o_tmp;
+        uint32_t* seg_cnt = (uint32_t*)(base + o_seg);
+        uint32_t* seg_fill = (uint32_t*)(base + o_fill);
+        uint64_t* seg_off = (uint64_t*)(base + o_soff);
+        uint32_t* long_list = (uint32_t*)(base + o_long);
+        // the pair list is ordered segment by segment unless the caller wants the bare set
+        static const bool seg_env = !(std::getenv("CB2_SAP_RADIX_PAIRS") && std::getenv("CB2_SAP_RADIX_PAIRS")[0] == '1');
+        const bool by_segment = seg_env && !(unordered && !brute_force);
+        if (by_segment) {
+            SAP_CK(cudaMemsetAsync(seg_cnt, 0, 4 * (n + 1), st));
+            SAP_CK(cudaMemsetAsync(seg_fill, 0, 4 * (n + 1), st));
+        }
+        uint32_t* seg_arg = by_segment ? seg_cnt : nullptr;
 
-        SAP_CK(cudaMemsetAsync(flag, 0, 4, st));
+        SAP_CK(cudaMemsetAsync(flag, 0, 256, st));
         SAP_CK(cudaMemsetAsync(G, 0, sizeof(grid_params), st));
         SAP_CK(cudaMemsetAsync(G, 0xFF, 2 * sizeof(uint32_t), st));  // min_u, min_v = +max
         SAP_CK(cudaMemsetAsync(c0, 0xFF, 4 * ne, st));  // unused entry records = sentinel cells
-        k_sap_keys<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, keys0, idx0, flag, brute_force);
         size_t tb = sort1;
-        SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, idx0, perm_out, (int64_t)n, 0,
-                                               64, st));
+        if (keys64) {
+            k_sap_keys<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, keys0, idx0, flag, brute_force);
+            SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys0, keys1, idx0, perm_out, (int64_t)n, 0,
+                                                   64, st));
+        } else {
+            uint32_t* k32a = reinterpret_cast<uint32_t*>(keys0);
+            uint32_t* k32b = reinterpret_cast<uint32_t*>(keys1);
+            k_sap_keys32<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, k32a, idx0, flag, brute_force);
+            SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, k32a, k32b, idx0, perm_out, (int64_t)n, 0, 32, st));
+            k_sap_fix_runs<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, k32b, perm_out, flag + 3);
+            ++*launches;
+        }
         k_sap_gather<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, perm_out, S, U, V);
         k_grid_stats<<<592, 256, 0, st>>>(U, V, n, G);
         k_grid_params<<<1, 32, 0, st>>>(G, n);
@@ -806,17 +1000,26 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, p0, p1, (int64_t)ne, 0, cell_bits, st));
         k_grid_pack<<<nblk(ne, 256), 256, 0, st>>>(S, U, V, c1, p1, ne, G, eS, eU, eV);
         k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, ne, G, pk, kcap, pos_bits, remap,
-                                                      b_lo, b_hi);
+                                                      b_lo, b_hi, seg_arg);
         k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, offs, ne, G, pk, kcap, pos_bits, remap, b_lo,
-                                         b_hi);
+                                         b_hi, seg_arg);
+        if (by_segment) {
+            k_seg_max<<<296, 256, 0, st>>>(seg_cnt, n, flag + 1);
+            ++*launches;
+        }
         k_grid_total<<<1, 32, 0, st>>>(G, flag, w->h_total);
         *launches += 13;
         SAP_CK(cudaGetLastError());
         SAP_CK(cudaStreamSynchronize(st));
-        if (w->h_total[1]) {
+        if (w->h_total[1] & 1ull) {
             *err = "NaN extent on the sweep axis";
             return CB2_ERR_NAN;
         }
+        if (w->h_total[1] & 2ull) {  // many boxes share a min (quantised input): full (min, max) keys
+            keys64 = true;
+            continue;
+        }
+        const uint32_t longest = (uint32_t)(w->h_total[1] >> 32);
         const uint64_t np = w->h_total[0];
         *n_pairs = np;
         if (np == 0) return CB2_OK;
@@ -824,6 +1027,24 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         if (np > kcap) {  // denser than 16 pairs per box: run again with the exact room
             kcap = np;
             continue;
+        }
+        if (by_segment && longest <= SEG_BLOCK_MAX) {
+            // counts -> offsets, keys -> their segments, every segment sorted on its own
+            tb = scan_tmp;
+            SAP_CK(cub::DeviceScan::ExclusiveScan(tmp, tb, seg_cnt, seg_off, cub::Sum(), (uint64_t)0,
+                                                  (int64_t)(n + 1), st));
+            k_seg_scatter<<<nblk(np, 256), 256, 0, st>>>(pk, np, pos_bits, seg_off, seg_fill, pk2);
+            SAP_CK(cudaMemsetAsync(flag + 2, 0, 4, st));
+            k_seg_sort<<<nblk(n, 128), 128, 0, st>>>(pk2, seg_off, n, pos_bits, brute_force, pairs_out, long_list,
+                                                      flag + 2);
+            *launches += 3;
+            if (longest > SEG_THREAD_MAX) {
+                k_seg_sort_long<<<592, 256, 0, st>>>(pk2, seg_off, pos_bits, brute_force, pairs_out, long_list,
+                                                      flag + 2);
+                ++*launches;
+            }
+            SAP_CK(cudaGetLastError());
+            return CB2_OK;
         }
         if (unordered && !brute_force) {
             // the caller wants the pair SET (e.g. to feed the narrow phase): no final sort

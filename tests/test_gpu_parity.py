@@ -361,6 +361,23 @@ def test_sap_ties_signed_zero_and_wide_boxes(ctx, oracle):
         _check_sap(ctx, oracle, a, axis)
 
 
+def test_sap_long_segments_of_the_pair_list(ctx, oracle):
+    """The pair list is ordered segment by segment (one segment per later box): a box that spans the
+    scene collects a long segment — block-sorted up to 4096 pairs, the radix-sort path beyond."""
+    for n, stride in ((3_000, 997), (9_000, 2_999), (2_000, 1)):
+        a = W.cfg4_aabbs(n, seed=n, extent=40.0)["aabbs"]
+        if stride > 1:
+            a["min"][::stride] = -100.0
+            a["max"][::stride] = 100.0
+        else:  # every box overlaps every other: segment k holds k pairs (33 .. 1999: thread and block paths)
+            a["min"] -= 50.0
+            a["max"] += 50.0
+        for axis in (0, 1):
+            _check_sap(ctx, oracle, a, axis)
+        exp = oracle.brute_force_pairs(a)
+        assert np.array_equal(ctx.brute_force(a), exp)
+
+
 def test_sap_small_n(ctx, oracle):
     w = W.cfg4_aabbs(64, extent=8.0)
     for n in (0, 1, 2, 3, 33):
