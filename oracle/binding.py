@@ -252,6 +252,20 @@ class Oracle:
                                  int(nthreads))
         return out
 
+    def sap3_mt(self, aabbs, axis=0, cap=None, nthreads=None):
+        """sap3 with the sweep split over host threads (same pairs, same order)."""
+        n = len(aabbs)
+        nthreads = nthreads or self.hw_threads()
+        perm = np.zeros(max(n, 1), np.uint32)
+        cap = int(cap) if cap is not None else 16 * n + 1024
+        pairs = np.zeros((max(cap, 1), 2), np.uint32)
+        ax = C.c_uint32(axis)
+        self.lib.orc_sap3_find_collider_pairs_mt.restype = C.c_uint64
+        cnt = self.lib.orc_sap3_find_collider_pairs_mt(_p(aabbs), C.c_uint64(n), C.byref(ax), _p(perm),
+                                                       _p(pairs), C.c_uint64(cap), int(nthreads))
+        assert cnt <= cap
+        return perm[:n].copy(), pairs[:int(cnt)].copy(), int(cnt), ax.value
+
     def sap3(self, aabbs, axis=0, cap=None):
         n = len(aabbs)
         perm = np.zeros(max(n, 1), np.uint32)

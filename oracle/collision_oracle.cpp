@@ -41,6 +41,9 @@
 #include <map>
 #include <vector>
 
+#include <map>
+#include <mutex>
+
 #include "../include/collision_b200.h"
 
 namespace orc {
@@ -1423,6 +1426,70 @@ uint64_t orc_sap3_find_collider_pairs(const cb2_aabb3* aabbs, uint64_t n, uint32
     }
     // Variance3::add_bound discards its sums (sweep_prune.rs:254-261: add_element_wise
     // returns by value) => compute_axis sees zeros => axis 0 (:264-277, :130-133).
+    *axis_inout = 0;
+    return np;
+}
+
+// The same sweep split over threads (for the 1 M-box comparison of the GPU tests; the reference is
+// single-threaded).  Thread t replays the loop of :100-122 literally over its range [j0, j1) of
+// sorted positions; all it needs is the `active` list as the serial loop would hold it when it
+// reaches j0.  With finite, ascending min extents `retain` is monotone — an entry dropped at step j
+// stays dropped — so that list is {a < j0 - 1 : max[a] >= min[j0 - 1]} in ascending order, plus
+// j0 - 1 itself.  Inputs that break the premise (NaN on the sweep axis) take the serial function.
+uint64_t orc_sap3_find_collider_pairs_mt(const cb2_aabb3* aabbs, uint64_t n, uint32_t* axis_inout,
+                                         uint32_t* perm_out, uint32_t* pairs_out, uint64_t cap,
+                                         int nthreads) {
+    const uint32_t axis = *axis_inout;
+    bool plain = n > 1 && nthreads > 1;
+    for (uint64_t i = 0; i < n && plain; ++i)
+        plain = aabbs[i].min[axis] == aabbs[i].min[axis] && aabbs[i].max[axis] == aabbs[i].max[axis];
+    if (!plain) return orc_sap3_find_collider_pairs(aabbs, n, axis_inout, perm_out, pairs_out, cap);
+    for (uint64_t i = 0; i < n; ++i) perm_out[i] = (uint32_t)i;
+    std::stable_sort(perm_out, perm_out + n, [&](uint32_t a, uint32_t b) {
+        return sap_cmp(aabbs[a].min, aabbs[b].min, axis) < 0;
+    });
+    std::vector<cb2_aabb3> s(n);
+    for (uint64_t i = 0; i < n; ++i) s[i] = aabbs[perm_out[i]];
+    // parallel_for hands out dynamic chunks: results are kept per chunk and stitched in chunk order
+    std::map<uint64_t, std::vector<uint32_t>> found;
+    std::mutex mu;
+    parallel_for(n - 1, nthreads, [&](uint64_t b, uint64_t e, int) {
+        const uint64_t j0 = b + 1, j1 = e + 1;  // positions 1 .. n-1
+        std::vector<uint32_t> active;
+        if (j0 >= 2) {
+            const float prev = s[j0 - 1].min[axis];
+            for (uint64_t a = 0; a + 1 < j0; ++a)
+                if (s[a].max[axis] >= prev) active.push_back((uint32_t)a);
+        }
+        active.push_back((uint32_t)(j0 - 1));
+        std::vector<uint32_t> out;
+        for (uint64_t j = j0; j < j1; ++j) {
+            const float mn = s[j].min[axis];
+            size_t w = 0;
+            for (size_t k = 0; k < active.size(); ++k)
+                if (s[active[k]].max[axis] >= mn) active[w++] = active[k];
+            active.resize(w);
+            for (size_t k = 0; k < active.size(); ++k)
+                if (aabb_intersects(s[active[k]].min, s[j].min)) {
+                    out.push_back(active[k]);
+                    out.push_back((uint32_t)j);
+                }
+            active.push_back((uint32_t)j);
+        }
+        std::lock_guard<std::mutex> lock(mu);
+        found[b].swap(out);
+    });
+    uint64_t np = 0;
+    for (auto& kv : found) {
+        const std::vector<uint32_t>& f = kv.second;
+        for (size_t k = 0; k + 1 < f.size(); k += 2) {
+            if (pairs_out && np < cap) {
+                pairs_out[2 * np] = f[k];
+                pairs_out[2 * np + 1] = f[k + 1];
+            }
+            ++np;
+        }
+    }
     *axis_inout = 0;
     return np;
 }

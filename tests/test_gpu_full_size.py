@@ -143,3 +143,16 @@ def test_cfg4_one_million_boxes_pipeline(ctx):
                                 st.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert int((st == 1).sum()) == m
+
+
+def test_cfg4_one_million_boxes_against_the_oracle(ctx, oracle):
+    """The whole pair list of cfg 4 — permutation and ~3.9 M pairs in the reference's Vec order —
+    byte for byte against the oracle (its sweep split over the host threads: 1e10 box tests)."""
+    n = 1_000_000
+    b = W.cfg4_aabbs(n)["aabbs"]
+    perm, pairs, axis = ctx.sap3(b, axis=0)
+    perm_e, pairs_e, cnt, axis_e = oracle.sap3_mt(b, axis=0)
+    assert cnt == len(pairs) and 3_900_000 < cnt < 4_000_000
+    assert np.array_equal(perm, perm_e)
+    assert np.array_equal(pairs, pairs_e)
+    assert axis == axis_e == 0

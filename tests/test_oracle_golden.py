@@ -466,3 +466,20 @@ def test_half_edge_rejects_degenerate_faces(oracle):
     faces = np.array([(0, 1, 2), (0, 1, 3), (1, 2, 3), (0, 2, 3)], np.uint32)  # first face collinear
     with pytest.raises(ValueError):
         oracle.build_half_edges(polyhedron_he(0, 4, 0, 4), pts, faces)
+
+
+def test_threaded_sweep_is_the_serial_sweep(oracle):
+    """sap3_mt (the oracle's sweep split over threads, used for the 1 M-box GPU comparison) returns
+    the serial function's permutation and pair list, ties and wide boxes included."""
+    from collision_rs_b200 import workloads as W
+    b = W.cfg4_aabbs(40_000, extent=200.0 * (40_000 / 1e6) ** (1 / 3))["aabbs"]
+    q = b.copy()
+    q["min"] = np.round(q["min"])
+    q["max"] = np.round(q["max"]) + 1
+    q["min"][::1501] = -100.0
+    q["max"][::1501] = 100.0
+    for boxes in (b, q):
+        for axis in (0, 2):
+            p1, r1, c1, a1 = oracle.sap3(boxes, axis=axis)
+            p2, r2, c2, a2 = oracle.sap3_mt(boxes, axis=axis, nthreads=5)
+            assert c1 == c2 and a1 == a2 and np.array_equal(p1, p2) and np.array_equal(r1, r2)
