@@ -263,7 +263,8 @@ class Oracle:
         self.lib.orc_sap3_find_collider_pairs_mt.restype = C.c_uint64
         cnt = self.lib.orc_sap3_find_collider_pairs_mt(_p(aabbs), C.c_uint64(n), C.byref(ax), _p(perm),
                                                        _p(pairs), C.c_uint64(cap), int(nthreads))
-        assert cnt <= cap
+        if cnt > cap:  # denser than the first guess: once more with the exact room
+            return self.sap3_mt(aabbs, axis, int(cnt), nthreads)
         return perm[:n].copy(), pairs[:int(cnt)].copy(), int(cnt), ax.value
 
     def sap3(self, aabbs, axis=0, cap=None):
