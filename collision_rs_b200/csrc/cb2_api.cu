@@ -531,10 +531,11 @@ int cb2_shapes_upload_faces(cb2_ctx* c, const cb2_shape* shapes, uint32_t n_shap
 // ---- narrow phase ---------------------------------------------------------------------------------
 enum op_kind { OP_INTERSECTION, OP_DISTANCE, OP_TOI, OP_INTERSECT, OP_MANIFOLD };
 
-static int check_settings(cb2_ctx* c, const cb2_settings* s) {
+static int check_settings(cb2_ctx* c, const cb2_settings* s, bool dim2 = false) {
     if (!s) return fail(c, CB2_ERR_ARG, "settings is null");
-    if (s->max_iterations > CB2_MAX_ITERATIONS)
-        return fail(c, CB2_ERR_UNSUPPORTED, "max_iterations above CB2_MAX_ITERATIONS (100)");
+    if (s->max_iterations > (dim2 ? CB2_MAX_ITERATIONS_2D : CB2_MAX_ITERATIONS))
+        return fail(c, CB2_ERR_UNSUPPORTED,
+                    dim2 ? "max_iterations above CB2_MAX_ITERATIONS_2D (100)" : "max_iterations above CB2_MAX_ITERATIONS (250)");
     return CB2_OK;
 }
 
@@ -1420,7 +1421,7 @@ static int complex_host(cb2_ctx* c, bool d2, op_kind op, uint32_t strategy, cons
     const uint32_t n_comp = d2 ? c->n_comp2 : c->n_comp;
     const std::vector<uint32_t>& h_off = d2 ? c->h_comp2_off : c->h_comp_off;
     const size_t contact_bytes = d2 ? sizeof(cb2_contact2) : sizeof(cb2_contact);
-    int rc = check_settings(c, settings);
+    int rc = check_settings(c, settings, d2);
     if (rc) return rc;
     if (op != OP_DISTANCE && strategy > CB2_COLLISION_ONLY) return fail(c, CB2_ERR_ARG, "bad strategy");
     if (n == 0) return CB2_OK;
@@ -1573,7 +1574,7 @@ static int narrow2_check(cb2_ctx* c, int op, uint32_t strategy, const cb2_settin
                          const void* l_shape, const void* r_shape, const void* l_t0, const void* l_t1,
                          const void* r_t0, const void* r_t1, const void* out, const void* status) {
     if (!c) return CB2_ERR_ARG;
-    int rc = check_settings(c, settings);
+    int rc = check_settings(c, settings, true);
     if (rc) return rc;
     if (op == 0 && strategy > CB2_COLLISION_ONLY) return fail(c, CB2_ERR_ARG, "bad strategy");
     if (!c->d_shapes2) return fail(c, CB2_ERR_ARG, "cb2_shapes2_upload has not been called");

@@ -57,12 +57,14 @@ struct aabb_args {
 cudaError_t launch_intersection(const narrow_args& A, bool full, cudaStream_t st);
 
 // ---- second chance for pairs whose EPA polytope outgrew the fast kernels' scratch ----------------
-constexpr int RETRY_FACES = 16384;
-constexpr int RETRY_EDGES = 4096;
+constexpr int RETRY_FACES = 65536;
+constexpr int RETRY_EDGES = 16384;
+constexpr int RETRY_VERTS = 256;
 constexpr int RETRY_BLOCKS = 64;
 constexpr uint32_t RETRY_LIST_CAP = 1u << 16;
-constexpr size_t RETRY_BYTES_PER_BLOCK =
-    (size_t)RETRY_FACES * 20 + 2 * 104 * 12 + (size_t)RETRY_EDGES * 2 + 64;
+constexpr size_t RETRY_BYTES_PER_BLOCK =  // fnd | pv | pa | fidx | vmask | edges
+    (size_t)RETRY_FACES * 16 + 2 * (size_t)RETRY_VERTS * 16 + (size_t)RETRY_FACES * 4 + RETRY_FACES / 8 +
+    (size_t)RETRY_EDGES * 2 + 256;
 struct retry_ws {
     uint32_t* list;   // RETRY_LIST_CAP
     uint32_t* count;  // [0] = overflow count, [1] = work cursor

@@ -41,22 +41,6 @@ struct local_store {
     CB2_DI int vcap() const { return EPA_MAX_VERTS; }
     CB2_DI int ecap() const { return EPA_MAX_EDGES; }
 };
-struct global_store {
-    float4* fnd_;
-    uint32_t* fidx_;
-    f3* pv_;
-    f3* pa_;
-    uint16_t* edges_;
-    CB2_DI float4& fnd(int i) { return fnd_[i]; }
-    CB2_DI uint32_t& fidx(int i) { return fidx_[i]; }
-    CB2_DI f3& pv(int i) { return pv_[i]; }
-    CB2_DI f3& pa(int i) { return pa_[i]; }
-    CB2_DI uint16_t& edge(int i) { return edges_[i]; }
-    CB2_DI int fcap() const { return RETRY_FACES; }
-    CB2_DI int vcap() const { return EPA_MAX_VERTS; }
-    CB2_DI int ecap() const { return RETRY_EDGES; }
-};
-
 // Face::new_impl, epa3d.rs:189-199
 template <class S>
 CB2_DI void face_new(S& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
@@ -817,7 +801,8 @@ __global__ void __launch_bounds__(256) k_collect_overflow(const uint8_t* __restr
 // as the fallback for polytopes that outgrow the shared-memory store.
 constexpr int COOP_FACES = 1536;
 constexpr int COOP_EDGES = 2048;
-struct coop_store {
+struct coop_store {   // shared memory: what nearly every second-chance pair fits
+    static constexpr int FCAP = COOP_FACES, ECAP = COOP_EDGES, VCAP = EPA_MAX_VERTS;
     float4 fnd[COOP_FACES];
     uint32_t fidx[COOP_FACES];
     float4 pv[EPA_MAX_VERTS];
@@ -825,11 +810,25 @@ struct coop_store {
     uint16_t edges[COOP_EDGES];
     uint32_t vmask[COOP_FACES / 32];
 };
-CB2_DI f3 cs_pv(const coop_store& P, uint32_t i) {
+// ... and the same arrays in global memory for the polytopes that do not (the 32 lanes stride over
+// the faces, so the accesses coalesce): RETRY_FACES faces, RETRY_EDGES horizon edges, RETRY_VERTS
+// vertices — the byte-sized vertex indices of a face record allow 255, i.e. max_iterations <= 250
+struct coop_gstore {
+    static constexpr int FCAP = RETRY_FACES, ECAP = RETRY_EDGES, VCAP = RETRY_VERTS;
+    float4* fnd;
+    uint32_t* fidx;
+    float4* pv;
+    float4* pa;
+    uint16_t* edges;
+    uint32_t* vmask;
+};
+template <class ST>
+CB2_DI f3 cs_pv(const ST& P, uint32_t i) {
     const float4 v = P.pv[i];
     return mk3(v.x, v.y, v.z);
 }
-CB2_DI void cs_face_new(coop_store& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
+template <class ST>
+CB2_DI void cs_face_new(ST& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
     const f3 va = cs_pv(P, a);
     const f3 ab = cs_pv(P, b) - va;
     const f3 ac = cs_pv(P, c) - va;
@@ -838,7 +837,8 @@ CB2_DI void cs_face_new(coop_store& P, int slot, uint32_t a, uint32_t b, uint32_
     P.fidx[slot] = a | (b << 8) | (c << 16);
 }
 // every lane runs this with identical arguments; control flow is warp-uniform
-__device__ __noinline__ uint8_t epa_process_coop(coop_store& P, const pair_in& p, const simplex<true>& s,
+template <class ST>
+__device__ __noinline__ uint8_t epa_process_coop(ST& P, const pair_in& p, const simplex<true>& s,
                                                  float tol, uint32_t max_iterations, contact_out& out) {
     const int lane = threadIdx.x & 31;
     if (lane < 4) {
@@ -971,7 +971,7 @@ __device__ __noinline__ uint8_t epa_process_coop(coop_store& P, const pair_in& p
                                 __syncwarp();
                             }
                             --ne;
-                        } else if (ne >= COOP_EDGES) {
+                        } else if (ne >= ST::ECAP) {
                             overflow = 1;
                         } else {
                             if (lane == 0) P.edges[ne] = (uint16_t)(ea | (eb << 8));
@@ -986,7 +986,7 @@ __device__ __noinline__ uint8_t epa_process_coop(coop_store& P, const pair_in& p
             }
         }
         __syncwarp();
-        if (overflow || nv >= EPA_MAX_VERTS || nf + ne > COOP_FACES) return ST_SCRATCH_OVERFLOW;
+        if (overflow || nv >= ST::VCAP || nf + ne > ST::FCAP) return ST_SCRATCH_OVERFLOW;
         const uint32_t nn = (uint32_t)nv;
         if (lane == 0) {
             P.pv[nn] = make_float4(sv.x, sv.y, sv.z, 0.f);
@@ -1012,13 +1012,14 @@ __global__ void __launch_bounds__(32) k_retry_overflow(narrow_args A, const uint
     const int lane = threadIdx.x;
     uint32_t total = *count;
     if (total > RETRY_LIST_CAP) total = RETRY_LIST_CAP;
-    global_store P;
+    coop_gstore P;
     char* base = scratch + (size_t)blockIdx.x * RETRY_BYTES_PER_BLOCK;
-    P.fnd_ = reinterpret_cast<float4*>(base);
-    P.fidx_ = reinterpret_cast<uint32_t*>(base + (size_t)RETRY_FACES * 16);
-    P.pv_ = reinterpret_cast<f3*>(base + (size_t)RETRY_FACES * 20);
-    P.pa_ = P.pv_ + EPA_MAX_VERTS;
-    P.edges_ = reinterpret_cast<uint16_t*>(P.pa_ + EPA_MAX_VERTS);
+    P.fnd = reinterpret_cast<float4*>(base);
+    P.pv = P.fnd + RETRY_FACES;
+    P.pa = P.pv + RETRY_VERTS;
+    P.fidx = reinterpret_cast<uint32_t*>(P.pa + RETRY_VERTS);
+    P.vmask = P.fidx + RETRY_FACES;
+    P.edges = reinterpret_cast<uint16_t*>(P.vmask + RETRY_FACES / 32);
     for (;;) {
         uint32_t k = 0;
         if (lane == 0) k = atomicAdd(cursor, 1u);
@@ -1048,12 +1049,8 @@ __global__ void __launch_bounds__(32) k_retry_overflow(narrow_args A, const uint
             }
             if (inside) {
                 st = epa_process_coop(CS, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
-                if (st == ST_SCRATCH_OVERFLOW) {
-                    // past the shared-memory store: the serial version over global scratch
-                    if (lane == 0)
-                        st = epa_process(P, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
-                    st = (uint8_t)__shfl_sync(0xffffffffu, (int)st, 0);  // the contact stays on lane 0
-                }
+                if (st == ST_SCRATCH_OVERFLOW)  // past the shared-memory store: the same, over global scratch
+                    st = epa_process_coop(P, p, s, A.settings.epa_tolerance, A.settings.max_iterations, c);
                 if (st != ST_SOME) c = zero_contact();
             }
             if (p.ls.hang | p.rs.hang) {

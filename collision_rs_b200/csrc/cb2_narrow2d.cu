@@ -319,7 +319,7 @@ CB2_DI void store_contact2(cb2_contact2* out, uint64_t i, uint32_t strategy, f2 
 // approx ulps_eq!(inf, x) (epa2d.rs:154 assert_ulps_ne!): x is +inf or within 4 ulps below it
 CB2_DI bool ulps_eq_inf(float x) { return x > 0.0f && __float_as_uint(x) >= 0x7f800000u - 4u && x == x; }
 
-constexpr int EPA2_CAP = 3 + (int)CB2_MAX_ITERATIONS + 1;
+constexpr int EPA2_CAP = 3 + (int)CB2_MAX_ITERATIONS_2D + 1;
 
 // edge (a -> b) of the EPA2 polygon: normal.xy, distance (epa2d.rs:141-147)
 CB2_DI float4 edge_of(f2 a, f2 b) {

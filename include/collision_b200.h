@@ -58,9 +58,11 @@ typedef enum cb2_status {
                                    (polyhedron.rs:184-206 loops while best_dot != previous) */
     CB2_PANIC_EPA_EMPTY = 6,    /* Polytope::closest_face_to_origin indexes
                                    faces[0] of an empty Vec, epa/epa3d.rs:138    */
-    CB2_SCRATCH_OVERFLOW = 7,   /* device EPA scratch exhausted (non-manifold horizon
-                                   grew the polytope past 2V-4 faces): result NOT
-                                   computed — loud, never a silent wrong answer  */
+    CB2_SCRATCH_OVERFLOW = 7,   /* device EPA scratch exhausted: a non-manifold horizon grew the
+                                   polytope past 65 536 faces or 16 384 horizon edges (a Particle
+                                   inside a Cylinder reaches 533 000 faces and takes the reference
+                                   100 s for ONE pair).  Result NOT computed — loud, never a silent
+                                   wrong answer; INTEGRATION.md lists it as a deliberate limit  */
     CB2_PANIC_CMP_NAN = 8,      /* intersection_complex: max_by(partial_cmp(..).unwrap())
                                    met a NaN penetration depth, gjk/mod.rs:455-459 */
     /* 9 and 10 are the 2-D path's CB2_PANIC_EPA2_EDGE / CB2_PANIC_INV_ROT below */
@@ -129,9 +131,14 @@ typedef struct cb2_settings {
     uint32_t max_iterations;
 } cb2_settings;
 
-/* Largest max_iterations the device kernels accept (EPA polytope scratch is
- * sized for it: <= 3+max_iterations vertices, <= 2*(3+max_iterations)-4 faces). */
-#define CB2_MAX_ITERATIONS 100u
+/* Largest max_iterations the 3-D entry points accept.  GJK::new_with_settings (gjk/mod.rs:71-84)
+ * takes any u32; here an EPA polytope names its vertices with bytes (<= 255 vertices = 4 + 250 adds).
+ * Up to 100 iterations (the crate's default MAX_ITERATIONS) every pair stays in the fast shared-
+ * memory tiers; beyond that the long pairs finish in the second-chance kernel over global scratch
+ * (65 536 faces, 16 384 horizon edges) — same results, slower.  The 2-D entry points keep the cap of
+ * 100 (their polygon ring is sized for it).  Larger values: CB2_ERR_UNSUPPORTED.                  */
+#define CB2_MAX_ITERATIONS 250u
+#define CB2_MAX_ITERATIONS_2D 100u
 
 /* Aabb3<f32> (volume/aabb/aabb3.rs:20-25): min.xyz, max.xyz (24 B). */
 typedef struct cb2_aabb3 {

@@ -9,7 +9,8 @@
 use std::os::raw::{c_char, c_int, c_void};
 
 pub const CB2_ABI_VERSION: u32 = 1;
-pub const CB2_MAX_ITERATIONS: u32 = 100;
+pub const CB2_MAX_ITERATIONS: u32 = 250;
+pub const CB2_MAX_ITERATIONS_2D: u32 = 100;
 
 // cb2_error
 pub const CB2_OK: c_int = 0;
