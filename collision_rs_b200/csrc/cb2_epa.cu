@@ -29,6 +29,7 @@
 //    vertex is only read by the final contact (epa3d.rs:84-114), so it lives in a global
 //    scratch, not shared memory.
 #include "cb2_epa_team.cuh"
+#include "cb2_tma.cuh"
 
 #ifndef CB2_T0_F  // build-time overrides for A/B experiments (tools/ab_variants.sh)
 #define CB2_T0_F 40
@@ -64,6 +65,7 @@ struct poly_smem {
     uint8_t order[OCAP];       // visible faces in the order Polytope::add examines them
     uint8_t mv_dst[OCAP];      // swap_remove: tail face mv_src lands in hole mv_dst
     uint8_t mv_src[OCAP];
+    uint64_t mbar;             // tracks the bulk copy that resumes a polytope from the previous tier
 };
 
 template <class PS>
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     const float epa_tol = A.settings.epa_tolerance;
     // the adjacency matrix is kept all-zero between iterations
     for (int k = gl; k < VCAP * AW; k += G) P.adj[k] = 0u;
+    uint32_t resume_phase = 0;  // parity of the group's mbarrier
+    if (RF > 0 && gl == 0) mbar_init(&P.mbar, 1);
     __syncwarp(gmask);
 
     int state = S_FETCH;
@@ -260,13 +264,19 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                     nf = (int)__float_as_uint(h.x);
                     nv = (int)__float_as_uint(h.y);
                     it = __float_as_uint(h.z);
-                    for (int j = gl; j < nf; j += G) P.fnd[j] = rec[DL::FND + j];
-                    for (int j = gl; j < nv; j += G) {
-                        P.pv[j] = rec[DL::PV + j];
-                        pa[j] = rec[DL::PA + j];
+                    // faces, vertices and face indices arrive as three bulk copies (TMA) tracked by
+                    // the group's mbarrier; sup_a goes from the record to this group's scratch
+                    const uint32_t b_fnd = (uint32_t)nf * 16u, b_pv = (uint32_t)nv * 16u,
+                                   b_idx = ((uint32_t)nf * 4u + 15u) & ~15u;
+                    if (gl == 0) {
+                        mbar_arrive_expect_tx(&P.mbar, b_fnd + b_pv + b_idx);
+                        bulk_load(P.fnd, rec + DL::FND, b_fnd, &P.mbar);
+                        bulk_load(P.pv, rec + DL::PV, b_pv, &P.mbar);
+                        bulk_load(P.fidx, rec + DL::FIDX, b_idx, &P.mbar);
                     }
-                    const uint32_t* fi = reinterpret_cast<const uint32_t*>(rec + DL::FIDX);
-                    for (int j = gl; j < nf; j += G) P.fidx[j] = fi[j];
+                    for (int j = gl; j < nv; j += G) pa[j] = rec[DL::PA + j];
+                    mbar_wait(&P.mbar, resume_phase);
+                    resume_phase ^= 1u;
                 } else {
                     // Polytope::new (epa3d.rs:41-45, 129-135): the 4 simplex points ...
                     for (int j = gl; j < 8; j += G) {
@@ -514,13 +524,20 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                     if (gl == 0)
                         rec[0] = make_float4(__uint_as_float((uint32_t)nf), __uint_as_float((uint32_t)nv),
                                              __uint_as_float(it), 0.f);
-                    for (int j = gl; j < nf; j += G) rec[DL::FND + j] = P.fnd[j];
-                    for (int j = gl; j < nv; j += G) {
-                        rec[DL::PV + j] = P.pv[j];
-                        rec[DL::PA + j] = pa[j];
+                    // the polytope leaves shared memory as three bulk copies (TMA): ordinary writes
+                    // are fenced towards the async proxy first, and the elected lane waits until the
+                    // copies have read their source before the group reuses it
+                    fence_proxy_async();
+                    __syncwarp(gmask);
+                    if (gl == 0) {
+                        bulk_store(rec + DL::FND, P.fnd, (uint32_t)nf * 16u);
+                        bulk_store(rec + DL::PV, P.pv, (uint32_t)nv * 16u);
+                        bulk_store(rec + DL::FIDX, P.fidx, ((uint32_t)nf * 4u + 15u) & ~15u);
+                        bulk_commit();
                     }
-                    uint32_t* fi = reinterpret_cast<uint32_t*>(rec + DL::FIDX);
-                    for (int j = gl; j < nf; j += G) fi[j] = P.fidx[j];
+                    for (int j = gl; j < nv; j += G) rec[DL::PA + j] = pa[j];
+                    if (gl == 0) bulk_wait_read();
+                    __syncwarp(gmask);
                 }
                 if (gl == 0) over_list[h] = pair | (room ? OVER_RESUME : 0u);
             } else if (gl == 0) {
