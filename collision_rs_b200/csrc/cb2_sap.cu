@@ -46,7 +46,7 @@ struct sap_workspace {
 
 sap_workspace* sap_workspace_create() {
     sap_workspace* w = new sap_workspace();
-    if (cudaMallocHost(&w->h_total, 2 * sizeof(uint64_t)) != cudaSuccess) {
+    if (cudaMallocHost(&w->h_total, 4 * sizeof(uint64_t)) != cudaSuccess) {
         delete w;
         return nullptr;
     }
@@ -372,35 +372,52 @@ __device__ __forceinline__ int box_class(const grid_params* __restrict__ G, floa
     return cnt > LARGE_CELLS ? BOX_LARGE : BOX_GRID;
 }
 
+// A sharded call (this GPU reports the pairs whose later box sits in [b_lo, b_hi)) only needs the
+// boxes that can take part in such a pair: the shard's own boxes, and the earlier ones whose sweep
+// interval reaches the shard's first box (min_s ascends with the position, so max_s[k] > min_s[b_lo]
+// is necessary for k < b_lo).  Everything else stays out of the grid: entries, cell sort, packing and
+// sweep shrink with the shard.
+__device__ __forceinline__ bool in_shard_reach(const float2* __restrict__ S, uint64_t k, uint32_t b_lo,
+                                               uint32_t b_hi, uint64_t n) {
+    if (b_lo == 0u && b_hi >= n) return true;
+    if (k >= b_hi) return false;
+    if (k >= b_lo) return true;
+    return __ldg(&S[k].y) > __ldg(&S[b_lo].x);
+}
+
 // Entries (cell, position), compacted in POSITION order through an exclusive scan of the per-box
 // cell counts: the stable sort by cell then leaves every cell's entries ascending by position.
 // The entry array holds n * SLOT_CELLS + n/4 records (the cell size covers the 99.9 % extent
 // quantile, so nearly every box touches <= 2 x 2 cells); a box that does not fit is treated as large.
-__global__ void __launch_bounds__(256) k_grid_count(const float2* __restrict__ U,
+__global__ void __launch_bounds__(256) k_grid_count(const float2* __restrict__ S, const float2* __restrict__ U,
                                                    const float2* __restrict__ V, uint64_t n,
                                                    const grid_params* __restrict__ G,
-                                                   uint32_t* __restrict__ counts) {
+                                                   uint32_t* __restrict__ counts, uint32_t b_lo, uint32_t b_hi) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     cell_range r;
     int cnt;
     const int cls = box_class(G, __ldg(U + k), __ldg(V + k), r, cnt);
-    counts[k] = cls == BOX_GRID ? (uint32_t)cnt : 0u;
+    counts[k] = (cls == BOX_GRID && in_shard_reach(S, k, b_lo, b_hi, n)) ? (uint32_t)cnt : 0u;
 }
 
-__global__ void __launch_bounds__(256) k_grid_emit(const float2* __restrict__ U,
+__global__ void __launch_bounds__(256) k_grid_emit(const float2* __restrict__ S, const float2* __restrict__ U,
                                                   const float2* __restrict__ V, uint64_t n,
                                                   grid_params* __restrict__ G,
                                                   const uint32_t* __restrict__ offs, uint64_t n_entries,
                                                   uint32_t* __restrict__ ecell,
                                                   uint32_t* __restrict__ epos,
-                                                  uint32_t* __restrict__ large_list) {
+                                                  uint32_t* __restrict__ large_list, uint32_t b_lo,
+                                                  uint32_t b_hi) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     cell_range r;
     int cnt;
     const int cls = box_class(G, __ldg(U + k), __ldg(V + k), r, cnt);
     if (cls == BOX_DEAD) return;
+    // (a large box is listed even outside the shard's reach: k_sap_large filters its pairs, and its
+    //  backward pass must recognise which partners are large themselves)
+    if (cls == BOX_GRID && !in_shard_reach(S, k, b_lo, b_hi, n)) return;
     const uint64_t o = offs[k];
     if (cls == BOX_LARGE || o + (uint64_t)cnt > n_entries) {
         large_list[atomicAdd(&G->n_large, 1u)] = (uint32_t)k;
@@ -685,6 +702,16 @@ __global__ void __launch_bounds__(256) k_sap_large(const float2* __restrict__ S,
                     emit_pair(G, keys, cap, pos_bits, (uint32_t)q, p, remap, seg_cnt);
             }
         }
+    }
+}
+
+// entries the grid really holds (the exclusive scan's total, clamped to the array): read back by the
+// host so that the cell sort, the packing and the sweep run over them and not over the capacity
+__global__ void k_grid_entries(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offs, uint64_t n,
+                               uint64_t capacity, uint64_t* __restrict__ h_out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint64_t t = (uint64_t)offs[n - 1] + counts[n - 1];
+        *h_out = t < capacity ? t : capacity;
     }
 }
 
@@ -992,14 +1019,20 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         k_sap_gather<<<nblk(n, 256), 256, 0, st>>>(boxes, n, axis, perm_out, S, U, V);
         k_grid_stats<<<592, 256, 0, st>>>(U, V, n, G);
         k_grid_params<<<1, 32, 0, st>>>(G, n);
-        k_grid_count<<<nblk(n, 256), 256, 0, st>>>(U, V, n, G, cnts);
+        k_grid_count<<<nblk(n, 256), 256, 0, st>>>(S, U, V, n, G, cnts, b_lo, b_hi);
         tb = scan_tmp;
         SAP_CK(cub::DeviceScan::ExclusiveSum(tmp, tb, cnts, offs, (int64_t)n, st));
-        k_grid_emit<<<nblk(n, 256), 256, 0, st>>>(U, V, n, G, offs, ne, c0, p0, large);
+        k_grid_entries<<<1, 32, 0, st>>>(cnts, offs, n, ne, w->h_total + 2);
+        k_grid_emit<<<nblk(n, 256), 256, 0, st>>>(S, U, V, n, G, offs, ne, c0, p0, large, b_lo, b_hi);
+        ++*launches;
+        // one short host wait buys the entry count: the array is sized for 4.25 entries per box, the
+        // grid of cfg 4 holds 1.6 (and a shard a fraction of that)
+        SAP_CK(cudaStreamSynchronize(st));
+        const uint64_t nu = w->h_total[2] ? w->h_total[2] : 1;
         tb = sort2;
-        SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, p0, p1, (int64_t)ne, 0, cell_bits, st));
-        k_grid_pack<<<nblk(ne, 256), 256, 0, st>>>(S, U, V, c1, p1, ne, G, eS, eU, eV);
-        k_grid_sweep<<<nblk(ne, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, ne, G, pk, kcap, pos_bits, remap,
+        SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, p0, p1, (int64_t)nu, 0, cell_bits, st));
+        k_grid_pack<<<nblk(nu, 256), 256, 0, st>>>(S, U, V, c1, p1, nu, G, eS, eU, eV);
+        k_grid_sweep<<<nblk(nu, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, nu, G, pk, kcap, pos_bits, remap,
                                                       b_lo, b_hi, seg_arg);
         k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, offs, ne, G, pk, kcap, pos_bits, remap, b_lo,
                                          b_hi, seg_arg);
