@@ -228,8 +228,16 @@ def kernel_rooflines(n, stage_ms, flops_pair, flops_gjk_pair, extra, fp32_peak, 
 
 
 def profiled_traffic(n):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
-    `ncu --set full` capture (profiles/r1_traffic.json: bytes per pair), scaled to this launch."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (the three k_epa tier
+    launches of one cfg-3 pass) from the committed ncu counters, per pair, scaled to this launch
+    (profiles/r2_kernels.json, taken at 4 M pairs; round 1's r1_traffic.json as a fallback)."""
+    p2 = os.path.join(ROOT, "profiles", "r2_kernels.json")
+    if os.path.exists(p2):
+        d = json.load(open(p2))
+        k = [r for name, r in d.get("kernels", {}).items() if name.startswith("cfg3:k_epa")]
+        units = d.get("units", {}).get("cfg3")
+        if k and units:
+            return sum(r["dram_bytes"] for r in k) / units * n
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if not os.path.exists(p):
         return None
