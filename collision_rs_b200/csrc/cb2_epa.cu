@@ -34,7 +34,7 @@
 #ifndef CB2_T0_F  // build-time overrides for A/B experiments (tools/ab_variants.sh)
 #define CB2_T0_F 40
 #define CB2_T0_V 24
-#define CB2_T0_O 24
+#define CB2_T0_O 20   // (20: the record is then 1392 bytes = -16 mod 128, see group_layout)
 #endif
 #ifndef CB2_EPA_MIN_BLOCKS
 #define CB2_EPA_MIN_BLOCKS 20
@@ -66,6 +66,22 @@ struct poly_smem {
     uint8_t mv_dst[OCAP];      // swap_remove: tail face mv_src lands in hole mv_dst
     uint8_t mv_src[OCAP];
     uint64_t mbar;             // tracks the bulk copy that resumes a polytope from the previous tier
+};
+
+// Where the groups of a warp keep their polytopes.  ncu (round 2, 4 M pairs) showed 60 % of tier 0's
+// shared-memory wavefronts to be bank-conflict replays: the records were laid out back to back with
+// a stride that is a multiple of 128 bytes, so the same field of every group sat in the same banks.
+// A stride of -16 (mod 128) bytes for 8 groups — 32 (mod 128) for 4 — spreads a unit-stride 32-bit
+// access of all groups over all 32 banks; and with 8 groups, the two groups that share a
+// quarter-warp (which is what a 128-bit access is split into) are given slots 4 apart, i.e. 64
+// bytes apart modulo 128, so their float4 reads do not collide either.
+template <class PS, int NG>
+struct group_layout {
+    static constexpr size_t TARGET = NG == 8 ? 112 : (NG == 4 ? 32 : 0);
+    static constexpr size_t STRIDE = NG >= 4 ? sizeof(PS) + ((TARGET + 128 - sizeof(PS) % 128) % 128) : sizeof(PS);
+    static constexpr size_t BYTES = STRIDE * NG;
+    static_assert(STRIDE % 16 == 0, "float4 members");
+    CB2_DI static int slot(int gw) { return NG == 8 ? ((gw & 1) * 4 + (gw >> 1)) : gw; }
 };
 
 template <class PS>
@@ -188,7 +204,8 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     const bool right = gl & 1;  // this lane evaluates the right shape's support
     const narrow_args& A = C.A;
     const shape_table T = table_of(A.T);
-    PS& P = reinterpret_cast<PS*>(smem)[gw];
+    using GL = group_layout<PS, NG>;
+    PS& P = *reinterpret_cast<PS*>(reinterpret_cast<char*>(smem) + (size_t)GL::slot(gw) * GL::STRIDE);
     float4* pa = C.W.pa + ((size_t)blockIdx.x * NG + gw) * VCAP;
 
     const uint32_t* list;
@@ -667,7 +684,7 @@ constexpr int T2_G = 8, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst ca
 template <int G, int F, int V, int O, int RF, int RV>
 static int epa_blocks(int sm_count) {
     auto kern = k_epa<G, F, V, O, RF, RV>;
-    const size_t smem = (size_t)(32 / G) * sizeof(poly_smem<F, V, O>);
+    const size_t smem = group_layout<poly_smem<F, V, O>, 32 / G>::BYTES;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1)
@@ -687,7 +704,7 @@ static int lane_blocks(int sm_count) {
 
 template <int G, int F, int V, int O, int RF, int RV>
 static cudaError_t launch_tier(const epa_args& C, int sm_count, cudaStream_t st) {
-    const size_t smem = (size_t)(32 / G) * sizeof(poly_smem<F, V, O>);
+    const size_t smem = group_layout<poly_smem<F, V, O>, 32 / G>::BYTES;
     k_epa<G, F, V, O, RF, RV><<<epa_blocks<G, F, V, O, RF, RV>(sm_count), 32, smem, st>>>(C);
     return cudaGetLastError();
 }
