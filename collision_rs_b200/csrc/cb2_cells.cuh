@@ -173,4 +173,63 @@ CB2_DI f3 poly_local_support(const poly_tables& T, const poly_ref& s, float R, f
     return best;
 }
 
+// The same query answered by NP lanes that hold the same shape and direction (the EPA kernel's
+// groups keep 2 or 4 lanes per side): the cell's list is cut into chunks of four candidates and
+// lane `part` scans chunks [part*q, (part+1)*q), q = ceil(chunks / NP) — a contiguous run, so every
+// candidate of a lower part precedes every candidate of a higher one.  The caller combines the
+// parts' (best_dot, best) with "greater dot wins, equal dots go to the lower part", which is the
+// full scan's first-strict-max rule.  `whole` is set when this lane answered the whole query on
+// its own (no cells, full scan, extension list): all parts then hold the same answer.
+template <uint32_t NP>
+CB2_DI f3 poly_local_support_part(const poly_tables& T, const poly_ref& s, float R, f3 d, uint32_t part,
+                                  float& best_dot, bool& whole) {
+    const float4* __restrict__ verts = T.verts + s.voff;
+    const uint32_t N = s.cfg & 0xFFu;
+    const bool wide = (s.cfg >> 8) & 1u;
+    whole = true;
+    best_dot = 0.0f;
+    if (N == 0) return poly_full_scan(verts, s.vcnt, d);
+    float m;
+    const uint32_t cell = cell_index(d, N, m);
+    const float scale = m * R;
+    if (!(scale >= 1.0e-30f && scale <= 1.0e30f)) return poly_full_scan(verts, s.vcnt, d);
+    const uint4 rec = __ldg(T.cells + s.cell_off + cell);
+    const uint32_t bits = wide ? 16u : 8u;
+    const uint32_t mask = wide ? 0xFFFFu : 0xFFu;
+    const uint32_t cnt = rec.x & mask;
+    if (cnt > (wide ? CELL_INLINE16 : CELL_INLINE8)) {
+        if (cnt == (mask & (0xFF00u | CELL_FULL))) return poly_full_scan(verts, s.vcnt, d);
+        return poly_ext_scan(verts, T.ext + rec.y, rec.z, d);
+    }
+    whole = false;
+    const uint32_t x = __funnelshift_r(rec.x, rec.y, bits), y = __funnelshift_r(rec.y, rec.z, bits),
+                   z = __funnelshift_r(rec.z, rec.w, bits), w = rec.w >> bits;
+    const uint32_t nch = (cnt + 3u) >> 2;
+    const uint32_t q = (nch + NP - 1u) / NP;
+    uint32_t c = part * q;
+    const uint32_t c_end = min(c + q, nch);
+    f3 best = zero3();
+    best_dot = -INFINITY;
+    for (; c < c_end; ++c) {
+        uint32_t i0, i1, i2, i3;
+        if (!wide) {
+            const uint32_t u = c == 0u ? x : (c == 1u ? y : (c == 2u ? z : w));
+            i0 = u & 0xFFu; i1 = (u >> 8) & 0xFFu; i2 = (u >> 16) & 0xFFu; i3 = u >> 24;
+        } else {
+            const uint32_t u = c == 0u ? x : z, v = c == 0u ? y : w;
+            i0 = u & 0xFFFFu; i1 = u >> 16; i2 = v & 0xFFFFu; i3 = v >> 16;
+        }
+        const float4 v0 = __ldg(verts + i0), v1 = __ldg(verts + i1);
+        const float4 v2 = __ldg(verts + i2), v3 = __ldg(verts + i3);
+        const uint32_t rem = cnt - 4u * c;
+        const float d0 = dot(mk3(v0.x, v0.y, v0.z), d), d1 = dot(mk3(v1.x, v1.y, v1.z), d);
+        const float d2 = dot(mk3(v2.x, v2.y, v2.z), d), d3 = dot(mk3(v3.x, v3.y, v3.z), d);
+        if (d0 > best_dot) { best_dot = d0; best = mk3(v0.x, v0.y, v0.z); }
+        if (rem > 1u && d1 > best_dot) { best_dot = d1; best = mk3(v1.x, v1.y, v1.z); }
+        if (rem > 2u && d2 > best_dot) { best_dot = d2; best = mk3(v2.x, v2.y, v2.z); }
+        if (rem > 3u && d3 > best_dot) { best_dot = d3; best = mk3(v3.x, v3.y, v3.z); }
+    }
+    return best;
+}
+
 }  // namespace cb2

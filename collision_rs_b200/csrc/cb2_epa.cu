@@ -36,6 +36,12 @@
 #define CB2_T0_V 24
 #define CB2_T0_O 20   // (20: the record is then 1392 bytes = -16 mod 128, see group_layout)
 #endif
+#ifndef CB2_OPT_SPLIT   // a polyhedron's support candidates are split over the lanes of a side
+#define CB2_OPT_SPLIT 1
+#endif
+#ifndef CB2_OPT_FOLD    // closest_face_to_origin folded into the visibility pass and Face::new: bit-identical,
+#define CB2_OPT_FOLD 0  // but no faster (tier 0 14.03 ms with, 13.95 ms without: three more live registers)
+#endif
 #ifndef CB2_EPA_MIN_BLOCKS
 #define CB2_EPA_MIN_BLOCKS 20
 #endif
@@ -92,7 +98,7 @@ CB2_DI f3 ps_pv(const PS& P, uint32_t i) {
 
 // Face::new_impl (epa3d.rs:189-199) into slot
 template <class PS>
-CB2_DI void ps_face_new(PS& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
+CB2_DI float ps_face_new(PS& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
     const f3 va = ps_pv(P, a);
     const f3 ab = ps_pv(P, b) - va;
     const f3 ac = ps_pv(P, c) - va;
@@ -100,6 +106,7 @@ CB2_DI void ps_face_new(PS& P, int slot, uint32_t a, uint32_t b, uint32_t c) {
     const float dist = dot(n, va);
     P.fnd[slot] = make_float4(n.x, n.y, n.z, dist);
     P.fidx[slot] = a | (b << 8) | (c << 16);
+    return dist;
 }
 
 // fixed-size bit mask in registers (fully unrolled accessors)
@@ -127,6 +134,13 @@ struct bitmask {
         for (int k = 0; k < W; ++k)
             if ((i >> 5) == k) w[k] &= ~(1u << (i & 31));
     }
+    CB2_DI bool any() const {
+        uint32_t v = 0u;
+#pragma unroll
+        for (int k = 0; k < W; ++k) v |= w[k];
+        return v != 0u;
+    }
+    CB2_DI int first() const { return next(0); }  // lowest set bit (any() must hold)
     // lowest set bit at position >= from, or -1
     CB2_DI int next(int from) const {
         int r = -1;
@@ -150,6 +164,8 @@ struct bitmask<2> {
     CB2_DI void or_bits(int pos, uint32_t bits) { m |= (unsigned long long)bits << pos; }
     CB2_DI bool test(int i) const { return (m >> i) & 1ull; }
     CB2_DI void reset(int i) { m &= ~(1ull << i); }
+    CB2_DI bool any() const { return m != 0ull; }
+    CB2_DI int first() const { return __ffsll((long long)m) - 1; }
     CB2_DI int next(int from) const {
         const unsigned long long v = from < 64 ? (m >> from) << from : 0ull;
         return v ? __ffsll((long long)v) - 1 : -1;
@@ -171,6 +187,8 @@ struct bitmask<4> {
         if (i < 64) lo &= ~(1ull << i);
         else hi &= ~(1ull << (i - 64));
     }
+    CB2_DI bool any() const { return (lo | hi) != 0ull; }
+    CB2_DI int first() const { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
     CB2_DI int next(int from) const {
         if (from < 64) {
             const unsigned long long v = (lo >> from) << from;
@@ -241,7 +259,8 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     xform xf = make_xform(make_float4(1.f, 1.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
     f3 d = zero3();
     uint32_t it = 0;
-    int nf = 0, nv = 0, best_face = 0;
+    int nf = 0, nv = 0;
+    int best_face = -1;  // < 0: closest_face_to_origin has to scan (after a fetch, a resume, or a tie)
 
     for (;;) {
         // ================= FETCH (divergent: only groups that finished) ================================
@@ -249,6 +268,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
             uint32_t k = 0;
             if (gl == 0) k = atomicAdd(cursor, 1u);
             k = __shfl_sync(gmask, k, gw * G);
+            best_face = -1;
             if (k >= count) {
                 state = S_EXIT;
                 nf = 0;
@@ -319,39 +339,49 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         const bool run = state == S_RUN;
 
         // ================= closest_face_to_origin (epa3d.rs:137-145) ====================================
-        // first strictly smallest distance; a NaN at index 0 sticks.  Its normal is the next
-        // support direction.
+        // first strictly smallest distance; a NaN at index 0 sticks.  Its normal is the next support
+        // direction.  Only groups without a tracked closest face scan (fresh or resumed polytopes,
+        // and the rare exact tie): otherwise the visibility pass and Face::new of the previous
+        // iteration have already seen every distance of the polytope (see below).
         {
-            const int nf_max = __reduce_max_sync(0xffffffffu, nf);
-            float bd = INFINITY;
-            uint32_t bi = 0xFFFFFFFFu;
-            CB2_UNROLL(CB2_U_CLOSEST)
-            for (int f = gl; f < nf_max; f += G) {
-                if (f < nf) {
-                    float dd = P.fnd[f].w;
-                    if (dd != dd) dd = INFINITY;  // NaN never compares smaller
-                    if (dd < bd) { bd = dd; bi = (uint32_t)f; }  // f ascends: ties keep the first
+            const bool need = run && best_face < 0;
+            const int nf_max = __reduce_max_sync(0xffffffffu, need ? nf : 0);
+            if (nf_max > 0) {
+                float bd = INFINITY;
+                uint32_t bi = 0xFFFFFFFFu;
+                CB2_UNROLL(CB2_U_CLOSEST)
+                for (int f = gl; f < nf_max; f += G) {
+                    if (need && f < nf) {
+                        float dd = P.fnd[f].w;
+                        if (dd != dd) dd = INFINITY;  // NaN never compares smaller
+                        if (dd < bd) { bd = dd; bi = (uint32_t)f; }  // f ascends: ties keep the first
+                    }
                 }
-            }
 #pragma unroll
-            for (int off = G / 2; off >= 1; off >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, bd, off);
-                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (ob < bd || (ob == bd && oi < bi)) { bd = ob; bi = oi; }
-            }
-            if (run) {
-                const float d0 = P.fnd[0].w;
-                best_face = (d0 != d0 || bi == 0xFFFFFFFFu) ? 0 : (int)bi;
+                for (int off = G / 2; off >= 1; off >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, bd, off);
+                    const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob < bd || (ob == bd && oi < bi)) { bd = ob; bi = oi; }
+                }
+                if (need) {
+                    const float d0 = P.fnd[0].w;
+                    best_face = (d0 != d0 || bi == 0xFFFFFFFFu) ? 0 : (int)bi;
+                }
             }
         }
         const float4 fb = run ? P.fnd[best_face] : make_float4(0.f, 0.f, 0.f, 0.f);
         const f3 n = mk3(fb.x, fb.y, fb.z);
 
         // ================= SupportPoint::from_minkowski(n), minkowski/mod.rs:39-60 ======================
-        // even lanes evaluate the left shape, odd lanes the right one
+        // even lanes evaluate the left shape, odd lanes the right one; the G/2 lanes of a side share
+        // the candidate list of a polyhedron's support cell (support_point_split)
         f3 sup_v, sup_a;
         {
+#if CB2_OPT_SPLIT
+            const f3 w = support_point_split<G / 2, 2>(T, sh, xf, right ? -n : n, (uint32_t)gl >> 1);
+#else
             const f3 w = support_point(T, sh, xf, right ? -n : n);
+#endif
             const f3 o = mk3(__shfl_xor_sync(0xffffffffu, w.x, 1), __shfl_xor_sync(0xffffffffu, w.y, 1),
                              __shfl_xor_sync(0xffffffffu, w.z, 1));
             sup_a = right ? o : w;
@@ -367,9 +397,16 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         const bool add = run && !hung && !conv;
 
         // ================= Polytope::add (epa3d.rs:147-175) =============================================
-        // (1) visibility of every face -> bit mask (uniform across the group)
+        // (1) visibility of every face -> bit mask (uniform across the group).  The same pass tracks
+        //     the smallest distance among the faces that stay (cd, ci per lane): together with the
+        //     distances Face::new computes below that is every face of the next polytope, so the next
+        //     closest_face_to_origin is their plain minimum — unless two distances are exactly equal
+        //     or one is NaN (ctie), where Vec order decides and the scan above runs instead.
         bitmask<FW> vis;
         vis.clear();
+        float cd = INFINITY;
+        int ci = -1;
+        bool ctie = false;
         {
             const int nf_max = __reduce_max_sync(0xffffffffu, add ? nf : 0);
             CB2_UNROLL(CB2_U_VIS)
@@ -380,6 +417,12 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                     const float4 fn = P.fnd[f];
                     const uint32_t idx = P.fidx[f];
                     v = dot(mk3(fn.x, fn.y, fn.z), sup_v - ps_pv(P, idx & 255u)) > 0.0f;
+#if CB2_OPT_FOLD
+                    if (!v) {
+                        if (fn.w < cd) { cd = fn.w; ci = f; }
+                        else if (!(fn.w > cd)) ctie = true;
+                    }
+#endif
                 }
                 const uint32_t bits = (__ballot_sync(0xffffffffu, v) >> (gw * G)) & gbits;
                 vis.or_bits(f0, bits);
@@ -388,18 +431,22 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         // (2) the swap_remove sweep as a two-pointer walk over the mask: `i` climbs from the front,
         //     `len` shrinks from the back; a visible face at slot i is examined, then the tail face
         //     dropped into slot i is examined next, and so on.  One walk step per warp iteration.
-        int len = nf, nvis = 0, nmv = 0;
+        //     Examined faces leave the mask, so the next `i` is simply its lowest bit (everything
+        //     below the old i and everything from len up has been examined or was never visible).
+        //     Lane k of the group keeps the k-th examined face (`mine`) for the horizon passes.
+        int len = nf, nvis = 0, nmv = 0, mine = 0;
         bool overflow = false;
         {
-            int i = vis.next(0);
+            bool walking = add && vis.any();
+            int i = walking ? vis.first() : 0;
             int cur = i;
-            bool walking = add && i >= 0;
             while (__any_sync(0xffffffffu, walking)) {
                 if (walking) {
                     if (nvis >= OCAP) {
                         overflow = true;
                         walking = false;
                     } else {
+                        if (nvis == gl) mine = cur;
                         if (gl == 0) P.order[nvis] = (uint8_t)cur;
                         ++nvis;
                         vis.reset(cur);
@@ -413,10 +460,11 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                                 P.mv_dst[nmv] = (uint8_t)i;
                                 P.mv_src[nmv] = (uint8_t)len;
                             }
+                            if (ci == len) ci = i;  // the tracked face moves with the swap
                             ++nmv;
-                            i = vis.next(i + 1);
+                            walking = vis.any();
+                            i = walking ? vis.first() : 0;
                             cur = i;
-                            walking = i >= 0 && i < len;
                         }
                     }
                 }
@@ -429,9 +477,11 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         const bool edges = add && !overflow;
         const int nvis_max = __reduce_max_sync(0xffffffffu, edges ? nvis : 0);
         bool dup = false;
-        for (int k = gl; k < nvis_max; k += G) {
+        const uint32_t idx_mine = (edges && gl < nvis) ? P.fidx[mine] : 0u;
+        for (int k0 = 0; k0 < nvis_max; k0 += G) {
+            const int k = k0 + gl;
             if (edges && k < nvis) {
-                const uint32_t idx = P.fidx[P.order[k]];
+                const uint32_t idx = k0 == 0 ? idx_mine : P.fidx[P.order[k]];
                 const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
                 const uint32_t o0 = atomicOr(&P.adj[v0 * AW + (v1 >> 5)], 1u << (v1 & 31));
                 const uint32_t o1 = atomicOr(&P.adj[v1 * AW + (v2 >> 5)], 1u << (v2 & 31));
@@ -445,7 +495,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
             const int k = k0 + gl;
             uint32_t keep = 0, v0 = 0, v1 = 0, v2 = 0;
             if (edges && k < nvis) {
-                const uint32_t idx = P.fidx[P.order[k]];
+                const uint32_t idx = k0 == 0 ? idx_mine : P.fidx[P.order[k]];
                 v0 = idx & 255u; v1 = (idx >> 8) & 255u; v2 = (idx >> 16) & 255u;
                 keep = (~(P.adj[v1 * AW + (v0 >> 5)] >> (v0 & 31)) & 1u) |
                        ((~(P.adj[v2 * AW + (v1 >> 5)] >> (v1 & 31)) & 1u) << 1) |
@@ -463,9 +513,10 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         dup = (__ballot_sync(0xffffffffu, dup) & gmask) != 0u;
         __syncwarp();
         // (4) clear the adjacency bits again
-        for (int k = gl; k < nvis_max; k += G) {
+        for (int k0 = 0; k0 < nvis_max; k0 += G) {
+            const int k = k0 + gl;
             if (edges && k < nvis) {
-                const uint32_t idx = P.fidx[P.order[k]];
+                const uint32_t idx = k0 == 0 ? idx_mine : P.fidx[P.order[k]];
                 const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
 #pragma unroll
                 for (int q = 0; q < AW; ++q) {
@@ -498,10 +549,30 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
             for (int k = gl; k < ne_max; k += G) {
                 if (grow && k < ne) {
                     const uint32_t e = P.elist[k];
-                    ps_face_new(P, len + k, (uint32_t)nv, e & 255u, e >> 8);
+                    const float dist = ps_face_new(P, len + k, (uint32_t)nv, e & 255u, e >> 8);
+#if CB2_OPT_FOLD
+                    if (dist < cd) { cd = dist; ci = len + k; }
+                    else if (!(dist > cd)) ctie = true;
+#else
+                    (void)dist;
+#endif
                 }
             }
         }
+#if CB2_OPT_FOLD
+        // the group's minimum of the tracked distances = the next closest face, unless tied
+#pragma unroll
+        for (int off = G / 2; off >= 1; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, cd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, ci, off);
+            if (ob < cd) { cd = ob; ci = oi; }
+            else if (ob == cd && (oi | ci) >= 0) ctie = true;
+        }
+        const bool gtie = (__ballot_sync(0xffffffffu, ctie) & gmask) != 0u;
+        const int next_best = (grow && !gtie) ? ci : -1;
+#else
+        const int next_best = -1;
+#endif
         uint8_t result = ST_NONE;
         if (grow) {
             ++nv;
@@ -564,6 +635,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
             state = S_FETCH;
             nf = 0;
         }
+        best_face = next_best;
         __syncwarp();
     }
 }

@@ -162,6 +162,46 @@ CB2_DI f3 support_point(const shape_table& T, const shape& s, const xform& t, f3
     if (s.kind == K_PARTICLE) return transform_point(t, zero3());
     return transform_point(t, local_support(T, s, inverse_transform_vector(t, dir)));
 }
+// support_point for kernels in which NP lanes (lane ^ STEP, lane ^ 2 STEP, ...) hold the same shape,
+// transform and direction (the EPA groups: even lanes carry the left shape, odd lanes the right
+// one, so STEP = 2).  A polyhedron's candidate list is split over those lanes
+// (poly_local_support_part) and the parts are combined by a butterfly: greater dot wins, equal
+// dots go to the lower part — the reference's first-strict-max over the whole list.  Must be
+// called by the whole warp (the shuffles use the full mask); `part` = this lane's rank among its NP.
+template <uint32_t NP, uint32_t STEP>
+CB2_DI f3 support_point_split(const shape_table& T, const shape& s, const xform& t, f3 dir, uint32_t part) {
+    f3 loc = zero3();
+    float bd = 0.0f;
+    bool whole = true;
+    if (s.kind == K_POLY) {
+        loc = poly_local_support_part<NP>(T.poly, s.poly, s.h.x, inverse_transform_vector(t, dir), part, bd, whole);
+    } else if (s.kind != K_PARTICLE) {
+        const f3 d = inverse_transform_vector(t, dir);
+        if (s.kind == K_CUBOID) loc = cuboid_local_support(s.h, d);
+        else if (s.kind == K_SPHERE) loc = sphere_local_support(s.h.x, d);
+        else if (s.kind == K_POLY_HE) {
+            const float4 r = poly_hill_climb(T.poly.verts + s.poly.voff, s.poly.vcnt, d);
+            if (r.w != 0.0f) s.hang = 1u;
+            loc = mk3(r.x, r.y, r.z);
+        } else loc = other_local_support(s.kind, s.h, d);
+    }
+    if (NP > 1) {
+#pragma unroll
+        for (uint32_t k = 1; k < NP; k <<= 1) {
+            const uint32_t off = k * STEP;
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const float ox = __shfl_xor_sync(0xffffffffu, loc.x, off);
+            const float oy = __shfl_xor_sync(0xffffffffu, loc.y, off);
+            const float oz = __shfl_xor_sync(0xffffffffu, loc.z, off);
+            const bool upper = (part & k) != 0u;
+            if (!whole && (od > bd || (upper && od == bd))) {
+                bd = od;
+                loc = mk3(ox, oy, oz);
+            }
+        }
+    }
+    return transform_point(t, loc);
+}
 // does support_point call inverse_transform_vector(..).unwrap() (the zero-scale panic site)?
 CB2_DI bool needs_inverse(uint32_t kind) { return kind != K_PARTICLE; }
 CB2_DI bool is_curved(uint32_t kind) { return kind == K_SPHERE || kind == K_CYLINDER || kind == K_CAPSULE; }

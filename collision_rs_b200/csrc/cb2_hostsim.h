@@ -43,6 +43,8 @@ static inline bool __all_sync(unsigned, bool p) { return p; }
 static inline bool __any_sync(unsigned, bool p) { return p; }
 template <class T>
 static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
     const uint32_t o = *p;
