@@ -49,7 +49,7 @@ struct cb2_ctx {
     uint64_t ws2_cap[CB2_NS_MAX] = {};
     // host-API staging
 #ifndef CB2_NS
-#define CB2_NS 4
+#define CB2_NS 8
 #endif
     static constexpr int NS = CB2_NS;  // host-API pipeline depth (streams / staging buffers)
     cudaStream_t stream[NS] = {};
@@ -57,6 +57,14 @@ struct cb2_ctx {
     // host-API pipeline events per staging buffer: inputs landed | kernels finished | buffer free
     cudaEvent_t ev_in[NS] = {}, ev_k[NS] = {}, ev_free[NS] = {};
     cudaEvent_t ev_tail[NS] = {};  // tier 0 finished -> the tail stream may start the later tiers
+    // GJK-ahead pipeline: GJK of a chunk done | the chunk's workspace slot free again
+    cudaEvent_t ev_front[NS] = {}, ev_wsfree[NS] = {};
+    cudaStream_t s_front = nullptr;  // high-priority stream of the GJK stages
+    cudaStream_t s_tail[2] = {nullptr, nullptr};  // EPA tiers 1, 2 and the second chance (above tier 0's priority)
+    int tail_prio = 0;               // CB2_TAIL_PRIO=1: the later tiers on their own streams, above tier 0's
+                                     // priority (measured: 23.1 against 21.0 ms per 4 M-pair call — their
+                                     // latency-bound tails then hold SM resources tier 0 would use)
+    int ahead = 1;                   // CB2_AHEAD=0: every stage of a chunk on the chunk's stream
     cudaStream_t s_in = nullptr, s_out = nullptr;  // the pipeline's copy-in / copy-out streams
     int n_cstreams = 3;  // compute streams the pipeline rotates over (CB2_NC overrides, <= NS)
     bool ramp = true;  // short chunks at both ends of a batch (CB2_RAMP=0 disables)
@@ -93,7 +101,7 @@ struct cb2_ctx {
     cudaEvent_t stage_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t stage_stream = nullptr;
     bool stage_valid = false;
-    uint64_t chunk_pairs = 1u << 19;  // host-API pipeline granularity (CB2_CHUNK_PAIRS overrides)
+    uint64_t chunk_pairs = 3u << 18;  // host-API pipeline granularity (CB2_CHUNK_PAIRS overrides)
     bool has_poly = false;
     bool legacy_epa = false;  // CB2_LEGACY_EPA=1: thread-per-pair EPA in local memory (A/B testing)
     bool no_cells = false;    // CB2_NO_CELLS=1: polyhedron support by full vertex scan (A/B testing)
@@ -200,6 +208,10 @@ int cb2_create(int device, cb2_ctx** out) {
         if (e4 && std::atoi(e4) >= 1 && std::atoi(e4) <= cb2_ctx::NS) c->n_cstreams = std::atoi(e4);
         const char* e5 = std::getenv("CB2_RAMP");
         if (e5 && e5[0] == '0') c->ramp = false;
+        const char* e6 = std::getenv("CB2_AHEAD");
+        if (e6) c->ahead = std::atoi(e6);
+        const char* e7 = std::getenv("CB2_TAIL_PRIO");
+        if (e7) c->tail_prio = std::atoi(e7);
         c->legacy_epa = e1 && e1[0] == '1';
         c->no_cells = e2 && e2[0] == '1';
     }
@@ -226,6 +238,10 @@ void cb2_destroy(cb2_ctx* c) {
         if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
         if (c->ev_tail[i]) cudaEventDestroy(c->ev_tail[i]);
+        if (c->ev_front[i]) cudaEventDestroy(c->ev_front[i]);
+        if (c->ev_wsfree[i]) cudaEventDestroy(c->ev_wsfree[i]);
+        if (i == 0 && c->s_front) cudaStreamDestroy(c->s_front);
+        if (i < 2 && c->s_tail[i]) cudaStreamDestroy(c->s_tail[i]);
         if (i == 0 && c->s_in) cudaStreamDestroy(c->s_in);
         if (i == 0 && c->s_out) cudaStreamDestroy(c->s_out);
         if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
@@ -569,8 +585,10 @@ static int ensure_retry(cb2_ctx* c, int slot) {
     return CB2_OK;
 }
 
+// phase: 0 = the whole operation; the GJK-ahead host pipeline issues FullResolution intersections in
+// two parts on two streams: 1 = counters + GJK stage, 2 = EPA tiers + second chance
 static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A,
-                           cudaStream_t st, int ws_slot, cudaStream_t tail);
+                           cudaStream_t st, int ws_slot, cudaStream_t tail, int phase);
 
 static void mark_stage(cb2_ctx* c, int k, cudaStream_t st) {
     if (c->stage_timing && c->stage_ev[k]) cudaEventRecord(c->stage_ev[k], st);
@@ -580,10 +598,11 @@ static void mark_stage(cb2_ctx* c, int k, cudaStream_t st) {
 // their own, so that the next chunk on `st` does not queue behind a long tier-2 tail); by default
 // everything is issued on `st`.
 static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, cudaStream_t st,
-                     int ws_slot = 0, cudaStream_t tail = nullptr) {
+                     int ws_slot = 0, cudaStream_t tail = nullptr, int phase = 0) {
     if (!tail) tail = st;
-    int rc = launch_op_inner(c, op, strategy, A, st, ws_slot, tail);
+    int rc = launch_op_inner(c, op, strategy, A, st, ws_slot, tail, phase);
     if (rc || !((op == OP_INTERSECTION && strategy == CB2_FULL_RESOLUTION) || op == OP_MANIFOLD)) return rc;
+    if (phase == 1) return CB2_OK;
     if (std::getenv("CB2_NO_RETRY")) return CB2_OK;  // diagnosis: leave CB2_SCRATCH_OVERFLOW visible
     // redo the rare pairs whose polytope outgrew the fast kernels' scratch
     rc = ensure_retry(c, ws_slot);
@@ -603,7 +622,7 @@ static int launch_op(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A, 
 }
 
 static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_args& A,
-                           cudaStream_t st, int ws_slot, cudaStream_t tail) {
+                           cudaStream_t st, int ws_slot, cudaStream_t tail, int phase) {
     A.T.shapes = c->d_shapes;
     A.T.verts = c->d_verts;
     A.T.cells = c->d_cells;
@@ -632,21 +651,26 @@ static int launch_op_inner(cb2_ctx* c, op_kind op, uint32_t strategy, narrow_arg
         int rc = ensure_ws(c, ws_slot, A.n);
         if (rc) return rc;
         const narrow_ws& W = c->ws[ws_slot];
-        CK(c, cudaMemsetAsync(W.EC, 0, sizeof(epa_counters), st));
         if (!c->d_queue[ws_slot]) CK(c, cudaMalloc(&c->d_queue[ws_slot], 64));
         A.queue = c->d_queue[ws_slot];
-        mark_stage(c, 0, st);
-        trace_stage("begin", st);
-        if (op == OP_MANIFOLD) {
-            A.seed_simplex = W.simplex;  // the second-chance kernel restarts from the caller's simplex
-            e = launch_manifold_seed(A, W, st);
-        } else {
-            e = launch_gjk_hits(A, full, W, c->sm_count, st);
+        e = cudaSuccess;
+        if (phase != 2) {
+            CK(c, cudaMemsetAsync(W.EC, 0, sizeof(epa_counters), st));
+            mark_stage(c, 0, st);
+            trace_stage("begin", st);
+            if (op == OP_MANIFOLD) {
+                A.seed_simplex = W.simplex;  // the second-chance kernel restarts from the caller's simplex
+                e = launch_manifold_seed(A, W, st);
+            } else {
+                e = launch_gjk_hits(A, full, W, c->sm_count, st);
+            }
+            ++c->launches;
+            mark_stage(c, 1, st);
+            trace_stage("gjk", st);
+        } else if (op == OP_MANIFOLD) {
+            A.seed_simplex = W.simplex;
         }
-        ++c->launches;
-        mark_stage(c, 1, st);
-        trace_stage("gjk", st);
-        if (e == cudaSuccess && full) {
+        if (e == cudaSuccess && full && phase != 1) {
             e = launch_epa_tier(0, A, W, c->sm_count, st);
             mark_stage(c, 2, st);
             trace_stage("tier0", st);
@@ -756,6 +780,17 @@ static int pipeline_prepare(cb2_ctx* c, size_t stage_bytes) {
         if (!c->ev_in[i]) CK(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         if (!c->ev_k[i]) CK(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
         if (!c->ev_free[i]) CK(c, cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        if (!c->ev_front[i]) CK(c, cudaEventCreateWithFlags(&c->ev_front[i], cudaEventDisableTiming));
+        if (!c->ev_wsfree[i]) CK(c, cudaEventCreateWithFlags(&c->ev_wsfree[i], cudaEventDisableTiming));
+    }
+    if (!c->s_front) {
+        int least = 0, greatest = 0;
+        CK(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(c, cudaStreamCreateWithPriority(&c->s_front, cudaStreamNonBlocking, greatest));
+        // the later tiers sit between the GJK stages and tier 0: they are short, and finishing them
+        // releases a staging buffer and a workspace slot
+        const int mid = greatest < least ? greatest + 1 : greatest;
+        for (int i = 0; i < 2; ++i) CK(c, cudaStreamCreateWithPriority(&c->s_tail[i], cudaStreamNonBlocking, mid));
     }
     return CB2_OK;
 }
@@ -780,11 +815,14 @@ static std::vector<uint64_t> pipeline_chunks(uint64_t n, uint64_t chunk, bool ra
         }
         tail = ramp[0] + ramp[1];
     }
+    // the middle in equal chunks (no short remainder chunk: every chunk pays the latency of its tiers' tails)
     uint64_t left = n - head - tail;
+    uint64_t parts = (left + chunk - 1) / chunk;
     while (left) {
-        const uint64_t m = left < chunk ? left : chunk;
+        const uint64_t m = (left + parts - 1) / parts;
         v.push_back(m);
         left -= m;
+        --parts;
     }
     if (tail) {
         v.push_back(ramp[1]);
@@ -882,6 +920,121 @@ static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut
     }
     return rc;
 }
+// The GJK-ahead variant (FullResolution intersections): a chunk's GJK stage cannot share the SMs
+// with the previous chunk's persistent EPA tier 0 (registers), so on one stream per chunk it ran in
+// that kernel's tail and the chunk's own tier 0 waited for it — 2.8 ms per 512 K pairs against 2.34 ms
+// inside one resident batch.  Here the GJK stages of all chunks go to ONE high-priority stream and
+// run as soon as their inputs have landed, i.e. one chunk ahead of the tier 0 that is about to
+// start: when tier 0 of chunk k-1 drains, GJK(k+1) and tier 0 of chunk k (whose own GJK finished a
+// chunk earlier) are both ready, the block scheduler serves the high-priority GJK blocks first and
+// tier 0's persistent blocks take what is left, then the rest.  No kernel ever waits for another
+// that still has to be scheduled behind it.  NW workspace slots (hit list, simplex hand-off,
+// dumps) rotate under their own `free` events; the staging buffers (NS) live from the copy-in to
+// the copy-out of a chunk, about five chunk periods.
+template <class FIn, class FComp, class FOut>
+static int pipeline_run_ahead(cb2_ctx* c, uint64_t n, int nw, FIn copy_in, FComp compute, FOut copy_out) {
+    static const bool trace = std::getenv("CB2_TRACE") && std::getenv("CB2_TRACE")[0] == '1';
+    cudaStream_t s_in = c->s_in, s_out = c->s_out, s_front = c->s_front;
+    const std::vector<uint64_t> sizes = pipeline_chunks(n, c->chunk_pairs, c->ramp);
+    std::vector<uint64_t> starts(sizes.size());
+    {
+        uint64_t b = 0;
+        for (size_t k = 0; k < sizes.size(); ++k) {
+            starts[k] = b;
+            b += sizes[k];
+        }
+    }
+    cudaEvent_t t0 = nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, s_in);
+    }
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    int rc = CB2_OK;
+#define CKA(x)                                                             \
+    {                                                                      \
+        cudaError_t e_ = (x);                                              \
+        if (e_ != cudaSuccess && rc == CB2_OK) {                           \
+            c->err = std::string(#x) + ": " + cudaGetErrorString(e_);      \
+            rc = CB2_ERR_CUDA;                                             \
+        }                                                                  \
+    }
+    // EPA tiers + second chance + copy-out of chunk j
+    auto issue_back = [&](size_t j) {
+        const int buf = (int)(j % cb2_ctx::NS), wslot = (int)(j % (size_t)nw);
+        cudaStream_t sb = c->stream[j % (size_t)c->n_cstreams];
+        char* base = c->d_stage[buf];
+        cudaStream_t stl = c->tail_prio ? c->s_tail[j % 2] : sb;
+        CKA(cudaStreamWaitEvent(sb, c->ev_front[wslot], 0))
+        if (rc == CB2_OK) rc = compute(starts[j], sizes[j], base, sb, wslot, stl, 2);
+        CKA(cudaEventRecord(c->ev_k[buf], stl))
+        CKA(cudaEventRecord(c->ev_wsfree[wslot], stl))
+        mark(stl);
+        CKA(cudaStreamWaitEvent(s_out, c->ev_k[buf], 0))
+        if (rc == CB2_OK) rc = copy_out(starts[j], sizes[j], base, s_out);
+        CKA(cudaEventRecord(c->ev_free[buf], s_out))
+        mark(s_out);
+    };
+    size_t issued_back = 0;
+    for (size_t k = 0; k < sizes.size() && rc == CB2_OK; ++k) {
+        const int buf = (int)(k % cb2_ctx::NS), wslot = (int)(k % (size_t)nw);
+        char* base = c->d_stage[buf];
+        // the staging buffer and the workspace slot of chunk k were last used by chunks k-NS and
+        // k-nw: their back parts must have been ISSUED before anybody can wait for their events
+        while (issued_back + (size_t)cb2_ctx::NS <= k || issued_back + (size_t)nw <= k) issue_back(issued_back++);
+        if (rc != CB2_OK) break;
+        if (k >= (size_t)cb2_ctx::NS) CKA(cudaStreamWaitEvent(s_in, c->ev_free[buf], 0))
+        if (rc == CB2_OK) rc = copy_in(starts[k], sizes[k], base, s_in);
+        CKA(cudaEventRecord(c->ev_in[buf], s_in))
+        mark(s_in);
+        CKA(cudaStreamWaitEvent(s_front, c->ev_in[buf], 0))
+        if (k >= (size_t)nw) CKA(cudaStreamWaitEvent(s_front, c->ev_wsfree[wslot], 0))
+        if (rc == CB2_OK) rc = compute(starts[k], sizes[k], base, s_front, wslot, s_front, 1);
+        CKA(cudaEventRecord(c->ev_front[wslot], s_front))
+        // GJK(k) precedes the EPA tiers of chunk k-1 in issue order as well
+        while (issued_back + 1 <= k && rc == CB2_OK) issue_back(issued_back++);
+    }
+    // every chunk whose GJK stage was issued gets its back part (a failed call still drains cleanly)
+    while (issued_back < sizes.size() && rc == CB2_OK) issue_back(issued_back++);
+#undef CKA
+    for (int i = 0; i < cb2_ctx::NS + 5; ++i) {
+        cudaStream_t st = i < cb2_ctx::NS ? c->stream[i]
+                          : (i == cb2_ctx::NS ? s_in : (i == cb2_ctx::NS + 1 ? s_out : (i == cb2_ctx::NS + 2 ? s_front : c->s_tail[i - cb2_ctx::NS - 3])));
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess && rc == CB2_OK) {
+            c->err = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
+            rc = CB2_ERR_CUDA;
+        }
+    }
+    if (trace) {
+        // per chunk: copy-in | (kernels, copy-out) are recorded in issue order: in(k) first, then the
+        // back of chunk k-1 — print them as they come
+        for (size_t q = 0; q < tev.size(); ++q) {
+            float a_ = 0;
+            cudaEventElapsedTime(&a_, t0, tev[q]);
+            std::fprintf(stderr, "[cb2 trace] mark %zu: %.3f ms\n", q, a_);
+        }
+        std::fprintf(stderr, "[cb2 trace] stages:");
+        for (auto& m : g_trace) {
+            float t_ = 0;
+            cudaEventElapsedTime(&t_, t0, m.ev);
+            std::fprintf(stderr, "%s %s %.3f", std::strcmp(m.what, "begin") == 0 ? "\n[cb2 trace]  " : ",", m.what, t_);
+            cudaEventDestroy(m.ev);
+        }
+        std::fprintf(stderr, "\n");
+        g_trace.clear();
+        for (auto e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(t0);
+    }
+    return rc;
+}
 // the 2-D host path checks its shape indices on the host, chunk by chunk (the 3-D kernels check on
 // the device, see narrow_host)
 static bool indices_in_range(const uint32_t* a, const uint32_t* b, uint64_t m, uint32_t limit) {
@@ -930,27 +1083,35 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
     static const bool split_env = std::getenv("CB2_SPLIT_TAIL") && std::getenv("CB2_SPLIT_TAIL")[0] == '1';
     const bool split = split_env && op == OP_INTERSECTION && !c->legacy_epa && strategy == CB2_FULL_RESOLUTION &&
                        cb2_ctx::NS >= 4;
+    // CB2_AHEAD (default on): the GJK stages run ahead on their own high-priority stream
+    // (pipeline_run_ahead); nw workspace slots rotate
+    const bool ahead = c->ahead != 0 && !split && op == OP_INTERSECTION && !c->legacy_epa &&
+                       strategy == CB2_FULL_RESOLUTION && cb2_ctx::NS >= 6;
+    const int nw = ahead ? (c->n_cstreams + 1 < cb2_ctx::NS ? c->n_cstreams + 1 : cb2_ctx::NS) : 0;
     if (op == OP_INTERSECTION && !c->legacy_epa)
-        for (int slot = 0; slot < (split ? cb2_ctx::NS : c->n_cstreams); ++slot) {
+        for (int slot = 0; slot < (split ? cb2_ctx::NS : (ahead ? nw : c->n_cstreams)); ++slot) {
             rc = ensure_ws(c, slot, chunk);
             if (rc) return rc;
+            if (ahead) {
+                rc = ensure_retry(c, slot);
+                if (rc) return rc;
+            }
         }
     const cb2_xform* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
     // a Rust slice index would panic on an out-of-range shape index: the kernels check every index
     // they load (status CB2_BAD_INDEX, nothing is read through it) and raise a device flag; the call
     // then fails as a whole (outputs of a failed call are unspecified)
     if (c->d_bad_index) CK(c, cudaMemsetAsync(c->d_bad_index, 0, sizeof(uint32_t), c->s_in));
-    rc = pipeline_run(
-        c, n,
-        [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
+    auto copy_in = [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
             for (int x = 0; x < n_xf; ++x)
                 CK(c, cudaMemcpyAsync(base + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform),
                                       cudaMemcpyHostToDevice, st));
             CK(c, cudaMemcpyAsync(base + o_ls, l_shape + b, m * 4, cudaMemcpyHostToDevice, st));
             CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
             return CB2_OK;
-        },
-        [&](uint64_t, uint64_t m, char* base, cudaStream_t st, int slot, cudaStream_t tail) -> int {
+        };
+    auto compute_phase = [&](uint64_t, uint64_t m, char* base, cudaStream_t st, int slot, cudaStream_t tail,
+                             int phase) -> int {
             narrow_args A;
             std::memset(&A, 0, sizeof(A));
             A.l_shape = reinterpret_cast<const uint32_t*>(base + o_ls);
@@ -967,9 +1128,9 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
             A.out_contact = reinterpret_cast<cb2_contact*>(base + o_out);
             A.out_distance = reinterpret_cast<float*>(base + o_out);
             A.out_status = reinterpret_cast<uint8_t*>(base + o_st);
-            return launch_op(c, op, strategy, A, st, slot, tail);
-        },
-        [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
+            return launch_op(c, op, strategy, A, st, slot, tail, phase);
+        };
+    auto copy_out = [&](uint64_t b, uint64_t m, char* base, cudaStream_t st) -> int {
             if (op == OP_DISTANCE)
                 CK(c, cudaMemcpyAsync(out_d + b, base + o_out, m * sizeof(float), cudaMemcpyDeviceToHost, st));
             else
@@ -977,8 +1138,21 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
                                       cudaMemcpyDeviceToHost, st));
             CK(c, cudaMemcpyAsync(status + b, base + o_st, m, cudaMemcpyDeviceToHost, st));
             return CB2_OK;
-        },
-        split);
+        };
+    if (ahead)
+        rc = pipeline_run_ahead(
+            c, n, nw, copy_in,
+            [&](uint64_t b, uint64_t m, char* base, cudaStream_t st, int slot, cudaStream_t tail, int phase) -> int {
+                return compute_phase(b, m, base, st, slot, tail, phase);
+            },
+            copy_out);
+    else
+        rc = pipeline_run(
+            c, n, copy_in,
+            [&](uint64_t b, uint64_t m, char* base, cudaStream_t st, int slot, cudaStream_t tail) -> int {
+                return compute_phase(b, m, base, st, slot, tail, 0);
+            },
+            copy_out, split);
     if (rc == CB2_OK && c->d_bad_index) {
         CK(c, cudaMemcpy(c->h_bad_index, c->d_bad_index, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (*c->h_bad_index) return fail(c, CB2_ERR_ARG, "shape index out of range");
