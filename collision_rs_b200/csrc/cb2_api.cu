@@ -22,6 +22,9 @@
 using namespace cb2;
 
 #define CB2_NS_MAX 8
+#ifndef CB2_DUMP0_DIV  // tier 0 -> 1 dump room: one pair in CB2_DUMP0_DIV
+#define CB2_DUMP0_DIV 4
+#endif
 struct cb2_ctx {
     int device = 0;
     int sm_count = 0;
@@ -567,7 +570,7 @@ static int ensure_ws(cb2_ctx* c, int slot, uint64_t n) {
         // room for 1 pair in 4 (tier 0 -> 1) and 1 in 32 (tier 1 -> 2) to hand their polytope
         // over; beyond that a pair restarts in the next tier instead of resuming
         for (int k = 0; k + 1 < EPA_TIERS; ++k) {
-            const uint64_t frac = k == 0 ? n / 4 : n / 32;
+            const uint64_t frac = k == 0 ? n / CB2_DUMP0_DIV : n / 32;
             const uint64_t dc = frac > 4096 ? frac : (n < 4096 ? n : 4096);
             CK(c, cudaMalloc(&w.dump[k], dc * epa_dump_record_bytes(k)));
             w.dump_cap[k] = (uint32_t)dc;

@@ -210,6 +210,8 @@ CB2_DI f3 poly_local_support_part(const poly_tables& T, const poly_ref& s, float
     const uint32_t c_end = min(c + q, nch);
     f3 best = zero3();
     best_dot = -INFINITY;
+    // (one chunk per lane is the rule: lists beyond 4 NP candidates are rare, keep the loop rolled)
+#pragma unroll 1
     for (; c < c_end; ++c) {
         uint32_t i0, i1, i2, i3;
         if (!wide) {

@@ -84,11 +84,25 @@ struct poly_smem {
 template <class PS, int NG>
 struct group_layout {
     static constexpr size_t TARGET = NG == 8 ? 112 : (NG == 4 ? 32 : 0);
-    static constexpr size_t STRIDE = NG >= 4 ? sizeof(PS) + ((TARGET + 128 - sizeof(PS) % 128) % 128) : sizeof(PS);
+    // (16 groups: an odd multiple of 16 bytes, so the groups visit all eight 16-byte columns of a 128-byte row)
+    static constexpr size_t STRIDE = NG == 16 ? sizeof(PS) + ((sizeof(PS) / 16) % 2 ? 0 : 16)
+                                     : (NG >= 4 ? sizeof(PS) + ((TARGET + 128 - sizeof(PS) % 128) % 128) : sizeof(PS));
     static constexpr size_t BYTES = STRIDE * NG;
     static_assert(STRIDE % 16 == 0, "float4 members");
     CB2_DI static int slot(int gw) { return NG == 8 ? ((gw & 1) * 4 + (gw >> 1)) : gw; }
 };
+
+// shared-memory loads the compiler may not move into a branch
+CB2_DI float4 lds128(uint32_t a) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+CB2_DI uint32_t lds32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
 
 template <class PS>
 CB2_DI f3 ps_pv(const PS& P, uint32_t i) {
@@ -134,6 +148,7 @@ struct bitmask {
         for (int k = 0; k < W; ++k)
             if ((i >> 5) == k) w[k] &= ~(1u << (i & 31));
     }
+    CB2_DI void set_word(int k, uint32_t v) { w[k] |= v; }
     CB2_DI bool any() const {
         uint32_t v = 0u;
 #pragma unroll
@@ -166,6 +181,7 @@ struct bitmask<2> {
     CB2_DI void reset(int i) { m &= ~(1ull << i); }
     CB2_DI bool any() const { return m != 0ull; }
     CB2_DI int first() const { return __ffsll((long long)m) - 1; }
+    CB2_DI void set_word(int k, uint32_t v) { m |= (unsigned long long)v << (32 * k); }  // k is a constant
     CB2_DI int next(int from) const {
         const unsigned long long v = from < 64 ? (m >> from) << from : 0ull;
         return v ? __ffsll((long long)v) - 1 : -1;
@@ -187,6 +203,7 @@ struct bitmask<4> {
         if (i < 64) lo &= ~(1ull << i);
         else hi &= ~(1ull << (i - 64));
     }
+    CB2_DI void set_word(int, uint32_t) {}  // (only the one- and two-word masks take the lean visibility pass)
     CB2_DI bool any() const { return (lo | hi) != 0ull; }
     CB2_DI int first() const { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
     CB2_DI int next(int from) const {
@@ -409,23 +426,61 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         bool ctie = false;
         {
             const int nf_max = __reduce_max_sync(0xffffffffu, add ? nf : 0);
-            CB2_UNROLL(CB2_U_VIS)
-            for (int f0 = 0; f0 < nf_max; f0 += G) {
-                const int f = f0 + gl;
-                bool v = false;
-                if (add && f < nf) {
-                    const float4 fn = P.fnd[f];
-                    const uint32_t idx = P.fidx[f];
-                    v = dot(mk3(fn.x, fn.y, fn.z), sup_v - ps_pv(P, idx & 255u)) > 0.0f;
+            if constexpr (FW <= 2) {
+                // Lean trips for the small tiers: shared-memory addresses advance by constants, every
+                // lane loads (slots past nf lie inside the record and are never used; the loads are
+                // volatile asm so that the compiler keeps them out of a branch) and only the result is
+                // predicated; the group's nibble of each ballot is appended to a 32-bit word by one
+                // multiply-add (the fields are disjoint, so + is |).
+                const uint32_t sb = (uint32_t)__cvta_generic_to_shared(&P);
+                const uint32_t s_pv = sb + (uint32_t)offsetof(PS, pv);
+#pragma unroll
+                for (int w = 0; w < FW; ++w) {
+                    uint32_t acc = 0u, pw = 1u;
+                    uint32_t a_f = sb + (uint32_t)offsetof(PS, fnd) + (uint32_t)(32 * w + gl) * 16u;
+                    uint32_t a_i = sb + (uint32_t)offsetof(PS, fidx) + (uint32_t)(32 * w + gl) * 4u;
+                    const int f_hi = min(nf_max, 32 * (w + 1));
+                    for (int f = 32 * w + gl; f - gl < f_hi; f += G, a_f += 16u * G, a_i += 4u * G) {
+                        const float4 fn = lds128(a_f);
+                        const uint32_t idx = lds32(a_i);
+                        // (a slot past nf may hold anything: keep its vertex index inside the record)
+                        static_assert(VCAP <= 32 || FW > 2, "index mask of the lean visibility pass");
+                        const float4 p0 = lds128(s_pv + ((idx & 31u) << 4));
+                        const float dv = dot(mk3(fn.x, fn.y, fn.z), sup_v - mk3(p0.x, p0.y, p0.z));
+                        const bool live = add & (f < nf);
+                        const bool v = live & (dv > 0.0f);
 #if CB2_OPT_FOLD
-                    if (!v) {
-                        if (fn.w < cd) { cd = fn.w; ci = f; }
-                        else if (!(fn.w > cd)) ctie = true;
-                    }
+                        const bool stay = live & !v;
+                        const bool lt = stay & (fn.w < cd);
+                        ctie |= stay & !lt & !(fn.w > cd);  // equal or NaN: Vec order decides
+                        cd = lt ? fn.w : cd;
+                        ci = lt ? f : ci;
 #endif
+                        const uint32_t nib = (__ballot_sync(0xffffffffu, v) >> (gw * G)) & gbits;
+                        acc += nib * pw;
+                        pw <<= G;
+                    }
+                    vis.set_word(w, acc);
                 }
-                const uint32_t bits = (__ballot_sync(0xffffffffu, v) >> (gw * G)) & gbits;
-                vis.or_bits(f0, bits);
+            } else {
+                CB2_UNROLL(CB2_U_VIS)
+                for (int f0 = 0; f0 < nf_max; f0 += G) {
+                    const int f = f0 + gl;
+                    bool v = false;
+                    if (add && f < nf) {
+                        const float4 fn = P.fnd[f];
+                        const uint32_t idx = P.fidx[f];
+                        v = dot(mk3(fn.x, fn.y, fn.z), sup_v - ps_pv(P, idx & 255u)) > 0.0f;
+#if CB2_OPT_FOLD
+                        if (!v) {
+                            if (fn.w < cd) { cd = fn.w; ci = f; }
+                            else if (!(fn.w > cd)) ctie = true;
+                        }
+#endif
+                    }
+                    const uint32_t bits = (__ballot_sync(0xffffffffu, v) >> (gw * G)) & gbits;
+                    vis.or_bits(f0, bits);
+                }
             }
         }
         // (2) the swap_remove sweep as a two-pointer walk over the mask: `i` climbs from the front,
@@ -437,37 +492,32 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         int len = nf, nvis = 0, nmv = 0, mine = 0;
         bool overflow = false;
         {
+            // branch-free step: every lane of the warp executes it, idle groups change nothing
             bool walking = add && vis.any();
-            int i = walking ? vis.first() : 0;
+            int i = vis.first();
             int cur = i;
             while (__any_sync(0xffffffffu, walking)) {
-                if (walking) {
-                    if (nvis >= OCAP) {
-                        overflow = true;
-                        walking = false;
-                    } else {
-                        if (nvis == gl) mine = cur;
-                        if (gl == 0) P.order[nvis] = (uint8_t)cur;
-                        ++nvis;
-                        vis.reset(cur);
-                        --len;
-                        if (i == len) {
-                            walking = false;
-                        } else if (vis.test(len)) {
-                            cur = len;
-                        } else {
-                            if (gl == 0) {
-                                P.mv_dst[nmv] = (uint8_t)i;
-                                P.mv_src[nmv] = (uint8_t)len;
-                            }
-                            if (ci == len) ci = i;  // the tracked face moves with the swap
-                            ++nmv;
-                            walking = vis.any();
-                            i = walking ? vis.first() : 0;
-                            cur = i;
-                        }
-                    }
+                const bool step = walking && nvis < OCAP;
+                overflow |= walking && !step;
+                mine = (step && nvis == gl) ? cur : mine;
+                if (step && gl == 0) P.order[nvis] = (uint8_t)cur;
+                if (step) vis.reset(cur);
+                const int len1 = len - 1;
+                const bool last = i == len1;               // the examined face was the tail itself
+                const bool tail_vis = vis.test(len1);      // the tail face dropped into slot i is examined next
+                const bool mv = step && !last && !tail_vis;  // ... or stays there
+                if (mv && gl == 0) {
+                    P.mv_dst[nmv] = (uint8_t)i;
+                    P.mv_src[nmv] = (uint8_t)len1;
                 }
+                ci = (mv && ci == len1) ? i : ci;  // (closest-face tracking: the tracked face moves with the swap)
+                const int nxt = vis.first();
+                i = mv ? nxt : i;
+                cur = tail_vis ? len1 : nxt;
+                nmv += mv ? 1 : 0;
+                nvis += step ? 1 : 0;
+                len = step ? len1 : len;
+                walking = step && !last && (tail_vis || vis.any());
             }
         }
         __syncwarp();
