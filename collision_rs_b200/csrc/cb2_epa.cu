@@ -42,6 +42,9 @@
 #ifndef CB2_OPT_FOLD    // closest_face_to_origin folded into the visibility pass and Face::new: bit-identical,
 #define CB2_OPT_FOLD 0  // but no faster (tier 0 14.03 ms with, 13.95 ms without: three more live registers)
 #endif
+#ifndef CB2_VIS2        // visibility pass: two faces per lane and trip (needs CB2_OPT_FOLD == 0)
+#define CB2_VIS2 1
+#endif
 #ifndef CB2_EPA_MIN_BLOCKS
 #define CB2_EPA_MIN_BLOCKS 20
 #endif
@@ -362,17 +365,22 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         // iteration have already seen every distance of the polytope (see below).
         {
             const bool need = run && best_face < 0;
-            const int nf_max = __reduce_max_sync(0xffffffffu, need ? nf : 0);
+            const int nfn = need ? nf : 0;  // idle groups (and groups with a tracked face) scan nothing
+            const int nf_max = __reduce_max_sync(0xffffffffu, nfn);
             if (nf_max > 0) {
+                // two faces per lane and trip (f, f + G: still ascending per lane, so ties keep the
+                // first); a NaN distance never compares smaller, so it needs no special case here
                 float bd = INFINITY;
                 uint32_t bi = 0xFFFFFFFFu;
-                CB2_UNROLL(CB2_U_CLOSEST)
-                for (int f = gl; f < nf_max; f += G) {
-                    if (need && f < nf) {
-                        float dd = P.fnd[f].w;
-                        if (dd != dd) dd = INFINITY;  // NaN never compares smaller
-                        if (dd < bd) { bd = dd; bi = (uint32_t)f; }  // f ascends: ties keep the first
-                    }
+                uint32_t a_d = (uint32_t)__cvta_generic_to_shared(&P) + (uint32_t)offsetof(PS, fnd) + (uint32_t)gl * 16u + 12u;
+                for (int f = gl; f - gl < nf_max; f += 2 * G, a_d += 32u * G) {
+                    const float d0 = __uint_as_float(lds32(a_d)), d1 = __uint_as_float(lds32(a_d + 16u * G));
+                    const bool t0 = (f < nfn) & (d0 < bd);
+                    bd = t0 ? d0 : bd;
+                    bi = t0 ? (uint32_t)f : bi;
+                    const bool t1 = (f + G < nfn) & (d1 < bd);
+                    bd = t1 ? d1 : bd;
+                    bi = t1 ? (uint32_t)(f + G) : bi;
                 }
 #pragma unroll
                 for (int off = G / 2; off >= 1; off >>= 1) {
@@ -434,17 +442,33 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                 // multiply-add (the fields are disjoint, so + is |).
                 const uint32_t sb = (uint32_t)__cvta_generic_to_shared(&P);
                 const uint32_t s_pv = sb + (uint32_t)offsetof(PS, pv);
+                static_assert(VCAP <= 32 || FW > 2, "index mask of the lean visibility pass");
 #pragma unroll
                 for (int w = 0; w < FW; ++w) {
                     uint32_t acc = 0u, pw = 1u;
                     uint32_t a_f = sb + (uint32_t)offsetof(PS, fnd) + (uint32_t)(32 * w + gl) * 16u;
                     uint32_t a_i = sb + (uint32_t)offsetof(PS, fidx) + (uint32_t)(32 * w + gl) * 4u;
                     const int f_hi = min(nf_max, 32 * (w + 1));
+#if CB2_VIS2
+                    // two faces per lane and trip: two independent load -> dot chains in flight
+                    for (int f = 32 * w + gl; f - gl < f_hi; f += 2 * G, a_f += 32u * G, a_i += 8u * G) {
+                        const float4 fn0 = lds128(a_f), fn1 = lds128(a_f + 16u * G);
+                        const uint32_t ix0 = lds32(a_i), ix1 = lds32(a_i + 4u * G);
+                        const float4 p0 = lds128(s_pv + ((ix0 & 31u) << 4)), p1 = lds128(s_pv + ((ix1 & 31u) << 4));
+                        const float dv0 = dot(mk3(fn0.x, fn0.y, fn0.z), sup_v - mk3(p0.x, p0.y, p0.z));
+                        const float dv1 = dot(mk3(fn1.x, fn1.y, fn1.z), sup_v - mk3(p1.x, p1.y, p1.z));
+                        const bool v0 = add & (f < nf) & (dv0 > 0.0f);
+                        const bool v1 = add & (f + G < nf) & (dv1 > 0.0f);
+                        const uint32_t n0 = (__ballot_sync(0xffffffffu, v0) >> (gw * G)) & gbits;
+                        const uint32_t n1 = (__ballot_sync(0xffffffffu, v1) >> (gw * G)) & gbits;
+                        acc += (n0 | (n1 << G)) * pw;
+                        pw <<= 2 * G;
+                    }
+#else
                     for (int f = 32 * w + gl; f - gl < f_hi; f += G, a_f += 16u * G, a_i += 4u * G) {
                         const float4 fn = lds128(a_f);
                         const uint32_t idx = lds32(a_i);
                         // (a slot past nf may hold anything: keep its vertex index inside the record)
-                        static_assert(VCAP <= 32 || FW > 2, "index mask of the lean visibility pass");
                         const float4 p0 = lds128(s_pv + ((idx & 31u) << 4));
                         const float dv = dot(mk3(fn.x, fn.y, fn.z), sup_v - mk3(p0.x, p0.y, p0.z));
                         const bool live = add & (f < nf);
@@ -460,6 +484,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                         acc += nib * pw;
                         pw <<= G;
                     }
+#endif
                     vis.set_word(w, acc);
                 }
             } else {
