@@ -72,8 +72,7 @@ struct poly_smem {
     uint32_t adj[VCAP * AW];   // directed-edge bit matrix (all zero between iterations)
     uint16_t elist[OCAP];      // horizon edges a | b<<8 in reference order
     uint8_t order[OCAP];       // visible faces in the order Polytope::add examines them
-    uint8_t mv_dst[OCAP];      // swap_remove: tail face mv_src lands in hole mv_dst
-    uint8_t mv_src[OCAP];
+    uint16_t mv[OCAP];         // swap_remove: tail face (mv >> 8) lands in hole (mv & 255)
     uint64_t mbar;             // tracks the bulk copy that resumes a polytope from the previous tier
 };
 
@@ -185,6 +184,7 @@ struct bitmask<2> {
     CB2_DI bool any() const { return m != 0ull; }
     CB2_DI int first() const { return __ffsll((long long)m) - 1; }
     CB2_DI void set_word(int k, uint32_t v) { m |= (unsigned long long)v << (32 * k); }  // k is a constant
+    CB2_DI uint32_t low_word() const { return (uint32_t)m; }
     CB2_DI int next(int from) const {
         const unsigned long long v = from < 64 ? (m >> from) << from : 0ull;
         return v ? __ffsll((long long)v) - 1 : -1;
@@ -222,6 +222,52 @@ struct bitmask<4> {
 template <>
 struct bitmask<3> : bitmask<4> {};
 
+// one-word mask (up to 32 faces)
+struct bitmask32 {
+    uint32_t m;
+    CB2_DI bool test(int i) const { return (m >> i) & 1u; }
+    CB2_DI void reset(int i) { m &= ~(1u << i); }
+    CB2_DI bool any() const { return m != 0u; }
+    CB2_DI int first() const { return __ffs((int)m) - 1; }
+};
+
+// The swap_remove sweep of Polytope::add (epa3d.rs:147-175) as a two-pointer walk over the mask of
+// visible faces: `i` climbs from the front, `len` shrinks from the back; a visible face at slot i
+// is examined, then the tail face dropped into slot i is examined next, and so on.  Examined
+// faces leave the mask, so the next `i` is simply its lowest bit (everything below the old i and
+// everything from len up has been examined or was never visible).  One walk step per warp
+// iteration, branch-free: every lane of the warp executes it, idle groups change nothing.  Lane k
+// of the group keeps the k-th examined face (`mine`) for the horizon passes; the examination
+// order goes to P.order, the moves (tail face src lands in hole dst) to P.mv as dst | src << 8.
+template <int G, int OCAP, class MK, class PS>
+CB2_DI void epa_walk(MK& vis, PS& P, bool add, int gl, int& len, int& nvis, int& nmv, int& mine,
+                     bool& overflow, int& ci) {
+    bool walking = add && vis.any();
+    bool step = walking && nvis < OCAP;  // (nvis is 0 here)
+    int i = vis.first();
+    int cur = i;
+    while (__any_sync(0xffffffffu, step)) {
+        mine = (step && nvis == gl) ? cur : mine;
+        if (step && gl == 0) P.order[nvis] = (uint8_t)cur;
+        if (step) vis.reset(cur);
+        const int len1 = len - 1;
+        const bool last = i == len1;                 // the examined face was the tail itself
+        const bool tail_vis = vis.test(len1);        // the tail face dropped into slot i is examined next
+        const bool mv = step && !last && !tail_vis;  // ... or stays there
+        if (mv && gl == 0) P.mv[nmv] = (uint16_t)(i | (len1 << 8));
+        ci = (mv && ci == len1) ? i : ci;  // (closest-face tracking: the tracked face moves with the swap)
+        const int nxt = vis.first();
+        i = mv ? nxt : i;
+        cur = tail_vis ? len1 : nxt;
+        nmv += mv ? 1 : 0;
+        nvis += step ? 1 : 0;
+        len = step ? len1 : len;
+        walking = step && !last && (tail_vis || vis.any());
+        step = walking && nvis < OCAP;
+    }
+    overflow = walking;  // faces left to examine, no room in the lists
+}
+
 enum : int { S_FETCH = 0, S_RUN = 1, S_EXIT = 2 };
 
 // RF/RV: caps of the tier whose dumps this instantiation resumes (0 = none)
@@ -233,6 +279,9 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     constexpr int FW = (FCAP + 31) / 32;
     constexpr int AW = PS::AW;
     constexpr int NG = 32 / G;
+    // adjacency bit (row a, column b): word a*AW + b/32, bit b%32
+    auto adj_word = [](uint32_t a, uint32_t b) -> uint32_t { return AW == 1 ? a : a * AW + (b >> 5); };
+    auto adj_bit = [](uint32_t b) -> uint32_t { return AW == 1 ? b : (b & 31u); };
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x;
     const int gl = lane & (G - 1);
@@ -432,8 +481,9 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         float cd = INFINITY;
         int ci = -1;
         bool ctie = false;
+        const int vis_top = __reduce_max_sync(0xffffffffu, add ? nf : 0);  // most faces any group tests
         {
-            const int nf_max = __reduce_max_sync(0xffffffffu, add ? nf : 0);
+            const int nf_max = vis_top;
             if constexpr (FW <= 2) {
                 // Lean trips for the small tiers: shared-memory addresses advance by constants, every
                 // lane loads (slots past nf lie inside the record and are never used; the loads are
@@ -508,42 +558,20 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                 }
             }
         }
-        // (2) the swap_remove sweep as a two-pointer walk over the mask: `i` climbs from the front,
-        //     `len` shrinks from the back; a visible face at slot i is examined, then the tail face
-        //     dropped into slot i is examined next, and so on.  One walk step per warp iteration.
-        //     Examined faces leave the mask, so the next `i` is simply its lowest bit (everything
-        //     below the old i and everything from len up has been examined or was never visible).
-        //     Lane k of the group keeps the k-th examined face (`mine`) for the horizon passes.
+        // (2) the swap_remove sweep (epa_walk above)
         int len = nf, nvis = 0, nmv = 0, mine = 0;
         bool overflow = false;
-        {
-            // branch-free step: every lane of the warp executes it, idle groups change nothing
-            bool walking = add && vis.any();
-            int i = vis.first();
-            int cur = i;
-            while (__any_sync(0xffffffffu, walking)) {
-                const bool step = walking && nvis < OCAP;
-                overflow |= walking && !step;
-                mine = (step && nvis == gl) ? cur : mine;
-                if (step && gl == 0) P.order[nvis] = (uint8_t)cur;
-                if (step) vis.reset(cur);
-                const int len1 = len - 1;
-                const bool last = i == len1;               // the examined face was the tail itself
-                const bool tail_vis = vis.test(len1);      // the tail face dropped into slot i is examined next
-                const bool mv = step && !last && !tail_vis;  // ... or stays there
-                if (mv && gl == 0) {
-                    P.mv_dst[nmv] = (uint8_t)i;
-                    P.mv_src[nmv] = (uint8_t)len1;
-                }
-                ci = (mv && ci == len1) ? i : ci;  // (closest-face tracking: the tracked face moves with the swap)
-                const int nxt = vis.first();
-                i = mv ? nxt : i;
-                cur = tail_vis ? len1 : nxt;
-                nmv += mv ? 1 : 0;
-                nvis += step ? 1 : 0;
-                len = step ? len1 : len;
-                walking = step && !last && (tail_vis || vis.any());
+        if constexpr (FW <= 2) {
+            // while no polytope of the warp has more than 32 faces the walk runs on one word
+            if (vis_top <= 32) {
+                bitmask32 v32;
+                v32.m = vis.low_word();
+                epa_walk<G, OCAP>(v32, P, add, gl, len, nvis, nmv, mine, overflow, ci);
+            } else {
+                epa_walk<G, OCAP>(vis, P, add, gl, len, nvis, nmv, mine, overflow, ci);
             }
+        } else {
+            epa_walk<G, OCAP>(vis, P, add, gl, len, nvis, nmv, mine, overflow, ci);
         }
         __syncwarp();
         // (3) horizon = edges of the examined faces, in examination order, whose reverse edge is not
@@ -553,28 +581,32 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         const int nvis_max = __reduce_max_sync(0xffffffffu, edges ? nvis : 0);
         bool dup = false;
         const uint32_t idx_mine = (edges && gl < nvis) ? P.fidx[mine] : 0u;
+        // (more than G examined faces are rare: the three passes stay rolled, the code stays small)
+#pragma unroll 1
         for (int k0 = 0; k0 < nvis_max; k0 += G) {
             const int k = k0 + gl;
             if (edges && k < nvis) {
                 const uint32_t idx = k0 == 0 ? idx_mine : P.fidx[P.order[k]];
                 const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
-                const uint32_t o0 = atomicOr(&P.adj[v0 * AW + (v1 >> 5)], 1u << (v1 & 31));
-                const uint32_t o1 = atomicOr(&P.adj[v1 * AW + (v2 >> 5)], 1u << (v2 & 31));
-                const uint32_t o2 = atomicOr(&P.adj[v2 * AW + (v0 >> 5)], 1u << (v0 & 31));
-                dup |= ((o0 >> (v1 & 31)) | (o1 >> (v2 & 31)) | (o2 >> (v0 & 31))) & 1u;
+                // (one word per row when VCAP <= 32: no word index, no bit mask)
+                const uint32_t o0 = atomicOr(&P.adj[adj_word(v0, v1)], 1u << adj_bit(v1));
+                const uint32_t o1 = atomicOr(&P.adj[adj_word(v1, v2)], 1u << adj_bit(v2));
+                const uint32_t o2 = atomicOr(&P.adj[adj_word(v2, v0)], 1u << adj_bit(v0));
+                dup |= ((o0 >> adj_bit(v1)) | (o1 >> adj_bit(v2)) | (o2 >> adj_bit(v0))) & 1u;
             }
         }
         __syncwarp();
         int ne = 0;
+#pragma unroll 1
         for (int k0 = 0; k0 < nvis_max; k0 += G) {
             const int k = k0 + gl;
             uint32_t keep = 0, v0 = 0, v1 = 0, v2 = 0;
             if (edges && k < nvis) {
                 const uint32_t idx = k0 == 0 ? idx_mine : P.fidx[P.order[k]];
                 v0 = idx & 255u; v1 = (idx >> 8) & 255u; v2 = (idx >> 16) & 255u;
-                keep = (~(P.adj[v1 * AW + (v0 >> 5)] >> (v0 & 31)) & 1u) |
-                       ((~(P.adj[v2 * AW + (v1 >> 5)] >> (v1 & 31)) & 1u) << 1) |
-                       ((~(P.adj[v0 * AW + (v2 >> 5)] >> (v2 & 31)) & 1u) << 2);
+                keep = (~(P.adj[adj_word(v1, v0)] >> adj_bit(v0)) & 1u) |
+                       ((~(P.adj[adj_word(v2, v1)] >> adj_bit(v1)) & 1u) << 1) |
+                       ((~(P.adj[adj_word(v0, v2)] >> adj_bit(v2)) & 1u) << 2);
             }
             uint32_t all = keep << (3 * gl);
 #pragma unroll
@@ -588,6 +620,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         dup = (__ballot_sync(0xffffffffu, dup) & gmask) != 0u;
         __syncwarp();
         // (4) clear the adjacency bits again
+#pragma unroll 1
         for (int k0 = 0; k0 < nvis_max; k0 += G) {
             const int k = k0 + gl;
             if (edges && k < nvis) {
@@ -607,7 +640,8 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         // (5) apply the swap_remove moves, append the vertex
         if (grow) {
             for (int m = gl; m < nmv; m += G) {
-                const int dst = P.mv_dst[m], src = P.mv_src[m];
+                const uint32_t mvr = P.mv[m];
+                const int dst = (int)(mvr & 255u), src = (int)(mvr >> 8);
                 P.fnd[dst] = P.fnd[src];
                 P.fidx[dst] = P.fidx[src];
             }
