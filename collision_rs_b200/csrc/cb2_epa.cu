@@ -206,7 +206,10 @@ struct bitmask<4> {
         if (i < 64) lo &= ~(1ull << i);
         else hi &= ~(1ull << (i - 64));
     }
-    CB2_DI void set_word(int, uint32_t) {}  // (only the one- and two-word masks take the lean visibility pass)
+    CB2_DI void set_word(int k, uint32_t v) {  // k is a constant
+        if (k < 2) lo |= (unsigned long long)v << (32 * k);
+        else hi |= (unsigned long long)v << (32 * (k - 2));
+    }
     CB2_DI bool any() const { return (lo | hi) != 0ull; }
     CB2_DI int first() const { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
     CB2_DI int next(int from) const {
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         const int vis_top = __reduce_max_sync(0xffffffffu, add ? nf : 0);  // most faces any group tests
         {
             const int nf_max = vis_top;
-            if constexpr (FW <= 2) {
+            if constexpr (FW <= 4) {
                 // Lean trips for the small tiers: shared-memory addresses advance by constants, every
                 // lane loads (slots past nf lie inside the record and are never used; the loads are
                 // volatile asm so that the compiler keeps them out of a branch) and only the result is
@@ -492,7 +495,9 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                 // multiply-add (the fields are disjoint, so + is |).
                 const uint32_t sb = (uint32_t)__cvta_generic_to_shared(&P);
                 const uint32_t s_pv = sb + (uint32_t)offsetof(PS, pv);
-                static_assert(VCAP <= 32 || FW > 2, "index mask of the lean visibility pass");
+                // (a slot past nf may hold anything: its vertex index is masked to stay inside the record)
+                constexpr uint32_t VM = VCAP <= 32 ? 31u : (VCAP <= 64 ? 63u : 127u);
+                static_assert(sizeof(PS) - offsetof(PS, pv) >= (VM + 1u) * 16u, "index mask of the lean visibility pass");
 #pragma unroll
                 for (int w = 0; w < FW; ++w) {
                     uint32_t acc = 0u, pw = 1u;
@@ -504,7 +509,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                     for (int f = 32 * w + gl; f - gl < f_hi; f += 2 * G, a_f += 32u * G, a_i += 8u * G) {
                         const float4 fn0 = lds128(a_f), fn1 = lds128(a_f + 16u * G);
                         const uint32_t ix0 = lds32(a_i), ix1 = lds32(a_i + 4u * G);
-                        const float4 p0 = lds128(s_pv + ((ix0 & 31u) << 4)), p1 = lds128(s_pv + ((ix1 & 31u) << 4));
+                        const float4 p0 = lds128(s_pv + ((ix0 & VM) << 4)), p1 = lds128(s_pv + ((ix1 & VM) << 4));
                         const float dv0 = dot(mk3(fn0.x, fn0.y, fn0.z), sup_v - mk3(p0.x, p0.y, p0.z));
                         const float dv1 = dot(mk3(fn1.x, fn1.y, fn1.z), sup_v - mk3(p1.x, p1.y, p1.z));
                         const bool v0 = add & (f < nf) & (dv0 > 0.0f);
@@ -518,8 +523,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                     for (int f = 32 * w + gl; f - gl < f_hi; f += G, a_f += 16u * G, a_i += 4u * G) {
                         const float4 fn = lds128(a_f);
                         const uint32_t idx = lds32(a_i);
-                        // (a slot past nf may hold anything: keep its vertex index inside the record)
-                        const float4 p0 = lds128(s_pv + ((idx & 31u) << 4));
+                        const float4 p0 = lds128(s_pv + ((idx & VM) << 4));
                         const float dv = dot(mk3(fn.x, fn.y, fn.z), sup_v - mk3(p0.x, p0.y, p0.z));
                         const bool live = add & (f < nf);
                         const bool v = live & (dv > 0.0f);
@@ -581,28 +585,22 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         const int nvis_max = __reduce_max_sync(0xffffffffu, edges ? nvis : 0);
         bool dup = false;
         const uint32_t idx_mine = (edges && gl < nvis) ? P.fidx[mine] : 0u;
-        // (more than G examined faces are rare: the three passes stay rolled, the code stays small)
-#pragma unroll 1
-        for (int k0 = 0; k0 < nvis_max; k0 += G) {
-            const int k = k0 + gl;
-            if (edges && k < nvis) {
-                const uint32_t idx = k0 == 0 ? idx_mine : P.fidx[P.order[k]];
-                const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
-                // (one word per row when VCAP <= 32: no word index, no bit mask)
-                const uint32_t o0 = atomicOr(&P.adj[adj_word(v0, v1)], 1u << adj_bit(v1));
-                const uint32_t o1 = atomicOr(&P.adj[adj_word(v1, v2)], 1u << adj_bit(v2));
-                const uint32_t o2 = atomicOr(&P.adj[adj_word(v2, v0)], 1u << adj_bit(v0));
-                dup |= ((o0 >> adj_bit(v1)) | (o1 >> adj_bit(v2)) | (o2 >> adj_bit(v0))) & 1u;
-            }
-        }
-        __syncwarp();
+        // Three passes over the examined faces — set the directed-edge bits, keep the edges whose
+        // reverse bit is clear, clear the bits again — each run straight-line for the first G faces
+        // (lane k holds the k-th examined face in a register); more than G examined faces are
+        // rare and take the rolled loops behind.
+        auto pass_set = [&](uint32_t idx) {
+            const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
+            // (one word per row when VCAP <= 32: no word index, no bit mask)
+            const uint32_t o0 = atomicOr(&P.adj[adj_word(v0, v1)], 1u << adj_bit(v1));
+            const uint32_t o1 = atomicOr(&P.adj[adj_word(v1, v2)], 1u << adj_bit(v2));
+            const uint32_t o2 = atomicOr(&P.adj[adj_word(v2, v0)], 1u << adj_bit(v0));
+            dup |= ((o0 >> adj_bit(v1)) | (o1 >> adj_bit(v2)) | (o2 >> adj_bit(v0))) & 1u;
+        };
         int ne = 0;
-#pragma unroll 1
-        for (int k0 = 0; k0 < nvis_max; k0 += G) {
-            const int k = k0 + gl;
+        auto pass_keep = [&](uint32_t idx, bool active) {
             uint32_t keep = 0, v0 = 0, v1 = 0, v2 = 0;
-            if (edges && k < nvis) {
-                const uint32_t idx = k0 == 0 ? idx_mine : P.fidx[P.order[k]];
+            if (active) {
                 v0 = idx & 255u; v1 = (idx >> 8) & 255u; v2 = (idx >> 16) & 255u;
                 keep = (~(P.adj[adj_word(v1, v0)] >> adj_bit(v0)) & 1u) |
                        ((~(P.adj[adj_word(v2, v1)] >> adj_bit(v1)) & 1u) << 1) |
@@ -616,24 +614,35 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
             if (keep & 2u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v1 | (v2 << 8)); ++pos; }
             if (keep & 4u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v2 | (v0 << 8)); }
             ne += __popc(all);
+        };
+        auto pass_clear = [&](uint32_t idx) {
+            const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
+#pragma unroll
+            for (int q = 0; q < AW; ++q) {
+                P.adj[v0 * AW + q] = 0u;
+                P.adj[v1 * AW + q] = 0u;
+                P.adj[v2 * AW + q] = 0u;
+            }
+        };
+        const bool act0 = edges && gl < nvis;
+        if (act0) pass_set(idx_mine);
+#pragma unroll 1
+        for (int k = G + gl; k - gl < nvis_max; k += G)
+            if (edges && k < nvis) pass_set(P.fidx[P.order[k]]);
+        __syncwarp();
+        pass_keep(idx_mine, act0);
+#pragma unroll 1
+        for (int k = G + gl; k - gl < nvis_max; k += G) {
+            const bool act = edges && k < nvis;
+            pass_keep(act ? P.fidx[P.order[k]] : 0u, act);
         }
         dup = (__ballot_sync(0xffffffffu, dup) & gmask) != 0u;
         __syncwarp();
         // (4) clear the adjacency bits again
+        if (act0) pass_clear(idx_mine);
 #pragma unroll 1
-        for (int k0 = 0; k0 < nvis_max; k0 += G) {
-            const int k = k0 + gl;
-            if (edges && k < nvis) {
-                const uint32_t idx = k0 == 0 ? idx_mine : P.fidx[P.order[k]];
-                const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
-#pragma unroll
-                for (int q = 0; q < AW; ++q) {
-                    P.adj[v0 * AW + q] = 0u;
-                    P.adj[v1 * AW + q] = 0u;
-                    P.adj[v2 * AW + q] = 0u;
-                }
-            }
-        }
+        for (int k = G + gl; k - gl < nvis_max; k += G)
+            if (edges && k < nvis) pass_clear(P.fidx[P.order[k]]);
         const bool spill = add && (overflow || dup || ne > OCAP || nv >= VCAP || len + ne > FCAP);
         const bool grow = add && !spill;
         __syncwarp();
