@@ -157,7 +157,7 @@ def kernel_rooflines(n, stage_ms, flops_pair, flops_gjk_pair, extra, fp32_peak, 
     pk, units = prof.get("kernels", {}), prof.get("units", {})
 
     def executed(keys, sec, live_units, ms):
-        recs = [pk[k] for k in keys if k in pk]
+        recs = [r for k in keys for name, r in pk.items() if name == k or (k.endswith(",") and name.startswith(k))]
         if not recs or not units.get(sec) or not ms:
             return None
         per_unit = sum(r["fadd"] + r["fmul"] + 2 * r["ffma"] for r in recs) / units[sec]
@@ -185,10 +185,10 @@ def kernel_rooflines(n, stage_ms, flops_pair, flops_gjk_pair, extra, fp32_peak, 
         entry("k_gjk_hits_p", "GJK::intersect, gjk/mod.rs:101-146", "cfg3", n, stage_ms[0], flops_gjk_pair,
               ["cfg3:k_gjk_hits_p<1>"], "cfg3"),
         entry("k_epa tier 0", "EPA3::process, epa3d.rs:27-175", "cfg3", n, stage_ms[1], None,
-              ["cfg3:k_epa<4,40,24,24,0,0>"], "cfg3"),
+              ["cfg3:k_epa<4,"], "cfg3"),
         entry("k_epa (all tiers)", "EPA3::process, epa3d.rs:27-175", "cfg3", n, stage_ms[1] + stage_ms[2],
               flops_pair - flops_gjk_pair,
-              ["cfg3:k_epa<4,40,24,24,0,0>", "cfg3:k_epa<8,72,40,32,40,24>", "cfg3:k_epa<8,208,104,96,72,40>"], "cfg3"),
+              ["cfg3:k_epa<4,", "cfg3:k_epa<8,72,", "cfg3:k_epa<8,208,"], "cfg3"),
     ]
     x = extra.get("cfg2_mixed_distance")
     if x:

@@ -150,6 +150,8 @@ CB2_DI f3 poly_local_support(const poly_tables& T, const poly_ref& s, float R, f
              z = __funnelshift_r(rec.z, rec.w, bits), w = rec.w >> bits;
     f3 best = zero3();  // no dot > -inf: P::origin() (polyhedron.rs:163)
     float best_dot = -INFINITY;
+    // (left to the compiler, which unrolls by two: rolled, k_gjk_hits_p gains 6 % and
+    // k_time_of_impact_p loses 14 %)
     for (uint32_t base = 0; base < cnt; base += 4u) {
         uint32_t i0, i1, i2, i3;
         if (!wide) {

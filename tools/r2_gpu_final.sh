@@ -11,7 +11,7 @@ python profiles/summarize_r2.py gpurun_out/r2_metrics.csv > gpurun_out/f_kernels
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_cfg3.csv python tools/profile_pass.py cfg3 > gpurun_out/f_ncu_l1.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_cfg4.csv python tools/profile_pass.py cfg4 > gpurun_out/f_ncu_l2.log 2>&1
 # --set full of tier 0 at 4 M pairs (second pass of the profile script: launch-skip 1)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_epaILi4|k_epa<4' --launch-skip 1 --launch-count 1 -f -o gpurun_out/prof_r2_tier0 python tools/profile_pass.py cfg3 > gpurun_out/f_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_epa --launch-skip 3 --launch-count 1 -f -o gpurun_out/prof_r2_tier0 python tools/profile_pass.py cfg3 > gpurun_out/f_ncu_full.log 2>&1
 ls -la gpurun_out/prof_r2_tier0.ncu-rep
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/f_bench1.json 2> gpurun_out/f_bench1.err; echo "bench rc=$?"; tail -2 gpurun_out/f_bench1.err
 python - <<'PY'
