@@ -617,55 +617,68 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
     const int au0 = cell_coord(au.x, org_u, inv_u, nu);
     const int av0 = cell_coord(av.x, org_v, inv_v, nv);
     const int cu = (int)(cell / (uint32_t)nv), cv = (int)(cell % (uint32_t)nv);
-    // two passes over the (short) window: count, reserve output room once per WARP (a single
-    // counter cannot take one atomic per pair), then write
+    // One pass over the (short) window.  The warp stays convergent (a lane whose window is closed
+    // idles), the hits of a trip are ranked by a ballot and staged in the warp's slice of shared
+    // memory; a full slice — and the remainder at the end — is flushed with ONE reservation on the
+    // global counter and coalesced stores.  (Round 1 walked every window twice: count, reserve per
+    // warp, write.)
+    constexpr int STAGE = 96;  // keys per warp slice; a trip adds at most 32
+    __shared__ unsigned long long stage[8][STAGE];
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t mine = 0;
-    unsigned long long w = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        const uint32_t a = (pass == 1 && mine) ? __ldg(epos + e) : 0u;
-        if (valid && (pass == 0 || mine)) {
-            for (uint64_t f = e + 1; f < n_entries; ++f) {
-                if (__ldg(ecell + f) != cell) break;
+    unsigned long long* mystage = stage[threadIdx.x >> 5];
+    uint32_t fill = 0;  // warp-uniform
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&G->n_pairs, (unsigned long long)fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (uint32_t j = lane; j < fill; j += 32u)
+            if (base + j < cap) keys[base + j] = mystage[j];
+        __syncwarp();
+        fill = 0;
+    };
+    const uint32_t a = valid ? __ldg(epos + e) : 0u;
+    uint64_t f = e + 1;
+    bool open = valid;
+    while (__any_sync(0xffffffffu, open)) {
+        bool hit = false;
+        uint32_t bp = 0;
+        if (open) {
+            if (f >= n_entries || __ldg(ecell + f) != cell) {
+                open = false;
+            } else {
                 const float2 bs = __ldg(eS + f);  // entries of a cell ascend by position, so by min_s
-                if (!(bs.x < as.y)) break;        // window closed
-                // Aabb3::intersects (aabb3.rs:246-253), strict on all three axes
-                if (!(as.x < bs.y)) continue;
-                const float2 bu = __ldg(eU + f);
-                if (!(au.y > bu.x && au.x < bu.y)) continue;
-                const float2 bv = __ldg(eV + f);
-                if (!(av.y > bv.x && av.x < bv.y)) continue;
-                // report only in the canonical cell of the pair
-                const int bu0 = cell_coord(bu.x, org_u, inv_u, nu);
-                const int bv0 = cell_coord(bv.x, org_v, inv_v, nv);
-                if ((au0 > bu0 ? au0 : bu0) != cu || (av0 > bv0 ? av0 : bv0) != cv) continue;
-                if (sharded) {
-                    const uint32_t bp = __ldg(epos + f);
-                    if (bp < b_lo || bp >= b_hi) continue;
+                if (!(bs.x < as.y)) {
+                    open = false;  // window closed
+                } else if (as.x < bs.y) {
+                    // Aabb3::intersects (aabb3.rs:246-253), strict on all three axes
+                    const float2 bu = __ldg(eU + f);
+                    const float2 bv = __ldg(eV + f);
+                    if (au.y > bu.x && au.x < bu.y && av.y > bv.x && av.x < bv.y) {
+                        // report only in the canonical cell of the pair
+                        const int bu0 = cell_coord(bu.x, org_u, inv_u, nu);
+                        const int bv0 = cell_coord(bv.x, org_v, inv_v, nv);
+                        if ((au0 > bu0 ? au0 : bu0) == cu && (av0 > bv0 ? av0 : bv0) == cv) {
+                            bp = __ldg(epos + f);
+                            hit = !sharded || (bp >= b_lo && bp < b_hi);
+                        }
+                    }
                 }
-                if (pass == 0) {
-                    ++mine;
-                } else {
-                    const unsigned long long key = pair_key(a, __ldg(epos + f), pos_bits, remap);
-                    if (w < cap) keys[w] = key;
-                    if (seg_cnt) atomicAdd(seg_cnt + (uint32_t)(key >> pos_bits), 1u);
-                    ++w;
-                }
+                ++f;
             }
         }
-        if (pass == 0) {
-            uint32_t incl = mine;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= (unsigned)off) incl += o;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            if (hit) {
+                const unsigned long long key = pair_key(a, bp, pos_bits, remap);
+                mystage[fill + __popc(m & ((1u << lane) - 1u))] = key;
+                if (seg_cnt) atomicAdd(seg_cnt + (uint32_t)(key >> pos_bits), 1u);
             }
-            unsigned long long base = 0;
-            if (lane == 31u && incl) base = atomicAdd(&G->n_pairs, (unsigned long long)incl);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            w = base + (incl - mine);
+            fill += __popc(m);
+            if (fill > STAGE - 32) flush();
         }
     }
+    if (fill) flush();
 }
 
 // large boxes (not in the grid): forward against every b of their window, backward against every
