@@ -521,9 +521,10 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "how": "cb2_gjk3_intersection on pinned host buffers: chunks through one copy-in "
-                       "stream, three compute streams and one copy-out stream, all inside the "
-                       "timed call"},
+                "how": "cb2_gjk3_intersection on pinned host buffers: 768 K-pair chunks through one "
+                       "copy-in stream, one high-priority stream for the GJK stages (running ahead), "
+                       "three streams for the EPA tiers and one copy-out stream over eight staging "
+                       "buffers, all inside the timed call"},
         "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
