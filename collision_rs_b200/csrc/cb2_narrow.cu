@@ -455,8 +455,11 @@ CB2_DI bool refill_lane(const narrow_args& A, bool want, uint64_t& i) {
 
 // GJK::intersect (gjk/mod.rs:101-146) as the first stage of the GJK -> EPA pipeline, lane-refill form
 // of k_gjk_hits: misses exit after 1-2 supports, hits after ~4, so a refilled lane is worth ~2x.
+#ifndef CB2_GJK_MINB  // resident blocks per SM the GJK stage is compiled for (4: 128 registers)
+#define CB2_GJK_MINB 4
+#endif
 template <bool FULL>
-__global__ void __launch_bounds__(128, 4) k_gjk_hits_p(narrow_args A, narrow_ws W) {
+__global__ void __launch_bounds__(128, CB2_GJK_MINB) k_gjk_hits_p(narrow_args A, narrow_ws W) {
     const uint32_t max_it = A.settings.max_iterations;
     bool active = false, done = false;
     uint64_t i = 0;
