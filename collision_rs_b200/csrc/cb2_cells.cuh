@@ -124,6 +124,10 @@ CB2_NOINLINE_DEVICE float4 poly_hill_climb(const float4* __restrict__ verts, uin
 
 // local-space support point of a polyhedron for direction d (already in model space);
 // R = max |vertex| of the shape, rounded up
+// ROLLED: keep the candidate loop rolled.  Unrolled by two (the compiler's choice) a warp in which
+// one lane holds five candidates runs an eight-candidate block for everybody: k_gjk_hits_p gains
+// 6 % rolled, k_time_of_impact_p loses 14 % — so the caller decides.
+template <bool ROLLED = false>
 CB2_DI f3 poly_local_support(const poly_tables& T, const poly_ref& s, float R, f3 d) {
     const float4* __restrict__ verts = T.verts + s.voff;
     const uint32_t N = s.cfg & 0xFFu;
@@ -150,9 +154,7 @@ CB2_DI f3 poly_local_support(const poly_tables& T, const poly_ref& s, float R, f
              z = __funnelshift_r(rec.z, rec.w, bits), w = rec.w >> bits;
     f3 best = zero3();  // no dot > -inf: P::origin() (polyhedron.rs:163)
     float best_dot = -INFINITY;
-    // (left to the compiler, which unrolls by two: rolled, k_gjk_hits_p gains 6 % and
-    // k_time_of_impact_p loses 14 %)
-    for (uint32_t base = 0; base < cnt; base += 4u) {
+    auto trip = [&](uint32_t base) {
         uint32_t i0, i1, i2, i3;
         if (!wide) {
             i0 = x & 0xFFu; i1 = (x >> 8) & 0xFFu; i2 = (x >> 16) & 0xFFu; i3 = x >> 24;
@@ -171,6 +173,12 @@ CB2_DI f3 poly_local_support(const poly_tables& T, const poly_ref& s, float R, f
         if (rem > 1u && d1 > best_dot) { best_dot = d1; best = mk3(v1.x, v1.y, v1.z); }
         if (rem > 2u && d2 > best_dot) { best_dot = d2; best = mk3(v2.x, v2.y, v2.z); }
         if (rem > 3u && d3 > best_dot) { best_dot = d3; best = mk3(v3.x, v3.y, v3.z); }
+    };
+    if constexpr (ROLLED) {
+#pragma unroll 1
+        for (uint32_t base = 0; base < cnt; base += 4u) trip(base);
+    } else {
+        for (uint32_t base = 0; base < cnt; base += 4u) trip(base);
     }
     return best;
 }

@@ -145,9 +145,10 @@ CB2_NOINLINE_DEVICE f3 other_local_support(uint32_t kind, f3 h, f3 d) {
 
 // Primitive3 dispatch (primitive3.rs:153-176); ConvexPolyhedron VertexOnly (polyhedron.rs:160-176)
 // goes through the support cells (cb2_cells.cuh)
+template <bool ROLLED = false>
 CB2_DI f3 local_support(const shape_table& T, const shape& s, f3 d) {
     if (s.kind == K_CUBOID) return cuboid_local_support(s.h, d);
-    if (s.kind == K_POLY) return poly_local_support(T.poly, s.poly, s.h.x, d);
+    if (s.kind == K_POLY) return poly_local_support<ROLLED>(T.poly, s.poly, s.h.x, d);
     if (s.kind == K_SPHERE) return sphere_local_support(s.h.x, d);
     if (s.kind == K_POLY_HE) {
         const float4 r = poly_hill_climb(T.poly.verts + s.poly.voff, s.poly.vcnt, d);
@@ -157,10 +158,11 @@ CB2_DI f3 local_support(const shape_table& T, const shape& s, f3 d) {
     return other_local_support(s.kind, s.h, d);
 }
 
+template <bool ROLLED = false>
 CB2_DI f3 support_point(const shape_table& T, const shape& s, const xform& t, f3 dir) {
     // Particle: transform.transform_point(origin) — no inverse transform (primitive3.rs:164)
     if (s.kind == K_PARTICLE) return transform_point(t, zero3());
-    return transform_point(t, local_support(T, s, inverse_transform_vector(t, dir)));
+    return transform_point(t, local_support<ROLLED>(T, s, inverse_transform_vector(t, dir)));
 }
 // support_point for kernels in which NP lanes (lane ^ STEP, lane ^ 2 STEP, ...) hold the same shape,
 // transform and direction (the EPA groups: even lanes carry the left shape, odd lanes the right

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(128, CB2_GJK_MINB) k_gjk_hits_p(narrow_args A,
         if (__all_sync(0xffffffffu, done && !active)) break;
         // ---- one Minkowski support, then the state's step ---------------------------------------------
         f3 v = zero3(), a = zero3();
-        if (active) minkowski<FULL>(p, d, v, a);
+        if (active) minkowski<FULL, true>(p, d, v, a);
         bool finished = false, inside = false;
         if (active) {
             if (dot(v, d) <= 0.0f) {

@@ -23,10 +23,10 @@ struct pair_in {
     xform lt, rt;
 };
 
-template <bool WITH_A>
+template <bool WITH_A, bool ROLLED = false>
 CB2_DI void minkowski(const pair_in& p, f3 dir, f3& v, f3& a) {
-    const f3 l = support_point(p.T, p.ls, p.lt, dir);
-    const f3 r = support_point(p.T, p.rs, p.rt, -dir);
+    const f3 l = support_point<ROLLED>(p.T, p.ls, p.lt, dir);
+    const f3 r = support_point<ROLLED>(p.T, p.rs, p.rt, -dir);
     v = l - r;
     if (WITH_A) a = l;
 }
