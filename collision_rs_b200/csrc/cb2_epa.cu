@@ -62,8 +62,10 @@
 #endif
 namespace cb2 {
 
-// per-group polytope scratch in shared memory
-template <int FCAP, int VCAP, int OCAP>
+// per-group polytope scratch in shared memory.  ADJ_IN_PV (one adjacency word per vertex row, i.e.
+// VCAP <= 32): the row of vertex v lives in the unused fourth word of pv[v] instead of an array of
+// its own — 96 bytes per group less, which is what lets a 20th block fit an SM in tier 0.
+template <int FCAP, int VCAP, int OCAP, bool ADJ_IN_PV = (VCAP <= 32)>
 struct poly_smem {
     static constexpr int AW = (VCAP + 31) / 32;  // adjacency words per vertex row
     float4 fnd[FCAP];          // normal.xyz, distance
@@ -74,6 +76,19 @@ struct poly_smem {
     uint8_t order[OCAP];       // visible faces in the order Polytope::add examines them
     uint16_t mv[OCAP];         // swap_remove: tail face (mv >> 8) lands in hole (mv & 255)
     uint64_t mbar;             // tracks the bulk copy that resumes a polytope from the previous tier
+    CB2_DI uint32_t* adj_word_ptr(uint32_t w) { return &adj[w]; }
+};
+template <int FCAP, int VCAP, int OCAP>
+struct poly_smem<FCAP, VCAP, OCAP, true> {
+    static constexpr int AW = 1;
+    float4 fnd[FCAP];
+    float4 pv[VCAP];           // (x, y, z, adjacency row of this vertex: all zero between iterations)
+    uint32_t fidx[FCAP];
+    uint16_t elist[OCAP];
+    uint8_t order[OCAP];
+    uint16_t mv[OCAP];
+    uint64_t mbar;
+    CB2_DI uint32_t* adj_word_ptr(uint32_t w) { return reinterpret_cast<uint32_t*>(&pv[w]) + 3; }
 };
 
 // Where the groups of a warp keep their polytopes.  ncu (round 2, 4 M pairs) showed 60 % of tier 0's
@@ -87,7 +102,9 @@ template <class PS, int NG>
 struct group_layout {
     static constexpr size_t TARGET = NG == 8 ? 112 : (NG == 4 ? 32 : 0);
     // (16 groups: an odd multiple of 16 bytes, so the groups visit all eight 16-byte columns of a 128-byte row)
-    static constexpr size_t STRIDE = NG == 16 ? sizeof(PS) + ((sizeof(PS) / 16) % 2 ? 0 : 16)
+    // (8 groups: any ODD multiple of 16 bytes does what -16 does — eight distinct 16-byte columns,
+    // slots 4 apart 64 bytes apart — so a record whose size already is one takes no padding)
+    static constexpr size_t STRIDE = (NG == 16 || NG == 8) ? sizeof(PS) + ((sizeof(PS) / 16) % 2 ? 0 : 16)
                                      : (NG >= 4 ? sizeof(PS) + ((TARGET + 128 - sizeof(PS) % 128) % 128) : sizeof(PS));
     static constexpr size_t BYTES = STRIDE * NG;
     static_assert(STRIDE % 16 == 0, "float4 members");
@@ -315,7 +332,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     const uint32_t max_it = A.settings.max_iterations;
     const float epa_tol = A.settings.epa_tolerance;
     // the adjacency matrix is kept all-zero between iterations
-    for (int k = gl; k < VCAP * AW; k += G) P.adj[k] = 0u;
+    for (int k = gl; k < VCAP * AW; k += G) *P.adj_word_ptr(k) = 0u;
     uint32_t resume_phase = 0;  // parity of the group's mbarrier
     if (RF > 0 && gl == 0) mbar_init(&P.mbar, 1);
     __syncwarp(gmask);
@@ -592,9 +609,9 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         auto pass_set = [&](uint32_t idx) {
             const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
             // (one word per row when VCAP <= 32: no word index, no bit mask)
-            const uint32_t o0 = atomicOr(&P.adj[adj_word(v0, v1)], 1u << adj_bit(v1));
-            const uint32_t o1 = atomicOr(&P.adj[adj_word(v1, v2)], 1u << adj_bit(v2));
-            const uint32_t o2 = atomicOr(&P.adj[adj_word(v2, v0)], 1u << adj_bit(v0));
+            const uint32_t o0 = atomicOr(P.adj_word_ptr(adj_word(v0, v1)), 1u << adj_bit(v1));
+            const uint32_t o1 = atomicOr(P.adj_word_ptr(adj_word(v1, v2)), 1u << adj_bit(v2));
+            const uint32_t o2 = atomicOr(P.adj_word_ptr(adj_word(v2, v0)), 1u << adj_bit(v0));
             dup |= ((o0 >> adj_bit(v1)) | (o1 >> adj_bit(v2)) | (o2 >> adj_bit(v0))) & 1u;
         };
         int ne = 0;
@@ -602,9 +619,9 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
             uint32_t keep = 0, v0 = 0, v1 = 0, v2 = 0;
             if (active) {
                 v0 = idx & 255u; v1 = (idx >> 8) & 255u; v2 = (idx >> 16) & 255u;
-                keep = (~(P.adj[adj_word(v1, v0)] >> adj_bit(v0)) & 1u) |
-                       ((~(P.adj[adj_word(v2, v1)] >> adj_bit(v1)) & 1u) << 1) |
-                       ((~(P.adj[adj_word(v0, v2)] >> adj_bit(v2)) & 1u) << 2);
+                keep = (~(*P.adj_word_ptr(adj_word(v1, v0)) >> adj_bit(v0)) & 1u) |
+                       ((~(*P.adj_word_ptr(adj_word(v2, v1)) >> adj_bit(v1)) & 1u) << 1) |
+                       ((~(*P.adj_word_ptr(adj_word(v0, v2)) >> adj_bit(v2)) & 1u) << 2);
             }
             uint32_t all = keep << (3 * gl);
 #pragma unroll
@@ -619,9 +636,9 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
             const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
 #pragma unroll
             for (int q = 0; q < AW; ++q) {
-                P.adj[v0 * AW + q] = 0u;
-                P.adj[v1 * AW + q] = 0u;
-                P.adj[v2 * AW + q] = 0u;
+                *P.adj_word_ptr(v0 * AW + q) = 0u;
+                *P.adj_word_ptr(v1 * AW + q) = 0u;
+                *P.adj_word_ptr(v2 * AW + q) = 0u;
             }
         };
         const bool act0 = edges && gl < nvis;
