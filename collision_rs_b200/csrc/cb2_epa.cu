@@ -22,12 +22,14 @@
 //    edge occurs twice; the (non-manifold) exception is detected by the same atomicOr and the
 //    pair goes to the serial second-chance kernel (cb2_narrow.cu).
 //  * The polytope lives in per-group shared memory in three tiers: 40 faces / 24 vertices and
-//    72 / 40 (4 and 8 lanes per pair; ~86 % and ~99.5 % of pairs) and 208 / 104 (8 lanes; the
+//    72 / 40 (4 and 8 lanes per pair; ~86 % and ~99.5 % of pairs) and 208 / 104 (16 lanes; the
 //    manifold worst case 2V-4 at the 100-iteration cap).  Small tiers buy residency: tier 0 runs
 //    20 warps per SM.  A pair that outgrows its tier dumps its polytope to global memory and the
 //    next tier RESUMES it at the same iteration (nothing is recomputed).  sup_a of each polytope
 //    vertex is only read by the final contact (epa3d.rs:84-114), so it lives in a global
 //    scratch, not shared memory.
+#include <type_traits>
+
 #include "cb2_epa_team.cuh"
 #include "cb2_tma.cuh"
 
@@ -110,6 +112,9 @@ struct group_layout {
     static_assert(STRIDE % 16 == 0, "float4 members");
     CB2_DI static int slot(int gw) { return NG == 8 ? ((gw & 1) * 4 + (gw >> 1)) : gw; }
 };
+
+CB2_DI int popc_any(uint32_t v) { return __popc(v); }
+CB2_DI int popc_any(unsigned long long v) { return __popcll(v); }
 
 // shared-memory loads the compiler may not move into a branch
 CB2_DI float4 lds128(uint32_t a) {
@@ -293,7 +298,7 @@ enum : int { S_FETCH = 0, S_RUN = 1, S_EXIT = 2 };
 // RF/RV: caps of the tier whose dumps this instantiation resumes (0 = none)
 template <int G, int FCAP, int VCAP, int OCAP, int RF, int RV>
 __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa(epa_args C) {
-    static_assert(G == 2 || G == 4 || G == 8, "3*G edge-keep bits must fit one word");
+    static_assert(G == 2 || G == 4 || G == 8 || G == 16, "3*G edge-keep bits must fit two words");
     static_assert(RF <= FCAP && RV <= VCAP, "a resumed polytope must fit");
     using PS = poly_smem<FCAP, VCAP, OCAP>;
     constexpr int FW = (FCAP + 31) / 32;
@@ -623,14 +628,16 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                        ((~(*P.adj_word_ptr(adj_word(v2, v1)) >> adj_bit(v1)) & 1u) << 1) |
                        ((~(*P.adj_word_ptr(adj_word(v0, v2)) >> adj_bit(v2)) & 1u) << 2);
             }
-            uint32_t all = keep << (3 * gl);
+            // (three keep bits per lane: one word up to 8 lanes per pair, two beyond)
+            using keep_t = typename std::conditional<(3 * G > 32), unsigned long long, uint32_t>::type;
+            keep_t all = (keep_t)keep << (3 * gl);
 #pragma unroll
             for (int off = G / 2; off >= 1; off >>= 1) all |= __shfl_xor_sync(0xffffffffu, all, off);
-            int pos = ne + __popc(all & ((1u << (3 * gl)) - 1u));
+            int pos = ne + popc_any(all & (((keep_t)1 << (3 * gl)) - 1));
             if (keep & 1u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v0 | (v1 << 8)); ++pos; }
             if (keep & 2u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v1 | (v2 << 8)); ++pos; }
             if (keep & 4u) { if (pos < OCAP) P.elist[pos] = (uint16_t)(v2 | (v0 << 8)); }
-            ne += __popc(all);
+            ne += popc_any(all);
         };
         auto pass_clear = [&](uint32_t idx) {
             const uint32_t v0 = idx & 255u, v1 = (idx >> 8) & 255u, v2 = (idx >> 16) & 255u;
@@ -886,7 +893,10 @@ constexpr int T0_G = CB2_T0_G, T0_F = CB2_T0_F, T0_V = CB2_T0_V, T0_O = CB2_T0_O
 constexpr bool LANE_T1 = CB2_LANE_TIER1 && !TIER0_GROUP;
 constexpr int T1_G = CB2_T1_G, T1_F = LANE_T1 ? L1_F : CB2_T1_F, T1_V = LANE_T1 ? L1_V : CB2_T1_V,
               T1_O = CB2_T1_O;
-constexpr int T2_G = 8, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
+#ifndef CB2_T2_G   // 16 lanes per pair in the last tier: it is bound by the latency of its longest pairs
+#define CB2_T2_G 16  // (cfg 3: 0.48 -> 0.36 ms; cfg 2's curved pairs, which start here: 96 -> 128 M pairs/s)
+#endif
+constexpr int T2_G = CB2_T2_G, T2_F = 208, T2_V = 104, T2_O = 96;  // manifold worst case at 100 iterations
 
 template <int G, int F, int V, int O, int RF, int RV>
 static int epa_blocks(int sm_count) {
