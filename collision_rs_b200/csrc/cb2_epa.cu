@@ -44,7 +44,7 @@
 #ifndef CB2_OPT_FOLD    // closest_face_to_origin folded into the visibility pass and Face::new: bit-identical,
 #define CB2_OPT_FOLD 0  // but no faster (tier 0 14.03 ms with, 13.95 ms without: three more live registers)
 #endif
-#ifndef CB2_VIS2        // visibility pass: two faces per lane and trip (needs CB2_OPT_FOLD == 0)
+#ifndef CB2_VIS2        // visibility pass: two faces per lane and trip
 #define CB2_VIS2 1
 #endif
 #ifndef CB2_EPA_MIN_BLOCKS
@@ -417,6 +417,29 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                     }
                     __syncwarp(gmask);
                     // ... and Face::new (3,2,1) (3,1,0) (3,0,2) (2,0,1), epa3d.rs:201-208
+#if CB2_OPT_FOLD
+                    if (G >= 4) {
+                        // lanes 0..3 of the group each build one face and hold its distance: the first
+                        // strictly smallest (NaN never smaller; a NaN at index 0 sticks) by a butterfly
+                        float fd = INFINITY;
+                        uint32_t fi = (uint32_t)gl;
+                        if (gl < 4) {
+                            const uint32_t tri = gl == 0 ? 0x010203u : (gl == 1 ? 0x000103u : (gl == 2 ? 0x020003u : 0x010002u));
+                            fd = ps_face_new(P, gl, tri & 255u, (tri >> 8) & 255u, tri >> 16);
+                        }
+                        const float d0 = __shfl_sync(gmask, fd, gw * G);
+                        if (fd != fd) fd = INFINITY;
+#pragma unroll
+                        for (int off = 2; off >= 1; off >>= 1) {
+                            const float ob = __shfl_xor_sync(gmask, fd, off);
+                            const uint32_t oi = __shfl_xor_sync(gmask, fi, off);
+                            if (ob < fd || (ob == fd && oi < fi)) { fd = ob; fi = oi; }
+                        }
+                        fd = __shfl_sync(gmask, fd, gw * G);  // (groups wider than four: lane 0 holds the result)
+                        fi = __shfl_sync(gmask, fi, gw * G);
+                        best_face = (d0 != d0 || fd == INFINITY) ? 0 : (int)fi;
+                    } else
+#endif
                     for (int j = gl; j < 4; j += G) {
                         const uint32_t tri = j == 0 ? 0x010203u : (j == 1 ? 0x000103u : (j == 2 ? 0x020003u : 0x010002u));
                         ps_face_new(P, j, tri & 255u, (tri >> 8) & 255u, tri >> 16);
@@ -505,7 +528,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
         vis.clear();
         float cd = INFINITY;
         int ci = -1;
-        bool ctie = false;
+        uint32_t ctie = 0u;
         const int vis_top = __reduce_max_sync(0xffffffffu, add ? nf : 0);  // most faces any group tests
         {
             const int nf_max = vis_top;
@@ -536,6 +559,20 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                         const float dv1 = dot(mk3(fn1.x, fn1.y, fn1.z), sup_v - mk3(p1.x, p1.y, p1.z));
                         const bool v0 = add & (f < nf) & (dv0 > 0.0f);
                         const bool v1 = add & (f + G < nf) & (dv1 > 0.0f);
+#if CB2_OPT_FOLD
+                        {   // smallest distance among the faces that stay (equal or NaN: Vec order decides)
+                            const bool s0 = add & (f < nf) & !v0;
+                            const bool l0 = s0 & (fn0.w < cd);
+                            ctie |= (uint32_t)(s0 & !l0 & !(fn0.w > cd));
+                            cd = l0 ? fn0.w : cd;
+                            ci = l0 ? f : ci;
+                            const bool s1 = add & (f + G < nf) & !v1;
+                            const bool l1 = s1 & (fn1.w < cd);
+                            ctie |= (uint32_t)(s1 & !l1 & !(fn1.w > cd));
+                            cd = l1 ? fn1.w : cd;
+                            ci = l1 ? f + G : ci;
+                        }
+#endif
                         const uint32_t n0 = (__ballot_sync(0xffffffffu, v0) >> (gw * G)) & gbits;
                         const uint32_t n1 = (__ballot_sync(0xffffffffu, v1) >> (gw * G)) & gbits;
                         acc += (n0 | (n1 << G)) * pw;
@@ -552,7 +589,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
 #if CB2_OPT_FOLD
                         const bool stay = live & !v;
                         const bool lt = stay & (fn.w < cd);
-                        ctie |= stay & !lt & !(fn.w > cd);  // equal or NaN: Vec order decides
+                        ctie |= (uint32_t)(stay & !lt & !(fn.w > cd));  // equal or NaN: Vec order decides
                         cd = lt ? fn.w : cd;
                         ci = lt ? f : ci;
 #endif
@@ -575,7 +612,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
 #if CB2_OPT_FOLD
                         if (!v) {
                             if (fn.w < cd) { cd = fn.w; ci = f; }
-                            else if (!(fn.w > cd)) ctie = true;
+                            else if (!(fn.w > cd)) ctie = 1u;
                         }
 #endif
                     }
@@ -694,7 +731,7 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
                     const float dist = ps_face_new(P, len + k, (uint32_t)nv, e & 255u, e >> 8);
 #if CB2_OPT_FOLD
                     if (dist < cd) { cd = dist; ci = len + k; }
-                    else if (!(dist > cd)) ctie = true;
+                    else if (!(dist > cd)) ctie = 1u;
 #else
                     (void)dist;
 #endif
@@ -708,9 +745,9 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
             const float ob = __shfl_xor_sync(0xffffffffu, cd, off);
             const int oi = __shfl_xor_sync(0xffffffffu, ci, off);
             if (ob < cd) { cd = ob; ci = oi; }
-            else if (ob == cd && (oi | ci) >= 0) ctie = true;
+            else if (ob == cd && (oi | ci) >= 0) ctie = 1u;
         }
-        const bool gtie = (__ballot_sync(0xffffffffu, ctie) & gmask) != 0u;
+        const bool gtie = (__ballot_sync(0xffffffffu, ctie != 0u) & gmask) != 0u;
         const int next_best = (grow && !gtie) ? ci : -1;
 #else
         const int next_best = -1;
