@@ -5,6 +5,9 @@
 
 #include "cb2_cells.cuh"
 #include "cb2_gjk.cuh"
+#include <cstdio>
+#include <cstdlib>
+
 #include "cb2_kernels.h"
 
 namespace cb2 {
@@ -158,6 +161,16 @@ __global__ void __launch_bounds__(128) k_build_cells(const dshape* __restrict__ 
 // choose the cube-map resolution of a polyhedron with V vertices
 uint32_t cells_resolution(uint32_t V) {
     if (V <= 8 || V > 65535) return 0;  // tiny: the scan is the list; huge: u16 indices do not fit
+    // CB2_CELL_N="a,b,c": resolutions for V <= 64, V <= 512 and beyond (experiments)
+    static const int* ovr = [] {
+        static int v[3] = {0, 0, 0};
+        const char* e = std::getenv("CB2_CELL_N");
+        if (e && std::sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3 && v[0] > 0 && v[1] > 0 && v[2] > 0 &&
+            v[0] < 64 && v[1] < 64 && v[2] < 64)
+            return (const int*)v;
+        return (const int*)nullptr;
+    }();
+    if (ovr) return (uint32_t)(V <= 64 ? ovr[0] : (V <= 512 ? ovr[1] : ovr[2]));
     if (V <= 64) return 4;
     if (V <= 512) return 8;
     return 16;
