@@ -588,6 +588,10 @@ __global__ void __launch_bounds__(256) k_sap_unpack(const unsigned long long* __
     reinterpret_cast<uint2*>(pairs)[p] = high_first ? make_uint2(high, low) : make_uint2(low, high);
 }
 
+#ifndef CB2_SWEEP_L   // lanes per entry of k_grid_sweep.  Measured at 1 M boxes (the whole call, ordered):
+#define CB2_SWEEP_L 1 // 1: 0.688 ms, 2: 0.717, 4: 0.820, 8: 1.023 — most windows are short, more lanes per
+#endif                // entry only multiply the idle trips; a thread per entry stays
+template <int L>
 __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ eS,
                                                    const float2* __restrict__ eU,
                                                    const float2* __restrict__ eV,
@@ -601,7 +605,10 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
     // b_lo/b_hi: this GPU's shard of the pair list — only pairs whose LATER box (the `b` the
     // reference's Vec is ordered by) sits at a sorted position in [b_lo, b_hi) are reported
     const bool sharded = b_lo != 0u || b_hi != 0xFFFFFFFFu;
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // L lanes share one entry and take its window L candidates at a time (an experiment against the
+    // 10 of 32 lanes one thread per entry keeps busy; L = 1 is the product path, see CB2_SWEEP_L)
+    const uint64_t e = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+    const unsigned sub = threadIdx.x & (L - 1);
     const float org_u = G->org_u, inv_u = G->inv_u, org_v = G->org_v, inv_v = G->inv_v;
     const int nu = G->nu, nv = G->nv;
     // no early return: every lane takes part in the warp-wide reservation below
@@ -638,40 +645,40 @@ __global__ void __launch_bounds__(256) k_grid_sweep(const float2* __restrict__ e
         fill = 0;
     };
     const uint32_t a = valid ? __ldg(epos + e) : 0u;
-    uint64_t f = e + 1;
-    bool open = valid;
+    uint64_t f = e + 1 + sub;
+    bool open = valid;  // uniform over the L lanes of an entry
+    const unsigned lane_bit = 1u << lane;
+    const unsigned last_of_sub = 1u << ((lane & ~(unsigned)(L - 1)) + (L - 1));
     while (__any_sync(0xffffffffu, open)) {
-        bool hit = false;
+        bool hit = false, inwin = false;
         uint32_t bp = 0;
-        if (open) {
-            if (f >= n_entries || __ldg(ecell + f) != cell) {
-                open = false;
-            } else {
-                const float2 bs = __ldg(eS + f);  // entries of a cell ascend by position, so by min_s
-                if (!(bs.x < as.y)) {
-                    open = false;  // window closed
-                } else if (as.x < bs.y) {
-                    // Aabb3::intersects (aabb3.rs:246-253), strict on all three axes
-                    const float2 bu = __ldg(eU + f);
-                    const float2 bv = __ldg(eV + f);
-                    if (au.y > bu.x && au.x < bu.y && av.y > bv.x && av.x < bv.y) {
-                        // report only in the canonical cell of the pair
-                        const int bu0 = cell_coord(bu.x, org_u, inv_u, nu);
-                        const int bv0 = cell_coord(bv.x, org_v, inv_v, nv);
-                        if ((au0 > bu0 ? au0 : bu0) == cu && (av0 > bv0 ? av0 : bv0) == cv) {
-                            bp = __ldg(epos + f);
-                            hit = !sharded || (bp >= b_lo && bp < b_hi);
-                        }
+        if (open && f < n_entries && __ldg(ecell + f) == cell) {
+            const float2 bs = __ldg(eS + f);  // entries of a cell ascend by position, so by min_s
+            inwin = bs.x < as.y;              // ... and a closed window stays closed for every later f
+            if (inwin && as.x < bs.y) {
+                // Aabb3::intersects (aabb3.rs:246-253), strict on all three axes
+                const float2 bu = __ldg(eU + f);
+                const float2 bv = __ldg(eV + f);
+                if (au.y > bu.x && au.x < bu.y && av.y > bv.x && av.x < bv.y) {
+                    // report only in the canonical cell of the pair
+                    const int bu0 = cell_coord(bu.x, org_u, inv_u, nu);
+                    const int bv0 = cell_coord(bv.x, org_v, inv_v, nv);
+                    if ((au0 > bu0 ? au0 : bu0) == cu && (av0 > bv0 ? av0 : bv0) == cv) {
+                        bp = __ldg(epos + f);
+                        hit = !sharded || (bp >= b_lo && bp < b_hi);
                     }
                 }
-                ++f;
             }
         }
+        f += L;
+        // the window goes on iff the entry's LAST lane was still inside it
+        const unsigned win = __ballot_sync(0xffffffffu, inwin);
+        open = open && (win & last_of_sub) != 0u;
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (m) {
             if (hit) {
                 const unsigned long long key = pair_key(a, bp, pos_bits, remap);
-                mystage[fill + __popc(m & ((1u << lane) - 1u))] = key;
+                mystage[fill + __popc(m & (lane_bit - 1u))] = key;
                 if (seg_cnt) atomicAdd(seg_cnt + (uint32_t)(key >> pos_bits), 1u);
             }
             fill += __popc(m);
@@ -1045,8 +1052,8 @@ int sap_find_pairs(sap_workspace* w, const cb2_aabb3* aabbs, uint64_t n, uint32_
         tb = sort2;
         SAP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, c0, c1, p0, p1, (int64_t)nu, 0, cell_bits, st));
         k_grid_pack<<<nblk(nu, 256), 256, 0, st>>>(S, U, V, c1, p1, nu, G, eS, eU, eV);
-        k_grid_sweep<<<nblk(nu, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, nu, G, pk, kcap, pos_bits, remap,
-                                                      b_lo, b_hi, seg_arg);
+        k_grid_sweep<CB2_SWEEP_L><<<nblk(nu * CB2_SWEEP_L, 256), 256, 0, st>>>(eS, eU, eV, c1, p1, nu, G, pk, kcap,
+                                                                               pos_bits, remap, b_lo, b_hi, seg_arg);
         k_sap_large<<<592, 256, 0, st>>>(S, U, V, n, large, offs, ne, G, pk, kcap, pos_bits, remap, b_lo,
                                          b_hi, seg_arg);
         if (by_segment) {
