@@ -497,6 +497,45 @@ def test_support_cells_match_full_scan_on_a_million_pairs(ctx):
     assert bits_equal(gd[edst == 1], ed[edst == 1]).all()
 
 
+def test_split_support_on_tied_candidate_lists(ctx):
+    """The EPA groups split a support cell's candidate list over the lanes of a side (chunks of four,
+    greater dot wins, equal dots go to the lower part).  Lattice hulls make exact ties and long
+    lists — narrow (u8) records with more than eight candidates and wide (u16) ones — so the split
+    scan must still return the first strictly greatest vertex: compare FullResolution contacts with
+    CB2_NO_CELLS=1 (every support a full scan on one lane, no split) on 60 k pairs."""
+    rng = np.random.default_rng(2718)
+    verts, shapes = [], []
+    for k, cnt in enumerate((60, 120, 200, 250, 300, 400, 600, 90, 150, 36)):
+        span = 2 + k % 3  # coarse lattices: many exactly equal dots along the axes and diagonals
+        p = np.unique(rng.integers(-span, span + 1, (cnt * 3, 3)), axis=0).astype(np.float32)
+        p = p[rng.permutation(len(p))][:cnt] * np.float32(0.25 + 0.1 * k)
+        s = np.zeros(1, host_abi.SHAPE_DT)
+        s["kind"] = host_abi.POLYHEDRON
+        s["vtx_off"] = sum(len(v) for v in verts)
+        s["vtx_cnt"] = len(p)
+        verts.append(p)
+        shapes.append(s)
+    shapes = np.concatenate(shapes)
+    pv = np.concatenate(verts)
+    n = 60_000
+    l = rng.integers(0, len(shapes), n).astype(np.uint32)
+    r = rng.integers(0, len(shapes), n).astype(np.uint32)
+    lt, rt = W.random_xforms(rng, n, 0.8), W.random_xforms(rng, n, 0.8)
+    # axis-aligned poses keep the ties exact in world space as well
+    lt["q"][: n // 2] = (1.0, 0.0, 0.0, 0.0)
+    rt["q"][: n // 2] = (1.0, 0.0, 0.0, 0.0)
+    ctx.upload_shapes(shapes, pv)
+    got, gst = ctx.intersection(0, l, r, lt, rt)
+    plain = _ctx_with_env(CB2_NO_CELLS=1)
+    try:
+        plain.upload_shapes(shapes, pv)
+        exp, est = plain.intersection(0, l, r, lt, rt)
+    finally:
+        plain.close()
+    assert (est == 1).sum() > n // 10
+    assert_contacts_equal(got, gst, exp, est, "split support vs full scan")
+
+
 def test_degenerate_polyhedra(ctx, oracle):
     """Hulls the cell construction must not trip over: interior points, duplicated vertices,
     coplanar and collinear point sets, a single point, tiny and huge coordinates."""
