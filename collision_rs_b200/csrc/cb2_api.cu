@@ -70,7 +70,8 @@ struct cb2_ctx {
     int ahead = 1;                   // CB2_AHEAD=0: every stage of a chunk on the chunk's stream
     cudaStream_t s_in = nullptr, s_out = nullptr;  // the pipeline's copy-in / copy-out streams
     int n_cstreams = 3;  // compute streams the pipeline rotates over (CB2_NC overrides, <= NS)
-    bool ramp = true;  // short chunks at both ends of a batch (CB2_RAMP=0 disables)
+    int ramp = 3;       // short chunks at the front of a batch: chunk/2^ramp ... chunk/2 (CB2_RAMP=h[,t]; 0 disables)
+    int ramp_tail = 3;  // ... and at its end
     char* d_stage[NS] = {};
     size_t stage_cap = 0;
     sap_workspace* sap = nullptr;
@@ -210,7 +211,10 @@ int cb2_create(int device, cb2_ctx** out) {
         const char* e4 = std::getenv("CB2_NC");
         if (e4 && std::atoi(e4) >= 1 && std::atoi(e4) <= cb2_ctx::NS) c->n_cstreams = std::atoi(e4);
         const char* e5 = std::getenv("CB2_RAMP");
-        if (e5 && e5[0] == '0') c->ramp = false;
+        if (e5 && e5[0] >= '0' && e5[0] <= '5') {
+            c->ramp = c->ramp_tail = e5[0] - '0';
+            if (e5[1] == ',' && e5[2] >= '0' && e5[2] <= '5') c->ramp_tail = e5[2] - '0';
+        }
         const char* e6 = std::getenv("CB2_AHEAD");
         if (e6) c->ahead = std::atoi(e6);
         const char* e7 = std::getenv("CB2_TAIL_PRIO");
@@ -799,9 +803,9 @@ static int pipeline_prepare(cb2_ctx* c, size_t stage_bytes) {
 }
 // chunk sizes: short chunks at both ends (the first copy-in and the last copy-out are the only
 // transfers nothing can hide), full chunks in between
-static std::vector<uint64_t> pipeline_chunks(uint64_t n, uint64_t chunk, bool ramped) {
+static std::vector<uint64_t> pipeline_chunks(uint64_t n, uint64_t chunk, int levels, int levels_tail) {
     std::vector<uint64_t> v;
-    if (!ramped) {
+    if (levels <= 0 && levels_tail <= 0) {
         for (uint64_t b = 0; b < n; b += chunk) v.push_back(n - b < chunk ? n - b : chunk);
         return v;
     }
@@ -809,14 +813,16 @@ static std::vector<uint64_t> pipeline_chunks(uint64_t n, uint64_t chunk, bool ra
         v.push_back(n);
         return v;
     }
-    const uint64_t ramp[2] = {chunk / 4, chunk / 2};
+    std::vector<uint64_t> ramp, ramp_t;  // chunk / 2^levels ... chunk / 2
+    for (int k = levels; k >= 1; --k) ramp.push_back(chunk >> k);
+    for (int k = levels_tail; k >= 1; --k) ramp_t.push_back(chunk >> k);
     uint64_t head = 0, tail = 0;
     if (n >= 4 * chunk) {
         for (uint64_t r : ramp) {
             v.push_back(r);
             head += r;
         }
-        tail = ramp[0] + ramp[1];
+        for (uint64_t r : ramp_t) tail += r;
     }
     // the middle in equal chunks (no short remainder chunk: every chunk pays the latency of its tiers' tails)
     uint64_t left = n - head - tail;
@@ -827,10 +833,8 @@ static std::vector<uint64_t> pipeline_chunks(uint64_t n, uint64_t chunk, bool ra
         left -= m;
         --parts;
     }
-    if (tail) {
-        v.push_back(ramp[1]);
-        v.push_back(ramp[0]);
-    }
+    if (tail)
+        for (size_t k = ramp_t.size(); k-- > 0;) v.push_back(ramp_t[k]);
     return v;
 }
 template <class FIn, class FComp, class FOut>
@@ -838,7 +842,7 @@ static int pipeline_run(cb2_ctx* c, uint64_t n, FIn copy_in, FComp compute, FOut
                         bool split_tail = false) {
     static const bool trace = std::getenv("CB2_TRACE") && std::getenv("CB2_TRACE")[0] == '1';
     cudaStream_t s_in = c->s_in, s_out = c->s_out;
-    const std::vector<uint64_t> sizes = pipeline_chunks(n, c->chunk_pairs, c->ramp);
+    const std::vector<uint64_t> sizes = pipeline_chunks(n, c->chunk_pairs, c->ramp, c->ramp_tail);
     std::vector<cudaEvent_t> tev;
     cudaEvent_t t0 = nullptr;
     if (trace) {
@@ -938,7 +942,7 @@ template <class FIn, class FComp, class FOut>
 static int pipeline_run_ahead(cb2_ctx* c, uint64_t n, int nw, FIn copy_in, FComp compute, FOut copy_out) {
     static const bool trace = std::getenv("CB2_TRACE") && std::getenv("CB2_TRACE")[0] == '1';
     cudaStream_t s_in = c->s_in, s_out = c->s_out, s_front = c->s_front;
-    const std::vector<uint64_t> sizes = pipeline_chunks(n, c->chunk_pairs, c->ramp);
+    const std::vector<uint64_t> sizes = pipeline_chunks(n, c->chunk_pairs, c->ramp, c->ramp_tail);
     std::vector<uint64_t> starts(sizes.size());
     {
         uint64_t b = 0;
