@@ -650,6 +650,112 @@ __global__ void __launch_bounds__(128, 4) k_distance_p(narrow_args A) {
     }
 }
 
+
+// ---- staged refill ------------------------------------------------------------------------------------
+// A lane whose pair finished used to fetch and prepare its next pair on the spot (shape and transform
+// loads, two quaternion inversions, for time of impact the end poses and the ray): ~400 instructions
+// executed with the two or three lanes that happened to finish in that round — a quarter of
+// k_time_of_impact_p's instructions at 2.6 of 32 lanes (ncu, cfg 5).  Now the WARP prepares 32 pairs
+// at once into its slice of shared memory (every lane one pair: coalesced loads, full lanes) and a
+// finished lane merely pops a prepared entry ([word][entry] layout: lanes that pop different entries
+// hit different banks).  The queue hands out blocks of 32 pairs per warp.
+constexpr int STG_PAIR = 42;  // i, status, ls (8), rs (8), lt (12), rt (12)
+constexpr int STG_TOI = STG_PAIR + 11;  // + ray (3), end rotation (4), end scale, end displacement (3)
+struct stage_io {
+    uint32_t* p;  // word k of this entry at p[k * 32]
+    CB2_DI void put(int k, uint32_t v) const { p[k * 32] = v; }
+    CB2_DI void putf(int k, float v) const { p[k * 32] = __float_as_uint(v); }
+    CB2_DI uint32_t get(int k) const { return p[k * 32]; }
+    CB2_DI float getf(int k) const { return __uint_as_float(p[k * 32]); }
+    CB2_DI void put_shape(int k, const shape& s) const {
+        put(k, s.kind); putf(k + 1, s.h.x); putf(k + 2, s.h.y); putf(k + 3, s.h.z);
+        put(k + 4, s.poly.voff); put(k + 5, s.poly.vcnt); put(k + 6, s.poly.cell_off); put(k + 7, s.poly.cfg);
+    }
+    CB2_DI shape get_shape(int k) const {
+        shape s;
+        s.kind = get(k); s.h = mk3(getf(k + 1), getf(k + 2), getf(k + 3));
+        s.poly.voff = get(k + 4); s.poly.vcnt = get(k + 5); s.poly.cell_off = get(k + 6); s.poly.cfg = get(k + 7);
+        s.hang = 0u;
+        return s;
+    }
+    CB2_DI void put_xform(int k, const xform& t) const {
+        putf(k, t.q.s); putf(k + 1, t.q.x); putf(k + 2, t.q.y); putf(k + 3, t.q.z);
+        putf(k + 4, t.qi.s); putf(k + 5, t.qi.x); putf(k + 6, t.qi.y); putf(k + 7, t.qi.z);
+        putf(k + 8, t.disp.x); putf(k + 9, t.disp.y); putf(k + 10, t.disp.z); putf(k + 11, t.scale);
+    }
+    CB2_DI xform get_xform(int k) const {
+        xform t;
+        t.q.s = getf(k); t.q.x = getf(k + 1); t.q.y = getf(k + 2); t.q.z = getf(k + 3);
+        t.qi.s = getf(k + 4); t.qi.x = getf(k + 5); t.qi.y = getf(k + 6); t.qi.z = getf(k + 7);
+        t.disp = mk3(getf(k + 8), getf(k + 9), getf(k + 10));
+        t.scale = getf(k + 11);
+        t.unit = (t.scale == 1.0f);
+        return t;
+    }
+};
+// prepare pair i (start poses lt / rt) into an entry; TOI: also the end poses' part
+template <bool TOI>
+CB2_NOINLINE_DEVICE void stage_prepare(const narrow_args& A, uint64_t i, uint32_t* entry) {
+    const stage_io io{entry};
+    pair_in p;
+    const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p);
+    io.put(0, (uint32_t)i);
+    io.put(1, (uint32_t)bad);
+    if (bad) return;
+    io.put_shape(2, p.ls);
+    io.put_shape(10, p.rs);
+    io.put_xform(18, p.lt);
+    io.put_xform(30, p.rt);
+    if (TOI) {
+        const xform lt1 = load_xform(A.l_t1, i);
+        const xform rt1 = load_xform(A.r_t1, i);
+        const f3 left_lin_vel = transform_point(lt1, zero3()) - transform_point(p.lt, zero3());
+        const f3 right_lin_vel = transform_point(rt1, zero3()) - transform_point(p.rt, zero3());
+        const f3 ray = right_lin_vel - left_lin_vel;
+        io.putf(STG_PAIR, ray.x); io.putf(STG_PAIR + 1, ray.y); io.putf(STG_PAIR + 2, ray.z);
+        io.putf(STG_PAIR + 3, rt1.q.s); io.putf(STG_PAIR + 4, rt1.q.x); io.putf(STG_PAIR + 5, rt1.q.y);
+        io.putf(STG_PAIR + 6, rt1.q.z); io.putf(STG_PAIR + 7, rt1.scale);
+        io.putf(STG_PAIR + 8, rt1.disp.x); io.putf(STG_PAIR + 9, rt1.disp.y); io.putf(STG_PAIR + 10, rt1.disp.z);
+    }
+}
+// The warp's supply of prepared pairs.  next(): true for a lane that wanted a pair and got one
+// (`entry` then points at it); lanes that wanted one and got none stay idle until the next round,
+// or are `done` when the queue is exhausted.  Must be called by the whole warp.
+template <bool TOI, int NW>
+struct stage_supply {
+    uint32_t* buf;       // this warp's NW x 32 words
+    uint32_t head, count;
+    bool exhausted;
+    CB2_DI void init(uint32_t* b) { buf = b; head = count = 0u; exhausted = false; }
+    CB2_DI bool next(const narrow_args& A, bool want, bool& done, stage_io& entry) {
+        const unsigned need = __ballot_sync(0xffffffffu, want);
+        if (!need) return false;
+        const unsigned lane = threadIdx.x & 31u;
+        if (head == count && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(A.queue, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint64_t left = (uint64_t)base < A.n ? A.n - base : 0ull;
+            count = left < 32ull ? (uint32_t)left : 32u;
+            head = 0u;
+            exhausted = count == 0u;
+            __syncwarp();  // every pop of the previous fill has been read
+            if (lane < count) stage_prepare<TOI>(A, (uint64_t)base + lane, buf + lane);
+            __syncwarp();
+        }
+        if (head == count) {  // (only when exhausted)
+            if (want) done = true;
+            return false;
+        }
+        const uint32_t e = head + (uint32_t)__popc(need & ((1u << lane) - 1u));
+        const bool got = want && e < count;
+        entry.p = buf + (got ? e : 0u);
+        const uint32_t served = (uint32_t)__popc(need);
+        head = head + served < count ? head + served : count;
+        return got;
+    }
+};
+
 // GJK::intersection_time_of_impact, gjk/mod.rs:163-256 (+ iter_cap -> ST_NONCONVERGED)
 __global__ void __launch_bounds__(128, 4) k_time_of_impact_p(narrow_args A) {
     const float tol = A.settings.continuous_tolerance;
@@ -667,33 +773,33 @@ __global__ void __launch_bounds__(128, 4) k_time_of_impact_p(narrow_args A) {
     float lambda = 0.0f;
     int state = 0;
     uint32_t it = 0;
+    __shared__ uint32_t stage[4][STG_TOI * 32];
+    stage_supply<true, STG_TOI> supply;
+    supply.init(stage[threadIdx.x >> 5]);
     for (;;) {
-        uint64_t ni;
-        if (refill_lane(A, !active && !done, ni)) {
-            if (ni >= A.n) {
-                done = true;
+        stage_io e{nullptr};
+        if (supply.next(A, !active && !done, done, e)) {
+            i = e.get(0);
+            if (const uint8_t bad = (uint8_t)e.get(1)) {
+                store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, zero_contact());
+                A.out_status[i] = bad;
             } else {
-                i = ni;
-                if (const uint8_t bad = load_pair(A, i, A.l_t, A.r_t, p)) {
-                    store_contact(A.out_contact, i, CB2_FULL_RESOLUTION, zero_contact());
-                    A.out_status[i] = bad;
-                } else {
-                    const xform lt1 = load_xform(A.l_t1, i);
-                    const xform rt1 = load_xform(A.r_t1, i);
-                    const f3 left_lin_vel = transform_point(lt1, zero3()) - transform_point(p.lt, zero3());
-                    const f3 right_lin_vel = transform_point(rt1, zero3()) - transform_point(p.rt, zero3());
-                    ray = right_lin_vel - left_lin_vel;
-                    r1q = rt1.q;
-                    r1scale = rt1.scale;
-                    r1disp = rt1.disp;
-                    lambda = 0.0f;
-                    normal = zero3();
-                    ray_origin = zero3();
-                    s.n = 0;
-                    it = 0;
-                    state = 0;
-                    active = true;
-                }
+                p.ls = e.get_shape(2);
+                p.rs = e.get_shape(10);
+                p.lt = e.get_xform(18);
+                p.rt = e.get_xform(30);
+                ray = mk3(e.getf(STG_PAIR), e.getf(STG_PAIR + 1), e.getf(STG_PAIR + 2));
+                r1q.s = e.getf(STG_PAIR + 3); r1q.x = e.getf(STG_PAIR + 4); r1q.y = e.getf(STG_PAIR + 5);
+                r1q.z = e.getf(STG_PAIR + 6);
+                r1scale = e.getf(STG_PAIR + 7);
+                r1disp = mk3(e.getf(STG_PAIR + 8), e.getf(STG_PAIR + 9), e.getf(STG_PAIR + 10));
+                lambda = 0.0f;
+                normal = zero3();
+                ray_origin = zero3();
+                s.n = 0;
+                it = 0;
+                state = 0;
+                active = true;
             }
         }
         if (__all_sync(0xffffffffu, done && !active)) break;
@@ -1216,7 +1322,8 @@ cudaError_t launch_distance(const narrow_args& A, int sm_count, cudaStream_t st)
 }
 cudaError_t launch_time_of_impact(const narrow_args& A, int sm_count, cudaStream_t st) {
     if (A.n == 0) return cudaSuccess;
-    if (no_refill() || !A.queue || A.n > 0xFFFFFF00ull) {
+    // (the staged refill claims 32 pairs per warp and overshoots the 32-bit queue by at most that per warp)
+    if (no_refill() || !A.queue || A.n > 0xFFF00000ull) {
         k_time_of_impact<<<grid_for(A.n, 128), 128, 0, st>>>(A);
         return cudaGetLastError();
     }
