@@ -457,6 +457,37 @@ def main():
     hits = int((h_st == 1).sum())
     bad = int((h_st > 1).sum())
 
+    # ---- the same through the body-table call (cb2_gjk3_intersection_bodies): a quarter as many bodies as
+    #      pairs, poses drawn like cfg 3's, so the pair statistics match; only 8 bytes per pair go in ----
+    bodies_e2e = None
+    if not a.no_extra:
+        rngb = np.random.default_rng([777, 9, rank])
+        nb = max(n // 4, 2)
+        b_shape = pinned(rngb.integers(0, len(shapes), nb).astype(np.uint32))
+        b_t = pinned(W.random_xforms(rngb, nb, 0.75))
+        b_pairs = pinned(rngb.integers(0, nb, (n, 2)).astype(np.uint32))
+
+        def step_bodies():
+            ctx._ck(ctx.lib.cb2_gjk3_intersection_bodies(
+                ctx.h, 0, C.byref(W_SETTINGS), b_shape.data_ptr(), b_t.data_ptr(), nb, b_pairs.data_ptr(), n,
+                h_out.data_ptr(), h_st.data_ptr()))
+
+        step_bodies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_bodies()
+        torch.cuda.synchronize()
+        t_b = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_b, op=dist.ReduceOp.MAX)
+        bodies_e2e = {"value": n * world * e2e_steps / float(t_b.item()), "unit": UNIT, "bodies_per_gpu": nb,
+                      "pairs_per_gpu": n, "hit_fraction": float((h_st == 1).sum()) / n,
+                      "h2d_bytes_per_step": int(b_shape.numel() + b_t.numel() + b_pairs.numel()),
+                      "d2h_bytes_per_step": d2h,
+                      "what": "cb2_gjk3_intersection_bodies on pinned host buffers: body table uploaded per "
+                              "call, 8 bytes per pair streamed"}
+
     # ---- N > 1: what only exists on several GPUs (every rank takes part; rank 0 reports) -------------
     multi = {}
     if world > 1:
@@ -525,6 +556,7 @@ def main():
                        "copy-in stream, one high-priority stream for the GJK stages (running ahead), "
                        "three streams for the EPA tiers and one copy-out stream over eight staging "
                        "buffers, all inside the timed call"},
+        "e2e_bodies": bodies_e2e,
         "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }

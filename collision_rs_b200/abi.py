@@ -60,7 +60,7 @@ SYMBOLS = [
     "cb2_shapes_upload", "cb2_shapes_upload_faces",
     "cb2_gjk3_intersection", "cb2_gjk3_distance", "cb2_gjk3_time_of_impact",
     "cb2_gjk3_intersection_dev", "cb2_gjk3_distance_dev", "cb2_gjk3_time_of_impact_dev",
-    "cb2_gjk3_intersection_bodies_dev",
+    "cb2_gjk3_intersection_bodies", "cb2_gjk3_intersection_bodies_dev",
     "cb2_gjk3_intersect", "cb2_gjk3_get_contact_manifold",
     "cb2_gjk3_intersect_dev", "cb2_gjk3_get_contact_manifold_dev",
     "cb2_create_multi", "cb2_destroy_multi", "cb2_multi_device_count", "cb2_multi_ctx",
@@ -117,6 +117,7 @@ def load():
     lib.cb2_gjk3_intersection_dev.argtypes = [vp, u32, sp, vp, vp, vp, vp, u64, vp, vp, vp]
     lib.cb2_gjk3_distance_dev.argtypes = [vp, sp, vp, vp, vp, vp, u64, vp, vp, vp]
     lib.cb2_gjk3_time_of_impact_dev.argtypes = [vp, sp, vp, vp, vp, vp, vp, vp, u64, u32, vp, vp, vp]
+    lib.cb2_gjk3_intersection_bodies.argtypes = [vp, u32, sp, vp, vp, u64, vp, u64, vp, vp]
     lib.cb2_gjk3_intersection_bodies_dev.argtypes = [vp, u32, sp, vp, vp, vp, u64, vp, vp, vp]
     lib.cb2_create_multi.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
     lib.cb2_destroy_multi.argtypes = [vp]

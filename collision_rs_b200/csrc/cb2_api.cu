@@ -91,6 +91,9 @@ struct cb2_ctx {
     size_t cx_cap = 0;
     cb2_aabb3* d_lift = nullptr;  // cb2_sap2_find_collider_pairs_dev: the boxes lifted to 3-D
     uint64_t lift_cap = 0;
+    uint32_t* d_body_shape = nullptr;  // body table of cb2_gjk3_intersection_bodies (host buffers)
+    float4* d_body_t = nullptr;
+    uint64_t body_cap = 0;
     void* d_misc = nullptr;  // host-API SAP / AABB buffers
     size_t misc_cap = 0;
     // classified (polyhedron) narrow phase workspaces: [0..NS) follow the host-API streams,
@@ -268,6 +271,8 @@ void cb2_destroy(cb2_ctx* c) {
     if (c->d_bad_index) cudaFree(c->d_bad_index);
     if (c->h_bad_index) cudaFreeHost(c->h_bad_index);
     if (c->d_misc) cudaFree(c->d_misc);
+    if (c->d_body_shape) cudaFree(c->d_body_shape);
+    if (c->d_body_t) cudaFree(c->d_body_t);
     if (c->d_lift) cudaFree(c->d_lift);
     if (c->d_comp_off) cudaFree(c->d_comp_off);
     if (c->d_comp_shape) cudaFree(c->d_comp_shape);
@@ -1054,30 +1059,35 @@ static bool indices_in_range(const uint32_t* a, const uint32_t* b, uint64_t m, u
 }
 
 // Host-buffer path of the 3-D narrow phase.
+// `pair_body` (intersection only): the pairs index ONE body table — l_shape / l_t0 then hold n_bodies
+// shape indices / transforms, uploaded once per call, and only the 8 bytes of a pair's two body
+// indices are staged per pair (72 bytes per pair otherwise).
 static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_settings* settings,
                        const uint32_t* l_shape, const uint32_t* r_shape, const cb2_xform* l_t0,
                        const cb2_xform* l_t1, const cb2_xform* r_t0, const cb2_xform* r_t1,
                        uint64_t n, uint32_t iter_cap, cb2_contact* out_c, float* out_d,
-                       uint8_t* status) {
+                       uint8_t* status, const uint32_t* pair_body = nullptr, uint64_t n_bodies = 0) {
     if (!c) return CB2_ERR_ARG;
     int rc = check_settings(c, settings);
     if (rc) return rc;
     if (op == OP_INTERSECTION && strategy > CB2_COLLISION_ONLY) return fail(c, CB2_ERR_ARG, "bad strategy");
     if (n == 0) return CB2_OK;
     if (!c->d_shapes) return fail(c, CB2_ERR_ARG, "cb2_shapes_upload has not been called");
-    if (!l_shape || !r_shape || !l_t0 || !r_t0 || !status) return fail(c, CB2_ERR_ARG, "null argument");
+    const bool bodies = pair_body != nullptr;
+    if (!l_shape || !l_t0 || !status || (!bodies && (!r_shape || !r_t0))) return fail(c, CB2_ERR_ARG, "null argument");
+    if (bodies && (op != OP_INTERSECTION || n_bodies == 0)) return fail(c, CB2_ERR_ARG, "empty body table");
     if (op == OP_DISTANCE ? !out_d : !out_c) return fail(c, CB2_ERR_ARG, "null output");
     if (op == OP_TOI && (!l_t1 || !r_t1)) return fail(c, CB2_ERR_ARG, "null end transform");
     CK(c, cudaSetDevice(c->device));
     const uint64_t chunk = n < c->chunk_pairs ? n : c->chunk_pairs;
-    const int n_xf = op == OP_TOI ? 4 : 2;
+    const int n_xf = bodies ? 0 : (op == OP_TOI ? 4 : 2);
     const size_t out_rec = op == OP_DISTANCE ? sizeof(float) : sizeof(cb2_contact);
     // staging layout per buffer: xforms | l_shape | r_shape | out | status   (256-byte aligned)
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t xf_bytes = al(chunk * sizeof(cb2_xform));
     const size_t o_ls = n_xf * xf_bytes;
-    const size_t o_rs = o_ls + al(chunk * 4);
-    const size_t o_out = o_rs + al(chunk * 4);
+    const size_t o_rs = o_ls + al(chunk * 4);  // (bodies: the 8-byte index pairs start at o_ls and run over o_rs)
+    const size_t o_out = o_rs + al(chunk * 4) + (bodies ? 256 : 0);
     const size_t o_st = o_out + al(chunk * out_rec);
     rc = pipeline_prepare(c, o_st + al(chunk));
     if (rc) return rc;
@@ -1104,6 +1114,21 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
                 if (rc) return rc;
             }
         }
+    if (bodies) {
+        if (c->body_cap < n_bodies) {
+            if (c->d_body_shape) cudaFree(c->d_body_shape);
+            if (c->d_body_t) cudaFree(c->d_body_t);
+            c->d_body_shape = nullptr;
+            c->d_body_t = nullptr;
+            c->body_cap = 0;
+            CK(c, cudaMalloc(&c->d_body_shape, n_bodies * sizeof(uint32_t)));
+            CK(c, cudaMalloc(&c->d_body_t, n_bodies * sizeof(cb2_xform)));
+            c->body_cap = n_bodies;
+        }
+        // on the copy-in stream: the first chunk's `inputs landed` event is recorded behind them
+        CK(c, cudaMemcpyAsync(c->d_body_shape, l_shape, n_bodies * sizeof(uint32_t), cudaMemcpyHostToDevice, c->s_in));
+        CK(c, cudaMemcpyAsync(c->d_body_t, l_t0, n_bodies * sizeof(cb2_xform), cudaMemcpyHostToDevice, c->s_in));
+    }
     const cb2_xform* xf_src[4] = {l_t0, r_t0, l_t1, r_t1};
     // a Rust slice index would panic on an out-of-range shape index: the kernels check every index
     // they load (status CB2_BAD_INDEX, nothing is read through it) and raise a device flag; the call
@@ -1113,6 +1138,10 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
             for (int x = 0; x < n_xf; ++x)
                 CK(c, cudaMemcpyAsync(base + x * xf_bytes, xf_src[x] + b, m * sizeof(cb2_xform),
                                       cudaMemcpyHostToDevice, st));
+            if (bodies) {
+                CK(c, cudaMemcpyAsync(base + o_ls, pair_body + 2 * b, m * 8, cudaMemcpyHostToDevice, st));
+                return CB2_OK;
+            }
             CK(c, cudaMemcpyAsync(base + o_ls, l_shape + b, m * 4, cudaMemcpyHostToDevice, st));
             CK(c, cudaMemcpyAsync(base + o_rs, r_shape + b, m * 4, cudaMemcpyHostToDevice, st));
             return CB2_OK;
@@ -1125,6 +1154,13 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
             A.r_shape = reinterpret_cast<const uint32_t*>(base + o_rs);
             A.l_t = reinterpret_cast<const float4*>(base);
             A.r_t = reinterpret_cast<const float4*>(base + xf_bytes);
+            if (bodies) {
+                A.pair_body = reinterpret_cast<const uint32_t*>(base + o_ls);
+                A.l_shape = c->d_body_shape;
+                A.r_shape = nullptr;
+                A.l_t = A.r_t = c->d_body_t;
+                A.n_bodies = n_bodies;
+            }
             if (op == OP_TOI) {
                 A.l_t1 = reinterpret_cast<const float4*>(base + 2 * xf_bytes);
                 A.r_t1 = reinterpret_cast<const float4*>(base + 3 * xf_bytes);
@@ -1162,7 +1198,7 @@ static int narrow_host(cb2_ctx* c, op_kind op, uint32_t strategy, const cb2_sett
             copy_out, split);
     if (rc == CB2_OK && c->d_bad_index) {
         CK(c, cudaMemcpy(c->h_bad_index, c->d_bad_index, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        if (*c->h_bad_index) return fail(c, CB2_ERR_ARG, "shape index out of range");
+        if (*c->h_bad_index) return fail(c, CB2_ERR_ARG, bodies ? "shape or body index out of range" : "shape index out of range");
     }
     return rc;
 }
@@ -1310,6 +1346,14 @@ int cb2_gjk3_intersection_bodies_dev(cb2_ctx* c, uint32_t strategy, const cb2_se
     if (!pair_body && n) return fail(c, CB2_ERR_ARG, "pair_body is null");
     return narrow_dev(c, OP_INTERSECTION, strategy, settings, body_shape, nullptr, body_t, nullptr,
                       nullptr, nullptr, pair_body, n, 0, out, nullptr, status, stream);
+}
+
+int cb2_gjk3_intersection_bodies(cb2_ctx* c, uint32_t strategy, const cb2_settings* settings,
+                                 const uint32_t* body_shape, const cb2_xform* body_t, uint64_t n_bodies,
+                                 const uint32_t* pair_body, uint64_t n, cb2_contact* out, uint8_t* status) {
+    if (!pair_body && n) return fail(c, CB2_ERR_ARG, "pair_body is null");
+    return narrow_host(c, OP_INTERSECTION, strategy, settings, body_shape, nullptr, body_t, nullptr, nullptr,
+                       nullptr, n, 0, out, nullptr, status, pair_body, n_bodies);
 }
 
 // ---- broad phase -------------------------------------------------------------------------------------

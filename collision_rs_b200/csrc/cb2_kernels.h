@@ -31,6 +31,8 @@ struct narrow_args {
     const uint32_t* dev_count;
     uint64_t n;
     uint32_t n_shapes;          // entries of the shape table: every shape index is checked against it
+    uint64_t n_bodies;          // entries of the body table when pair_body is set and the caller wants the
+                                // body indices checked as well (0: trusted, the device-buffer contract)
     uint32_t* bad_index;        // optional device flag, set when a pair's shape index is out of range
     uint32_t* queue;            // device work-queue cursor of the persistent (lane-refill) kernels
     cb2_settings settings;

@@ -80,6 +80,10 @@ CB2_DI uint8_t load_pair(const narrow_args& A, uint64_t i, const float4* lt, con
         const uint2 b = __ldg(reinterpret_cast<const uint2*>(A.pair_body) + i);
         lx = b.x;
         rx = b.y;
+        if (A.n_bodies && (lx >= A.n_bodies || rx >= A.n_bodies)) {
+            if (A.bad_index) *A.bad_index = 1u;
+            return ST_BAD_INDEX;
+        }
         li = __ldg(A.l_shape + lx);
         ri = __ldg(A.l_shape + rx);
     } else {

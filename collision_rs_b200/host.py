@@ -239,6 +239,21 @@ class Context:
             ptr(r_t), n, ptr(out), ptr(status)))
         return out, status
 
+    def intersection_bodies(self, strategy, body_shape, body_t, pair_body, settings=None, out=None,
+                            status=None):
+        """GJK3::intersection over a pair list that indexes one body table (gjk/mod.rs:362-391 called
+        as `intersection(&shape[a], &pose[a], &shape[b], &pose[b])` for the (a, b) of a broad phase):
+        pair_body is an (n, 2) uint32 array."""
+        settings = settings or Settings.default()
+        pair_body = np.ascontiguousarray(pair_body, np.uint32).reshape(-1, 2)
+        n = len(pair_body)
+        out = np.zeros(n, CONTACT_DT) if out is None else out
+        status = np.zeros(n, np.uint8) if status is None else status
+        self._ck(self.lib.cb2_gjk3_intersection_bodies(
+            self.h, int(strategy), C.byref(settings), ptr(body_shape), ptr(body_t), len(body_shape),
+            ptr(pair_body), n, ptr(out), ptr(status)))
+        return out, status
+
     def distance(self, l_shape, r_shape, l_t, r_t, settings=None):
         settings = settings or Settings.default()
         n = len(l_shape)

@@ -274,6 +274,15 @@ int cb2_gjk3_time_of_impact_dev(cb2_ctx* ctx, const cb2_settings* settings,
                                 const cb2_xform* r_t0, const cb2_xform* r_t1, uint64_t n,
                                 uint32_t iter_cap, cb2_contact* out, uint8_t* status,
                                 void* stream);
+/* The same with HOST buffers: the body table (n_bodies shape indices and transforms) is uploaded
+ * once per call and only the pairs' body indices are streamed (8 bytes per pair instead of the 72
+ * of cb2_gjk3_intersection) — how a caller that iterates a broad phase's pair list over its bodies
+ * holds the data (`intersection(&shape[a], &pose[a], &shape[b], &pose[b])`, gjk/mod.rs:362-391).
+ * Body and shape indices are checked (CB2_ERR_ARG for the call).                               */
+int cb2_gjk3_intersection_bodies(cb2_ctx* ctx, uint32_t strategy, const cb2_settings* settings,
+                                 const uint32_t* body_shape, const cb2_xform* body_t,
+                                 uint64_t n_bodies, const uint32_t* pair_body /* 2 x n, interleaved */,
+                                 uint64_t n, cb2_contact* out, uint8_t* status);
 int cb2_gjk3_intersection_bodies_dev(cb2_ctx* ctx, uint32_t strategy,
                                      const cb2_settings* settings,
                                      const uint32_t* body_shape, const cb2_xform* body_t,

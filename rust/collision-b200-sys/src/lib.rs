@@ -230,6 +230,10 @@ extern "C" {
                                        r_t0: *const cb2_xform, r_t1: *const cb2_xform, n: u64,
                                        iter_cap: u32, out: *mut cb2_contact, status: *mut u8,
                                        stream: *mut c_void) -> c_int;
+    pub fn cb2_gjk3_intersection_bodies(ctx: *mut cb2_ctx, strategy: u32, settings: *const cb2_settings,
+                                        body_shape: *const u32, body_t: *const cb2_xform, n_bodies: u64,
+                                        pair_body: *const u32, n: u64, out: *mut cb2_contact,
+                                        status: *mut u8) -> c_int;
     pub fn cb2_gjk3_intersection_bodies_dev(ctx: *mut cb2_ctx, strategy: u32,
                                             settings: *const cb2_settings,
                                             body_shape: *const u32, body_t: *const cb2_xform,

@@ -227,6 +227,29 @@ impl<'c> GJK3<'c> {
         }).collect())
     }
 
+    /// `GJK3::intersection` for every `(a, b)` of a broad phase's pair list over one body table:
+    /// element i is the reference's `intersection(strategy, &shape[a], &pose[a], &shape[b], &pose[b])`.
+    /// Only the index pairs are streamed to the device per call (8 bytes per pair).
+    pub fn intersection_bodies(&mut self, strategy: &CollisionStrategy, body_shape: &[ShapeId], body_pose: &[Transform3],
+                               pairs: &[(usize, usize)]) -> Result<Vec<Option<Contact<Point3<f32>>>>, Error> {
+        assert!(body_shape.len() == body_pose.len());
+        let sh: Vec<u32> = body_shape.iter().map(|s| s.0).collect();
+        let t: Vec<sys::cb2_xform> = body_pose.iter().map(xf).collect();
+        let pb: Vec<u32> = pairs.iter().flat_map(|&(a, b)| [a as u32, b as u32]).collect();
+        let n = pairs.len();
+        let mut out = vec![sys::cb2_contact::default(); n];
+        let mut status = vec![0u8; n];
+        let strat = match strategy { CollisionStrategy::FullResolution => sys::CB2_FULL_RESOLUTION, CollisionStrategy::CollisionOnly => sys::CB2_COLLISION_ONLY };
+        let rc = unsafe { sys::cb2_gjk3_intersection_bodies(self.ctx.raw, strat, &self.settings, sh.as_ptr(), t.as_ptr(),
+                                                            sh.len() as u64, pb.as_ptr(), n as u64, out.as_mut_ptr(), status.as_mut_ptr()) };
+        self.ctx.check(rc)?;
+        Ok(out.iter().zip(status.iter()).map(|(c, s)| match *s {
+            sys::CB2_NONE => None,
+            sys::CB2_SOME => Some(contact(c)),
+            other => reraise(other),
+        }).collect())
+    }
+
     /// The original single-pair signature, as a batch of one (no CPU fallback).
     pub fn intersection(&mut self, strategy: &CollisionStrategy, left: ShapeId, left_transform: &Transform3,
                         right: ShapeId, right_transform: &Transform3) -> Option<Contact<Point3<f32>>> {

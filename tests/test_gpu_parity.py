@@ -497,6 +497,38 @@ def test_support_cells_match_full_scan_on_a_million_pairs(ctx):
     assert bits_equal(gd[edst == 1], ed[edst == 1]).all()
 
 
+def test_intersection_bodies_matches_the_per_pair_call(ctx):
+    """cb2_gjk3_intersection_bodies (host buffers, one body table, 8 bytes per pair streamed) must give
+    what cb2_gjk3_intersection gives on the expanded per-pair arrays, for both strategies and across
+    several pipeline chunks; a body index outside the table fails the call."""
+    w = W.cfg3_polyhedron_pairs(16, n_shapes=256)
+    rng = np.random.default_rng(99)
+    nb, n = 50_000, 300_000
+    body_shape = rng.integers(0, 256, nb).astype(np.uint32)
+    body_t = W.random_xforms(rng, nb, 0.75)
+    pairs = rng.integers(0, nb, (n, 2)).astype(np.uint32)
+    small = _ctx_with_env(CB2_CHUNK_PAIRS=40_000)  # 300 k pairs = many chunks, ramps included
+    try:
+        small.upload_shapes(w["shapes"], w["verts"])
+        for strategy in (0, 1):
+            got, gst = small.intersection_bodies(strategy, body_shape, body_t, pairs)
+            exp, est = small.intersection(strategy, body_shape[pairs[:, 0]], body_shape[pairs[:, 1]],
+                                          body_t[pairs[:, 0]], body_t[pairs[:, 1]])
+            assert (est == 1).sum() > n // 2
+            assert_contacts_equal(got, gst, exp, est, f"bodies vs per pair, strategy {strategy}")
+        bad = pairs.copy()
+        bad[1234, 1] = nb
+        with pytest.raises(Cb2Error):
+            small.intersection_bodies(0, body_shape, body_t, bad)
+        # and the context is usable afterwards
+        got, gst = small.intersection_bodies(1, body_shape, body_t, pairs[:1000])
+        exp, est = small.intersection(1, body_shape[pairs[:1000, 0]], body_shape[pairs[:1000, 1]],
+                                      body_t[pairs[:1000, 0]], body_t[pairs[:1000, 1]])
+        assert_contacts_equal(got, gst, exp, est, "after a failed call")
+    finally:
+        small.close()
+
+
 def test_split_support_on_tied_candidate_lists(ctx):
     """The EPA groups split a support cell's candidate list over the lanes of a side (chunks of four,
     greater dot wins, equal dots go to the lower part).  Lattice hulls make exact ties and long

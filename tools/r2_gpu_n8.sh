@@ -9,5 +9,5 @@ python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/n8_bench.json').read())
 print('N', d['n_gpus'], 'value', round(d['value']/1e6,1), 'e2e', round(d['e2e']['value']/1e6,1), d['run'])
-print(json.dumps(d['extra'].get('multi'), indent=1))
+print("bodies e2e", d.get("e2e_bodies")); print(json.dumps(d["extra"].get("multi"), indent=1))
 PY
