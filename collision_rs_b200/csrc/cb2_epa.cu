@@ -28,6 +28,11 @@
 //    next tier RESUMES it at the same iteration (nothing is recomputed).  sup_a of each polytope
 //    vertex is only read by the final contact (epa3d.rs:84-114), so it lives in a global
 //    scratch, not shared memory.
+//  * The kernel is issue-bound at 20 warps per SM and its time follows its executed warp
+//    instructions, so the per-round phases are written against their SASS (profiles/README.md,
+//    round 2): running shared-memory addresses and unconditional loads in the per-face loops, a
+//    branch-free walk step, the lanes of a side sharing a polyhedron's candidate list
+//    (support_point_split), rare multi-trip loops kept rolled.
 #include <type_traits>
 
 #include "cb2_epa_team.cuh"
