@@ -306,6 +306,12 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     static_assert(G == 2 || G == 4 || G == 8 || G == 16, "3*G edge-keep bits must fit two words");
     static_assert(RF <= FCAP && RV <= VCAP, "a resumed polytope must fit");
     using PS = poly_smem<FCAP, VCAP, OCAP>;
+    // The per-face loops (closest-face scan, lean visibility pass) take two faces per lane and trip
+    // and load before they predicate: the last trip may read face slots up to FCAP + 2 G - 2.  Those
+    // reads must stay inside the group's own record (their values are never used).
+    static_assert((size_t)(FCAP + 2 * G - 1) * 16 <= sizeof(PS), "face slots read past nf leave the record");
+    static_assert(offsetof(PS, fidx) + (size_t)(FCAP + 2 * G - 1) * sizeof(uint32_t) <= sizeof(PS),
+                  "face index slots read past nf leave the record");
     constexpr int FW = (FCAP + 31) / 32;
     constexpr int AW = PS::AW;
     constexpr int NG = 32 / G;
