@@ -49,6 +49,9 @@
 #ifndef CB2_OPT_FOLD    // closest_face_to_origin folded into the visibility pass and Face::new: bit-identical,
 #define CB2_OPT_FOLD 0  // but no faster (tier 0 14.03 ms with, 13.95 ms without: three more live registers)
 #endif
+#ifndef CB2_OPT_STAGED  // tier 0 adopts hits the warp prepared 32 at a time (staged fetch): bit-identical,
+#define CB2_OPT_STAGED 0  // 10.75 ms against 10.61 ms without — the other warps already hide the fetch chain
+#endif
 #ifndef CB2_VIS2        // visibility pass: two faces per lane and trip
 #define CB2_VIS2 1
 #endif
@@ -298,6 +301,71 @@ CB2_DI void epa_walk(MK& vis, PS& P, bool add, int gl, int& len, int& nvis, int&
     overflow = walking;  // faces left to examine, no room in the lists
 }
 
+// ---- staged fetch (tier 0) ------------------------------------------------------------------------------
+// A group that finished used to fetch its next hit on the spot: work-list entry, shape indices,
+// shape records, transforms and their inverse rotations, the simplex, the four initial faces — ~250
+// instructions and four or five dependent memory round trips, executed by the 1.3 groups that
+// happened to finish in that round while the rest of the warp waited (8 % of tier 0's instructions
+// at 5 of 32 lanes).  Now the WARP prepares 32 hits at once — every lane one hit, full lanes, one
+// chain of round trips per 32 hits — into a per-warp record array in global memory (L2 resident:
+// 12 KB), and a finished group adopts a prepared record with a handful of 128-bit loads.
+constexpr int SUP_HDR = 0, SUP_SHAPE = 1, SUP_XF = 5, SUP_PV = 11, SUP_PA = 15, SUP_FND = 19, SUP_FIDX = 23,
+              SUP_SIZE = 24;  // float4 per record
+CB2_NOINLINE_DEVICE void epa_prepare_hit(const narrow_args& A, const shape_table& T, const float4* simplex,
+                                         uint32_t pair, float4* rec) {
+    f3 pv[4];
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        uint32_t si;
+        uint64_t xi;
+        if (A.pair_body) {
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(A.pair_body) + pair);
+            xi = side ? b.y : b.x;
+            si = __ldg(A.l_shape + xi);
+        } else {
+            xi = pair;
+            si = __ldg((side ? A.r_shape : A.l_shape) + pair);
+        }
+        const float4* sp = reinterpret_cast<const float4*>(T.shapes + si);
+        rec[SUP_SHAPE + 2 * side] = __ldg(sp);
+        rec[SUP_SHAPE + 2 * side + 1] = __ldg(sp + 1);
+        const float4* tp = (side ? A.r_t : A.l_t) + 2 * xi;
+        const xform t = make_xform(__ldg(tp), __ldg(tp + 1));
+        rec[SUP_XF + 3 * side] = make_float4(t.q.s, t.q.x, t.q.y, t.q.z);
+        rec[SUP_XF + 3 * side + 1] = make_float4(t.qi.s, t.qi.x, t.qi.y, t.qi.z);
+        rec[SUP_XF + 3 * side + 2] = make_float4(t.disp.x, t.disp.y, t.disp.z, t.scale);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 v = simplex[(size_t)pair * 8 + j];
+        rec[SUP_PV + j] = v;
+        rec[SUP_PA + j] = simplex[(size_t)pair * 8 + 4 + j];
+        pv[j] = mk3(v.x, v.y, v.z);
+    }
+    // Polytope::new: Face::new (3,2,1) (3,1,0) (3,0,2) (2,0,1), epa3d.rs:201-208, and the closest of
+    // them (first strictly smallest distance; a NaN at index 0 sticks)
+    uint32_t idx[4];
+    float bd = INFINITY;
+    uint32_t bi = 0xFFFFFFFFu;
+    float d0 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t tri = j == 0 ? 0x010203u : (j == 1 ? 0x000103u : (j == 2 ? 0x020003u : 0x010002u));
+        const uint32_t a = tri & 255u, b = (tri >> 8) & 255u, c = tri >> 16;
+        const f3 va = pv[a];
+        const f3 n = normalize(cross(pv[b] - va, pv[c] - va));
+        const float dist = dot(n, va);
+        rec[SUP_FND + j] = make_float4(n.x, n.y, n.z, dist);
+        idx[j] = a | (b << 8) | (c << 16);
+        if (j == 0) d0 = dist;
+        if (dist < bd) { bd = dist; bi = (uint32_t)j; }
+    }
+    rec[SUP_FIDX] = make_float4(__uint_as_float(idx[0]), __uint_as_float(idx[1]), __uint_as_float(idx[2]),
+                                __uint_as_float(idx[3]));
+    const uint32_t best = (d0 != d0 || bi == 0xFFFFFFFFu) ? 0u : bi;
+    rec[SUP_HDR] = make_float4(__uint_as_float(pair), __uint_as_float(best), 0.f, 0.f);
+}
+
 enum : int { S_FETCH = 0, S_RUN = 1, S_EXIT = 2 };
 
 // RF/RV: caps of the tier whose dumps this instantiation resumes (0 = none)
@@ -367,7 +435,72 @@ __global__ void __launch_bounds__(32, (RF == 0 ? CB2_EPA_MIN_BLOCKS : 20)) k_epa
     int nf = 0, nv = 0;
     int best_face = -1;  // < 0: closest_face_to_origin has to scan (after a fetch, a resume, or a tie)
 
+    // tier 0: the warp's supply of prepared hits (staged fetch above)
+    constexpr bool STAGED = CB2_OPT_STAGED && RF == 0 && G == 4;
+    float4* const sup = STAGED ? C.supply + (size_t)blockIdx.x * 32 * SUP_SIZE : nullptr;
+    uint32_t sup_head = 0, sup_count = 0;  // warp-uniform: records [head, count) are ready
+    bool sup_dry = false;                  // the work list is exhausted
+
     for (;;) {
+        if constexpr (STAGED) {
+            // ================= ADOPT a prepared hit (groups that finished) ==============================
+            const bool want = state == S_FETCH;
+            const unsigned need = __ballot_sync(0xffffffffu, want && gl == 0);  // one bit per wanting group
+            if (need) {
+                if (sup_head == sup_count && !sup_dry) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(cursor, 32u);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    sup_count = base < count ? (count - base < 32u ? count - base : 32u) : 0u;
+                    sup_head = 0u;
+                    sup_dry = sup_count == 0u;
+                    if ((uint32_t)lane < sup_count)
+                        epa_prepare_hit(A, T, C.W.simplex, list[base + lane] & ~OVER_RESUME, sup + (size_t)lane * SUP_SIZE);
+                    __syncwarp();
+                }
+                if (want) {
+                    const uint32_t e = sup_head + (uint32_t)__popc(need & ((1u << (gw * G)) - 1u));
+                    if (sup_dry && sup_head == sup_count) {
+                        state = S_EXIT;
+                        nf = 0;
+                        best_face = -1;
+                        sh.kind = K_CUBOID;
+                        sh.h = zero3();
+                    } else if (e < sup_count) {
+                        // (L2 loads: the records were written by other lanes of this warp a moment ago)
+                        const float4* rec = sup + (size_t)e * SUP_SIZE;
+                        const float4 hdr = __ldcg(rec + SUP_HDR);
+                        pair = __float_as_uint(hdr.x);
+                        best_face = (int)__float_as_uint(hdr.y);
+                        const int side = right ? 1 : 0;
+                        const float4 s0 = __ldcg(rec + SUP_SHAPE + 2 * side), s1 = __ldcg(rec + SUP_SHAPE + 2 * side + 1);
+                        sh.kind = __float_as_uint(s0.x);
+                        sh.h = mk3(s0.y, s0.z, s0.w);
+                        sh.poly.voff = __float_as_uint(s1.x);
+                        sh.poly.vcnt = __float_as_uint(s1.y);
+                        sh.poly.cell_off = __float_as_uint(s1.z);
+                        sh.poly.cfg = __float_as_uint(s1.w);
+                        sh.hang = 0u;
+                        const float4 x0 = __ldcg(rec + SUP_XF + 3 * side), x1 = __ldcg(rec + SUP_XF + 3 * side + 1),
+                                     x2 = __ldcg(rec + SUP_XF + 3 * side + 2);
+                        xf.q.s = x0.x; xf.q.x = x0.y; xf.q.y = x0.z; xf.q.z = x0.w;
+                        xf.qi.s = x1.x; xf.qi.x = x1.y; xf.qi.y = x1.z; xf.qi.z = x1.w;
+                        xf.disp = mk3(x2.x, x2.y, x2.z);
+                        xf.scale = x2.w;
+                        xf.unit = (x2.w == 1.0f);
+                        P.pv[gl] = __ldcg(rec + SUP_PV + gl);
+                        pa[gl] = __ldcg(rec + SUP_PA + gl);
+                        P.fnd[gl] = __ldcg(rec + SUP_FND + gl);
+                        P.fidx[gl] = __ldcg(reinterpret_cast<const uint32_t*>(rec + SUP_FIDX) + gl);
+                        nv = 4;
+                        nf = 4;
+                        it = 1;
+                        state = S_RUN;
+                    }  // else: the supply ran short this round; the group asks again in the next one
+                }
+                sup_head = sup_head + (uint32_t)__popc(need) < sup_count ? sup_head + (uint32_t)__popc(need) : sup_count;
+            }
+        } else
         // ================= FETCH (divergent: only groups that finished) ================================
         if (state == S_FETCH) {
             uint32_t k = 0;
@@ -996,7 +1129,7 @@ static cudaError_t launch_lane_tier(const epa_args& C, int sm_count, cudaStream_
     return cudaGetLastError();
 }
 
-size_t epa_pa_scratch_bytes(int sm_count) {
+static size_t epa_pa_region_bytes(int sm_count) {
     size_t m, b;
 #if CB2_TIER0_KIND == 0
     m = (size_t)epa_blocks<T0_G, T0_F, T0_V, T0_O, 0, 0>(sm_count) * (32 / T0_G) * T0_V * sizeof(float4);
@@ -1018,6 +1151,15 @@ size_t epa_pa_scratch_bytes(int sm_count) {
     m = m > c ? m : c;
     return m;
 }
+// tier 0's supply of prepared hits sits behind the sup_a scratch: 32 records per warp
+static size_t epa_supply_bytes(int sm_count) {
+#if CB2_TIER0_KIND == 0
+    return (size_t)epa_blocks<T0_G, T0_F, T0_V, T0_O, 0, 0>(sm_count) * 32 * SUP_SIZE * sizeof(float4);
+#else
+    return 0;
+#endif
+}
+size_t epa_pa_scratch_bytes(int sm_count) { return epa_pa_region_bytes(sm_count) + epa_supply_bytes(sm_count); }
 size_t epa_dump_record_bytes(int tier) {
     return (tier == 0 ? dump_layout<L0_F, L0_V>::SIZE : dump_layout<T1_F, T1_V>::SIZE) * sizeof(float4);
 }
@@ -1029,6 +1171,7 @@ cudaError_t launch_epa_tier(int tier, const narrow_args& A, const narrow_ws& W, 
     C.W = W;
     C.tier = (uint32_t)tier;
     C.sm_count = (uint32_t)sm_count;
+    C.supply = reinterpret_cast<float4*>(reinterpret_cast<char*>(W.pa) + epa_pa_region_bytes(sm_count));
     if (tier == 0) {
 #if CB2_TIER0_KIND == 0
         return launch_tier<T0_G, T0_F, T0_V, T0_O, 0, 0>(C, sm_count, st);

@@ -35,6 +35,7 @@ struct epa_args {
     narrow_ws W;
     uint32_t tier;      // 0 .. EPA_TIERS-1
     uint32_t sm_count;  // SMs of the device (the later tiers size their active grid by it)
+    float4* supply;     // tier 0 of the group kernel: 32 prepared hits per warp (behind the sup_a scratch)
 };
 
 // polytope dump record, in float4 units: header (nf, nv, it) | fnd | pv | pa | fidx
